@@ -1,0 +1,152 @@
+/* rgbd_recon_b200.h — C ABI of the B200-native volumetric-fusion path (librr_b200.so).
+ *
+ * The reference (steppobeck/rgbd-recon) has no plugin/FFI interface: its boundary is the public C++ surface that
+ * source/kinect_client.cpp calls plus implicit OpenGL state. Each entry point below names the
+ * reference interface it stands in for (paths relative to the reference root). The kept C++ classes
+ * (rgbd-recon_b200/host/: kinect::CalibVolumes, NetKinectArray, ReconIntegration, CalibrationInverter) are thin
+ * shims over these calls. No OpenGL context, no torch types; plain pointers and sizes only.
+ *
+ * Conventions: every call returns 0 on success or a negative rr_status; rr_last_error(ctx) gives the text.
+ * A context is single-caller (the reference issues everything from its one GL thread) and owns one CUDA stream
+ * on one device. Host pointers passed in stay owned by the caller. Arrays are C-contiguous:
+ *   depth  float32 [N][H][W]        metres, 0 = no return       (NetKinectArray.cpp:135-142)
+ *   colour uint8   [N][CH][CW][3]   RGB8                        (NetKinectArray.cpp:120-131)
+ *   cv_xyz float32 [Z][Y][X][3], cv_uv float32 [Z][Y][X][2], cv_xyz_inv float32 [Z][Y][X][4]
+ *                                   index z*X*Y + y*X + x       (framework/calibration/calibration_volume.hpp:18-27)
+ *   tsdf   float32 [Z][Y][X]        x fastest                   (glsl/tsdf_integration.vs:57-58)
+ */
+#ifndef RGBD_RECON_B200_H
+#define RGBD_RECON_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rr_ctx rr_ctx;
+
+typedef enum rr_status {
+  RR_OK = 0,
+  RR_ERR_INVALID = -1,     /* bad argument / call order */
+  RR_ERR_CUDA = -2,        /* CUDA runtime failure (text in rr_last_error) */
+  RR_ERR_NO_DEVICE = -3,   /* no usable GPU: there is no CPU fallback */
+  RR_ERR_UNSUPPORTED = -4
+} rr_status;
+
+/* Runtime knobs of ReconIntegration (framework/reconstruction/recon_integration.cpp:30-60, kinect_client.cpp:87-93). */
+typedef struct rr_config {
+  float limit;                    /* TSDF truncation in normalised sensor-depth units (setTsdfLimit)            */
+  float voxel_size;               /* metres (setVoxelSize, :341-354)                                            */
+  float brick_size;               /* metres, rounded to a voxel multiple (setBrickSize, :474-484)               */
+  uint32_t min_voxels_per_brick;  /* setMinVoxelsPerBrick, default 10                                           */
+  int32_t use_bricks;             /* setUseBricks: integrate occupied bricks only                               */
+  int32_t skip_space;             /* setSpaceSkip: raymarch starts/ends at the occupied-brick hull              */
+  int32_t store_weight;           /* extension: also keep the shader-local total_weight per voxel (float32)     */
+} rr_config;
+
+/* Inputs of ReconIntegration::draw (recon_integration.cpp:177-241): the fixed-function matrices it reads back,
+ * column-major float[16] like gloost::Matrix / glGetFloatv. */
+typedef struct rr_view {
+  float modelview[16];
+  float projection[16];
+  int32_t viewport[4];            /* x, y, width, height (glGetIntegerv(GL_VIEWPORT))                           */
+  int32_t shade_mode;             /* Settings.g_shade_mode, glsl/shading.glsl:14-21: 0 colour 1 shaded 2 normal 3 camera */
+} rr_view;
+
+/* Intermediate images a test or GUI texture viewer can read back (kinect_client.cpp:486-518). */
+typedef enum rr_stage {
+  RR_STAGE_MORPH = 0,       /* float32 [N][H][W]     m_textures_depth2.front  */
+  RR_STAGE_DEPTH = 1,       /* float32 [N][H][W][2]  m_textures_depth         */
+  RR_STAGE_LAB = 2,         /* float32 [N][H][W][3]  m_textures_color         */
+  RR_STAGE_DEPTH_B = 3,     /* float32 [N][H][W][2]  m_textures_depth_b       */
+  RR_STAGE_SILHOUETTE = 4,  /* float32 [N][H][W]     m_textures_silhouette    */
+  RR_STAGE_NORMAL = 5,      /* float32 [N][H][W][3]  m_textures_normal        */
+  RR_STAGE_QUALITY = 6      /* float32 [N][H][W]     m_textures_quality       */
+} rr_stage;
+
+/* ---- lifetime ------------------------------------------------------------------------------------------- */
+/* Replaces the GL object ownership spread over NetKinectArray::init (NetKinectArray.cpp:114-219),
+ * CalibVolumes::createVolumeTextures (CalibVolumes.cpp:132-144) and the ReconIntegration ctor. */
+int rr_create(rr_ctx** out, int device, int num_sensors, int depth_w, int depth_h, int color_w, int color_h);
+void rr_destroy(rr_ctx* ctx);
+const char* rr_last_error(const rr_ctx* ctx);
+int rr_synchronize(rr_ctx* ctx);
+/* The CUDA stream (cudaStream_t) all work of this context is enqueued on; for event timing by the caller. */
+void* rr_stream(rr_ctx* ctx);
+
+/* ---- calibration (CalibVolumes) -------------------------------------------------------------------------- */
+/* CalibVolumes ctor: bbox UBO binding 2 (CalibVolumes.cpp:45-49). */
+int rr_set_bbox(rr_ctx* ctx, const float bbox_min[3], const float bbox_max[3]);
+/* CalibVolumes::addVolume + createVolumeTextures (CalibVolumes.cpp:115-144). Also derives the sensor frustum and
+ * camera position (Frustum::getCameraPos, frustum.cpp:21-33) used by the quality pass. */
+int rr_calib_upload(rr_ctx* ctx, int sensor, const float* cv_xyz, const float* cv_uv, const uint32_t res[3],
+                    const float depth_limits[2]);
+/* CalibVolumes::loadInverseCalibs (CalibVolumes.cpp:64-80). All sensors must share one resolution (getVolumeRes). */
+int rr_calib_upload_inv(rr_ctx* ctx, int sensor, const float* cv_xyz_inv, const uint32_t res[3]);
+/* CalibVolumes::getCameraPositions (CalibVolumes.cpp:224-230): out float[N][3]. */
+int rr_get_camera_positions(const rr_ctx* ctx, float* out);
+/* CalibVolumes::getFrustum(i): the six planes (float[6][4]) of frustum.cpp:166-176. */
+int rr_get_frustum_planes(const rr_ctx* ctx, int sensor, float* out);
+/* CalibrationInverter::calculateInverseVolumes for one sensor (calibration_inverter.cpp:99-155): exact 8-NN +
+ * inverse-distance weighting + frustum cull on the GPU. host_out: float32 [res.z][res.y][res.x][4]. Synchronous.
+ * If keep_on_device != 0 the result also becomes the sensor's inverse volume (as rr_calib_upload_inv would). */
+int rr_calib_invert(rr_ctx* ctx, int sensor, const uint32_t out_res[3], float* host_out, int keep_on_device);
+
+/* ---- settings (ReconIntegration setters) ------------------------------------------------------------------ */
+/* setVoxelSize / setBrickSize / setTsdfLimit / setMinVoxelsPerBrick / setUseBricks / setSpaceSkip in one call;
+ * (re)allocates the volume and rebuilds the brick table (divideBox, recon_integration.cpp:361-407). */
+int rr_configure(rr_ctx* ctx, const rr_config* cfg);
+int rr_get_volume_res(const rr_ctx* ctx, uint32_t res[3]);
+/* numBricks / getBrickSize / m_res_bricks. Any out pointer may be NULL. */
+int rr_get_brick_info(const rr_ctx* ctx, uint32_t res_bricks[3], float* brick_size, uint32_t* num_bricks);
+/* Per-brick voxel ranges int32 [num_bricks][6] = x0,x1,y0,y1,z0,z1 (VolumeSampler::containedVoxels). */
+int rr_get_brick_ranges(const rr_ctx* ctx, int32_t* out);
+/* Multi-GPU: this context integrates/raymarches only voxel slices z in [z0, z1). Default: all. */
+int rr_set_slab(rr_ctx* ctx, uint32_t z0, uint32_t z1);
+
+/* ---- per frame (NetKinectArray + ReconIntegration) -------------------------------------------------------- */
+/* NetKinectArray::update (NetKinectArray.cpp:226-238): one frame set, host buffers -> device, async on the stream.
+ * For full overlap pass pinned memory. color may be NULL if no colour is needed. */
+int rr_upload_frames(rr_ctx* ctx, const void* color, size_t color_bytes, const void* depth, size_t depth_bytes);
+/* Same, but the frame set is already in device memory of this context's GPU (e.g. after an NCCL broadcast). */
+int rr_upload_frames_device(rr_ctx* ctx, const void* d_color, size_t color_bytes, const void* d_depth, size_t depth_bytes);
+/* ReconIntegration::clearOccupiedBricks (recon_integration.cpp:272-278). */
+int rr_bricks_clear(rr_ctx* ctx);
+/* NetKinectArray::processTextures (NetKinectArray.cpp:311-428): morph -> bilateral -> boundary -> normal(+bricks)
+ * -> quality, with the flags of filterTextures / useProcessedDepths / refineBoundary. */
+int rr_preprocess(rr_ctx* ctx, int filter_textures, int use_processed_depth, int refine_boundary);
+/* ReconIntegration::updateOccupiedBricks (recon_integration.cpp:431-446), on the device (ordered compaction).
+ * If either out pointer is non-NULL the call synchronises to return the count / occupied ratio. */
+int rr_bricks_update(rr_ctx* ctx, uint32_t* out_num_occupied, float* out_ratio);
+/* ReconIntegration::integrate (recon_integration.cpp:243-270) + glsl/tsdf_integration.vs. */
+int rr_integrate(rr_ctx* ctx);
+/* ReconIntegration::drawF/draw (recon_integration.cpp:151-241) + glsl/tsdf_raymarch.fs, bricks.{vs,gs,fs}.
+ * out_rgba float32 [h][w][4], out_depth float32 [h][w] (gl_FragDepth, 1.0 where no surface), both host, may be NULL. */
+int rr_raymarch(rr_ctx* ctx, const rr_view* view, float* out_rgba, float* out_depth);
+
+/* ---- read-back (tests, debug views) ------------------------------------------------------------------------ */
+int rr_download_tsdf(rr_ctx* ctx, float* out);
+int rr_download_weight(rr_ctx* ctx, float* out);
+int rr_download_stage(rr_ctx* ctx, int stage, float* out);
+/* Brick counters uint32 [num_bricks] and the ordered occupied list; *num_occupied receives its length. */
+int rr_download_bricks(rr_ctx* ctx, uint32_t* counters, uint32_t* occupied, uint32_t* num_occupied);
+/* Last raymarch: sample-count image float32 [h][w] (tex_num_samples, tsdf_raymarch.fs:403-406). */
+int rr_download_num_samples(rr_ctx* ctx, float* out);
+
+/* ---- instrumentation ---------------------------------------------------------------------------------------- */
+/* TimerDatabase stage names (NetKinectArray.cpp:211-216, recon_integration.cpp:146-148): "morph", "bilateral",
+ * "boundary", "normal", "quality", "1preprocess", "2integrate", "brickdraw", "draw". Enable with rr_set_timing;
+ * rr_get_stage_ms synchronises and returns the last duration. */
+int rr_set_timing(rr_ctx* ctx, int enabled);
+int rr_get_stage_ms(rr_ctx* ctx, const char* name, float* ms);
+/* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
+uint64_t rr_launch_count(const rr_ctx* ctx);
+/* Library/ABI version. */
+int rr_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RGBD_RECON_B200_H */

@@ -1,0 +1,158 @@
+"""ORACLE binding (test infrastructure, NOT product code).
+
+ctypes wrapper over oracle/librr_oracle.so, the scalar CPU restatement of the reference's volumetric-fusion path.
+Import this only from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "librr_oracle.so")
+    if force or not os.path.exists(so):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "librr_oracle.so"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    L = C.CDLL(build())
+    L.ro_set_threads.argtypes = [C.c_int]
+    L.ro_get_max_threads.restype = C.c_int
+    for n in ("ro_kat_log2", "ro_kat_exp2"):
+        getattr(L, n).argtypes = [C.c_float]
+        getattr(L, n).restype = C.c_float
+    L.ro_kat_pow.argtypes = [C.c_float, C.c_float]
+    L.ro_kat_pow.restype = C.c_float
+    L.ro_kat_tex3d.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, f32p]
+    L.ro_kat_tex2d.argtypes = [f32p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int]
+    L.ro_kat_tex2d.restype = C.c_float
+    L.ro_kat_rgb_to_lab.argtypes = [f32p, f32p]
+    L.ro_pre_morph.argtypes = [f32p, C.c_int, C.c_int, f32p]
+    L.ro_pre_depth.argtypes = [f32p, C.c_int, C.c_int, f32p, f32p, C.c_int, C.c_int, C.c_int, u8p, C.c_int, C.c_int,
+                               f32p, f32p, C.c_float, C.c_float, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, f32p, f32p]
+    L.ro_pre_boundary.argtypes = [f32p, f32p, C.c_int, C.c_int, C.c_int, f32p, f32p]
+    L.ro_pre_normal.argtypes = [f32p, C.c_int, C.c_int, f32p, C.c_int, C.c_int, C.c_int, f32p, C.c_float, u32p, C.c_uint32, u32p, f32p]
+    L.ro_pre_quality.argtypes = [f32p, f32p, C.c_int, C.c_int, f32p, C.c_int, C.c_int, C.c_int, f32p, f32p]
+    L.ro_volume_res.argtypes = [f32p, f32p, C.c_float, u32p]
+    L.ro_adjust_brick_size.argtypes = [C.c_float, C.c_float]
+    L.ro_adjust_brick_size.restype = C.c_float
+    L.ro_divide_box.argtypes = [f32p, f32p, C.c_float, u32p, u32p, C.c_void_p]
+    L.ro_divide_box.restype = C.c_uint32
+    L.ro_occupied_bricks.argtypes = [u32p, C.c_uint32, C.c_uint32, u32p]
+    L.ro_occupied_bricks.restype = C.c_uint32
+    L.ro_integrate.argtypes = [C.c_int, f32p, i32p, f32p, f32p, f32p, C.c_int, C.c_int, C.c_float, u32p, C.c_int,
+                               i32p, u32p, C.c_uint32, f32p, C.c_void_p]
+    L.ro_frustum.argtypes = [f32p, C.c_int, C.c_int, C.c_int, f32p, f32p]
+    L.ro_frustum_inside.argtypes = [f32p, f32p]
+    L.ro_frustum_inside.restype = C.c_int
+    L.ro_calib_invert.argtypes = [f32p, C.c_int, C.c_int, C.c_int, f32p, f32p, u32p, f32p, C.c_void_p, C.c_int]
+    _LIB = L
+    return L
+
+
+def set_threads(n):
+    lib().ro_set_threads(int(n))
+
+
+def max_threads():
+    return lib().ro_get_max_threads()
+
+
+# ---------------------------------------------------------------------------------------------- brick grid
+
+def brick_grid(bbox_min, bbox_max, voxel_size, brick_size_req):
+    """setVoxelSize + setBrickSize + divideBox. Returns dict(res, brick_size, res_bricks, ranges[nb,6])."""
+    L = lib()
+    bmin = np.ascontiguousarray(bbox_min, np.float32)
+    bmax = np.ascontiguousarray(bbox_max, np.float32)
+    res = np.zeros(3, np.uint32)
+    L.ro_volume_res(bmin, bmax, np.float32(voxel_size), res)
+    bs = L.ro_adjust_brick_size(np.float32(voxel_size), np.float32(brick_size_req))
+    rb = np.zeros(3, np.uint32)
+    nb = L.ro_divide_box(bmin, bmax, bs, res, rb, None)
+    ranges = np.zeros((nb, 6), np.int32)
+    L.ro_divide_box(bmin, bmax, bs, res, rb, ranges.ctypes.data)
+    return dict(res=res, brick_size=np.float32(bs), res_bricks=rb, ranges=ranges, num_bricks=int(nb))
+
+
+def frustum(cv_xyz_one):
+    Z, Y, X, _ = cv_xyz_one.shape
+    planes = np.zeros((6, 4), np.float32)
+    cam = np.zeros(3, np.float32)
+    lib().ro_frustum(np.ascontiguousarray(cv_xyz_one), X, Y, Z, planes, cam)
+    return planes, cam
+
+
+def calib_invert(cv_xyz_one, bbox_min, bbox_max, out_res, want_neighbours=False, brute=False):
+    Z, Y, X, _ = cv_xyz_one.shape
+    ox, oy, oz = [int(v) for v in out_res]
+    out = np.zeros((oz, oy, ox, 4), np.float32)
+    neigh = np.zeros((oz, oy, ox, 8), np.uint32) if want_neighbours else None
+    lib().ro_calib_invert(np.ascontiguousarray(cv_xyz_one), X, Y, Z, np.ascontiguousarray(bbox_min, np.float32),
+                          np.ascontiguousarray(bbox_max, np.float32), np.array([ox, oy, oz], np.uint32), out,
+                          neigh.ctypes.data if neigh is not None else None, int(brute))
+    return (out, neigh) if want_neighbours else out
+
+
+# ---------------------------------------------------------------------------------------------- frame
+
+def preprocess(scene, grid, camera_positions, filter_textures=True, use_processed_depth=True, refine=True):
+    """NetKinectArray::processTextures for all layers (+ ReconIntegration::clearOccupiedBricks before it)."""
+    L = lib()
+    N, H, W = scene.depth.shape
+    X, Y, Z = scene.cv_res
+    out = dict(
+        morph=np.zeros((N, H, W), np.float32), depth=np.zeros((N, H, W, 2), np.float32),
+        lab=np.zeros((N, H, W, 3), np.float32), depth_b=np.zeros((N, H, W, 2), np.float32),
+        sil=np.zeros((N, H, W), np.float32), normal=np.zeros((N, H, W, 3), np.float32),
+        quality=np.zeros((N, H, W), np.float32), bricks=np.zeros(grid["num_bricks"], np.uint32))
+    bmin = np.ascontiguousarray(scene.bbox_min, np.float32)
+    bmax = np.ascontiguousarray(scene.bbox_max, np.float32)
+    for i in range(N):
+        raw = np.ascontiguousarray(scene.depth[i])
+        L.ro_pre_morph(raw, W, H, out["morph"][i])
+        src = out["morph"][i] if use_processed_depth else raw
+        L.ro_pre_depth(src, W, H, scene.cv_xyz[i], scene.cv_uv[i], X, Y, Z, scene.color[i], scene.CW, scene.CH, bmin, bmax,
+                       0.5, 4.5, int(filter_textures), 0, 0.0, 0.0, 0.0, out["depth"][i], out["lab"][i])
+        L.ro_pre_boundary(out["depth"][i], out["lab"][i], W, H, int(refine), out["depth_b"][i], out["sil"][i])
+        L.ro_pre_normal(out["depth_b"][i], W, H, scene.cv_xyz[i], X, Y, Z, bmin, grid["brick_size"], grid["res_bricks"],
+                        grid["num_bricks"], out["bricks"], out["normal"][i])
+        L.ro_pre_quality(out["depth_b"][i], out["normal"][i], W, H, scene.cv_xyz[i], X, Y, Z,
+                         np.ascontiguousarray(camera_positions[i], np.float32), out["quality"][i])
+    return out
+
+
+def occupied_bricks(counters, min_voxels=10):
+    occ = np.zeros(len(counters), np.uint32)
+    n = lib().ro_occupied_bricks(np.ascontiguousarray(counters, np.uint32), len(counters), int(min_voxels), occ)
+    return occ[:n].copy()
+
+
+def integrate(inv, pre, grid, limit, use_bricks, occupied, want_weight=False):
+    """ReconIntegration::integrate. inv: [N][IZ][IY][IX][4]."""
+    N, IZ, IY, IX, _ = inv.shape
+    _, H, W = pre["sil"].shape
+    res = grid["res"]
+    tsdf = np.zeros((int(res[2]), int(res[1]), int(res[0])), np.float32)
+    weight = np.zeros_like(tsdf) if want_weight else None
+    occ = np.ascontiguousarray(occupied, np.uint32) if len(occupied) else np.zeros(1, np.uint32)
+    lib().ro_integrate(N, np.ascontiguousarray(inv), np.array([IX, IY, IZ], np.int32), pre["sil"], pre["depth_b"], pre["quality"],
+                       W, H, np.float32(limit), res, int(use_bricks), grid["ranges"], occ, len(occupied), tsdf,
+                       weight.ctypes.data if weight is not None else None)
+    return (tsdf, weight) if want_weight else tsdf

@@ -1,0 +1,53 @@
+/* ORACLE (test infrastructure, NOT product code): C entry points of the scalar CPU restatement of
+ * steppobeck/rgbd-recon's volumetric-fusion path. Loaded with ctypes by tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs ONLY. Parity is unpinned by the reference's own tests (it has
+ * none); see ro_math.h for what is pinned against reference code compiled into oracle/_ref. */
+#ifndef RR_ORACLE_H
+#define RR_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+void ro_set_threads(int n);
+int ro_get_max_threads(void);
+
+/* scalar known-answer hooks for the math pins */
+float ro_kat_log2(float x);
+float ro_kat_exp2(float x);
+float ro_kat_pow(float x, float y);
+void ro_kat_tex3d(const float* vol, int C, int X, int Y, int Z, float s, float t, float r, float* out);
+float ro_kat_tex2d(const float* img, int W, int H, float s, float t, int nearest);
+void ro_kat_rgb_to_lab(const float* rgb, float* lab);
+
+void ro_pre_morph(const float* depth_in, int W, int H, float* depth_out);
+void ro_pre_depth(const float* depth_in, int W, int H, const float* cv_xyz, const float* cv_uv, int CX, int CY, int CZ,
+                  const uint8_t* color, int CW, int CH, const float* bbox_min, const float* bbox_max,
+                  float cv_min_ds, float cv_max_ds, int filter_textures, int compress, float scale, float near_,
+                  float scaled_near, float* out_depth, float* out_lab);
+void ro_pre_boundary(const float* depth_rg, const float* lab, int W, int H, int refine, float* out_depth_b, float* out_sil);
+void ro_pre_normal(const float* depth_b, int W, int H, const float* cv_xyz, int CX, int CY, int CZ,
+                   const float* bbox_min, float brick_size, const uint32_t* brick_res, uint32_t num_bricks,
+                   uint32_t* bricks, float* out_normal);
+void ro_pre_quality(const float* depth_b, const float* normals, int W, int H, const float* cv_xyz, int CX, int CY, int CZ,
+                    const float* camera_pos, float* out_quality);
+
+void ro_volume_res(const float* bbox_min, const float* bbox_max, float voxel_size, uint32_t* res_out);
+float ro_adjust_brick_size(float voxel_size, float size);
+uint32_t ro_divide_box(const float* bbox_min, const float* bbox_max, float brick_size, const uint32_t* res_volume,
+                       uint32_t* res_bricks_out, int32_t* ranges);
+uint32_t ro_occupied_bricks(const uint32_t* counters, uint32_t num_bricks, uint32_t min_voxels, uint32_t* occupied_out);
+void ro_integrate(int N, const float* inv, const int32_t* inv_res, const float* sil, const float* depth_b,
+                  const float* quality, int W, int H, float limit, const uint32_t* res, int use_bricks,
+                  const int32_t* brick_ranges, const uint32_t* occupied, uint32_t num_occupied, float* tsdf, float* weight);
+
+void ro_frustum(const float* cv_xyz, int X, int Y, int Z, float* planes_out, float* campos_out);
+int ro_frustum_inside(const float* planes, const float* p);
+void ro_calib_invert(const float* cv_xyz, int X, int Y, int Z, const float* bbox_min, const float* bbox_max,
+                     const uint32_t* out_res, float* out, uint32_t* neigh_out, int brute);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,478 @@
+// C ABI of librr_b200.so (include/rgbd_recon_b200.h): context lifetime, uploads, settings, read-back, timing.
+// There is no CPU fallback: without a CUDA device rr_create fails with RR_ERR_NO_DEVICE.
+#include "rr_context.h"
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+namespace rr {
+
+int fail(rr_ctx* c, int code, const std::string& msg) {
+  if (c) c->error = msg;
+  return code;
+}
+
+int check(rr_ctx* c, cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return RR_OK;
+  return fail(c, RR_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+void timer_begin(rr_ctx* c, const char* name) {
+  if (!c->timing) return;
+  StageTimer& t = c->timers[name];
+  if (!t.beg) { cudaEventCreate(&t.beg); cudaEventCreate(&t.end); }
+  cudaEventRecord(t.beg, c->stream);
+}
+
+void timer_end(rr_ctx* c, const char* name) {
+  if (!c->timing) return;
+  StageTimer& t = c->timers[name];
+  if (!t.beg) return;
+  cudaEventRecord(t.end, c->stream);
+  t.valid = true;
+}
+
+SensorTables sensor_tables(const rr_ctx* c) {
+  SensorTables st{};
+  for (int i = 0; i < c->N; ++i) {
+    st.xyz[i] = c->d_xyz[i]; st.uv[i] = c->d_uv[i];
+    st.cx[i] = (int)c->cres[i][0]; st.cy[i] = (int)c->cres[i][1]; st.cz[i] = (int)c->cres[i][2];
+    st.dmin[i] = c->dlim[i][0]; st.dmax[i] = c->dlim[i][1];
+    for (int a = 0; a < 3; ++a) st.cam[i][a] = c->cam_pos[i][a];
+  }
+  return st;
+}
+
+template <typename T>
+static int dev_alloc(rr_ctx* c, T** p, size_t count, const char* what) {
+  if (*p) { cudaFree(*p); *p = nullptr; }
+  if (count == 0) return RR_OK;
+  return check(c, cudaMalloc((void**)p, count * sizeof(T)), what);
+}
+
+__global__ void k_pad_xyz(const float* __restrict__ src, float4* __restrict__ dst, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = make_float4(src[i * 3], src[i * 3 + 1], src[i * 3 + 2], 0.0f);
+}
+
+__global__ void k_unpad3(const float4* __restrict__ src, float* __restrict__ dst, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { const float4 v = src[i]; dst[i * 3] = v.x; dst[i * 3 + 1] = v.y; dst[i * 3 + 2] = v.z; }
+}
+
+}  // namespace rr
+
+using namespace rr;
+
+#define RR_REQUIRE(c, cond, msg) do { if (!(cond)) return fail((c), RR_ERR_INVALID, (msg)); } while (0)
+#define RR_TRY(expr) do { int rc__ = (expr); if (rc__ != RR_OK) return rc__; } while (0)
+#define RR_SET_DEVICE(c) do { cudaError_t e__ = cudaSetDevice((c)->device); if (e__ != cudaSuccess) return check((c), e__, "cudaSetDevice"); } while (0)
+
+extern "C" {
+
+int rr_version(void) { return 100; }
+
+int rr_create(rr_ctx** out, int device, int num_sensors, int depth_w, int depth_h, int color_w, int color_h) {
+  if (!out) return RR_ERR_INVALID;
+  *out = nullptr;
+  if (num_sensors < 1 || num_sensors > RR_MAX_SENSORS || depth_w < 1 || depth_h < 1 || color_w < 1 || color_h < 1) return RR_ERR_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) return RR_ERR_NO_DEVICE;
+  rr_ctx* c = new (std::nothrow) rr_ctx();
+  if (!c) return RR_ERR_INVALID;
+  c->device = device; c->N = num_sensors; c->W = depth_w; c->H = depth_h; c->CW = color_w; c->CH = color_h;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete c;
+    return RR_ERR_CUDA;
+  }
+  const size_t px = (size_t)c->N * c->W * c->H;
+  int rc = RR_OK;
+  if (rc == RR_OK) rc = dev_alloc(c, &c->d_depth_raw, px, "depth");
+  if (rc == RR_OK) rc = dev_alloc(c, &c->d_color, (size_t)c->N * c->CW * c->CH * 3, "color");
+  if (rc == RR_OK) rc = dev_alloc(c, &c->d_morph, px, "morph");
+  if (rc == RR_OK) rc = dev_alloc(c, &c->d_depth, px, "depth rg");
+  if (rc == RR_OK) rc = dev_alloc(c, &c->d_lab, px, "lab");
+  if (rc == RR_OK) rc = dev_alloc(c, &c->d_depth_b, px, "depth_b");
+  if (rc == RR_OK) rc = dev_alloc(c, &c->d_sil, px, "silhouette");
+  if (rc == RR_OK) rc = dev_alloc(c, &c->d_normal, px, "normal");
+  if (rc == RR_OK) rc = dev_alloc(c, &c->d_quality, px, "quality");
+  if (rc == RR_OK) rc = dev_alloc(c, &c->d_gather, (size_t)c->N * (c->W + 1) * (c->H + 1) * 2, "gather");
+  if (rc == RR_OK) rc = dev_alloc(c, &c->d_flags, 4, "flags");
+  if (rc == RR_OK) rc = dev_alloc(c, &c->d_num_occ, 1, "num_occ");
+  if (rc == RR_OK) rc = check(c, cudaMallocHost((void**)&c->h_num_occ, sizeof(uint32_t)), "pinned count");
+  if (rc == RR_OK) {
+    cudaMemsetAsync(c->d_flags, 0, 4 * sizeof(uint32_t), c->stream);
+    cudaMemsetAsync(c->d_num_occ, 0, sizeof(uint32_t), c->stream);
+    cudaMemsetAsync(c->d_color, 0, (size_t)c->N * c->CW * c->CH * 3, c->stream);
+    *c->h_num_occ = 0;
+    rc = check(c, cudaStreamSynchronize(c->stream), "create sync");
+  }
+  if (rc != RR_OK) { rr_destroy(c); return rc; }
+  *out = c;
+  return RR_OK;
+}
+
+void rr_destroy(rr_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  for (int i = 0; i < RR_MAX_SENSORS; ++i) { cudaFree(c->d_xyz[i]); cudaFree(c->d_uv[i]); }
+  cudaFree(c->d_inv); cudaFree(c->d_depth_raw); cudaFree(c->d_color); cudaFree(c->d_morph); cudaFree(c->d_depth);
+  cudaFree(c->d_lab); cudaFree(c->d_depth_b); cudaFree(c->d_sil); cudaFree(c->d_normal); cudaFree(c->d_quality);
+  cudaFree(c->d_gather); cudaFree(c->d_flags); cudaFree(c->d_ranges); cudaFree(c->d_counters); cudaFree(c->d_occupied);
+  cudaFree(c->d_num_occ); cudaFree(c->d_near_occ); cudaFree(c->d_tsdf); cudaFree(c->d_weight);
+  cudaFree(c->d_rgba); cudaFree(c->d_zbuf); cudaFree(c->d_nsamples);
+  if (c->h_num_occ) cudaFreeHost(c->h_num_occ);
+  for (auto& kv : c->timers) { if (kv.second.beg) { cudaEventDestroy(kv.second.beg); cudaEventDestroy(kv.second.end); } }
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char* rr_last_error(const rr_ctx* c) { return c ? c->error.c_str() : "null context"; }
+
+int rr_synchronize(rr_ctx* c) {
+  if (!c) return RR_ERR_INVALID;
+  RR_SET_DEVICE(c);
+  return check(c, cudaStreamSynchronize(c->stream), "synchronize");
+}
+
+void* rr_stream(rr_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int rr_set_bbox(rr_ctx* c, const float bmin[3], const float bmax[3]) {
+  if (!c) return RR_ERR_INVALID;
+  RR_REQUIRE(c, bmin && bmax, "rr_set_bbox: null pointer");
+  for (int a = 0; a < 3; ++a) {
+    RR_REQUIRE(c, bmax[a] > bmin[a], "rr_set_bbox: empty box");
+    c->bbox_min[a] = bmin[a]; c->bbox_max[a] = bmax[a];
+  }
+  c->have_bbox = true;
+  c->configured = false;
+  return RR_OK;
+}
+
+int rr_calib_upload(rr_ctx* c, int sensor, const float* cv_xyz, const float* cv_uv, const uint32_t res[3], const float dl[2]) {
+  if (!c) return RR_ERR_INVALID;
+  RR_REQUIRE(c, sensor >= 0 && sensor < c->N, "rr_calib_upload: sensor index out of range");
+  RR_REQUIRE(c, cv_xyz && cv_uv && res && dl, "rr_calib_upload: null pointer");
+  RR_REQUIRE(c, res[0] >= 2 && res[1] >= 2 && res[2] >= 2, "rr_calib_upload: volume needs >= 2 voxels per axis");
+  RR_SET_DEVICE(c);
+  const size_t n = (size_t)res[0] * res[1] * res[2];
+  RR_TRY(dev_alloc(c, &c->d_xyz[sensor], n, "cv_xyz"));
+  RR_TRY(dev_alloc(c, &c->d_uv[sensor], n, "cv_uv"));
+  float* staging = nullptr;
+  RR_TRY(check(c, cudaMalloc((void**)&staging, n * 3 * sizeof(float)), "cv_xyz staging"));
+  cudaMemcpyAsync(staging, cv_xyz, n * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream);
+  k_pad_xyz<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(staging, c->d_xyz[sensor], n);
+  ++c->launches;
+  cudaMemcpyAsync(c->d_uv[sensor], cv_uv, n * 2 * sizeof(float), cudaMemcpyHostToDevice, c->stream);
+  int rc = check(c, cudaStreamSynchronize(c->stream), "calib upload");
+  cudaFree(staging);
+  RR_TRY(rc);
+  for (int a = 0; a < 3; ++a) c->cres[sensor][a] = res[a];
+  c->dlim[sensor][0] = dl[0]; c->dlim[sensor][1] = dl[1];
+  host_frustum(cv_xyz, res, c->planes[sensor], c->cam_pos[sensor]);
+  c->have_calib[sensor] = true;
+  return RR_OK;
+}
+
+int rr_calib_upload_inv(rr_ctx* c, int sensor, const float* inv, const uint32_t res[3]) {
+  if (!c) return RR_ERR_INVALID;
+  RR_REQUIRE(c, sensor >= 0 && sensor < c->N, "rr_calib_upload_inv: sensor index out of range");
+  RR_REQUIRE(c, inv && res && res[0] && res[1] && res[2], "rr_calib_upload_inv: null pointer or empty volume");
+  RR_SET_DEVICE(c);
+  const size_t n = (size_t)res[0] * res[1] * res[2];
+  const bool same = c->d_inv && c->ires[0] == res[0] && c->ires[1] == res[1] && c->ires[2] == res[2];
+  if (!same) {
+    bool any = false;
+    for (int i = 0; i < c->N; ++i) any = any || (c->have_inv[i] && i != sensor);
+    RR_REQUIRE(c, !any, "rr_calib_upload_inv: all sensors must share one inverse-volume resolution (CalibVolumes::getVolumeRes)");
+    RR_TRY(dev_alloc(c, &c->d_inv, n * c->N, "cv_xyz_inv"));
+    for (int a = 0; a < 3; ++a) c->ires[a] = res[a];
+    for (int i = 0; i < c->N; ++i) c->have_inv[i] = false;
+  }
+  RR_TRY(check(c, cudaMemcpyAsync(c->d_inv + n * sensor, inv, n * sizeof(float4), cudaMemcpyHostToDevice, c->stream), "inv upload"));
+  RR_TRY(check(c, cudaStreamSynchronize(c->stream), "inv upload sync"));
+  c->have_inv[sensor] = true;
+  return RR_OK;
+}
+
+int rr_get_camera_positions(const rr_ctx* c, float* out) {
+  if (!c || !out) return RR_ERR_INVALID;
+  for (int i = 0; i < c->N; ++i) for (int a = 0; a < 3; ++a) out[i * 3 + a] = c->cam_pos[i][a];
+  return RR_OK;
+}
+
+int rr_get_frustum_planes(const rr_ctx* c, int sensor, float* out) {
+  if (!c || !out || sensor < 0 || sensor >= c->N || !c->have_calib[sensor]) return RR_ERR_INVALID;
+  std::memcpy(out, c->planes[sensor], sizeof(float) * 24);
+  return RR_OK;
+}
+
+int rr_configure(rr_ctx* c, const rr_config* cfg) {
+  if (!c) return RR_ERR_INVALID;
+  RR_REQUIRE(c, cfg, "rr_configure: null config");
+  RR_REQUIRE(c, c->have_bbox, "rr_configure: call rr_set_bbox first");
+  RR_REQUIRE(c, cfg->voxel_size > 0.0f && cfg->brick_size > 0.0f && cfg->limit > 0.0f, "rr_configure: sizes and limit must be positive");
+  RR_SET_DEVICE(c);
+  RR_TRY(check(c, cudaStreamSynchronize(c->stream), "configure sync"));
+  uint32_t res[3];
+  host_volume_res(c->bbox_min, c->bbox_max, cfg->voxel_size, res);
+  RR_REQUIRE(c, res[0] && res[1] && res[2], "rr_configure: empty volume");
+  const float bs = host_adjust_brick_size(cfg->voxel_size, cfg->brick_size);
+  RR_REQUIRE(c, bs > 0.0f, "rr_configure: brick size rounds to zero voxels");
+  const bool new_volume = !c->configured || res[0] != c->res[0] || res[1] != c->res[1] || res[2] != c->res[2] ||
+                          (cfg->store_weight != 0) != (c->d_weight != nullptr);
+  const bool new_bricks = new_volume || bs != c->bricks.brick_size;
+  if (new_volume) {
+    const size_t nvox = (size_t)res[0] * res[1] * res[2];
+    RR_TRY(dev_alloc(c, &c->d_tsdf, nvox, "tsdf volume"));
+    RR_TRY(dev_alloc(c, &c->d_weight, cfg->store_weight ? nvox : 0, "weight volume"));
+    for (int a = 0; a < 3; ++a) c->res[a] = res[a];
+    c->slab_z0 = 0; c->slab_z1 = res[2];
+  }
+  if (new_bricks) {
+    uint32_t rb[3];
+    const uint32_t nb = host_divide_box(c->bbox_min, c->bbox_max, bs, res, rb, &c->h_ranges);
+    c->bricks.brick_size = bs; c->bricks.num = nb;
+    for (int a = 0; a < 3; ++a) c->bricks.res[a] = rb[a];
+    RR_TRY(dev_alloc(c, &c->d_ranges, (size_t)nb * 6, "brick ranges"));
+    RR_TRY(dev_alloc(c, &c->d_counters, nb, "brick counters"));
+    RR_TRY(dev_alloc(c, &c->d_occupied, nb, "occupied list"));
+    RR_TRY(dev_alloc(c, &c->d_near_occ, nb, "near-occupied mask"));
+    cudaMemcpyAsync(c->d_ranges, c->h_ranges.data(), (size_t)nb * 6 * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream);
+    cudaMemsetAsync(c->d_counters, 0, nb * sizeof(uint32_t), c->stream);
+    cudaMemsetAsync(c->d_near_occ, 0, nb, c->stream);
+    cudaMemsetAsync(c->d_num_occ, 0, sizeof(uint32_t), c->stream);
+    *c->h_num_occ = 0;
+    RR_TRY(check(c, cudaStreamSynchronize(c->stream), "brick table upload"));
+  }
+  c->cfg = *cfg;
+  c->configured = true;
+  return RR_OK;
+}
+
+int rr_get_volume_res(const rr_ctx* c, uint32_t res[3]) {
+  if (!c || !res || !c->configured) return RR_ERR_INVALID;
+  for (int a = 0; a < 3; ++a) res[a] = c->res[a];
+  return RR_OK;
+}
+
+int rr_get_brick_info(const rr_ctx* c, uint32_t rb[3], float* bs, uint32_t* nb) {
+  if (!c || !c->configured) return RR_ERR_INVALID;
+  if (rb) for (int a = 0; a < 3; ++a) rb[a] = c->bricks.res[a];
+  if (bs) *bs = c->bricks.brick_size;
+  if (nb) *nb = c->bricks.num;
+  return RR_OK;
+}
+
+int rr_get_brick_ranges(const rr_ctx* c, int32_t* out) {
+  if (!c || !out || !c->configured) return RR_ERR_INVALID;
+  std::memcpy(out, c->h_ranges.data(), c->h_ranges.size() * sizeof(int32_t));
+  return RR_OK;
+}
+
+int rr_set_slab(rr_ctx* c, uint32_t z0, uint32_t z1) {
+  if (!c) return RR_ERR_INVALID;
+  RR_REQUIRE(c, c->configured, "rr_set_slab: call rr_configure first");
+  RR_REQUIRE(c, z0 <= z1 && z1 <= c->res[2], "rr_set_slab: slab outside the volume");
+  c->slab_z0 = z0; c->slab_z1 = z1;
+  return RR_OK;
+}
+
+static int upload_frames(rr_ctx* c, const void* color, size_t cb, const void* depth, size_t db, cudaMemcpyKind kind) {
+  if (!c) return RR_ERR_INVALID;
+  RR_SET_DEVICE(c);
+  const size_t want_d = (size_t)c->N * c->W * c->H * sizeof(float);
+  const size_t want_c = (size_t)c->N * c->CW * c->CH * 3;
+  RR_REQUIRE(c, depth && db == want_d, "rr_upload_frames: depth must be float32 [N][H][W]");
+  RR_REQUIRE(c, !color || cb == want_c, "rr_upload_frames: colour must be uint8 [N][CH][CW][3]");
+  RR_TRY(check(c, cudaMemcpyAsync(c->d_depth_raw, depth, want_d, kind, c->stream), "depth upload"));
+  if (color) RR_TRY(check(c, cudaMemcpyAsync(c->d_color, color, want_c, kind, c->stream), "colour upload"));
+  return RR_OK;
+}
+
+int rr_upload_frames(rr_ctx* c, const void* color, size_t cb, const void* depth, size_t db) {
+  return upload_frames(c, color, cb, depth, db, cudaMemcpyHostToDevice);
+}
+
+int rr_upload_frames_device(rr_ctx* c, const void* color, size_t cb, const void* depth, size_t db) {
+  return upload_frames(c, color, cb, depth, db, cudaMemcpyDeviceToDevice);
+}
+
+static int require_ready(rr_ctx* c, bool need_inv) {
+  RR_REQUIRE(c, c->configured, "call rr_configure first");
+  for (int i = 0; i < c->N; ++i) {
+    RR_REQUIRE(c, c->have_calib[i], "missing forward calibration volume (rr_calib_upload)");
+    if (need_inv) RR_REQUIRE(c, c->have_inv[i], "missing inverse calibration volume (rr_calib_upload_inv / rr_calib_invert)");
+  }
+  return RR_OK;
+}
+
+int rr_bricks_clear(rr_ctx* c) {
+  if (!c) return RR_ERR_INVALID;
+  RR_REQUIRE(c, c->configured, "rr_bricks_clear: call rr_configure first");
+  RR_SET_DEVICE(c);
+  return launch_bricks_clear(c);
+}
+
+int rr_preprocess(rr_ctx* c, int filter_textures, int use_processed_depth, int refine_boundary) {
+  if (!c) return RR_ERR_INVALID;
+  RR_TRY(require_ready(c, false));
+  RR_SET_DEVICE(c);
+  return launch_preprocess(c, filter_textures, use_processed_depth, refine_boundary);
+}
+
+int rr_bricks_update(rr_ctx* c, uint32_t* out_num, float* out_ratio) {
+  if (!c) return RR_ERR_INVALID;
+  RR_REQUIRE(c, c->configured, "rr_bricks_update: call rr_configure first");
+  RR_SET_DEVICE(c);
+  RR_TRY(launch_bricks_update(c));
+  if (out_num || out_ratio) {
+    RR_TRY(check(c, cudaStreamSynchronize(c->stream), "bricks update sync"));
+    if (out_num) *out_num = *c->h_num_occ;
+    if (out_ratio) *out_ratio = float(*c->h_num_occ) / float(c->bricks.num);
+  }
+  return RR_OK;
+}
+
+int rr_integrate(rr_ctx* c) {
+  if (!c) return RR_ERR_INVALID;
+  RR_TRY(require_ready(c, true));
+  RR_SET_DEVICE(c);
+  return launch_integrate(c);
+}
+
+int rr_raymarch(rr_ctx* c, const rr_view* view, float* out_rgba, float* out_depth) {
+  if (!c) return RR_ERR_INVALID;
+  RR_REQUIRE(c, view, "rr_raymarch: null view");
+  RR_TRY(require_ready(c, true));
+  RR_REQUIRE(c, view->viewport[2] > 0 && view->viewport[3] > 0, "rr_raymarch: empty viewport");
+  RR_SET_DEVICE(c);
+  const int w = view->viewport[2], h = view->viewport[3];
+  if (w != c->view_w || h != c->view_h) {
+    RR_TRY(check(c, cudaStreamSynchronize(c->stream), "raymarch resize sync"));
+    RR_TRY(dev_alloc(c, &c->d_rgba, (size_t)w * h, "view rgba"));
+    RR_TRY(dev_alloc(c, &c->d_zbuf, (size_t)w * h, "view depth"));
+    RR_TRY(dev_alloc(c, &c->d_nsamples, (size_t)w * h, "view samples"));
+    c->view_w = w; c->view_h = h;
+  }
+  RR_TRY(launch_raymarch(c, view));
+  if (out_rgba) RR_TRY(check(c, cudaMemcpyAsync(out_rgba, c->d_rgba, (size_t)w * h * sizeof(float4), cudaMemcpyDeviceToHost, c->stream), "rgba download"));
+  if (out_depth) RR_TRY(check(c, cudaMemcpyAsync(out_depth, c->d_zbuf, (size_t)w * h * sizeof(float), cudaMemcpyDeviceToHost, c->stream), "depth download"));
+  if (out_rgba || out_depth) RR_TRY(check(c, cudaStreamSynchronize(c->stream), "raymarch sync"));
+  return RR_OK;
+}
+
+int rr_calib_invert(rr_ctx* c, int sensor, const uint32_t out_res[3], float* host_out, int keep) {
+  if (!c) return RR_ERR_INVALID;
+  RR_REQUIRE(c, sensor >= 0 && sensor < c->N && c->have_calib[sensor], "rr_calib_invert: upload the sensor's cv_xyz first");
+  RR_REQUIRE(c, c->have_bbox, "rr_calib_invert: call rr_set_bbox first");
+  RR_REQUIRE(c, out_res && out_res[0] && out_res[1] && out_res[2], "rr_calib_invert: empty output resolution");
+  RR_SET_DEVICE(c);
+  const size_t n = (size_t)out_res[0] * out_res[1] * out_res[2];
+  float4* d_out = nullptr;
+  bool own = true;
+  if (keep) {
+    const bool same = c->d_inv && c->ires[0] == out_res[0] && c->ires[1] == out_res[1] && c->ires[2] == out_res[2];
+    if (!same) {
+      bool any = false;
+      for (int i = 0; i < c->N; ++i) any = any || (c->have_inv[i] && i != sensor);
+      RR_REQUIRE(c, !any, "rr_calib_invert: all sensors must share one inverse-volume resolution");
+      RR_TRY(dev_alloc(c, &c->d_inv, n * c->N, "cv_xyz_inv"));
+      for (int a = 0; a < 3; ++a) c->ires[a] = out_res[a];
+      for (int i = 0; i < c->N; ++i) c->have_inv[i] = false;
+    }
+    d_out = c->d_inv + n * sensor;
+    own = false;
+  } else {
+    RR_TRY(check(c, cudaMalloc((void**)&d_out, n * sizeof(float4)), "inverse volume"));
+  }
+  int rc = launch_calib_invert(c, sensor, out_res, d_out);
+  if (rc == RR_OK && host_out) rc = check(c, cudaMemcpyAsync(host_out, d_out, n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream), "inverse download");
+  if (rc == RR_OK) rc = check(c, cudaStreamSynchronize(c->stream), "invert sync");
+  if (own) cudaFree(d_out);
+  if (rc == RR_OK && keep) c->have_inv[sensor] = true;
+  return rc;
+}
+
+static int download(rr_ctx* c, void* dst, const void* src, size_t bytes, const char* what) {
+  RR_SET_DEVICE(c);
+  RR_TRY(check(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream), what));
+  return check(c, cudaStreamSynchronize(c->stream), what);
+}
+
+int rr_download_tsdf(rr_ctx* c, float* out) {
+  if (!c) return RR_ERR_INVALID;
+  RR_REQUIRE(c, out && c->configured, "rr_download_tsdf: not configured or null pointer");
+  return download(c, out, c->d_tsdf, (size_t)c->res[0] * c->res[1] * c->res[2] * sizeof(float), "tsdf download");
+}
+
+int rr_download_weight(rr_ctx* c, float* out) {
+  if (!c) return RR_ERR_INVALID;
+  RR_REQUIRE(c, out && c->configured && c->d_weight, "rr_download_weight: store_weight is off");
+  return download(c, out, c->d_weight, (size_t)c->res[0] * c->res[1] * c->res[2] * sizeof(float), "weight download");
+}
+
+int rr_download_stage(rr_ctx* c, int stage, float* out) {
+  if (!c) return RR_ERR_INVALID;
+  RR_REQUIRE(c, out, "rr_download_stage: null pointer");
+  const size_t px = (size_t)c->N * c->W * c->H;
+  switch (stage) {
+    case RR_STAGE_MORPH: return download(c, out, c->d_morph, px * sizeof(float), "stage download");
+    case RR_STAGE_DEPTH: return download(c, out, c->d_depth, px * sizeof(float2), "stage download");
+    case RR_STAGE_DEPTH_B: return download(c, out, c->d_depth_b, px * sizeof(float2), "stage download");
+    case RR_STAGE_SILHOUETTE: return download(c, out, c->d_sil, px * sizeof(float), "stage download");
+    case RR_STAGE_QUALITY: return download(c, out, c->d_quality, px * sizeof(float), "stage download");
+    case RR_STAGE_LAB:
+    case RR_STAGE_NORMAL: {
+      RR_SET_DEVICE(c);
+      float* tmp = nullptr;
+      RR_TRY(check(c, cudaMalloc((void**)&tmp, px * 3 * sizeof(float)), "stage staging"));
+      k_unpad3<<<(unsigned)((px + 255) / 256), 256, 0, c->stream>>>(stage == RR_STAGE_LAB ? c->d_lab : c->d_normal, tmp, px);
+      ++c->launches;
+      int rc = download(c, out, tmp, px * 3 * sizeof(float), "stage download");
+      cudaFree(tmp);
+      return rc;
+    }
+    default: return fail(c, RR_ERR_INVALID, "rr_download_stage: unknown stage");
+  }
+}
+
+int rr_download_bricks(rr_ctx* c, uint32_t* counters, uint32_t* occupied, uint32_t* num_occupied) {
+  if (!c) return RR_ERR_INVALID;
+  RR_REQUIRE(c, c->configured, "rr_download_bricks: call rr_configure first");
+  RR_SET_DEVICE(c);
+  RR_TRY(check(c, cudaStreamSynchronize(c->stream), "bricks download sync"));
+  uint32_t n = 0;
+  RR_TRY(download(c, &n, c->d_num_occ, sizeof(uint32_t), "count download"));
+  if (counters) RR_TRY(download(c, counters, c->d_counters, c->bricks.num * sizeof(uint32_t), "counters download"));
+  if (occupied && n) RR_TRY(download(c, occupied, c->d_occupied, n * sizeof(uint32_t), "occupied download"));
+  if (num_occupied) *num_occupied = n;
+  return RR_OK;
+}
+
+int rr_download_num_samples(rr_ctx* c, float* out) {
+  if (!c) return RR_ERR_INVALID;
+  RR_REQUIRE(c, out && c->d_nsamples, "rr_download_num_samples: no raymarch yet");
+  return download(c, out, c->d_nsamples, (size_t)c->view_w * c->view_h * sizeof(float), "samples download");
+}
+
+int rr_set_timing(rr_ctx* c, int enabled) {
+  if (!c) return RR_ERR_INVALID;
+  c->timing = enabled != 0;
+  return RR_OK;
+}
+
+int rr_get_stage_ms(rr_ctx* c, const char* name, float* ms) {
+  if (!c || !name || !ms) return RR_ERR_INVALID;
+  auto it = c->timers.find(name);
+  RR_REQUIRE(c, it != c->timers.end() && it->second.valid, "rr_get_stage_ms: stage has not run with timing enabled");
+  RR_SET_DEVICE(c);
+  RR_TRY(check(c, cudaEventSynchronize(it->second.end), "stage timer sync"));
+  return check(c, cudaEventElapsedTime(ms, it->second.beg, it->second.end), "stage timer");
+}
+
+uint64_t rr_launch_count(const rr_ctx* c) { return c ? c->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,138 @@
+// Internal state behind the opaque rr_ctx of include/rgbd_recon_b200.h. One context = one GPU, one stream.
+//
+// Device memory layout (all allocations live for the context's lifetime; sized for 180 GB HBM3e, nothing is paged):
+//   frames     depth float[N][H][W], colour uint8[N][CH][CW][3]                       (written by rr_upload_frames)
+//   calib      per sensor cv_xyz as float4[Z][Y][X] (xyz padded to 16 B so a corner is one LDG.128),
+//              cv_uv float2[Z][Y][X]; cv_xyz_inv float4[N][IZ][IY][IX] in one allocation
+//   stages     morph float, depth float2, lab float4, depth_b float2, silhouette float, normal float4, quality float,
+//              each [N][H][W]
+//   gather     float4[N][H+1][W+1][2]: per bilinear footprint (i0,j0) the four depth_b.x taps and the four quality
+//              taps (silhouette in the sign bit) = one 32-byte sector per voxel-sensor lookup in the integrator
+//   bricks     uint32 counters[nb], occupied[nb], count; int32 ranges[nb][6]; uint8 near_occupied[nb]
+//   volume     tsdf float[Z][Y][X] (+ weight float[Z][Y][X] when rr_config.store_weight)
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/rgbd_recon_b200.h"
+
+#define RR_MAX_SENSORS 8
+
+namespace rr {
+
+struct SensorTables {            // passed to kernels by value (__grid_constant__)
+  const float4* xyz[RR_MAX_SENSORS];
+  const float2* uv[RR_MAX_SENSORS];
+  int cx[RR_MAX_SENSORS], cy[RR_MAX_SENSORS], cz[RR_MAX_SENSORS];
+  float dmin[RR_MAX_SENSORS], dmax[RR_MAX_SENSORS];
+  float cam[RR_MAX_SENSORS][3];
+};
+
+struct BrickGrid {
+  float brick_size;
+  uint32_t res[3];
+  uint32_t num;
+};
+
+struct StageTimer {
+  cudaEvent_t beg = nullptr, end = nullptr;
+  bool valid = false;
+};
+
+}  // namespace rr
+
+struct rr_ctx {
+  int device = 0;
+  int N = 0, W = 0, H = 0, CW = 0, CH = 0;
+  cudaStream_t stream = nullptr;
+  std::string error;
+  uint64_t launches = 0;
+  bool timing = false;
+  std::map<std::string, rr::StageTimer> timers;
+
+  // calibration
+  float bbox_min[3] = {0, 0, 0}, bbox_max[3] = {0, 0, 0};
+  bool have_bbox = false;
+  float4* d_xyz[RR_MAX_SENSORS] = {};
+  float2* d_uv[RR_MAX_SENSORS] = {};
+  uint32_t cres[RR_MAX_SENSORS][3] = {};
+  float dlim[RR_MAX_SENSORS][2] = {};
+  float cam_pos[RR_MAX_SENSORS][3] = {};
+  float planes[RR_MAX_SENSORS][6][4] = {};
+  bool have_calib[RR_MAX_SENSORS] = {};
+  float4* d_inv = nullptr;
+  uint32_t ires[3] = {0, 0, 0};
+  bool have_inv[RR_MAX_SENSORS] = {};
+
+  // frames + stages
+  float* d_depth_raw = nullptr;
+  uint8_t* d_color = nullptr;
+  float* d_morph = nullptr;
+  float2* d_depth = nullptr;
+  float4* d_lab = nullptr;
+  float2* d_depth_b = nullptr;
+  float* d_sil = nullptr;
+  float4* d_normal = nullptr;
+  float* d_quality = nullptr;
+  float4* d_gather = nullptr;
+  uint32_t* d_flags = nullptr;     // [0] pack-encoding violation counter
+
+  // settings + bricks + volume
+  rr_config cfg{};
+  bool configured = false;
+  uint32_t res[3] = {0, 0, 0};
+  uint32_t slab_z0 = 0, slab_z1 = 0;
+  rr::BrickGrid bricks{};
+  std::vector<int32_t> h_ranges;
+  int32_t* d_ranges = nullptr;
+  uint32_t* d_counters = nullptr;
+  uint32_t* d_occupied = nullptr;
+  uint32_t* d_num_occ = nullptr;
+  uint8_t* d_near_occ = nullptr;
+  uint32_t* h_num_occ = nullptr;   // pinned
+  float* d_tsdf = nullptr;
+  float* d_weight = nullptr;
+
+  // raymarch outputs
+  int view_w = 0, view_h = 0;
+  float4* d_rgba = nullptr;
+  float* d_zbuf = nullptr;
+  float* d_nsamples = nullptr;
+};
+
+namespace rr {
+
+int fail(rr_ctx* c, int code, const std::string& msg);
+int check(rr_ctx* c, cudaError_t e, const char* what);
+void timer_begin(rr_ctx* c, const char* name);
+void timer_end(rr_ctx* c, const char* name);
+SensorTables sensor_tables(const rr_ctx* c);
+
+// kernels' host launchers (one translation unit each)
+int launch_preprocess(rr_ctx* c, int filter_textures, int use_processed_depth, int refine);
+int launch_bricks_clear(rr_ctx* c);
+int launch_bricks_update(rr_ctx* c);
+int launch_integrate(rr_ctx* c);
+int launch_raymarch(rr_ctx* c, const rr_view* v);
+int launch_calib_invert(rr_ctx* c, int sensor, const uint32_t out_res[3], float4* d_out);
+
+// host geometry (rr_host_geom.cpp)
+void host_frustum(const float* cv_xyz, const uint32_t res[3], float planes[6][4], float cam[3]);
+void host_volume_res(const float bmin[3], const float bmax[3], float voxel_size, uint32_t res[3]);
+float host_adjust_brick_size(float voxel_size, float size);
+uint32_t host_divide_box(const float bmin[3], const float bmax[3], float brick_size, const uint32_t res[3],
+                         uint32_t res_bricks[3], std::vector<int32_t>* ranges);
+
+}  // namespace rr
+
+#define RR_LAUNCH_CHECK(c, what)                                   \
+  do {                                                             \
+    ++(c)->launches;                                               \
+    cudaError_t e__ = cudaGetLastError();                          \
+    if (e__ != cudaSuccess) return rr::check((c), e__, (what));    \
+  } while (0)

@@ -1,0 +1,192 @@
+// TSDF integration for sm_100a: the per-voxel work of glsl/tsdf_integration.vs:23-59, driven like
+// ReconIntegration::integrate (framework/reconstruction/recon_integration.cpp:243-270): clear to -limit, then either
+// every voxel (dense) or the voxels of every occupied brick.
+//
+// Kernel shape (DESIGN.md "integrate"): one thread owns an (x, y) column of the volume and marches z. The x/y part of
+// the trilinear inverse-calibration lookup (cv_xyz_inv, LINEAR filtering restated in fp32) is reduced once per coarse
+// z-plane and kept in registers for all N sensors, so the 8-corner gather of the shader becomes 4 corner loads per
+// coarse plane per sensor; consecutive lanes are consecutive x, so the R32F stores are 128-byte coalesced rows.
+// Silhouette (bilinear), depth (nearest) and quality (bilinear) come from ONE 32-byte gather texel per voxel-sensor
+// (see k_pack_gather). HBM-bound integer/float gather work: no tensor-core path applies.
+#include "rr_context.h"
+#include "rr_math.cuh"
+
+namespace rr {
+
+struct IntegrateParams {
+  const float4* inv;      // [N][IZ][IY][IX]
+  const float4* gather;   // [N][H+1][W+1][2]
+  float* tsdf;
+  float* weight;
+  const int32_t* ranges;  // [num_bricks][6]
+  const uint32_t* occupied;
+  const uint32_t* num_occupied;
+  int IX, IY, IZ, W, H, X, Y, Z;
+  int z_begin, z_end;     // slab
+  int z_chunk;
+  float limit;
+};
+
+template <int N, bool WEIGHT>
+__device__ __forceinline__ void march_column(const IntegrateParams& p, int x, int y, int zb, int ze) {
+  const float stepX = 1.0f / (float)p.X, stepY = 1.0f / (float)p.Y, stepZ = 1.0f / (float)p.Z;
+  const float px = ((float)x + 0.5f) * stepX, py = ((float)y + 0.5f) * stepY;
+  int x0, x1, y0, y1; float a, b;
+  lin_coord(px, p.IX, x0, x1, a);
+  lin_coord(py, p.IY, y0, y1, b);
+  const int o00 = y0 * p.IX + x0, o10 = y0 * p.IX + x1, o01 = y1 * p.IX + x0, o11 = y1 * p.IX + x1;
+  const size_t plane_sz = (size_t)p.IX * p.IY;
+  const size_t gstride = (size_t)(p.W + 1) * (p.H + 1) * 2;
+  const float limit = p.limit;
+  float3 A[N], B[N];
+  int ck0 = -1, ck1 = -1;
+
+  auto plane = [&](int s, int k) -> float3 {
+    const float4* base = p.inv + ((size_t)s * p.IZ + k) * plane_sz;
+    const float4 p00 = __ldg(base + o00), p10 = __ldg(base + o10), p01 = __ldg(base + o01), p11 = __ldg(base + o11);
+    float3 r;
+    r.x = lerpf(lerpf(p00.x, p10.x, a), lerpf(p01.x, p11.x, a), b);
+    r.y = lerpf(lerpf(p00.y, p10.y, a), lerpf(p01.y, p11.y, a), b);
+    r.z = lerpf(lerpf(p00.z, p10.z, a), lerpf(p01.z, p11.z, a), b);
+    return r;
+  };
+
+  for (int z = zb; z < ze; ++z) {
+    const float pz = ((float)z + 0.5f) * stepZ;
+    int k0, k1; float g;
+    lin_coord(pz, p.IZ, k0, k1, g);
+    const bool needA = (k0 != ck0), a_from_b = needA && (k0 == ck1);
+    const bool needB = (k1 != ck1), b_from_a = needB && (k1 == k0);
+    float weighted_tsd = limit, total_weight = 0.0f;
+#pragma unroll
+    for (int s = 0; s < N; ++s) {
+      if (needA) A[s] = a_from_b ? B[s] : plane(s, k0);
+      if (needB) B[s] = b_from_a ? A[s] : plane(s, k1);
+      const float u = lerpf(A[s].x, B[s].x, g), v = lerpf(A[s].y, B[s].y, g), d = lerpf(A[s].z, B[s].z, g);
+      // footprint of the bilinear (silhouette, quality) and nearest (depth) lookups at (u, v)
+      const float tu = u * (float)p.W, tv = v * (float)p.H;
+      const float uu = tu - 0.5f, vv = tv - 0.5f;
+      const float fu = floorf(uu), fv = floorf(vv);
+      const float wa = uu - fu, wb = vv - fv;
+      const int ex = f2i_clamp(fu, -1, p.W - 1) + 1, ey = f2i_clamp(fv, -1, p.H - 1) + 1;
+      const bool selx = f2i_clamp(floorf(tu), 0, p.W - 1) != f2i_clamp(fu, 0, p.W - 1);
+      const bool sely = f2i_clamp(floorf(tv), 0, p.H - 1) != f2i_clamp(fv, 0, p.H - 1);
+      const float4* g4 = p.gather + (size_t)s * gstride + ((size_t)ey * (p.W + 1) + ex) * 2;
+      const float4 lo = __ldg(g4), hi = __ldg(g4 + 1);
+      const float s00 = (float)(__float_as_uint(hi.x) >> 31), s10 = (float)(__float_as_uint(hi.y) >> 31);
+      const float s01 = (float)(__float_as_uint(hi.z) >> 31), s11 = (float)(__float_as_uint(hi.w) >> 31);
+      const float silhouette = lerpf(lerpf(s00, s10, wa), lerpf(s01, s11, wa), wb);
+      if (silhouette < 1.0f) {
+        if (weighted_tsd >= limit) { weighted_tsd = -limit; continue; }
+      }
+      const float depth = sely ? (selx ? lo.w : lo.z) : (selx ? lo.y : lo.x);
+      const float sdist = d - depth;
+      if (sdist <= -limit) {
+        weighted_tsd = -limit;
+      } else if (sdist >= limit) {
+      } else {
+        const float q00 = fabsf(hi.x), q10 = fabsf(hi.y), q01 = fabsf(hi.z), q11 = fabsf(hi.w);
+        const float w = lerpf(lerpf(q00, q10, wa), lerpf(q01, q11, wa), wb);
+        weighted_tsd = (weighted_tsd * total_weight + w * sdist) / (total_weight + w);
+        total_weight += w;
+      }
+    }
+    ck0 = k0; ck1 = k1;
+    const size_t o = ((size_t)z * p.Y + y) * p.X + x;
+    p.tsdf[o] = weighted_tsd;
+    if (WEIGHT) p.weight[o] = total_weight;
+  }
+}
+
+template <int N, bool WEIGHT>
+__global__ void __launch_bounds__(256) k_integrate_dense(const __grid_constant__ IntegrateParams p) {
+  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  if (x >= p.X || y >= p.Y) return;
+  const int zb = p.z_begin + blockIdx.z * p.z_chunk;
+  const int ze = min(zb + p.z_chunk, p.z_end);
+  march_column<N, WEIGHT>(p, x, y, zb, ze);
+}
+
+// One block per occupied brick (VolumeSampler::sample(indices), volume_sampler.cpp:74-76). Bricks may overlap or
+// leave gaps by one voxel (float rounding in divideBox/containedVoxels); overlapping voxels get the same value twice.
+template <int N, bool WEIGHT>
+__global__ void __launch_bounds__(256) k_integrate_bricks(const __grid_constant__ IntegrateParams p) {
+  if (blockIdx.x >= *p.num_occupied) return;
+  const int32_t* r = p.ranges + (size_t)p.occupied[blockIdx.x] * 6;
+  const int x0 = r[0], x1 = r[1], y0 = r[2], y1 = r[3];
+  const int zb = max(r[4], p.z_begin), ze = min(r[5], p.z_end);
+  if (zb >= ze) return;
+  for (int y = y0 + threadIdx.y; y < y1; y += 8)
+    for (int x = x0 + threadIdx.x; x < x1; x += 32) march_column<N, WEIGHT>(p, x, y, zb, ze);
+}
+
+// glClearTexImage(-limit) (recon_integration.cpp:250-251): 16-byte streaming stores over the slab.
+__global__ void __launch_bounds__(256) k_fill(float* __restrict__ dst, size_t n, float value) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t n4 = n / 4;
+  float4* d4 = reinterpret_cast<float4*>(dst);
+  const float4 v = make_float4(value, value, value, value);
+  for (size_t j = i; j < n4; j += stride) __stcs(d4 + j, v);
+  for (size_t j = n4 * 4 + i; j < n; j += stride) dst[j] = value;
+}
+
+template <int N>
+static int launch_n(rr_ctx* c, const IntegrateParams& p, bool bricks, bool weight) {
+  const dim3 blk(32, 8, 1);
+  if (bricks) {
+    const dim3 grd(c->bricks.num, 1, 1);
+    if (weight) k_integrate_bricks<N, true><<<grd, blk, 0, c->stream>>>(p);
+    else k_integrate_bricks<N, false><<<grd, blk, 0, c->stream>>>(p);
+  } else {
+    const int nz = p.z_end - p.z_begin;
+    const dim3 grd((p.X + 31) / 32, (p.Y + 7) / 8, (nz + p.z_chunk - 1) / p.z_chunk);
+    if (weight) k_integrate_dense<N, true><<<grd, blk, 0, c->stream>>>(p);
+    else k_integrate_dense<N, false><<<grd, blk, 0, c->stream>>>(p);
+  }
+  RR_LAUNCH_CHECK(c, "k_integrate");
+  return RR_OK;
+}
+
+int launch_integrate(rr_ctx* c) {
+  IntegrateParams p{};
+  p.inv = c->d_inv; p.gather = c->d_gather; p.tsdf = c->d_tsdf; p.weight = c->d_weight;
+  p.ranges = c->d_ranges; p.occupied = c->d_occupied; p.num_occupied = c->d_num_occ;
+  p.IX = (int)c->ires[0]; p.IY = (int)c->ires[1]; p.IZ = (int)c->ires[2];
+  p.W = c->W; p.H = c->H; p.X = (int)c->res[0]; p.Y = (int)c->res[1]; p.Z = (int)c->res[2];
+  p.z_begin = (int)c->slab_z0; p.z_end = (int)c->slab_z1;
+  p.z_chunk = 32;
+  p.limit = c->cfg.limit;
+  const bool weight = c->cfg.store_weight != 0;
+  const bool bricks = c->cfg.use_bricks != 0;
+  timer_begin(c, "2integrate");
+  const size_t plane = (size_t)p.X * p.Y;
+  const size_t nslab = plane * (size_t)(p.z_end - p.z_begin);
+  if (bricks && nslab) {
+    // dense mode overwrites every voxel, so only the brick path needs the clear
+    k_fill<<<148 * 8, 256, 0, c->stream>>>(c->d_tsdf + plane * p.z_begin, nslab, -p.limit);
+    RR_LAUNCH_CHECK(c, "k_fill");
+    if (weight) {
+      k_fill<<<148 * 8, 256, 0, c->stream>>>(c->d_weight + plane * p.z_begin, nslab, 0.0f);
+      RR_LAUNCH_CHECK(c, "k_fill");
+    }
+  }
+  int rc = RR_OK;
+  if (nslab) {
+    switch (c->N) {
+      case 1: rc = launch_n<1>(c, p, bricks, weight); break;
+      case 2: rc = launch_n<2>(c, p, bricks, weight); break;
+      case 3: rc = launch_n<3>(c, p, bricks, weight); break;
+      case 4: rc = launch_n<4>(c, p, bricks, weight); break;
+      case 5: rc = launch_n<5>(c, p, bricks, weight); break;
+      case 6: rc = launch_n<6>(c, p, bricks, weight); break;
+      case 7: rc = launch_n<7>(c, p, bricks, weight); break;
+      case 8: rc = launch_n<8>(c, p, bricks, weight); break;
+      default: return fail(c, RR_ERR_UNSUPPORTED, "integrate: 1..8 sensors supported");
+    }
+  }
+  timer_end(c, "2integrate");
+  return rc;
+}
+
+}  // namespace rr

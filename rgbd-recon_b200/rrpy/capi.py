@@ -1,0 +1,296 @@
+"""ctypes binding of librr_b200.so (include/rgbd_recon_b200.h) for tests and bench.py.
+
+This is harness code: the product's host side is the C++ in rgbd-recon_b200/host/. Loading fails loudly when the
+CUDA library has not been built; there is no CPU fallback of any kind.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "librr_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(os.path.dirname(_HERE)), "include", "rgbd_recon_b200.h")
+
+STAGES = dict(morph=0, depth=1, lab=2, depth_b=3, sil=4, normal=5, quality=6)
+_STAGE_CH = dict(morph=1, depth=2, lab=3, depth_b=2, sil=1, normal=3, quality=1)
+
+
+class Config(C.Structure):
+    _fields_ = [("limit", C.c_float), ("voxel_size", C.c_float), ("brick_size", C.c_float),
+                ("min_voxels_per_brick", C.c_uint32), ("use_bricks", C.c_int32), ("skip_space", C.c_int32),
+                ("store_weight", C.c_int32)]
+
+
+class View(C.Structure):
+    _fields_ = [("modelview", C.c_float * 16), ("projection", C.c_float * 16), ("viewport", C.c_int32 * 4),
+                ("shade_mode", C.c_int32)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: build it with `make -C rgbd-recon_b200` (or __graft_entry__.build()); "
+                           "there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, f32, u32, i32 = C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(C.c_int32)
+    L.rr_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.rr_destroy.argtypes = [vp]
+    L.rr_destroy.restype = None
+    L.rr_last_error.argtypes = [vp]
+    L.rr_last_error.restype = C.c_char_p
+    L.rr_synchronize.argtypes = [vp]
+    L.rr_stream.argtypes = [vp]
+    L.rr_stream.restype = vp
+    L.rr_set_bbox.argtypes = [vp, f32, f32]
+    L.rr_calib_upload.argtypes = [vp, C.c_int, f32, f32, u32, f32]
+    L.rr_calib_upload_inv.argtypes = [vp, C.c_int, f32, u32]
+    L.rr_get_camera_positions.argtypes = [vp, f32]
+    L.rr_get_frustum_planes.argtypes = [vp, C.c_int, f32]
+    L.rr_calib_invert.argtypes = [vp, C.c_int, u32, f32, C.c_int]
+    L.rr_configure.argtypes = [vp, C.POINTER(Config)]
+    L.rr_get_volume_res.argtypes = [vp, u32]
+    L.rr_get_brick_info.argtypes = [vp, u32, f32, u32]
+    L.rr_get_brick_ranges.argtypes = [vp, i32]
+    L.rr_set_slab.argtypes = [vp, C.c_uint32, C.c_uint32]
+    L.rr_upload_frames.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t]
+    L.rr_upload_frames_device.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t]
+    L.rr_bricks_clear.argtypes = [vp]
+    L.rr_preprocess.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+    L.rr_bricks_update.argtypes = [vp, u32, f32]
+    L.rr_integrate.argtypes = [vp]
+    L.rr_raymarch.argtypes = [vp, C.POINTER(View), f32, f32]
+    L.rr_download_tsdf.argtypes = [vp, f32]
+    L.rr_download_weight.argtypes = [vp, f32]
+    L.rr_download_stage.argtypes = [vp, C.c_int, f32]
+    L.rr_download_bricks.argtypes = [vp, u32, u32, u32]
+    L.rr_download_num_samples.argtypes = [vp, f32]
+    L.rr_set_timing.argtypes = [vp, C.c_int]
+    L.rr_get_stage_ms.argtypes = [vp, C.c_char_p, f32]
+    L.rr_launch_count.argtypes = [vp]
+    L.rr_launch_count.restype = C.c_uint64
+    L.rr_version.restype = C.c_int
+    _lib = L
+    return L
+
+
+def _f32(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _u32(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint32))
+
+
+class RRError(RuntimeError):
+    pass
+
+
+class Fusion:
+    """Thin object wrapper: one rr_ctx. Method names follow the C ABI."""
+
+    def __init__(self, N, W, H, CW, CH, device=0):
+        self.L = lib()
+        self.h = C.c_void_p()
+        self.N, self.W, self.H, self.CW, self.CH = N, W, H, CW, CH
+        rc = self.L.rr_create(C.byref(self.h), device, N, W, H, CW, CH)
+        if rc != 0:
+            raise RRError(f"rr_create failed with status {rc} (no CUDA device? there is no CPU fallback)")
+
+    def close(self):
+        if self.h:
+            self.L.rr_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise RRError(f"status {rc}: {self.L.rr_last_error(self.h).decode()}")
+
+    # calibration
+    def set_bbox(self, bmin, bmax):
+        bmin = np.ascontiguousarray(bmin, np.float32)
+        bmax = np.ascontiguousarray(bmax, np.float32)
+        self._ck(self.L.rr_set_bbox(self.h, _f32(bmin), _f32(bmax)))
+
+    def calib_upload(self, sensor, cv_xyz, cv_uv, depth_limits=(0.5, 4.5)):
+        Z, Y, X, _ = cv_xyz.shape
+        xyz = np.ascontiguousarray(cv_xyz, np.float32)
+        uv = np.ascontiguousarray(cv_uv, np.float32)
+        res = np.array([X, Y, Z], np.uint32)
+        dl = np.array(depth_limits, np.float32)
+        self._ck(self.L.rr_calib_upload(self.h, sensor, _f32(xyz), _f32(uv), _u32(res), _f32(dl)))
+
+    def calib_upload_inv(self, sensor, inv):
+        Z, Y, X, _ = inv.shape
+        a = np.ascontiguousarray(inv, np.float32)
+        res = np.array([X, Y, Z], np.uint32)
+        self._ck(self.L.rr_calib_upload_inv(self.h, sensor, _f32(a), _u32(res)))
+
+    def camera_positions(self):
+        out = np.zeros((self.N, 3), np.float32)
+        self._ck(self.L.rr_get_camera_positions(self.h, _f32(out)))
+        return out
+
+    def frustum_planes(self, sensor):
+        out = np.zeros((6, 4), np.float32)
+        self._ck(self.L.rr_get_frustum_planes(self.h, sensor, _f32(out)))
+        return out
+
+    def calib_invert(self, sensor, out_res, keep=False, download=True):
+        ox, oy, oz = [int(v) for v in out_res]
+        res = np.array([ox, oy, oz], np.uint32)
+        out = np.zeros((oz, oy, ox, 4), np.float32) if download else None
+        self._ck(self.L.rr_calib_invert(self.h, sensor, _u32(res), _f32(out) if download else None, int(keep)))
+        return out
+
+    # settings
+    def configure(self, limit=0.01, voxel_size=0.01, brick_size=0.1, min_voxels=10, use_bricks=True, skip_space=True,
+                  store_weight=False):
+        cfg = Config(limit, voxel_size, brick_size, min_voxels, int(use_bricks), int(skip_space), int(store_weight))
+        self._ck(self.L.rr_configure(self.h, C.byref(cfg)))
+
+    def volume_res(self):
+        r = np.zeros(3, np.uint32)
+        self._ck(self.L.rr_get_volume_res(self.h, _u32(r)))
+        return r
+
+    def brick_info(self):
+        rb = np.zeros(3, np.uint32)
+        bs = C.c_float()
+        nb = C.c_uint32()
+        self._ck(self.L.rr_get_brick_info(self.h, _u32(rb), C.byref(bs), C.byref(nb)))
+        return dict(res_bricks=rb, brick_size=np.float32(bs.value), num_bricks=int(nb.value))
+
+    def brick_ranges(self):
+        nb = self.brick_info()["num_bricks"]
+        out = np.zeros((nb, 6), np.int32)
+        self._ck(self.L.rr_get_brick_ranges(self.h, out.ctypes.data_as(C.POINTER(C.c_int32))))
+        return out
+
+    def set_slab(self, z0, z1):
+        self._ck(self.L.rr_set_slab(self.h, int(z0), int(z1)))
+
+    # per frame
+    def upload_frames(self, color, depth):
+        depth = np.ascontiguousarray(depth, np.float32)
+        if color is not None:
+            color = np.ascontiguousarray(color, np.uint8)
+        self._ck(self.L.rr_upload_frames(self.h, color.ctypes.data if color is not None else None,
+                                         color.nbytes if color is not None else 0, depth.ctypes.data, depth.nbytes))
+        self.synchronize()   # numpy buffers are pageable and may be temporaries
+
+    def upload_frames_ptr(self, color_ptr, color_bytes, depth_ptr, depth_bytes, device=False):
+        f = self.L.rr_upload_frames_device if device else self.L.rr_upload_frames
+        self._ck(f(self.h, color_ptr, color_bytes, depth_ptr, depth_bytes))
+
+    def bricks_clear(self):
+        self._ck(self.L.rr_bricks_clear(self.h))
+
+    def preprocess(self, filter_textures=True, use_processed_depth=True, refine=True):
+        self._ck(self.L.rr_preprocess(self.h, int(filter_textures), int(use_processed_depth), int(refine)))
+
+    def bricks_update(self, sync=True):
+        if not sync:
+            self._ck(self.L.rr_bricks_update(self.h, None, None))
+            return None
+        n = C.c_uint32()
+        r = C.c_float()
+        self._ck(self.L.rr_bricks_update(self.h, C.byref(n), C.byref(r)))
+        return int(n.value), float(r.value)
+
+    def integrate(self):
+        self._ck(self.L.rr_integrate(self.h))
+
+    def raymarch(self, modelview, projection, width, height, shade_mode=0, download=True):
+        v = View()
+        v.modelview[:] = [float(x) for x in np.asarray(modelview, np.float32).reshape(16)]
+        v.projection[:] = [float(x) for x in np.asarray(projection, np.float32).reshape(16)]
+        v.viewport[:] = [0, 0, int(width), int(height)]
+        v.shade_mode = int(shade_mode)
+        if not download:
+            self._ck(self.L.rr_raymarch(self.h, C.byref(v), None, None))
+            return None
+        rgba = np.zeros((height, width, 4), np.float32)
+        depth = np.zeros((height, width), np.float32)
+        self._ck(self.L.rr_raymarch(self.h, C.byref(v), _f32(rgba), _f32(depth)))
+        return rgba, depth
+
+    def frame(self, filter_textures=True, use_processed_depth=True, refine=True, sync_bricks=False):
+        """The per-frame sequence of kinect_client.cpp:572-600 after update(): clear, process, update bricks, integrate."""
+        self.bricks_clear()
+        self.preprocess(filter_textures, use_processed_depth, refine)
+        r = self.bricks_update(sync=sync_bricks)
+        self.integrate()
+        return r
+
+    # read-back
+    def synchronize(self):
+        self._ck(self.L.rr_synchronize(self.h))
+
+    def download_tsdf(self):
+        r = self.volume_res()
+        out = np.zeros((int(r[2]), int(r[1]), int(r[0])), np.float32)
+        self._ck(self.L.rr_download_tsdf(self.h, _f32(out)))
+        return out
+
+    def download_weight(self):
+        r = self.volume_res()
+        out = np.zeros((int(r[2]), int(r[1]), int(r[0])), np.float32)
+        self._ck(self.L.rr_download_weight(self.h, _f32(out)))
+        return out
+
+    def download_stage(self, name):
+        ch = _STAGE_CH[name]
+        shape = (self.N, self.H, self.W) + ((ch,) if ch > 1 else ())
+        out = np.zeros(shape, np.float32)
+        self._ck(self.L.rr_download_stage(self.h, STAGES[name], _f32(out)))
+        return out
+
+    def download_bricks(self):
+        nb = self.brick_info()["num_bricks"]
+        counters = np.zeros(nb, np.uint32)
+        occ = np.zeros(nb, np.uint32)
+        n = C.c_uint32()
+        self._ck(self.L.rr_download_bricks(self.h, _u32(counters), _u32(occ), C.byref(n)))
+        return counters, occ[: n.value].copy()
+
+    def download_num_samples(self, width, height):
+        out = np.zeros((height, width), np.float32)
+        self._ck(self.L.rr_download_num_samples(self.h, _f32(out)))
+        return out
+
+    def set_timing(self, on=True):
+        self._ck(self.L.rr_set_timing(self.h, int(on)))
+
+    def stage_ms(self, name):
+        ms = C.c_float()
+        self._ck(self.L.rr_get_stage_ms(self.h, name.encode(), C.byref(ms)))
+        return float(ms.value)
+
+    def launch_count(self):
+        return int(self.L.rr_launch_count(self.h))
+
+    def stream(self):
+        return self.L.rr_stream(self.h)
+
+
+def load_scene(fu: "Fusion", scene, inv=None):
+    """Upload a synth.Scene (bbox, forward volumes, optional inverse volumes) into a context."""
+    fu.set_bbox(scene.bbox_min, scene.bbox_max)
+    for i in range(scene.N):
+        fu.calib_upload(i, scene.cv_xyz[i], scene.cv_uv[i])
+        if inv is not None:
+            fu.calib_upload_inv(i, inv[i])

@@ -1,0 +1,89 @@
+"""GPU parity: CUDA path through the C ABI vs the scalar oracle on the same seeded synthetic frames.
+
+Bars (BASELINE.json north_star): brick counters / occupied lists bit-exact; TSDF, weights, normals within
+1e-5 * limit — in practice the pinned arithmetic makes every stage bit-identical, and that is what is asserted.
+"""
+import numpy as np
+import pytest
+
+from conftest import bits_equal, mismatch_report
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_both(scene, voxel_size, inv_res, use_bricks, flags=(True, True, True), store_weight=False, limit=0.01):
+    import oracle_py as O
+    from rrpy import capi, synth
+    inv = synth.analytic_inverse(scene, inv_res)
+    fu = capi.Fusion(scene.N, scene.W, scene.H, scene.CW, scene.CH)
+    capi.load_scene(fu, scene, inv)
+    fu.configure(limit=limit, voxel_size=voxel_size, brick_size=0.1, min_voxels=10, use_bricks=use_bricks, store_weight=store_weight)
+    fu.upload_frames(scene.color, scene.depth)
+    n_occ, ratio = fu.frame(*flags, sync_bricks=True)
+    got = {k: fu.download_stage(k) for k in capi.STAGES}
+    got["counters"], got["occupied"] = fu.download_bricks()
+    got["tsdf"] = fu.download_tsdf()
+    if store_weight:
+        got["weight"] = fu.download_weight()
+    got["n_occ"], got["ratio"] = n_occ, ratio
+    got["cams"] = fu.camera_positions()
+    got["res"] = fu.volume_res()
+    got["brick_info"] = fu.brick_info()
+    got["ranges"] = fu.brick_ranges()
+    fu.close()
+
+    grid = O.brick_grid(scene.bbox_min, scene.bbox_max, voxel_size, 0.1)
+    cams = [O.frustum(scene.cv_xyz[i])[1] for i in range(scene.N)]
+    pre = O.preprocess(scene, grid, cams, *flags)
+    occ = O.occupied_bricks(pre["bricks"], 10)
+    ts = O.integrate(inv, pre, grid, limit, use_bricks, occ, want_weight=store_weight)
+    want = dict(pre)
+    want["counters"], want["occupied"] = pre["bricks"], occ
+    if store_weight:
+        want["tsdf"], want["weight"] = ts
+    else:
+        want["tsdf"] = ts
+    want["grid"], want["cams"] = grid, np.array(cams)
+    return got, want
+
+
+def _assert_frame(got, want, stages=("morph", "depth", "lab", "depth_b", "sil", "normal", "quality")):
+    g = want["grid"]
+    assert np.array_equal(got["res"], g["res"])
+    assert got["brick_info"]["num_bricks"] == g["num_bricks"]
+    assert np.array_equal(got["brick_info"]["res_bricks"], g["res_bricks"])
+    assert np.float32(got["brick_info"]["brick_size"]).tobytes() == np.float32(g["brick_size"]).tobytes()
+    assert np.array_equal(got["ranges"], g["ranges"])
+    assert bits_equal(got["cams"], want["cams"]).all(), mismatch_report("camera positions", got["cams"], want["cams"])
+    for k in stages:
+        assert bits_equal(got[k], want[k]).all(), mismatch_report(k, got[k], want[k])
+    assert np.array_equal(got["counters"], want["counters"]), "brick counters differ"
+    assert np.array_equal(got["occupied"], want["occupied"]), "occupied brick list differs"
+    assert got["n_occ"] == len(want["occupied"])
+    assert bits_equal(got["tsdf"], want["tsdf"]).all(), mismatch_report("tsdf", got["tsdf"], want["tsdf"])
+    if "weight" in want:
+        assert bits_equal(got["weight"], want["weight"]).all(), mismatch_report("weight", got["weight"], want["weight"])
+
+
+def test_frame_bricks_small(small_scene):
+    got, want = _run_both(small_scene, 0.02, (50, 55, 50), use_bricks=True)
+    assert len(want["occupied"]) > 20, "synthetic scene should occupy bricks"
+    assert ((want["tsdf"] > -0.01) & (want["tsdf"] < 0.01)).sum() > 1000, "scene should produce a TSDF band"
+    _assert_frame(got, want)
+
+
+def test_frame_dense_small_with_weight(small_scene):
+    got, want = _run_both(small_scene, 0.02, (50, 55, 50), use_bricks=False, store_weight=True)
+    _assert_frame(got, want)
+
+
+@pytest.mark.parametrize("flags", [(False, True, True), (True, False, True), (True, True, False)])
+def test_frame_flag_variants(small_scene, flags):
+    got, want = _run_both(small_scene, 0.025, (40, 44, 40), use_bricks=True, flags=flags)
+    _assert_frame(got, want)
+
+
+def test_frame_inverse_finer_than_volume(small_scene):
+    # reference default: 1 cm voxels over a 7 mm inverse volume (coarse cells smaller than voxels)
+    got, want = _run_both(small_scene, 0.03, (96, 100, 90), use_bricks=False)
+    _assert_frame(got, want)
