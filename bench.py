@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native volumetric-fusion path.
+
+Metric (BASELINE.json): 4-sensor TSDF Gvoxel-updates/s (+ fused frames/s) at 512^3.
+A "step" is one fused frame set: clearOccupiedBricks -> processTextures (5 passes) -> updateOccupiedBricks ->
+integrate, i.e. kinect_client.cpp:572-600 after NetKinectArray::update. `value` is measured with the frame set
+already resident in HBM; `e2e` runs the same step through the C ABI from pinned HOST buffers (H2D of the colour and
+depth frames inside the timed region, D2H of the occupied-brick count the reference reads back every frame).
+
+  python bench.py --gpus N --steps K --warmup W          # our arm (torchrun launches N ranks for N > 1)
+  python bench.py --impl reference ...                   # the reference's algorithm on the host cores (oracle port)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "rgbd-recon_b200"))
+
+R = 512                       # TSDF resolution (R^3)
+N_SENSORS = 4
+W, H, CW, CH = 512, 424, 1280, 1080
+CV_RES = (128, 128, 256)      # forward calibration volumes
+INV_RES = (128, 128, 256)     # inverse calibration volumes (4,194,304 voxels each)
+EXTENT = 2.048
+BBOX = ((-EXTENT / 2, 1.1 - EXTENT / 2, -EXTENT / 2), (EXTENT / 2, 1.1 + EXTENT / 2, EXTENT / 2))
+LIMIT, BRICK, MIN_VOX = 0.01, 0.1, 10
+N_FRAMES = 2                  # distinct synthetic frame sets cycled through the steps
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def make_inputs(res=R):
+    from rrpy import synth
+    voxel = EXTENT / res
+    scenes = [synth.make_scene(N=N_SENSORS, W=W, H=H, CW=CW, CH=CH, cv_res=CV_RES, bbox=BBOX, frame=0, seed=1234)]
+    scenes += [synth.rerender(scenes[0], 7 * t) for t in range(1, N_FRAMES)]
+    inv = synth.analytic_inverse(scenes[0], INV_RES)
+    return scenes, inv, np.float32(voxel)
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled while the timed region runs (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.lines = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes(res, n_occ_vox, covered_inv_vox, nbricks, bricks):
+    """bytes one integrate launch must move."""
+    P = W * H
+    if not bricks:
+        return 4 * res ** 3 + 16 * INV_RES[0] * INV_RES[1] * INV_RES[2] * N_SENSORS + 16 * P * N_SENSORS
+    return 4 * res ** 3 + 4 * n_occ_vox + 16 * covered_inv_vox * N_SENSORS + 16 * P * N_SENSORS + 4 * nbricks
+
+
+def run_ours(args):
+    import torch
+    from rrpy import capi
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    scenes, inv, voxel = make_inputs()
+    fu = capi.Fusion(N_SENSORS, W, H, CW, CH, device=local)
+    capi.load_scene(fu, scenes[0], inv)
+    bricks = args.mode == "bricks"
+    fu.configure(limit=LIMIT, voxel_size=voxel, brick_size=BRICK, min_voxels=MIN_VOX, use_bricks=bricks)
+    res = fu.volume_res()
+    assert tuple(int(v) for v in res) == (R, R, R), res
+    # z-slab of this rank: contiguous slices, remainder spread over the first ranks
+    base, rem = divmod(R, world)
+    z0 = rank * base + min(rank, rem)
+    z1 = z0 + base + (1 if rank < rem else 0)
+    fu.set_slab(z0, z1)
+
+    stream = torch.cuda.ExternalStream(fu.stream(), device=dev)
+    # frame sets: pinned host copies (e2e) and device copies (value)
+    h_color = [torch.from_numpy(s.color).pin_memory() for s in scenes]
+    h_depth = [torch.from_numpy(s.depth).pin_memory() for s in scenes]
+    d_color = [t.to(dev) for t in h_color]
+    d_depth = [t.to(dev) for t in h_depth]
+    cb, db = h_color[0].numel(), h_depth[0].numel() * 4
+    bcast_c = torch.empty_like(d_color[0]) if world > 1 else None
+    bcast_d = torch.empty_like(d_depth[0]) if world > 1 else None
+
+    def step_device(i):
+        k = i % N_FRAMES
+        if world > 1:
+            # each frame set arrives on rank 0 and is broadcast over NVLink (NCCL) before every GPU pre-processes it
+            if rank == 0:
+                bcast_c.copy_(d_color[k], non_blocking=True); bcast_d.copy_(d_depth[k], non_blocking=True)
+            dist.broadcast(bcast_c, 0); dist.broadcast(bcast_d, 0)
+            stream.wait_stream(torch.cuda.current_stream(dev))
+            fu.upload_frames_ptr(bcast_c.data_ptr(), cb, bcast_d.data_ptr(), db, device=True)
+        else:
+            fu.upload_frames_ptr(d_color[k].data_ptr(), cb, d_depth[k].data_ptr(), db, device=True)
+        fu.frame(sync_bricks=False)
+        if world > 1:
+            torch.cuda.current_stream(dev).wait_stream(stream)
+
+    def step_host(i):
+        k = i % N_FRAMES
+        if world > 1:
+            if rank == 0:
+                bcast_c.copy_(h_color[k], non_blocking=True); bcast_d.copy_(h_depth[k], non_blocking=True)
+            dist.broadcast(bcast_c, 0); dist.broadcast(bcast_d, 0)
+            stream.wait_stream(torch.cuda.current_stream(dev))
+            fu.upload_frames_ptr(bcast_c.data_ptr(), cb, bcast_d.data_ptr(), db, device=True)
+            fu.bricks_clear(); fu.preprocess(); n = fu.bricks_update(sync=True); fu.integrate()
+            torch.cuda.current_stream(dev).wait_stream(stream)
+        else:
+            fu.upload_frames_ptr(h_color[k].data_ptr(), cb, h_depth[k].data_ptr(), db, device=False)
+            fu.bricks_clear(); fu.preprocess(); n = fu.bricks_update(sync=True); fu.integrate()
+        return n
+
+    def barrier():
+        fu.synchronize()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+
+    def timed(step, steps, warmup, with_stage_timers):
+        for i in range(warmup):
+            step(i)
+        barrier()
+        fu.set_timing(1 if with_stage_timers else 0)
+        fu.stage_stats("2integrate"); fu.stage_stats("1preprocess")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(steps):
+            step(warmup + i)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        fu.set_timing(0)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    launches0 = fu.launch_count()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_total = timed(step_device, args.steps, args.warmup, True)
+    gpu_launches = fu.launch_count() - launches0 - 0
+    int_ms, int_n = fu.stage_stats("2integrate")
+    pre_ms, pre_n = fu.stage_stats("1preprocess")
+    ms_e2e = timed(step_host, args.steps, max(3, args.warmup), False)
+    # keep the GPU busy until nvidia-smi has a few samples under load (the timed region can be < 100 ms)
+    t_end = time.time() + 1.2
+    i = 0
+    while rank == 0 and sampler and time.time() < t_end:
+        step_device(i); i += 1
+        if i % 64 == 0:
+            fu.synchronize()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+
+    # occupancy statistics of the last frame for the algorithmic-bytes figure
+    n_occ, ratio = fu.bricks_update(sync=True)
+    counters, occ = fu.download_bricks()
+    ranges = fu.brick_ranges()
+    rr = ranges[occ]
+    n_occ_vox = int(((rr[:, 1] - rr[:, 0]) * (rr[:, 3] - rr[:, 2]) * (np.clip(rr[:, 5], z0, z1) - np.clip(rr[:, 4], z0, z1)).clip(0)).sum()) if len(occ) else 0
+    kernel_launches_per_step = (fu.launch_count() - launches0) and gpu_launches / (args.steps + args.warmup)
+
+    frames_s = args.steps / (ms_total / 1e3)
+    value = R ** 3 * frames_s / 1e9
+    e2e_frames_s = args.steps / (ms_e2e / 1e3)
+    peak, peak_src = peaks()
+    slab_frac = (z1 - z0) / R
+    if bricks:
+        covered_inv = int(INV_RES[0] * INV_RES[1] * INV_RES[2] * min(1.0, n_occ_vox / max(1, R ** 3 * slab_frac)) * slab_frac)
+        abytes = (4 * R ** 3 * slab_frac + 4 * n_occ_vox + 16 * covered_inv * N_SENSORS + 16 * W * H * N_SENSORS + 4 * len(counters))
+    else:
+        abytes = 4 * R ** 3 * slab_frac + 16 * INV_RES[0] * INV_RES[1] * INV_RES[2] * N_SENSORS * slab_frac + 16 * W * H * N_SENSORS
+    int_avg_ms = int_ms / max(1, int_n)
+    achieved = abytes / (int_avg_ms / 1e3) / 1e9 if int_avg_ms > 0 else 0.0
+
+    out = {
+        "metric": "4-sensor TSDF Gvoxel-updates/s at 512^3 (fused frames/s in frames_per_s)",
+        "value": round(value, 3), "unit": "Gvoxel-updates/s", "frames_per_s": round(frames_s, 2),
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 5),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"4 Kinect-v2 sensors 512x424 depth + 1280x1080 RGB8, {R}^3 R32F TSDF ({EXTENT} m cube), "
+                               f"inverse calibration volumes 128x128x256, step = clear bricks + 5 pre-process passes + brick update + integrate",
+                   "integration": "occupied bricks (reference default m_use_bricks=true)" if bricks else "dense (every voxel x every sensor)",
+                   "parallelism": f"z-slabs x{world}" if world > 1 else "single GPU",
+                   "l2": "inputs+outputs per step (268 MB inverse volumes, 537 MB TSDF) exceed the 126 MB L2; no explicit flush",
+                   "occupied_bricks": int(n_occ), "occupied_ratio": round(float(ratio), 4), "frames_cycled": N_FRAMES},
+        "e2e": {"value": round(R ** 3 * e2e_frames_s / 1e9, 3), "unit": "Gvoxel-updates/s", "frames_per_s": round(e2e_frames_s, 2),
+                "h2d_bytes_per_step": int(cb + db), "d2h_bytes_per_step": 4},
+        "gpu_launches": int(gpu_launches),
+        "stages_ms": {"1preprocess": round(pre_ms / max(1, pre_n), 5), "2integrate": round(int_avg_ms, 5)},
+        "roofline": {"bound": "hbm", "kernel": "2integrate stage (k_fill + k_integrate_bricks)" if bricks else "k_integrate_dense",
+                     "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                     "traffic": None, "algorithmic_bytes_per_launch": int(abytes), "peak_source": peak_src},
+        "clocks": clocks,
+    }
+    if rank == 0:
+        if args.cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(scenes[0], inv, voxel, bricks, budget_s=20.0)
+        print(json.dumps(out), flush=True)
+    fu.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_frame(scene, inv, voxel, bricks, threads, int_fraction=1.0):
+    """One fused frame with the oracle port on `threads` host threads. Returns (seconds_pre, seconds_int, n_occ)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py as O
+    O.set_threads(threads)
+    grid = O.brick_grid(scene.bbox_min, scene.bbox_max, voxel, BRICK)
+    cams = [O.frustum(scene.cv_xyz[i])[1] for i in range(scene.N)]
+    t0 = time.perf_counter()
+    pre = O.preprocess(scene, grid, cams)
+    occ = O.occupied_bricks(pre["bricks"], MIN_VOX)
+    t1 = time.perf_counter()
+    if bricks:
+        sub = occ[:: max(1, int(round(1.0 / int_fraction)))]
+        O.integrate(inv, pre, grid, LIMIT, True, sub)
+        scale = len(occ) / max(1, len(sub))
+    else:
+        raise NotImplementedError
+    t2 = time.perf_counter()
+    return t1 - t0, (t2 - t1) * scale, len(occ), len(sub)
+
+
+def cpu_baseline(scene, inv, voxel, bricks, budget_s):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py as O
+    cores = O.max_threads()
+    frac = 0.25
+    tp, ti, n_occ, n_sub = cpu_frame(scene, inv, voxel, True, cores, frac)
+    fps = 1.0 / (tp + ti)
+    return {"value": round(R ** 3 * fps / 1e9, 5), "unit": "Gvoxel-updates/s", "frames_per_s": round(fps, 4), "cores": cores, "kind": "port",
+            "sample": f"one 4-sensor frame set at {R}^3: all 5 pre-process passes on every pixel ({tp:.2f} s) + brick integration of "
+                      f"{n_sub} of {n_occ} occupied bricks scaled to all ({ti:.2f} s); oracle port (-O2, OpenMP), bricks mode"}
+
+
+def run_reference(args):
+    """The reference's own algorithm for this path on the host cores. The reference (GLSL, needs an OpenGL 4.4 context,
+    CGAL, ZeroMQ) cannot be built here, so this is the oracle port — the scalar C++ transcription of its shaders."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py as O
+    scenes, inv, voxel = make_inputs()
+    cores = O.max_threads()
+    frac = 1.0 / 8.0
+    times = []
+    n_occ = n_sub = 0
+    total = args.warmup + args.steps
+    for i in range(total):
+        tp, ti, n_occ, n_sub = cpu_frame(scenes[i % N_FRAMES], inv, voxel, True, cores, frac)
+        if i == 0 and (tp + ti / 1.0) * total > 150.0:
+            # bound the whole run to a few minutes: shrink the integrated brick sample for the remaining steps
+            frac = max(1.0 / 64.0, frac * 150.0 / ((tp + ti) * total))
+        if i >= args.warmup:
+            times.append(tp + ti)
+    t = float(np.mean(times))
+    fps = 1.0 / t
+    value = R ** 3 * fps / 1e9
+    out = {"impl": "reference", "metric": "4-sensor TSDF Gvoxel-updates/s at 512^3 (fused frames/s in frames_per_s)",
+           "value": round(value, 5), "unit": "Gvoxel-updates/s", "frames_per_s": round(fps, 4), "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": round(t * 1e3, 2), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"4 Kinect-v2 sensors 512x424 depth + 1280x1080 RGB8, {R}^3 R32F TSDF, same inputs as the GPU arm",
+                      "integration": "occupied bricks (reference default m_use_bricks=true)"},
+           "cpu_baseline": {"value": round(value, 5), "unit": "Gvoxel-updates/s", "cores": cores, "kind": "port",
+                            "sample": f"per step: full pre-processing of 4x512x424 pixels + integration of {n_sub} of {n_occ} occupied bricks, "
+                                      f"integration time scaled to all occupied bricks"},
+           "e2e": {"value": round(value, 5), "unit": "Gvoxel-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="bricks", choices=["bricks", "dense"])
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

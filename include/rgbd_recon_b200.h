@@ -136,11 +136,15 @@ int rr_download_bricks(rr_ctx* ctx, uint32_t* counters, uint32_t* occupied, uint
 int rr_download_num_samples(rr_ctx* ctx, float* out);
 
 /* ---- instrumentation ---------------------------------------------------------------------------------------- */
-/* TimerDatabase stage names (NetKinectArray.cpp:211-216, recon_integration.cpp:146-148): "morph", "bilateral",
- * "boundary", "normal", "quality", "1preprocess", "2integrate", "brickdraw", "draw". Enable with rr_set_timing;
- * rr_get_stage_ms synchronises and returns the last duration. */
-int rr_set_timing(rr_ctx* ctx, int enabled);
+/* TimerDatabase stage names (framework/rendering/timer_database.cpp:26-41; NetKinectArray.cpp:211-216,
+ * recon_integration.cpp:146-148, reconstruction.cpp:25-26): "morph", "bilateral", "boundary", "normal", "quality",
+ * "1preprocess", "2integrate", "3recon", "brickdraw", "draw" — CUDA events on the context's stream instead of GL
+ * timestamp queries. level 0 = off, 1 = the numbered top-level stages only, 2 = every pass.
+ * rr_get_stage_ms: last recorded duration. rr_get_stage_stats: sum and count of all intervals recorded since the
+ * previous call (TimerDatabase's running mean), then resets them. Both synchronise on the events they read. */
+int rr_set_timing(rr_ctx* ctx, int level);
 int rr_get_stage_ms(rr_ctx* ctx, const char* name, float* ms);
+int rr_get_stage_stats(rr_ctx* ctx, const char* name, float* total_ms, uint32_t* count);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 uint64_t rr_launch_count(const rr_ctx* ctx);
 /* Library/ABI version. */

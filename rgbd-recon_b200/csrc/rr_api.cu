@@ -18,19 +18,28 @@ int check(rr_ctx* c, cudaError_t e, const char* what) {
   return fail(c, RR_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
 
+static bool timer_is_top(const char* name) { return name[0] >= '0' && name[0] <= '9'; }   // "1preprocess", "2integrate", "3recon"
+
 void timer_begin(rr_ctx* c, const char* name) {
-  if (!c->timing) return;
+  if (c->timing == 0 || (c->timing == 1 && !timer_is_top(name))) return;
   StageTimer& t = c->timers[name];
-  if (!t.beg) { cudaEventCreate(&t.beg); cudaEventCreate(&t.end); }
-  cudaEventRecord(t.beg, c->stream);
+  if (t.used == t.beg.size()) {
+    cudaEvent_t b, e;
+    cudaEventCreate(&b); cudaEventCreate(&e);
+    t.beg.push_back(b); t.end.push_back(e);
+  }
+  cudaEventRecord(t.beg[t.used], c->stream);
+  t.open = true;
 }
 
 void timer_end(rr_ctx* c, const char* name) {
-  if (!c->timing) return;
-  StageTimer& t = c->timers[name];
-  if (!t.beg) return;
-  cudaEventRecord(t.end, c->stream);
-  t.valid = true;
+  if (c->timing == 0 || (c->timing == 1 && !timer_is_top(name))) return;
+  auto it = c->timers.find(name);
+  if (it == c->timers.end() || !it->second.open) return;
+  StageTimer& t = it->second;
+  cudaEventRecord(t.end[t.used], c->stream);
+  ++t.used;
+  t.open = false;
 }
 
 SensorTables sensor_tables(const rr_ctx* c) {
@@ -124,7 +133,10 @@ void rr_destroy(rr_ctx* c) {
   cudaFree(c->d_num_occ); cudaFree(c->d_near_occ); cudaFree(c->d_tsdf); cudaFree(c->d_weight);
   cudaFree(c->d_rgba); cudaFree(c->d_zbuf); cudaFree(c->d_nsamples);
   if (c->h_num_occ) cudaFreeHost(c->h_num_occ);
-  for (auto& kv : c->timers) { if (kv.second.beg) { cudaEventDestroy(kv.second.beg); cudaEventDestroy(kv.second.end); } }
+  for (auto& kv : c->timers) {
+    for (cudaEvent_t e : kv.second.beg) cudaEventDestroy(e);
+    for (cudaEvent_t e : kv.second.end) cudaEventDestroy(e);
+  }
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -458,19 +470,38 @@ int rr_download_num_samples(rr_ctx* c, float* out) {
   return download(c, out, c->d_nsamples, (size_t)c->view_w * c->view_h * sizeof(float), "samples download");
 }
 
-int rr_set_timing(rr_ctx* c, int enabled) {
+int rr_set_timing(rr_ctx* c, int level) {
   if (!c) return RR_ERR_INVALID;
-  c->timing = enabled != 0;
+  c->timing = level < 0 ? 0 : (level > 2 ? 2 : level);
   return RR_OK;
 }
 
 int rr_get_stage_ms(rr_ctx* c, const char* name, float* ms) {
   if (!c || !name || !ms) return RR_ERR_INVALID;
   auto it = c->timers.find(name);
-  RR_REQUIRE(c, it != c->timers.end() && it->second.valid, "rr_get_stage_ms: stage has not run with timing enabled");
+  RR_REQUIRE(c, it != c->timers.end() && it->second.used > 0, "rr_get_stage_ms: stage has not run with timing enabled");
   RR_SET_DEVICE(c);
-  RR_TRY(check(c, cudaEventSynchronize(it->second.end), "stage timer sync"));
-  return check(c, cudaEventElapsedTime(ms, it->second.beg, it->second.end), "stage timer");
+  const size_t i = it->second.used - 1;
+  RR_TRY(check(c, cudaEventSynchronize(it->second.end[i]), "stage timer sync"));
+  return check(c, cudaEventElapsedTime(ms, it->second.beg[i], it->second.end[i]), "stage timer");
+}
+
+int rr_get_stage_stats(rr_ctx* c, const char* name, float* total_ms, uint32_t* count) {
+  if (!c || !name || !total_ms || !count) return RR_ERR_INVALID;
+  *total_ms = 0.0f; *count = 0;
+  auto it = c->timers.find(name);
+  if (it == c->timers.end()) return RR_OK;
+  RR_SET_DEVICE(c);
+  StageTimer& t = it->second;
+  for (size_t i = 0; i < t.used; ++i) {
+    float ms = 0.0f;
+    RR_TRY(check(c, cudaEventSynchronize(t.end[i]), "stage timer sync"));
+    RR_TRY(check(c, cudaEventElapsedTime(&ms, t.beg[i], t.end[i]), "stage timer"));
+    *total_ms += ms;
+  }
+  *count = (uint32_t)t.used;
+  t.used = 0;
+  return RR_OK;
 }
 
 uint64_t rr_launch_count(const rr_ctx* c) { return c ? c->launches : 0; }

@@ -39,9 +39,10 @@ struct BrickGrid {
   uint32_t num;
 };
 
-struct StageTimer {
-  cudaEvent_t beg = nullptr, end = nullptr;
-  bool valid = false;
+struct StageTimer {            // one CUDA-event pair per recorded interval; summed and recycled by rr_get_stage_stats
+  std::vector<cudaEvent_t> beg, end;
+  size_t used = 0;             // intervals recorded since the last reset
+  bool open = false;
 };
 
 }  // namespace rr
@@ -52,7 +53,7 @@ struct rr_ctx {
   cudaStream_t stream = nullptr;
   std::string error;
   uint64_t launches = 0;
-  bool timing = false;
+  int timing = 0;              // 0 off, 1 top-level stages, 2 every pass
   std::map<std::string, rr::StageTimer> timers;
 
   // calibration

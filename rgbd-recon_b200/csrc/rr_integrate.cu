@@ -11,6 +11,8 @@
 #include "rr_context.h"
 #include "rr_math.cuh"
 
+#include <algorithm>
+
 namespace rr {
 
 struct IntegrateParams {
@@ -27,6 +29,7 @@ struct IntegrateParams {
   float limit;
 };
 
+// One (x, y) column, z in [zb, ze). All index arithmetic is 32-bit (sizes are validated on the host).
 template <int N, bool WEIGHT>
 __device__ __forceinline__ void march_column(const IntegrateParams& p, int x, int y, int zb, int ze) {
   const float stepX = 1.0f / (float)p.X, stepY = 1.0f / (float)p.Y, stepZ = 1.0f / (float)p.Z;
@@ -34,15 +37,17 @@ __device__ __forceinline__ void march_column(const IntegrateParams& p, int x, in
   int x0, x1, y0, y1; float a, b;
   lin_coord(px, p.IX, x0, x1, a);
   lin_coord(py, p.IY, y0, y1, b);
-  const int o00 = y0 * p.IX + x0, o10 = y0 * p.IX + x1, o01 = y1 * p.IX + x0, o11 = y1 * p.IX + x1;
-  const size_t plane_sz = (size_t)p.IX * p.IY;
-  const size_t gstride = (size_t)(p.W + 1) * (p.H + 1) * 2;
+  const unsigned o00 = y0 * p.IX + x0, o10 = y0 * p.IX + x1, o01 = y1 * p.IX + x0, o11 = y1 * p.IX + x1;
+  const unsigned plane_sz = (unsigned)(p.IX * p.IY);
+  const unsigned gstride = (unsigned)((p.W + 1) * (p.H + 1) * 2);
+  const unsigned grow = (unsigned)(p.W + 1);
   const float limit = p.limit;
+  const float fW = (float)p.W, fH = (float)p.H, exmax = (float)(p.W - 1), eymax = (float)(p.H - 1);
   float3 A[N], B[N];
   int ck0 = -1, ck1 = -1;
 
   auto plane = [&](int s, int k) -> float3 {
-    const float4* base = p.inv + ((size_t)s * p.IZ + k) * plane_sz;
+    const float4* base = p.inv + (unsigned)(s * p.IZ + k) * plane_sz;
     const float4 p00 = __ldg(base + o00), p10 = __ldg(base + o10), p01 = __ldg(base + o01), p11 = __ldg(base + o11);
     float3 r;
     r.x = lerpf(lerpf(p00.x, p10.x, a), lerpf(p01.x, p11.x, a), b);
@@ -51,7 +56,9 @@ __device__ __forceinline__ void march_column(const IntegrateParams& p, int x, in
     return r;
   };
 
-  for (int z = zb; z < ze; ++z) {
+  unsigned o = (unsigned)((zb * p.Y + y) * p.X + x);
+  const unsigned ostep = (unsigned)(p.X * p.Y);
+  for (int z = zb; z < ze; ++z, o += ostep) {
     const float pz = ((float)z + 0.5f) * stepZ;
     int k0, k1; float g;
     lin_coord(pz, p.IZ, k0, k1, g);
@@ -63,22 +70,32 @@ __device__ __forceinline__ void march_column(const IntegrateParams& p, int x, in
       if (needA) A[s] = a_from_b ? B[s] : plane(s, k0);
       if (needB) B[s] = b_from_a ? A[s] : plane(s, k1);
       const float u = lerpf(A[s].x, B[s].x, g), v = lerpf(A[s].y, B[s].y, g), d = lerpf(A[s].z, B[s].z, g);
-      // footprint of the bilinear (silhouette, quality) and nearest (depth) lookups at (u, v)
-      const float tu = u * (float)p.W, tv = v * (float)p.H;
-      const float uu = tu - 0.5f, vv = tv - 0.5f;
+      // Bilinear footprint (silhouette, quality) at (u, v): lower-left texel floor(u*W - 0.5), weights (wa, wb).
+      const float uu = u * fW - 0.5f, vv = v * fH - 0.5f;
       const float fu = floorf(uu), fv = floorf(vv);
       const float wa = uu - fu, wb = vv - fv;
-      const int ex = f2i_clamp(fu, -1, p.W - 1) + 1, ey = f2i_clamp(fv, -1, p.H - 1) + 1;
-      const bool selx = f2i_clamp(floorf(tu), 0, p.W - 1) != f2i_clamp(fu, 0, p.W - 1);
-      const bool sely = f2i_clamp(floorf(tv), 0, p.H - 1) != f2i_clamp(fv, 0, p.H - 1);
-      const float4* g4 = p.gather + (size_t)s * gstride + ((size_t)ey * (p.W + 1) + ex) * 2;
+      // gather-texel index = clamp(footprint, -1, W-1) + 1; fmaxf/fminf drop a NaN operand, so NaN -> entry 0
+      const int ex = (int)fminf(fmaxf(fu, -1.0f), exmax) + 1, ey = (int)fminf(fmaxf(fv, -1.0f), eymax) + 1;
+      const float4* g4 = p.gather + ((unsigned)s * gstride + ((unsigned)ey * grow + (unsigned)ex) * 2u);
       const float4 lo = __ldg(g4), hi = __ldg(g4 + 1);
-      const float s00 = (float)(__float_as_uint(hi.x) >> 31), s10 = (float)(__float_as_uint(hi.y) >> 31);
-      const float s01 = (float)(__float_as_uint(hi.z) >> 31), s11 = (float)(__float_as_uint(hi.w) >> 31);
-      const float silhouette = lerpf(lerpf(s00, s10, wa), lerpf(s01, s11, wa), wb);
-      if (silhouette < 1.0f) {
-        if (weighted_tsd >= limit) { weighted_tsd = -limit; continue; }
+      // silhouette < 1 ? The four taps are exactly 0 or 1 (sign bits of hi). lerp(1,1,t) == 1 and lerp(0,0,t) == 0
+      // exactly for every finite t, so uniform footprints need no arithmetic; NaN weights compare false either way.
+      const uint32_t bx = __float_as_uint(hi.x), by = __float_as_uint(hi.y), bz = __float_as_uint(hi.z), bw = __float_as_uint(hi.w);
+      const uint32_t all1 = (bx & by & bz & bw) >> 31, any1 = (bx | by | bz | bw) >> 31;
+      bool sil_lt1;
+      if (all1) {
+        sil_lt1 = false;
+      } else if (!any1) {
+        sil_lt1 = (wa == wa) && (wb == wb);
+      } else {
+        const float s00 = (int)bx < 0 ? 1.0f : 0.0f, s10 = (int)by < 0 ? 1.0f : 0.0f;
+        const float s01 = (int)bz < 0 ? 1.0f : 0.0f, s11 = (int)bw < 0 ? 1.0f : 0.0f;
+        sil_lt1 = lerpf(lerpf(s00, s10, wa), lerpf(s01, s11, wa), wb) < 1.0f;
       }
+      if (sil_lt1 && weighted_tsd >= limit) { weighted_tsd = -limit; continue; }
+      // NEAREST depth tap = upper tap of the footprint iff the bilinear weight is >= 0.5 (floor(t) == floor(t-0.5)+1);
+      // where the subtraction t-0.5 can round (t < 0.5) both taps are the same clamped texel.
+      const bool selx = wa >= 0.5f, sely = wb >= 0.5f;
       const float depth = sely ? (selx ? lo.w : lo.z) : (selx ? lo.y : lo.x);
       const float sdist = d - depth;
       if (sdist <= -limit) {
@@ -92,7 +109,6 @@ __device__ __forceinline__ void march_column(const IntegrateParams& p, int x, in
       }
     }
     ck0 = k0; ck1 = k1;
-    const size_t o = ((size_t)z * p.Y + y) * p.X + x;
     p.tsdf[o] = weighted_tsd;
     if (WEIGHT) p.weight[o] = total_weight;
   }
@@ -107,17 +123,32 @@ __global__ void __launch_bounds__(256) k_integrate_dense(const __grid_constant__
   march_column<N, WEIGHT>(p, x, y, zb, ze);
 }
 
-// One block per occupied brick (VolumeSampler::sample(indices), volume_sampler.cpp:74-76). Bricks may overlap or
-// leave gaps by one voxel (float rounding in divideBox/containedVoxels); overlapping voxels get the same value twice.
+// Occupied bricks only (VolumeSampler::sample(indices), volume_sampler.cpp:74-76). Persistent kernel: a fixed grid
+// (a multiple of the 148 SMs) strides over work items = (occupied brick, z-chunk, block of BRICK_COLS columns); the
+// item count comes from the device-side occupied count, so no host round trip and no empty blocks.
+// Bricks may overlap or leave one-voxel gaps (float rounding in divideBox/containedVoxels): overlapping voxels are
+// written twice with the same value, gaps keep the cleared -limit.
+#define BRICK_MAX_THREADS 320
+#define BRICK_ZCHUNK 9
 template <int N, bool WEIGHT>
-__global__ void __launch_bounds__(256) k_integrate_bricks(const __grid_constant__ IntegrateParams p) {
-  if (blockIdx.x >= *p.num_occupied) return;
-  const int32_t* r = p.ranges + (size_t)p.occupied[blockIdx.x] * 6;
-  const int x0 = r[0], x1 = r[1], y0 = r[2], y1 = r[3];
-  const int zb = max(r[4], p.z_begin), ze = min(r[5], p.z_end);
-  if (zb >= ze) return;
-  for (int y = y0 + threadIdx.y; y < y1; y += 8)
-    for (int x = x0 + threadIdx.x; x < x1; x += 32) march_column<N, WEIGHT>(p, x, y, zb, ze);
+__global__ void __launch_bounds__(BRICK_MAX_THREADS) k_integrate_bricks(const __grid_constant__ IntegrateParams p, int max_cols, int max_nz) {
+  const unsigned n_occ = *p.num_occupied;
+  const unsigned col_blocks = ((unsigned)max_cols + blockDim.x - 1u) / blockDim.x;
+  const unsigned z_blocks = (unsigned)(max_nz + BRICK_ZCHUNK - 1) / BRICK_ZCHUNK;
+  const unsigned per_brick = col_blocks * z_blocks;
+  const unsigned items = n_occ * per_brick;
+  for (unsigned w = blockIdx.x; w < items; w += gridDim.x) {
+    const unsigned b = w / per_brick, r = w - b * per_brick;
+    const unsigned zc = r / col_blocks, cc = r - zc * col_blocks;
+    const int32_t* rg = p.ranges + (size_t)p.occupied[b] * 6;
+    const int x0 = rg[0], nx = rg[1] - rg[0], y0 = rg[2], ny = rg[3] - rg[2];
+    const int zb = max(rg[4] + (int)zc * BRICK_ZCHUNK, p.z_begin);
+    const int ze = min(min(rg[4] + (int)(zc + 1) * BRICK_ZCHUNK, rg[5]), p.z_end);
+    const int ci = (int)(cc * blockDim.x + threadIdx.x);
+    if (zb >= ze || ci >= nx * ny) continue;
+    const int cy = ci / nx, cx = ci - cy * nx;
+    march_column<N, WEIGHT>(p, x0 + cx, y0 + cy, zb, ze);
+  }
 }
 
 // glClearTexImage(-limit) (recon_integration.cpp:250-251): 16-byte streaming stores over the slab.
@@ -135,9 +166,22 @@ template <int N>
 static int launch_n(rr_ctx* c, const IntegrateParams& p, bool bricks, bool weight) {
   const dim3 blk(32, 8, 1);
   if (bricks) {
-    const dim3 grd(c->bricks.num, 1, 1);
-    if (weight) k_integrate_bricks<N, true><<<grd, blk, 0, c->stream>>>(p);
-    else k_integrate_bricks<N, false><<<grd, blk, 0, c->stream>>>(p);
+    int max_cols = 0, max_nz = 0;
+    for (size_t i = 0; i + 5 < c->h_ranges.size(); i += 6) {
+      max_cols = std::max(max_cols, (c->h_ranges[i + 1] - c->h_ranges[i]) * (c->h_ranges[i + 3] - c->h_ranges[i + 2]));
+      max_nz = std::max(max_nz, c->h_ranges[i + 5] - c->h_ranges[i + 4]);
+    }
+    if (max_cols == 0 || max_nz == 0) return RR_OK;
+    // block size: the multiple of 32 (128..320) that wastes the fewest lanes on a brick's column count
+    int threads = 256;
+    double best = 1e9;
+    for (int t = 128; t <= BRICK_MAX_THREADS; t += 32) {
+      const double waste = double((max_cols + t - 1) / t * t) / double(max_cols);
+      if (waste < best - 1e-9 || (waste < best + 1e-9 && t > threads)) { best = waste; threads = t; }
+    }
+    const dim3 grd(148 * 6, 1, 1);
+    if (weight) k_integrate_bricks<N, true><<<grd, threads, 0, c->stream>>>(p, max_cols, max_nz);
+    else k_integrate_bricks<N, false><<<grd, threads, 0, c->stream>>>(p, max_cols, max_nz);
   } else {
     const int nz = p.z_end - p.z_begin;
     const dim3 grd((p.X + 31) / 32, (p.Y + 7) / 8, (nz + p.z_chunk - 1) / p.z_chunk);

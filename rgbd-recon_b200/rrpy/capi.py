@@ -74,6 +74,7 @@ def lib():
     L.rr_download_num_samples.argtypes = [vp, f32]
     L.rr_set_timing.argtypes = [vp, C.c_int]
     L.rr_get_stage_ms.argtypes = [vp, C.c_char_p, f32]
+    L.rr_get_stage_stats.argtypes = [vp, C.c_char_p, f32, u32]
     L.rr_launch_count.argtypes = [vp]
     L.rr_launch_count.restype = C.c_uint64
     L.rr_version.restype = C.c_int
@@ -272,8 +273,14 @@ class Fusion:
         self._ck(self.L.rr_download_num_samples(self.h, _f32(out)))
         return out
 
-    def set_timing(self, on=True):
-        self._ck(self.L.rr_set_timing(self.h, int(on)))
+    def set_timing(self, level=1):
+        self._ck(self.L.rr_set_timing(self.h, int(level)))
+
+    def stage_stats(self, name):
+        ms = C.c_float()
+        n = C.c_uint32()
+        self._ck(self.L.rr_get_stage_stats(self.h, name.encode(), C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
 
     def stage_ms(self, name):
         ms = C.c_float()

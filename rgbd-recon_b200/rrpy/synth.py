@@ -187,6 +187,12 @@ def make_scene(N=4, W=512, H=424, CW=1280, CH=1080, cv_res=(128, 128, 256), bbox
     return Scene(N, W, H, CW, CH, bmin, bmax, sensors, tuple(cv_res), cv_xyz, cv_uv, depth, color)
 
 
+def rerender(scene: Scene, frame, seed=1234, sdf=scene_sdf) -> Scene:
+    """Same rig and calibration, new depth maps for scene frame `frame` (colour unchanged)."""
+    depth = np.stack([render_depth(s, sdf, frame, seed + i) for i, s in enumerate(scene.sensors)])
+    return dataclasses.replace(scene, depth=depth)
+
+
 def analytic_inverse(scene: Scene, res) -> np.ndarray:
     """Closed-form stand-in for calib_inverter output: [N][Z][Y][X][4] float32, (u, v, d, 1) in normalised texture
     coordinates of the forward volume for voxel centres inside the sensor frustum, all -1 outside (the convention of
