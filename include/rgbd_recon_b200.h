@@ -134,6 +134,9 @@ int rr_download_stage(rr_ctx* ctx, int stage, float* out);
 int rr_download_bricks(rr_ctx* ctx, uint32_t* counters, uint32_t* occupied, uint32_t* num_occupied);
 /* Last raymarch: sample-count image float32 [h][w] (tex_num_samples, tsdf_raymarch.fs:403-406). */
 int rr_download_num_samples(rr_ctx* ctx, float* out);
+/* Last raymarch: surface point per pixel in volume (texture) space, float32 [h][w][4] = x, y, z, hit flag
+ * (the refined sample_pos of tsdf_raymarch.fs:100; world = bbox_min + xyz * bbox_size). For tests. */
+int rr_download_hit_positions(rr_ctx* ctx, float* out);
 
 /* ---- instrumentation ---------------------------------------------------------------------------------------- */
 /* TimerDatabase stage names (framework/rendering/timer_database.cpp:26-41; NetKinectArray.cpp:211-216,

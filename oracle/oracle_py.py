@@ -62,6 +62,10 @@ def lib():
     L.ro_frustum_inside.argtypes = [f32p, f32p]
     L.ro_frustum_inside.restype = C.c_int
     L.ro_calib_invert.argtypes = [f32p, C.c_int, C.c_int, C.c_int, f32p, f32p, u32p, f32p, C.c_void_p, C.c_int]
+    L.ro_raymarch_uniforms.argtypes = [f32p, f32p, f32p, f32p, C.c_int, C.c_int, f32p]
+    L.ro_raymarch.argtypes = [f32p, u32p, C.c_float, C.c_int, f32p, i32p, f32p, i32p, u8p, C.c_int, C.c_int, f32p, f32p, C.c_int, C.c_int,
+                              f32p, f32p, f32p, f32p, C.c_int, C.c_int, C.c_int, C.c_int, u32p, C.c_uint32, u32p, C.c_float,
+                              f32p, f32p, f32p, f32p]
     _LIB = L
     return L
 
@@ -156,3 +160,28 @@ def integrate(inv, pre, grid, limit, use_bricks, occupied, want_weight=False):
                        W, H, np.float32(limit), res, int(use_bricks), grid["ranges"], occ, len(occupied), tsdf,
                        weight.ctypes.data if weight is not None else None)
     return (tsdf, weight) if want_weight else tsdf
+
+
+def raymarch(tsdf, limit, inv, scene, pre, grid, occupied, modelview, projection, width, height, shade_mode=0, skip_space=True):
+    """ReconIntegration::draw (+ drawDepthLimits). Returns dict(rgba[h,w,4], depth[h,w], samples[h,w], pos[h,w,3])."""
+    N, IZ, IY, IX, _ = inv.shape
+    X, Y, Z = scene.cv_res
+    _, H, W = pre["quality"].shape
+    res = np.array([tsdf.shape[2], tsdf.shape[1], tsdf.shape[0]], np.uint32)
+    out = dict(rgba=np.zeros((height, width, 4), np.float32), depth=np.zeros((height, width), np.float32),
+               samples=np.zeros((height, width), np.float32), pos=np.zeros((height, width, 3), np.float32))
+    occ = np.ascontiguousarray(occupied, np.uint32) if len(occupied) else np.zeros(1, np.uint32)
+    lib().ro_raymarch(np.ascontiguousarray(tsdf), res, np.float32(limit), N, np.ascontiguousarray(inv), np.array([IX, IY, IZ], np.int32),
+                      np.ascontiguousarray(scene.cv_uv), np.array([X, Y, Z], np.int32), np.ascontiguousarray(scene.color), scene.CW, scene.CH,
+                      pre["depth_b"], pre["quality"], W, H, np.ascontiguousarray(scene.bbox_min, np.float32),
+                      np.ascontiguousarray(scene.bbox_max, np.float32), np.ascontiguousarray(modelview, np.float32).reshape(16),
+                      np.ascontiguousarray(projection, np.float32).reshape(16), int(width), int(height), int(shade_mode), int(skip_space),
+                      occ, len(occupied), grid["res_bricks"], grid["brick_size"], out["rgba"], out["depth"], out["samples"], out["pos"])
+    return out
+
+
+def raymarch_uniforms(modelview, projection, bbox_min, bbox_max, width, height):
+    out = np.zeros(83, np.float32)
+    lib().ro_raymarch_uniforms(np.ascontiguousarray(modelview, np.float32).reshape(16), np.ascontiguousarray(projection, np.float32).reshape(16),
+                               np.ascontiguousarray(bbox_min, np.float32), np.ascontiguousarray(bbox_max, np.float32), int(width), int(height), out)
+    return out

@@ -47,6 +47,14 @@ int ro_frustum_inside(const float* planes, const float* p);
 void ro_calib_invert(const float* cv_xyz, int X, int Y, int Z, const float* bbox_min, const float* bbox_max,
                      const uint32_t* out_res, float* out, uint32_t* neigh_out, int brute);
 
+void ro_raymarch_uniforms(const float* mv, const float* proj, const float* bmin, const float* bmax, int vw, int vh, float* out);
+void ro_raymarch(const float* tsdf, const uint32_t* res, float limit, int N, const float* inv, const int32_t* inv_res,
+                 const float* cv_uv, const int32_t* cv_res, const uint8_t* color, int CW, int CH,
+                 const float* depth_b, const float* quality, int W, int H, const float* bbox_min, const float* bbox_max,
+                 const float* modelview, const float* projection, int vw, int vh, int shade_mode, int skip_space,
+                 const uint32_t* occupied, uint32_t n_occ, const uint32_t* brick_res, float brick_size,
+                 float* out_rgba, float* out_depth, float* out_samples, float* out_pos);
+
 #ifdef __cplusplus
 }
 #endif

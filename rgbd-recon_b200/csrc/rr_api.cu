@@ -130,7 +130,7 @@ void rr_destroy(rr_ctx* c) {
   cudaFree(c->d_inv); cudaFree(c->d_depth_raw); cudaFree(c->d_color); cudaFree(c->d_morph); cudaFree(c->d_depth);
   cudaFree(c->d_lab); cudaFree(c->d_depth_b); cudaFree(c->d_sil); cudaFree(c->d_normal); cudaFree(c->d_quality);
   cudaFree(c->d_gather); cudaFree(c->d_flags); cudaFree(c->d_ranges); cudaFree(c->d_counters); cudaFree(c->d_occupied);
-  cudaFree(c->d_num_occ); cudaFree(c->d_near_occ); cudaFree(c->d_tsdf); cudaFree(c->d_weight);
+  cudaFree(c->d_num_occ); cudaFree(c->d_near_occ); cudaFree(c->d_occ_mask); cudaFree(c->d_pos); cudaFree(c->d_step); cudaFree(c->d_tsdf); cudaFree(c->d_weight);
   cudaFree(c->d_rgba); cudaFree(c->d_zbuf); cudaFree(c->d_nsamples);
   if (c->h_num_occ) cudaFreeHost(c->h_num_occ);
   for (auto& kv : c->timers) {
@@ -252,9 +252,11 @@ int rr_configure(rr_ctx* c, const rr_config* cfg) {
     RR_TRY(dev_alloc(c, &c->d_counters, nb, "brick counters"));
     RR_TRY(dev_alloc(c, &c->d_occupied, nb, "occupied list"));
     RR_TRY(dev_alloc(c, &c->d_near_occ, nb, "near-occupied mask"));
+    RR_TRY(dev_alloc(c, &c->d_occ_mask, nb, "occupied mask"));
     cudaMemcpyAsync(c->d_ranges, c->h_ranges.data(), (size_t)nb * 6 * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream);
     cudaMemsetAsync(c->d_counters, 0, nb * sizeof(uint32_t), c->stream);
     cudaMemsetAsync(c->d_near_occ, 0, nb, c->stream);
+    cudaMemsetAsync(c->d_occ_mask, 0, nb, c->stream);
     cudaMemsetAsync(c->d_num_occ, 0, sizeof(uint32_t), c->stream);
     *c->h_num_occ = 0;
     RR_TRY(check(c, cudaStreamSynchronize(c->stream), "brick table upload"));
@@ -367,6 +369,8 @@ int rr_raymarch(rr_ctx* c, const rr_view* view, float* out_rgba, float* out_dept
     RR_TRY(dev_alloc(c, &c->d_rgba, (size_t)w * h, "view rgba"));
     RR_TRY(dev_alloc(c, &c->d_zbuf, (size_t)w * h, "view depth"));
     RR_TRY(dev_alloc(c, &c->d_nsamples, (size_t)w * h, "view samples"));
+    RR_TRY(dev_alloc(c, &c->d_pos, (size_t)w * h, "view positions"));
+    RR_TRY(dev_alloc(c, &c->d_step, (size_t)w * h, "view steps"));
     c->view_w = w; c->view_h = h;
   }
   RR_TRY(launch_raymarch(c, view));
@@ -468,6 +472,12 @@ int rr_download_num_samples(rr_ctx* c, float* out) {
   if (!c) return RR_ERR_INVALID;
   RR_REQUIRE(c, out && c->d_nsamples, "rr_download_num_samples: no raymarch yet");
   return download(c, out, c->d_nsamples, (size_t)c->view_w * c->view_h * sizeof(float), "samples download");
+}
+
+int rr_download_hit_positions(rr_ctx* c, float* out) {
+  if (!c) return RR_ERR_INVALID;
+  RR_REQUIRE(c, out && c->d_pos, "rr_download_hit_positions: no raymarch yet");
+  return download(c, out, c->d_pos, (size_t)c->view_w * c->view_h * sizeof(float4), "positions download");
 }
 
 int rr_set_timing(rr_ctx* c, int level) {

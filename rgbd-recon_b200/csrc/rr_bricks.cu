@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(1024) k_bricks_compact(const uint32_t* __restr
 // near_occ[b] = 1 if brick b or any of its 26 neighbours is occupied: the raymarcher may skip the TSDF fetches of
 // samples inside bricks with near_occ == 0 (every trilinear tap there still holds the cleared value -limit).
 __global__ void __launch_bounds__(256) k_bricks_near(const uint32_t* __restrict__ counters, uint32_t rx, uint32_t ry, uint32_t rz,
-                                                     uint32_t min_voxels, uint8_t* __restrict__ near_occ) {
+                                                     uint32_t min_voxels, uint8_t* __restrict__ near_occ, uint8_t* __restrict__ occ_mask) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rx * ry * rz) return;
   const int bx = (int)(i % rx), by = (int)((i / rx) % ry), bz = (int)(i / (rx * ry));
@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(256) k_bricks_near(const uint32_t* __restrict_
         if (counters[((size_t)z * ry + y) * rx + x] >= min_voxels) any = 1;
       }
   near_occ[i] = any;
+  occ_mask[i] = counters[i] >= min_voxels ? 1 : 0;
 }
 
 int launch_bricks_clear(rr_ctx* c) {
@@ -64,7 +65,7 @@ int launch_bricks_update(rr_ctx* c) {
   const uint32_t nb = c->bricks.num;
   if (nb == c->bricks.res[0] * c->bricks.res[1] * c->bricks.res[2]) {
     k_bricks_near<<<(nb + 255) / 256, 256, 0, c->stream>>>(c->d_counters, c->bricks.res[0], c->bricks.res[1], c->bricks.res[2],
-                                                           c->cfg.min_voxels_per_brick, c->d_near_occ);
+                                                           c->cfg.min_voxels_per_brick, c->d_near_occ, c->d_occ_mask);
     RR_LAUNCH_CHECK(c, "k_bricks_near");
   }
   cudaError_t e = cudaMemcpyAsync(c->h_num_occ, c->d_num_occ, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);

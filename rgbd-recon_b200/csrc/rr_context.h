@@ -95,6 +95,7 @@ struct rr_ctx {
   uint32_t* d_occupied = nullptr;
   uint32_t* d_num_occ = nullptr;
   uint8_t* d_near_occ = nullptr;
+  uint8_t* d_occ_mask = nullptr;
   uint32_t* h_num_occ = nullptr;   // pinned
   float* d_tsdf = nullptr;
   float* d_weight = nullptr;
@@ -104,6 +105,8 @@ struct rr_ctx {
   float4* d_rgba = nullptr;
   float* d_zbuf = nullptr;
   float* d_nsamples = nullptr;
+  float4* d_pos = nullptr;         // hit position in volume space (w = 1 on a hit)
+  uint32_t* d_step = nullptr;      // step index of the hit, 0xFFFFFFFF = none (multi-GPU compositing key)
 };
 
 namespace rr {

@@ -12,6 +12,7 @@
 #include "rr_math.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace rr {
 
@@ -129,9 +130,8 @@ __global__ void __launch_bounds__(256) k_integrate_dense(const __grid_constant__
 // Bricks may overlap or leave one-voxel gaps (float rounding in divideBox/containedVoxels): overlapping voxels are
 // written twice with the same value, gaps keep the cleared -limit.
 #define BRICK_MAX_THREADS 320
-#define BRICK_ZCHUNK 9
-template <int N, bool WEIGHT>
-__global__ void __launch_bounds__(BRICK_MAX_THREADS) k_integrate_bricks(const __grid_constant__ IntegrateParams p, int max_cols, int max_nz) {
+template <int N, bool WEIGHT, int MINB>
+__global__ void __launch_bounds__(BRICK_MAX_THREADS, MINB) k_integrate_bricks(const __grid_constant__ IntegrateParams p, int max_cols, int max_nz, int BRICK_ZCHUNK) {
   const unsigned n_occ = *p.num_occupied;
   const unsigned col_blocks = ((unsigned)max_cols + blockDim.x - 1u) / blockDim.x;
   const unsigned z_blocks = (unsigned)(max_nz + BRICK_ZCHUNK - 1) / BRICK_ZCHUNK;
@@ -179,9 +179,15 @@ static int launch_n(rr_ctx* c, const IntegrateParams& p, bool bricks, bool weigh
       const double waste = double((max_cols + t - 1) / t * t) / double(max_cols);
       if (waste < best - 1e-9 || (waste < best + 1e-9 && t > threads)) { best = waste; threads = t; }
     }
-    const dim3 grd(148 * 6, 1, 1);
-    if (weight) k_integrate_bricks<N, true><<<grd, threads, 0, c->stream>>>(p, max_cols, max_nz);
-    else k_integrate_bricks<N, false><<<grd, threads, 0, c->stream>>>(p, max_cols, max_nz);
+    static const int zchunk = getenv("RR_BRICK_ZCHUNK") ? atoi(getenv("RR_BRICK_ZCHUNK")) : 9;
+    static const int gmult = getenv("RR_BRICK_GRID") ? atoi(getenv("RR_BRICK_GRID")) : 6;
+    static const int minb = getenv("RR_BRICK_MINB") ? atoi(getenv("RR_BRICK_MINB")) : 2;
+    if (getenv("RR_BRICK_THREADS")) threads = atoi(getenv("RR_BRICK_THREADS"));
+    const dim3 grd(148 * gmult, 1, 1);
+    if (weight) k_integrate_bricks<N, true, 2><<<grd, threads, 0, c->stream>>>(p, max_cols, max_nz, zchunk);
+    else if (minb == 3) k_integrate_bricks<N, false, 3><<<grd, threads, 0, c->stream>>>(p, max_cols, max_nz, zchunk);
+    else if (minb == 4) k_integrate_bricks<N, false, 4><<<grd, threads, 0, c->stream>>>(p, max_cols, max_nz, zchunk);
+    else k_integrate_bricks<N, false, 2><<<grd, threads, 0, c->stream>>>(p, max_cols, max_nz, zchunk);
   } else {
     const int nz = p.z_end - p.z_begin;
     const dim3 grd((p.X + 31) / 32, (p.Y + 7) / 8, (nz + p.z_chunk - 1) / p.z_chunk);

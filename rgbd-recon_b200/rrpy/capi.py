@@ -72,6 +72,7 @@ def lib():
     L.rr_download_stage.argtypes = [vp, C.c_int, f32]
     L.rr_download_bricks.argtypes = [vp, u32, u32, u32]
     L.rr_download_num_samples.argtypes = [vp, f32]
+    L.rr_download_hit_positions.argtypes = [vp, f32]
     L.rr_set_timing.argtypes = [vp, C.c_int]
     L.rr_get_stage_ms.argtypes = [vp, C.c_char_p, f32]
     L.rr_get_stage_stats.argtypes = [vp, C.c_char_p, f32, u32]
@@ -271,6 +272,11 @@ class Fusion:
     def download_num_samples(self, width, height):
         out = np.zeros((height, width), np.float32)
         self._ck(self.L.rr_download_num_samples(self.h, _f32(out)))
+        return out
+
+    def download_hit_positions(self, width, height):
+        out = np.zeros((height, width, 4), np.float32)
+        self._ck(self.L.rr_download_hit_positions(self.h, _f32(out)))
         return out
 
     def set_timing(self, level=1):

@@ -217,3 +217,25 @@ def analytic_inverse(scene: Scene, res) -> np.ndarray:
         o[~ok] = -1.0
         out[i] = o.astype(np.float32)
     return out
+
+
+def look_at(eye, target, up=(0.0, 1.0, 0.0)) -> np.ndarray:
+    """Column-major float32[16] modelview, as glGetFloatv(GL_MODELVIEW_MATRIX) would return it (gluLookAt)."""
+    eye, target, up = (np.asarray(v, np.float64) for v in (eye, target, up))
+    f = _normalize(target - eye)
+    s = _normalize(np.cross(f, up))
+    u = np.cross(s, f)
+    m = np.eye(4)
+    m[0, :3], m[1, :3], m[2, :3] = s, u, -f
+    m[:3, 3] = -m[:3, :3] @ eye
+    return np.ascontiguousarray(m.T, np.float32).reshape(16)
+
+
+def perspective(fovy_deg, aspect, near, far) -> np.ndarray:
+    """Column-major float32[16] projection (gluPerspective)."""
+    f = 1.0 / math.tan(math.radians(fovy_deg) / 2.0)
+    m = np.zeros((4, 4))
+    m[0, 0], m[1, 1] = f / aspect, f
+    m[2, 2], m[2, 3] = (far + near) / (near - far), 2.0 * far * near / (near - far)
+    m[3, 2] = -1.0
+    return np.ascontiguousarray(m.T, np.float32).reshape(16)
