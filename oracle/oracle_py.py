@@ -54,6 +54,8 @@ def lib():
     L.ro_adjust_brick_size.restype = C.c_float
     L.ro_divide_box.argtypes = [f32p, f32p, C.c_float, u32p, u32p, C.c_void_p]
     L.ro_divide_box.restype = C.c_uint32
+    L.ro_divide_box_args.argtypes = [f32p, f32p, C.c_float, u32p, C.c_void_p, C.c_void_p]
+    L.ro_divide_box_args.restype = C.c_uint32
     L.ro_occupied_bricks.argtypes = [u32p, C.c_uint32, C.c_uint32, u32p]
     L.ro_occupied_bricks.restype = C.c_uint32
     L.ro_integrate.argtypes = [C.c_int, f32p, i32p, f32p, f32p, f32p, C.c_int, C.c_int, C.c_float, u32p, C.c_int,
@@ -93,6 +95,19 @@ def brick_grid(bbox_min, bbox_max, voxel_size, brick_size_req):
     ranges = np.zeros((nb, 6), np.int32)
     L.ro_divide_box(bmin, bmax, bs, res, rb, ranges.ctypes.data)
     return dict(res=res, brick_size=np.float32(bs), res_bricks=rb, ranges=ranges, num_bricks=int(nb))
+
+
+def divide_box_args(bbox_min, bbox_max, brick_size, res, want_raw=False):
+    """(pos_n, size_n) per brick as divideBox hands them to containedVoxels; optionally the unclamped loop bounds."""
+    L = lib()
+    bmin = np.ascontiguousarray(bbox_min, np.float32)
+    bmax = np.ascontiguousarray(bbox_max, np.float32)
+    res = np.ascontiguousarray(res, np.uint32)
+    n = L.ro_divide_box_args(bmin, bmax, np.float32(brick_size), res, None, None)
+    args = np.zeros((n, 6), np.float32)
+    raw = np.zeros((n, 6), np.int32)
+    L.ro_divide_box_args(bmin, bmax, np.float32(brick_size), res, args.ctypes.data, raw.ctypes.data)
+    return (args, raw) if want_raw else args
 
 
 def frustum(cv_xyz_one):

@@ -74,6 +74,46 @@ uint32_t ro_divide_box(const float* bbox_min, const float* bbox_max, float brick
   return count;
 }
 
+// The (pos, size) arguments divideBox passes to VolumeSampler::containedVoxels for every brick, in brick order
+// (recon_integration.cpp:371-373): args float[num_bricks][6] = pos_n.xyz, size_n.xyz. Also returns the UNCLAMPED
+// per-axis ranges (the raw loop bounds of volume_sampler.cpp:53-55) in raw_ranges int32[num_bricks][6] (nullable).
+uint32_t ro_divide_box_args(const float* bbox_min, const float* bbox_max, float brick_size, const uint32_t* res_volume,
+                            float* args, int32_t* raw_ranges) {
+  const V3 mn{bbox_min[0], bbox_min[1], bbox_min[2]};
+  const V3 size{bbox_max[0] - mn.x, bbox_max[1] - mn.y, bbox_max[2] - mn.z};
+  const V3 step{1.0f / (float)res_volume[0], 1.0f / (float)res_volume[1], 1.0f / (float)res_volume[2]};
+  V3 start = mn;
+  uint32_t count = 0;
+  auto raw = [](float pos, float sz, float st, int32_t& lo, int32_t& hi) {
+    uint32_t a = (uint32_t)(pos / st), b = a;
+    const float lim = (pos + sz) / st;
+    while ((float)b < lim) ++b;
+    lo = (int32_t)a; hi = (int32_t)b;
+  };
+  while (size.z - start.z + mn.z > 0.0f) {
+    while (size.y - start.y + mn.y > 0.0f) {
+      while (size.x - start.x + mn.x > 0.0f) {
+        V3 rem{size.x - start.x + mn.x, size.y - start.y + mn.y, size.z - start.z + mn.z};
+        V3 bs{gl_min(brick_size, rem.x), gl_min(brick_size, rem.y), gl_min(brick_size, rem.z)};
+        V3 pn = (start - mn) / size;
+        V3 sn = bs / size;
+        if (args) { float* a = args + (size_t)count * 6; a[0] = pn.x; a[1] = pn.y; a[2] = pn.z; a[3] = sn.x; a[4] = sn.y; a[5] = sn.z; }
+        if (raw_ranges) {
+          int32_t* r = raw_ranges + (size_t)count * 6;
+          raw(pn.x, sn.x, step.x, r[0], r[1]); raw(pn.y, sn.y, step.y, r[2], r[3]); raw(pn.z, sn.z, step.z, r[4], r[5]);
+        }
+        ++count;
+        start.x += brick_size;
+      }
+      start.x = mn.x;
+      start.y += brick_size;
+    }
+    start.y = mn.y;
+    start.z += brick_size;
+  }
+  return count;
+}
+
 // updateOccupiedBricks (recon_integration.cpp:436-441): ascending ids with counter >= min_voxels.
 uint32_t ro_occupied_bricks(const uint32_t* counters, uint32_t num_bricks, uint32_t min_voxels, uint32_t* occupied_out) {
   uint32_t n = 0;

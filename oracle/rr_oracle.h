@@ -37,6 +37,8 @@ void ro_volume_res(const float* bbox_min, const float* bbox_max, float voxel_siz
 float ro_adjust_brick_size(float voxel_size, float size);
 uint32_t ro_divide_box(const float* bbox_min, const float* bbox_max, float brick_size, const uint32_t* res_volume,
                        uint32_t* res_bricks_out, int32_t* ranges);
+uint32_t ro_divide_box_args(const float* bbox_min, const float* bbox_max, float brick_size, const uint32_t* res_volume,
+                            float* args, int32_t* raw_ranges);
 uint32_t ro_occupied_bricks(const uint32_t* counters, uint32_t num_bricks, uint32_t min_voxels, uint32_t* occupied_out);
 void ro_integrate(int N, const float* inv, const int32_t* inv_res, const float* sil, const float* depth_b,
                   const float* quality, int W, int H, float limit, const uint32_t* res, int use_bricks,

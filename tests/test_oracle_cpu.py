@@ -1,0 +1,323 @@
+"""CPU tests (no GPU): the oracle (scalar restatement) against
+  * golden vectors produced by REAL reference code (tests/golden/ref_*.npz, made by tools/make_golden.py from oracle/_ref),
+  * the live oracle/_ref library when it is present (build container only),
+  * known answers of the arithmetic pins (GL filtering equations, deterministic pow),
+  * self-regression pins of the shader restatement, whose GLSL originals cannot run here (parity unpinned by the
+    reference: it ships no tests).
+"""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from conftest import bits_equal
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def gold(name):
+    return np.load(os.path.join(GOLD, name))
+
+
+@pytest.fixture(scope="module")
+def O():
+    import oracle_py
+    return oracle_py
+
+
+# ------------------------------------------------------------------------------------------------ reference goldens
+
+def test_frustum_matches_reference_golden(O):
+    g = gold("ref_calib_invert.npz")
+    planes, cam = O.frustum(g["cv_xyz"])
+    assert bits_equal(planes, g["planes"]).all()
+    assert bits_equal(cam, g["cam"]).all()
+    L = O.lib()
+    inside = np.array([L.ro_frustum_inside(np.ascontiguousarray(planes), np.ascontiguousarray(p)) for p in g["points"]], np.int32)
+    assert np.array_equal(inside, g["inside"])
+    assert 0.02 < inside.mean() < 0.9, "the sample should straddle the frustum"
+
+
+@pytest.mark.parametrize("brute", [False, True])
+def test_calib_invert_matches_reference_golden(O, brute):
+    g = gold("ref_calib_invert.npz")
+    inv = O.calib_invert(g["cv_xyz"], g["bbox_min"], g["bbox_max"], g["out_res"], brute=brute)
+    assert inv.shape == g["inv"].shape
+    valid = g["inv"][..., 3] > 0
+    assert 0.3 < valid.mean() < 1.0
+    assert (g["inv"][~valid] == -1.0).all()
+    assert bits_equal(inv, g["inv"]).all(), f"{(~bits_equal(inv, g['inv'])).sum()} values differ from calibration_inverter.cpp"
+
+
+def test_calib_invert_roundtrip_property(O):
+    """cv_xyz(cv_xyz_inv(p)) ~ p: what the reference checks visually (calib_vis.vs:26-37)."""
+    g = gold("ref_calib_invert.npz")
+    xyz, inv = g["cv_xyz"], g["inv"]
+    Z, Y, X, _ = xyz.shape
+    oz, oy, ox, _ = inv.shape
+    bmin, bmax = g["bbox_min"], g["bbox_max"]
+    L = O.lib()
+    errs = []
+    out = np.zeros(4, np.float32)
+    for (z, y, x) in np.argwhere(inv[..., 3] > 0)[::37]:
+        uvd = inv[z, y, x, :3]
+        if (uvd < 1.5 / np.array([X, Y, Z])).any() or (uvd > 1 - 1.5 / np.array([X, Y, Z])).any():
+            continue   # IDW of 8 neighbours is biased at the volume border
+        L.ro_kat_tex3d(np.ascontiguousarray(xyz), 3, X, Y, Z, uvd[0], uvd[1], uvd[2], out)
+        p = bmin + (np.array([x, y, z]) + 0.5) / np.array([ox, oy, oz]) * (bmax - bmin)
+        errs.append(np.linalg.norm(out[:3] - p))
+    assert len(errs) > 50
+    assert np.median(errs) < 0.05, "inverse lookup should land within a fraction of a calibration cell (cells are ~0.15 m here)"
+
+
+def test_volume_file_format_matches_reference_golden():
+    """CalibrationVolume<T> layout: uint32 res[3]; float limits[2]; T data[] (calibration_volume.hpp:18-27)."""
+    g = gold("ref_volume_file.npz")
+    data = g["data"]
+    Z, Y, X, ch = data.shape
+    want = np.array([X, Y, Z], np.uint32).tobytes() + np.array([0.5, 4.5], np.float32).tobytes() + data.tobytes()
+    assert g["raw"].tobytes() == want
+    assert np.array_equal(g["back"], data)
+    from rrpy import volume_io
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "v.cv_xyz_inv")
+        volume_io.write_volume(p, data, (0.5, 4.5))
+        assert open(p, "rb").read() == want
+        back, lim = volume_io.read_volume(p, ch)
+        assert np.array_equal(back, data) and tuple(lim) == (0.5, 4.5)
+
+
+def test_brick_ranges_match_reference_contained_voxels(O):
+    """divideBox + VolumeSampler::containedVoxels: per-brick voxel lists, order y -> x -> z (volume_sampler.cpp:50-62)."""
+    g = gold("ref_bricks.npz")
+    for ci in range(4):
+        dims = g[f"c{ci}_dims"].astype(int)
+        voxel, brick = g[f"c{ci}_voxel_brick"]
+        bmax = g[f"c{ci}_bmax"]
+        grid = O.brick_grid(np.zeros(3, np.float32), bmax, voxel, brick)
+        assert np.array_equal(grid["res"], dims.astype(np.uint32))
+        _, raw = O.divide_box_args(np.zeros(3, np.float32), bmax, grid["brick_size"], grid["res"], want_raw=True)
+        assert (raw[:, 1::2] <= dims).all(), "index lists must not run past the volume (aliasing is defined as dropped)"
+        off = 0
+        for b, n in zip(g[f"c{ci}_sel"], g[f"c{ci}_counts"]):
+            r = grid["ranges"][b]
+            want = g[f"c{ci}_indices"][off:off + n]
+            off += n
+            ys, xs, zs = np.meshgrid(np.arange(r[2], r[3]), np.arange(r[0], r[1]), np.arange(r[4], r[5]), indexing="ij")
+            mine = (zs * dims[0] * dims[1] + ys * dims[0] + xs).reshape(-1).astype(np.uint32)
+            assert np.array_equal(mine, want), f"case {ci} brick {b}"
+    # voxel centres (volume_sampler.cpp:33-48)
+    pos = g["positions_7_5_3"]
+    z, y, x = np.meshgrid(np.arange(3), np.arange(5), np.arange(7), indexing="ij")
+    for a, (idx, n) in enumerate(((x, 7), (y, 5), (z, 3))):
+        mine = (idx.astype(np.float32) + np.float32(0.5)) * (np.float32(1.0) / np.float32(n))
+        assert bits_equal(mine, pos[..., a]).all()
+    # glm::round as used by setBrickSize (recon_integration.cpp:475)
+    L = O.lib()
+    mine = np.array([L.ro_adjust_brick_size(np.float32(1.0), v) for v in g["round_in"]], np.float32)
+    assert bits_equal(mine, g["round_out"]).all()
+
+
+def test_draw_uniforms_match_reference_golden(O):
+    """recon_integration.cpp:183-206 evaluated with gloost / glm in float vs the oracle's double-then-round inverses."""
+    g = gold("ref_draw_uniforms.npz")
+    for v in g["views"]:
+        mv, pr, i2e, nm, cam = v[:16], v[16:32], v[32:48], v[48:64], v[64:67]
+        u = O.raymarch_uniforms(mv, pr, g["bbox_min"], g["bbox_max"], 320, 180)
+        np.testing.assert_allclose(u[:16], i2e, rtol=2e-5, atol=2e-6)
+        np.testing.assert_allclose(u[64:80], nm, rtol=2e-5, atol=2e-6)
+        np.testing.assert_allclose(u[80:83], cam, rtol=2e-5, atol=2e-6)
+
+
+def test_trilinear_agrees_with_reference_get_trilinear(O):
+    """DataTypes.cpp getTrilinear (voxel-unit coordinates, weights w*a + (1-w)*b) vs the GL LINEAR restatement
+    (normalised coordinates, fma form): same value up to rounding."""
+    g = gold("ref_trilinear.npz")
+    xyz = gold("ref_calib_invert.npz")["cv_xyz"]
+    Z, Y, X, _ = xyz.shape
+    L = O.lib()
+    out = np.zeros(4, np.float32)
+    for c, want in zip(g["coords"], g["values"]):
+        s, t, r = (c[0] + 0.5) / X, (c[1] + 0.5) / Y, (c[2] + 0.5) / Z
+        L.ro_kat_tex3d(np.ascontiguousarray(xyz), 3, X, Y, Z, s, t, r, out)
+        np.testing.assert_allclose(out[:3], want, rtol=0, atol=3e-5)
+
+
+# ------------------------------------------------------------------------------------------------ live oracle/_ref
+
+def _ref():
+    import ref_py
+    if not ref_py.available():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    return ref_py
+
+
+def test_live_reference_inverter_and_frustum(O):
+    R = _ref()
+    from rrpy import synth
+    sc = synth.make_scene(N=2, W=64, H=53, CW=80, CH=68, cv_res=(12, 14, 24), seed=4321)
+    for i in range(2):
+        p, c = R.frustum(sc.cv_xyz[i])
+        po, co = O.frustum(sc.cv_xyz[i])
+        assert bits_equal(p, po).all() and bits_equal(c, co).all()
+        a = R.calib_invert(sc.cv_xyz[i], sc.bbox_min, sc.bbox_max, (17, 19, 15))
+        b = O.calib_invert(sc.cv_xyz[i], sc.bbox_min, sc.bbox_max, (17, 19, 15))
+        assert bits_equal(a, b).all()
+
+
+def test_goldens_are_current():
+    """tests/golden was generated by tools/make_golden.py from the reference present in this container."""
+    R = _ref()
+    g = gold("ref_calib_invert.npz")
+    inv = R.calib_invert(g["cv_xyz"], g["bbox_min"], g["bbox_max"], g["out_res"])
+    assert bits_equal(inv, g["inv"]).all()
+
+
+# ------------------------------------------------------------------------------------------------ arithmetic pins
+
+def test_gl_sampling_known_answers(O):
+    L = O.lib()
+    img = np.arange(12, dtype=np.float32).reshape(3, 4)          # H=3, W=4, value = 4*y + x
+    # texel centres reproduce texels exactly; NEAREST picks floor(s*W)
+    for y in range(3):
+        for x in range(4):
+            s, t = (x + 0.5) / 4, (y + 0.5) / 3
+            assert L.ro_kat_tex2d(img, 4, 3, s, t, 0) == img[y, x]
+            assert L.ro_kat_tex2d(img, 4, 3, s, t, 1) == img[y, x]
+    assert L.ro_kat_tex2d(img, 4, 3, 0.5, 0.5, 0) == pytest.approx(5.5)      # midway between four texels
+    assert L.ro_kat_tex2d(img, 4, 3, -3.0, -1.0, 0) == 0.0                   # CLAMP_TO_EDGE
+    assert L.ro_kat_tex2d(img, 4, 3, 7.0, 9.0, 0) == 11.0
+    assert L.ro_kat_tex2d(img, 4, 3, 0.49999, 0.0, 1) == 1.0 and L.ro_kat_tex2d(img, 4, 3, 0.5, 0.0, 1) == 2.0
+    vol = np.zeros((2, 2, 2, 4), np.float32)
+    vol[1, :, :, 0] = 1.0; vol[:, 1, :, 1] = 1.0; vol[:, :, 1, 2] = 1.0      # channels = z, y, x ramps
+    out = np.zeros(4, np.float32)
+    L.ro_kat_tex3d(vol, 4, 2, 2, 2, 0.5, 0.25, 0.75, out)
+    assert out[2] == pytest.approx(0.5) and out[1] == 0.0 and out[0] == 1.0
+    L.ro_kat_tex3d(vol, 4, 2, 2, 2, 0.4, 0.6, 0.5, out)
+    np.testing.assert_allclose(out[:3], [0.5, 0.7, 0.3], atol=1e-6)
+
+
+def test_deterministic_pow_accuracy(O):
+    """pow(x,y) = exp2(y*log2 x): a few ulp from libm over the ranges the shaders use; NaN for x < 0 (NVIDIA GL)."""
+    L = O.lib()
+    xs = np.concatenate([np.linspace(1e-4, 1.0, 400), np.linspace(1.0, 120.0, 200)]).astype(np.float32)
+    for y in (2.0, 6.0, 2.4, 1.0 / 3.0, 20.0):
+        got = np.array([L.ro_kat_pow(x, np.float32(y)) for x in xs], np.float64)
+        want = np.power(xs.astype(np.float64), np.float64(np.float32(y)))
+        ok = (want > 1e-30) & (want < 1e30)
+        rel = np.abs(got - want)[ok] / want[ok]
+        assert ok.sum() > 400 and rel.max() < 1e-5, (y, rel.max())
+    assert L.ro_kat_pow(np.float32(0.0), np.float32(6.0)) == 0.0
+    assert L.ro_kat_pow(np.float32(1.0), np.float32(20.0)) == 1.0
+    assert np.isnan(L.ro_kat_pow(np.float32(-0.5), np.float32(2.0)))
+    assert L.ro_kat_exp2(np.float32(10.0)) == 1024.0 and L.ro_kat_log2(np.float32(0.125)) == -3.0
+
+
+def test_rgb_to_lab_known_answers(O):
+    """inc_color.glsl divides by 255 once more than needed, so inputs in [0,1] land near black: L is tiny but monotone."""
+    L = O.lib()
+    lab = np.zeros(3, np.float32)
+    L.ro_kat_rgb_to_lab(np.zeros(3, np.float32), lab)
+    assert np.allclose(lab, 0.0, atol=1e-6)
+    prev = -1.0
+    for v in (0.1, 0.5, 1.0):
+        L.ro_kat_rgb_to_lab(np.full(3, v, np.float32), lab)
+        assert lab[0] > prev and abs(lab[1]) < 1e-3 and abs(lab[2]) < 1e-3      # grey: a = b = 0
+        prev = lab[0]
+    # closed form for the linear branch: n/12.92*100, Y/100 <= eps -> L = 903.3*Y/100 ... (kappa branch)
+    L.ro_kat_rgb_to_lab(np.ones(3, np.float32), lab)
+    Y = (1.0 / 255.0) / 12.92 * 100.0 * (0.2126 + 0.7152 + 0.0722) / 100.0
+    assert lab[0] == pytest.approx(116.0 * ((903.3 * Y + 16.0) / 116.0) - 16.0, rel=1e-4)
+
+
+# ------------------------------------------------------------------------------------------------ shader restatement
+
+@pytest.fixture(scope="module")
+def small_frame(O, small_scene):
+    from rrpy import synth
+    inv = synth.analytic_inverse(small_scene, (50, 55, 50))
+    grid = O.brick_grid(small_scene.bbox_min, small_scene.bbox_max, 0.02, 0.1)
+    cams = [O.frustum(small_scene.cv_xyz[i])[1] for i in range(small_scene.N)]
+    pre = O.preprocess(small_scene, grid, cams)
+    occ = O.occupied_bricks(pre["bricks"], 10)
+    tsdf = O.integrate(inv, pre, grid, 0.01, True, occ)
+    return dict(inv=inv, grid=grid, pre=pre, occ=occ, tsdf=tsdf)
+
+
+def test_oracle_self_regression_pins(O, small_scene, small_frame):
+    from rrpy import synth
+    g = gold("oracle_frame_pins.npz")
+    pins = dict(zip(g["names"], g["sha256"]))
+    f = small_frame
+    mv, pr = synth.look_at((1.6, 1.5, 2.2), (0.0, 1.1, 0.0)), synth.perspective(50.0, 16 / 9, 0.1, 10.0)
+    rm = O.raymarch(f["tsdf"], 0.01, f["inv"], small_scene, f["pre"], f["grid"], f["occ"], mv, pr, 160, 90, 1, True)
+    got = dict(f["pre"])
+    got.update(occupied=f["occ"], tsdf=f["tsdf"], rgba=rm["rgba"], depth=rm["depth"], samples=rm["samples"])
+    for k, want in pins.items():
+        assert hashlib.sha256(np.ascontiguousarray(got[k]).tobytes()).hexdigest() == want, f"oracle output '{k}' changed"
+    assert len(f["occ"]) == int(g["n_occupied"]) and int((rm["depth"] < 1).sum()) == int(g["hits"])
+
+
+def test_oracle_stage_invariants(small_scene, small_frame):
+    """Properties the shaders guarantee by construction."""
+    pre, sc = small_frame["pre"], small_scene
+    raw = sc.depth
+    valid_raw = (raw > 0.5) & (raw < 4.5)
+    assert np.array_equal(pre["morph"][valid_raw], raw[valid_raw]), "dilate keeps valid pixels"
+    assert ((pre["morph"] > 0) & ~valid_raw).sum() > 0, "dilate fills some holes"
+    d, db, sil, q, n = pre["depth"], pre["depth_b"], pre["sil"], pre["quality"], pre["normal"]
+    assert set(np.unique(sil)) <= {0.0, 1.0}
+    assert ((d[..., 1] >= 0) & (d[..., 1] <= 1.0 + 1e-6)).all(), "mean range weight is a fraction of 169 taps"
+    assert (sil[db[..., 0] <= 0] == 0).all() and (db[..., 1][sil == 1] == 0).all()
+    assert set(np.unique(db[..., 0][db[..., 0] < 0])) <= {-1.0}
+    inside = (db[..., 0] > 0) & (db[..., 0] < 1)
+    nn = np.linalg.norm(n, axis=-1)
+    assert np.allclose(nn[inside & np.isfinite(nn)], 1.0, atol=1e-4) and (nn[~inside] == 0).all()
+    assert (q[~inside] == 0).all() and (q[inside & np.isfinite(q)] >= 0).all()
+    assert pre["bricks"].sum() >= inside.sum(), "every valid pixel marks its own brick (+ at most one neighbour)"
+    assert pre["bricks"].sum() <= 2 * inside.sum()
+
+
+def test_oracle_integration_invariants(O, small_scene, small_frame):
+    f = small_frame
+    tsdf, grid = f["tsdf"], f["grid"]
+    limit = np.float32(0.01)
+    fin = tsdf[np.isfinite(tsdf)]
+    assert fin.min() >= -limit and fin.max() <= limit
+    # voxels outside every occupied brick keep the cleared value
+    mask = np.zeros(tsdf.shape, bool)
+    for b in f["occ"]:
+        r = grid["ranges"][b]
+        mask[r[4]:r[5], r[2]:r[3], r[0]:r[1]] = True
+    assert (tsdf[~mask] == -limit).all()
+    assert ((tsdf > -limit) & (tsdf < limit)).sum() > 1000
+    # dense integration agrees with the brick path inside occupied bricks
+    dense = O.integrate(f["inv"], f["pre"], grid, 0.01, False, f["occ"])
+    assert bits_equal(dense[mask], tsdf[mask]).all()
+    # weight channel: zero where nothing was fused
+    t2, w = O.integrate(f["inv"], f["pre"], grid, 0.01, True, f["occ"], want_weight=True)
+    assert bits_equal(t2, tsdf).all() and (w >= 0).all() and (w[~mask] == 0).all() and (w > 0).sum() > 1000
+
+
+def test_planar_wall_gives_linear_ramp(O):
+    """Analytic scene: a wall perpendicular to sensor 0 => along the optical axis the fused TSDF is the
+    clamped linear ramp (voxel depth - wall depth) in normalised depth units."""
+    from rrpy import synth
+    sc = synth.make_scene(N=1, W=128, H=106, CW=160, CH=135, cv_res=(32, 32, 64), sdf=synth.wall_sdf)
+    sc.depth[:] = np.where(sc.depth > 0, 2.0, 0.0).astype(np.float32)       # exact wall, no noise
+    inv = synth.analytic_inverse(sc, (50, 55, 50))
+    grid = O.brick_grid(sc.bbox_min, sc.bbox_max, 0.02, 0.1)
+    cams = [O.frustum(sc.cv_xyz[0])[1]]
+    pre = O.preprocess(sc, grid, cams)
+    tsdf = O.integrate(inv, pre, grid, 0.04, False, np.zeros(0, np.uint32))
+    s = sc.sensors[0]
+    Z, Y, X = tsdf.shape
+    zz, yy, xx = np.meshgrid(np.arange(Z), np.arange(Y), np.arange(X), indexing="ij")
+    P = sc.bbox_min + (np.stack([xx, yy, zz], -1) + 0.5) / np.array([X, Y, Z]) * (sc.bbox_max - sc.bbox_min)
+    depth_m = (P - s.pos) @ s.fwd
+    want = (depth_m - 2.0) / 4.0
+    band = (np.abs(want) < 0.03) & (tsdf > -0.04) & (tsdf < 0.04)
+    assert band.sum() > 2000
+    assert np.abs(tsdf[band] - want[band]).max() < 2e-3, "ramp slope/offset (trilinear lookup of an affine field is exact up to the 2 mm distortion)"
