@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <vector>
 
 namespace rr {
 
@@ -109,6 +110,7 @@ int rr_create(rr_ctx** out, int device, int num_sensors, int depth_w, int depth_
   if (rc == RR_OK) rc = dev_alloc(c, &c->d_gather, (size_t)c->N * (c->W + 1) * (c->H + 1) * 2, "gather");
   if (rc == RR_OK) rc = dev_alloc(c, &c->d_flags, 4, "flags");
   if (rc == RR_OK) rc = dev_alloc(c, &c->d_num_occ, 1, "num_occ");
+  if (rc == RR_OK) rc = dev_alloc(c, &c->d_work, 4, "work counters");
   if (rc == RR_OK) rc = check(c, cudaMallocHost((void**)&c->h_num_occ, sizeof(uint32_t)), "pinned count");
   if (rc == RR_OK) {
     cudaMemsetAsync(c->d_flags, 0, 4 * sizeof(uint32_t), c->stream);
@@ -130,7 +132,7 @@ void rr_destroy(rr_ctx* c) {
   cudaFree(c->d_inv); cudaFree(c->d_depth_raw); cudaFree(c->d_color); cudaFree(c->d_morph); cudaFree(c->d_depth);
   cudaFree(c->d_lab); cudaFree(c->d_depth_b); cudaFree(c->d_sil); cudaFree(c->d_normal); cudaFree(c->d_quality);
   cudaFree(c->d_gather); cudaFree(c->d_flags); cudaFree(c->d_ranges); cudaFree(c->d_counters); cudaFree(c->d_occupied);
-  cudaFree(c->d_num_occ); cudaFree(c->d_near_occ); cudaFree(c->d_occ_mask); cudaFree(c->d_pos); cudaFree(c->d_step); cudaFree(c->d_tsdf); cudaFree(c->d_weight);
+  cudaFree(c->d_num_occ); cudaFree(c->d_work); cudaFree(c->d_rowmask); cudaFree(c->d_rowany); cudaFree(c->d_cand_y); cudaFree(c->d_cand_z); cudaFree(c->d_near_occ); cudaFree(c->d_occ_mask); cudaFree(c->d_pos); cudaFree(c->d_step); cudaFree(c->d_tsdf); cudaFree(c->d_weight);
   cudaFree(c->d_rgba); cudaFree(c->d_zbuf); cudaFree(c->d_nsamples);
   if (c->h_num_occ) cudaFreeHost(c->h_num_occ);
   for (auto& kv : c->timers) {
@@ -184,6 +186,13 @@ int rr_calib_upload(rr_ctx* c, int sensor, const float* cv_xyz, const float* cv_
   for (int a = 0; a < 3; ++a) c->cres[sensor][a] = res[a];
   c->dlim[sensor][0] = dl[0]; c->dlim[sensor][1] = dl[1];
   host_frustum(cv_xyz, res, c->planes[sensor], c->cam_pos[sensor]);
+  for (int a = 0; a < 3; ++a) { c->xyz_min[sensor][a] = cv_xyz[a]; c->xyz_max[sensor][a] = cv_xyz[a]; }
+  for (size_t i = 0; i < n; ++i)
+    for (int a = 0; a < 3; ++a) {
+      const float v = cv_xyz[i * 3 + a];
+      if (v < c->xyz_min[sensor][a]) c->xyz_min[sensor][a] = v;
+      if (v > c->xyz_max[sensor][a]) c->xyz_max[sensor][a] = v;
+    }
   c->have_calib[sensor] = true;
   return RR_OK;
 }
@@ -253,6 +262,33 @@ int rr_configure(rr_ctx* c, const rr_config* cfg) {
     RR_TRY(dev_alloc(c, &c->d_occupied, nb, "occupied list"));
     RR_TRY(dev_alloc(c, &c->d_near_occ, nb, "near-occupied mask"));
     RR_TRY(dev_alloc(c, &c->d_occ_mask, nb, "occupied mask"));
+    // per-axis candidate bricks of every voxel index (bricks may overlap by a voxel, or leave a gap)
+    c->mask_words = (int)((res[0] + 31) / 32);
+    c->fused_ok = rb[0] <= 32767 && rb[1] <= 32767 && rb[2] <= 32767;
+    std::vector<int16_t> cand[3];
+    for (int a = 0; a < 3 && c->fused_ok; ++a) {
+      cand[a].assign((size_t)res[a] * 2, (int16_t)-1);
+      const size_t stride = (a == 0) ? 1 : (a == 1 ? rb[0] : (size_t)rb[0] * rb[1]);
+      for (uint32_t i = 0; i < rb[a] && c->fused_ok; ++i) {
+        const int32_t* r = c->h_ranges.data() + (size_t)i * stride * 6 + 2 * a;
+        for (int32_t v = r[0]; v < r[1]; ++v) {
+          int16_t* slot = cand[a].data() + (size_t)v * 2;
+          if (slot[0] < 0) slot[0] = (int16_t)i;
+          else if (slot[1] < 0) slot[1] = (int16_t)i;
+          else c->fused_ok = false;     // three bricks share a voxel on one axis: use the unfused path
+        }
+      }
+    }
+    RR_TRY(dev_alloc(c, &c->d_rowmask, (size_t)rb[2] * rb[1] * c->mask_words, "row masks"));
+    RR_TRY(dev_alloc(c, &c->d_rowany, (size_t)rb[2] * rb[1], "row flags"));
+    RR_TRY(dev_alloc(c, &c->d_cand_y, (size_t)res[1] * 2, "cand y"));
+    RR_TRY(dev_alloc(c, &c->d_cand_z, (size_t)res[2] * 2, "cand z"));
+    if (c->fused_ok) {
+      cudaMemcpyAsync(c->d_cand_y, cand[1].data(), cand[1].size() * sizeof(int16_t), cudaMemcpyHostToDevice, c->stream);
+      cudaMemcpyAsync(c->d_cand_z, cand[2].data(), cand[2].size() * sizeof(int16_t), cudaMemcpyHostToDevice, c->stream);
+    }
+    cudaMemsetAsync(c->d_rowmask, 0, (size_t)rb[2] * rb[1] * c->mask_words * sizeof(uint32_t), c->stream);
+    cudaMemsetAsync(c->d_rowany, 0, (size_t)rb[2] * rb[1], c->stream);
     cudaMemcpyAsync(c->d_ranges, c->h_ranges.data(), (size_t)nb * 6 * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream);
     cudaMemsetAsync(c->d_counters, 0, nb * sizeof(uint32_t), c->stream);
     cudaMemsetAsync(c->d_near_occ, 0, nb, c->stream);

@@ -8,7 +8,8 @@
 //              each [N][H][W]
 //   gather     float4[N][H+1][W+1][2]: per bilinear footprint (i0,j0) the four depth_b.x taps and the four quality
 //              taps (silhouette in the sign bit) = one 32-byte sector per voxel-sensor lookup in the integrator
-//   bricks     uint32 counters[nb], occupied[nb], count; int32 ranges[nb][6]; uint8 near_occupied[nb]
+//   bricks     uint32 counters[nb], occupied[nb], count; int32 ranges[nb][6]; uint8 near_occupied[nb], occ_mask[nb];
+//              uint32 rowmask[nbz][nby][ceil(X/32)], uint8 rowany[nbz][nby], int16 cand_y[Y][2], cand_z[Z][2]
 //   volume     tsdf float[Z][Y][X] (+ weight float[Z][Y][X] when rr_config.store_weight)
 #pragma once
 
@@ -65,6 +66,7 @@ struct rr_ctx {
   float dlim[RR_MAX_SENSORS][2] = {};
   float cam_pos[RR_MAX_SENSORS][3] = {};
   float planes[RR_MAX_SENSORS][6][4] = {};
+  float xyz_min[RR_MAX_SENSORS][3] = {}, xyz_max[RR_MAX_SENSORS][3] = {};   // bounding box of the cv_xyz samples
   bool have_calib[RR_MAX_SENSORS] = {};
   float4* d_inv = nullptr;
   uint32_t ires[3] = {0, 0, 0};
@@ -96,6 +98,15 @@ struct rr_ctx {
   uint32_t* d_num_occ = nullptr;
   uint8_t* d_near_occ = nullptr;
   uint8_t* d_occ_mask = nullptr;
+  // fused clear+integrate support: per brick row (bz, by) the x bitmask of voxels inside occupied bricks, a byte that
+  // says whether the row has any, and per voxel y / z index the (at most two) brick indices whose range contains it
+  uint32_t* d_rowmask = nullptr;   // [nbz][nby][mask_words]
+  uint8_t* d_rowany = nullptr;     // [nbz][nby]
+  int16_t* d_cand_y = nullptr;     // [Y][2], -1 = none
+  int16_t* d_cand_z = nullptr;     // [Z][2]
+  uint32_t* d_work = nullptr;      // [4] work-item counters of the persistent fused kernel
+  int mask_words = 0;
+  bool fused_ok = false;           // brick table is separable with <= 2 bricks per voxel and axis
   uint32_t* h_num_occ = nullptr;   // pinned
   float* d_tsdf = nullptr;
   float* d_weight = nullptr;

@@ -151,6 +151,127 @@ __global__ void __launch_bounds__(BRICK_MAX_THREADS, MINB) k_integrate_bricks(co
   }
 }
 
+// ---- fused clear + integrate (bricks mode) ----------------------------------------------------------------------
+// ReconIntegration::integrate clears the whole volume to -limit and then overwrites the voxels of the occupied bricks
+// (recon_integration.cpp:248-259). Here ONE persistent kernel writes every voxel of the slab exactly once: the clear is
+// an HBM-bound stream of 16-byte stores (4 bytes per voxel), the brick evaluation is issue/latency-bound gather work,
+// so warps of both kinds share each SM and overlap. Work is handed out per WARP from two device counters:
+//   fill item    = FILL_ROWS consecutive (y, z) voxel rows; voxels inside an occupied brick are skipped (row bitmask
+//                  built by k_bricks_masks), everything else gets -limit (and weight 0);
+//   compute item = 32 consecutive columns of the flattened (occupied brick, column) space x one z-chunk.
+// The first `fill_warps` warps of a CTA start on fill items, the others on compute items; a warp that runs out of its
+// own kind helps with the other, so the kernel ends when both counters are exhausted.
+struct FusedParams {
+  IntegrateParams ip;
+  const uint32_t* rowmask; const uint8_t* rowany; const int16_t* cand_y; const int16_t* cand_z;
+  int mask_words, nby;
+  uint32_t* work;              // [0] compute items handed out, [1] fill items handed out
+  int max_cols, max_nz, zchunk, n_zchunks;
+  int fill_rows; uint32_t fill_items; uint32_t row_begin, row_end;
+  int fill_warps;
+  float fill_value;
+};
+
+template <bool WEIGHT>
+__device__ __forceinline__ void fill_rows(const FusedParams& p, uint32_t row0, uint32_t row1, int lane) {
+  const int X = p.ip.X, Y = p.ip.Y;
+  const float4 v4 = make_float4(p.fill_value, p.fill_value, p.fill_value, p.fill_value);
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool vec = (X & 3) == 0;
+  for (uint32_t row = row0; row < row1; ++row) {
+    const int z = (int)(row / (uint32_t)Y), y = (int)(row - (uint32_t)z * (uint32_t)Y);
+    const int cy0 = p.cand_y[2 * y], cy1 = p.cand_y[2 * y + 1], cz0 = p.cand_z[2 * z], cz1 = p.cand_z[2 * z + 1];
+    // brick rows that contain this voxel row (at most 2 x 2)
+    int br[4];
+    br[0] = (cy0 >= 0 && cz0 >= 0) ? cz0 * p.nby + cy0 : -1;
+    br[1] = (cy1 >= 0 && cz0 >= 0) ? cz0 * p.nby + cy1 : -1;
+    br[2] = (cy0 >= 0 && cz1 >= 0) ? cz1 * p.nby + cy0 : -1;
+    br[3] = (cy1 >= 0 && cz1 >= 0) ? cz1 * p.nby + cy1 : -1;
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) any = any || (br[k] >= 0 && p.rowany[br[k]] != 0);
+    float* trow = p.ip.tsdf + (size_t)row * X;
+    float* wrow = WEIGHT ? p.ip.weight + (size_t)row * X : nullptr;
+    for (int chunk = 0; chunk * 1024 < X; ++chunk) {
+      uint32_t comb = 0;
+      if (any) {
+        const int w = chunk * 32 + lane;
+        if (w < p.mask_words) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) if (br[k] >= 0) comb |= __ldg(p.rowmask + (size_t)br[k] * p.mask_words + w);
+        }
+      }
+      const int xbase = chunk * 1024;
+      if (vec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t word = any ? __shfl_sync(0xffffffffu, comb, j * 4 + (lane >> 3)) : 0u;
+          const int x = xbase + (j * 32 + lane) * 4;
+          if (x >= X) continue;
+          const uint32_t nib = (word >> ((lane & 7) * 4)) & 15u;
+          if (nib == 0) {
+            __stcs(reinterpret_cast<float4*>(trow + x), v4);
+            if (WEIGHT) __stcs(reinterpret_cast<float4*>(wrow + x), z4);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (!((nib >> e) & 1u)) { trow[x + e] = p.fill_value; if (WEIGHT) wrow[x + e] = 0.0f; }
+          }
+        }
+      } else {
+        for (int i = 0; i < 32; ++i) {
+          const uint32_t word = any ? __shfl_sync(0xffffffffu, comb, i) : 0u;
+          const int x = xbase + i * 32 + lane;
+          if (x >= X) continue;
+          if (!((word >> lane) & 1u)) { trow[x] = p.fill_value; if (WEIGHT) wrow[x] = 0.0f; }
+        }
+      }
+    }
+  }
+}
+
+#ifndef RR_FUSED_THREADS
+#define RR_FUSED_THREADS 512
+#endif
+template <int N, bool WEIGHT>
+__global__ void __launch_bounds__(RR_FUSED_THREADS, 2) k_integrate_fused(const __grid_constant__ FusedParams p) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned n_occ = *p.ip.num_occupied;
+  const unsigned col_blocks = (n_occ * (unsigned)p.max_cols + 31u) / 32u;
+  const unsigned citems = col_blocks * (unsigned)p.n_zchunks;
+  bool filling = warp < p.fill_warps;
+  for (int phase = 0; phase < 2; ++phase, filling = !filling) {
+    if (filling) {
+      for (;;) {
+        unsigned it = 0;
+        if (lane == 0) it = atomicAdd(p.work + 1, 1u);
+        it = __shfl_sync(0xffffffffu, it, 0);
+        if (it >= p.fill_items) break;
+        const uint32_t r0 = p.row_begin + it * (uint32_t)p.fill_rows;
+        fill_rows<WEIGHT>(p, r0, min(r0 + (uint32_t)p.fill_rows, p.row_end), lane);
+      }
+    } else {
+      for (;;) {
+        unsigned it = 0;
+        if (lane == 0) it = atomicAdd(p.work, 1u);
+        it = __shfl_sync(0xffffffffu, it, 0);
+        if (it >= citems) break;
+        const unsigned cb = it / (unsigned)p.n_zchunks, zc = it - cb * (unsigned)p.n_zchunks;
+        const unsigned slot = cb * 32u + (unsigned)lane;
+        const unsigned b = slot / (unsigned)p.max_cols, col = slot - b * (unsigned)p.max_cols;
+        if (b >= n_occ) continue;
+        const int32_t* rg = p.ip.ranges + (size_t)p.ip.occupied[b] * 6;
+        const int x0 = rg[0], nx = rg[1] - rg[0], y0 = rg[2], ny = rg[3] - rg[2];
+        const int zb = max(rg[4] + (int)zc * p.zchunk, p.ip.z_begin);
+        const int ze = min(min(rg[4] + (int)(zc + 1) * p.zchunk, rg[5]), p.ip.z_end);
+        if (zb >= ze || (int)col >= nx * ny) continue;
+        const int cy = (int)col / nx, cx = (int)col - cy * nx;
+        march_column<N, WEIGHT>(p.ip, x0 + cx, y0 + cy, zb, ze);
+      }
+    }
+  }
+}
+
 // glClearTexImage(-limit) (recon_integration.cpp:250-251): 16-byte streaming stores over the slab.
 __global__ void __launch_bounds__(256) k_fill(float* __restrict__ dst, size_t n, float value) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -163,7 +284,7 @@ __global__ void __launch_bounds__(256) k_fill(float* __restrict__ dst, size_t n,
 }
 
 template <int N>
-static int launch_n(rr_ctx* c, const IntegrateParams& p, bool bricks, bool weight) {
+static int launch_n(rr_ctx* c, const IntegrateParams& p, bool bricks, bool weight, bool fused) {
   const dim3 blk(32, 8, 1);
   if (bricks) {
     int max_cols = 0, max_nz = 0;
@@ -172,6 +293,31 @@ static int launch_n(rr_ctx* c, const IntegrateParams& p, bool bricks, bool weigh
       max_nz = std::max(max_nz, c->h_ranges[i + 5] - c->h_ranges[i + 4]);
     }
     if (max_cols == 0 || max_nz == 0) return RR_OK;
+    static const int zchunk_env = getenv("RR_BRICK_ZCHUNK") ? atoi(getenv("RR_BRICK_ZCHUNK")) : 0;
+    if (fused) {
+      // z-chunks: split a brick's z extent into pieces of ~zchunk voxels of equal size
+      const int want = zchunk_env > 0 ? zchunk_env : 13;
+      const int n_zchunks = std::max(1, (max_nz + want - 1) / want);
+      FusedParams f{};
+      f.ip = p;
+      f.rowmask = c->d_rowmask; f.rowany = c->d_rowany; f.cand_y = c->d_cand_y; f.cand_z = c->d_cand_z;
+      f.mask_words = c->mask_words; f.nby = (int)c->bricks.res[1];
+      f.work = c->d_work;
+      f.max_cols = max_cols; f.max_nz = max_nz; f.n_zchunks = n_zchunks; f.zchunk = (max_nz + n_zchunks - 1) / n_zchunks;
+      static const int fill_rows = getenv("RR_FUSED_FILL_ROWS") ? atoi(getenv("RR_FUSED_FILL_ROWS")) : 32;
+      static const int fill_warps = getenv("RR_FUSED_FILL_WARPS") ? atoi(getenv("RR_FUSED_FILL_WARPS")) : 2;
+      static const int ctas_per_sm = getenv("RR_FUSED_CTAS") ? atoi(getenv("RR_FUSED_CTAS")) : 2;
+      f.fill_rows = fill_rows; f.fill_warps = fill_warps;
+      f.row_begin = (uint32_t)p.z_begin * (uint32_t)p.Y; f.row_end = (uint32_t)p.z_end * (uint32_t)p.Y;
+      f.fill_items = (f.row_end - f.row_begin + (uint32_t)fill_rows - 1u) / (uint32_t)fill_rows;
+      f.fill_value = -p.limit;
+      cudaMemsetAsync(c->d_work, 0, 4 * sizeof(uint32_t), c->stream);
+      const dim3 grd(148 * ctas_per_sm, 1, 1);
+      if (weight) k_integrate_fused<N, true><<<grd, RR_FUSED_THREADS, 0, c->stream>>>(f);
+      else k_integrate_fused<N, false><<<grd, RR_FUSED_THREADS, 0, c->stream>>>(f);
+      RR_LAUNCH_CHECK(c, "k_integrate_fused");
+      return RR_OK;
+    }
     // block size: the multiple of 32 (128..320) that wastes the fewest lanes on a brick's column count
     int threads = 256;
     double best = 1e9;
@@ -179,14 +325,10 @@ static int launch_n(rr_ctx* c, const IntegrateParams& p, bool bricks, bool weigh
       const double waste = double((max_cols + t - 1) / t * t) / double(max_cols);
       if (waste < best - 1e-9 || (waste < best + 1e-9 && t > threads)) { best = waste; threads = t; }
     }
-    static const int zchunk = getenv("RR_BRICK_ZCHUNK") ? atoi(getenv("RR_BRICK_ZCHUNK")) : 9;
+    const int zchunk = zchunk_env > 0 ? zchunk_env : 9;
     static const int gmult = getenv("RR_BRICK_GRID") ? atoi(getenv("RR_BRICK_GRID")) : 6;
-    static const int minb = getenv("RR_BRICK_MINB") ? atoi(getenv("RR_BRICK_MINB")) : 2;
-    if (getenv("RR_BRICK_THREADS")) threads = atoi(getenv("RR_BRICK_THREADS"));
     const dim3 grd(148 * gmult, 1, 1);
     if (weight) k_integrate_bricks<N, true, 2><<<grd, threads, 0, c->stream>>>(p, max_cols, max_nz, zchunk);
-    else if (minb == 3) k_integrate_bricks<N, false, 3><<<grd, threads, 0, c->stream>>>(p, max_cols, max_nz, zchunk);
-    else if (minb == 4) k_integrate_bricks<N, false, 4><<<grd, threads, 0, c->stream>>>(p, max_cols, max_nz, zchunk);
     else k_integrate_bricks<N, false, 2><<<grd, threads, 0, c->stream>>>(p, max_cols, max_nz, zchunk);
   } else {
     const int nz = p.z_end - p.z_begin;
@@ -212,7 +354,10 @@ int launch_integrate(rr_ctx* c) {
   timer_begin(c, "2integrate");
   const size_t plane = (size_t)p.X * p.Y;
   const size_t nslab = plane * (size_t)(p.z_end - p.z_begin);
-  if (bricks && nslab) {
+  // RR_INTEGRATE_FUSED=0 selects the two-kernel path (k_fill, then k_integrate_bricks) for A/B measurements
+  const bool fused_env = !(getenv("RR_INTEGRATE_FUSED") && atoi(getenv("RR_INTEGRATE_FUSED")) == 0);
+  const bool fused = bricks && fused_env && c->fused_ok;
+  if (bricks && !fused && nslab) {
     // dense mode overwrites every voxel, so only the brick path needs the clear
     k_fill<<<148 * 8, 256, 0, c->stream>>>(c->d_tsdf + plane * p.z_begin, nslab, -p.limit);
     RR_LAUNCH_CHECK(c, "k_fill");
@@ -224,14 +369,14 @@ int launch_integrate(rr_ctx* c) {
   int rc = RR_OK;
   if (nslab) {
     switch (c->N) {
-      case 1: rc = launch_n<1>(c, p, bricks, weight); break;
-      case 2: rc = launch_n<2>(c, p, bricks, weight); break;
-      case 3: rc = launch_n<3>(c, p, bricks, weight); break;
-      case 4: rc = launch_n<4>(c, p, bricks, weight); break;
-      case 5: rc = launch_n<5>(c, p, bricks, weight); break;
-      case 6: rc = launch_n<6>(c, p, bricks, weight); break;
-      case 7: rc = launch_n<7>(c, p, bricks, weight); break;
-      case 8: rc = launch_n<8>(c, p, bricks, weight); break;
+      case 1: rc = launch_n<1>(c, p, bricks, weight, fused); break;
+      case 2: rc = launch_n<2>(c, p, bricks, weight, fused); break;
+      case 3: rc = launch_n<3>(c, p, bricks, weight, fused); break;
+      case 4: rc = launch_n<4>(c, p, bricks, weight, fused); break;
+      case 5: rc = launch_n<5>(c, p, bricks, weight, fused); break;
+      case 6: rc = launch_n<6>(c, p, bricks, weight, fused); break;
+      case 7: rc = launch_n<7>(c, p, bricks, weight, fused); break;
+      case 8: rc = launch_n<8>(c, p, bricks, weight, fused); break;
       default: return fail(c, RR_ERR_UNSUPPORTED, "integrate: 1..8 sensors supported");
     }
   }

@@ -65,7 +65,9 @@ def _assert_frame(got, want, stages=("morph", "depth", "lab", "depth_b", "sil", 
         assert bits_equal(got["weight"], want["weight"]).all(), mismatch_report("weight", got["weight"], want["weight"])
 
 
-def test_frame_bricks_small(small_scene):
+@pytest.mark.parametrize("fused", ["1", "0"])
+def test_frame_bricks_small(small_scene, fused, monkeypatch):
+    monkeypatch.setenv("RR_INTEGRATE_FUSED", fused)     # fused clear+integrate kernel vs k_fill + k_integrate_bricks
     got, want = _run_both(small_scene, 0.02, (50, 55, 50), use_bricks=True)
     assert len(want["occupied"]) > 20, "synthetic scene should occupy bricks"
     assert ((want["tsdf"] > -0.01) & (want["tsdf"] < 0.01)).sum() > 1000, "scene should produce a TSDF band"
@@ -80,6 +82,13 @@ def test_frame_dense_small_with_weight(small_scene):
 @pytest.mark.parametrize("flags", [(False, True, True), (True, False, True), (True, True, False)])
 def test_frame_flag_variants(small_scene, flags):
     got, want = _run_both(small_scene, 0.025, (40, 44, 40), use_bricks=True, flags=flags)
+    _assert_frame(got, want)
+
+
+@pytest.mark.parametrize("voxel", [0.03, 0.025])
+def test_frame_bricks_with_weight_odd_sizes(small_scene, voxel):
+    # 0.03 -> 67x74x67 voxels (row length not a multiple of 4: scalar fill path, 1-voxel brick overlaps); weight volume on
+    got, want = _run_both(small_scene, voxel, (50, 55, 50), use_bricks=True, store_weight=True)
     _assert_frame(got, want)
 
 
