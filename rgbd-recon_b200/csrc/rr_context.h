@@ -106,6 +106,8 @@ struct rr_ctx {
   int16_t* d_cand_z = nullptr;     // [Z][2]
   uint32_t* d_work = nullptr;      // [4] work-item counters of the persistent fused kernel
   int mask_words = 0;
+  float4* d_ztab = nullptr;        // [Z] (k0, k1, g, 1-g) of the z filter tap against the inverse volume (k_build_ztab)
+  int ztab_Z = 0, ztab_IZ = 0;
   bool fused_ok = false;           // brick table is separable with <= 2 bricks per voxel and axis
   uint32_t* h_num_occ = nullptr;   // pinned
   float* d_tsdf = nullptr;

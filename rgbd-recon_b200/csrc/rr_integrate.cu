@@ -19,31 +19,53 @@ namespace rr {
 struct IntegrateParams {
   const float4* inv;      // [N][IZ][IY][IX]
   const float4* gather;   // [N][H+1][W+1][2]
+  const float4* ztab;     // [Z]: per fine z the coarse plane pair and weight of the z filter tap: (k0, k1, g, 1-g)
   float* tsdf;
   float* weight;
   const int32_t* ranges;  // [num_bricks][6]
   const uint32_t* occupied;
   const uint32_t* num_occupied;
   int IX, IY, IZ, W, H, X, Y, Z;
+  float fW, fH, exmax, eymax;   // (float)W, (float)H, (float)(W-1), (float)(H-1)
   int z_begin, z_end;     // slab
   int z_chunk;
   float limit;
 };
 
+// lin_coord of every fine z against the inverse volume's z axis, evaluated once per (Z, IZ) pair with the same
+// float operations march_column used to repeat per voxel (identical results, ~25 instructions saved per voxel).
+__global__ void k_build_ztab(float4* __restrict__ ztab, int Z, int IZ) {
+  const int z = blockIdx.x * blockDim.x + threadIdx.x;
+  if (z >= Z) return;
+  const float stepZ = 1.0f / (float)Z;
+  const float pz = ((float)z + 0.5f) * stepZ;
+  int k0, k1; float g;
+  lin_coord(pz, IZ, k0, k1, g);
+  ztab[z] = make_float4(__int_as_float(k0), __int_as_float(k1), g, 1.0f - g);
+}
+
+// One sensor's lookup for one voxel: bilinear weights, interpolated depth coordinate and the 32-byte gather texel.
+struct Tap {
+  float wa, wb, d;
+  float4 lo, hi;
+};
+
 // One (x, y) column, z in [zb, ze). All index arithmetic is 32-bit (sizes are validated on the host).
+// z (hence the coarse plane pair) is uniform across a warp wherever the callers keep a warp inside one brick / one
+// dense tile, so the plane-advance branches below do not diverge.
 template <int N, bool WEIGHT>
 __device__ __forceinline__ void march_column(const IntegrateParams& p, int x, int y, int zb, int ze) {
-  const float stepX = 1.0f / (float)p.X, stepY = 1.0f / (float)p.Y, stepZ = 1.0f / (float)p.Z;
+  const float stepX = 1.0f / (float)p.X, stepY = 1.0f / (float)p.Y;
   const float px = ((float)x + 0.5f) * stepX, py = ((float)y + 0.5f) * stepY;
   int x0, x1, y0, y1; float a, b;
   lin_coord(px, p.IX, x0, x1, a);
   lin_coord(py, p.IY, y0, y1, b);
+  const float oma = 1.0f - a, omb = 1.0f - b;            // lerp(v0, v1, t) = fma(t, v1, (1 - t) * v0)
   const unsigned o00 = y0 * p.IX + x0, o10 = y0 * p.IX + x1, o01 = y1 * p.IX + x0, o11 = y1 * p.IX + x1;
   const unsigned plane_sz = (unsigned)(p.IX * p.IY);
   const unsigned gstride = (unsigned)((p.W + 1) * (p.H + 1) * 2);
   const unsigned grow = (unsigned)(p.W + 1);
-  const float limit = p.limit;
-  const float fW = (float)p.W, fH = (float)p.H, exmax = (float)(p.W - 1), eymax = (float)(p.H - 1);
+  const float limit = p.limit, neg_limit = -p.limit;
   float3 A[N], B[N];
   int ck0 = -1, ck1 = -1;
 
@@ -51,65 +73,95 @@ __device__ __forceinline__ void march_column(const IntegrateParams& p, int x, in
     const float4* base = p.inv + (unsigned)(s * p.IZ + k) * plane_sz;
     const float4 p00 = __ldg(base + o00), p10 = __ldg(base + o10), p01 = __ldg(base + o01), p11 = __ldg(base + o11);
     float3 r;
-    r.x = lerpf(lerpf(p00.x, p10.x, a), lerpf(p01.x, p11.x, a), b);
-    r.y = lerpf(lerpf(p00.y, p10.y, a), lerpf(p01.y, p11.y, a), b);
-    r.z = lerpf(lerpf(p00.z, p10.z, a), lerpf(p01.z, p11.z, a), b);
+    r.x = fmaf(b, fmaf(a, p11.x, oma * p01.x), omb * fmaf(a, p10.x, oma * p00.x));
+    r.y = fmaf(b, fmaf(a, p11.y, oma * p01.y), omb * fmaf(a, p10.y, oma * p00.y));
+    r.z = fmaf(b, fmaf(a, p11.z, oma * p01.z), omb * fmaf(a, p10.z, oma * p00.z));
     return r;
   };
 
   unsigned o = (unsigned)((zb * p.Y + y) * p.X + x);
   const unsigned ostep = (unsigned)(p.X * p.Y);
   for (int z = zb; z < ze; ++z, o += ostep) {
-    const float pz = ((float)z + 0.5f) * stepZ;
-    int k0, k1; float g;
-    lin_coord(pz, p.IZ, k0, k1, g);
-    const bool needA = (k0 != ck0), a_from_b = needA && (k0 == ck1);
-    const bool needB = (k1 != ck1), b_from_a = needB && (k1 == k0);
-    float weighted_tsd = limit, total_weight = 0.0f;
+    const float4 zt = __ldg(p.ztab + z);
+    const int k0 = __float_as_int(zt.x), k1 = __float_as_int(zt.y);
+    const float g = zt.z, omg = zt.w;
+    if (k0 != ck0) {
+      if (k0 == ck1) {
 #pragma unroll
-    for (int s = 0; s < N; ++s) {
-      if (needA) A[s] = a_from_b ? B[s] : plane(s, k0);
-      if (needB) B[s] = b_from_a ? A[s] : plane(s, k1);
-      const float u = lerpf(A[s].x, B[s].x, g), v = lerpf(A[s].y, B[s].y, g), d = lerpf(A[s].z, B[s].z, g);
-      // Bilinear footprint (silhouette, quality) at (u, v): lower-left texel floor(u*W - 0.5), weights (wa, wb).
-      const float uu = u * fW - 0.5f, vv = v * fH - 0.5f;
+        for (int s = 0; s < N; ++s) A[s] = B[s];
+      } else {
+#pragma unroll
+        for (int s = 0; s < N; ++s) A[s] = plane(s, k0);
+      }
+      ck0 = k0;
+    }
+    if (k1 != ck1) {
+      if (k1 == k0) {
+#pragma unroll
+        for (int s = 0; s < N; ++s) B[s] = A[s];
+      } else {
+#pragma unroll
+        for (int s = 0; s < N; ++s) B[s] = plane(s, k1);
+      }
+      ck1 = k1;
+    }
+    float weighted_tsd = limit, total_weight = 0.0f;
+
+    // z filter tap, bilinear footprint (silhouette, quality) at (u, v) and the gather loads for sensor s
+    auto fetch = [&](int s) -> Tap {
+      Tap t;
+      const float u = fmaf(g, B[s].x, omg * A[s].x), v = fmaf(g, B[s].y, omg * A[s].y);
+      t.d = fmaf(g, B[s].z, omg * A[s].z);
+      // lower-left texel floor(u*W - 0.5), weights (wa, wb)
+      const float uu = u * p.fW - 0.5f, vv = v * p.fH - 0.5f;
       const float fu = floorf(uu), fv = floorf(vv);
-      const float wa = uu - fu, wb = vv - fv;
+      t.wa = uu - fu; t.wb = vv - fv;
       // gather-texel index = clamp(footprint, -1, W-1) + 1; fmaxf/fminf drop a NaN operand, so NaN -> entry 0
-      const int ex = (int)fminf(fmaxf(fu, -1.0f), exmax) + 1, ey = (int)fminf(fmaxf(fv, -1.0f), eymax) + 1;
+      const int ex = (int)fminf(fmaxf(fu, -1.0f), p.exmax) + 1, ey = (int)fminf(fmaxf(fv, -1.0f), p.eymax) + 1;
       const float4* g4 = p.gather + ((unsigned)s * gstride + ((unsigned)ey * grow + (unsigned)ex) * 2u);
-      const float4 lo = __ldg(g4), hi = __ldg(g4 + 1);
+      t.lo = __ldg(g4); t.hi = __ldg(g4 + 1);
+      return t;
+    };
+    // tsdf_integration.vs:30-55 for one sensor
+    auto fuse = [&](const Tap& t) {
       // silhouette < 1 ? The four taps are exactly 0 or 1 (sign bits of hi). lerp(1,1,t) == 1 and lerp(0,0,t) == 0
       // exactly for every finite t, so uniform footprints need no arithmetic; NaN weights compare false either way.
-      const uint32_t bx = __float_as_uint(hi.x), by = __float_as_uint(hi.y), bz = __float_as_uint(hi.z), bw = __float_as_uint(hi.w);
+      const uint32_t bx = __float_as_uint(t.hi.x), by = __float_as_uint(t.hi.y), bz = __float_as_uint(t.hi.z), bw = __float_as_uint(t.hi.w);
       const uint32_t all1 = (bx & by & bz & bw) >> 31, any1 = (bx | by | bz | bw) >> 31;
       bool sil_lt1;
       if (all1) {
         sil_lt1 = false;
       } else if (!any1) {
-        sil_lt1 = (wa == wa) && (wb == wb);
+        sil_lt1 = (t.wa == t.wa) && (t.wb == t.wb);
       } else {
         const float s00 = (int)bx < 0 ? 1.0f : 0.0f, s10 = (int)by < 0 ? 1.0f : 0.0f;
         const float s01 = (int)bz < 0 ? 1.0f : 0.0f, s11 = (int)bw < 0 ? 1.0f : 0.0f;
-        sil_lt1 = lerpf(lerpf(s00, s10, wa), lerpf(s01, s11, wa), wb) < 1.0f;
+        sil_lt1 = lerpf(lerpf(s00, s10, t.wa), lerpf(s01, s11, t.wa), t.wb) < 1.0f;
       }
-      if (sil_lt1 && weighted_tsd >= limit) { weighted_tsd = -limit; continue; }
+      if (sil_lt1 && weighted_tsd >= limit) { weighted_tsd = neg_limit; return; }
       // NEAREST depth tap = upper tap of the footprint iff the bilinear weight is >= 0.5 (floor(t) == floor(t-0.5)+1);
       // where the subtraction t-0.5 can round (t < 0.5) both taps are the same clamped texel.
-      const bool selx = wa >= 0.5f, sely = wb >= 0.5f;
-      const float depth = sely ? (selx ? lo.w : lo.z) : (selx ? lo.y : lo.x);
-      const float sdist = d - depth;
-      if (sdist <= -limit) {
-        weighted_tsd = -limit;
+      const bool selx = t.wa >= 0.5f, sely = t.wb >= 0.5f;
+      const float depth = sely ? (selx ? t.lo.w : t.lo.z) : (selx ? t.lo.y : t.lo.x);
+      const float sdist = t.d - depth;
+      if (sdist <= neg_limit) {
+        weighted_tsd = neg_limit;
       } else if (sdist >= limit) {
       } else {
-        const float q00 = fabsf(hi.x), q10 = fabsf(hi.y), q01 = fabsf(hi.z), q11 = fabsf(hi.w);
-        const float w = lerpf(lerpf(q00, q10, wa), lerpf(q01, q11, wa), wb);
+        const float q00 = fabsf(t.hi.x), q10 = fabsf(t.hi.y), q01 = fabsf(t.hi.z), q11 = fabsf(t.hi.w);
+        const float w = lerpf(lerpf(q00, q10, t.wa), lerpf(q01, q11, t.wa), t.wb);
         weighted_tsd = (weighted_tsd * total_weight + w * sdist) / (total_weight + w);
         total_weight += w;
       }
+    };
+    // two sensors' gathers are in flight before the first decision chain runs
+#pragma unroll
+    for (int s = 0; s + 1 < N; s += 2) {
+      const Tap t0 = fetch(s), t1 = fetch(s + 1);
+      fuse(t0);
+      fuse(t1);
     }
-    ck0 = k0; ck1 = k1;
+    if (N & 1) { const Tap t = fetch(N - 1); fuse(t); }
     p.tsdf[o] = weighted_tsd;
     if (WEIGHT) p.weight[o] = total_weight;
   }
@@ -167,45 +219,64 @@ struct FusedParams {
   int mask_words, nby;
   uint32_t* work;              // [0] compute items handed out, [1] fill items handed out
   int max_cols, max_nz, zchunk, n_zchunks;
-  int fill_rows; uint32_t fill_items; uint32_t row_begin, row_end;
+  int fill_rows; uint32_t fill_items; uint32_t row_begin, row_end;   // fill_rows <= 32
   int fill_warps;
   float fill_value;
 };
 
+// One fill item: rows [row0, row1), at most 32. Lane r classifies row row0 + r (which brick rows cover it, does any of
+// them hold an occupied brick); rows without occupied bricks are streamed with 16-byte stores, the others consult the
+// row bitmask per 4-voxel group.
 template <bool WEIGHT>
 __device__ __forceinline__ void fill_rows(const FusedParams& p, uint32_t row0, uint32_t row1, int lane) {
   const int X = p.ip.X, Y = p.ip.Y;
   const float4 v4 = make_float4(p.fill_value, p.fill_value, p.fill_value, p.fill_value);
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
   const bool vec = (X & 3) == 0;
-  for (uint32_t row = row0; row < row1; ++row) {
+  int br0 = -1, br1 = -1, br2 = -1, br3 = -1;
+  bool any = false;
+  if (row0 + (uint32_t)lane < row1) {
+    const uint32_t row = row0 + (uint32_t)lane;
     const int z = (int)(row / (uint32_t)Y), y = (int)(row - (uint32_t)z * (uint32_t)Y);
     const int cy0 = p.cand_y[2 * y], cy1 = p.cand_y[2 * y + 1], cz0 = p.cand_z[2 * z], cz1 = p.cand_z[2 * z + 1];
-    // brick rows that contain this voxel row (at most 2 x 2)
-    int br[4];
-    br[0] = (cy0 >= 0 && cz0 >= 0) ? cz0 * p.nby + cy0 : -1;
-    br[1] = (cy1 >= 0 && cz0 >= 0) ? cz0 * p.nby + cy1 : -1;
-    br[2] = (cy0 >= 0 && cz1 >= 0) ? cz1 * p.nby + cy0 : -1;
-    br[3] = (cy1 >= 0 && cz1 >= 0) ? cz1 * p.nby + cy1 : -1;
-    bool any = false;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) any = any || (br[k] >= 0 && p.rowany[br[k]] != 0);
-    float* trow = p.ip.tsdf + (size_t)row * X;
-    float* wrow = WEIGHT ? p.ip.weight + (size_t)row * X : nullptr;
+    br0 = (cy0 >= 0 && cz0 >= 0) ? cz0 * p.nby + cy0 : -1;
+    br1 = (cy1 >= 0 && cz0 >= 0) ? cz0 * p.nby + cy1 : -1;
+    br2 = (cy0 >= 0 && cz1 >= 0) ? cz1 * p.nby + cy0 : -1;
+    br3 = (cy1 >= 0 && cz1 >= 0) ? cz1 * p.nby + cy1 : -1;
+    any = (br0 >= 0 && p.rowany[br0]) || (br1 >= 0 && p.rowany[br1]) || (br2 >= 0 && p.rowany[br2]) || (br3 >= 0 && p.rowany[br3]);
+  }
+  const uint32_t anymask = __ballot_sync(0xffffffffu, any);
+  const int nrows = (int)(row1 - row0);
+  for (int r = 0; r < nrows; ++r) {
+    float* trow = p.ip.tsdf + (size_t)(row0 + (uint32_t)r) * X;
+    float* wrow = WEIGHT ? p.ip.weight + (size_t)(row0 + (uint32_t)r) * X : nullptr;
+    if (!((anymask >> r) & 1u)) {
+      if (vec) {
+        for (int x4 = lane; x4 * 4 < X; x4 += 32) {
+          __stcs(reinterpret_cast<float4*>(trow) + x4, v4);
+          if (WEIGHT) __stcs(reinterpret_cast<float4*>(wrow) + x4, z4);
+        }
+      } else {
+        for (int x = lane; x < X; x += 32) { trow[x] = p.fill_value; if (WEIGHT) wrow[x] = 0.0f; }
+      }
+      continue;
+    }
+    const int b0 = __shfl_sync(0xffffffffu, br0, r), b1 = __shfl_sync(0xffffffffu, br1, r);
+    const int b2 = __shfl_sync(0xffffffffu, br2, r), b3 = __shfl_sync(0xffffffffu, br3, r);
     for (int chunk = 0; chunk * 1024 < X; ++chunk) {
       uint32_t comb = 0;
-      if (any) {
-        const int w = chunk * 32 + lane;
-        if (w < p.mask_words) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) if (br[k] >= 0) comb |= __ldg(p.rowmask + (size_t)br[k] * p.mask_words + w);
-        }
+      const int w = chunk * 32 + lane;
+      if (w < p.mask_words) {
+        if (b0 >= 0) comb |= __ldg(p.rowmask + (size_t)b0 * p.mask_words + w);
+        if (b1 >= 0) comb |= __ldg(p.rowmask + (size_t)b1 * p.mask_words + w);
+        if (b2 >= 0) comb |= __ldg(p.rowmask + (size_t)b2 * p.mask_words + w);
+        if (b3 >= 0) comb |= __ldg(p.rowmask + (size_t)b3 * p.mask_words + w);
       }
       const int xbase = chunk * 1024;
       if (vec) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const uint32_t word = any ? __shfl_sync(0xffffffffu, comb, j * 4 + (lane >> 3)) : 0u;
+          const uint32_t word = __shfl_sync(0xffffffffu, comb, j * 4 + (lane >> 3));
           const int x = xbase + (j * 32 + lane) * 4;
           if (x >= X) continue;
           const uint32_t nib = (word >> ((lane & 7) * 4)) & 15u;
@@ -220,7 +291,7 @@ __device__ __forceinline__ void fill_rows(const FusedParams& p, uint32_t row0, u
         }
       } else {
         for (int i = 0; i < 32; ++i) {
-          const uint32_t word = any ? __shfl_sync(0xffffffffu, comb, i) : 0u;
+          const uint32_t word = __shfl_sync(0xffffffffu, comb, i);
           const int x = xbase + i * 32 + lane;
           if (x >= X) continue;
           if (!((word >> lane) & 1u)) { trow[x] = p.fill_value; if (WEIGHT) wrow[x] = 0.0f; }
@@ -230,15 +301,14 @@ __device__ __forceinline__ void fill_rows(const FusedParams& p, uint32_t row0, u
   }
 }
 
-#ifndef RR_FUSED_THREADS
-#define RR_FUSED_THREADS 512
-#endif
-template <int N, bool WEIGHT>
-__global__ void __launch_bounds__(RR_FUSED_THREADS, 2) k_integrate_fused(const __grid_constant__ FusedParams p) {
+// THREADS = 512 caps the kernel at 64 registers (32 warps/SM), 384 at 85 registers (24 warps/SM).
+template <int N, bool WEIGHT, int THREADS>
+__global__ void __launch_bounds__(THREADS, 2) k_integrate_fused(const __grid_constant__ FusedParams p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned n_occ = *p.ip.num_occupied;
-  const unsigned col_blocks = (n_occ * (unsigned)p.max_cols + 31u) / 32u;
-  const unsigned citems = col_blocks * (unsigned)p.n_zchunks;
+  const unsigned cbpb = ((unsigned)p.max_cols + 31u) / 32u;          // 32-column blocks per brick (a warp never straddles bricks)
+  const unsigned per_brick = cbpb * (unsigned)p.n_zchunks;
+  const unsigned citems = n_occ * per_brick;
   bool filling = warp < p.fill_warps;
   for (int phase = 0; phase < 2; ++phase, filling = !filling) {
     if (filling) {
@@ -256,10 +326,8 @@ __global__ void __launch_bounds__(RR_FUSED_THREADS, 2) k_integrate_fused(const _
         if (lane == 0) it = atomicAdd(p.work, 1u);
         it = __shfl_sync(0xffffffffu, it, 0);
         if (it >= citems) break;
-        const unsigned cb = it / (unsigned)p.n_zchunks, zc = it - cb * (unsigned)p.n_zchunks;
-        const unsigned slot = cb * 32u + (unsigned)lane;
-        const unsigned b = slot / (unsigned)p.max_cols, col = slot - b * (unsigned)p.max_cols;
-        if (b >= n_occ) continue;
+        const unsigned b = it / per_brick, rem = it - b * per_brick;
+        const unsigned zc = rem / cbpb, col = (rem - zc * cbpb) * 32u + (unsigned)lane;
         const int32_t* rg = p.ip.ranges + (size_t)p.ip.occupied[b] * 6;
         const int x0 = rg[0], nx = rg[1] - rg[0], y0 = rg[2], ny = rg[3] - rg[2];
         const int zb = max(rg[4] + (int)zc * p.zchunk, p.ip.z_begin);
@@ -304,7 +372,7 @@ static int launch_n(rr_ctx* c, const IntegrateParams& p, bool bricks, bool weigh
       f.mask_words = c->mask_words; f.nby = (int)c->bricks.res[1];
       f.work = c->d_work;
       f.max_cols = max_cols; f.max_nz = max_nz; f.n_zchunks = n_zchunks; f.zchunk = (max_nz + n_zchunks - 1) / n_zchunks;
-      static const int fill_rows = getenv("RR_FUSED_FILL_ROWS") ? atoi(getenv("RR_FUSED_FILL_ROWS")) : 32;
+      static const int fill_rows = std::min(32, std::max(1, getenv("RR_FUSED_FILL_ROWS") ? atoi(getenv("RR_FUSED_FILL_ROWS")) : 16));
       static const int fill_warps = getenv("RR_FUSED_FILL_WARPS") ? atoi(getenv("RR_FUSED_FILL_WARPS")) : 2;
       static const int ctas_per_sm = getenv("RR_FUSED_CTAS") ? atoi(getenv("RR_FUSED_CTAS")) : 2;
       f.fill_rows = fill_rows; f.fill_warps = fill_warps;
@@ -313,8 +381,10 @@ static int launch_n(rr_ctx* c, const IntegrateParams& p, bool bricks, bool weigh
       f.fill_value = -p.limit;
       cudaMemsetAsync(c->d_work, 0, 4 * sizeof(uint32_t), c->stream);
       const dim3 grd(148 * ctas_per_sm, 1, 1);
-      if (weight) k_integrate_fused<N, true><<<grd, RR_FUSED_THREADS, 0, c->stream>>>(f);
-      else k_integrate_fused<N, false><<<grd, RR_FUSED_THREADS, 0, c->stream>>>(f);
+      static const int threads = getenv("RR_FUSED_THREADS") ? atoi(getenv("RR_FUSED_THREADS")) : 512;
+      if (weight) k_integrate_fused<N, true, 384><<<grd, 384, 0, c->stream>>>(f);
+      else if (threads == 384) k_integrate_fused<N, false, 384><<<grd, 384, 0, c->stream>>>(f);
+      else k_integrate_fused<N, false, 512><<<grd, 512, 0, c->stream>>>(f);
       RR_LAUNCH_CHECK(c, "k_integrate_fused");
       return RR_OK;
     }
@@ -348,6 +418,15 @@ int launch_integrate(rr_ctx* c) {
   p.W = c->W; p.H = c->H; p.X = (int)c->res[0]; p.Y = (int)c->res[1]; p.Z = (int)c->res[2];
   p.z_begin = (int)c->slab_z0; p.z_end = (int)c->slab_z1;
   p.z_chunk = 32;
+  p.fW = (float)c->W; p.fH = (float)c->H; p.exmax = (float)(c->W - 1); p.eymax = (float)(c->H - 1);
+  if (!c->d_ztab || c->ztab_Z != p.Z || c->ztab_IZ != p.IZ) {
+    if (c->d_ztab) { cudaStreamSynchronize(c->stream); cudaFree(c->d_ztab); c->d_ztab = nullptr; }
+    if (cudaMalloc((void**)&c->d_ztab, sizeof(float4) * (size_t)p.Z) != cudaSuccess) return fail(c, RR_ERR_CUDA, "integrate: z table allocation failed");
+    k_build_ztab<<<(p.Z + 127) / 128, 128, 0, c->stream>>>(c->d_ztab, p.Z, p.IZ);
+    RR_LAUNCH_CHECK(c, "k_build_ztab");
+    c->ztab_Z = p.Z; c->ztab_IZ = p.IZ;
+  }
+  p.ztab = c->d_ztab;
   p.limit = c->cfg.limit;
   const bool weight = c->cfg.store_weight != 0;
   const bool bricks = c->cfg.use_bricks != 0;
