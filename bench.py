@@ -125,10 +125,11 @@ def run_ours(args):
     res = fu.volume_res()
     assert tuple(int(v) for v in res) == (R, R, R), res
     # z-slab of this rank: contiguous slices, remainder spread over the first ranks
-    base, rem = divmod(R, world)
-    z0 = rank * base + min(rank, rem)
-    z1 = z0 + base + (1 if rank < rem else 0)
+    from rrpy import multigpu
+    z0, z1 = multigpu.slab_range(rank, world, R)
     fu.set_slab(z0, z1)
+    halo = multigpu.halo(LIMIT, R) if world > 1 else 0
+    zc0, zc1 = max(0, z0 - halo), min(R, z1 + halo)          # slices this rank actually writes (slab + halo)
 
     stream = torch.cuda.ExternalStream(fu.stream(), device=dev)
     # frame sets: pinned host copies (e2e) and device copies (value)
@@ -183,11 +184,13 @@ def run_ours(args):
         fu.set_timing(1 if with_stage_timers else 0)
         fu.stage_stats("2integrate"); fu.stage_stats("1preprocess")
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = fu.launch_count()
         e0.record(stream)
         for i in range(steps):
             step(warmup + i)
         e1.record(stream)
         barrier()
+        timed.launches = fu.launch_count() - l0
         ms = e0.elapsed_time(e1)
         fu.set_timing(0)
         if world > 1:
@@ -196,10 +199,9 @@ def run_ours(args):
             ms = float(t.item())
         return ms
 
-    launches0 = fu.launch_count()
     sampler = ClockSampler(local) if rank == 0 else None
     ms_total = timed(step_device, args.steps, args.warmup, True)
-    gpu_launches = fu.launch_count() - launches0 - 0
+    gpu_launches = timed.launches
     int_ms, int_n = fu.stage_stats("2integrate")
     pre_ms, pre_n = fu.stage_stats("1preprocess")
     ms_e2e = timed(step_host, args.steps, max(3, args.warmup), False)
@@ -218,19 +220,56 @@ def run_ours(args):
     counters, occ = fu.download_bricks()
     ranges = fu.brick_ranges()
     rr = ranges[occ]
-    n_occ_vox = int(((rr[:, 1] - rr[:, 0]) * (rr[:, 3] - rr[:, 2]) * (np.clip(rr[:, 5], z0, z1) - np.clip(rr[:, 4], z0, z1)).clip(0)).sum()) if len(occ) else 0
-    kernel_launches_per_step = (fu.launch_count() - launches0) and gpu_launches / (args.steps + args.warmup)
+    n_occ_vox = int(((rr[:, 1] - rr[:, 0]) * (rr[:, 3] - rr[:, 2]) * (np.clip(rr[:, 5], zc0, zc1) - np.clip(rr[:, 4], zc0, zc1)).clip(0)).sum()) if len(occ) else 0
+
+    # the view path (reported beside the headline, not part of it): raymarch at 1280x720; for N > 1 every rank marches
+    # its slab into partial records, ONE gather brings them to rank 0, which composites
+    from rrpy import synth
+    VW, VH = 1280, 720
+    mv = synth.look_at((1.7, 1.6, 2.3), (0.0, 1.1, 0.0))
+    pr = synth.perspective(50.0, VW / VH, 0.1, 10.0)
+    records = torch.empty((VW * VH, multigpu.RECORD_FLOATS), dtype=torch.float32, device=dev)
+    gathered = torch.empty((world, VW * VH, multigpu.RECORD_FLOATS), dtype=torch.float32, device=dev) if (world > 1 and rank == 0) else None
+
+    def view_once():
+        if world == 1:
+            fu.raymarch(mv, pr, VW, VH, shade_mode=1, download=False)
+            return
+        fu.raymarch_partial(mv, pr, VW, VH, records.data_ptr(), shade_mode=1)
+        torch.cuda.current_stream(dev).wait_stream(stream)
+        out = multigpu.gather_records(dist, records, dst=0, out=gathered)
+        if rank == 0:
+            stream.wait_stream(torch.cuda.current_stream(dev))
+            fu.composite(out.data_ptr(), world, VW, VH, download=False)
+
+    for _ in range(3):
+        view_once()
+    barrier()
+    v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_views = 20
+    v0.record(stream)
+    for _ in range(n_views):
+        view_once()
+    v1.record(stream)
+    barrier()
+    view_ms = v0.elapsed_time(v1) / n_views
+    if world > 1:
+        t = torch.tensor([view_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        view_ms = float(t.item())
 
     frames_s = args.steps / (ms_total / 1e3)
     value = R ** 3 * frames_s / 1e9
     e2e_frames_s = args.steps / (ms_e2e / 1e3)
     peak, peak_src = peaks()
-    slab_frac = (z1 - z0) / R
+    slab_frac = (zc1 - zc0) / R
     if bricks:
+        # fused clear+integrate: every voxel of the slab is written once (4 B), the inverse volumes are read where occupied
+        # bricks cover them, the packed depth/quality/silhouette texels once, the brick tables once
         covered_inv = int(INV_RES[0] * INV_RES[1] * INV_RES[2] * min(1.0, n_occ_vox / max(1, R ** 3 * slab_frac)) * slab_frac)
-        abytes = (4 * R ** 3 * slab_frac + 4 * n_occ_vox + 16 * covered_inv * N_SENSORS + 16 * W * H * N_SENSORS + 4 * len(counters))
+        abytes = (4 * R ** 3 * slab_frac + 16 * covered_inv * N_SENSORS + 32 * (W + 1) * (H + 1) * N_SENSORS + 4 * len(counters))
     else:
-        abytes = 4 * R ** 3 * slab_frac + 16 * INV_RES[0] * INV_RES[1] * INV_RES[2] * N_SENSORS * slab_frac + 16 * W * H * N_SENSORS
+        abytes = 4 * R ** 3 * slab_frac + 16 * INV_RES[0] * INV_RES[1] * INV_RES[2] * N_SENSORS * slab_frac + 32 * (W + 1) * (H + 1) * N_SENSORS
     int_avg_ms = int_ms / max(1, int_n)
     achieved = abytes / (int_avg_ms / 1e3) / 1e9 if int_avg_ms > 0 else 0.0
 
@@ -249,14 +288,15 @@ def run_ours(args):
                 "h2d_bytes_per_step": int(cb + db), "d2h_bytes_per_step": 4},
         "gpu_launches": int(gpu_launches),
         "stages_ms": {"1preprocess": round(pre_ms / max(1, pre_n), 5), "2integrate": round(int_avg_ms, 5)},
-        "roofline": {"bound": "hbm", "kernel": "2integrate stage (k_fill + k_integrate_bricks)" if bricks else "k_integrate_dense",
+        "view": {"ms_per_view": round(view_ms, 4), "resolution": [VW, VH], "what": "tsdf_raymarch (shaded, brick space skipping)" + (f" per slab + 1 gather of {multigpu.RECORD_FLOATS * 4}-byte records + composite" if world > 1 else "")},
+        "roofline": {"bound": "hbm", "kernel": "k_integrate_fused (clear + occupied-brick integration, one launch = the 2integrate stage)" if bricks else "k_integrate_dense",
                      "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                      "traffic": None, "algorithmic_bytes_per_launch": int(abytes), "peak_source": peak_src},
         "clocks": clocks,
     }
     if rank == 0:
         if args.cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(scenes[0], inv, voxel, bricks, budget_s=20.0)
+            out["cpu_baseline"] = cpu_baseline(scenes[0], inv, voxel, bricks, budget_s=12.0)
         print(json.dumps(out), flush=True)
     fu.close()
     if world > 1:
@@ -285,15 +325,24 @@ def cpu_frame(scene, inv, voxel, bricks, threads, int_fraction=1.0):
 
 
 def cpu_baseline(scene, inv, voxel, bricks, budget_s):
+    """The oracle port timed on this box's host cores on a bounded sample of the same workload: whole fused frames
+    (all pixels, all occupied bricks) repeated until ~budget_s seconds of CPU work are spent."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_py as O
     cores = O.max_threads()
-    frac = 0.25
-    tp, ti, n_occ, n_sub = cpu_frame(scene, inv, voxel, True, cores, frac)
-    fps = 1.0 / (tp + ti)
+    times, tps, tis = [], [], []
+    t_start = time.perf_counter()
+    n_occ = 0
+    while True:
+        tp, ti, n_occ, _ = cpu_frame(scene, inv, voxel, True, cores, 1.0)
+        times.append(tp + ti); tps.append(tp); tis.append(ti)
+        if (time.perf_counter() - t_start >= budget_s and len(times) >= 2) or len(times) >= 200:
+            break
+    fps = 1.0 / float(np.mean(times))
     return {"value": round(R ** 3 * fps / 1e9, 5), "unit": "Gvoxel-updates/s", "frames_per_s": round(fps, 4), "cores": cores, "kind": "port",
-            "sample": f"one 4-sensor frame set at {R}^3: all 5 pre-process passes on every pixel ({tp:.2f} s) + brick integration of "
-                      f"{n_sub} of {n_occ} occupied bricks scaled to all ({ti:.2f} s); oracle port (-O2, OpenMP), bricks mode"}
+            "sample": f"{len(times)} whole 4-sensor frame sets at {R}^3 ({sum(times):.1f} s of wall time on {cores} threads): per frame all 5 "
+                      f"pre-process passes on every pixel ({np.mean(tps) * 1e3:.0f} ms) + brick integration of all {n_occ} occupied bricks "
+                      f"({np.mean(tis) * 1e3:.0f} ms); oracle port (-O2, OpenMP), bricks mode"}
 
 
 def run_reference(args):
@@ -306,7 +355,7 @@ def run_reference(args):
     import oracle_py as O
     scenes, inv, voxel = make_inputs()
     cores = O.max_threads()
-    frac = 1.0 / 8.0
+    frac = 1.0
     times = []
     n_occ = n_sub = 0
     total = args.warmup + args.steps

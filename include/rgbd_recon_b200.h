@@ -103,7 +103,8 @@ int rr_get_volume_res(const rr_ctx* ctx, uint32_t res[3]);
 int rr_get_brick_info(const rr_ctx* ctx, uint32_t res_bricks[3], float* brick_size, uint32_t* num_bricks);
 /* Per-brick voxel ranges int32 [num_bricks][6] = x0,x1,y0,y1,z0,z1 (VolumeSampler::containedVoxels). */
 int rr_get_brick_ranges(const rr_ctx* ctx, int32_t* out);
-/* Multi-GPU: this context integrates/raymarches only voxel slices z in [z0, z1). Default: all. */
+/* Multi-GPU: this context owns voxel slices z in [z0, z1): it raymarches only samples whose nearest z
+ * texel it owns and integrates its slab plus a read-only halo of ceil(limit * Z) + 2 slices. Default: the whole volume. */
 int rr_set_slab(rr_ctx* ctx, uint32_t z0, uint32_t z1);
 
 /* ---- per frame (NetKinectArray + ReconIntegration) -------------------------------------------------------- */
@@ -125,6 +126,15 @@ int rr_integrate(rr_ctx* ctx);
 /* ReconIntegration::drawF/draw (recon_integration.cpp:151-241) + glsl/tsdf_raymarch.fs, bricks.{vs,gs,fs}.
  * out_rgba float32 [h][w][4], out_depth float32 [h][w] (gl_FragDepth, 1.0 where no surface), both host, may be NULL. */
 int rr_raymarch(rr_ctx* ctx, const rr_view* view, float* out_rgba, float* out_depth);
+
+/* Multi-GPU view (z-slab sharding): every slab context marches its own samples and writes one 32-byte
+ * record per pixel {float rgba[4]; float depth; uint32 first_hit_step (0xFFFFFFFF none); float sample_count; float 0}
+ * into d_records (DEVICE memory, viewport w*h records). The records of all slabs are gathered (one NCCL gather) into
+ * n_parts consecutive images on the display GPU, where rr_composite keeps, per pixel, the record with the smallest
+ * step index — the hit ReconIntegration::draw would have found first — and optionally downloads colour and depth. */
+#define RR_PARTIAL_RECORD_BYTES 32
+int rr_raymarch_partial(rr_ctx* ctx, const rr_view* view, void* d_records);
+int rr_composite(rr_ctx* ctx, const void* d_records, int n_parts, int width, int height, float* out_rgba, float* out_depth);
 
 /* ---- read-back (tests, debug views) ------------------------------------------------------------------------ */
 int rr_download_tsdf(rr_ctx* ctx, float* out);

@@ -393,6 +393,18 @@ int rr_integrate(rr_ctx* c) {
   return launch_integrate(c);
 }
 
+static int ensure_view(rr_ctx* c, int w, int h) {
+  if (w == c->view_w && h == c->view_h) return RR_OK;
+  RR_TRY(check(c, cudaStreamSynchronize(c->stream), "raymarch resize sync"));
+  RR_TRY(dev_alloc(c, &c->d_rgba, (size_t)w * h, "view rgba"));
+  RR_TRY(dev_alloc(c, &c->d_zbuf, (size_t)w * h, "view depth"));
+  RR_TRY(dev_alloc(c, &c->d_nsamples, (size_t)w * h, "view samples"));
+  RR_TRY(dev_alloc(c, &c->d_pos, (size_t)w * h, "view positions"));
+  RR_TRY(dev_alloc(c, &c->d_step, (size_t)w * h, "view steps"));
+  c->view_w = w; c->view_h = h;
+  return RR_OK;
+}
+
 int rr_raymarch(rr_ctx* c, const rr_view* view, float* out_rgba, float* out_depth) {
   if (!c) return RR_ERR_INVALID;
   RR_REQUIRE(c, view, "rr_raymarch: null view");
@@ -400,19 +412,37 @@ int rr_raymarch(rr_ctx* c, const rr_view* view, float* out_rgba, float* out_dept
   RR_REQUIRE(c, view->viewport[2] > 0 && view->viewport[3] > 0, "rr_raymarch: empty viewport");
   RR_SET_DEVICE(c);
   const int w = view->viewport[2], h = view->viewport[3];
-  if (w != c->view_w || h != c->view_h) {
-    RR_TRY(check(c, cudaStreamSynchronize(c->stream), "raymarch resize sync"));
-    RR_TRY(dev_alloc(c, &c->d_rgba, (size_t)w * h, "view rgba"));
-    RR_TRY(dev_alloc(c, &c->d_zbuf, (size_t)w * h, "view depth"));
-    RR_TRY(dev_alloc(c, &c->d_nsamples, (size_t)w * h, "view samples"));
-    RR_TRY(dev_alloc(c, &c->d_pos, (size_t)w * h, "view positions"));
-    RR_TRY(dev_alloc(c, &c->d_step, (size_t)w * h, "view steps"));
-    c->view_w = w; c->view_h = h;
-  }
+  RR_TRY(ensure_view(c, w, h));
   RR_TRY(launch_raymarch(c, view));
   if (out_rgba) RR_TRY(check(c, cudaMemcpyAsync(out_rgba, c->d_rgba, (size_t)w * h * sizeof(float4), cudaMemcpyDeviceToHost, c->stream), "rgba download"));
   if (out_depth) RR_TRY(check(c, cudaMemcpyAsync(out_depth, c->d_zbuf, (size_t)w * h * sizeof(float), cudaMemcpyDeviceToHost, c->stream), "depth download"));
   if (out_rgba || out_depth) RR_TRY(check(c, cudaStreamSynchronize(c->stream), "raymarch sync"));
+  return RR_OK;
+}
+
+int rr_raymarch_partial(rr_ctx* c, const rr_view* view, void* d_records) {
+  if (!c) return RR_ERR_INVALID;
+  RR_REQUIRE(c, view && d_records, "rr_raymarch_partial: null pointer");
+  RR_TRY(require_ready(c, true));
+  RR_REQUIRE(c, view->viewport[2] > 0 && view->viewport[3] > 0, "rr_raymarch_partial: empty viewport");
+  RR_SET_DEVICE(c);
+  RR_TRY(ensure_view(c, view->viewport[2], view->viewport[3]));
+  RR_TRY(launch_raymarch(c, view));
+  return launch_pack_partial(c, (float4*)d_records);
+}
+
+int rr_composite(rr_ctx* c, const void* d_records, int n_parts, int width, int height, float* out_rgba, float* out_depth) {
+  if (!c) return RR_ERR_INVALID;
+  RR_REQUIRE(c, d_records && n_parts >= 1 && width > 0 && height > 0, "rr_composite: bad arguments");
+  RR_SET_DEVICE(c);
+  RR_TRY(ensure_view(c, width, height));
+  timer_begin(c, "composite");
+  RR_TRY(launch_composite(c, (const float4*)d_records, n_parts));
+  timer_end(c, "composite");
+  const size_t n = (size_t)width * height;
+  if (out_rgba) RR_TRY(check(c, cudaMemcpyAsync(out_rgba, c->d_rgba, n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream), "rgba download"));
+  if (out_depth) RR_TRY(check(c, cudaMemcpyAsync(out_depth, c->d_zbuf, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream), "depth download"));
+  if (out_rgba || out_depth) RR_TRY(check(c, cudaStreamSynchronize(c->stream), "composite sync"));
   return RR_OK;
 }
 

@@ -136,6 +136,8 @@ int launch_bricks_clear(rr_ctx* c);
 int launch_bricks_update(rr_ctx* c);
 int launch_integrate(rr_ctx* c);
 int launch_raymarch(rr_ctx* c, const rr_view* v);
+int launch_pack_partial(rr_ctx* c, float4* d_rec);
+int launch_composite(rr_ctx* c, const float4* d_rec, int n_parts);
 int launch_calib_invert(rr_ctx* c, int sensor, const uint32_t out_res[3], float4* d_out);
 
 // host geometry (rr_host_geom.cpp)

@@ -12,6 +12,7 @@
 #include "rr_math.cuh"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 
 namespace rr {
@@ -417,6 +418,14 @@ int launch_integrate(rr_ctx* c) {
   p.IX = (int)c->ires[0]; p.IY = (int)c->ires[1]; p.IZ = (int)c->ires[2];
   p.W = c->W; p.H = c->H; p.X = (int)c->res[0]; p.Y = (int)c->res[1]; p.Z = (int)c->res[2];
   p.z_begin = (int)c->slab_z0; p.z_end = (int)c->slab_z1;
+  if (c->slab_z0 > 0 || c->slab_z1 < c->res[2]) {
+    // a slab owner also computes a read-only halo: the raymarcher's refinement and gradient taps reach at most
+    // 2 * (limit/2) * Z voxels (+1 for the trilinear tap) past the owned samples; integration is pure, so the halo is
+    // recomputed locally instead of exchanged
+    const int halo = (int)std::ceil(c->cfg.limit * (float)c->res[2]) + 2;
+    p.z_begin = std::max(0, p.z_begin - halo);
+    p.z_end = std::min((int)c->res[2], p.z_end + halo);
+  }
   p.z_chunk = 32;
   p.fW = (float)c->W; p.fH = (float)c->H; p.exmax = (float)(c->W - 1); p.eymax = (float)(c->H - 1);
   if (!c->d_ztab || c->ztab_Z != p.Z || c->ztab_IZ != p.IZ) {

@@ -321,6 +321,47 @@ __global__ void __launch_bounds__(64) k_raymarch(const __grid_constant__ RayPara
   p.out_step[o] = hit_step;
 }
 
+// ---- multi-GPU: per-slab partial ray records and their composite -------------------------------------
+// A slab context marches only the steps whose nearest z texel it owns and reports, per pixel, a 32-byte record
+// {rgba; depth, step index of its first hit (0xFFFFFFFF = none), sample count, 0}. After ONE gather the display GPU keeps
+// the record with the smallest step index: exactly the hit the single-volume march would have found first.
+__global__ void __launch_bounds__(256) k_pack_partial(const float4* __restrict__ rgba, const float* __restrict__ depth,
+                                                      const uint32_t* __restrict__ step, const float* __restrict__ nsamp,
+                                                      float4* __restrict__ rec, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  rec[2 * i] = rgba[i];
+  rec[2 * i + 1] = make_float4(depth[i], __uint_as_float(step[i]), nsamp[i], 0.0f);
+}
+
+__global__ void __launch_bounds__(256) k_composite(const float4* __restrict__ rec, int n_parts, int n, float4* __restrict__ rgba,
+                                                   float* __restrict__ depth, uint32_t* __restrict__ step, float* __restrict__ nsamp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 best_a = rec[2 * i], best_b = rec[2 * i + 1];
+  uint32_t best_step = __float_as_uint(best_b.y);
+  for (int p = 1; p < n_parts; ++p) {
+    const float4 b = rec[((size_t)p * n + i) * 2 + 1];
+    const uint32_t st = __float_as_uint(b.y);
+    if (st < best_step) { best_step = st; best_b = b; best_a = rec[((size_t)p * n + i) * 2]; }
+  }
+  rgba[i] = best_a; depth[i] = best_b.x; step[i] = best_step; nsamp[i] = best_b.z;
+}
+
+int launch_pack_partial(rr_ctx* c, float4* d_rec) {
+  const int n = c->view_w * c->view_h;
+  k_pack_partial<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_rgba, c->d_zbuf, c->d_step, c->d_nsamples, d_rec, n);
+  RR_LAUNCH_CHECK(c, "k_pack_partial");
+  return RR_OK;
+}
+
+int launch_composite(rr_ctx* c, const float4* d_rec, int n_parts) {
+  const int n = c->view_w * c->view_h;
+  k_composite<<<(n + 255) / 256, 256, 0, c->stream>>>(d_rec, n_parts, n, c->d_rgba, c->d_zbuf, c->d_step, c->d_nsamples);
+  RR_LAUNCH_CHECK(c, "k_composite");
+  return RR_OK;
+}
+
 // ---- host side: per-frame uniforms of ReconIntegration::draw (recon_integration.cpp:183-206) ----------------------
 namespace {
 

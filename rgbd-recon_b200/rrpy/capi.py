@@ -67,6 +67,8 @@ def lib():
     L.rr_bricks_update.argtypes = [vp, u32, f32]
     L.rr_integrate.argtypes = [vp]
     L.rr_raymarch.argtypes = [vp, C.POINTER(View), f32, f32]
+    L.rr_raymarch_partial.argtypes = [vp, C.POINTER(View), vp]
+    L.rr_composite.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, f32, f32]
     L.rr_download_tsdf.argtypes = [vp, f32]
     L.rr_download_weight.argtypes = [vp, f32]
     L.rr_download_stage.argtypes = [vp, C.c_int, f32]
@@ -228,6 +230,28 @@ class Fusion:
         rgba = np.zeros((height, width, 4), np.float32)
         depth = np.zeros((height, width), np.float32)
         self._ck(self.L.rr_raymarch(self.h, C.byref(v), _f32(rgba), _f32(depth)))
+        return rgba, depth
+
+    def _view(self, modelview, projection, width, height, shade_mode):
+        v = View()
+        v.modelview[:] = [float(x) for x in np.asarray(modelview, np.float32).reshape(16)]
+        v.projection[:] = [float(x) for x in np.asarray(projection, np.float32).reshape(16)]
+        v.viewport[:] = [0, 0, int(width), int(height)]
+        v.shade_mode = int(shade_mode)
+        return v
+
+    def raymarch_partial(self, modelview, projection, width, height, d_records_ptr, shade_mode=0):
+        """Slab march into a DEVICE record buffer (width*height*32 bytes), see rr_raymarch_partial."""
+        v = self._view(modelview, projection, width, height, shade_mode)
+        self._ck(self.L.rr_raymarch_partial(self.h, C.byref(v), d_records_ptr))
+
+    def composite(self, d_records_ptr, n_parts, width, height, download=True):
+        if not download:
+            self._ck(self.L.rr_composite(self.h, d_records_ptr, n_parts, width, height, None, None))
+            return None
+        rgba = np.zeros((height, width, 4), np.float32)
+        depth = np.zeros((height, width), np.float32)
+        self._ck(self.L.rr_composite(self.h, d_records_ptr, n_parts, width, height, _f32(rgba), _f32(depth)))
         return rgba, depth
 
     def frame(self, filter_textures=True, use_processed_depth=True, refine=True, sync_bricks=False):

@@ -1,0 +1,86 @@
+"""CPU tests of the N>1 host logic: slab partition maths, and the broadcast / gather plumbing over torch.distributed
+with the gloo backend at world_size 2 (the B200 box runs the same code over NCCL)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+
+def test_slab_ranges_tile_the_volume():
+    from rrpy import multigpu as M
+    for Z in (1, 7, 128, 512, 1000):
+        for world in (1, 2, 3, 4, 8):
+            prev = 0
+            sizes = []
+            for r in range(world):
+                z0, z1 = M.slab_range(r, world, Z)
+                assert z0 == prev and z1 >= z0
+                sizes.append(z1 - z0)
+                prev = z1
+            assert prev == Z and max(sizes) - min(sizes) <= 1
+    assert M.halo(0.01, 512) == 8 and M.halo(0.01, 100) == 3
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from rrpy import multigpu as M
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # frame broadcast: rank 0 holds the frame set, everybody ends up with it
+        g = torch.Generator().manual_seed(5)
+        color_src = torch.randint(0, 255, (2, 6, 8, 3), dtype=torch.uint8, generator=g)
+        depth_src = torch.rand((2, 5, 7), generator=g)
+        color = color_src.clone() if rank == 0 else torch.zeros_like(color_src)
+        depth = depth_src.clone() if rank == 0 else torch.zeros_like(depth_src)
+        M.broadcast_frames(dist, color, depth, 0)
+        ok = bool(torch.equal(color, color_src) and torch.equal(depth, depth_src))
+        # record gather: each rank "hits" a different subset of 6 pixels at rank-dependent step indices
+        n = 6
+        rec = np.zeros((n, M.RECORD_FLOATS), np.float32)
+        steps = np.full(n, 0xFFFFFFFF, np.uint32)
+        mine = [0, 2, 4] if rank == 0 else [2, 3, 4]
+        for px in mine:
+            steps[px] = 10 + 5 * rank + (0 if px != 4 else 20 * (1 - rank))      # pixel 4: rank 1 is earlier, pixel 2: rank 0
+        rec[:, 5] = steps.view(np.float32)
+        rec[:, 0] = rank + 1                                                      # colour tags the owner
+        out = M.gather_records(dist, torch.from_numpy(rec), dst=0)
+        if rank == 0:
+            parts = out.numpy()
+            comp, win = M.composite_reference(parts)
+            q.put((ok, parts.shape, win.tolist(), comp[:, 0].tolist()))
+        else:
+            q.put((ok, None, None, None))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_broadcast_and_gather_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[0] for r in results), "broadcast did not deliver the frame set"
+    root = [r for r in results if r[1] is not None][0]
+    assert root[1] == (2, 6, 8)
+    # pixel 0: only rank 0; 1: nobody (first = rank 0); 2: rank 0 earlier; 3: only rank 1; 4: rank 1 earlier; 5: nobody
+    assert root[2] == [0, 0, 0, 1, 1, 0]
+    assert root[3] == [1.0, 1.0, 1.0, 2.0, 2.0, 1.0]
