@@ -113,7 +113,8 @@ def run_ours(args):
         dist = dist_
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
 
@@ -205,12 +206,12 @@ def run_ours(args):
     int_ms, int_n = fu.stage_stats("2integrate")
     pre_ms, pre_n = fu.stage_stats("1preprocess")
     ms_e2e = timed(step_host, args.steps, max(3, args.warmup), False)
-    # keep the GPU busy until nvidia-smi has a few samples under load (the timed region can be < 100 ms)
-    t_end = time.time() + 1.2
-    i = 0
-    while rank == 0 and sampler and time.time() < t_end:
-        step_device(i); i += 1
-        if i % 64 == 0:
+    # keep the GPU busy until nvidia-smi has a few samples under load (the timed region can be < 100 ms). Every rank
+    # runs the same number of extra steps (derived from the all-reduced step time), since steps contain collectives.
+    n_extra = int(min(20000, max(64, 1200.0 / max(1e-3, ms_total / args.steps))))
+    for i in range(n_extra):
+        step_device(i)
+        if i % 64 == 63:
             fu.synchronize()
     barrier()
     clocks = sampler.stop() if sampler else None
@@ -238,8 +239,8 @@ def run_ours(args):
         fu.raymarch_partial(mv, pr, VW, VH, records.data_ptr(), shade_mode=1)
         torch.cuda.current_stream(dev).wait_stream(stream)
         out = multigpu.gather_records(dist, records, dst=0, out=gathered)
+        stream.wait_stream(torch.cuda.current_stream(dev))      # the next march may not overwrite `records` before the gather read it
         if rank == 0:
-            stream.wait_stream(torch.cuda.current_stream(dev))
             fu.composite(out.data_ptr(), world, VW, VH, download=False)
 
     for _ in range(3):
@@ -294,13 +295,14 @@ def run_ours(args):
                      "traffic": None, "algorithmic_bytes_per_launch": int(abytes), "peak_source": peak_src},
         "clocks": clocks,
     }
-    if rank == 0:
-        if args.cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(scenes[0], inv, voxel, bricks, budget_s=12.0)
-        print(json.dumps(out), flush=True)
     fu.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+    if rank == 0:
+        if args.cpu_baseline and world == 1:
+            out["cpu_baseline"] = cpu_baseline(scenes[0], inv, voxel, bricks, budget_s=12.0)
+        print(json.dumps(out), flush=True)
 
 
 def cpu_frame(scene, inv, voxel, bricks, threads, int_fraction=1.0):

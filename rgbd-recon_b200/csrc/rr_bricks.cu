@@ -6,33 +6,39 @@
 
 namespace rr {
 
-__global__ void __launch_bounds__(1024) k_bricks_compact(const uint32_t* __restrict__ counters, uint32_t num_bricks,
-                                                         uint32_t min_voxels, uint32_t* __restrict__ occupied,
-                                                         uint32_t* __restrict__ num_occupied) {
+// Ordered compaction by one 1024-thread block: every thread owns a contiguous run of brick ids, counts its occupied
+// ones, a block-wide exclusive scan (warp shuffles + one shared-memory hop) gives its output offset, and it writes its ids
+// in ascending order. One pass over the counters, two barriers.
+__device__ void bricks_compact_block(const uint32_t* __restrict__ counters, uint32_t num_bricks, uint32_t min_voxels,
+                                     uint32_t* __restrict__ occupied, uint32_t* __restrict__ num_occupied) {
   __shared__ uint32_t warp_sums[32];
-  __shared__ uint32_t base;
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) base = 0;
-  __syncthreads();
-  for (uint32_t start = 0; start < num_bricks; start += 1024u) {
-    const uint32_t i = start + threadIdx.x;
-    const bool occ = (i < num_bricks) && (counters[i] >= min_voxels);
-    const unsigned ballot = __ballot_sync(0xffffffffu, occ);
-    const uint32_t rank_in_warp = __popc(ballot & ((1u << lane) - 1u));
-    if (lane == 0) warp_sums[warp] = __popc(ballot);
-    __syncthreads();
-    uint32_t warp_off = 0, total = 0;
-    for (unsigned w = 0; w < 32; ++w) {
-      const uint32_t s = warp_sums[w];
-      if (w < warp) warp_off += s;
-      total += s;
-    }
-    if (occ) occupied[base + warp_off + rank_in_warp] = i;
-    __syncthreads();
-    if (threadIdx.x == 0) base += total;
-    __syncthreads();
+  const uint32_t per = (num_bricks + 1023u) / 1024u;
+  const uint32_t i0 = min(threadIdx.x * per, num_bricks), i1 = min(i0 + per, num_bricks);
+  uint32_t mine = 0;
+  for (uint32_t i = i0; i < i1; ++i) mine += (counters[i] >= min_voxels) ? 1u : 0u;
+  uint32_t incl = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+    if ((int)lane >= d) incl += v;
   }
-  if (threadIdx.x == 0) *num_occupied = base;
+  if (lane == 31) warp_sums[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = warp_sums[lane];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, w, d);
+      if ((int)lane >= d) w += v;
+    }
+    warp_sums[lane] = w;                      // inclusive sums of the warp totals
+  }
+  __syncthreads();
+  uint32_t out = (warp ? warp_sums[warp - 1] : 0u) + incl - mine;
+  for (uint32_t i = i0; i < i1; ++i)
+    if (counters[i] >= min_voxels) occupied[out++] = i;
+  if (threadIdx.x == 1023) *num_occupied = warp_sums[31];
 }
 
 // Per-brick and per-brick-row masks derived from the counters (one launch):
@@ -41,11 +47,15 @@ __global__ void __launch_bounds__(1024) k_bricks_compact(const uint32_t* __restr
 //   occ_mask[b] = brick b is occupied;
 //   rowmask[bz][by][w] = bit x set iff voxel column x lies inside the x range of an occupied brick of row (by, bz);
 //   rowany[bz][by]     = the row has an occupied brick  (both read by the fused clear+integrate kernel).
-__global__ void __launch_bounds__(256) k_bricks_masks(const uint32_t* __restrict__ counters, uint32_t rx, uint32_t ry, uint32_t rz,
-                                                      uint32_t min_voxels, const int32_t* __restrict__ ranges, int mask_words,
-                                                      uint8_t* __restrict__ near_occ, uint8_t* __restrict__ occ_mask,
-                                                      uint32_t* __restrict__ rowmask, uint8_t* __restrict__ rowany) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+// Block 0 performs the ordered compaction (updateOccupiedBricks), the other blocks build the masks: one launch.
+__global__ void __launch_bounds__(1024) k_bricks_update(const uint32_t* __restrict__ counters, uint32_t num_bricks, uint32_t rx, uint32_t ry,
+                                                        uint32_t rz, uint32_t min_voxels, const int32_t* __restrict__ ranges, int mask_words,
+                                                        uint32_t* __restrict__ occupied, uint32_t* __restrict__ num_occupied,
+                                                        uint8_t* __restrict__ near_occ, uint8_t* __restrict__ occ_mask,
+                                                        uint32_t* __restrict__ rowmask, uint8_t* __restrict__ rowany) {
+  if (blockIdx.x == 0) { bricks_compact_block(counters, num_bricks, min_voxels, occupied, num_occupied); return; }
+  if (near_occ == nullptr) return;
+  const uint32_t i = (blockIdx.x - 1) * blockDim.x + threadIdx.x;
   if (i < rx * ry * rz) {
     const int bx = (int)(i % rx), by = (int)((i / rx) % ry), bz = (int)(i / (rx * ry));
     uint8_t any = 0;
@@ -80,17 +90,14 @@ int launch_bricks_clear(rr_ctx* c) {
 }
 
 int launch_bricks_update(rr_ctx* c) {
-  k_bricks_compact<<<1, 1024, 0, c->stream>>>(c->d_counters, c->bricks.num, c->cfg.min_voxels_per_brick, c->d_occupied, c->d_num_occ);
-  RR_LAUNCH_CHECK(c, "k_bricks_compact");
   const uint32_t nb = c->bricks.num;
-  if (nb == c->bricks.res[0] * c->bricks.res[1] * c->bricks.res[2]) {
-    const uint32_t rows_words = c->fused_ok ? c->bricks.res[1] * c->bricks.res[2] * (uint32_t)c->mask_words : 0u;
-    const uint32_t threads = nb > rows_words ? nb : rows_words;
-    k_bricks_masks<<<(threads + 255) / 256, 256, 0, c->stream>>>(c->d_counters, c->bricks.res[0], c->bricks.res[1], c->bricks.res[2],
-                                                             c->cfg.min_voxels_per_brick, c->d_ranges, c->mask_words, c->d_near_occ,
-                                                             c->d_occ_mask, c->fused_ok ? c->d_rowmask : nullptr, c->d_rowany);
-    RR_LAUNCH_CHECK(c, "k_bricks_masks");
-  }
+  const bool grid_ok = nb == c->bricks.res[0] * c->bricks.res[1] * c->bricks.res[2];
+  const uint32_t rows_words = (grid_ok && c->fused_ok) ? c->bricks.res[1] * c->bricks.res[2] * (uint32_t)c->mask_words : 0u;
+  const uint32_t threads = grid_ok ? (nb > rows_words ? nb : rows_words) : 0u;
+  k_bricks_update<<<1 + (threads + 1023) / 1024, 1024, 0, c->stream>>>(
+      c->d_counters, nb, c->bricks.res[0], c->bricks.res[1], c->bricks.res[2], c->cfg.min_voxels_per_brick, c->d_ranges, c->mask_words,
+      c->d_occupied, c->d_num_occ, grid_ok ? c->d_near_occ : nullptr, c->d_occ_mask, (grid_ok && c->fused_ok) ? c->d_rowmask : nullptr, c->d_rowany);
+  RR_LAUNCH_CHECK(c, "k_bricks_update");
   cudaError_t e = cudaMemcpyAsync(c->h_num_occ, c->d_num_occ, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
   return check(c, e, "bricks count copy");
 }

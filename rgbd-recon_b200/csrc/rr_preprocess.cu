@@ -81,29 +81,30 @@ __global__ void __launch_bounds__(256) k_bilateral(const float* __restrict__ dep
                                                    float2* __restrict__ out_depth, float4* __restrict__ out_lab,
                                                    int W, int H, int CW, int CH,
                                                    const __grid_constant__ SensorTables st, const __grid_constant__ DepthParams dp) {
+  // Tile of the 13x13 neighbourhoods. A sample the shader would skip because it lies outside the depth limits
+  // (is_outside, pre_depth.fs:40-42) is stored as +inf: |inf - depth| = inf exceeds every finite range threshold, so the
+  // single range comparison below also rejects it. The centre depth itself is kept in a register, untouched.
   __shared__ float tile[SM_H][SM_W];
-  __shared__ float gspace[2 * KS + 1][2 * KS + 1];
   const int layer = blockIdx.z;
   const float* img = depth_in + (size_t)layer * W * H;
   const int bx = blockIdx.x * TILE_X, by = blockIdx.y * TILE_Y;
   const int tid = threadIdx.y * TILE_X + threadIdx.x;
   const bool compress = dp.compress[layer] != 0;
+  const float cv_min = st.dmin[layer], cv_max = st.dmax[layer];
+  auto decode = [&](float d) -> float {
+    if (compress) d = (d < dp.scaled_near[layer]) ? 0.0f : (d * d + 0.15f * dp.scaled_near[layer]) * dp.scale[layer] + dp.near_[layer];
+    return d;
+  };
   for (int i = tid; i < SM_W * SM_H; i += TILE_X * TILE_Y) {
     int ty = i / SM_W, tx = i - ty * SM_W;
-    float d = img[(size_t)iclamp(by + ty - KS, 0, H - 1) * W + iclamp(bx + tx - KS, 0, W - 1)];
-    if (compress) d = (d < dp.scaled_near[layer]) ? 0.0f : (d * d + 0.15f * dp.scaled_near[layer]) * dp.scale[layer] + dp.near_[layer];
-    tile[ty][tx] = d;
-  }
-  if (tid < (2 * KS + 1) * (2 * KS + 1)) {
-    int y = tid / (2 * KS + 1) - KS, x = tid % (2 * KS + 1) - KS;
-    gspace[y + KS][x + KS] = 1.0f - sqrtf((float)(x * x + y * y)) * (1.0f / 6.0f);
+    const float d = decode(img[(size_t)iclamp(by + ty - KS, 0, H - 1) * W + iclamp(bx + tx - KS, 0, W - 1)]);
+    tile[ty][tx] = ((d < cv_min) || (d > cv_max)) ? __int_as_float(0x7f800000) : d;
   }
   __syncthreads();
   const int px = bx + threadIdx.x, py = by + threadIdx.y;
   if (px >= W || py >= H) return;
-  const float cv_min = st.dmin[layer], cv_max = st.dmax[layer];
   const float tcx = ((float)px + 0.5f) / (float)W, tcy = ((float)py + 0.5f) / (float)H;
-  const float depth = tile[threadIdx.y + KS][threadIdx.x + KS];
+  const float depth = decode(img[(size_t)py * W + px]);
   const float depth_norm = (depth - cv_min) / (cv_max - cv_min);
   const float3 pos_world = tex3d_xyz(st.xyz[layer], st.cx[layer], st.cy[layer], st.cz[layer], tcx, tcy, depth_norm);
   const bool in_box = pos_world.x >= dp.bmin[0] && pos_world.y >= dp.bmin[1] && pos_world.z >= dp.bmin[2] &&
@@ -119,18 +120,40 @@ __global__ void __launch_bounds__(256) k_bilateral(const float* __restrict__ dep
   const float dist_range_max = 0.35f * d_dmax;
   const float dist_range_max_inv = 1.0f / dist_range_max;
   float depth_bf = 0.0f, w = 0.0f, w_range = 0.0f;
-#pragma unroll 1
-  for (int y = 0; y <= 2 * KS; ++y) {
+  if (depth - depth == 0.0f) {
+    // finite centre (always, for real frames): one comparison per tap; the space weights 1 - |offset|/6 fold to constants
 #pragma unroll
-    for (int x = 0; x <= 2 * KS; ++x) {
-      const float depth_s = tile[threadIdx.y + y][threadIdx.x + x];
-      const float depth_range = fabsf(depth_s - depth);
-      if ((depth_s < cv_min) || (depth_s > cv_max) || (depth_range > dist_range_max)) continue;
-      const float gauss_range = 1.0f - gmin(depth_range, dist_range_max) * dist_range_max_inv;
-      const float w_s = gspace[y][x] * gauss_range;
-      depth_bf = fmaf(w_s, depth_s, depth_bf);
-      w += w_s;
-      w_range += gauss_range;
+    for (int y = -KS; y <= KS; ++y) {
+#pragma unroll
+      for (int x = -KS; x <= KS; ++x) {
+        const float depth_s = tile[threadIdx.y + KS + y][threadIdx.x + KS + x];
+        const float depth_range = fabsf(depth_s - depth);
+        if (depth_range > dist_range_max) continue;
+        // min(depth_range, dist_range_max) == depth_range here (pre_depth.fs:112)
+        const float gauss_range = 1.0f - depth_range * dist_range_max_inv;
+        const float gauss_space = 1.0f - sqrtf((float)(x * x + y * y)) * (1.0f / 6.0f);
+        const float w_s = gauss_space * gauss_range;
+        depth_bf = fmaf(w_s, depth_s, depth_bf);
+        w += w_s;
+        w_range += gauss_range;
+      }
+    }
+  } else {
+    // inf / NaN centre: keep the shader's literal predicate order
+#pragma unroll 1
+    for (int y = -KS; y <= KS; ++y) {
+#pragma unroll 1
+      for (int x = -KS; x <= KS; ++x) {
+        const float depth_s = decode(img[(size_t)iclamp(py + y, 0, H - 1) * W + iclamp(px + x, 0, W - 1)]);
+        const float depth_range = fabsf(depth_s - depth);
+        if ((depth_s < cv_min) || (depth_s > cv_max) || (depth_range > dist_range_max)) continue;
+        const float gauss_range = 1.0f - gmin(depth_range, dist_range_max) * dist_range_max_inv;
+        const float gauss_space = 1.0f - sqrtf((float)(x * x + y * y)) * (1.0f / 6.0f);
+        const float w_s = gauss_space * gauss_range;
+        depth_bf = fmaf(w_s, depth_s, depth_bf);
+        w += w_s;
+        w_range += gauss_range;
+      }
     }
   }
   const float filtered = depth_bf / w;
@@ -256,6 +279,7 @@ __global__ void __launch_bounds__(256) k_normal(const float2* __restrict__ depth
 __global__ void __launch_bounds__(256) k_quality(const float2* __restrict__ depth_b, const float4* __restrict__ normals,
                                                  float* __restrict__ out_quality, int W, int H,
                                                  const __grid_constant__ SensorTables st) {
+  // as in k_bilateral: samples outside (0, 1) are stored as +inf so that the range comparison alone rejects them
   __shared__ float tile[SM_H][SM_W];
   const int layer = blockIdx.z;
   const size_t base = (size_t)layer * W * H;
@@ -263,25 +287,38 @@ __global__ void __launch_bounds__(256) k_quality(const float2* __restrict__ dept
   const int tid = threadIdx.y * TILE_X + threadIdx.x;
   for (int i = tid; i < SM_W * SM_H; i += TILE_X * TILE_Y) {
     int ty = i / SM_W, tx = i - ty * SM_W;
-    tile[ty][tx] = depth_b[base + (size_t)iclamp(by + ty - KS, 0, H - 1) * W + iclamp(bx + tx - KS, 0, W - 1)].x;
+    const float d = depth_b[base + (size_t)iclamp(by + ty - KS, 0, H - 1) * W + iclamp(bx + tx - KS, 0, W - 1)].x;
+    tile[ty][tx] = ((d <= 0.0f) || (d >= 1.0f)) ? __int_as_float(0x7f800000) : d;
   }
   __syncthreads();
   const int px = bx + threadIdx.x, py = by + threadIdx.y;
   if (px >= W || py >= H) return;
   const size_t o = base + (size_t)py * W + px;
-  const float depth = tile[threadIdx.y + KS][threadIdx.x + KS];
-  if ((depth <= 0.0f) || (depth >= 1.0f)) { out_quality[o] = 0.0f; return; }
+  const float depth = depth_b[o].x;
+  if ((depth <= 0.0f) || (depth >= 1.0f)) { out_quality[o] = 0.0f; return; }     // a NaN centre passes, as in the shader
   const float dist_range_max = 0.35f * (depth / 1.0f);
   const float dist_range_max_inv = 1.0f / dist_range_max;
   float w_range = 0.0f, border = 0.0f;
-#pragma unroll 1
-  for (int y = 0; y <= 2 * KS; ++y) {
+  if (depth - depth == 0.0f) {
 #pragma unroll
-    for (int x = 0; x <= 2 * KS; ++x) {
-      const float depth_s = tile[threadIdx.y + y][threadIdx.x + x];
-      const float depth_range = fabsf(depth_s - depth);
-      if ((depth_s <= 0.0f) || (depth_s >= 1.0f) || (depth_range > dist_range_max)) { border += 1.0f; continue; }
-      w_range += 1.0f - gmin(depth_range, dist_range_max) * dist_range_max_inv;
+    for (int y = 0; y <= 2 * KS; ++y) {
+#pragma unroll
+      for (int x = 0; x <= 2 * KS; ++x) {
+        const float depth_range = fabsf(tile[threadIdx.y + y][threadIdx.x + x] - depth);
+        if (depth_range > dist_range_max) { border += 1.0f; continue; }
+        w_range += 1.0f - depth_range * dist_range_max_inv;
+      }
+    }
+  } else {
+#pragma unroll 1
+    for (int y = -KS; y <= KS; ++y) {
+#pragma unroll 1
+      for (int x = -KS; x <= KS; ++x) {
+        const float depth_s = depth_b[base + (size_t)iclamp(py + y, 0, H - 1) * W + iclamp(px + x, 0, W - 1)].x;
+        const float depth_range = fabsf(depth_s - depth);
+        if ((depth_s <= 0.0f) || (depth_s >= 1.0f) || (depth_range > dist_range_max)) { border += 1.0f; continue; }
+        w_range += 1.0f - gmin(depth_range, dist_range_max) * dist_range_max_inv;
+      }
     }
   }
   const float lateral_quality = 1.0f - border / 169.0f;
