@@ -1,0 +1,112 @@
+// fusion_playback — headless equivalent of kinect_client's init() + frame loop (source/kinect_client.cpp:194-279,
+// 572-617) for the TSDF-integration mode: plays .stream files through NetKinectArray, fuses every frame set and
+// raymarches it. Prints the TimerDatabase stage means; optionally dumps the last TSDF volume and image.
+//   fusion_playback <file.ks> --depth W H --color CW CH --streams "s0;s1;..." [--frames K] [--voxel m] [--limit l]
+//                   [--eye x y z | --matrices file] [--view W H] [--shade m] [--dump-tsdf file] [--dump-image file] [--dense]
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+
+#include "rr_host.hpp"
+
+static void look_at(const float eye[3], const float at[3], float m[16]) {          // gluLookAt, column-major
+  float f[3] = {at[0] - eye[0], at[1] - eye[1], at[2] - eye[2]};
+  float fl = std::sqrt(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]);
+  for (float& v : f) v /= fl;
+  const float up[3] = {0.f, 1.f, 0.f};
+  float s[3] = {f[1] * up[2] - f[2] * up[1], f[2] * up[0] - f[0] * up[2], f[0] * up[1] - f[1] * up[0]};
+  float sl = std::sqrt(s[0] * s[0] + s[1] * s[1] + s[2] * s[2]);
+  for (float& v : s) v /= sl;
+  const float u[3] = {s[1] * f[2] - s[2] * f[1], s[2] * f[0] - s[0] * f[2], s[0] * f[1] - s[1] * f[0]};
+  const float r[3][3] = {{s[0], s[1], s[2]}, {u[0], u[1], u[2]}, {-f[0], -f[1], -f[2]}};
+  for (int row = 0; row < 3; ++row) {
+    for (int c = 0; c < 3; ++c) m[c * 4 + row] = r[row][c];
+    m[12 + row] = -(r[row][0] * eye[0] + r[row][1] * eye[1] + r[row][2] * eye[2]);
+  }
+  m[3] = m[7] = m[11] = 0.f; m[15] = 1.f;
+}
+static void perspective(float fovy_deg, float aspect, float n, float f, float m[16]) {   // gluPerspective
+  std::memset(m, 0, sizeof(float) * 16);
+  const float t = 1.0f / std::tan(fovy_deg * 3.14159265358979f / 360.0f);
+  m[0] = t / aspect; m[5] = t; m[10] = (f + n) / (n - f); m[11] = -1.f; m[14] = 2.f * f * n / (n - f);
+}
+
+int main(int argc, char** argv) {
+  std::string ks, streams, dump_tsdf, dump_image, matrices;
+  unsigned W = 512, H = 424, CW = 1280, CH = 1080, VW = 1280, VH = 720;
+  int frames = 10, shade = 1;
+  float voxel = 0.01f, limit = 0.01f, eye[3] = {1.6f, 1.5f, 2.2f};
+  bool dense = false;
+  for (int i = 1; i < argc; ++i) {
+    auto next = [&](int k) { return std::atof(argv[i + k]); };
+    if (!std::strcmp(argv[i], "--depth")) { W = (unsigned)next(1); H = (unsigned)next(2); i += 2; }
+    else if (!std::strcmp(argv[i], "--color")) { CW = (unsigned)next(1); CH = (unsigned)next(2); i += 2; }
+    else if (!std::strcmp(argv[i], "--view")) { VW = (unsigned)next(1); VH = (unsigned)next(2); i += 2; }
+    else if (!std::strcmp(argv[i], "--eye")) { eye[0] = (float)next(1); eye[1] = (float)next(2); eye[2] = (float)next(3); i += 3; }
+    else if (!std::strcmp(argv[i], "--streams")) streams = argv[++i];
+    else if (!std::strcmp(argv[i], "--frames")) frames = std::atoi(argv[++i]);
+    else if (!std::strcmp(argv[i], "--voxel")) voxel = (float)std::atof(argv[++i]);
+    else if (!std::strcmp(argv[i], "--limit")) limit = (float)std::atof(argv[++i]);
+    else if (!std::strcmp(argv[i], "--shade")) shade = std::atoi(argv[++i]);
+    else if (!std::strcmp(argv[i], "--dump-tsdf")) dump_tsdf = argv[++i];
+    else if (!std::strcmp(argv[i], "--dump-image")) dump_image = argv[++i];
+    else if (!std::strcmp(argv[i], "--dense")) dense = true;
+    else if (!std::strcmp(argv[i], "--matrices")) matrices = argv[++i];     // 32 floats: modelview, projection (column-major)
+    else ks = argv[i];
+  }
+  if (ks.empty() || streams.empty()) { std::cerr << "usage: fusion_playback <file.ks> --streams \"a;b\" [...]" << std::endl; return 1; }
+  try {
+    using namespace kinect;
+    SceneFile sc = readSceneFile(ks);                                                  // init(): kinect_client.cpp:213-234
+    CalibrationFiles calib_files(sc.calib_filenames, W, H, CW, CH);
+    gpu::Context gpu(0, calib_files);                                                  // stands where the GL context stood
+    CalibVolumes cv(sc.calib_filenames, sc.bbox);                                      // :241
+    NetKinectArray nka(streams, "", &calib_files, &cv, true);                          // :242
+    cv.loadInverseCalibs(sc.resource_path);                                            // :248
+    ReconIntegration recon(calib_files, &cv, sc.bbox, limit, voxel);                   // :252
+    recon.setUseBricks(!dense);
+    recon.setShadeMode(shade);
+    recon.resize(VW, VH);
+    float mv[16], pr[16];
+    const float at[3] = {0.5f * (sc.bbox.getPMin()[0] + sc.bbox.getPMax()[0]), 1.1f, 0.5f * (sc.bbox.getPMin()[2] + sc.bbox.getPMax()[2])};
+    look_at(eye, at, mv);
+    perspective(50.0f, float(VW) / float(VH), 0.1f, 10.0f, pr);
+    if (!matrices.empty()) {
+      std::ifstream m(matrices, std::ios::binary);
+      m.read(reinterpret_cast<char*>(mv), sizeof(mv));
+      m.read(reinterpret_cast<char*>(pr), sizeof(pr));
+      if (!m) throw std::runtime_error("cannot read 32 floats from " + matrices);
+    }
+    recon.setViewMatrices(mv, pr);
+    TimerDatabase::instance().enable(1);
+    int done = 0;
+    while (done < frames) {                                                            // draw3d(): :583-617
+      if (!nka.update()) continue;
+      recon.clearOccupiedBricks();                                                     // process_textures(): :572-580
+      nka.processTextures();
+      recon.updateOccupiedBricks();
+      recon.integrate();
+      recon.drawF();
+      ++done;
+    }
+    std::cout << "frames " << done << " bricks " << recon.numBricks() << " occupied ratio " << recon.occupiedRatio() << " brick size " << recon.getBrickSize() << std::endl;
+    for (char const* name : {"1preprocess", "2integrate", "3recon"})
+      std::cout << name << " mean ms " << TimerDatabase::instance().mean(name) << std::endl;
+    if (!dump_tsdf.empty()) {
+      std::vector<float> tsdf;
+      recon.downloadTsdf(tsdf);
+      std::ofstream(dump_tsdf, std::ios::binary).write(reinterpret_cast<char const*>(tsdf.data()), (std::streamsize)(tsdf.size() * sizeof(float)));
+    }
+    if (!dump_image.empty()) {
+      std::ofstream o(dump_image, std::ios::binary);
+      o.write(reinterpret_cast<char const*>(recon.colorImage().data()), (std::streamsize)(recon.colorImage().size() * sizeof(float)));
+      o.write(reinterpret_cast<char const*>(recon.depthImage().data()), (std::streamsize)(recon.depthImage().size() * sizeof(float)));
+    }
+  } catch (std::exception const& e) {
+    std::cerr << "fusion_playback: " << e.what() << std::endl;
+    return 1;
+  }
+  return 0;
+}

@@ -26,6 +26,8 @@
 #include "../../include/rgbd_recon_b200.h"
 #include "mini_math.hpp"
 
+#define RR_HOST_MAX_SENSORS 8
+
 namespace kinect {
 
 // ---- framework/DataTypes.h:12-34 ---------------------------------------------------------------------------------

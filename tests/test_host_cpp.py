@@ -1,0 +1,109 @@
+"""The GL-free C++ host layer (rgbd-recon_b200/host/) and its two programs, driven the way the reference's programs are:
+.ks scene file + .cv_xyz/.cv_uv volumes + .stream files in, .cv_xyz_inv / fused volume / image out."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import bits_equal, mismatch_report
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "rgbd-recon_b200", "bin")
+
+
+def write_scene_files(d, scene, frames=None):
+    """The on-disk inputs kinect_client / calib_inverter expect."""
+    from rrpy import volume_io
+    ks = ["serverport 127.0.0.1:7000"]
+    for i in range(scene.N):
+        open(os.path.join(d, f"sensor{i}.yml"), "w").write("# parsed by the reference's KinectCalibrationFile; unused here\n")
+        volume_io.write_volume(os.path.join(d, f"sensor{i}.cv_xyz"), scene.cv_xyz[i])
+        volume_io.write_volume(os.path.join(d, f"sensor{i}.cv_uv"), scene.cv_uv[i])
+        ks.append(f"kinect sensor{i}.yml")
+    ks.append("bbx " + " ".join(repr(float(v)) for v in list(scene.bbox_min) + list(scene.bbox_max)))
+    ks_path = os.path.join(d, "scene.ks")
+    open(ks_path, "w").write("\n".join(ks) + "\n")
+    streams = []
+    for i in range(scene.N):
+        p = os.path.join(d, f"sensor{i}.stream")
+        with open(p, "wb") as f:
+            for fr in (frames or [scene]):
+                f.write(fr.color[i].tobytes())
+                f.write(fr.depth[i].tobytes())
+        streams.append(p)
+    return ks_path, streams
+
+
+def test_programs_are_built_and_report_usage():
+    for name in ("calib_inverter", "fusion_playback"):
+        exe = os.path.join(BIN, name)
+        assert os.path.exists(exe), "build first: make -C rgbd-recon_b200"
+        r = subprocess.run([exe], capture_output=True, text=True)
+        assert r.returncode == 1 and "usage" in r.stderr
+
+
+def test_scene_file_errors_are_reported(tmp_path):
+    r = subprocess.run([os.path.join(BIN, "calib_inverter"), str(tmp_path / "missing.ks")], capture_output=True, text=True)
+    assert r.returncode == 1 and "cannot open scene file" in r.stderr
+    (tmp_path / "empty.ks").write_text("serverport x\n")
+    r = subprocess.run([os.path.join(BIN, "calib_inverter"), str(tmp_path / "empty.ks")], capture_output=True, text=True)
+    assert r.returncode == 1 and "no 'kinect" in r.stderr
+
+
+def test_no_gpu_means_loud_failure(tmp_path, small_scene):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    ks, _ = write_scene_files(str(tmp_path), small_scene)
+    r = subprocess.run([os.path.join(BIN, "calib_inverter"), ks, "-s", "0.1"], capture_output=True, text=True)
+    assert r.returncode == 1 and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+def test_calib_inverter_program_matches_oracle(tmp_path, small_scene):
+    import oracle_py as O
+    from rrpy import volume_io
+    ks, _ = write_scene_files(str(tmp_path), small_scene)
+    r = subprocess.run([os.path.join(BIN, "calib_inverter"), ks, "-s", "0.05"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "using resolution 40, 44, 40" in r.stdout
+    for i in range(small_scene.N):
+        got, lim = volume_io.read_volume(str(tmp_path / f"sensor{i}.cv_xyz_inv"), 4)
+        assert lim == (0.5, 4.5)
+        want = O.calib_invert(small_scene.cv_xyz[i], small_scene.bbox_min, small_scene.bbox_max, (40, 44, 40))
+        assert bits_equal(got, want).all(), mismatch_report(f"sensor{i}.cv_xyz_inv", got, want)
+
+
+@pytest.mark.gpu
+def test_fusion_playback_program_matches_oracle(tmp_path, small_scene):
+    import oracle_py as O
+    from rrpy import synth, volume_io
+    sc = small_scene
+    ks, streams = write_scene_files(str(tmp_path), sc)
+    inv = synth.analytic_inverse(sc, (50, 55, 50))
+    for i in range(sc.N):
+        volume_io.write_volume(str(tmp_path / f"sensor{i}.cv_xyz_inv"), inv[i])
+    VW, VH = 320, 180
+    mv, pr = synth.look_at((1.6, 1.5, 2.2), (0.0, 1.1, 0.0)), synth.perspective(50.0, VW / VH, 0.1, 10.0)
+    np.concatenate([mv, pr]).astype(np.float32).tofile(str(tmp_path / "view.bin"))
+    r = subprocess.run([os.path.join(BIN, "fusion_playback"), ks, "--depth", str(sc.W), str(sc.H), "--color", str(sc.CW), str(sc.CH),
+                        "--streams", ";".join(streams), "--frames", "3", "--voxel", "0.02", "--view", str(VW), str(VH), "--shade", "1",
+                        "--matrices", str(tmp_path / "view.bin"), "--dump-tsdf", str(tmp_path / "tsdf.bin"), "--dump-image", str(tmp_path / "img.bin")],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "2integrate mean ms" in r.stdout
+    grid = O.brick_grid(sc.bbox_min, sc.bbox_max, 0.02, 0.1)
+    cams = [O.frustum(sc.cv_xyz[i])[1] for i in range(sc.N)]
+    pre = O.preprocess(sc, grid, cams)
+    occ = O.occupied_bricks(pre["bricks"], 10)
+    want = O.integrate(inv, pre, grid, 0.01, True, occ)
+    got = np.fromfile(str(tmp_path / "tsdf.bin"), np.float32).reshape(want.shape)
+    assert bits_equal(got, want).all(), mismatch_report("tsdf", got, want)
+    img = np.fromfile(str(tmp_path / "img.bin"), np.float32)
+    rgba, depth = img[:VW * VH * 4].reshape(VH, VW, 4), img[VW * VH * 4:].reshape(VH, VW)
+    rm = O.raymarch(want, 0.01, inv, sc, pre, grid, occ, mv, pr, VW, VH, 1, True)
+    assert (rm["depth"] < 1).sum() > 500
+    assert bits_equal(depth, rm["depth"]).all() and bits_equal(rgba, rm["rgba"]).all()
+    ratio = float(r.stdout.split("occupied ratio")[1].split()[0])
+    assert abs(ratio - len(occ) / grid["num_bricks"]) < 1e-6
