@@ -160,6 +160,10 @@ int rr_get_stage_ms(rr_ctx* ctx, const char* name, float* ms);
 int rr_get_stage_stats(rr_ctx* ctx, const char* name, float* total_ms, uint32_t* count);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 uint64_t rr_launch_count(const rr_ctx* ctx);
+/* Launch-shape knob of the integrator, process-wide (no reference counterpart; the reference's draw-call structure is
+ * fixed). Names: "fused", "zchunk", "fill_rows", "fill_warps", "ctas", "threads", "chunk", "brick_grid".
+ * Results never depend on these. Returns RR_ERR_INVALID for an unknown name. */
+int rr_set_tunable(const char* name, int value);
 /* Library/ABI version. */
 int rr_version(void);
 

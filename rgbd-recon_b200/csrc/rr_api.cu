@@ -582,4 +582,20 @@ int rr_get_stage_stats(rr_ctx* c, const char* name, float* total_ms, uint32_t* c
 
 uint64_t rr_launch_count(const rr_ctx* c) { return c ? c->launches : 0; }
 
+int rr_set_tunable(const char* name, int value) {
+  if (!name) return RR_ERR_INVALID;
+  Tunables& t = tunables();
+  const std::string n(name);
+  if (n == "fused") t.fused = value;
+  else if (n == "zchunk") t.zchunk = value;
+  else if (n == "fill_rows") t.fill_rows = value;
+  else if (n == "fill_warps") t.fill_warps = value;
+  else if (n == "ctas") t.ctas = value;
+  else if (n == "threads") t.threads = value;
+  else if (n == "chunk") t.chunk = value;
+  else if (n == "brick_grid") t.brick_grid = value;
+  else return RR_ERR_INVALID;
+  return RR_OK;
+}
+
 }  // extern "C"

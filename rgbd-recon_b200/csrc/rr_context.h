@@ -124,6 +124,19 @@ struct rr_ctx {
 
 namespace rr {
 
+// launch-shape knobs of the integrator, process-wide (rr_set_tunable / environment RR_*)
+struct Tunables {
+  int fused = 1;        // one persistent clear+integrate kernel (0: k_fill + k_integrate_bricks)
+  int zchunk = 13;      // voxels of a brick's z extent per compute item
+  int fill_rows = 16;   // voxel rows per fill item
+  int fill_warps = 2;   // warps of a CTA that start on fill items
+  int ctas = 2;         // resident CTAs per SM
+  int threads = 512;    // CTA size (register budget): 512 (64 registers) or 384 (85 registers)
+  int chunk = 1;        // compute items a CTA draws at a time (0: one z-chunk of one brick)
+  int brick_grid = 6;   // grid multiple of the unfused brick kernel
+};
+Tunables& tunables();
+
 int fail(rr_ctx* c, int code, const std::string& msg);
 int check(rr_ctx* c, cudaError_t e, const char* what);
 void timer_begin(rr_ctx* c, const char* name);

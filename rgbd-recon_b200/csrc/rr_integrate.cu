@@ -222,6 +222,7 @@ struct FusedParams {
   int max_cols, max_nz, zchunk, n_zchunks;
   int fill_rows; uint32_t fill_items; uint32_t row_begin, row_end;   // fill_rows <= 32
   int fill_warps;
+  int chunk;                   // compute items a CTA draws from the global counter at a time
   float fill_value;
 };
 
@@ -302,14 +303,26 @@ __device__ __forceinline__ void fill_rows(const FusedParams& p, uint32_t row0, u
   }
 }
 
+// Compute items are handed out to a CTA in chunks of `chunk` consecutive items (one global atomic per chunk) and to
+// its warps one at a time from a shared counter, so the warps of a CTA work on neighbouring column blocks of the same
+// brick at the same time: their inverse-volume corners and gather texels hit the SM's L1 instead of L2.
+// Slot protocol: the warp that draws the first index of a chunk fetches the chunk base from the global counter and
+// publishes (chunk number + 1, base) as one 64-bit word; the other warps of that chunk spin on the word.
+#define FUSED_SLOTS 8
 // THREADS = 512 caps the kernel at 64 registers (32 warps/SM), 384 at 85 registers (24 warps/SM).
 template <int N, bool WEIGHT, int THREADS>
 __global__ void __launch_bounds__(THREADS, 2) k_integrate_fused(const __grid_constant__ FusedParams p) {
+  __shared__ unsigned s_taken;
+  __shared__ unsigned long long s_slot[FUSED_SLOTS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_taken = 0;
+  if (threadIdx.x < FUSED_SLOTS) s_slot[threadIdx.x] = 0ull;
+  __syncthreads();
   const unsigned n_occ = *p.ip.num_occupied;
   const unsigned cbpb = ((unsigned)p.max_cols + 31u) / 32u;          // 32-column blocks per brick (a warp never straddles bricks)
   const unsigned per_brick = cbpb * (unsigned)p.n_zchunks;
   const unsigned citems = n_occ * per_brick;
+  const unsigned chunk = (unsigned)p.chunk;
   bool filling = warp < p.fill_warps;
   for (int phase = 0; phase < 2; ++phase, filling = !filling) {
     if (filling) {
@@ -324,7 +337,24 @@ __global__ void __launch_bounds__(THREADS, 2) k_integrate_fused(const __grid_con
     } else {
       for (;;) {
         unsigned it = 0;
-        if (lane == 0) it = atomicAdd(p.work, 1u);
+        if (lane == 0) {
+          if (chunk <= 1u) {
+            it = atomicAdd(p.work, 1u);
+          } else {
+            const unsigned i = atomicAdd(&s_taken, 1u);
+            const unsigned c = i / chunk, j = i - c * chunk;
+            volatile unsigned long long* slot = s_slot + (c % FUSED_SLOTS);
+            if (j == 0) {
+              const unsigned g = atomicAdd(p.work, chunk);
+              *slot = ((unsigned long long)(c + 1u) << 32) | g;
+              it = g;
+            } else {
+              unsigned long long v;
+              do { v = *slot; } while ((unsigned)(v >> 32) != c + 1u);
+              it = (unsigned)v + j;
+            }
+          }
+        }
         it = __shfl_sync(0xffffffffu, it, 0);
         if (it >= citems) break;
         const unsigned b = it / per_brick, rem = it - b * per_brick;
@@ -352,9 +382,28 @@ __global__ void __launch_bounds__(256) k_fill(float* __restrict__ dst, size_t n,
   for (size_t j = n4 * 4 + i; j < n; j += stride) dst[j] = value;
 }
 
+// Launch-shape knobs of the integrator (rr_set_tunable; environment RR_<NAME> gives the initial value).
+Tunables& tunables() {
+  static Tunables t = [] {
+    Tunables v;
+    auto env = [](const char* n, int d) { const char* e = getenv(n); return e ? atoi(e) : d; };
+    v.fused = env("RR_INTEGRATE_FUSED", v.fused);
+    v.zchunk = env("RR_BRICK_ZCHUNK", v.zchunk);
+    v.fill_rows = env("RR_FUSED_FILL_ROWS", v.fill_rows);
+    v.fill_warps = env("RR_FUSED_FILL_WARPS", v.fill_warps);
+    v.ctas = env("RR_FUSED_CTAS", v.ctas);
+    v.threads = env("RR_FUSED_THREADS", v.threads);
+    v.chunk = env("RR_FUSED_CHUNK", v.chunk);
+    v.brick_grid = env("RR_BRICK_GRID", v.brick_grid);
+    return v;
+  }();
+  return t;
+}
+
 template <int N>
 static int launch_n(rr_ctx* c, const IntegrateParams& p, bool bricks, bool weight, bool fused) {
   const dim3 blk(32, 8, 1);
+  const Tunables& tn = tunables();
   if (bricks) {
     int max_cols = 0, max_nz = 0;
     for (size_t i = 0; i + 5 < c->h_ranges.size(); i += 6) {
@@ -362,10 +411,9 @@ static int launch_n(rr_ctx* c, const IntegrateParams& p, bool bricks, bool weigh
       max_nz = std::max(max_nz, c->h_ranges[i + 5] - c->h_ranges[i + 4]);
     }
     if (max_cols == 0 || max_nz == 0) return RR_OK;
-    static const int zchunk_env = getenv("RR_BRICK_ZCHUNK") ? atoi(getenv("RR_BRICK_ZCHUNK")) : 0;
     if (fused) {
       // z-chunks: split a brick's z extent into pieces of ~zchunk voxels of equal size
-      const int want = zchunk_env > 0 ? zchunk_env : 13;
+      const int want = std::max(1, tn.zchunk);
       const int n_zchunks = std::max(1, (max_nz + want - 1) / want);
       FusedParams f{};
       f.ip = p;
@@ -373,18 +421,16 @@ static int launch_n(rr_ctx* c, const IntegrateParams& p, bool bricks, bool weigh
       f.mask_words = c->mask_words; f.nby = (int)c->bricks.res[1];
       f.work = c->d_work;
       f.max_cols = max_cols; f.max_nz = max_nz; f.n_zchunks = n_zchunks; f.zchunk = (max_nz + n_zchunks - 1) / n_zchunks;
-      static const int fill_rows = std::min(32, std::max(1, getenv("RR_FUSED_FILL_ROWS") ? atoi(getenv("RR_FUSED_FILL_ROWS")) : 16));
-      static const int fill_warps = getenv("RR_FUSED_FILL_WARPS") ? atoi(getenv("RR_FUSED_FILL_WARPS")) : 2;
-      static const int ctas_per_sm = getenv("RR_FUSED_CTAS") ? atoi(getenv("RR_FUSED_CTAS")) : 2;
-      f.fill_rows = fill_rows; f.fill_warps = fill_warps;
+      f.fill_rows = std::min(32, std::max(1, tn.fill_rows)); f.fill_warps = tn.fill_warps;
+      // chunk <= 0: one z-chunk of one brick (all its column blocks) per draw
+      f.chunk = tn.chunk > 0 ? tn.chunk : (max_cols + 31) / 32;
       f.row_begin = (uint32_t)p.z_begin * (uint32_t)p.Y; f.row_end = (uint32_t)p.z_end * (uint32_t)p.Y;
-      f.fill_items = (f.row_end - f.row_begin + (uint32_t)fill_rows - 1u) / (uint32_t)fill_rows;
+      f.fill_items = (f.row_end - f.row_begin + (uint32_t)f.fill_rows - 1u) / (uint32_t)f.fill_rows;
       f.fill_value = -p.limit;
       cudaMemsetAsync(c->d_work, 0, 4 * sizeof(uint32_t), c->stream);
-      const dim3 grd(148 * ctas_per_sm, 1, 1);
-      static const int threads = getenv("RR_FUSED_THREADS") ? atoi(getenv("RR_FUSED_THREADS")) : 512;
+      const dim3 grd(148 * std::min(2, std::max(1, tn.ctas)), 1, 1);
       if (weight) k_integrate_fused<N, true, 384><<<grd, 384, 0, c->stream>>>(f);
-      else if (threads == 384) k_integrate_fused<N, false, 384><<<grd, 384, 0, c->stream>>>(f);
+      else if (tn.threads == 384) k_integrate_fused<N, false, 384><<<grd, 384, 0, c->stream>>>(f);
       else k_integrate_fused<N, false, 512><<<grd, 512, 0, c->stream>>>(f);
       RR_LAUNCH_CHECK(c, "k_integrate_fused");
       return RR_OK;
@@ -396,9 +442,8 @@ static int launch_n(rr_ctx* c, const IntegrateParams& p, bool bricks, bool weigh
       const double waste = double((max_cols + t - 1) / t * t) / double(max_cols);
       if (waste < best - 1e-9 || (waste < best + 1e-9 && t > threads)) { best = waste; threads = t; }
     }
-    const int zchunk = zchunk_env > 0 ? zchunk_env : 9;
-    static const int gmult = getenv("RR_BRICK_GRID") ? atoi(getenv("RR_BRICK_GRID")) : 6;
-    const dim3 grd(148 * gmult, 1, 1);
+    const int zchunk = 9;
+    const dim3 grd(148 * std::max(1, tn.brick_grid), 1, 1);
     if (weight) k_integrate_bricks<N, true, 2><<<grd, threads, 0, c->stream>>>(p, max_cols, max_nz, zchunk);
     else k_integrate_bricks<N, false, 2><<<grd, threads, 0, c->stream>>>(p, max_cols, max_nz, zchunk);
   } else {
@@ -442,9 +487,8 @@ int launch_integrate(rr_ctx* c) {
   timer_begin(c, "2integrate");
   const size_t plane = (size_t)p.X * p.Y;
   const size_t nslab = plane * (size_t)(p.z_end - p.z_begin);
-  // RR_INTEGRATE_FUSED=0 selects the two-kernel path (k_fill, then k_integrate_bricks) for A/B measurements
-  const bool fused_env = !(getenv("RR_INTEGRATE_FUSED") && atoi(getenv("RR_INTEGRATE_FUSED")) == 0);
-  const bool fused = bricks && fused_env && c->fused_ok;
+  // tunable fused=0 selects the two-kernel path (k_fill, then k_integrate_bricks) for A/B measurements
+  const bool fused = bricks && tunables().fused != 0 && c->fused_ok;
   if (bricks && !fused && nslab) {
     // dense mode overwrites every voxel, so only the brick path needs the clear
     k_fill<<<148 * 8, 256, 0, c->stream>>>(c->d_tsdf + plane * p.z_begin, nslab, -p.limit);

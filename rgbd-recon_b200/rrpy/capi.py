@@ -81,8 +81,14 @@ def lib():
     L.rr_launch_count.argtypes = [vp]
     L.rr_launch_count.restype = C.c_uint64
     L.rr_version.restype = C.c_int
+    L.rr_set_tunable.argtypes = [C.c_char_p, C.c_int]
     _lib = L
     return L
+
+
+def set_tunable(name, value):
+    if lib().rr_set_tunable(name.encode(), int(value)) != 0:
+        raise ValueError(f"unknown tunable {name}")
 
 
 def _f32(a):
