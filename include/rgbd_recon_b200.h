@@ -108,8 +108,17 @@ int rr_get_brick_ranges(const rr_ctx* ctx, int32_t* out);
 int rr_set_slab(rr_ctx* ctx, uint32_t z0, uint32_t z1);
 
 /* ---- per frame (NetKinectArray + ReconIntegration) -------------------------------------------------------- */
-/* NetKinectArray::update (NetKinectArray.cpp:226-238): one frame set, host buffers -> device, async on the stream.
- * For full overlap pass pinned memory. color may be NULL if no colour is needed. */
+/* The reference double-buffers ingest (double_pixel_buffer.cpp:18-33,57-82): the reader thread fills the back PBO while
+ * the main thread draws from the front one, and NetKinectArray::update (NetKinectArray.cpp:226-238) swaps them. Here:
+ *   rr_stage_frames  = the reader's write: one frame set, host buffers (pinned for overlap) -> the BACK device slot,
+ *                      asynchronously on a copy stream, overlapping kernels that still read the current slot.
+ *                      color may be NULL if no colour is needed (the slot keeps its previous colour).
+ *   rr_swap_frames   = update(): the staged slot becomes current; the compute stream waits for the staged copies.
+ *   rr_stage_sync    = host wait until the staged copies have completed (the host buffers may be reused).
+ *   rr_upload_frames = rr_stage_frames + rr_swap_frames (no overlap; the simple path). */
+int rr_stage_frames(rr_ctx* ctx, const void* color, size_t color_bytes, const void* depth, size_t depth_bytes);
+int rr_swap_frames(rr_ctx* ctx);
+int rr_stage_sync(rr_ctx* ctx);
 int rr_upload_frames(rr_ctx* ctx, const void* color, size_t color_bytes, const void* depth, size_t depth_bytes);
 /* Same, but the frame set is already in device memory of this context's GPU (e.g. after an NCCL broadcast). */
 int rr_upload_frames_device(rr_ctx* ctx, const void* d_color, size_t color_bytes, const void* d_depth, size_t depth_bytes);

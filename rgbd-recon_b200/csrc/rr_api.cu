@@ -98,8 +98,14 @@ int rr_create(rr_ctx** out, int device, int num_sensors, int depth_w, int depth_
   }
   const size_t px = (size_t)c->N * c->W * c->H;
   int rc = RR_OK;
-  if (rc == RR_OK) rc = dev_alloc(c, &c->d_depth_raw, px, "depth");
-  if (rc == RR_OK) rc = dev_alloc(c, &c->d_color, (size_t)c->N * c->CW * c->CH * 3, "color");
+  for (int b = 0; b < 2; ++b) {
+    if (rc == RR_OK) rc = dev_alloc(c, &c->d_depth_slot[b], px, "depth");
+    if (rc == RR_OK) rc = dev_alloc(c, &c->d_color_slot[b], (size_t)c->N * c->CW * c->CH * 3, "color");
+    if (rc == RR_OK) rc = check(c, cudaEventCreateWithFlags(&c->ev_free[b], cudaEventDisableTiming), "event");
+  }
+  if (rc == RR_OK) rc = check(c, cudaEventCreateWithFlags(&c->ev_staged, cudaEventDisableTiming), "event");
+  if (rc == RR_OK) rc = check(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking), "copy stream");
+  c->d_depth_raw = c->d_depth_slot[0]; c->d_color = c->d_color_slot[0];
   if (rc == RR_OK) rc = dev_alloc(c, &c->d_morph, px, "morph");
   if (rc == RR_OK) rc = dev_alloc(c, &c->d_depth, px, "depth rg");
   if (rc == RR_OK) rc = dev_alloc(c, &c->d_lab, px, "lab");
@@ -115,7 +121,10 @@ int rr_create(rr_ctx** out, int device, int num_sensors, int depth_w, int depth_
   if (rc == RR_OK) {
     cudaMemsetAsync(c->d_flags, 0, 4 * sizeof(uint32_t), c->stream);
     cudaMemsetAsync(c->d_num_occ, 0, sizeof(uint32_t), c->stream);
-    cudaMemsetAsync(c->d_color, 0, (size_t)c->N * c->CW * c->CH * 3, c->stream);
+    for (int b = 0; b < 2; ++b) {
+      cudaMemsetAsync(c->d_color_slot[b], 0, (size_t)c->N * c->CW * c->CH * 3, c->stream);
+      cudaMemsetAsync(c->d_depth_slot[b], 0, px * sizeof(float), c->stream);
+    }
     *c->h_num_occ = 0;
     rc = check(c, cudaStreamSynchronize(c->stream), "create sync");
   }
@@ -127,9 +136,13 @@ int rr_create(rr_ctx** out, int device, int num_sensors, int depth_w, int depth_
 void rr_destroy(rr_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (int i = 0; i < RR_MAX_SENSORS; ++i) { cudaFree(c->d_xyz[i]); cudaFree(c->d_uv[i]); }
-  cudaFree(c->d_inv); cudaFree(c->d_depth_raw); cudaFree(c->d_color); cudaFree(c->d_morph); cudaFree(c->d_depth);
+  for (int b = 0; b < 2; ++b) { cudaFree(c->d_depth_slot[b]); cudaFree(c->d_color_slot[b]); if (c->ev_free[b]) cudaEventDestroy(c->ev_free[b]); }
+  if (c->ev_staged) cudaEventDestroy(c->ev_staged);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  cudaFree(c->d_inv); cudaFree(c->d_morph); cudaFree(c->d_depth);
   cudaFree(c->d_lab); cudaFree(c->d_depth_b); cudaFree(c->d_sil); cudaFree(c->d_normal); cudaFree(c->d_quality);
   cudaFree(c->d_gather); cudaFree(c->d_flags); cudaFree(c->d_ranges); cudaFree(c->d_counters); cudaFree(c->d_occupied);
   cudaFree(c->d_num_occ); cudaFree(c->d_work); cudaFree(c->d_ztab); cudaFree(c->d_rowmask); cudaFree(c->d_rowany); cudaFree(c->d_cand_y); cudaFree(c->d_cand_z); cudaFree(c->d_near_occ); cudaFree(c->d_occ_mask); cudaFree(c->d_pos); cudaFree(c->d_step); cudaFree(c->d_tsdf); cudaFree(c->d_weight);
@@ -148,6 +161,7 @@ const char* rr_last_error(const rr_ctx* c) { return c ? c->error.c_str() : "null
 int rr_synchronize(rr_ctx* c) {
   if (!c) return RR_ERR_INVALID;
   RR_SET_DEVICE(c);
+  RR_TRY(check(c, cudaStreamSynchronize(c->copy_stream), "synchronize (copy stream)"));
   return check(c, cudaStreamSynchronize(c->stream), "synchronize");
 }
 
@@ -330,24 +344,64 @@ int rr_set_slab(rr_ctx* c, uint32_t z0, uint32_t z1) {
   return RR_OK;
 }
 
-static int upload_frames(rr_ctx* c, const void* color, size_t cb, const void* depth, size_t db, cudaMemcpyKind kind) {
-  if (!c) return RR_ERR_INVALID;
-  RR_SET_DEVICE(c);
+static int check_frame_sizes(rr_ctx* c, const void* color, size_t cb, const void* depth, size_t db) {
   const size_t want_d = (size_t)c->N * c->W * c->H * sizeof(float);
   const size_t want_c = (size_t)c->N * c->CW * c->CH * 3;
   RR_REQUIRE(c, depth && db == want_d, "rr_upload_frames: depth must be float32 [N][H][W]");
   RR_REQUIRE(c, !color || cb == want_c, "rr_upload_frames: colour must be uint8 [N][CH][CW][3]");
-  RR_TRY(check(c, cudaMemcpyAsync(c->d_depth_raw, depth, want_d, kind, c->stream), "depth upload"));
-  if (color) RR_TRY(check(c, cudaMemcpyAsync(c->d_color, color, want_c, kind, c->stream), "colour upload"));
   return RR_OK;
 }
 
+int rr_stage_frames(rr_ctx* c, const void* color, size_t cb, const void* depth, size_t db) {
+  if (!c) return RR_ERR_INVALID;
+  RR_SET_DEVICE(c);
+  RR_TRY(check_frame_sizes(c, color, cb, depth, db));
+  const int t = c->cur_slot ^ 1;
+  // the slot may still be read by kernels launched while it was current
+  if (c->free_recorded[t]) RR_TRY(check(c, cudaStreamWaitEvent(c->copy_stream, c->ev_free[t], 0), "stage wait"));
+  RR_TRY(check(c, cudaMemcpyAsync(c->d_depth_slot[t], depth, db, cudaMemcpyHostToDevice, c->copy_stream), "depth upload"));
+  if (color) RR_TRY(check(c, cudaMemcpyAsync(c->d_color_slot[t], color, cb, cudaMemcpyHostToDevice, c->copy_stream), "colour upload"));
+  RR_TRY(check(c, cudaEventRecord(c->ev_staged, c->copy_stream), "stage record"));
+  c->staged = true;
+  return RR_OK;
+}
+
+int rr_swap_frames(rr_ctx* c) {
+  if (!c) return RR_ERR_INVALID;
+  RR_REQUIRE(c, c->staged, "rr_swap_frames: no staged frame set (call rr_stage_frames first)");
+  RR_SET_DEVICE(c);
+  const int old = c->cur_slot, t = old ^ 1;
+  RR_TRY(check(c, cudaEventRecord(c->ev_free[old], c->stream), "swap record"));
+  c->free_recorded[old] = true;
+  RR_TRY(check(c, cudaStreamWaitEvent(c->stream, c->ev_staged, 0), "swap wait"));
+  c->cur_slot = t;
+  c->d_depth_raw = c->d_depth_slot[t]; c->d_color = c->d_color_slot[t];
+  c->staged = false;
+  return RR_OK;
+}
+
+int rr_stage_sync(rr_ctx* c) {
+  if (!c) return RR_ERR_INVALID;
+  RR_SET_DEVICE(c);
+  return check(c, cudaStreamSynchronize(c->copy_stream), "stage sync");
+}
+
 int rr_upload_frames(rr_ctx* c, const void* color, size_t cb, const void* depth, size_t db) {
-  return upload_frames(c, color, cb, depth, db, cudaMemcpyHostToDevice);
+  if (!c) return RR_ERR_INVALID;
+  if (c->staged) RR_TRY(rr_swap_frames(c));     // a frame set staged earlier is superseded, but its slot must be released in order
+  RR_TRY(rr_stage_frames(c, color, cb, depth, db));
+  return rr_swap_frames(c);
 }
 
 int rr_upload_frames_device(rr_ctx* c, const void* color, size_t cb, const void* depth, size_t db) {
-  return upload_frames(c, color, cb, depth, db, cudaMemcpyDeviceToDevice);
+  if (!c) return RR_ERR_INVALID;
+  RR_SET_DEVICE(c);
+  RR_TRY(check_frame_sizes(c, color, cb, depth, db));
+  // already on this GPU (e.g. the output of an NCCL broadcast ordered before the context's stream): straight into the
+  // current slot, on the compute stream
+  RR_TRY(check(c, cudaMemcpyAsync(c->d_depth_raw, depth, db, cudaMemcpyDeviceToDevice, c->stream), "depth upload"));
+  if (color) RR_TRY(check(c, cudaMemcpyAsync(c->d_color, color, cb, cudaMemcpyDeviceToDevice, c->stream), "colour upload"));
+  return RR_OK;
 }
 
 static int require_ready(rr_ctx* c, bool need_inv) {

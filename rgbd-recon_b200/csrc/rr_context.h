@@ -72,9 +72,18 @@ struct rr_ctx {
   uint32_t ires[3] = {0, 0, 0};
   bool have_inv[RR_MAX_SENSORS] = {};
 
-  // frames + stages
+  // frames + stages. Two device frame slots (the reference's double PBO, double_pixel_buffer.cpp): d_depth_raw / d_color
+  // alias the CURRENT slot (read by the kernels); rr_stage_frames copies into the other one on copy_stream.
   float* d_depth_raw = nullptr;
   uint8_t* d_color = nullptr;
+  float* d_depth_slot[2] = {nullptr, nullptr};
+  uint8_t* d_color_slot[2] = {nullptr, nullptr};
+  int cur_slot = 0;
+  bool staged = false;                       // the other slot holds a frame set that has not been swapped in yet
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_staged = nullptr;           // recorded on copy_stream after the staged copies
+  cudaEvent_t ev_free[2] = {nullptr, nullptr};   // recorded on stream when a slot stops being current
+  bool free_recorded[2] = {false, false};
   float* d_morph = nullptr;
   float2* d_depth = nullptr;
   float4* d_lab = nullptr;

@@ -154,9 +154,14 @@ NetKinectArray::~NetKinectArray() {
 
 void NetKinectArray::pushFrame(void const* color, void const* depth) {
   std::lock_guard<std::mutex> lock(m_mutex_pbo);
+  // the reader's side of the double buffer: fill the back pinned buffer and start its copy into the back device slot;
+  // the copy overlaps whatever the main thread is still computing on the current slot
+  ck(rr_stage_sync(ctx()), "rr_stage_sync");          // the copy that last read this pinned buffer pair has finished
   uint8_t* dst = m_staging[m_back];
   std::memcpy(dst, color, m_colorsize * m_numLayers);
   std::memcpy(dst + m_colorsize * m_numLayers, depth, m_depthsize * m_numLayers);
+  ck(rr_stage_frames(ctx(), dst, m_colorsize * m_numLayers, dst + m_colorsize * m_numLayers, m_depthsize * m_numLayers), "rr_stage_frames");
+  m_back ^= 1;
   m_dirty = true;
   ++m_num_frame;
 }
@@ -195,11 +200,8 @@ void NetKinectArray::readFromFiles() {
 bool NetKinectArray::update() {
   std::lock_guard<std::mutex> lock(m_mutex_pbo);
   if (!m_dirty) return false;
-  // the previous upload from the other buffer has completed (single stream), so the producer may reuse it after the swap
-  uint8_t const* src = m_staging[m_back];
-  ck(rr_upload_frames(ctx(), src, m_colorsize * m_numLayers, src + m_colorsize * m_numLayers, m_depthsize * m_numLayers), "rr_upload_frames");
-  ck(rr_synchronize(ctx()), "rr_synchronize");
-  m_back ^= 1;
+  // swapBuffers (NetKinectArray.cpp:229-236): the staged device slot becomes the one the kernels read
+  ck(rr_swap_frames(ctx()), "rr_swap_frames");
   m_dirty = false;
   return true;
 }

@@ -62,6 +62,9 @@ def lib():
     L.rr_set_slab.argtypes = [vp, C.c_uint32, C.c_uint32]
     L.rr_upload_frames.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t]
     L.rr_upload_frames_device.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t]
+    L.rr_stage_frames.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t]
+    L.rr_swap_frames.argtypes = [vp]
+    L.rr_stage_sync.argtypes = [vp]
     L.rr_bricks_clear.argtypes = [vp]
     L.rr_preprocess.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.rr_bricks_update.argtypes = [vp, u32, f32]
@@ -205,6 +208,16 @@ class Fusion:
     def upload_frames_ptr(self, color_ptr, color_bytes, depth_ptr, depth_bytes, device=False):
         f = self.L.rr_upload_frames_device if device else self.L.rr_upload_frames
         self._ck(f(self.h, color_ptr, color_bytes, depth_ptr, depth_bytes))
+
+    def stage_frames_ptr(self, color_ptr, color_bytes, depth_ptr, depth_bytes):
+        """Async copy of a (pinned) host frame set into the back device slot; see rr_stage_frames."""
+        self._ck(self.L.rr_stage_frames(self.h, color_ptr, color_bytes, depth_ptr, depth_bytes))
+
+    def swap_frames(self):
+        self._ck(self.L.rr_swap_frames(self.h))
+
+    def stage_sync(self):
+        self._ck(self.L.rr_stage_sync(self.h))
 
     def bricks_clear(self):
         self._ck(self.L.rr_bricks_clear(self.h))

@@ -96,3 +96,46 @@ def test_frame_inverse_finer_than_volume(small_scene):
     # reference default: 1 cm voxels over a 7 mm inverse volume (coarse cells smaller than voxels)
     got, want = _run_both(small_scene, 0.03, (96, 100, 90), use_bricks=False)
     _assert_frame(got, want)
+
+
+def test_staged_ingest_double_buffer(small_scene):
+    """rr_stage_frames / rr_swap_frames (the double PBO of double_pixel_buffer.cpp): a staged frame set must not be
+    visible before the swap, and a pipelined sequence must give the same volumes as plain uploads."""
+    import torch
+    from rrpy import capi, synth
+    scene = small_scene
+    scene2 = synth.rerender(scene, 11)
+    inv = synth.analytic_inverse(scene, (40, 44, 40))
+
+    def tsdf_plain(sc):
+        fu = capi.Fusion(sc.N, sc.W, sc.H, sc.CW, sc.CH)
+        capi.load_scene(fu, scene, inv)
+        fu.configure(limit=0.01, voxel_size=0.025, brick_size=0.1, min_voxels=10, use_bricks=True)
+        fu.upload_frames(sc.color, sc.depth)
+        fu.frame(sync_bricks=True)
+        out = fu.download_tsdf()
+        fu.close()
+        return out
+
+    want1, want2 = tsdf_plain(scene), tsdf_plain(scene2)
+    assert not np.array_equal(want1.view(np.uint32), want2.view(np.uint32))
+
+    hc = [torch.from_numpy(s.color).pin_memory() for s in (scene, scene2)]
+    hd = [torch.from_numpy(s.depth).pin_memory() for s in (scene, scene2)]
+    cb, db = hc[0].numel(), hd[0].numel() * 4
+    fu = capi.Fusion(scene.N, scene.W, scene.H, scene.CW, scene.CH)
+    capi.load_scene(fu, scene, inv)
+    fu.configure(limit=0.01, voxel_size=0.025, brick_size=0.1, min_voxels=10, use_bricks=True)
+    with pytest.raises(capi.RRError):
+        fu.swap_frames()                      # nothing staged yet
+    fu.stage_frames_ptr(hc[0].data_ptr(), cb, hd[0].data_ptr(), db)
+    for i in range(4):
+        fu.swap_frames()                                                  # frame set i becomes current
+        nxt = (i + 1) % 2
+        fu.stage_frames_ptr(hc[nxt].data_ptr(), cb, hd[nxt].data_ptr(), db)   # set i+1 copies while set i is fused
+        fu.frame(sync_bricks=True)
+        got = fu.download_tsdf()
+        want = want1 if i % 2 == 0 else want2
+        assert bits_equal(got, want).all(), mismatch_report(f"tsdf of pipelined frame {i}", got, want)
+    fu.stage_sync()
+    fu.close()
