@@ -247,6 +247,7 @@ def run_ours(args):
     def view_once():
         if world == 1:
             fu.raymarch(mv, pr, VW, VH, shade_mode=1, download=False)
+            fu.fill_colors(download=False)          # m_fill_holes is on by default (recon_integration.cpp:54)
             return
         fu.raymarch_partial(mv, pr, VW, VH, records.data_ptr(), shade_mode=1)
         torch.cuda.current_stream(dev).wait_stream(stream)
@@ -254,6 +255,7 @@ def run_ours(args):
         stream.wait_stream(torch.cuda.current_stream(dev))      # the next march may not overwrite `records` before the gather read it
         if rank == 0:
             fu.composite(out.data_ptr(), world, VW, VH, download=False)
+            fu.fill_colors(download=False)
 
     for _ in range(3):
         view_once()
@@ -301,7 +303,7 @@ def run_ours(args):
                 "h2d_bytes_per_step": int(cb + db), "d2h_bytes_per_step": 4},
         "gpu_launches": int(gpu_launches),
         "stages_ms": {"1preprocess": round(pre_ms / max(1, pre_n), 5), "2integrate": round(int_avg_ms, 5)},
-        "view": {"ms_per_view": round(view_ms, 4), "resolution": [VW, VH], "what": "tsdf_raymarch (shaded, brick space skipping)" + (f" per slab + 1 gather of {multigpu.RECORD_FLOATS * 4}-byte records + composite" if world > 1 else "")},
+        "view": {"ms_per_view": round(view_ms, 4), "resolution": [VW, VH], "what": "tsdf_raymarch (shaded, brick space skipping) + colour hole filling" + (f" per slab + 1 gather of {multigpu.RECORD_FLOATS * 4}-byte records + composite" if world > 1 else "")},
         "roofline": {"bound": "hbm", "kernel": "k_integrate_fused (clear + occupied-brick integration, one launch = the 2integrate stage)" if bricks else "k_integrate_dense",
                      "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                      "traffic": None, "algorithmic_bytes_per_launch": int(abytes), "peak_source": peak_src},

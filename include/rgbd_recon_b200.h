@@ -136,6 +136,16 @@ int rr_integrate(rr_ctx* ctx);
  * out_rgba float32 [h][w][4], out_depth float32 [h][w] (gl_FragDepth, 1.0 where no surface), both host, may be NULL. */
 int rr_raymarch(rr_ctx* ctx, const rr_view* view, float* out_rgba, float* out_depth);
 
+/* ReconIntegration::fillColors (recon_integration.cpp:280-339; on by default, m_fill_holes, :54) + ViewLod
+ * (view_lod.cpp:24-61) + glsl/framebuffer_transfer.fs, tsdf_inpaint.fs, tsdf_colorfill.fs: push-pull colour hole filling
+ * of the LAST view (rr_raymarch, rr_composite or rr_upload_view): pixels the raymarch hit but could only colour with the
+ * fallback blend (alpha -1) take colour from the coarser lods of the mip atlas. out_rgba float32 [h][w][4], host, may be
+ * NULL; pixels without a surface keep the raymarch value. setColorFilling(false) = do not call it. */
+int rr_fill_colors(rr_ctx* ctx, float* out_rgba);
+/* Test hook: make host images the "last view" (rgba float32 [h][w][4], depth float32 [h][w]) so that rr_fill_colors can
+ * be checked on arbitrary inputs. */
+int rr_upload_view(rr_ctx* ctx, int width, int height, const float* rgba, const float* depth);
+
 /* Multi-GPU view (z-slab sharding): every slab context marches its own samples and writes one 32-byte
  * record per pixel {float rgba[4]; float depth; uint32 first_hit_step (0xFFFFFFFF none); float sample_count; float 0}
  * into d_records (DEVICE memory, viewport w*h records). The records of all slabs are gathered (one NCCL gather) into

@@ -68,6 +68,9 @@ def lib():
     L.ro_raymarch.argtypes = [f32p, u32p, C.c_float, C.c_int, f32p, i32p, f32p, i32p, u8p, C.c_int, C.c_int, f32p, f32p, C.c_int, C.c_int,
                               f32p, f32p, f32p, f32p, C.c_int, C.c_int, C.c_int, C.c_int, u32p, C.c_uint32, u32p, C.c_float,
                               f32p, f32p, f32p, f32p]
+    L.ro_fill_num_lods.argtypes = [C.c_int, C.c_int]
+    L.ro_fill_num_lods.restype = C.c_int
+    L.ro_fill_colors.argtypes = [f32p, f32p, C.c_int, C.c_int, f32p, C.c_void_p, C.c_void_p]
     _LIB = L
     return L
 
@@ -200,3 +203,20 @@ def raymarch_uniforms(modelview, projection, bbox_min, bbox_max, width, height):
     lib().ro_raymarch_uniforms(np.ascontiguousarray(modelview, np.float32).reshape(16), np.ascontiguousarray(projection, np.float32).reshape(16),
                                np.ascontiguousarray(bbox_min, np.float32), np.ascontiguousarray(bbox_max, np.float32), int(width), int(height), out)
     return out
+
+
+def fill_colors(rgba, depth, want_atlas=False):
+    """ReconIntegration::fillColors on a raymarch result: rgba [H,W,4], depth [H,W] -> filled rgba [H,W,4]
+    (and the final mip atlas when want_atlas)."""
+    rgba = np.ascontiguousarray(rgba, np.float32)
+    depth = np.ascontiguousarray(depth, np.float32)
+    H, W, _ = rgba.shape
+    out = np.zeros_like(rgba)
+    if not want_atlas:
+        lib().ro_fill_colors(rgba, depth, W, H, out, None, None)
+        return out
+    FW = int(np.float32(W) * np.float32(1.5))
+    ac = np.zeros((H, FW, 4), np.float32)
+    ad = np.zeros((H, FW), np.float32)
+    lib().ro_fill_colors(rgba, depth, W, H, out, ac.ctypes.data, ad.ctypes.data)
+    return out, ac, ad

@@ -57,6 +57,12 @@ void ro_raymarch(const float* tsdf, const uint32_t* res, float limit, int N, con
                  const uint32_t* occupied, uint32_t n_occ, const uint32_t* brick_res, float brick_size,
                  float* out_rgba, float* out_depth, float* out_samples, float* out_pos);
 
+
+/* Colour hole filling after the raymarch (ReconIntegration::fillColors + ViewLod + framebuffer_transfer / tsdf_inpaint /
+ * tsdf_colorfill): rgba [H][W][4] and depth [H][W] in, out_rgba [H][W][4]; atlas_* optional ([H][1.5W][4] / [H][1.5W]). */
+int ro_fill_num_lods(int W, int H);
+void ro_fill_colors(const float* rgba, const float* depth, int W, int H, float* out_rgba, float* atlas_rgba, float* atlas_depth);
+
 #ifdef __cplusplus
 }
 #endif

@@ -147,6 +147,7 @@ void rr_destroy(rr_ctx* c) {
   cudaFree(c->d_gather); cudaFree(c->d_flags); cudaFree(c->d_ranges); cudaFree(c->d_counters); cudaFree(c->d_occupied);
   cudaFree(c->d_num_occ); cudaFree(c->d_work); cudaFree(c->d_ztab); cudaFree(c->d_rowmask); cudaFree(c->d_rowany); cudaFree(c->d_cand_y); cudaFree(c->d_cand_z); cudaFree(c->d_near_occ); cudaFree(c->d_occ_mask); cudaFree(c->d_pos); cudaFree(c->d_step); cudaFree(c->d_tsdf); cudaFree(c->d_weight);
   cudaFree(c->d_rgba); cudaFree(c->d_zbuf); cudaFree(c->d_nsamples);
+  cudaFree(c->d_fill_fc); cudaFree(c->d_fill_fd); cudaFree(c->d_fill_sc); cudaFree(c->d_fill_sd); cudaFree(c->d_filled);
   if (c->h_num_occ) cudaFreeHost(c->h_num_occ);
   for (auto& kv : c->timers) {
     for (cudaEvent_t e : kv.second.beg) cudaEventDestroy(e);
@@ -472,6 +473,29 @@ int rr_raymarch(rr_ctx* c, const rr_view* view, float* out_rgba, float* out_dept
   if (out_depth) RR_TRY(check(c, cudaMemcpyAsync(out_depth, c->d_zbuf, (size_t)w * h * sizeof(float), cudaMemcpyDeviceToHost, c->stream), "depth download"));
   if (out_rgba || out_depth) RR_TRY(check(c, cudaStreamSynchronize(c->stream), "raymarch sync"));
   return RR_OK;
+}
+
+int rr_fill_colors(rr_ctx* c, float* out_rgba) {
+  if (!c) return RR_ERR_INVALID;
+  RR_REQUIRE(c, c->d_rgba && c->view_w > 0 && c->view_h > 0, "rr_fill_colors: no view yet (rr_raymarch / rr_composite / rr_upload_view first)");
+  RR_SET_DEVICE(c);
+  RR_TRY(launch_fill_colors(c));
+  if (out_rgba) {
+    RR_TRY(check(c, cudaMemcpyAsync(out_rgba, c->d_filled, (size_t)c->view_w * c->view_h * sizeof(float4), cudaMemcpyDeviceToHost, c->stream), "filled colour download"));
+    RR_TRY(check(c, cudaStreamSynchronize(c->stream), "fill sync"));
+  }
+  return RR_OK;
+}
+
+int rr_upload_view(rr_ctx* c, int width, int height, const float* rgba, const float* depth) {
+  if (!c) return RR_ERR_INVALID;
+  RR_REQUIRE(c, width > 0 && height > 0 && rgba && depth, "rr_upload_view: bad arguments");
+  RR_SET_DEVICE(c);
+  RR_TRY(ensure_view(c, width, height));
+  const size_t n = (size_t)width * height;
+  RR_TRY(check(c, cudaMemcpyAsync(c->d_rgba, rgba, n * sizeof(float4), cudaMemcpyHostToDevice, c->stream), "view upload"));
+  RR_TRY(check(c, cudaMemcpyAsync(c->d_zbuf, depth, n * sizeof(float), cudaMemcpyHostToDevice, c->stream), "view upload"));
+  return check(c, cudaStreamSynchronize(c->stream), "view upload sync");
 }
 
 int rr_raymarch_partial(rr_ctx* c, const rr_view* view, void* d_records) {

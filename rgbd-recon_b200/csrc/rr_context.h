@@ -129,6 +129,12 @@ struct rr_ctx {
   float* d_nsamples = nullptr;
   float4* d_pos = nullptr;         // hit position in volume space (w = 1 on a hit)
   uint32_t* d_step = nullptr;      // step index of the hit, 0xFFFFFFFF = none (multi-GPU compositing key)
+
+  // colour hole filling (rr_colorfill.cu): atlas right of column W, squeezed copy, filled colour
+  int fill_w = 0, fill_h = 0;
+  float4* d_fill_fc = nullptr; float* d_fill_fd = nullptr;
+  float4* d_fill_sc = nullptr; float* d_fill_sd = nullptr;
+  float4* d_filled = nullptr;
 };
 
 namespace rr {
@@ -160,6 +166,7 @@ int launch_integrate(rr_ctx* c);
 int launch_raymarch(rr_ctx* c, const rr_view* v);
 int launch_pack_partial(rr_ctx* c, float4* d_rec);
 int launch_composite(rr_ctx* c, const float4* d_rec, int n_parts);
+int launch_fill_colors(rr_ctx* c);
 int launch_calib_invert(rr_ctx* c, int sensor, const uint32_t out_res[3], float4* d_out);
 
 // host geometry (rr_host_geom.cpp)

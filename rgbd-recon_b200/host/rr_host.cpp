@@ -271,8 +271,10 @@ void ReconIntegration::draw() {
   ck(rr_raymarch(ctx(), &m_view, m_rgba.data(), m_depth.data()), "rr_raymarch");
 }
 void ReconIntegration::drawF() {
-  // drawDepthLimits + draw (+ fillColors, SURVEY.md §8f-1: not built) : brick space skipping happens inside rr_raymarch
+  // drawDepthLimits + draw + fillColors (recon_integration.cpp:151-175): brick space skipping happens inside
+  // rr_raymarch; with m_fill_holes (the default) the colour image is the hole-filled one
   Reconstruction::drawF();
+  if (m_fill_holes) ck(rr_fill_colors(ctx(), m_rgba.data()), "rr_fill_colors");
 }
 void ReconIntegration::downloadTsdf(std::vector<float>& out) const {
   const glm::uvec3 r = volumeResolution();

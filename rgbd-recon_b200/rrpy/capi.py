@@ -72,6 +72,8 @@ def lib():
     L.rr_raymarch.argtypes = [vp, C.POINTER(View), f32, f32]
     L.rr_raymarch_partial.argtypes = [vp, C.POINTER(View), vp]
     L.rr_composite.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, f32, f32]
+    L.rr_fill_colors.argtypes = [vp, f32]
+    L.rr_upload_view.argtypes = [vp, C.c_int, C.c_int, f32, f32]
     L.rr_download_tsdf.argtypes = [vp, f32]
     L.rr_download_weight.argtypes = [vp, f32]
     L.rr_download_stage.argtypes = [vp, C.c_int, f32]
@@ -243,6 +245,7 @@ class Fusion:
         v.projection[:] = [float(x) for x in np.asarray(projection, np.float32).reshape(16)]
         v.viewport[:] = [0, 0, int(width), int(height)]
         v.shade_mode = int(shade_mode)
+        self._vw, self._vh = int(width), int(height)
         if not download:
             self._ck(self.L.rr_raymarch(self.h, C.byref(v), None, None))
             return None
@@ -250,6 +253,21 @@ class Fusion:
         depth = np.zeros((height, width), np.float32)
         self._ck(self.L.rr_raymarch(self.h, C.byref(v), _f32(rgba), _f32(depth)))
         return rgba, depth
+
+    def fill_colors(self, download=True):
+        """ReconIntegration::fillColors on the last view; returns the filled rgba [h, w, 4] when download."""
+        if not download:
+            self._ck(self.L.rr_fill_colors(self.h, None))
+            return None
+        out = np.zeros((self._vh, self._vw, 4), np.float32)
+        self._ck(self.L.rr_fill_colors(self.h, _f32(out)))
+        return out
+
+    def upload_view(self, rgba, depth):
+        rgba = np.ascontiguousarray(rgba, np.float32)
+        depth = np.ascontiguousarray(depth, np.float32)
+        self._vh, self._vw = depth.shape
+        self._ck(self.L.rr_upload_view(self.h, self._vw, self._vh, _f32(rgba), _f32(depth)))
 
     def _view(self, modelview, projection, width, height, shade_mode):
         v = View()
@@ -265,6 +283,7 @@ class Fusion:
         self._ck(self.L.rr_raymarch_partial(self.h, C.byref(v), d_records_ptr))
 
     def composite(self, d_records_ptr, n_parts, width, height, download=True):
+        self._vw, self._vh = int(width), int(height)
         if not download:
             self._ck(self.L.rr_composite(self.h, d_records_ptr, n_parts, width, height, None, None))
             return None

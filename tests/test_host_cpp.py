@@ -104,6 +104,8 @@ def test_fusion_playback_program_matches_oracle(tmp_path, small_scene):
     rgba, depth = img[:VW * VH * 4].reshape(VH, VW, 4), img[VW * VH * 4:].reshape(VH, VW)
     rm = O.raymarch(want, 0.01, inv, sc, pre, grid, occ, mv, pr, VW, VH, 1, True)
     assert (rm["depth"] < 1).sum() > 500
-    assert bits_equal(depth, rm["depth"]).all() and bits_equal(rgba, rm["rgba"]).all()
+    # m_fill_holes is on by default (recon_integration.cpp:54): drawF() = raymarch + fillColors
+    filled = O.fill_colors(rm["rgba"], rm["depth"])
+    assert bits_equal(depth, rm["depth"]).all() and bits_equal(rgba, filled).all()
     ratio = float(r.stdout.split("occupied ratio")[1].split()[0])
     assert abs(ratio - len(occ) / grid["num_bricks"]) < 1e-6

@@ -321,3 +321,39 @@ def test_planar_wall_gives_linear_ramp(O):
     band = (np.abs(want) < 0.03) & (tsdf > -0.04) & (tsdf < 0.04)
     assert band.sum() > 2000
     assert np.abs(tsdf[band] - want[band]).max() < 2e-3, "ramp slope/offset (trilinear lookup of an affine field is exact up to the 2 mm distortion)"
+
+
+def test_colorfill_oracle_properties(O):
+    """Stage invariants of the colour hole filling restatement (oracle/ro_colorfill.cpp): only surface pixels change,
+    every hole ends up with a blended colour of alpha 1 when valid neighbours exist, the atlas layout follows ViewLod."""
+    rng = np.random.default_rng(7)
+    H, W = 90, 160
+    yy, xx = np.mgrid[0:H, 0:W]
+    hit = ((xx - 80) ** 2 + (yy - 45) ** 2) < 38 ** 2
+    rgba = np.zeros((H, W, 4), np.float32)
+    depth = np.ones((H, W), np.float32)
+    rgba[hit, :3] = rng.random((int(hit.sum()), 3), dtype=np.float32)
+    holes = hit & (rng.random((H, W)) < 0.25)
+    rgba[hit, 3] = 1.0
+    rgba[holes, 3] = -1.0
+    depth[hit] = (0.5 + 0.3 * rng.random(int(hit.sum()))).astype(np.float32)
+    out, atlas_c, atlas_d = O.fill_colors(rgba, depth, want_atlas=True)
+    assert O.lib().ro_fill_num_lods(W, H) == 1 + int(np.floor(np.log2(min(W, H))))
+    assert atlas_c.shape == (H, int(W * 1.5), 4)
+    # lod 0 of the atlas is the raymarch result (cleared where nothing was drawn)
+    assert np.array_equal(atlas_c[:, :W][hit], rgba[hit])
+    assert np.array_equal(atlas_c[:, :W][~hit], np.broadcast_to(np.float32([0, 1, 0, 0]), (int((~hit).sum()), 4)))
+    assert np.array_equal(atlas_d[:, :W][~hit], np.ones(int((~hit).sum()), np.float32))
+    # lod 1 sits right of column W in the top rows and holds averaged colours of alpha 1 inside the blob
+    lod1 = atlas_c[H - H // 2:, W:W + W // 2]
+    assert (lod1[..., 3] == 1.0).sum() > 0.3 * lod1.shape[0] * lod1.shape[1]
+    # background untouched, holes filled with alpha-1 blends in the colour range of their neighbours
+    assert np.array_equal(out[~hit], rgba[~hit])
+    filled = out[holes]
+    assert np.isfinite(filled).all() and (filled[:, 3] > 0).mean() > 0.95
+    assert filled[:, :3].min() >= 0.0 and filled[:, :3].max() <= 1.0
+    # idempotent on an image without holes apart from the texel-fetch rounding of the shader's px / W * W
+    clean = rgba.copy()
+    clean[holes, 3] = 1.0
+    out2 = O.fill_colors(clean, depth)
+    assert np.isin(out2[hit].reshape(-1, 4).view(np.uint32), clean.view(np.uint32)).all()
