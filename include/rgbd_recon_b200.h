@@ -117,6 +117,16 @@ int rr_set_slab(rr_ctx* ctx, uint32_t z0, uint32_t z1);
  *   rr_stage_sync    = host wait until the staged copies have completed (the host buffers may be reused).
  *   rr_upload_frames = rr_stage_frames + rr_swap_frames (no overlap; the simple path). */
 int rr_stage_frames(rr_ctx* ctx, const void* color, size_t color_bytes, const void* depth, size_t depth_bytes);
+/* Stream formats of the reference (KinectCalibrationFile compress_rgb / compress_depth; NetKinectArray.cpp:120-142,
+ * 149-159,170-175): colour RGB8 [N][CH][CW][3] or DXT1 blocks (CW*CH/2 bytes per sensor, CW and CH multiples of 4);
+ * depth float32 metres [N][H][W] or 8-bit sqrt-compressed [N][H][W] with per-sensor (near, far) of the calibration file
+ * (near_far float [N][2]; pre_depth.fs uncompress(), :51-61, with scale = far - near). Sets the sizes the upload calls
+ * expect; packed frame sets are expanded on the device. Default: RGB8 + float32. */
+#define RR_COLOR_RGB8 0
+#define RR_COLOR_DXT1 1
+#define RR_DEPTH_F32 0
+#define RR_DEPTH_U8 1
+int rr_set_frame_format(rr_ctx* ctx, int color_format, int depth_format, const float* near_far);
 int rr_swap_frames(rr_ctx* ctx);
 int rr_stage_sync(rr_ctx* ctx);
 int rr_upload_frames(rr_ctx* ctx, const void* color, size_t color_bytes, const void* depth, size_t depth_bytes);

@@ -68,6 +68,8 @@ def lib():
     L.ro_raymarch.argtypes = [f32p, u32p, C.c_float, C.c_int, f32p, i32p, f32p, i32p, u8p, C.c_int, C.c_int, f32p, f32p, C.c_int, C.c_int,
                               f32p, f32p, f32p, f32p, C.c_int, C.c_int, C.c_int, C.c_int, u32p, C.c_uint32, u32p, C.c_float,
                               f32p, f32p, f32p, f32p]
+    L.ro_decode_dxt1.argtypes = [u8p, C.c_int, C.c_int, u8p]
+    L.ro_depth8_to_float.argtypes = [u8p, C.c_size_t, f32p]
     L.ro_fill_num_lods.argtypes = [C.c_int, C.c_int]
     L.ro_fill_num_lods.restype = C.c_int
     L.ro_fill_colors.argtypes = [f32p, f32p, C.c_int, C.c_int, f32p, C.c_void_p, C.c_void_p]
@@ -134,8 +136,24 @@ def calib_invert(cv_xyz_one, bbox_min, bbox_max, out_res, want_neighbours=False,
 
 # ---------------------------------------------------------------------------------------------- frame
 
-def preprocess(scene, grid, camera_positions, filter_textures=True, use_processed_depth=True, refine=True):
-    """NetKinectArray::processTextures for all layers (+ ReconIntegration::clearOccupiedBricks before it)."""
+def decode_dxt1(blocks, W, H):
+    """DXT1 block bytes -> uint8 [H][W][3] (what the GL sampler returns as .rgb * 255)."""
+    out = np.zeros((H, W, 3), np.uint8)
+    lib().ro_decode_dxt1(np.ascontiguousarray(blocks, np.uint8), W, H, out)
+    return out
+
+
+def depth8_to_float(d8):
+    d8 = np.ascontiguousarray(d8, np.uint8)
+    out = np.zeros(d8.shape, np.float32)
+    lib().ro_depth8_to_float(d8.reshape(-1), d8.size, out.reshape(-1))
+    return out
+
+
+def preprocess(scene, grid, camera_positions, filter_textures=True, use_processed_depth=True, refine=True, compress=None):
+    """NetKinectArray::processTextures for all layers (+ ReconIntegration::clearOccupiedBricks before it).
+    compress: None, or per sensor (near, far) when scene.depth holds the normalised 8-bit values byte/255
+    (NetKinectArray.cpp:345-351: scale = far - near, scaled_near = scale / 255)."""
     L = lib()
     N, H, W = scene.depth.shape
     X, Y, Z = scene.cv_res
@@ -150,8 +168,14 @@ def preprocess(scene, grid, camera_positions, filter_textures=True, use_processe
         raw = np.ascontiguousarray(scene.depth[i])
         L.ro_pre_morph(raw, W, H, out["morph"][i])
         src = out["morph"][i] if use_processed_depth else raw
+        if compress is None:
+            cz, scale, near, snear = 0, 0.0, 0.0, 0.0
+        else:
+            near = np.float32(compress[i][0])
+            scale = np.float32(compress[i][1]) - near
+            cz, snear = 1, scale / np.float32(255.0)
         L.ro_pre_depth(src, W, H, scene.cv_xyz[i], scene.cv_uv[i], X, Y, Z, scene.color[i], scene.CW, scene.CH, bmin, bmax,
-                       0.5, 4.5, int(filter_textures), 0, 0.0, 0.0, 0.0, out["depth"][i], out["lab"][i])
+                       0.5, 4.5, int(filter_textures), cz, float(scale), float(near), float(snear), out["depth"][i], out["lab"][i])
         L.ro_pre_boundary(out["depth"][i], out["lab"][i], W, H, int(refine), out["depth_b"][i], out["sil"][i])
         L.ro_pre_normal(out["depth_b"][i], W, H, scene.cv_xyz[i], X, Y, Z, bmin, grid["brick_size"], grid["res_bricks"],
                         grid["num_bricks"], out["bricks"], out["normal"][i])

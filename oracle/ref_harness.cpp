@@ -2,7 +2,7 @@
 // under /root/reference by oracle/Makefile into oracle/_ref/libref_harness.so (git-ignored, never copied into the repo):
 //   framework/calibration/frustum.cpp, calibration_inverter.cpp, nearest_neighbour_search.cpp, calibration_volume.hpp,
 //   framework/rendering/volume_sampler.cpp, framework/DataTypes.cpp, external/gloost/{Matrix,Point3,Vector3,Ray,
-//   BoundingBox,BoundingVolume}.cpp and the header-only glm 0.9.5.3.
+//   BoundingBox,BoundingVolume}.cpp, external/squish/*.cpp (DXT codec) and the header-only glm 0.9.5.3.
 // OpenGL / globjects / CGAL / boost are absent from this image: oracle/ref_stubs provides no-op GL and globjects
 // declarations and an exact-kNN stand-in for CGAL's Orthogonal_k_neighbor_search (its header states the contract).
 // This file only marshals arguments; it contains no algorithmic code of its own except ref_draw_uniforms, which calls
@@ -23,6 +23,7 @@
 #include <BoundingBox.h>
 #include <glm/gtc/matrix_inverse.hpp>
 #include <glm/gtc/matrix_transform.hpp>
+#include <squish.h>
 
 using namespace kinect;
 
@@ -33,6 +34,15 @@ static std::array<glm::fvec3, 8> corners_of(const float* c) {
 }
 
 extern "C" {
+
+// external/squish (the reference's CPU DXT codec, used at NetKinectArray.cpp:635): rgba uint8 [h][w][4] <-> DXT1 blocks
+void ref_squish_compress_dxt1(const unsigned char* rgba, int w, int h, unsigned char* blocks) {
+  squish::CompressImage(rgba, w, h, blocks, squish::kDxt1 | squish::kColourRangeFit);
+}
+void ref_squish_decompress_dxt1(const unsigned char* blocks, int w, int h, unsigned char* rgba) {
+  squish::DecompressImage(rgba, w, h, blocks, squish::kDxt1);
+}
+int ref_squish_storage_dxt1(int w, int h) { return squish::GetStorageRequirements(w, h, squish::kDxt1); }
 
 // kinect::Frustum (frustum.cpp): planes float[6][4], camera position float[3]
 void ref_frustum(const float* corners, float* planes_out, float* cam_out) {

@@ -41,6 +41,11 @@ def lib():
         L.ref_glm_distance.argtypes = [f32p, f32p]
         L.ref_glm_distance.restype = C.c_float
         L.ref_draw_uniforms.argtypes = [f32p, f32p, f32p, f32p, C.c_uint, C.c_uint, f32p]
+        u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+        L.ref_squish_compress_dxt1.argtypes = [u8p, C.c_int, C.c_int, u8p]
+        L.ref_squish_decompress_dxt1.argtypes = [u8p, C.c_int, C.c_int, u8p]
+        L.ref_squish_storage_dxt1.argtypes = [C.c_int, C.c_int]
+        L.ref_squish_storage_dxt1.restype = C.c_int
         _LIB = L
     return _LIB
 
@@ -124,3 +129,19 @@ def draw_uniforms(modelview, projection, bbox_min, bbox_max, vw, vh):
     lib().ref_draw_uniforms(np.ascontiguousarray(modelview, np.float32).reshape(16), np.ascontiguousarray(projection, np.float32).reshape(16),
                             np.ascontiguousarray(bbox_min, np.float32), np.ascontiguousarray(bbox_max, np.float32), int(vw), int(vh), out)
     return dict(img_to_eye=out[:16].copy(), normal_matrix=out[16:32].copy(), camera_pos=out[32:35].copy())
+
+
+def squish_compress_dxt1(rgb):
+    """external/squish CompressImage (kDxt1 | kColourRangeFit) of uint8 [H][W][3] -> block bytes."""
+    H, W, _ = rgb.shape
+    rgba = np.concatenate([rgb, np.full((H, W, 1), 255, np.uint8)], axis=2)
+    out = np.zeros(lib().ref_squish_storage_dxt1(W, H), np.uint8)
+    lib().ref_squish_compress_dxt1(np.ascontiguousarray(rgba), W, H, out)
+    return out
+
+
+def squish_decompress_dxt1(blocks, W, H):
+    """external/squish DecompressImage (kDxt1) -> uint8 [H][W][4]."""
+    out = np.zeros((H, W, 4), np.uint8)
+    lib().ref_squish_decompress_dxt1(np.ascontiguousarray(blocks, np.uint8), W, H, out)
+    return out

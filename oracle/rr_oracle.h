@@ -4,6 +4,7 @@
  * none); see ro_math.h for what is pinned against reference code compiled into oracle/_ref. */
 #ifndef RR_ORACLE_H
 #define RR_ORACLE_H
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -57,6 +58,10 @@ void ro_raymarch(const float* tsdf, const uint32_t* res, float limit, int N, con
                  const uint32_t* occupied, uint32_t n_occ, const uint32_t* brick_res, float brick_size,
                  float* out_rgba, float* out_depth, float* out_samples, float* out_pos);
 
+
+/* Compressed ingest: DXT1 colour blocks -> uint8 [H][W][3]; 8-bit depth -> byte/255. */
+void ro_decode_dxt1(const uint8_t* blocks, int W, int H, uint8_t* out_rgb);
+void ro_depth8_to_float(const uint8_t* in, size_t n, float* out);
 
 /* Colour hole filling after the raymarch (ReconIntegration::fillColors + ViewLod + framebuffer_transfer / tsdf_inpaint /
  * tsdf_colorfill): rgba [H][W][4] and depth [H][W] in, out_rgba [H][W][4]; atlas_* optional ([H][1.5W][4] / [H][1.5W]). */

@@ -139,6 +139,7 @@ void rr_destroy(rr_ctx* c) {
   if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (int i = 0; i < RR_MAX_SENSORS; ++i) { cudaFree(c->d_xyz[i]); cudaFree(c->d_uv[i]); }
+  for (int b = 0; b < 2; ++b) { cudaFree(c->d_color_packed[b]); cudaFree(c->d_depth_packed[b]); }
   for (int b = 0; b < 2; ++b) { cudaFree(c->d_depth_slot[b]); cudaFree(c->d_color_slot[b]); if (c->ev_free[b]) cudaEventDestroy(c->ev_free[b]); }
   if (c->ev_staged) cudaEventDestroy(c->ev_staged);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -345,11 +346,38 @@ int rr_set_slab(rr_ctx* c, uint32_t z0, uint32_t z1) {
   return RR_OK;
 }
 
+static size_t color_bytes_of(const rr_ctx* c) {
+  return c->color_format == RR_COLOR_DXT1 ? (size_t)c->N * c->CW * c->CH / 2 : (size_t)c->N * c->CW * c->CH * 3;
+}
+static size_t depth_bytes_of(const rr_ctx* c) {
+  return (size_t)c->N * c->W * c->H * (c->depth_format == RR_DEPTH_U8 ? 1 : sizeof(float));
+}
+
 static int check_frame_sizes(rr_ctx* c, const void* color, size_t cb, const void* depth, size_t db) {
-  const size_t want_d = (size_t)c->N * c->W * c->H * sizeof(float);
-  const size_t want_c = (size_t)c->N * c->CW * c->CH * 3;
-  RR_REQUIRE(c, depth && db == want_d, "rr_upload_frames: depth must be float32 [N][H][W]");
-  RR_REQUIRE(c, !color || cb == want_c, "rr_upload_frames: colour must be uint8 [N][CH][CW][3]");
+  RR_REQUIRE(c, depth && db == depth_bytes_of(c), "rr_upload_frames: depth must be [N][H][W] in the format of rr_set_frame_format (default float32)");
+  RR_REQUIRE(c, !color || cb == color_bytes_of(c), "rr_upload_frames: colour must be [N] layers in the format of rr_set_frame_format (default uint8 [CH][CW][3])");
+  return RR_OK;
+}
+
+int rr_set_frame_format(rr_ctx* c, int color_format, int depth_format, const float* near_far) {
+  if (!c) return RR_ERR_INVALID;
+  RR_REQUIRE(c, color_format == RR_COLOR_RGB8 || color_format == RR_COLOR_DXT1, "rr_set_frame_format: unknown colour format (DXT5 streams are not supported)");
+  RR_REQUIRE(c, depth_format == RR_DEPTH_F32 || depth_format == RR_DEPTH_U8, "rr_set_frame_format: unknown depth format");
+  RR_REQUIRE(c, color_format != RR_COLOR_DXT1 || ((c->CW % 4) == 0 && (c->CH % 4) == 0), "rr_set_frame_format: DXT1 needs colour width and height that are multiples of 4");
+  RR_REQUIRE(c, depth_format != RR_DEPTH_U8 || near_far, "rr_set_frame_format: 8-bit depth needs the per-sensor (near, far) range");
+  RR_SET_DEVICE(c);
+  RR_TRY(check(c, cudaStreamSynchronize(c->copy_stream), "format sync"));
+  RR_TRY(check(c, cudaStreamSynchronize(c->stream), "format sync"));
+  c->staged = false;
+  c->color_format = color_format; c->depth_format = depth_format;
+  for (int b = 0; b < 2; ++b) {
+    if (color_format == RR_COLOR_DXT1 && !c->d_color_packed[b]) RR_TRY(dev_alloc(c, &c->d_color_packed[b], (size_t)c->N * c->CW * c->CH / 2, "packed colour"));
+    if (depth_format == RR_DEPTH_U8 && !c->d_depth_packed[b]) RR_TRY(dev_alloc(c, &c->d_depth_packed[b], (size_t)c->N * c->W * c->H, "packed depth"));
+  }
+  for (int i = 0; i < c->N; ++i) {
+    c->depth_near[i] = near_far ? near_far[2 * i] : 0.0f;
+    c->depth_far[i] = near_far ? near_far[2 * i + 1] : 0.0f;
+  }
   return RR_OK;
 }
 
@@ -360,8 +388,11 @@ int rr_stage_frames(rr_ctx* c, const void* color, size_t cb, const void* depth, 
   const int t = c->cur_slot ^ 1;
   // the slot may still be read by kernels launched while it was current
   if (c->free_recorded[t]) RR_TRY(check(c, cudaStreamWaitEvent(c->copy_stream, c->ev_free[t], 0), "stage wait"));
-  RR_TRY(check(c, cudaMemcpyAsync(c->d_depth_slot[t], depth, db, cudaMemcpyHostToDevice, c->copy_stream), "depth upload"));
-  if (color) RR_TRY(check(c, cudaMemcpyAsync(c->d_color_slot[t], color, cb, cudaMemcpyHostToDevice, c->copy_stream), "colour upload"));
+  void* dd = c->depth_format == RR_DEPTH_U8 ? (void*)c->d_depth_packed[t] : (void*)c->d_depth_slot[t];
+  void* dc = c->color_format == RR_COLOR_DXT1 ? (void*)c->d_color_packed[t] : (void*)c->d_color_slot[t];
+  RR_TRY(check(c, cudaMemcpyAsync(dd, depth, db, cudaMemcpyHostToDevice, c->copy_stream), "depth upload"));
+  if (color) RR_TRY(check(c, cudaMemcpyAsync(dc, color, cb, cudaMemcpyHostToDevice, c->copy_stream), "colour upload"));
+  c->staged_color = color != nullptr;
   RR_TRY(check(c, cudaEventRecord(c->ev_staged, c->copy_stream), "stage record"));
   c->staged = true;
   return RR_OK;
@@ -378,7 +409,12 @@ int rr_swap_frames(rr_ctx* c) {
   c->cur_slot = t;
   c->d_depth_raw = c->d_depth_slot[t]; c->d_color = c->d_color_slot[t];
   c->staged = false;
-  return RR_OK;
+  // packed layers (DXT1 colour, 8-bit depth) are expanded here, once, behind the staged copy
+  const int keep_color = c->color_format;
+  if (!c->staged_color) c->color_format = RR_COLOR_RGB8;      // no colour was staged: nothing to decode
+  const int rc = launch_unpack_frames(c, t);
+  c->color_format = keep_color;
+  return rc;
 }
 
 int rr_stage_sync(rr_ctx* c) {
@@ -400,9 +436,16 @@ int rr_upload_frames_device(rr_ctx* c, const void* color, size_t cb, const void*
   RR_TRY(check_frame_sizes(c, color, cb, depth, db));
   // already on this GPU (e.g. the output of an NCCL broadcast ordered before the context's stream): straight into the
   // current slot, on the compute stream
-  RR_TRY(check(c, cudaMemcpyAsync(c->d_depth_raw, depth, db, cudaMemcpyDeviceToDevice, c->stream), "depth upload"));
-  if (color) RR_TRY(check(c, cudaMemcpyAsync(c->d_color, color, cb, cudaMemcpyDeviceToDevice, c->stream), "colour upload"));
-  return RR_OK;
+  const int t = c->cur_slot;
+  void* dd = c->depth_format == RR_DEPTH_U8 ? (void*)c->d_depth_packed[t] : (void*)c->d_depth_slot[t];
+  void* dc = c->color_format == RR_COLOR_DXT1 ? (void*)c->d_color_packed[t] : (void*)c->d_color_slot[t];
+  RR_TRY(check(c, cudaMemcpyAsync(dd, depth, db, cudaMemcpyDeviceToDevice, c->stream), "depth upload"));
+  if (color) RR_TRY(check(c, cudaMemcpyAsync(dc, color, cb, cudaMemcpyDeviceToDevice, c->stream), "colour upload"));
+  const int keep_color = c->color_format;
+  if (!color) c->color_format = RR_COLOR_RGB8;
+  const int rc = launch_unpack_frames(c, t);
+  c->color_format = keep_color;
+  return rc;
 }
 
 static int require_ready(rr_ctx* c, bool need_inv) {

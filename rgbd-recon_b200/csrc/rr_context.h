@@ -80,10 +80,16 @@ struct rr_ctx {
   uint8_t* d_color_slot[2] = {nullptr, nullptr};
   int cur_slot = 0;
   bool staged = false;                       // the other slot holds a frame set that has not been swapped in yet
+  bool staged_color = false;                 // ... and it came with colour
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_staged = nullptr;           // recorded on copy_stream after the staged copies
   cudaEvent_t ev_free[2] = {nullptr, nullptr};   // recorded on stream when a slot stops being current
   bool free_recorded[2] = {false, false};
+  // compressed ingest (rr_set_frame_format): packed layers per slot, expanded by launch_unpack_frames at the swap
+  int color_format = 0, depth_format = 0;
+  uint8_t* d_color_packed[2] = {nullptr, nullptr};
+  uint8_t* d_depth_packed[2] = {nullptr, nullptr};
+  float depth_near[RR_MAX_SENSORS] = {}, depth_far[RR_MAX_SENSORS] = {};
   float* d_morph = nullptr;
   float2* d_depth = nullptr;
   float4* d_lab = nullptr;
@@ -167,6 +173,7 @@ int launch_raymarch(rr_ctx* c, const rr_view* v);
 int launch_pack_partial(rr_ctx* c, float4* d_rec);
 int launch_composite(rr_ctx* c, const float4* d_rec, int n_parts);
 int launch_fill_colors(rr_ctx* c);
+int launch_unpack_frames(rr_ctx* c, int slot);
 int launch_calib_invert(rr_ctx* c, int sensor, const uint32_t out_res[3], float4* d_out);
 
 // host geometry (rr_host_geom.cpp)

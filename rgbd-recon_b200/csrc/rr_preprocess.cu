@@ -380,6 +380,13 @@ int launch_preprocess(rr_ctx* c, int filter_textures, int use_processed_depth, i
   DepthParams dp{};
   for (int a = 0; a < 3; ++a) { dp.bmin[a] = c->bbox_min[a]; dp.bmax[a] = c->bbox_max[a]; }
   dp.filter_textures = filter_textures;
+  for (int i = 0; i < N; ++i) {
+    // NetKinectArray.cpp:345-351: compress, scale = far - near, near, scaled_near = scale / 255
+    dp.compress[i] = c->depth_format == RR_DEPTH_U8 ? 1 : 0;
+    dp.near_[i] = c->depth_near[i];
+    dp.scale[i] = c->depth_far[i] - c->depth_near[i];
+    dp.scaled_near[i] = dp.scale[i] / 255.0f;
+  }
   k_bilateral<<<grd, blk, 0, s>>>(use_processed_depth ? c->d_morph : c->d_depth_raw, c->d_color, c->d_depth, c->d_lab,
                                   W, H, c->CW, c->CH, st, dp);
   RR_LAUNCH_CHECK(c, "k_bilateral");

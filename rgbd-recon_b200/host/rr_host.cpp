@@ -133,10 +133,15 @@ void CalibrationInverter::writeInverseVolumes(std::string const& path) const {
 NetKinectArray::NetKinectArray(std::string const& serverport, std::string const& slaveport, CalibrationFiles const* calibs, CalibVolumes const* vols, bool readfromfile)
     : m_resolution_color(calibs->getWidthC(), calibs->getHeightC()), m_resolution_depth(calibs->getWidth(), calibs->getHeight()),
       m_numLayers(calibs->num()), m_serverport(serverport), m_slaveport(slaveport), m_calib_files(calibs), m_calib_vols(vols) {
-  if (calibs->isCompressedRGB() || calibs->isCompressedDepth())
-    throw std::runtime_error("compressed colour/depth streams are not supported yet (SURVEY.md §8f-2)");
-  m_colorsize = (std::size_t)m_resolution_color.x * m_resolution_color.y * 3;                 // RGB8, NetKinectArray.cpp:120-131
-  m_depthsize = (std::size_t)m_resolution_depth.x * m_resolution_depth.y * sizeof(float);     // float metres, :135-142
+  if (calibs->isCompressedRGB() > 1) throw std::runtime_error("DXT5 colour streams are not supported (DXT1 and RGB8 are)");
+  // NetKinectArray.cpp:120-142: DXT1 = w*h/2 bytes, RGB8 = w*h*3; depth 1 byte (sqrt-compressed) or a float per texel
+  m_colorsize = calibs->isCompressedRGB() == 1 ? (std::size_t)m_resolution_color.x * m_resolution_color.y / 2
+                                               : (std::size_t)m_resolution_color.x * m_resolution_color.y * 3;
+  m_depthsize = (std::size_t)m_resolution_depth.x * m_resolution_depth.y * (calibs->isCompressedDepth() ? 1 : sizeof(float));
+  std::vector<float> near_far;
+  for (unsigned i = 0; i < m_numLayers; ++i) { near_far.push_back(calibs->getNear()); near_far.push_back(calibs->getFar()); }
+  ck(rr_set_frame_format(ctx(), calibs->isCompressedRGB() == 1 ? RR_COLOR_DXT1 : RR_COLOR_RGB8,
+                         calibs->isCompressedDepth() ? RR_DEPTH_U8 : RR_DEPTH_F32, near_far.data()), "rr_set_frame_format");
   for (int b = 0; b < 2; ++b)
     if (cudaMallocHost((void**)&m_staging[b], (m_colorsize + m_depthsize) * m_numLayers) != cudaSuccess) throw std::runtime_error("pinned staging allocation failed");
   if (readfromfile) {

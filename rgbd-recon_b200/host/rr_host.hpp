@@ -92,10 +92,15 @@ class CalibrationFiles {
   unsigned num() const { return (unsigned)m_filenames.size(); }
   unsigned isCompressedRGB() const { return m_compressed_rgb; }
   bool isCompressedDepth() const { return m_compressed_d; }
+  // KinectCalibrationFile::getNear / getFar (the range of the 8-bit depth stream), the same for every sensor here
+  void setDepthRange(float near_, float far_) { m_near = near_; m_far = far_; }
+  float getNear() const { return m_near; }
+  float getFar() const { return m_far; }
   std::vector<std::string> const& getFileNames() const { return m_filenames; }
  private:
   unsigned m_width, m_widthc, m_height, m_heightc, m_compressed_rgb;
   bool m_compressed_d;
+  float m_near = 0.5f, m_far = 4.5f;
   std::vector<std::string> m_filenames;
 };
 

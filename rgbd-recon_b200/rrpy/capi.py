@@ -64,6 +64,7 @@ def lib():
     L.rr_upload_frames_device.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t]
     L.rr_stage_frames.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t]
     L.rr_swap_frames.argtypes = [vp]
+    L.rr_set_frame_format.argtypes = [vp, C.c_int, C.c_int, f32]
     L.rr_stage_sync.argtypes = [vp]
     L.rr_bricks_clear.argtypes = [vp]
     L.rr_preprocess.argtypes = [vp, C.c_int, C.c_int, C.c_int]
@@ -198,9 +199,15 @@ class Fusion:
     def set_slab(self, z0, z1):
         self._ck(self.L.rr_set_slab(self.h, int(z0), int(z1)))
 
+    def set_frame_format(self, dxt1_color=False, depth8=False, near_far=None):
+        """Stream formats (rr_set_frame_format): DXT1 colour blocks and / or 8-bit sqrt-compressed depth."""
+        nf = np.ascontiguousarray(near_far, np.float32) if near_far is not None else None
+        self._depth8 = bool(depth8)
+        self._ck(self.L.rr_set_frame_format(self.h, 1 if dxt1_color else 0, 1 if depth8 else 0, _f32(nf) if nf is not None else None))
+
     # per frame
     def upload_frames(self, color, depth):
-        depth = np.ascontiguousarray(depth, np.float32)
+        depth = np.ascontiguousarray(depth, np.uint8 if getattr(self, "_depth8", False) else np.float32)
         if color is not None:
             color = np.ascontiguousarray(color, np.uint8)
         self._ck(self.L.rr_upload_frames(self.h, color.ctypes.data if color is not None else None,

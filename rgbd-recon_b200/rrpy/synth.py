@@ -239,3 +239,52 @@ def perspective(fovy_deg, aspect, near, far) -> np.ndarray:
     m[2, 2], m[2, 3] = (far + near) / (near - far), 2.0 * far * near / (near - far)
     m[3, 2] = -1.0
     return np.ascontiguousarray(m.T, np.float32).reshape(16)
+
+
+# ---- compressed stream formats: what a sender with compress_rgb / compress_depth puts on the wire ----
+def encode_depth8(depth_m, near, far):
+    """Inverse of pre_depth.fs uncompress() (:51-61): byte = round(255 * sqrt((d - near) / (far - near) - 0.15 * s)),
+    s = (far - near) / 255 / ... as the shader defines scaled_near; 0 metres (no measurement) -> byte 0."""
+    d = np.asarray(depth_m, np.float64)
+    scale = float(far) - float(near)
+    sn = scale / 255.0
+    t = (d - near) / scale - 0.15 * sn
+    dc = np.sqrt(np.clip(t, 0.0, 1.0))
+    b = np.clip(np.rint(dc * 255.0), 0, 255)
+    b[d <= 0.0] = 0
+    return b.astype(np.uint8)
+
+
+def encode_dxt1(rgb):
+    """Minimal DXT1 (BC1) encoder for synthetic streams: per 4x4 block the endpoints are the corners of the colour
+    bounding box in 5:6:5, four-colour mode, nearest palette entry per texel. uint8 [H][W][3] -> block bytes."""
+    rgb = np.ascontiguousarray(rgb, np.uint8)
+    H, W, _ = rgb.shape
+    assert H % 4 == 0 and W % 4 == 0
+    blk = rgb.reshape(H // 4, 4, W // 4, 4, 3).transpose(0, 2, 1, 3, 4).reshape(-1, 16, 3).astype(np.int32)
+    hi, lo = blk.max(axis=1), blk.min(axis=1)
+
+    def to565(c):
+        return ((c[:, 0] >> 3) << 11) | ((c[:, 1] >> 2) << 5) | (c[:, 2] >> 3)
+
+    c0, c1 = to565(hi), to565(lo)
+    swap = c0 < c1
+    c0, c1 = np.where(swap, c1, c0), np.where(swap, c0, c1)
+    same = c0 == c1                     # a flat block: three-colour mode, every index 0
+
+    def from565(v):
+        r, g, b = (v >> 11) & 31, (v >> 5) & 63, v & 31
+        return np.stack([(r << 3) | (r >> 2), (g << 2) | (g >> 4), (b << 3) | (b >> 2)], axis=1)
+
+    e0, e1 = from565(c0), from565(c1)
+    pal = np.stack([e0, e1, (2 * e0 + e1) // 3, (e0 + 2 * e1) // 3], axis=1)          # [nb][4][3]
+    dist = ((blk[:, :, None, :] - pal[:, None, :, :]) ** 2).sum(axis=3)                # [nb][16][4]
+    idx = dist.argmin(axis=2).astype(np.uint32)
+    idx[same] = 0
+    bits = (idx << (2 * np.arange(16, dtype=np.uint32))[None, :]).sum(axis=1).astype(np.uint32)
+    out = np.zeros((blk.shape[0], 8), np.uint8)
+    out[:, 0], out[:, 1] = c0 & 255, c0 >> 8
+    out[:, 2], out[:, 3] = c1 & 255, c1 >> 8
+    for k in range(4):
+        out[:, 4 + k] = (bits >> (8 * k)) & 255
+    return out.reshape(-1)

@@ -357,3 +357,22 @@ def test_colorfill_oracle_properties(O):
     clean[holes, 3] = 1.0
     out2 = O.fill_colors(clean, depth)
     assert np.isin(out2[hit].reshape(-1, 4).view(np.uint32), clean.view(np.uint32)).all()
+
+
+def test_dxt1_decoder_against_reference_squish(O):
+    """DXT1 colour ingest: the oracle's BC1 decoder against blocks compressed AND decoded by the reference's own codec
+    external/squish (tests/golden/ref_dxt1.npz, made by tools/make_golden.py through oracle/_ref), including arbitrary
+    block bytes that hit the three-colour (endpoint0 <= endpoint1) mode."""
+    g = gold("ref_dxt1.npz")
+    H, W, _ = g["image"].shape
+    assert np.array_equal(O.decode_dxt1(g["blocks"], W, H), g["decoded"][..., :3])
+    assert np.array_equal(O.decode_dxt1(g["random_blocks"], W, H), g["random_decoded"][..., :3])
+    assert (g["random_decoded"][..., 3] == 0).sum() > 0            # the fixture does contain three-colour blocks
+    import ref_py as R
+    if R.available():
+        assert np.array_equal(R.squish_decompress_dxt1(g["blocks"], W, H), g["decoded"])
+    # 8-bit depth: normalised fixed point, then pre_depth.fs uncompress (through the synthetic sender's inverse)
+    from rrpy import synth
+    d = np.float32([0.0, 0.6, 1.0, 2.0, 3.9, 4.4])
+    f = O.depth8_to_float(synth.encode_depth8(d, 0.5, 4.5))
+    assert np.array_equal(f, (synth.encode_depth8(d, 0.5, 4.5).astype(np.float32) / np.float32(255.0)))

@@ -28,9 +28,29 @@ def golden_scene():
     return synth.make_scene(N=1, W=64, H=53, CW=80, CH=68, cv_res=(16, 16, 32), seed=77)
 
 
+def golden_dxt1():
+    """DXT1 colour ingest: blocks made and decoded by the reference's own codec external/squish."""
+    rng = np.random.default_rng(11)
+    H, W = 48, 64
+    yy, xx = np.mgrid[0:H, 0:W]
+    img = np.stack([(xx * 4) % 256, (yy * 5) % 256, ((xx // 8 + yy // 8) % 2) * 200 + 20], axis=2).astype(np.int32)
+    img = np.clip(img + rng.integers(-12, 13, size=img.shape), 0, 255).astype(np.uint8)
+    blocks = R.squish_compress_dxt1(img)
+    decoded = R.squish_decompress_dxt1(blocks, W, H)
+    # arbitrary block bytes exercise both endpoint orders (4-colour and 3-colour + transparent-black mode)
+    rnd = rng.integers(0, 256, size=(W // 4) * (H // 4) * 8, dtype=np.uint8)
+    rnd_decoded = R.squish_decompress_dxt1(rnd, W, H)
+    np.savez_compressed(os.path.join(OUT, "ref_dxt1.npz"), image=img, blocks=blocks, decoded=decoded, random_blocks=rnd,
+                        random_decoded=rnd_decoded)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     assert R.available(), "build oracle/_ref first (make -C oracle all)"
+    if "--only-dxt" in sys.argv:
+        golden_dxt1()
+        return
+    golden_dxt1()
     sc = golden_scene()
     xyz = sc.cv_xyz[0]
     # --- calibration inversion + frustum (real calibration_inverter.cpp / frustum.cpp)
