@@ -41,6 +41,18 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def measured_traffic(bricks):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this workload
+    (profiles/integrate_traffic.json, written by tools/ncu_summary.py --traffic); None when no capture is committed."""
+    p = os.path.join(ROOT, "profiles", "integrate_traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    t = json.load(open(p)).get("bricks" if bricks else "dense")
+    if not t:
+        return None, None
+    return int(t["dram_bytes_read"] + t["dram_bytes_write"]), t.get("source")
+
+
 def make_inputs(res=R):
     from rrpy import synth
     voxel = EXTENT / res
@@ -218,6 +230,45 @@ def run_ours(args):
     # the closing swap makes the compute stream (and so the end event) wait for the last staged copy: all K host->device
     # copies issued inside the timed region are also completed inside it
     ms_e2e = timed(step_host, args.steps, max(50, args.warmup), False, finish=(fu.swap_frames if world == 1 else None))   # >= 50 untimed steps: lets the PCIe link leave its idle state
+    # what bounds e2e: the host->device link. Bandwidth of the same 20 MB pinned copy alone (CUDA events, copy stream idle).
+    link_gbs = None
+    e2e_dxt1 = None
+    if world == 1:
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_copies = 50
+        for _ in range(5):
+            d_color[0].copy_(h_color[0], non_blocking=True); d_depth[0].copy_(h_depth[0], non_blocking=True)
+        torch.cuda.synchronize(dev)
+        l0.record()
+        for _ in range(n_copies):
+            d_color[0].copy_(h_color[0], non_blocking=True); d_depth[0].copy_(h_depth[0], non_blocking=True)
+        l1.record()
+        torch.cuda.synchronize(dev)
+        link_gbs = (cb + db) * n_copies / (l0.elapsed_time(l1) / 1e3) / 1e9
+        # the same step fed the reference's default stream format (compress_rgb: 1, KinectCalibrationFile.cpp:94): DXT1
+        # colour blocks decoded on the device (rr_set_frame_format), float32 depth. Reported beside the RGB8 headline.
+        from rrpy import synth as synth_
+        h_dxt = [torch.from_numpy(np.stack([synth_.encode_dxt1(s.color[i]) for i in range(N_SENSORS)])).pin_memory() for s in scenes]
+        xb = h_dxt[0].numel()
+        fu.synchronize()
+        fu.set_frame_format(dxt1_color=True)
+
+        def step_host_dxt1(i):
+            k1 = (i + 1) % N_FRAMES
+            fu.swap_frames()
+            fu.stage_frames_ptr(h_dxt[k1].data_ptr(), xb, h_depth[k1].data_ptr(), db)
+            fu.bricks_clear(); fu.preprocess(); n = fu.bricks_update(sync=True); fu.integrate()
+            return n
+
+        fu.stage_frames_ptr(h_dxt[0].data_ptr(), xb, h_depth[0].data_ptr(), db)
+        ms_dxt = timed(step_host_dxt1, args.steps, max(50, args.warmup), False, finish=fu.swap_frames)
+        fps_dxt = args.steps / (ms_dxt / 1e3)
+        e2e_dxt1 = {"value": round(R ** 3 * fps_dxt / 1e9, 3), "unit": "Gvoxel-updates/s", "frames_per_s": round(fps_dxt, 2),
+                    "h2d_bytes_per_step": int(xb + db), "d2h_bytes_per_step": 4,
+                    "what": "same step, colour streamed as DXT1 blocks (the reference's default stream format) and decoded on the device"}
+        fu.synchronize()
+        fu.set_frame_format(dxt1_color=False)
+        fu.upload_frames_ptr(d_color[0].data_ptr(), cb, d_depth[0].data_ptr(), db, device=True)
     # keep the GPU busy until nvidia-smi has a few samples under load (the timed region can be < 100 ms). Every rank
     # runs the same number of extra steps (derived from the all-reduced step time), since steps contain collectives.
     n_extra = int(min(20000, max(64, 1200.0 / max(1e-3, ms_total / args.steps))))
@@ -288,6 +339,7 @@ def run_ours(args):
     int_avg_ms = int_ms / max(1, int_n)
     achieved = abytes / (int_avg_ms / 1e3) / 1e9 if int_avg_ms > 0 else 0.0
 
+    traffic, traffic_src = measured_traffic(bricks) if world == 1 else (None, None)
     out = {
         "metric": "4-sensor TSDF Gvoxel-updates/s at 512^3 (fused frames/s in frames_per_s)",
         "value": round(value, 3), "unit": "Gvoxel-updates/s", "frames_per_s": round(frames_s, 2),
@@ -300,13 +352,16 @@ def run_ours(args):
                    "l2": "inputs+outputs per step (268 MB inverse volumes, 537 MB TSDF) exceed the 126 MB L2; no explicit flush",
                    "occupied_bricks": int(n_occ), "occupied_ratio": round(float(ratio), 4), "frames_cycled": N_FRAMES},
         "e2e": {"value": round(R ** 3 * e2e_frames_s / 1e9, 3), "unit": "Gvoxel-updates/s", "frames_per_s": round(e2e_frames_s, 2),
-                "h2d_bytes_per_step": int(cb + db), "d2h_bytes_per_step": 4},
+                "h2d_bytes_per_step": int(cb + db), "d2h_bytes_per_step": 4,
+                "h2d_link_gbs": round(link_gbs, 2) if link_gbs else None,
+                "bound": (f"host->device link: {cb + db} B/step at the measured {link_gbs:.1f} GB/s caps e2e at {link_gbs * 1e9 / (cb + db):.0f} frames/s" if link_gbs else None),
+                "dxt1_stream": e2e_dxt1},
         "gpu_launches": int(gpu_launches),
         "stages_ms": {"1preprocess": round(pre_ms / max(1, pre_n), 5), "2integrate": round(int_avg_ms, 5)},
         "view": {"ms_per_view": round(view_ms, 4), "resolution": [VW, VH], "what": "tsdf_raymarch (shaded, brick space skipping) + colour hole filling" + (f" per slab + 1 gather of {multigpu.RECORD_FLOATS * 4}-byte records + composite" if world > 1 else "")},
         "roofline": {"bound": "hbm", "kernel": "k_integrate_fused (clear + occupied-brick integration, one launch = the 2integrate stage)" if bricks else "k_integrate_dense",
                      "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                     "traffic": None, "algorithmic_bytes_per_launch": int(abytes), "peak_source": peak_src},
+                     "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": int(abytes), "peak_source": peak_src},
         "clocks": clocks,
     }
     fu.close()

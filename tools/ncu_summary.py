@@ -1,6 +1,9 @@
 """Summarise an .ncu-rep (read with the ncu CLI, no GPU needed): the metrics the roofline discussion uses.
 
   python tools/ncu_summary.py gpurun_out/x.ncu-rep [--md]
+  python tools/ncu_summary.py gpurun_out/x.ncu-rep --traffic profiles/integrate_traffic.json bricks
+      also records the capture's DRAM bytes per launch (mean over the captured launches) under the given key; bench.py
+      reports it as roofline.traffic
 """
 import csv
 import io
@@ -54,5 +57,30 @@ def main():
             print(f"{w:84s} {units[i]:14s} {vals}")
 
 
+def traffic(rep, out_json, key):
+    import json
+    import os
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+    def col(name):
+        i = hdr.index(name)
+        return sum(float(r[i].replace(",", "")) * scale[units[i]] for r in data) / len(data)
+
+    rec = {"kernel": data[0][hdr.index("Kernel Name")], "launches": len(data),
+           "dram_bytes_read": int(col("dram__bytes_read.sum")), "dram_bytes_write": int(col("dram__bytes_write.sum")),
+           "source": f"ncu --set full --clock-control none, {os.path.basename(rep)}"}
+    cur = json.load(open(out_json)) if os.path.exists(out_json) else {}
+    cur[key] = rec
+    json.dump(cur, open(out_json, "w"), indent=1)
+    print(json.dumps(rec))
+
+
 if __name__ == "__main__":
+    if "--traffic" in sys.argv:
+        k = sys.argv.index("--traffic")
+        traffic(sys.argv[1], sys.argv[k + 1], sys.argv[k + 2])
+        sys.argv = sys.argv[:k]
     main()
