@@ -36,6 +36,8 @@ typedef enum rr_status {
 } rr_status;
 
 /* Runtime knobs of ReconIntegration (framework/reconstruction/recon_integration.cpp:30-60, kinect_client.cpp:87-93). */
+enum rr_voxel_format { RR_VOXELS_F32 = 0, RR_VOXELS_F32_WEIGHT = 1, RR_VOXELS_HALF2 = 2 };
+
 typedef struct rr_config {
   float limit;                    /* TSDF truncation in normalised sensor-depth units (setTsdfLimit)            */
   float voxel_size;               /* metres (setVoxelSize, :341-354)                                            */
@@ -43,7 +45,10 @@ typedef struct rr_config {
   uint32_t min_voxels_per_brick;  /* setMinVoxelsPerBrick, default 10                                           */
   int32_t use_bricks;             /* setUseBricks: integrate occupied bricks only                               */
   int32_t skip_space;             /* setSpaceSkip: raymarch starts/ends at the occupied-brick hull              */
-  int32_t store_weight;           /* extension: also keep the shader-local total_weight per voxel (float32)     */
+  int32_t store_weight;           /* voxel format, an rr_voxel_format: 0 = R32F tsdf like the reference's image3D
+                                     (recon_integration.cpp:86-95); 1 = also keep the shader-local total_weight
+                                     in a second R32F volume; 2 = half2 voxels (tsdf, weight), both rounded to
+                                     nearest-even binary16 at the store (BASELINE config 5)                        */
 } rr_config;
 
 /* Inputs of ReconIntegration::draw (recon_integration.cpp:177-241): the fixed-function matrices it reads back,

@@ -251,6 +251,7 @@ int rr_configure(rr_ctx* c, const rr_config* cfg) {
   RR_REQUIRE(c, cfg, "rr_configure: null config");
   RR_REQUIRE(c, c->have_bbox, "rr_configure: call rr_set_bbox first");
   RR_REQUIRE(c, cfg->voxel_size > 0.0f && cfg->brick_size > 0.0f && cfg->limit > 0.0f, "rr_configure: sizes and limit must be positive");
+  RR_REQUIRE(c, cfg->store_weight >= RR_VOXELS_F32 && cfg->store_weight <= RR_VOXELS_HALF2, "rr_configure: unknown voxel format (store_weight must be 0, 1 or 2)");
   RR_SET_DEVICE(c);
   RR_TRY(check(c, cudaStreamSynchronize(c->stream), "configure sync"));
   uint32_t res[3];
@@ -259,12 +260,12 @@ int rr_configure(rr_ctx* c, const rr_config* cfg) {
   const float bs = host_adjust_brick_size(cfg->voxel_size, cfg->brick_size);
   RR_REQUIRE(c, bs > 0.0f, "rr_configure: brick size rounds to zero voxels");
   const bool new_volume = !c->configured || res[0] != c->res[0] || res[1] != c->res[1] || res[2] != c->res[2] ||
-                          (cfg->store_weight != 0) != (c->d_weight != nullptr);
+                          (cfg->store_weight == RR_VOXELS_F32_WEIGHT) != (c->d_weight != nullptr);
   const bool new_bricks = new_volume || bs != c->bricks.brick_size;
   if (new_volume) {
     const size_t nvox = (size_t)res[0] * res[1] * res[2];
     RR_TRY(dev_alloc(c, &c->d_tsdf, nvox, "tsdf volume"));
-    RR_TRY(dev_alloc(c, &c->d_weight, cfg->store_weight ? nvox : 0, "weight volume"));
+    RR_TRY(dev_alloc(c, &c->d_weight, cfg->store_weight == RR_VOXELS_F32_WEIGHT ? nvox : 0, "weight volume"));
     for (int a = 0; a < 3; ++a) c->res[a] = res[a];
     c->slab_z0 = 0; c->slab_z1 = res[2];
   }
@@ -605,15 +606,53 @@ static int download(rr_ctx* c, void* dst, const void* src, size_t bytes, const c
   return check(c, cudaStreamSynchronize(c->stream), what);
 }
 
+// binary16 -> binary32, exact (host side of the half2 voxel downloads)
+static float half_bits_to_float(uint16_t h) {
+  const uint32_t sign = (uint32_t)(h & 0x8000u) << 16, exp = (h >> 10) & 31u, man = h & 1023u;
+  uint32_t u;
+  if (exp == 0) {
+    if (man == 0) {
+      u = sign;
+    } else {                                   // subnormal half: normalise
+      int e = -1;
+      uint32_t m = man;
+      do { ++e; m <<= 1; } while (!(m & 1024u));
+      u = sign | ((uint32_t)(127 - 15 - e) << 23) | ((m & 1023u) << 13);
+    }
+  } else if (exp == 31) {
+    u = sign | 0x7f800000u | (man << 13);
+  } else {
+    u = sign | ((exp + 112u) << 23) | (man << 13);
+  }
+  float f;
+  std::memcpy(&f, &u, sizeof(f));
+  return f;
+}
+
+// half2 voxels are 4 bytes like R32F ones: download raw, then widen the chosen half in place
+static int download_half2(rr_ctx* c, float* out, int which) {
+  const size_t n = (size_t)c->res[0] * c->res[1] * c->res[2];
+  RR_TRY(download(c, out, c->d_tsdf, n * sizeof(float), "voxel download"));
+  for (size_t i = 0; i < n; ++i) {
+    uint32_t u;
+    std::memcpy(&u, out + i, sizeof(u));
+    out[i] = half_bits_to_float((uint16_t)(which ? (u >> 16) : (u & 0xffffu)));
+  }
+  return RR_OK;
+}
+
 int rr_download_tsdf(rr_ctx* c, float* out) {
   if (!c) return RR_ERR_INVALID;
   RR_REQUIRE(c, out && c->configured, "rr_download_tsdf: not configured or null pointer");
+  if (c->cfg.store_weight == RR_VOXELS_HALF2) return download_half2(c, out, 0);
   return download(c, out, c->d_tsdf, (size_t)c->res[0] * c->res[1] * c->res[2] * sizeof(float), "tsdf download");
 }
 
 int rr_download_weight(rr_ctx* c, float* out) {
   if (!c) return RR_ERR_INVALID;
-  RR_REQUIRE(c, out && c->configured && c->d_weight, "rr_download_weight: store_weight is off");
+  RR_REQUIRE(c, out && c->configured, "rr_download_weight: not configured or null pointer");
+  if (c->cfg.store_weight == RR_VOXELS_HALF2) return download_half2(c, out, 1);
+  RR_REQUIRE(c, c->d_weight, "rr_download_weight: store_weight is off");
   return download(c, out, c->d_weight, (size_t)c->res[0] * c->res[1] * c->res[2] * sizeof(float), "weight download");
 }
 

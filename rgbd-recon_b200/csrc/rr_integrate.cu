@@ -11,9 +11,12 @@
 #include "rr_context.h"
 #include "rr_math.cuh"
 
+#include <cuda_fp16.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 
 namespace rr {
 
@@ -54,7 +57,7 @@ struct Tap {
 // One (x, y) column, z in [zb, ze). All index arithmetic is 32-bit (sizes are validated on the host).
 // z (hence the coarse plane pair) is uniform across a warp wherever the callers keep a warp inside one brick / one
 // dense tile, so the plane-advance branches below do not diverge.
-template <int N, bool WEIGHT>
+template <int N, int MODE>
 __device__ __forceinline__ void march_column(const IntegrateParams& p, int x, int y, int zb, int ze) {
   const float stepX = 1.0f / (float)p.X, stepY = 1.0f / (float)p.Y;
   const float px = ((float)x + 0.5f) * stepX, py = ((float)y + 0.5f) * stepY;
@@ -163,18 +166,24 @@ __device__ __forceinline__ void march_column(const IntegrateParams& p, int x, in
       fuse(t1);
     }
     if (N & 1) { const Tap t = fetch(N - 1); fuse(t); }
-    p.tsdf[o] = weighted_tsd;
-    if (WEIGHT) p.weight[o] = total_weight;
+    if (MODE == 2) {
+      // half2 voxel: (tsdf, weight) rounded to nearest-even half, one 4-byte store
+      const __half2 h = __floats2half2_rn(weighted_tsd, total_weight);
+      reinterpret_cast<uint32_t*>(p.tsdf)[o] = *reinterpret_cast<const uint32_t*>(&h);
+    } else {
+      p.tsdf[o] = weighted_tsd;
+      if (MODE == 1) p.weight[o] = total_weight;
+    }
   }
 }
 
-template <int N, bool WEIGHT>
+template <int N, int MODE>
 __global__ void __launch_bounds__(256) k_integrate_dense(const __grid_constant__ IntegrateParams p) {
   const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
   if (x >= p.X || y >= p.Y) return;
   const int zb = p.z_begin + blockIdx.z * p.z_chunk;
   const int ze = min(zb + p.z_chunk, p.z_end);
-  march_column<N, WEIGHT>(p, x, y, zb, ze);
+  march_column<N, MODE>(p, x, y, zb, ze);
 }
 
 // Occupied bricks only (VolumeSampler::sample(indices), volume_sampler.cpp:74-76). Persistent kernel: a fixed grid
@@ -183,7 +192,7 @@ __global__ void __launch_bounds__(256) k_integrate_dense(const __grid_constant__
 // Bricks may overlap or leave one-voxel gaps (float rounding in divideBox/containedVoxels): overlapping voxels are
 // written twice with the same value, gaps keep the cleared -limit.
 #define BRICK_MAX_THREADS 320
-template <int N, bool WEIGHT, int MINB>
+template <int N, int MODE, int MINB>
 __global__ void __launch_bounds__(BRICK_MAX_THREADS, MINB) k_integrate_bricks(const __grid_constant__ IntegrateParams p, int max_cols, int max_nz, int BRICK_ZCHUNK) {
   const unsigned n_occ = *p.num_occupied;
   const unsigned col_blocks = ((unsigned)max_cols + blockDim.x - 1u) / blockDim.x;
@@ -200,7 +209,7 @@ __global__ void __launch_bounds__(BRICK_MAX_THREADS, MINB) k_integrate_bricks(co
     const int ci = (int)(cc * blockDim.x + threadIdx.x);
     if (zb >= ze || ci >= nx * ny) continue;
     const int cy = ci / nx, cx = ci - cy * nx;
-    march_column<N, WEIGHT>(p, x0 + cx, y0 + cy, zb, ze);
+    march_column<N, MODE>(p, x0 + cx, y0 + cy, zb, ze);
   }
 }
 
@@ -310,7 +319,7 @@ __device__ __forceinline__ void fill_rows(const FusedParams& p, uint32_t row0, u
 // publishes (chunk number + 1, base) as one 64-bit word; the other warps of that chunk spin on the word.
 #define FUSED_SLOTS 8
 // THREADS = 512 caps the kernel at 64 registers (32 warps/SM), 384 at 85 registers (24 warps/SM).
-template <int N, bool WEIGHT, int THREADS>
+template <int N, int MODE, int THREADS>
 __global__ void __launch_bounds__(THREADS, 2) k_integrate_fused(const __grid_constant__ FusedParams p) {
   __shared__ unsigned s_taken;
   __shared__ unsigned long long s_slot[FUSED_SLOTS];
@@ -332,7 +341,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_integrate_fused(const __grid_con
         it = __shfl_sync(0xffffffffu, it, 0);
         if (it >= p.fill_items) break;
         const uint32_t r0 = p.row_begin + it * (uint32_t)p.fill_rows;
-        fill_rows<WEIGHT>(p, r0, min(r0 + (uint32_t)p.fill_rows, p.row_end), lane);
+        fill_rows<MODE == 1>(p, r0, min(r0 + (uint32_t)p.fill_rows, p.row_end), lane);
       }
     } else {
       for (;;) {
@@ -365,7 +374,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_integrate_fused(const __grid_con
         const int ze = min(min(rg[4] + (int)(zc + 1) * p.zchunk, rg[5]), p.ip.z_end);
         if (zb >= ze || (int)col >= nx * ny) continue;
         const int cy = (int)col / nx, cx = (int)col - cy * nx;
-        march_column<N, WEIGHT>(p.ip, x0 + cx, y0 + cy, zb, ze);
+        march_column<N, MODE>(p.ip, x0 + cx, y0 + cy, zb, ze);
       }
     }
   }
@@ -380,6 +389,15 @@ __global__ void __launch_bounds__(256) k_fill(float* __restrict__ dst, size_t n,
   const float4 v = make_float4(value, value, value, value);
   for (size_t j = i; j < n4; j += stride) __stcs(d4 + j, v);
   for (size_t j = n4 * 4 + i; j < n; j += stride) dst[j] = value;
+}
+
+// The cleared voxel as the 4 bytes the fill stores write: -limit (R32F), or half2(-limit, 0) for half2 voxels.
+static float cleared_voxel(int mode, float limit) {
+  if (mode != 2) return -limit;
+  const __half2 h = __floats2half2_rn(-limit, 0.0f);
+  float f;
+  std::memcpy(&f, &h, sizeof(f));
+  return f;
 }
 
 // Launch-shape knobs of the integrator (rr_set_tunable; environment RR_<NAME> gives the initial value).
@@ -401,7 +419,7 @@ Tunables& tunables() {
 }
 
 template <int N>
-static int launch_n(rr_ctx* c, const IntegrateParams& p, bool bricks, bool weight, bool fused) {
+static int launch_n(rr_ctx* c, const IntegrateParams& p, bool bricks, int mode, bool fused) {
   const dim3 blk(32, 8, 1);
   const Tunables& tn = tunables();
   if (bricks) {
@@ -426,12 +444,20 @@ static int launch_n(rr_ctx* c, const IntegrateParams& p, bool bricks, bool weigh
       f.chunk = tn.chunk > 0 ? tn.chunk : (max_cols + 31) / 32;
       f.row_begin = (uint32_t)p.z_begin * (uint32_t)p.Y; f.row_end = (uint32_t)p.z_end * (uint32_t)p.Y;
       f.fill_items = (f.row_end - f.row_begin + (uint32_t)f.fill_rows - 1u) / (uint32_t)f.fill_rows;
-      f.fill_value = -p.limit;
+      f.fill_value = cleared_voxel(mode, p.limit);
       cudaMemsetAsync(c->d_work, 0, 4 * sizeof(uint32_t), c->stream);
       const dim3 grd(148 * std::min(2, std::max(1, tn.ctas)), 1, 1);
-      if (weight) k_integrate_fused<N, true, 384><<<grd, 384, 0, c->stream>>>(f);
-      else if (tn.threads == 384) k_integrate_fused<N, false, 384><<<grd, 384, 0, c->stream>>>(f);
-      else k_integrate_fused<N, false, 512><<<grd, 512, 0, c->stream>>>(f);
+      if constexpr (N > 4) {
+        // 6 registers of plane state per sensor: more than 4 sensors get 256-thread CTAs (128 registers)
+        if (mode == 1) k_integrate_fused<N, 1, 256><<<grd, 256, 0, c->stream>>>(f);
+        else if (mode == 2) k_integrate_fused<N, 2, 256><<<grd, 256, 0, c->stream>>>(f);
+        else k_integrate_fused<N, 0, 256><<<grd, 256, 0, c->stream>>>(f);
+      } else {
+        if (mode == 1) k_integrate_fused<N, 1, 384><<<grd, 384, 0, c->stream>>>(f);
+        else if (mode == 2) k_integrate_fused<N, 2, 384><<<grd, 384, 0, c->stream>>>(f);
+        else if (tn.threads == 384) k_integrate_fused<N, 0, 384><<<grd, 384, 0, c->stream>>>(f);
+        else k_integrate_fused<N, 0, 512><<<grd, 512, 0, c->stream>>>(f);
+      }
       RR_LAUNCH_CHECK(c, "k_integrate_fused");
       return RR_OK;
     }
@@ -444,13 +470,15 @@ static int launch_n(rr_ctx* c, const IntegrateParams& p, bool bricks, bool weigh
     }
     const int zchunk = 9;
     const dim3 grd(148 * std::max(1, tn.brick_grid), 1, 1);
-    if (weight) k_integrate_bricks<N, true, 2><<<grd, threads, 0, c->stream>>>(p, max_cols, max_nz, zchunk);
-    else k_integrate_bricks<N, false, 2><<<grd, threads, 0, c->stream>>>(p, max_cols, max_nz, zchunk);
+    if (mode == 1) k_integrate_bricks<N, 1, 2><<<grd, threads, 0, c->stream>>>(p, max_cols, max_nz, zchunk);
+    else if (mode == 2) k_integrate_bricks<N, 2, 2><<<grd, threads, 0, c->stream>>>(p, max_cols, max_nz, zchunk);
+    else k_integrate_bricks<N, 0, 2><<<grd, threads, 0, c->stream>>>(p, max_cols, max_nz, zchunk);
   } else {
     const int nz = p.z_end - p.z_begin;
     const dim3 grd((p.X + 31) / 32, (p.Y + 7) / 8, (nz + p.z_chunk - 1) / p.z_chunk);
-    if (weight) k_integrate_dense<N, true><<<grd, blk, 0, c->stream>>>(p);
-    else k_integrate_dense<N, false><<<grd, blk, 0, c->stream>>>(p);
+    if (mode == 1) k_integrate_dense<N, 1><<<grd, blk, 0, c->stream>>>(p);
+    else if (mode == 2) k_integrate_dense<N, 2><<<grd, blk, 0, c->stream>>>(p);
+    else k_integrate_dense<N, 0><<<grd, blk, 0, c->stream>>>(p);
   }
   RR_LAUNCH_CHECK(c, "k_integrate");
   return RR_OK;
@@ -482,7 +510,8 @@ int launch_integrate(rr_ctx* c) {
   }
   p.ztab = c->d_ztab;
   p.limit = c->cfg.limit;
-  const bool weight = c->cfg.store_weight != 0;
+  const int mode = c->cfg.store_weight == RR_VOXELS_HALF2 ? 2 : (c->cfg.store_weight != 0 ? 1 : 0);
+  const bool weight = mode == 1;
   const bool bricks = c->cfg.use_bricks != 0;
   timer_begin(c, "2integrate");
   const size_t plane = (size_t)p.X * p.Y;
@@ -491,7 +520,7 @@ int launch_integrate(rr_ctx* c) {
   const bool fused = bricks && tunables().fused != 0 && c->fused_ok;
   if (bricks && !fused && nslab) {
     // dense mode overwrites every voxel, so only the brick path needs the clear
-    k_fill<<<148 * 8, 256, 0, c->stream>>>(c->d_tsdf + plane * p.z_begin, nslab, -p.limit);
+    k_fill<<<148 * 8, 256, 0, c->stream>>>(c->d_tsdf + plane * p.z_begin, nslab, cleared_voxel(mode, p.limit));
     RR_LAUNCH_CHECK(c, "k_fill");
     if (weight) {
       k_fill<<<148 * 8, 256, 0, c->stream>>>(c->d_weight + plane * p.z_begin, nslab, 0.0f);
@@ -501,14 +530,14 @@ int launch_integrate(rr_ctx* c) {
   int rc = RR_OK;
   if (nslab) {
     switch (c->N) {
-      case 1: rc = launch_n<1>(c, p, bricks, weight, fused); break;
-      case 2: rc = launch_n<2>(c, p, bricks, weight, fused); break;
-      case 3: rc = launch_n<3>(c, p, bricks, weight, fused); break;
-      case 4: rc = launch_n<4>(c, p, bricks, weight, fused); break;
-      case 5: rc = launch_n<5>(c, p, bricks, weight, fused); break;
-      case 6: rc = launch_n<6>(c, p, bricks, weight, fused); break;
-      case 7: rc = launch_n<7>(c, p, bricks, weight, fused); break;
-      case 8: rc = launch_n<8>(c, p, bricks, weight, fused); break;
+      case 1: rc = launch_n<1>(c, p, bricks, mode, fused); break;
+      case 2: rc = launch_n<2>(c, p, bricks, mode, fused); break;
+      case 3: rc = launch_n<3>(c, p, bricks, mode, fused); break;
+      case 4: rc = launch_n<4>(c, p, bricks, mode, fused); break;
+      case 5: rc = launch_n<5>(c, p, bricks, mode, fused); break;
+      case 6: rc = launch_n<6>(c, p, bricks, mode, fused); break;
+      case 7: rc = launch_n<7>(c, p, bricks, mode, fused); break;
+      case 8: rc = launch_n<8>(c, p, bricks, mode, fused); break;
       default: return fail(c, RR_ERR_UNSUPPORTED, "integrate: 1..8 sensors supported");
     }
   }

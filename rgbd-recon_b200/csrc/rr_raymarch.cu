@@ -13,6 +13,8 @@
 #include "rr_context.h"
 #include "rr_math.cuh"
 
+#include <cuda_fp16.h>
+
 #include <cmath>
 
 namespace rr {
@@ -23,6 +25,7 @@ struct RayParams {
   float cam[3];
   float proj22, proj32;
   const float* tsdf; int X, Y, Z;
+  int half2;                      // voxels are half2 (tsdf, weight): the density is the low half
   float limit;
   int N; const float4* inv; int IX, IY, IZ;
   const float2* uv[RR_MAX_SENSORS]; int cx[RR_MAX_SENSORS], cy[RR_MAX_SENSORS], cz[RR_MAX_SENSORS];
@@ -52,17 +55,25 @@ __device__ __forceinline__ bool slab(float3 o, float3 invd, float3 lo, float3 hi
   return t0 <= t1;
 }
 
+// One voxel's density: R32F, or the low half of a half2 (tsdf, weight) voxel widened exactly (warp-uniform branch).
+__device__ __forceinline__ float ld_density(const RayParams& p, unsigned i) {
+  if (p.half2) {
+    const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(p.tsdf) + i);
+    return __half2float(__ushort_as_half((unsigned short)(u & 0xffffu)));
+  }
+  return __ldg(p.tsdf + i);
+}
+
 __device__ __forceinline__ float sample_tsdf(const RayParams& p, float3 q) {
   int x0, x1, y0, y1, z0, z1; float a, b, g;
   lin_coord(q.x, p.X, x0, x1, a);
   lin_coord(q.y, p.Y, y0, y1, b);
   lin_coord(q.z, p.Z, z0, z1, g);
   const unsigned sy = (unsigned)p.X, sz = (unsigned)(p.X * p.Y);
-  const float* T = p.tsdf;
-  const float c00 = lerpf(__ldg(T + z0 * sz + y0 * sy + x0), __ldg(T + z0 * sz + y0 * sy + x1), a);
-  const float c10 = lerpf(__ldg(T + z0 * sz + y1 * sy + x0), __ldg(T + z0 * sz + y1 * sy + x1), a);
-  const float c01 = lerpf(__ldg(T + z1 * sz + y0 * sy + x0), __ldg(T + z1 * sz + y0 * sy + x1), a);
-  const float c11 = lerpf(__ldg(T + z1 * sz + y1 * sy + x0), __ldg(T + z1 * sz + y1 * sy + x1), a);
+  const float c00 = lerpf(ld_density(p, z0 * sz + y0 * sy + x0), ld_density(p, z0 * sz + y0 * sy + x1), a);
+  const float c10 = lerpf(ld_density(p, z0 * sz + y1 * sy + x0), ld_density(p, z0 * sz + y1 * sy + x1), a);
+  const float c01 = lerpf(ld_density(p, z1 * sz + y0 * sy + x0), ld_density(p, z1 * sz + y0 * sy + x1), a);
+  const float c11 = lerpf(ld_density(p, z1 * sz + y1 * sy + x0), ld_density(p, z1 * sz + y1 * sy + x1), a);
   return lerpf(lerpf(c00, c10, b), lerpf(c01, c11, b), g);
 }
 
@@ -429,6 +440,7 @@ int launch_raymarch(rr_ctx* c, const rr_view* v) {
       p.cam[r] = std::fmaf(p.inv_v2w[12 + r], cw[3], std::fmaf(p.inv_v2w[8 + r], cw[2], std::fmaf(p.inv_v2w[4 + r], cw[1], p.inv_v2w[r] * cw[0])));
   }
   p.proj22 = v->projection[10]; p.proj32 = v->projection[14];
+  p.half2 = c->cfg.store_weight == RR_VOXELS_HALF2 ? 1 : 0;
   p.tsdf = c->d_tsdf; p.X = (int)c->res[0]; p.Y = (int)c->res[1]; p.Z = (int)c->res[2];
   p.limit = c->cfg.limit;
   p.N = c->N; p.inv = c->d_inv; p.IX = (int)c->ires[0]; p.IY = (int)c->ires[1]; p.IZ = (int)c->ires[2];

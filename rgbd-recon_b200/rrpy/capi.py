@@ -24,6 +24,10 @@ class Config(C.Structure):
                 ("store_weight", C.c_int32)]
 
 
+# rr_voxel_format (rr_config.store_weight)
+VOXELS_F32, VOXELS_F32_WEIGHT, VOXELS_HALF2 = 0, 1, 2
+
+
 class View(C.Structure):
     _fields_ = [("modelview", C.c_float * 16), ("projection", C.c_float * 16), ("viewport", C.c_int32 * 4),
                 ("shade_mode", C.c_int32)]
@@ -175,6 +179,7 @@ class Fusion:
     # settings
     def configure(self, limit=0.01, voxel_size=0.01, brick_size=0.1, min_voxels=10, use_bricks=True, skip_space=True,
                   store_weight=False):
+        """store_weight: False/0 R32F tsdf, True/1 + R32F weight volume, VOXELS_HALF2 (2) half2 (tsdf, weight) voxels."""
         cfg = Config(limit, voxel_size, brick_size, min_voxels, int(use_bricks), int(skip_space), int(store_weight))
         self._ck(self.L.rr_configure(self.h, C.byref(cfg)))
 

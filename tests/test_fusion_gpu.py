@@ -139,3 +139,54 @@ def test_staged_ingest_double_buffer(small_scene):
         assert bits_equal(got, want).all(), mismatch_report(f"tsdf of pipelined frame {i}", got, want)
     fu.stage_sync()
     fu.close()
+
+
+def _half_round(a):
+    """The value a half2 voxel holds: binary32 -> nearest-even binary16 -> binary32 (numpy's float16 cast is IEEE RN)."""
+    with np.errstate(over="ignore"):
+        return np.asarray(a, np.float32).astype(np.float16).astype(np.float32)
+
+
+@pytest.mark.parametrize("use_bricks,fused", [(True, "1"), (True, "0"), (False, "1")])
+def test_half2_voxels_are_the_rounded_oracle(small_scene, use_bricks, fused, monkeypatch):
+    """BASELINE config 5 voxel format: (tsdf, weight) as half2. The arithmetic stays fp32; only the store rounds, so the
+    volume must equal the fp16-rounded oracle bit for bit ('report against an fp16-rounded oracle')."""
+    import oracle_py as O
+    from rrpy import capi, synth
+    capi.set_tunable("fused", int(fused))
+    try:
+        sc = small_scene
+        inv = synth.analytic_inverse(sc, (50, 55, 50))
+        fu = capi.Fusion(sc.N, sc.W, sc.H, sc.CW, sc.CH)
+        capi.load_scene(fu, sc, inv)
+        fu.configure(limit=0.01, voxel_size=0.02, brick_size=0.1, min_voxels=10, use_bricks=use_bricks, store_weight=capi.VOXELS_HALF2)
+        fu.upload_frames(sc.color, sc.depth)
+        fu.frame(sync_bricks=True)
+        tsdf, weight = fu.download_tsdf(), fu.download_weight()
+        fu.close()
+    finally:
+        capi.set_tunable("fused", 1)
+    grid = O.brick_grid(sc.bbox_min, sc.bbox_max, 0.02, 0.1)
+    cams = [O.frustum(sc.cv_xyz[i])[1] for i in range(sc.N)]
+    pre = O.preprocess(sc, grid, cams)
+    occ = O.occupied_bricks(pre["bricks"], 10)
+    wt, ww = O.integrate(inv, pre, grid, 0.01, use_bricks, occ, want_weight=True)
+    wt, ww = _half_round(wt), _half_round(ww)
+    assert (np.abs(wt) > 0).any() and (ww > 0).any()
+    assert bits_equal(tsdf, wt).all(), mismatch_report("half2 tsdf", tsdf, wt)
+    assert bits_equal(weight, ww).all(), mismatch_report("half2 weight", weight, ww)
+    # the stated fp16 tolerance (SURVEY.md 8d): 11-bit mantissa on |v| <= limit -> within 2^-11 * limit of the fp32 oracle
+    full = O.integrate(inv, pre, grid, 0.01, use_bricks, occ)
+    ok = np.isfinite(full)
+    assert np.abs(tsdf[ok] - full[ok]).max() <= 0.01 * 2.0 ** -11
+
+
+def test_frame_eight_sensors(monkeypatch):
+    """BASELINE config 5 sensor count: 8 sensors on the ring (the reference's uniform arrays stop at 5; the kernels are
+    instantiated up to 8). Bricks + dense, bit-identical to the oracle."""
+    from rrpy import synth
+    sc = synth.make_scene(N=8, W=96, H=80, CW=128, CH=108, cv_res=(24, 24, 48))
+    for use_bricks in (True, False):
+        got, want = _run_both(sc, 0.025, (40, 44, 40), use_bricks=use_bricks, store_weight=True)
+        _assert_frame(got, want)
+    assert len(want["occupied"]) > 10

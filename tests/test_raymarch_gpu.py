@@ -76,3 +76,26 @@ def test_raymarch_dense_volume_camera_inside_box(small_scene):
     exact, dmm = _compare(small_scene, fu, st, (0.7, 1.3, 0.75), 1, True, use_bricks=False)
     fu.close()
     assert exact
+
+
+def test_raymarch_half2_volume(small_scene):
+    """Raymarch a half2-voxel volume (BASELINE config 5): must equal the oracle marching the fp16-rounded oracle volume."""
+    import oracle_py as O
+    from rrpy import capi, synth
+    sc = small_scene
+    inv = synth.analytic_inverse(sc, (50, 55, 50))
+    fu = capi.Fusion(sc.N, sc.W, sc.H, sc.CW, sc.CH)
+    capi.load_scene(fu, sc, inv)
+    fu.configure(limit=0.01, voxel_size=0.02, brick_size=0.1, min_voxels=10, use_bricks=True, skip_space=True, store_weight=capi.VOXELS_HALF2)
+    fu.upload_frames(sc.color, sc.depth)
+    fu.frame(sync_bricks=True)
+    grid = O.brick_grid(sc.bbox_min, sc.bbox_max, 0.02, 0.1)
+    cams = [O.frustum(sc.cv_xyz[i])[1] for i in range(sc.N)]
+    pre = O.preprocess(sc, grid, cams)
+    occ = O.occupied_bricks(pre["bricks"], 10)
+    tsdf = O.integrate(inv, pre, grid, 0.01, True, occ).astype(np.float16).astype(np.float32)
+    assert bits_equal(fu.download_tsdf(), tsdf).all()
+    st = dict(inv=inv, grid=grid, pre=pre, occ=occ, tsdf=tsdf)
+    exact, dmm = _compare(sc, fu, st, (1.6, 1.5, 2.2), 1, True)
+    fu.close()
+    assert exact, f"image not bit-identical to the oracle on the rounded volume (max surface deviation {dmm} mm)"
