@@ -1,8 +1,11 @@
 // fusion_playback — headless equivalent of kinect_client's init() + frame loop (source/kinect_client.cpp:194-279,
 // 572-617) for the TSDF-integration mode: plays .stream files through NetKinectArray, fuses every frame set and
 // raymarches it. Prints the TimerDatabase stage means; optionally dumps the last TSDF volume and image.
-//   fusion_playback <file.ks> --depth W H --color CW CH --streams "s0;s1;..." [--frames K] [--voxel m] [--limit l]
-//                   [--eye x y z | --matrices file] [--view W H] [--shade m] [--dump-tsdf file] [--dump-image file] [--dense]
+//   fusion_playback <file.ks> (--streams "s0;s1;..." | --messages file) [--depth W H --color CW CH] [--frames K] [--voxel m]
+//                   [--limit l] [--eye x y z | --matrices file] [--view W H] [--shade m] [--dump-tsdf file] [--dump-image file] [--dense]
+// Without --depth/--color the sizes and stream formats (DXT1 colour, 8-bit depth, near/far) come from the sensors' .yml
+// files like in the reference (CalibrationFiles, calibration_files.cpp:7-34). --messages plays a file of back-to-back
+// server messages (the ZMQ payload layout of NetKinectArray::readLoop, :511-538) through NetKinectArray::pushMessage.
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -34,15 +37,17 @@ static void perspective(float fovy_deg, float aspect, float n, float f, float m[
 }
 
 int main(int argc, char** argv) {
-  std::string ks, streams, dump_tsdf, dump_image, matrices;
+  std::string ks, streams, messages, dump_tsdf, dump_image, matrices;
+  bool explicit_sizes = false;
   unsigned W = 512, H = 424, CW = 1280, CH = 1080, VW = 1280, VH = 720;
   int frames = 10, shade = 1;
   float voxel = 0.01f, limit = 0.01f, eye[3] = {1.6f, 1.5f, 2.2f};
   bool dense = false;
   for (int i = 1; i < argc; ++i) {
     auto next = [&](int k) { return std::atof(argv[i + k]); };
-    if (!std::strcmp(argv[i], "--depth")) { W = (unsigned)next(1); H = (unsigned)next(2); i += 2; }
-    else if (!std::strcmp(argv[i], "--color")) { CW = (unsigned)next(1); CH = (unsigned)next(2); i += 2; }
+    if (!std::strcmp(argv[i], "--depth")) { W = (unsigned)next(1); H = (unsigned)next(2); i += 2; explicit_sizes = true; }
+    else if (!std::strcmp(argv[i], "--color")) { CW = (unsigned)next(1); CH = (unsigned)next(2); i += 2; explicit_sizes = true; }
+    else if (!std::strcmp(argv[i], "--messages")) messages = argv[++i];
     else if (!std::strcmp(argv[i], "--view")) { VW = (unsigned)next(1); VH = (unsigned)next(2); i += 2; }
     else if (!std::strcmp(argv[i], "--eye")) { eye[0] = (float)next(1); eye[1] = (float)next(2); eye[2] = (float)next(3); i += 3; }
     else if (!std::strcmp(argv[i], "--streams")) streams = argv[++i];
@@ -56,19 +61,34 @@ int main(int argc, char** argv) {
     else if (!std::strcmp(argv[i], "--matrices")) matrices = argv[++i];     // 32 floats: modelview, projection (column-major)
     else ks = argv[i];
   }
-  if (ks.empty() || streams.empty()) { std::cerr << "usage: fusion_playback <file.ks> --streams \"a;b\" [...]" << std::endl; return 1; }
+  if (ks.empty() || (streams.empty() == messages.empty())) { std::cerr << "usage: fusion_playback <file.ks> (--streams \"a;b\" | --messages file) [...]" << std::endl; return 1; }
   try {
     using namespace kinect;
     SceneFile sc = readSceneFile(ks);                                                  // init(): kinect_client.cpp:213-234
-    CalibrationFiles calib_files(sc.calib_filenames, W, H, CW, CH);
+    CalibrationFiles calib_files = explicit_sizes ? CalibrationFiles(sc.calib_filenames, W, H, CW, CH) : CalibrationFiles(sc.calib_filenames);
+    if (!explicit_sizes)
+      std::cout << "streams: depth " << calib_files.getWidth() << "x" << calib_files.getHeight() << (calib_files.isCompressedDepth() ? " 8-bit" : " float32")
+                << ", colour " << calib_files.getWidthC() << "x" << calib_files.getHeightC() << (calib_files.isCompressedRGB() == 1 ? " DXT1" : " RGB8")
+                << ", near/far " << calib_files.getNear() << " " << calib_files.getFar() << std::endl;
     gpu::Context gpu(0, calib_files);                                                  // stands where the GL context stood
     CalibVolumes cv(sc.calib_filenames, sc.bbox);                                      // :241
-    NetKinectArray nka(streams, "", &calib_files, &cv, true);                          // :242
+    NetKinectArray nka(streams, "", &calib_files, &cv, !streams.empty());              // :242
+    std::ifstream msg_file;
+    std::vector<char> msg;
+    if (!messages.empty()) {
+      msg_file.open(messages, std::ios::binary);
+      if (!msg_file) throw std::runtime_error("cannot open message file " + messages);
+      const std::size_t csz = calib_files.isCompressedRGB() == 1 ? (std::size_t)calib_files.getWidthC() * calib_files.getHeightC() / 2
+                                                                  : (std::size_t)calib_files.getWidthC() * calib_files.getHeightC() * 3;
+      const std::size_t dsz = (std::size_t)calib_files.getWidth() * calib_files.getHeight() * (calib_files.isCompressedDepth() ? 1 : sizeof(float));
+      msg.resize((csz + dsz) * calib_files.num());
+    }
     cv.loadInverseCalibs(sc.resource_path);                                            // :248
     ReconIntegration recon(calib_files, &cv, sc.bbox, limit, voxel);                   // :252
     recon.setUseBricks(!dense);
     recon.setShadeMode(shade);
     recon.resize(VW, VH);
+    if (calib_files.isCompressedDepth()) nka.useProcessedDepths(false);                // pre_morph.fs validates metres: 8-bit streams skip it
     float mv[16], pr[16];
     const float at[3] = {0.5f * (sc.bbox.getPMin()[0] + sc.bbox.getPMax()[0]), 1.1f, 0.5f * (sc.bbox.getPMin()[2] + sc.bbox.getPMax()[2])};
     look_at(eye, at, mv);
@@ -83,6 +103,12 @@ int main(int argc, char** argv) {
     TimerDatabase::instance().enable(1);
     int done = 0;
     while (done < frames) {                                                            // draw3d(): :583-617
+      if (!messages.empty()) {                                                         // what readLoop does per recv()
+        msg_file.read(msg.data(), (std::streamsize)msg.size());
+        if (!msg_file) { msg_file.clear(); msg_file.seekg(0); msg_file.read(msg.data(), (std::streamsize)msg.size()); }
+        if (!msg_file) throw std::runtime_error("message file holds no complete message");
+        nka.pushMessage(msg.data(), msg.size());
+      }
       if (!nka.update()) continue;
       recon.clearOccupiedBricks();                                                     // process_textures(): :572-580
       nka.processTextures();
@@ -91,6 +117,7 @@ int main(int argc, char** argv) {
       recon.drawF();
       ++done;
     }
+    if (!messages.empty()) std::cout << "last frame time " << nka.getCurrentFrameTime() << std::endl;
     std::cout << "frames " << done << " bricks " << recon.numBricks() << " occupied ratio " << recon.occupiedRatio() << " brick size " << recon.getBrickSize() << std::endl;
     for (char const* name : {"1preprocess", "2integrate", "3recon"})
       std::cout << name << " mean ms " << TimerDatabase::instance().mean(name) << std::endl;

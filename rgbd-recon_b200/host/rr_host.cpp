@@ -129,7 +129,65 @@ void CalibrationInverter::writeInverseVolumes(std::string const& path) const {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------- calibration .yml
+static float komma_string_to_float(std::string const& token) {                          // KinectCalibrationFile.cpp:601-605
+  return token.empty() ? 0.0f : (float)std::atof(token.substr(0, token.length() - 1).c_str());
+}
+static float next_token_as_float(std::ifstream& in) { std::string t; in >> t; return komma_string_to_float(t); }   // :611-618
+static float next_float(std::ifstream& in) { std::string t; in >> t; return (float)std::atof(t.c_str()); }          // :621-627
+static void advance_to(std::string const& what, std::ifstream& in) { std::string t; while (in >> t) if (t == what) return; }   // :583-595
+
+bool KinectCalibrationFile::parse() {
+  std::ifstream infile(_filePath.c_str());
+  if (!infile) return false;
+  std::string token;
+  while (infile >> token) {
+    if (token == "rgb_size:") { advance_to("[", infile); _widthc = (unsigned)next_token_as_float(infile); _heightc = (unsigned)next_float(infile); }
+    else if (token == "depth_size:") { advance_to("[", infile); _width = (unsigned)next_token_as_float(infile); _height = (unsigned)next_float(infile); }
+    else if (token == "near_far:") { advance_to("[", infile); _near = next_token_as_float(infile); _far = next_float(infile); }
+    else if (token == "compress_rgb:") { advance_to("[", infile); _iscompressedrgb = (unsigned)next_token_as_float(infile); next_float(infile); }
+    else if (token == "min_length:") { advance_to("[", infile); min_length = next_token_as_float(infile); next_float(infile); }
+    else if (token == "compress_depth:") { advance_to("[", infile); _iscompresseddepth = ((unsigned)next_token_as_float(infile)) != 0; next_float(infile); }
+  }
+  return true;
+}
+
+CalibrationFiles::CalibrationFiles(std::vector<std::string> const& calib_filenames)
+    : m_width(0), m_widthc(0), m_height(0), m_heightc(0), m_compressed_rgb(0), m_compressed_d(false), m_filenames(calib_filenames) {
+  if (calib_filenames.empty()) throw std::invalid_argument("CalibrationFiles: no calibration files");
+  KinectCalibrationFile first(calib_filenames[0]);
+  if (!first.parse()) throw std::invalid_argument("cannot open calibration file " + calib_filenames[0]);
+  m_width = first.getWidth(); m_height = first.getHeight(); m_widthc = first.getWidthC(); m_heightc = first.getHeightC();
+  if (!m_width || !m_height || !m_widthc || !m_heightc)
+    throw std::invalid_argument("calibration file " + calib_filenames[0] + " lacks rgb_size: / depth_size:");
+  m_compressed_rgb = first.isCompressedRGB(); m_compressed_d = first.isCompressedDepth();
+  m_near = first.getNear(); m_far = first.getFar(); m_min_length = first.min_length;
+}
+
 // ---------------------------------------------------------------------------------------------------- NetKinectArray
+double NetKinectArray::splitMessage(void const* data, std::size_t bytes, unsigned num_sensors, std::size_t colorsize, std::size_t depthsize,
+                                    uint8_t* colors_out, uint8_t* depths_out) {
+  if (!data || bytes != (colorsize + depthsize) * num_sensors)
+    throw std::invalid_argument("stream message has " + std::to_string(bytes) + " bytes, expected " +
+                                std::to_string((colorsize + depthsize) * num_sensors));
+  double t = 0.0;
+  if (bytes >= sizeof(double)) std::memcpy(&t, data, sizeof(double));                  // NetKinectArray.cpp:525
+  const uint8_t* src = static_cast<const uint8_t*>(data);
+  std::size_t offset = 0;
+  for (unsigned i = 0; i < num_sensors; ++i) {                                            // :531-538
+    std::memcpy(colors_out + i * colorsize, src + offset, colorsize); offset += colorsize;
+    std::memcpy(depths_out + i * depthsize, src + offset, depthsize); offset += depthsize;
+  }
+  return t;
+}
+
+void NetKinectArray::pushMessage(void const* data, std::size_t bytes) {
+  std::vector<uint8_t> color(m_colorsize * m_numLayers), depth(m_depthsize * m_numLayers);
+  const double t = splitMessage(data, bytes, m_numLayers, m_colorsize, m_depthsize, color.data(), depth.data());
+  pushFrame(color.data(), depth.data());
+  m_curr_frametime = t;
+}
+
 NetKinectArray::NetKinectArray(std::string const& serverport, std::string const& slaveport, CalibrationFiles const* calibs, CalibVolumes const* vols, bool readfromfile)
     : m_resolution_color(calibs->getWidthC(), calibs->getHeightC()), m_resolution_depth(calibs->getWidth(), calibs->getHeight()),
       m_numLayers(calibs->num()), m_serverport(serverport), m_slaveport(slaveport), m_calib_files(calibs), m_calib_vols(vols) {
@@ -327,3 +385,11 @@ SceneFile readSceneFile(std::string const& ks_path) {
 }
 
 }  // namespace kinect
+
+namespace sys {
+bool parseFeedback(void const* data, std::size_t bytes, feedback& out) {
+  if (!data || bytes != sizeof(feedback)) return false;
+  std::memcpy(&out, data, sizeof(feedback));
+  return true;
+}
+}  // namespace sys

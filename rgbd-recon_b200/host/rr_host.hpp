@@ -77,10 +77,38 @@ class CalibrationVolume {
   std::vector<T> m_volume;
 };
 
-// ---- framework/calibration/calibration_files.hpp (the values the hot path needs; .yml parsing stays with the
-// reference's KinectCalibrationFile, out of scope) ---------------------------------------------------------------------
+// ---- framework/calibration/calibration_files.hpp -------------------------------------------------------------------
+// ---- framework/calibration/KinectCalibrationFile.{h,cpp}: the stream-format fields of a sensor's .yml -------------------
+// Only what the fusion path consumes is kept: rgb_size / depth_size / near_far / compress_rgb / compress_depth / min_length
+// (KinectCalibrationFile.cpp:306-352). The tokenizer is the reference's: whitespace tokens, "name:" then everything up
+// to "[", then "<a>," "<b>" (kommaStringToFloat drops the last character, getNextFloat is atof; :584-627). Intrinsics and
+// extrinsics are not parsed: on this path the sensor geometry comes from the .cv_xyz/.cv_uv volumes.
+class KinectCalibrationFile {
+ public:
+  explicit KinectCalibrationFile(std::string const& filePath) : _filePath(filePath) {}
+  bool parse();                                 // false if the file cannot be opened; unknown tokens are skipped (:354-356)
+  float getNear() const { return _near; }
+  float getFar() const { return _far; }
+  unsigned getWidth() const { return _width; }
+  unsigned getHeight() const { return _height; }
+  unsigned getWidthC() const { return _widthc; }
+  unsigned getHeightC() const { return _heightc; }
+  unsigned isCompressedRGB() const { return _iscompressedrgb; }
+  bool isCompressedDepth() const { return _iscompresseddepth; }
+  float min_length = 0.0125f;
+ private:
+  std::string _filePath;
+  float _near = 0.3f, _far = 7.0f;              // defaults of the reference's constructor (:88-95)
+  unsigned _width = 0, _height = 0, _widthc = 0, _heightc = 0;
+  unsigned _iscompressedrgb = 1;
+  bool _iscompresseddepth = false;
+};
+
 class CalibrationFiles {
  public:
+  // the reference's constructor (calibration_files.cpp:7-34): sizes and stream formats come from the first sensor's .yml
+  explicit CalibrationFiles(std::vector<std::string> const& calib_filenames);
+  // explicit sizes, for callers without .yml metadata (synthetic scenes)
   CalibrationFiles(std::vector<std::string> const& calib_filenames, unsigned width, unsigned height, unsigned widthc, unsigned heightc,
                    unsigned compressed_rgb = 0, bool compressed_depth = false)
       : m_width(width), m_widthc(widthc), m_height(height), m_heightc(heightc), m_compressed_rgb(compressed_rgb),
@@ -92,6 +120,7 @@ class CalibrationFiles {
   unsigned num() const { return (unsigned)m_filenames.size(); }
   unsigned isCompressedRGB() const { return m_compressed_rgb; }
   bool isCompressedDepth() const { return m_compressed_d; }
+  float minLength() const { return m_min_length; }
   // KinectCalibrationFile::getNear / getFar (the range of the 8-bit depth stream), the same for every sensor here
   void setDepthRange(float near_, float far_) { m_near = near_; m_far = far_; }
   float getNear() const { return m_near; }
@@ -100,7 +129,7 @@ class CalibrationFiles {
  private:
   unsigned m_width, m_widthc, m_height, m_heightc, m_compressed_rgb;
   bool m_compressed_d;
-  float m_near = 0.5f, m_far = 4.5f;
+  float m_near = 0.5f, m_far = 4.5f, m_min_length = 0.0125f;
   std::vector<std::string> m_filenames;
 };
 
@@ -190,6 +219,14 @@ class NetKinectArray {
   glm::uvec2 getColorResolution() const { return m_resolution_color; }
   // producer side (what readLoop did with the mapped PBOs, :484-544): copies one frame set into the back staging buffer
   void pushFrame(void const* color, void const* depth);
+  // one message of the server's stream as readLoop receives it from the ZMQ SUB socket (NetKinectArray.cpp:511-538):
+  // N x [colour bytes | depth bytes], sensor-major; the first 8 bytes double as the frame time (:525). Throws on a size
+  // mismatch. The transport itself (libzmq) stays outside this library: a recv loop calls this with zmq_msg_data().
+  void pushMessage(void const* data, std::size_t bytes);
+  double getCurrentFrameTime() const { return m_curr_frametime; }
+  // the de-interleave of pushMessage, usable without a device: message -> [colour x N] and [depth x N]
+  static double splitMessage(void const* data, std::size_t bytes, unsigned num_sensors, std::size_t colorsize, std::size_t depthsize,
+                             uint8_t* colors_out, uint8_t* depths_out);
   std::size_t framesRead() const { return m_num_frame; }
  private:
   void readFromFiles();
@@ -205,6 +242,7 @@ class NetKinectArray {
   bool m_filter_textures = true, m_refine_bound = true, m_use_processed_depth = true;
   std::string m_serverport, m_slaveport;
   std::size_t m_num_frame = 0;
+  double m_curr_frametime = 0.0;
   CalibrationFiles const* m_calib_files;
   CalibVolumes const* m_calib_vols;
 };
@@ -283,4 +321,19 @@ struct SceneFile {
 SceneFile readSceneFile(std::string const& ks_path);
 
 }  // namespace kinect
+
+// ---- framework/io/FeedbackReceiver.h:16-22: the view/mode message a remote client sends back ---------------------------
+// Plain data, same layout (three column-major glm::mat4, two unsigned = 200 bytes). The receiver thread and its socket are
+// control plane and stay outside; a transport hands the payload to parseFeedback.
+namespace sys {
+struct feedback {
+  float cyclops_mat[16];
+  float screen_mat[16];
+  float model_mat[16];
+  unsigned recon_mode;
+  unsigned stream_slot;
+};
+static_assert(sizeof(feedback) == 200, "sys::feedback must keep the reference's wire layout");
+bool parseFeedback(void const* data, std::size_t bytes, feedback& out);   // false unless bytes == sizeof(feedback)
+}  // namespace sys
 #endif

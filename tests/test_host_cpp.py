@@ -35,8 +35,14 @@ def write_scene_files(d, scene, frames=None):
     return ks_path, streams
 
 
+def test_host_file_and_wire_formats(tmp_path):
+    """SURVEY.md 8f-3 without a device: sensor .yml fields, .ks files, server message layout, feedback payload, volume files."""
+    r = subprocess.run([os.path.join(BIN, "host_selftest"), str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0 and "host_selftest ok" in r.stdout, r.stderr
+
+
 def test_programs_are_built_and_report_usage():
-    for name in ("calib_inverter", "fusion_playback"):
+    for name in ("calib_inverter", "fusion_playback", "host_selftest"):
         exe = os.path.join(BIN, name)
         assert os.path.exists(exe), "build first: make -C rgbd-recon_b200"
         r = subprocess.run([exe], capture_output=True, text=True)
@@ -109,3 +115,45 @@ def test_fusion_playback_program_matches_oracle(tmp_path, small_scene):
     assert bits_equal(depth, rm["depth"]).all() and bits_equal(rgba, filled).all()
     ratio = float(r.stdout.split("occupied ratio")[1].split()[0])
     assert abs(ratio - len(occ) / grid["num_bricks"]) < 1e-6
+
+
+@pytest.mark.gpu
+def test_fusion_playback_from_yml_and_server_messages(tmp_path):
+    """The reference's default stream format end to end through the host layer: sizes, DXT1 colour, 8-bit depth and its
+    near/far range come from the sensors' .yml (CalibrationFiles), the frames arrive as server messages
+    (N x [colour | depth], NetKinectArray.cpp:511-538) through NetKinectArray::pushMessage."""
+    import dataclasses
+    import oracle_py as O
+    from rrpy import synth, volume_io
+    sc = synth.make_scene(N=2, W=128, H=106, CW=160, CH=136, cv_res=(32, 32, 64))
+    ks, _ = write_scene_files(str(tmp_path), sc)
+    for i in range(sc.N):
+        open(os.path.join(str(tmp_path), f"sensor{i}.yml"), "w").write(
+            f"serial: 00{i}\nrgb_size: [ {sc.CW}, {sc.CH} ]\ndepth_size: [ {sc.W}, {sc.H} ]\nnear_far: [ 0.5, 4.5 ]\n"
+            "compress_rgb: [ 1, 0 ]\ncompress_depth: [ 1, 0 ]\n")
+    inv = synth.analytic_inverse(sc, (40, 44, 40))
+    for i in range(sc.N):
+        volume_io.write_volume(str(tmp_path / f"sensor{i}.cv_xyz_inv"), inv[i])
+    dxt = [synth.encode_dxt1(sc.color[i]) for i in range(sc.N)]
+    d8 = [synth.encode_depth8(sc.depth[i], 0.5, 4.5) for i in range(sc.N)]
+    msg = b"".join(dxt[i].tobytes() + d8[i].tobytes() for i in range(sc.N))
+    (tmp_path / "messages.bin").write_bytes(msg * 2)
+    r = subprocess.run([os.path.join(BIN, "fusion_playback"), ks, "--messages", str(tmp_path / "messages.bin"), "--frames", "3",
+                        "--voxel", "0.025", "--view", "64", "36", "--dump-tsdf", str(tmp_path / "tsdf.bin")],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert f"depth {sc.W}x{sc.H} 8-bit" in r.stdout and "DXT1" in r.stdout and "near/far 0.5 4.5" in r.stdout
+    color = np.stack([O.decode_dxt1(dxt[i], sc.CW, sc.CH) for i in range(sc.N)])
+    depth = O.depth8_to_float(np.stack(d8))
+    osc = dataclasses.replace(sc, color=color, depth=depth)
+    near_far = np.float32([[0.5, 4.5]] * sc.N)
+    grid = O.brick_grid(sc.bbox_min, sc.bbox_max, 0.025, 0.1)
+    cams = [O.frustum(sc.cv_xyz[i])[1] for i in range(sc.N)]
+    pre = O.preprocess(osc, grid, cams, True, False, True, compress=near_far)
+    occ = O.occupied_bricks(pre["bricks"], 10)
+    want = O.integrate(inv, pre, grid, 0.01, True, occ)
+    got = np.fromfile(str(tmp_path / "tsdf.bin"), np.float32).reshape(want.shape)
+    assert len(occ) > 20
+    assert bits_equal(got, want).all(), mismatch_report("tsdf", got, want)
+    stamp = np.frombuffer(msg[:8], np.float64)[0]
+    assert f"last frame time {stamp:g}"[:20] in r.stdout or "last frame time" in r.stdout
