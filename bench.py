@@ -124,6 +124,8 @@ def run_ours(args):
         import torch.distributed as dist_
         dist = dist_
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"        # keeps NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         torch.cuda.set_device(local)
         import datetime
         dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
@@ -151,23 +153,26 @@ def run_ours(args):
     d_color = [t.to(dev) for t in h_color]
     d_depth = [t.to(dev) for t in h_depth]
     cb, db = h_color[0].numel(), h_depth[0].numel() * 4
-    bcast_c = torch.empty_like(d_color[0]) if world > 1 else None
-    bcast_d = torch.empty_like(d_depth[0]) if world > 1 else None
+    # N > 1: one packed broadcast per frame set, double-buffered (the broadcast of set i+1 overlaps the fusion of set i)
+    fb = multigpu.FrameBroadcaster(dist, dev, cb, db, src=0) if world > 1 else None
+
+    def consume_broadcast():
+        packed, slot = fb.consume(stream)
+        fu.upload_frames_ptr(packed.data_ptr(), cb, packed.data_ptr() + cb, db, device=True)    # into the current frame slot, on the compute stream
+        fb.release(slot, stream)
 
     def step_device(i):
         k = i % N_FRAMES
         if world > 1:
             # each frame set arrives on rank 0 and is broadcast over NVLink (NCCL) before every GPU pre-processes it
-            if rank == 0:
-                bcast_c.copy_(d_color[k], non_blocking=True); bcast_d.copy_(d_depth[k], non_blocking=True)
-            dist.broadcast(bcast_c, 0); dist.broadcast(bcast_d, 0)
-            stream.wait_stream(torch.cuda.current_stream(dev))
-            fu.upload_frames_ptr(bcast_c.data_ptr(), cb, bcast_d.data_ptr(), db, device=True)
+            if fb.in_flight() == 0:
+                fb.issue(d_color[k], d_depth[k])                     # pipeline prologue (first step only)
+            consume_broadcast()
+            fu.frame(sync_bricks=False)
+            fb.issue(d_color[(i + 1) % N_FRAMES], d_depth[(i + 1) % N_FRAMES])
         else:
             fu.upload_frames_ptr(d_color[k].data_ptr(), cb, d_depth[k].data_ptr(), db, device=True)
-        fu.frame(sync_bricks=False)
-        if world > 1:
-            torch.cuda.current_stream(dev).wait_stream(stream)
+            fu.frame(sync_bricks=False)
 
     def step_host(i):
         # the reference's ingest is double-buffered (reader thread fills the back PBO while the front one is drawn,
@@ -177,13 +182,13 @@ def run_ours(args):
         k = i % N_FRAMES
         k1 = (i + 1) % N_FRAMES
         if world > 1:
-            if rank == 0:
-                bcast_c.copy_(h_color[k], non_blocking=True); bcast_d.copy_(h_depth[k], non_blocking=True)
-            dist.broadcast(bcast_c, 0); dist.broadcast(bcast_d, 0)
-            stream.wait_stream(torch.cuda.current_stream(dev))
-            fu.upload_frames_ptr(bcast_c.data_ptr(), cb, bcast_d.data_ptr(), db, device=True)
-            fu.bricks_clear(); fu.preprocess(); n = fu.bricks_update(sync=True); fu.integrate()
-            torch.cuda.current_stream(dev).wait_stream(stream)
+            # rank 0 copies the pinned host frame set into the broadcast slot (its host->device copy), then one broadcast
+            if fb.in_flight() == 0:
+                fb.issue(h_color[k], h_depth[k])
+            consume_broadcast()
+            fu.bricks_clear(); fu.preprocess()
+            fb.issue(h_color[k1], h_depth[k1])                       # next set's host->device copy + broadcast run behind this set's kernels
+            n = fu.bricks_update(sync=True); fu.integrate()
         else:
             fu.swap_frames()
             fu.stage_frames_ptr(h_color[k1].data_ptr(), cb, h_depth[k1].data_ptr(), db)
@@ -191,6 +196,9 @@ def run_ours(args):
         return n
 
     def barrier():
+        if fb is not None:
+            while fb.in_flight():                     # drain the pipeline: every rank consumes what every rank issued
+                consume_broadcast()
         fu.synchronize()
         torch.cuda.synchronize(dev)
         if world > 1:

@@ -155,6 +155,7 @@ struct Tunables {
   int threads = 512;    // CTA size (register budget): 512 (64 registers) or 384 (85 registers)
   int chunk = 1;        // compute items a CTA draws at a time (0: one z-chunk of one brick)
   int brick_grid = 6;   // grid multiple of the unfused brick kernel
+  int ldg256 = 1;       // gather texels with one 256-bit load (0: two 128-bit loads)
 };
 Tunables& tunables();
 

@@ -34,6 +34,7 @@ struct IntegrateParams {
   int z_begin, z_end;     // slab
   int z_chunk;
   float limit;
+  int wide_loads;         // tunable ldg256: gather texels with one 256-bit load
 };
 
 // lin_coord of every fine z against the inverse volume's z axis, evaluated once per (Z, IZ) pair with the same
@@ -46,6 +47,14 @@ __global__ void k_build_ztab(float4* __restrict__ ztab, int Z, int IZ) {
   int k0, k1; float g;
   lin_coord(pz, IZ, k0, k1, g);
   ztab[z] = make_float4(__int_as_float(k0), __int_as_float(k1), g, 1.0f - g);
+}
+
+// One 32-byte gather texel with a single 256-bit load (LDG.E.256, sm_100+): half the load instructions and L1 requests
+// of two LDG.128 on the same sector.
+__device__ __forceinline__ void ldg_texel(const float4* p, float4& lo, float4& hi) {
+  asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
+               : "l"(p));
 }
 
 // One sensor's lookup for one voxel: bilinear weights, interpolated depth coordinate and the 32-byte gather texel.
@@ -123,7 +132,7 @@ __device__ __forceinline__ void march_column(const IntegrateParams& p, int x, in
       // gather-texel index = clamp(footprint, -1, W-1) + 1; fmaxf/fminf drop a NaN operand, so NaN -> entry 0
       const int ex = (int)fminf(fmaxf(fu, -1.0f), p.exmax) + 1, ey = (int)fminf(fmaxf(fv, -1.0f), p.eymax) + 1;
       const float4* g4 = p.gather + ((unsigned)s * gstride + ((unsigned)ey * grow + (unsigned)ex) * 2u);
-      t.lo = __ldg(g4); t.hi = __ldg(g4 + 1);
+      if (p.wide_loads) ldg_texel(g4, t.lo, t.hi); else { t.lo = __ldg(g4); t.hi = __ldg(g4 + 1); }
       return t;
     };
     // tsdf_integration.vs:30-55 for one sensor
@@ -413,6 +422,7 @@ Tunables& tunables() {
     v.threads = env("RR_FUSED_THREADS", v.threads);
     v.chunk = env("RR_FUSED_CHUNK", v.chunk);
     v.brick_grid = env("RR_BRICK_GRID", v.brick_grid);
+    v.ldg256 = env("RR_LDG256", v.ldg256);
     return v;
   }();
   return t;
@@ -510,6 +520,7 @@ int launch_integrate(rr_ctx* c) {
   }
   p.ztab = c->d_ztab;
   p.limit = c->cfg.limit;
+  p.wide_loads = tunables().ldg256;
   const int mode = c->cfg.store_weight == RR_VOXELS_HALF2 ? 2 : (c->cfg.store_weight != 0 ? 1 : 0);
   const bool weight = mode == 1;
   const bool bricks = c->cfg.use_bricks != 0;

@@ -29,6 +29,68 @@ def broadcast_frames(dist, color, depth, src=0):
     return color, depth
 
 
+class FrameBroadcaster:
+    """The per-frame-set collective of the slab path: ONE broadcast of the packed raw frame set
+    (colour bytes then depth bytes, like one server message) from the ingest rank, double-buffered so that the broadcast
+    of frame set i+1 runs while frame set i is pre-processed and integrated.
+
+      issue(color, depth)    enqueue the broadcast of the next frame set (sources are read on the ingest rank only:
+                             device tensors, or pinned host tensors for the end-to-end path)
+      consume(stream)        make `stream` wait for the oldest broadcast in flight; returns (packed uint8 tensor, slot)
+      release(slot, stream)  the consumer's last read of the slot has been enqueued on `stream`
+
+    On CPU tensors (gloo tests) the stream/event arguments are ignored."""
+
+    def __init__(self, dist, device, color_bytes, depth_bytes, src=0):
+        import torch
+        assert color_bytes % 4 == 0, "depth must stay 4-byte aligned behind the colour bytes"
+        self.dist, self.src, self.cb, self.db = dist, src, int(color_bytes), int(depth_bytes)
+        self.cuda = torch.device(device).type == "cuda"
+        self.device = device
+        self.buf = [torch.empty(self.cb + self.db, dtype=torch.uint8, device=device) for _ in range(2)]
+        self.done = [torch.cuda.Event() for _ in range(2)] if self.cuda else None
+        self.free = [torch.cuda.Event() for _ in range(2)] if self.cuda else None
+        self.free_recorded = [False, False]
+        self.issued = self.consumed = 0
+
+    def in_flight(self):
+        return self.issued - self.consumed
+
+    def issue(self, color=None, depth=None):
+        import torch
+        assert self.in_flight() < 2, "both slots hold frame sets that were not consumed"
+        b = self.issued % 2
+        if self.cuda:
+            cur = torch.cuda.current_stream(self.device)
+            if self.free_recorded[b]:
+                cur.wait_event(self.free[b])
+        if self.dist.get_rank() == self.src:
+            self.buf[b][:self.cb].copy_(color.reshape(-1).view(torch.uint8), non_blocking=True)
+            self.buf[b][self.cb:].copy_(depth.reshape(-1).view(torch.uint8), non_blocking=True)
+        self.dist.broadcast(self.buf[b], self.src)
+        if self.cuda:
+            self.done[b].record(cur)
+        self.issued += 1
+
+    def consume(self, stream=None):
+        assert self.in_flight() > 0, "no broadcast in flight"
+        b = self.consumed % 2
+        if self.cuda:
+            stream.wait_event(self.done[b])
+        self.consumed += 1
+        return self.buf[b], b
+
+    def release(self, slot, stream=None):
+        if self.cuda:
+            self.free[slot].record(stream)
+            self.free_recorded[slot] = True
+
+    def unpack(self, packed, color_shape, depth_shape):
+        """Views of a packed frame set: (colour uint8 color_shape, depth float32 depth_shape)."""
+        import torch
+        return packed[:self.cb].view(color_shape), packed[self.cb:].view(torch.float32).view(depth_shape)
+
+
 def gather_records(dist, records, dst=0, out=None):
     """The one gather per view: every rank's [h*w][8] float32 record image onto `dst` as [world][h*w][8]."""
     world, rank = dist.get_world_size(), dist.get_rank()

@@ -46,6 +46,17 @@ def _worker(rank, world, port, q):
         depth = depth_src.clone() if rank == 0 else torch.zeros_like(depth_src)
         M.broadcast_frames(dist, color, depth, 0)
         ok = bool(torch.equal(color, color_src) and torch.equal(depth, depth_src))
+        # the packed, double-buffered broadcaster of the slab path: two frame sets in flight, consumed in order
+        fb = M.FrameBroadcaster(dist, "cpu", color_src.numel(), depth_src.numel() * 4, src=0)
+        sets = [(color_src, depth_src), (255 - color_src, depth_src * 2.0)]
+        for c_, d_ in sets:
+            fb.issue(c_ if rank == 0 else None, d_ if rank == 0 else None)
+        for c_, d_ in sets:
+            packed, slot = fb.consume()
+            gc, gd = fb.unpack(packed, tuple(color_src.shape), tuple(depth_src.shape))
+            ok = ok and bool(torch.equal(gc, c_) and torch.equal(gd, d_))
+            fb.release(slot)
+        ok = ok and fb.in_flight() == 0
         # record gather: each rank "hits" a different subset of 6 pixels at rank-dependent step indices
         n = 6
         rec = np.zeros((n, M.RECORD_FLOATS), np.float32)
