@@ -755,7 +755,6 @@ int rr_set_tunable(const char* name, int value) {
   else if (n == "chunk") t.chunk = value;
   else if (n == "brick_grid") t.brick_grid = value;
   else if (n == "ldg256") t.ldg256 = value;
-  else if (n == "prefetch") t.prefetch = value;
   else return RR_ERR_INVALID;
   return RR_OK;
 }

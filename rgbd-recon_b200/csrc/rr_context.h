@@ -156,7 +156,6 @@ struct Tunables {
   int chunk = 1;        // compute items a CTA draws at a time (0: one z-chunk of one brick)
   int brick_grid = 6;   // grid multiple of the unfused brick kernel
   int ldg256 = 1;       // gather texels with one 256-bit load (0: two 128-bit loads)
-  int prefetch = 0;     // L1 prefetch of the next coarse inverse-volume plane one voxel ahead
 };
 Tunables& tunables();
 

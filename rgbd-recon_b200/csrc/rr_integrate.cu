@@ -35,7 +35,6 @@ struct IntegrateParams {
   int z_chunk;
   float limit;
   int wide_loads;         // tunable ldg256: gather texels with one 256-bit load
-  int prefetch_planes;    // tunable prefetch: L1 prefetch of the next coarse plane's corners one voxel ahead
 };
 
 // lin_coord of every fine z against the inverse volume's z axis, evaluated once per (Z, IZ) pair with the same
@@ -118,19 +117,6 @@ __device__ __forceinline__ void march_column(const IntegrateParams& p, int x, in
         for (int s = 0; s < N; ++s) B[s] = plane(s, k1);
       }
       ck1 = k1;
-    }
-    // L1 prefetch (CCTL.PF1) of the coarse plane the NEXT voxel will advance to: its corner loads are the top stall
-    // site of the kernel (ncu source page, profiles/r1_j_*); one voxel of compute hides the L2 round trip
-    if (p.prefetch_planes && z + 1 < ze) {
-      const int nk1 = __float_as_int(__ldg(reinterpret_cast<const float*>(p.ztab + z + 1) + 1));
-      if (nk1 != ck1) {
-#pragma unroll
-        for (int s = 0; s < N; ++s) {
-          const float4* base = p.inv + (unsigned)(s * p.IZ + nk1) * plane_sz;
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(base + o00));
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(base + o01));
-        }
-      }
     }
     float weighted_tsd = limit, total_weight = 0.0f;
 
@@ -437,7 +423,6 @@ Tunables& tunables() {
     v.chunk = env("RR_FUSED_CHUNK", v.chunk);
     v.brick_grid = env("RR_BRICK_GRID", v.brick_grid);
     v.ldg256 = env("RR_LDG256", v.ldg256);
-    v.prefetch = env("RR_PREFETCH", v.prefetch);
     return v;
   }();
   return t;
@@ -536,7 +521,6 @@ int launch_integrate(rr_ctx* c) {
   p.ztab = c->d_ztab;
   p.limit = c->cfg.limit;
   p.wide_loads = tunables().ldg256;
-  p.prefetch_planes = tunables().prefetch;
   const int mode = c->cfg.store_weight == RR_VOXELS_HALF2 ? 2 : (c->cfg.store_weight != 0 ? 1 : 0);
   const bool weight = mode == 1;
   const bool bricks = c->cfg.use_bricks != 0;

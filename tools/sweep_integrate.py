@@ -17,7 +17,7 @@ sys.path.insert(0, os.path.join(ROOT, "rgbd-recon_b200"))
 import bench  # noqa: E402
 from rrpy import capi  # noqa: E402
 
-DEFAULTS = dict(fused=1, zchunk=13, fill_rows=16, fill_warps=2, ctas=2, threads=512, chunk=1, ldg256=1, prefetch=0)
+DEFAULTS = dict(fused=1, zchunk=13, fill_rows=16, fill_warps=2, ctas=2, threads=512, chunk=1, ldg256=1)
 
 
 def main():
