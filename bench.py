@@ -155,6 +155,12 @@ def run_ours(args):
     cb, db = h_color[0].numel(), h_depth[0].numel() * 4
     # N > 1: one packed broadcast per frame set, double-buffered (the broadcast of set i+1 overlaps the fusion of set i)
     fb = multigpu.FrameBroadcaster(dist, dev, cb, db, src=0) if world > 1 else None
+    if world > 1 and rank == 0:
+        # the ingest rank holds every frame set packed like a server message (colour bytes then depth bytes): one copy per set
+        d_packed = [torch.cat([c.reshape(-1), d.reshape(-1).view(torch.uint8)]) for c, d in zip(d_color, d_depth)]
+        h_packed = [torch.cat([c.reshape(-1), d.reshape(-1).view(torch.uint8)]).pin_memory() for c, d in zip(h_color, h_depth)]
+    else:
+        d_packed = h_packed = [None] * N_FRAMES
 
     def consume_broadcast():
         packed, slot = fb.consume(stream)
@@ -166,10 +172,12 @@ def run_ours(args):
         if world > 1:
             # each frame set arrives on rank 0 and is broadcast over NVLink (NCCL) before every GPU pre-processes it
             if fb.in_flight() == 0:
-                fb.issue(d_color[k], d_depth[k])                     # pipeline prologue (first step only)
+                fb.issue(packed=d_packed[k])                         # pipeline prologue (first step only)
             consume_broadcast()
+            # the next set's broadcast is enqueued BEFORE this set's kernels: NCCL's CTAs then share the SMs with the small
+            # pre-processing kernels instead of queueing behind the persistent integrate kernel, which fills every SM
+            fb.issue(packed=d_packed[(i + 1) % N_FRAMES])
             fu.frame(sync_bricks=False)
-            fb.issue(d_color[(i + 1) % N_FRAMES], d_depth[(i + 1) % N_FRAMES])
         else:
             fu.upload_frames_ptr(d_color[k].data_ptr(), cb, d_depth[k].data_ptr(), db, device=True)
             fu.frame(sync_bricks=False)
@@ -184,11 +192,10 @@ def run_ours(args):
         if world > 1:
             # rank 0 copies the pinned host frame set into the broadcast slot (its host->device copy), then one broadcast
             if fb.in_flight() == 0:
-                fb.issue(h_color[k], h_depth[k])
+                fb.issue(packed=h_packed[k])
             consume_broadcast()
-            fu.bricks_clear(); fu.preprocess()
-            fb.issue(h_color[k1], h_depth[k1])                       # next set's host->device copy + broadcast run behind this set's kernels
-            n = fu.bricks_update(sync=True); fu.integrate()
+            fb.issue(packed=h_packed[k1])                            # next set's host->device copy + broadcast run beside this set's kernels
+            fu.bricks_clear(); fu.preprocess(); n = fu.bricks_update(sync=True); fu.integrate()
         else:
             fu.swap_frames()
             fu.stage_frames_ptr(h_color[k1].data_ptr(), cb, h_depth[k1].data_ptr(), db)
@@ -213,8 +220,10 @@ def run_ours(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = fu.launch_count()
         e0.record(stream)
+        h0 = time.perf_counter()
         for i in range(steps):
             step(warmup + i)
+        timed.host_ms = (time.perf_counter() - h0) * 1e3 / steps      # host time to ENQUEUE one step (diagnostic)
         if finish:
             finish()
         e1.record(stream)
@@ -231,6 +240,7 @@ def run_ours(args):
     sampler = ClockSampler(local, args.clock_ms) if (rank == 0 and args.clock_ms > 0) else None
     ms_total = timed(step_device, args.steps, args.warmup, True)
     gpu_launches = timed.launches
+    host_enqueue_ms = timed.host_ms
     int_ms, int_n = fu.stage_stats("2integrate")
     pre_ms, pre_n = fu.stage_stats("1preprocess")
     if world == 1:
@@ -277,6 +287,22 @@ def run_ours(args):
         fu.synchronize()
         fu.set_frame_format(dxt1_color=False)
         fu.upload_frames_ptr(d_color[0].data_ptr(), cb, d_depth[0].data_ptr(), db, device=True)
+    bcast_ms = None
+    if world > 1:
+        # the broadcast alone (nothing else on the GPUs): what the pipelined step hides, or is bound by
+        barrier()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(3):
+            fb.issue(packed=d_packed[0]); fb.consume(stream)
+        torch.cuda.synchronize(dev)
+        b0.record()
+        for _ in range(20):
+            fb.issue(packed=d_packed[0]); fb.consume(stream)
+        b1.record()
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([b0.elapsed_time(b1) / 20], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        bcast_ms = float(t.item())
     # keep the GPU busy until nvidia-smi has a few samples under load (the timed region can be < 100 ms). Every rank
     # runs the same number of extra steps (derived from the all-reduced step time), since steps contain collectives.
     n_extra = int(min(20000, max(64, 1200.0 / max(1e-3, ms_total / args.steps))))
@@ -364,7 +390,7 @@ def run_ours(args):
                 "h2d_link_gbs": round(link_gbs, 2) if link_gbs else None,
                 "bound": (f"host->device link: {cb + db} B/step at the measured {link_gbs:.1f} GB/s caps e2e at {link_gbs * 1e9 / (cb + db):.0f} frames/s" if link_gbs else None),
                 "dxt1_stream": e2e_dxt1},
-        "gpu_launches": int(gpu_launches),
+        "gpu_launches": int(gpu_launches), "host_enqueue_ms_per_step": round(host_enqueue_ms, 5),
         "stages_ms": {"1preprocess": round(pre_ms / max(1, pre_n), 5), "2integrate": round(int_avg_ms, 5)},
         "view": {"ms_per_view": round(view_ms, 4), "resolution": [VW, VH], "what": "tsdf_raymarch (shaded, brick space skipping) + colour hole filling" + (f" per slab + 1 gather of {multigpu.RECORD_FLOATS * 4}-byte records + composite" if world > 1 else "")},
         "roofline": {"bound": "hbm", "kernel": "k_integrate_fused (clear + occupied-brick integration, one launch = the 2integrate stage)" if bricks else "k_integrate_dense",
@@ -372,6 +398,10 @@ def run_ours(args):
                      "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": int(abytes), "peak_source": peak_src},
         "clocks": clocks,
     }
+    if world > 1:
+        out["broadcast"] = {"bytes": int(cb + db), "ms_alone": round(bcast_ms, 4), "gbs": round((cb + db) / bcast_ms / 1e6, 1),
+                            "what": "one packed NCCL broadcast per frame set, double-buffered beside the previous set's kernels",
+                            "nccl_min_nchannels": os.environ.get("NCCL_MIN_NCHANNELS")}
     fu.close()
     if world > 1:
         dist.barrier()

@@ -47,7 +47,10 @@ class FrameBroadcaster:
         self.dist, self.src, self.cb, self.db = dist, src, int(color_bytes), int(depth_bytes)
         self.cuda = torch.device(device).type == "cuda"
         self.device = device
+        self.rank = dist.get_rank()
         self.buf = [torch.empty(self.cb + self.db, dtype=torch.uint8, device=device) for _ in range(2)]
+        self.buf_color = [t[:self.cb] for t in self.buf]
+        self.buf_depth = [t[self.cb:] for t in self.buf]
         self.done = [torch.cuda.Event() for _ in range(2)] if self.cuda else None
         self.free = [torch.cuda.Event() for _ in range(2)] if self.cuda else None
         self.free_recorded = [False, False]
@@ -56,7 +59,8 @@ class FrameBroadcaster:
     def in_flight(self):
         return self.issued - self.consumed
 
-    def issue(self, color=None, depth=None):
+    def issue(self, color=None, depth=None, packed=None):
+        """Sources matter on the ingest rank only: either (color, depth) tensors or one already packed uint8 tensor."""
         import torch
         assert self.in_flight() < 2, "both slots hold frame sets that were not consumed"
         b = self.issued % 2
@@ -64,9 +68,12 @@ class FrameBroadcaster:
             cur = torch.cuda.current_stream(self.device)
             if self.free_recorded[b]:
                 cur.wait_event(self.free[b])
-        if self.dist.get_rank() == self.src:
-            self.buf[b][:self.cb].copy_(color.reshape(-1).view(torch.uint8), non_blocking=True)
-            self.buf[b][self.cb:].copy_(depth.reshape(-1).view(torch.uint8), non_blocking=True)
+        if self.rank == self.src:
+            if packed is not None:
+                self.buf[b].copy_(packed, non_blocking=True)
+            else:
+                self.buf_color[b].copy_(color.reshape(-1).view(torch.uint8), non_blocking=True)
+                self.buf_depth[b].copy_(depth.reshape(-1).view(torch.uint8), non_blocking=True)
         self.dist.broadcast(self.buf[b], self.src)
         if self.cuda:
             self.done[b].record(cur)
