@@ -177,10 +177,10 @@ def run_ours(args):
             # the next set's broadcast is enqueued BEFORE this set's kernels: NCCL's CTAs then share the SMs with the small
             # pre-processing kernels instead of queueing behind the persistent integrate kernel, which fills every SM
             fb.issue(packed=d_packed[(i + 1) % N_FRAMES])
-            fu.frame(sync_bricks=False)
+            fu.fuse_frame()
         else:
             fu.upload_frames_ptr(d_color[k].data_ptr(), cb, d_depth[k].data_ptr(), db, device=True)
-            fu.frame(sync_bricks=False)
+            fu.fuse_frame()                  # one call; a captured CUDA graph while stage timing is off, direct launches otherwise
 
     def step_host(i):
         # the reference's ingest is double-buffered (reader thread fills the back PBO while the front one is drawn,
@@ -238,9 +238,13 @@ def run_ours(args):
         return ms
 
     sampler = ClockSampler(local, args.clock_ms) if (rank == 0 and args.clock_ms > 0) else None
-    ms_total = timed(step_device, args.steps, args.warmup, True)
+    ms_total = timed(step_device, args.steps, args.warmup, False)
     gpu_launches = timed.launches
     host_enqueue_ms = timed.host_ms
+    # stage breakdown and the dominant kernel's launch duration: the same steps again with CUDA-event stage timers on the
+    # context's stream (timers need direct launches, so this pass is not the one `value` comes from)
+    stage_steps = max(10, min(args.steps, 100))
+    ms_stage_pass = timed(step_device, stage_steps, 3, True)
     int_ms, int_n = fu.stage_stats("2integrate")
     pre_ms, pre_n = fu.stage_stats("1preprocess")
     if world == 1:
@@ -391,7 +395,9 @@ def run_ours(args):
                 "bound": (f"host->device link: {cb + db} B/step at the measured {link_gbs:.1f} GB/s caps e2e at {link_gbs * 1e9 / (cb + db):.0f} frames/s" if link_gbs else None),
                 "dxt1_stream": e2e_dxt1},
         "gpu_launches": int(gpu_launches), "host_enqueue_ms_per_step": round(host_enqueue_ms, 5),
-        "stages_ms": {"1preprocess": round(pre_ms / max(1, pre_n), 5), "2integrate": round(int_avg_ms, 5)},
+        "stages_ms": {"1preprocess": round(pre_ms / max(1, pre_n), 5), "2integrate": round(int_avg_ms, 5),
+                      "how": f"CUDA-event stage timers over {stage_steps} further steps of the same loop with direct launches "
+                             f"({ms_stage_pass / stage_steps:.5f} ms/step); `value` is timed with the frame replayed as one CUDA graph"},
         "view": {"ms_per_view": round(view_ms, 4), "resolution": [VW, VH], "what": "tsdf_raymarch (shaded, brick space skipping) + colour hole filling" + (f" per slab + 1 gather of {multigpu.RECORD_FLOATS * 4}-byte records + composite" if world > 1 else "")},
         "roofline": {"bound": "hbm", "kernel": "k_integrate_fused (clear + occupied-brick integration, one launch = the 2integrate stage)" if bricks else "k_integrate_dense",
                      "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),

@@ -147,6 +147,12 @@ int rr_preprocess(rr_ctx* ctx, int filter_textures, int use_processed_depth, int
 int rr_bricks_update(rr_ctx* ctx, uint32_t* out_num_occupied, float* out_ratio);
 /* ReconIntegration::integrate (recon_integration.cpp:243-270) + glsl/tsdf_integration.vs. */
 int rr_integrate(rr_ctx* ctx);
+/* The whole per-frame-set sequence of kinect_client.cpp:572-600 after NetKinectArray::update() in ONE call:
+ * clearOccupiedBricks -> processTextures -> updateOccupiedBricks -> integrate (= rr_bricks_clear, rr_preprocess,
+ * rr_bricks_update(NULL, NULL), rr_integrate). With stage timing off the launch sequence is captured once per
+ * (frame slot, flags) as a CUDA graph and replayed, so a frame costs one launch on the host; any rr_configure /
+ * rr_set_slab / rr_set_frame_format / calibration upload / rr_set_tunable drops the captured graphs. Same results. */
+int rr_fuse_frame(rr_ctx* ctx, int filter_textures, int use_processed_depth, int refine_boundary);
 /* ReconIntegration::drawF/draw (recon_integration.cpp:151-241) + glsl/tsdf_raymarch.fs, bricks.{vs,gs,fs}.
  * out_rgba float32 [h][w][4], out_depth float32 [h][w] (gl_FragDepth, 1.0 where no surface), both host, may be NULL. */
 int rr_raymarch(rr_ctx* ctx, const rr_view* view, float* out_rgba, float* out_depth);

@@ -19,6 +19,13 @@ int check(rr_ctx* c, cudaError_t e, const char* what) {
   return fail(c, RR_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
 
+void drop_frame_graphs(rr_ctx* c) {
+  if (c->frame_graphs.empty()) return;
+  cudaStreamSynchronize(c->stream);
+  for (auto& g : c->frame_graphs) cudaGraphExecDestroy(g.exec);
+  c->frame_graphs.clear();
+}
+
 static bool timer_is_top(const char* name) { return name[0] >= '0' && name[0] <= '9'; }   // "1preprocess", "2integrate", "3recon"
 
 void timer_begin(rr_ctx* c, const char* name) {
@@ -136,6 +143,7 @@ int rr_create(rr_ctx** out, int device, int num_sensors, int depth_w, int depth_
 void rr_destroy(rr_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  drop_frame_graphs(c);
   if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (int i = 0; i < RR_MAX_SENSORS; ++i) { cudaFree(c->d_xyz[i]); cudaFree(c->d_uv[i]); }
@@ -171,6 +179,7 @@ void* rr_stream(rr_ctx* c) { return c ? (void*)c->stream : nullptr; }
 
 int rr_set_bbox(rr_ctx* c, const float bmin[3], const float bmax[3]) {
   if (!c) return RR_ERR_INVALID;
+  drop_frame_graphs(c);
   RR_REQUIRE(c, bmin && bmax, "rr_set_bbox: null pointer");
   for (int a = 0; a < 3; ++a) {
     RR_REQUIRE(c, bmax[a] > bmin[a], "rr_set_bbox: empty box");
@@ -183,6 +192,7 @@ int rr_set_bbox(rr_ctx* c, const float bmin[3], const float bmax[3]) {
 
 int rr_calib_upload(rr_ctx* c, int sensor, const float* cv_xyz, const float* cv_uv, const uint32_t res[3], const float dl[2]) {
   if (!c) return RR_ERR_INVALID;
+  drop_frame_graphs(c);
   RR_REQUIRE(c, sensor >= 0 && sensor < c->N, "rr_calib_upload: sensor index out of range");
   RR_REQUIRE(c, cv_xyz && cv_uv && res && dl, "rr_calib_upload: null pointer");
   RR_REQUIRE(c, res[0] >= 2 && res[1] >= 2 && res[2] >= 2, "rr_calib_upload: volume needs >= 2 voxels per axis");
@@ -215,6 +225,7 @@ int rr_calib_upload(rr_ctx* c, int sensor, const float* cv_xyz, const float* cv_
 
 int rr_calib_upload_inv(rr_ctx* c, int sensor, const float* inv, const uint32_t res[3]) {
   if (!c) return RR_ERR_INVALID;
+  drop_frame_graphs(c);
   RR_REQUIRE(c, sensor >= 0 && sensor < c->N, "rr_calib_upload_inv: sensor index out of range");
   RR_REQUIRE(c, inv && res && res[0] && res[1] && res[2], "rr_calib_upload_inv: null pointer or empty volume");
   RR_SET_DEVICE(c);
@@ -248,6 +259,7 @@ int rr_get_frustum_planes(const rr_ctx* c, int sensor, float* out) {
 
 int rr_configure(rr_ctx* c, const rr_config* cfg) {
   if (!c) return RR_ERR_INVALID;
+  drop_frame_graphs(c);
   RR_REQUIRE(c, cfg, "rr_configure: null config");
   RR_REQUIRE(c, c->have_bbox, "rr_configure: call rr_set_bbox first");
   RR_REQUIRE(c, cfg->voxel_size > 0.0f && cfg->brick_size > 0.0f && cfg->limit > 0.0f, "rr_configure: sizes and limit must be positive");
@@ -341,6 +353,7 @@ int rr_get_brick_ranges(const rr_ctx* c, int32_t* out) {
 
 int rr_set_slab(rr_ctx* c, uint32_t z0, uint32_t z1) {
   if (!c) return RR_ERR_INVALID;
+  drop_frame_graphs(c);
   RR_REQUIRE(c, c->configured, "rr_set_slab: call rr_configure first");
   RR_REQUIRE(c, z0 <= z1 && z1 <= c->res[2], "rr_set_slab: slab outside the volume");
   c->slab_z0 = z0; c->slab_z1 = z1;
@@ -362,6 +375,7 @@ static int check_frame_sizes(rr_ctx* c, const void* color, size_t cb, const void
 
 int rr_set_frame_format(rr_ctx* c, int color_format, int depth_format, const float* near_far) {
   if (!c) return RR_ERR_INVALID;
+  drop_frame_graphs(c);
   RR_REQUIRE(c, color_format == RR_COLOR_RGB8 || color_format == RR_COLOR_DXT1, "rr_set_frame_format: unknown colour format (DXT5 streams are not supported)");
   RR_REQUIRE(c, depth_format == RR_DEPTH_F32 || depth_format == RR_DEPTH_U8, "rr_set_frame_format: unknown depth format");
   RR_REQUIRE(c, color_format != RR_COLOR_DXT1 || ((c->CW % 4) == 0 && (c->CH % 4) == 0), "rr_set_frame_format: DXT1 needs colour width and height that are multiples of 4");
@@ -492,6 +506,54 @@ int rr_integrate(rr_ctx* c) {
   return launch_integrate(c);
 }
 
+static int frame_direct(rr_ctx* c, int f, int p, int r) {
+  RR_TRY(launch_bricks_clear(c));
+  RR_TRY(launch_preprocess(c, f, p, r));
+  RR_TRY(launch_bricks_update(c));
+  return launch_integrate(c);
+}
+
+int rr_fuse_frame(rr_ctx* c, int filter_textures, int use_processed_depth, int refine_boundary) {
+  if (!c) return RR_ERR_INVALID;
+  RR_TRY(require_ready(c, true));
+  RR_SET_DEVICE(c);
+  const int f = filter_textures ? 1 : 0, p = use_processed_depth ? 1 : 0, r = refine_boundary ? 1 : 0;
+  // capture needs a launch sequence without allocations or event timers: the z table exists (first frame ran direct)
+  // and stage timing is off
+  const bool ready = rr::tunables().graph != 0 && !c->graphs_broken && c->timing == 0 && c->d_ztab &&
+                     c->ztab_Z == (int)c->res[2] && c->ztab_IZ == (int)c->ires[2];
+  if (!ready) return frame_direct(c, f, p, r);
+  const uint64_t key = ((uint64_t)rr::tunables().generation << 8) | (uint64_t)(c->cur_slot << 3 | f << 2 | p << 1 | r);
+  for (auto& g : c->frame_graphs)
+    if (g.key == key) {
+      c->launches += g.launches;
+      return check(c, cudaGraphLaunch(g.exec, c->stream), "frame graph launch");
+    }
+  if (c->frame_graphs.size() >= 16) drop_frame_graphs(c);          // stale tunable generations
+  const uint64_t l0 = c->launches;
+  if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    c->graphs_broken = true;
+    return frame_direct(c, f, p, r);
+  }
+  const int rc = frame_direct(c, f, p, r);
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+  cudaGraphExec_t exec = nullptr;
+  if (rc == RR_OK && e == cudaSuccess && graph) e = cudaGraphInstantiate(&exec, graph, 0);
+  if (graph) cudaGraphDestroy(graph);
+  const uint64_t captured = c->launches - l0;
+  c->launches = l0;
+  if (rc != RR_OK || e != cudaSuccess || !exec) {
+    cudaGetLastError();
+    c->graphs_broken = true;
+    return frame_direct(c, f, p, r);
+  }
+  c->frame_graphs.push_back({key, exec, captured});
+  c->launches += captured;
+  return check(c, cudaGraphLaunch(exec, c->stream), "frame graph launch");
+}
+
 static int ensure_view(rr_ctx* c, int w, int h) {
   if (w == c->view_w && h == c->view_h) return RR_OK;
   RR_TRY(check(c, cudaStreamSynchronize(c->stream), "raymarch resize sync"));
@@ -570,6 +632,7 @@ int rr_composite(rr_ctx* c, const void* d_records, int n_parts, int width, int h
 
 int rr_calib_invert(rr_ctx* c, int sensor, const uint32_t out_res[3], float* host_out, int keep) {
   if (!c) return RR_ERR_INVALID;
+  drop_frame_graphs(c);
   RR_REQUIRE(c, sensor >= 0 && sensor < c->N && c->have_calib[sensor], "rr_calib_invert: upload the sensor's cv_xyz first");
   RR_REQUIRE(c, c->have_bbox, "rr_calib_invert: call rr_set_bbox first");
   RR_REQUIRE(c, out_res && out_res[0] && out_res[1] && out_res[2], "rr_calib_invert: empty output resolution");
@@ -755,7 +818,9 @@ int rr_set_tunable(const char* name, int value) {
   else if (n == "chunk") t.chunk = value;
   else if (n == "brick_grid") t.brick_grid = value;
   else if (n == "ldg256") t.ldg256 = value;
+  else if (n == "graph") t.graph = value;
   else return RR_ERR_INVALID;
+  ++t.generation;              // captured frame graphs bake the launch shapes in: stale keys never match again
   return RR_OK;
 }
 

@@ -124,6 +124,10 @@ struct rr_ctx {
   float4* d_ztab = nullptr;        // [Z] (k0, k1, g, 1-g) of the z filter tap against the inverse volume (k_build_ztab)
   int ztab_Z = 0, ztab_IZ = 0;
   bool fused_ok = false;           // brick table is separable with <= 2 bricks per voxel and axis
+  // rr_fuse_frame: captured launch sequences, keyed by (frame slot, pre-process flags, tunable generation)
+  struct FrameGraph { uint64_t key; cudaGraphExec_t exec; uint64_t launches; };
+  std::vector<FrameGraph> frame_graphs;
+  bool graphs_broken = false;      // a capture failed once: stay on direct launches
   uint32_t* h_num_occ = nullptr;   // pinned
   float* d_tsdf = nullptr;
   float* d_weight = nullptr;
@@ -156,6 +160,8 @@ struct Tunables {
   int chunk = 1;        // compute items a CTA draws at a time (0: one z-chunk of one brick)
   int brick_grid = 6;   // grid multiple of the unfused brick kernel
   int ldg256 = 1;       // gather texels with one 256-bit load (0: two 128-bit loads)
+  int graph = 1;        // rr_fuse_frame replays a captured CUDA graph (0: direct launches)
+  unsigned generation = 0;   // bumped by every rr_set_tunable (invalidates captured graphs)
 };
 Tunables& tunables();
 
@@ -176,6 +182,7 @@ int launch_composite(rr_ctx* c, const float4* d_rec, int n_parts);
 int launch_fill_colors(rr_ctx* c);
 int launch_unpack_frames(rr_ctx* c, int slot);
 int launch_calib_invert(rr_ctx* c, int sensor, const uint32_t out_res[3], float4* d_out);
+void drop_frame_graphs(rr_ctx* c);
 
 // host geometry (rr_host_geom.cpp)
 void host_frustum(const float* cv_xyz, const uint32_t res[3], float planes[6][4], float cam[3]);

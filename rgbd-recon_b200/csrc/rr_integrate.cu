@@ -423,6 +423,7 @@ Tunables& tunables() {
     v.chunk = env("RR_FUSED_CHUNK", v.chunk);
     v.brick_grid = env("RR_BRICK_GRID", v.brick_grid);
     v.ldg256 = env("RR_LDG256", v.ldg256);
+    v.graph = env("RR_GRAPH", v.graph);
     return v;
   }();
   return t;

@@ -74,6 +74,7 @@ def lib():
     L.rr_preprocess.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.rr_bricks_update.argtypes = [vp, u32, f32]
     L.rr_integrate.argtypes = [vp]
+    L.rr_fuse_frame.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.rr_raymarch.argtypes = [vp, C.POINTER(View), f32, f32]
     L.rr_raymarch_partial.argtypes = [vp, C.POINTER(View), vp]
     L.rr_composite.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, f32, f32]
@@ -311,6 +312,10 @@ class Fusion:
         r = self.bricks_update(sync=sync_bricks)
         self.integrate()
         return r
+
+    def fuse_frame(self, filter_textures=True, use_processed_depth=True, refine=True):
+        """frame() as ONE call (rr_fuse_frame): replays a captured CUDA graph when stage timing is off."""
+        self._ck(self.L.rr_fuse_frame(self.h, int(filter_textures), int(use_processed_depth), int(refine)))
 
     # read-back
     def synchronize(self):

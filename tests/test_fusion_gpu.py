@@ -190,3 +190,55 @@ def test_frame_eight_sensors(monkeypatch):
         got, want = _run_both(sc, 0.025, (40, 44, 40), use_bricks=use_bricks, store_weight=True)
         _assert_frame(got, want)
     assert len(want["occupied"]) > 10
+
+
+def test_fuse_frame_graph_replay(small_scene):
+    """rr_fuse_frame: one call per frame set, captured as a CUDA graph per frame slot and replayed. Alternating frame sets
+    through the double-buffered ingest, a tunable change and a reconfiguration must all keep the volume bit-identical to
+    the oracle (and to the call-by-call path)."""
+    import oracle_py as O
+    from rrpy import capi, synth
+    sc = small_scene
+    scenes = [sc, synth.rerender(sc, 9)]
+    inv = synth.analytic_inverse(sc, (50, 55, 50))
+    fu = capi.Fusion(sc.N, sc.W, sc.H, sc.CW, sc.CH)
+    capi.load_scene(fu, sc, inv)
+
+    def oracle(scene, voxel):
+        grid = O.brick_grid(scene.bbox_min, scene.bbox_max, voxel, 0.1)
+        cams = [O.frustum(scene.cv_xyz[i])[1] for i in range(scene.N)]
+        pre = O.preprocess(scene, grid, cams)
+        occ = O.occupied_bricks(pre["bricks"], 10)
+        return O.integrate(inv, pre, grid, 0.01, True, occ), pre["bricks"], occ
+
+    try:
+        for voxel in (0.02, 0.025):
+            fu.configure(limit=0.01, voxel_size=voxel, brick_size=0.1, min_voxels=10, use_bricks=True)
+            want = [oracle(s_, voxel) for s_ in scenes]
+            fu.upload_frames(scenes[0].color, scenes[0].depth)
+            fu.frame()                                           # builds the z table (an extra launch, and an allocation)
+            l0 = fu.launch_count()
+            per_frame = None
+            for i in range(7):                                   # capture slot A, capture slot B, replays, re-capture ...
+                k = i % 2
+                fu.upload_frames(scenes[k].color, scenes[k].depth)      # stage + swap: the frame slot alternates
+                l1 = fu.launch_count()
+                if i == 4:
+                    capi.set_tunable("zchunk", 7)                # new launch shape: the captured graphs must not be reused
+                fu.fuse_frame()
+                n = fu.launch_count() - l1
+                per_frame = per_frame or n
+                assert n == per_frame, "a replayed frame must account for the same kernel launches as a direct one"
+                tsdf = fu.download_tsdf()
+                counters, occupied = fu.download_bricks()
+                assert np.array_equal(counters, want[k][1]) and np.array_equal(occupied, want[k][2])
+                assert bits_equal(tsdf, want[k][0]).all(), mismatch_report(f"tsdf frame {i} voxel {voxel}", tsdf, want[k][0])
+            assert fu.launch_count() > l0
+            capi.set_tunable("zchunk", 13)
+        # the call-by-call path gives the same volume
+        fu.upload_frames(scenes[0].color, scenes[0].depth)
+        fu.frame(sync_bricks=True)
+        assert bits_equal(fu.download_tsdf(), want[0][0]).all()
+    finally:
+        capi.set_tunable("zchunk", 13)
+        fu.close()
