@@ -16,6 +16,30 @@ def slab_range(rank: int, world: int, Z: int):
     return z0, z0 + base + (1 if rank < rem else 0)
 
 
+def balanced_slabs(world: int, Z: int, plane_voxels: int, brick_ranges, occupied, compute_to_fill: float = 45.0):
+    """Contiguous z-slabs of (nearly) equal integrate cost instead of equal thickness: occupied bricks cluster around the
+    captured subject, so equal slabs leave the outer ranks idle while the middle ones work (measured on 4 B200: 0.05 ms
+    on the edge slab against 0.11 ms in the middle). Cost of slice z = plane_voxels (the clear stream) +
+    compute_to_fill * (voxels of occupied bricks in the slice); compute_to_fill is the measured per-voxel cost ratio of
+    the brick evaluation against the clear. Deterministic in its inputs, and every rank holds the same
+    brick counters (pre-processing is replicated), so all ranks derive the same boundaries without communication.
+    Returns [(z0, z1)] * world tiling [0, Z), every slab non-empty."""
+    Z, world = int(Z), int(world)
+    assert 1 <= world <= Z
+    cost = np.full(Z, float(plane_voxels), np.float64)
+    rr = np.asarray(brick_ranges, np.int64)[np.asarray(occupied, np.int64)] if len(occupied) else np.zeros((0, 6), np.int64)
+    for x0, x1, y0, y1, z0, z1 in rr:
+        cost[max(0, z0):min(Z, z1)] += compute_to_fill * float((x1 - x0) * (y1 - y0))
+    cum = np.concatenate([[0.0], np.cumsum(cost)])
+    bounds = [0]
+    for r in range(1, world):
+        z = int(np.searchsorted(cum, cum[-1] * r / world, side="left"))
+        z = min(max(z, bounds[-1] + 1), Z - (world - r))          # keep every slab non-empty
+        bounds.append(z)
+    bounds.append(Z)
+    return [(bounds[r], bounds[r + 1]) for r in range(world)]
+
+
 def halo(limit: float, Z: int) -> int:
     """Slices a slab owner recomputes past its slab on each side (rr_integrate does this internally)."""
     return int(np.ceil(np.float32(limit) * np.float32(Z))) + 2

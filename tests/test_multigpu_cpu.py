@@ -95,3 +95,22 @@ def test_gloo_broadcast_and_gather_world2():
     # pixel 0: only rank 0; 1: nobody (first = rank 0); 2: rank 0 earlier; 3: only rank 1; 4: rank 1 earlier; 5: nobody
     assert root[2] == [0, 0, 0, 1, 1, 0]
     assert root[3] == [1.0, 1.0, 1.0, 2.0, 2.0, 1.0]
+
+
+def test_balanced_slabs_tile_the_volume_and_follow_the_occupancy():
+    from rrpy import multigpu as M
+    Z, plane = 64, 64 * 64
+    # occupied bricks only in z in [24, 40): the middle of the volume
+    ranges = np.array([[0, 16, 0, 16, z, z + 8] for z in range(0, 64, 8)], np.int32)
+    occupied = np.array([3, 4], np.uint32)
+    for world in (1, 2, 3, 4, 8):
+        slabs = M.balanced_slabs(world, Z, plane, ranges, occupied)
+        assert slabs[0][0] == 0 and slabs[-1][1] == Z and len(slabs) == world
+        assert all(a[1] == b[0] for a, b in zip(slabs, slabs[1:])) and all(z1 > z0 for z0, z1 in slabs)
+    four = M.balanced_slabs(4, Z, plane, ranges, occupied, compute_to_fill=45.0)
+    thick = [z1 - z0 for z0, z1 in four]
+    assert thick[0] > thick[1] and thick[3] > thick[2], f"edge slabs should be thicker than the occupied middle: {four}"
+    # no occupancy -> equal thickness, like slab_range
+    assert M.balanced_slabs(4, Z, plane, ranges, np.zeros(0, np.uint32)) == [M.slab_range(r, 4, Z) for r in range(4)]
+    # world == Z: one slice each
+    assert M.balanced_slabs(8, 8, 4, ranges[:1], np.array([0], np.uint32)) == [(i, i + 1) for i in range(8)]
