@@ -1,0 +1,219 @@
+// ORACLE TOOLING (test infrastructure, NOT product code).
+// Runs the reference's own shader sources on the CPU: every .inc included below is generated at build time by
+// transpile.py from /root/reference/glsl/<name> (see that script for the exact textual changes) and compiled against the
+// GLSL host environment of glsl_compat.hpp. The entry points take the same arrays as the oracle's ro_pre_* / ro_integrate
+// (oracle/rr_oracle.h), so tests can put the two side by side on identical inputs. The pass order, bindings, sampler
+// filters and uniforms set here are the ones the reference's host code sets:
+//   pre_morph / pre_depth / pre_boundary / pre_normal / pre_quality: NetKinectArray::processDepth + processTextures
+//     (framework/NetKinectArray.cpp:251-290, 311-428), filters from :163-197 (depth arrays NEAREST, everything else LINEAR),
+//     pass_TexCoord at pixel centres (framework/rendering/screen_quad.cpp:11-15), texSizeInv = 1/resolution (:197);
+//   tsdf_integration: ReconIntegration::integrate (framework/reconstruction/recon_integration.cpp:243-270), one vertex
+//     per voxel centre (framework/rendering/volume_sampler.cpp:33-48).
+// Built only where the reference tree is present; output oracle/_ref/libref_glsl.so (git-ignored).
+#include <cstdint>
+#include <vector>
+
+#include "glsl_compat.hpp"
+
+namespace glsl {
+struct S_pre_morph {
+#include "pre_morph.inc"
+};
+struct S_pre_depth {
+#include "pre_depth.inc"
+};
+struct S_pre_boundary {
+#include "pre_boundary.inc"
+};
+struct S_pre_normal {
+#include "pre_normal.inc"
+};
+struct S_pre_quality {
+#include "pre_quality.inc"
+};
+struct S_tsdf_integration {
+#include "tsdf_integration.inc"
+};
+}  // namespace glsl
+
+using namespace glsl;
+
+static sampler2DArray tex2d(const float* p, int W, int H, int C, bool linear) {
+  sampler2DArray t;
+  t.f32 = p; t.W = W; t.H = H; t.L = 1; t.C = C; t.linear = linear;
+  return t;
+}
+static sampler3D tex3d(const float* p, int X, int Y, int Z, int C) {
+  sampler3D t;
+  t.f32 = p; t.X = X; t.Y = Y; t.Z = Z; t.C = C; t.linear = true;
+  return t;
+}
+static const float kOne[4] = {1.f, 1.f, 1.f, 1.f};
+
+// Every pass renders ONE layer; the harness presents that layer as a one-layer array and sets `layer` to 0, so
+// vec3(coords, layer) selects it and cv_*[layer] is the sensor's volume.
+extern "C" {
+
+void rg_pre_morph(const float* depth_in, int W, int H, float* depth_out) {
+  S_pre_morph proto{};
+  proto.layer = 0u;
+  proto.mode = 0u;                                                    // processDepth: mode 0 = dilate (:258-266); mode 1 copies
+  proto.kinect_depths = tex2d(depth_in, W, H, 1, false);
+  proto.texSizeInv = vec2(1.0f / (float)W, 1.0f / (float)H);
+  proto.cv_xyz[0] = tex3d(kOne, 1, 1, 1, 3);                          // sampled by in_bbox(vec2, float), result unused ("return true")
+  proto.bbox_min = vec3(0.f); proto.bbox_max = vec3(0.f);
+#pragma omp parallel for schedule(dynamic, 4)
+  for (int y = 0; y < H; ++y)
+    for (int x = 0; x < W; ++x) {
+      S_pre_morph s(proto);
+      s.pass_TexCoord = vec2(((float)x + 0.5f) / (float)W, ((float)y + 0.5f) / (float)H);
+      s.main();
+      depth_out[(size_t)y * W + x] = s.out_Depth;
+    }
+}
+
+void rg_pre_depth(const float* depth_in, int W, int H, const float* cv_xyz, const float* cv_uv, int CX, int CY, int CZ,
+                  const uint8_t* color, int CW, int CH, const float* bbox_min, const float* bbox_max, float cv_min_ds,
+                  float cv_max_ds, int filter_textures, int compress, float scale, float near_, float scaled_near,
+                  float* out_depth, float* out_lab) {
+  S_pre_depth proto{};
+  proto.layer = 0u;
+  proto.kinect_depths = tex2d(depth_in, W, H, 1, false);
+  sampler2DArray col;
+  col.u8 = color; col.W = CW; col.H = CH; col.L = 1; col.C = 3; col.linear = true;
+  proto.kinect_colors = col;
+  proto.texSizeInv = vec2(1.0f / (float)W, 1.0f / (float)H);
+  proto.filter_textures = filter_textures != 0;
+  proto.cv_xyz[0] = tex3d(cv_xyz, CX, CY, CZ, 3);
+  proto.cv_uv[0] = tex3d(cv_uv, CX, CY, CZ, 2);
+  proto.compress = compress != 0; proto.scale = scale; proto.near = near_; proto.scaled_near = scaled_near;
+  proto.cv_min_ds = cv_min_ds; proto.cv_max_ds = cv_max_ds;
+  proto.mode = 0; proto.processed_depth = true;
+  proto.bbox_min = vec3(bbox_min[0], bbox_min[1], bbox_min[2]);
+  proto.bbox_max = vec3(bbox_max[0], bbox_max[1], bbox_max[2]);
+#pragma omp parallel for schedule(dynamic, 4)
+  for (int y = 0; y < H; ++y)
+    for (int x = 0; x < W; ++x) {
+      S_pre_depth s(proto);
+      s.pass_TexCoord = vec2(((float)x + 0.5f) / (float)W, ((float)y + 0.5f) / (float)H);
+      s.main();
+      const size_t o = (size_t)y * W + x;
+      out_depth[o * 2] = s.out_Depth.x; out_depth[o * 2 + 1] = s.out_Depth.y;
+      out_lab[o * 3] = s.out_Color.x; out_lab[o * 3 + 1] = s.out_Color.y; out_lab[o * 3 + 2] = s.out_Color.z;
+    }
+}
+
+void rg_pre_boundary(const float* depth_rg, const float* lab, int W, int H, int refine, float* out_depth_b, float* out_sil) {
+  S_pre_boundary proto{};
+  proto.layer = 0u;
+  proto.kinect_depths = tex2d(depth_rg, W, H, 2, false);
+  proto.kinect_colors_lab = tex2d(lab, W, H, 3, true);
+  proto.kinect_colors = tex2d(kOne, 1, 1, 3, true);                   // only recompute_depth() reads these; main() never calls it
+  proto.cv_uv[0] = tex3d(kOne, 1, 1, 1, 2);
+  proto.refine = refine != 0;
+  proto.texSizeInv = vec2(1.0f / (float)W, 1.0f / (float)H);
+#pragma omp parallel for schedule(dynamic, 4)
+  for (int y = 0; y < H; ++y)
+    for (int x = 0; x < W; ++x) {
+      S_pre_boundary s(proto);
+      s.pass_TexCoord = vec2(((float)x + 0.5f) / (float)W, ((float)y + 0.5f) / (float)H);
+      s.main();
+      const size_t o = (size_t)y * W + x;
+      out_depth_b[o * 2] = s.out_Depth.x; out_depth_b[o * 2 + 1] = s.out_Depth.y;
+      out_sil[o] = s.out_Silhouette;
+    }
+}
+
+void rg_pre_normal(const float* depth_b, int W, int H, const float* cv_xyz, int CX, int CY, int CZ, const float* bbox_min,
+                   float brick_size, const uint32_t* brick_res, uint32_t num_bricks, uint32_t* bricks, float* out_normal) {
+  (void)num_bricks;
+  S_pre_normal proto{};
+  proto.layer = 0u;
+  proto.kinect_depths = tex2d(depth_b, W, H, 2, false);
+  proto.texSizeInv = vec2(1.0f / (float)W, 1.0f / (float)H);
+  proto.cv_xyz[0] = tex3d(cv_xyz, CX, CY, CZ, 3);
+  proto.cv_uv[0] = tex3d(kOne, 1, 1, 1, 2);
+  proto.bbox_min = vec3(bbox_min[0], bbox_min[1], bbox_min[2]);
+  proto.bbox_max = vec3(0.f);
+  proto.brick_size = brick_size;
+  proto.resolution = uvec3(brick_res[0], brick_res[1], brick_res[2]);
+  proto.bricks = bricks;
+  proto.bricks_occupied = nullptr;
+#pragma omp parallel for schedule(dynamic, 4)
+  for (int y = 0; y < H; ++y)
+    for (int x = 0; x < W; ++x) {
+      S_pre_normal s(proto);
+      s.pass_TexCoord = vec2(((float)x + 0.5f) / (float)W, ((float)y + 0.5f) / (float)H);
+      s.main();
+      const size_t o = (size_t)y * W + x;
+      out_normal[o * 3] = s.out_Normal.x; out_normal[o * 3 + 1] = s.out_Normal.y; out_normal[o * 3 + 2] = s.out_Normal.z;
+    }
+}
+
+void rg_pre_quality(const float* depth_b, const float* normals, const float* lab, int W, int H, const float* cv_xyz, int CX, int CY,
+                    int CZ, const float* camera_pos, float* out_quality) {
+  S_pre_quality proto{};
+  proto.layer = 0u;
+  proto.kinect_depths = tex2d(depth_b, W, H, 2, false);
+  proto.kinect_normals = tex2d(normals, W, H, 3, true);
+  proto.kinect_colors_lab = tex2d(lab, W, H, 3, true);                // read by the dead get_color_diff() loop (:115)
+  proto.texSizeInv = vec2(1.0f / (float)W, 1.0f / (float)H);
+  proto.camera_positions[0] = vec3(camera_pos[0], camera_pos[1], camera_pos[2]);
+  proto.processed_depth = true;
+  proto.cv_xyz[0] = tex3d(cv_xyz, CX, CY, CZ, 3);
+#pragma omp parallel for schedule(dynamic, 4)
+  for (int y = 0; y < H; ++y)
+    for (int x = 0; x < W; ++x) {
+      S_pre_quality s(proto);
+      s.pass_TexCoord = vec2(((float)x + 0.5f) / (float)W, ((float)y + 0.5f) / (float)H);
+      s.main();
+      out_quality[(size_t)y * W + x] = s.out_Quality;
+    }
+}
+
+// ReconIntegration::integrate: clear to -limit, then one vertex per voxel (all of them, or those of the occupied bricks).
+void rg_integrate(int N, const float* inv, const int32_t* inv_res, const float* sil, const float* depth_b, const float* quality,
+                  int W, int H, float limit, const uint32_t* res, int use_bricks, const int32_t* brick_ranges,
+                  const uint32_t* occupied, uint32_t num_occupied, float* tsdf) {
+  if (N > 5) return;                                                  // uniform sampler3D[5] cv_xyz_inv
+  const int X = (int)res[0], Y = (int)res[1], Z = (int)res[2];
+  const size_t nvox = (size_t)X * Y * Z;
+  for (size_t i = 0; i < nvox; ++i) tsdf[i] = -limit;                 // glClearTexImage(-limit), recon_integration.cpp:250-251
+  S_tsdf_integration proto{};
+  sampler2DArray s_sil = tex2d(sil, W, H, 1, true), s_depth = tex2d(depth_b, W, H, 2, false), s_q = tex2d(quality, W, H, 1, true);
+  s_sil.L = s_depth.L = s_q.L = N;
+  proto.kinect_silhouettes = s_sil; proto.kinect_depths = s_depth; proto.kinect_qualities = s_q;
+  const size_t inv_vox = (size_t)inv_res[0] * inv_res[1] * inv_res[2];
+  for (int i = 0; i < N; ++i) {
+    sampler3D t = tex3d(inv + (size_t)i * inv_vox * 4, inv_res[0], inv_res[1], inv_res[2], 4);
+    proto.cv_xyz_inv[i] = t;
+  }
+  image3D img;
+  img.data = tsdf; img.X = X; img.Y = Y; img.Z = Z;
+  proto.volume_tsdf = img;
+  proto.limit = limit;
+  proto.num_kinects = (uint)N;
+  proto.res_tsdf = uvec3(res[0], res[1], res[2]);
+  proto.bricks = nullptr; proto.bricks_occupied = nullptr;
+  auto run = [&](int x0, int x1, int y0, int y1, int z0, int z1) {
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int z = z0; z < z1; ++z)
+      for (int y = y0; y < y1; ++y)
+        for (int x = x0; x < x1; ++x) {
+          S_tsdf_integration s(proto);
+          // VolumeSampler::sample: (pos + 0.5) * step, step = 1 / res (volume_sampler.cpp:36-42)
+          s.in_Position = vec3(((float)x + 0.5f) * (1.0f / (float)X), ((float)y + 0.5f) * (1.0f / (float)Y), ((float)z + 0.5f) * (1.0f / (float)Z));
+          s.main();
+        }
+  };
+  if (!use_bricks) {
+    run(0, X, 0, Y, 0, Z);
+  } else {
+    for (uint32_t b = 0; b < num_occupied; ++b) {
+      const int32_t* r = brick_ranges + (size_t)occupied[b] * 6;
+      run(r[0], r[1], r[2], r[3], r[4], r[5]);
+    }
+  }
+}
+
+}  // extern "C"

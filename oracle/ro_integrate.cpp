@@ -1,4 +1,5 @@
-// ORACLE (test infrastructure, NOT product code) — parity unpinned by the reference's own tests (none exist).
+// ORACLE (test infrastructure, NOT product code). The reference ships no tests; this file is pinned against the reference's
+// own glsl/tsdf_integration.vs compiled as C++ and run on the CPU (oracle/glsl_host/, oracle/_ref/libref_glsl.so).
 // Scalar restatement of the brick bookkeeping and of the per-voxel TSDF integration:
 //   ReconIntegration::setVoxelSize / setBrickSize / divideBox / updateOccupiedBricks
 //     (framework/reconstruction/recon_integration.cpp:341-354, 474-484, 361-407, 431-446),

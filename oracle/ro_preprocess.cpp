@@ -1,4 +1,5 @@
-// ORACLE (test infrastructure, NOT product code) — parity unpinned by the reference's own tests (none exist).
+// ORACLE (test infrastructure, NOT product code). The reference ships no tests; this file is pinned against the reference's
+// own shaders compiled as C++ and run on the CPU (oracle/glsl_host/, oracle/_ref/libref_glsl.so, tests/golden/ref_glsl_stages.npz).
 // Scalar restatement of the five depth pre-processing passes that NetKinectArray::processTextures drives
 // (framework/NetKinectArray.cpp:251-290, 311-428). One call = one pass over one sensor layer.
 // Arithmetic rules: see ro_math.h. Image layout: row-major [y][x][channels], texel (0,0) first.

@@ -1,7 +1,9 @@
 /* ORACLE (test infrastructure, NOT product code): C entry points of the scalar CPU restatement of
  * steppobeck/rgbd-recon's volumetric-fusion path. Loaded with ctypes by tests/, __graft_entry__.smoke() and
- * bench.py's cpu_baseline / --impl reference legs ONLY. Parity is unpinned by the reference's own tests (it has
- * none); see ro_math.h for what is pinned against reference code compiled into oracle/_ref. */
+ * bench.py's cpu_baseline / --impl reference legs ONLY. The reference ships no tests; the
+ * restatement is pinned against reference code compiled into oracle/_ref: C++ sources (libref_harness.so, see ro_math.h) and
+ * the pre-processing / integration SHADERS run on the CPU (libref_glsl.so, oracle/glsl_host/). The raymarch and colour-fill
+ * restatements (ro_raymarch.cpp, ro_colorfill.cpp) remain unpinned. */
 #ifndef RR_ORACLE_H
 #define RR_ORACLE_H
 #include <stddef.h>

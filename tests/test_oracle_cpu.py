@@ -2,8 +2,10 @@
   * golden vectors produced by REAL reference code (tests/golden/ref_*.npz, made by tools/make_golden.py from oracle/_ref),
   * the live oracle/_ref library when it is present (build container only),
   * known answers of the arithmetic pins (GL filtering equations, deterministic pow),
-  * self-regression pins of the shader restatement, whose GLSL originals cannot run here (parity unpinned by the
-    reference: it ships no tests).
+  * the reference's OWN shaders for pre-processing and integration, compiled as C++ and run on the CPU
+    (oracle/_ref/libref_glsl.so, oracle/glsl_host/) - live where built, and as tests/golden/ref_glsl_stages.npz elsewhere,
+  * self-regression pins of the shader restatement (the raymarch / colour-fill shaders are not yet run this way; the
+    reference ships no tests of its own).
 """
 import hashlib
 import os
@@ -173,6 +175,117 @@ def test_goldens_are_current():
     g = gold("ref_calib_invert.npz")
     inv = R.calib_invert(g["cv_xyz"], g["bbox_min"], g["bbox_max"], g["out_res"])
     assert bits_equal(inv, g["inv"]).all()
+    import ref_glsl_py as G
+    if G.available():
+        import oracle_py as O_
+        from rrpy import synth
+        gs = gold("ref_glsl_stages.npz")
+        sc = synth.make_scene(N=1, W=128, H=106, CW=160, CH=135, cv_res=(24, 24, 48), seed=77)
+        grid = O_.brick_grid(sc.bbox_min, sc.bbox_max, float(gs["voxel"]), 0.1)
+        pre = G.preprocess(sc, grid, [O_.frustum(sc.cv_xyz[0])[1]])
+        for k, v in pre.items():
+            assert bits_equal(v, gs["pre_" + k]).all() if v.dtype == np.float32 else np.array_equal(v, gs["pre_" + k]), k
+
+
+# ------------------------------------------------------------------------------------------------ the reference's shaders, run
+# oracle/_ref/libref_glsl.so = the reference's own glsl/pre_*.fs, inc_*.glsl and tsdf_integration.vs compiled as C++ against a
+# GLSL host environment (oracle/glsl_host/) that evaluates filtering and built-ins in a DIFFERENT formulation than the
+# oracle (mix() without fma, libm pow, plain dot products). Agreement is therefore to rounding, not to the bit; the bars:
+STAGE_TOL = dict(morph=0.0, depth=5e-7, lab=5e-5, depth_b=5e-7, sil=0.0, normal=5e-5, quality=1e-5)
+
+
+def _assert_stage(name, got, want, tol, max_flips=0):
+    """|got - want| <= tol except for at most max_flips elements (discrete decisions on a rounding-sized margin)."""
+    assert ((got != got) == (want != want)).all(), f"{name}: NaN pattern differs"
+    ok = np.isfinite(got.astype(np.float64)) & np.isfinite(want.astype(np.float64))
+    assert ((got == want) | ok | ((got != got) & (want != want))).all(), f"{name}: infinities differ"
+    d = np.abs(got.astype(np.float64) - want.astype(np.float64))[ok]
+    bad = int((d > tol).sum())
+    assert bad <= max_flips, f"{name}: {bad} elements differ by more than {tol} (max {d.max():.3e})"
+
+
+def _glsl_stagewise(O, G, sc, voxel, inv_res):
+    """Each shader stage of the reference against the oracle ON THE SAME INPUTS (the oracle's previous stage)."""
+    import dataclasses
+    from rrpy import synth
+    grid = O.brick_grid(sc.bbox_min, sc.bbox_max, voxel, 0.1)
+    cams = [O.frustum(sc.cv_xyz[i])[1] for i in range(sc.N)]
+    pre = O.preprocess(sc, grid, cams)
+    L = G.lib()
+    N, H, W = sc.depth.shape
+    X, Y, Z = sc.cv_res
+    bmin, bmax = np.ascontiguousarray(sc.bbox_min, np.float32), np.ascontiguousarray(sc.bbox_max, np.float32)
+    bricks = np.zeros(grid["num_bricks"], np.uint32)
+    for i in range(N):
+        out = np.zeros((H, W), np.float32)
+        L.rg_pre_morph(np.ascontiguousarray(sc.depth[i]), W, H, out)
+        assert bits_equal(out, pre["morph"][i]).all(), "pre_morph.fs: the hole fill must match bit for bit"
+        d2, lab = np.zeros((H, W, 2), np.float32), np.zeros((H, W, 3), np.float32)
+        L.rg_pre_depth(pre["morph"][i], W, H, sc.cv_xyz[i], sc.cv_uv[i], X, Y, Z, sc.color[i], sc.CW, sc.CH, bmin, bmax, 0.5, 4.5,
+                       1, 0, 0.0, 0.0, 0.0, d2, lab)
+        _assert_stage("pre_depth.fs depth", d2, pre["depth"][i], STAGE_TOL["depth"])
+        _assert_stage("pre_depth.fs lab", lab, pre["lab"][i], STAGE_TOL["lab"])
+        db, sil = np.zeros((H, W, 2), np.float32), np.zeros((H, W), np.float32)
+        L.rg_pre_boundary(pre["depth"][i], pre["lab"][i], W, H, 1, db, sil)
+        assert bits_equal(sil, pre["sil"][i]).all(), "pre_boundary.fs: silhouettes must be identical"
+        assert bits_equal(db, pre["depth_b"][i]).all(), "pre_boundary.fs only selects and flags: identical on identical inputs"
+        nrm = np.zeros((H, W, 3), np.float32)
+        L.rg_pre_normal(pre["depth_b"][i], W, H, sc.cv_xyz[i], X, Y, Z, bmin, grid["brick_size"], grid["res_bricks"],
+                        grid["num_bricks"], bricks, nrm)
+        _assert_stage("pre_normal.fs", nrm, pre["normal"][i], STAGE_TOL["normal"])
+        q = np.zeros((H, W), np.float32)
+        L.rg_pre_quality(pre["depth_b"][i], pre["normal"][i], pre["lab"][i], W, H, sc.cv_xyz[i], X, Y, Z,
+                         np.ascontiguousarray(cams[i], np.float32), q)
+        _assert_stage("pre_quality.fs", q, pre["quality"][i], STAGE_TOL["quality"])
+    assert np.array_equal(bricks, pre["bricks"]), "inc_bricks.glsl mark_brick: brick counters must be bit-exact"
+    inv = synth.analytic_inverse(sc, inv_res)
+    occ = O.occupied_bricks(pre["bricks"], 10)
+    worst = 0.0
+    for use_bricks in (True, False):
+        want = O.integrate(inv, pre, grid, 0.01, use_bricks, occ)
+        got = G.integrate(inv, pre, grid, 0.01, use_bricks, occ)
+        _assert_stage("tsdf_integration.vs", got, want, 1e-5 * 0.01)       # BASELINE bar: within 1e-5 of the truncation distance
+        ok = np.isfinite(want)
+        worst = max(worst, float(np.abs(got[ok].astype(np.float64) - want[ok]).max()))
+    return len(occ), worst
+
+
+def test_oracle_matches_the_reference_shaders_run_on_cpu(O):
+    """The pin of the GLSL stages: the reference's shader sources executed on the CPU vs the oracle's restatement."""
+    import ref_glsl_py as G
+    if not G.available():
+        pytest.skip("oracle/_ref/libref_glsl.so not built (needs the reference tree at build time)")
+    from rrpy import synth
+    n_occ, worst = _glsl_stagewise(O, G, synth.make_scene(N=2, W=128, H=106, CW=160, CH=135, cv_res=(32, 32, 64)), 0.02, (50, 55, 50))
+    assert n_occ > 50
+    n_occ, worst2 = _glsl_stagewise(O, G, synth.make_scene(N=3, W=96, H=80, CW=128, CH=108, cv_res=(24, 24, 48), seed=99), 0.025, (40, 44, 40))
+    assert n_occ > 20 and max(worst, worst2) < 1e-7
+
+
+def test_oracle_against_reference_shader_goldens(O):
+    """Same pin for machines without oracle/_ref: tests/golden/ref_glsl_stages.npz holds what the reference's shaders computed
+    (full chain, every stage fed by the shaders' own previous stage). The oracle's own chain must stay within rounding:
+    discrete outputs identical, the volume within 2e-5 of the truncation distance (1e-5 per the stagewise test above, plus
+    the drift the chained float stages add)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(GOLD), "..", "tools"))
+    from rrpy import synth
+    g = gold("ref_glsl_stages.npz")
+    sc = synth.make_scene(N=1, W=128, H=106, CW=160, CH=135, cv_res=(24, 24, 48), seed=77)    # tools/make_golden.py::glsl_scene
+    voxel = float(g["voxel"])
+    grid = O.brick_grid(sc.bbox_min, sc.bbox_max, voxel, 0.1)
+    cams = [O.frustum(sc.cv_xyz[i])[1] for i in range(sc.N)]
+    pre = O.preprocess(sc, grid, cams)
+    assert bits_equal(pre["morph"], g["pre_morph"]).all() and bits_equal(pre["sil"], g["pre_sil"]).all()
+    assert np.array_equal(pre["bricks"], g["pre_bricks"])
+    for k in ("depth", "lab", "depth_b", "normal", "quality"):
+        _assert_stage(k, pre[k], g["pre_" + k], 4 * STAGE_TOL[k])
+    occ = O.occupied_bricks(pre["bricks"], 10)
+    assert np.array_equal(occ, g["occupied"]) and len(occ) > 10
+    for use_bricks, key in ((True, "tsdf_bricks"), (False, "tsdf_dense")):
+        got = O.integrate(g["inv"], pre, grid, 0.01, use_bricks, occ)
+        assert (np.abs(g[key]) < 0.0099).sum() > 200, "the golden volume must hold in-band voxels"
+        _assert_stage(key, got, g[key], 2e-5 * 0.01)
 
 
 # ------------------------------------------------------------------------------------------------ arithmetic pins

@@ -28,6 +28,11 @@ def golden_scene():
     return synth.make_scene(N=1, W=64, H=53, CW=80, CH=68, cv_res=(16, 16, 32), seed=77)
 
 
+def glsl_scene():
+    # large enough for the 13x13 support tests of pre_depth / pre_boundary to keep a surface (golden_scene() is too small)
+    return synth.make_scene(N=1, W=128, H=106, CW=160, CH=135, cv_res=(24, 24, 48), seed=77)
+
+
 def golden_dxt1():
     """DXT1 colour ingest: blocks made and decoded by the reference's own codec external/squish."""
     rng = np.random.default_rng(11)
@@ -44,13 +49,36 @@ def golden_dxt1():
                         random_decoded=rnd_decoded)
 
 
+def golden_glsl():
+    """The reference's OWN shaders (glsl/pre_*.fs, inc_*.glsl, tsdf_integration.vs) compiled as C++ and run on the CPU
+    (oracle/_ref/libref_glsl.so, oracle/glsl_host/): every pre-processing stage and the integrated volume on the golden
+    scene, chained exactly like NetKinectArray::processTextures + ReconIntegration::integrate."""
+    import ref_glsl_py as G
+    assert G.available(), "build oracle/_ref/libref_glsl.so first (make -C oracle all)"
+    sc = glsl_scene()
+    voxel = 0.035
+    grid = O.brick_grid(sc.bbox_min, sc.bbox_max, voxel, 0.1)
+    cams = [O.frustum(sc.cv_xyz[i])[1] for i in range(sc.N)]
+    pre = G.preprocess(sc, grid, cams)
+    inv = synth.analytic_inverse(sc, (20, 22, 20))
+    occ = O.occupied_bricks(pre["bricks"], 10)
+    tsdf_bricks = G.integrate(inv, pre, grid, 0.01, True, occ)
+    tsdf_dense = G.integrate(inv, pre, grid, 0.01, False, occ)
+    np.savez_compressed(os.path.join(OUT, "ref_glsl_stages.npz"), voxel=np.float32(voxel), inv=inv, occupied=occ,
+                        tsdf_bricks=tsdf_bricks, tsdf_dense=tsdf_dense, **{"pre_" + k: v for k, v in pre.items()})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     assert R.available(), "build oracle/_ref first (make -C oracle all)"
     if "--only-dxt" in sys.argv:
         golden_dxt1()
         return
+    if "--only-glsl" in sys.argv:
+        golden_glsl()
+        return
     golden_dxt1()
+    golden_glsl()
     sc = golden_scene()
     xyz = sc.cv_xyz[0]
     # --- calibration inversion + frustum (real calibration_inverter.cpp / frustum.cpp)
