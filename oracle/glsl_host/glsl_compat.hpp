@@ -53,6 +53,8 @@ struct vec3 {
   inline vec3(const ivec3& v);
   vec2 xy() const { return vec2(x, y); }
   vec2 rg() const { return vec2(x, y); }
+  vec2 xx() const { return vec2(x, x); }
+  vec2 yz() const { return vec2(y, z); }
   vec3 xyz() const { return *this; }
   vec3 rgb() const { return *this; }
   float& operator[](int i) { return i == 0 ? x : (i == 1 ? y : z); }
@@ -72,12 +74,24 @@ struct vec4 {
   vec2 rg() const { return vec2(x, y); }
   vec3 xyz() const { return vec3(x, y, z); }
   vec3 rgb() const { return vec3(x, y, z); }
+  float& operator[](int i) { return i == 0 ? x : (i == 1 ? y : (i == 2 ? z : w)); }
+  float operator[](int i) const { return i == 0 ? x : (i == 1 ? y : (i == 2 ? z : w)); }
 };
 
 struct ivec2 {
   int x, y;
   ivec2() : x(0), y(0) {}
   template <typename A, typename B> ivec2(A a, B b) : x((int)a), y((int)b) {}
+  explicit ivec2(const vec2& v) : x((int)v.x), y((int)v.y) {}     // truncation toward zero
+};
+
+// T[5] as a value (GLSL arrays are first-class: returned from functions, assigned)
+template <typename T> struct arr5 {
+  T v[5];
+  arr5() : v{} {}
+  arr5(const T& a, const T& b, const T& c, const T& d, const T& e) : v{a, b, c, d, e} {}
+  T& operator[](uint i) { return v[i]; }
+  const T& operator[](uint i) const { return v[i]; }
 };
 
 struct ivec3 {
@@ -127,6 +141,10 @@ inline vec3& operator-=(vec3& a, const vec3& b) { a = a - b; return a; }
 inline vec3& operator*=(vec3& a, float s) { a = a * s; return a; }
 inline vec3& operator/=(vec3& a, float s) { a = a / s; return a; }
 inline vec2& operator+=(vec2& a, const vec2& b) { a = a + b; return a; }
+inline vec3 operator/(float s, const vec3& a) { return vec3(s / a.x, s / a.y, s / a.z); }
+inline vec4 operator+(const vec4& a, const vec4& b) { return vec4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+inline vec4 operator*(const vec4& a, float s) { return vec4(a.x * s, a.y * s, a.z * s, a.w * s); }
+inline vec4 operator/(const vec4& a, float s) { return vec4(a.x / s, a.y / s, a.z / s, a.w / s); }
 inline ivec3 operator+(const ivec3& a, const ivec3& b) { return ivec3(a.x + b.x, a.y + b.y, a.z + b.z); }
 inline ivec3 operator-(const ivec3& a, const ivec3& b) { return ivec3(a.x - b.x, a.y - b.y, a.z - b.z); }
 inline uvec3 operator-(const uvec3& a, uint s) { return uvec3(a.x - s, a.y - s, a.z - s); }
@@ -148,6 +166,11 @@ inline vec3 floor(const vec3& v) { return vec3(std::floor(v.x), std::floor(v.y),
 inline float sign(float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); }
 inline vec3 sign(const vec3& v) { return vec3(sign(v.x), sign(v.y), sign(v.z)); }
 inline float sqrt(float x) { return std::sqrt(x); }
+inline float ceil(float x) { return std::ceil(x); }
+inline vec2 min(const vec2& a, const vec2& b) { return vec2(min(a.x, b.x), min(a.y, b.y)); }
+inline vec2 max(const vec2& a, const vec2& b) { return vec2(max(a.x, b.x), max(a.y, b.y)); }
+inline vec3 min(const vec3& a, const vec3& b) { return vec3(min(a.x, b.x), min(a.y, b.y), min(a.z, b.z)); }
+inline vec3 max(const vec3& a, const vec3& b) { return vec3(max(a.x, b.x), max(a.y, b.y), max(a.z, b.z)); }
 inline float dot(const vec2& a, const vec2& b) { return a.x * b.x + a.y * b.y; }
 inline float dot(const vec3& a, const vec3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 inline float length(const vec2& v) { return std::sqrt(dot(v, v)); }
@@ -241,7 +264,67 @@ inline vec4 texture(const sampler3D& t, const vec3& p) {
   return vec4(o[0], o[1], o[2], o[3]);
 }
 
-struct sampler2D {};                                  // declared by pre_depth.fs ("gauss"), never sampled
+// 2D texture of RGBA32F texels; only texelFetch() is used on it (tsdf_raymarch.fs getStartPos); pre_depth.fs declares one
+// ("gauss") and never samples it
+struct sampler2D {
+  const float* f32 = nullptr;
+  int W = 0, H = 0;
+};
+inline vec4 texelFetch(const sampler2D& t, const ivec2& p, int) {
+  if (p.x < 0 || p.y < 0 || p.x >= t.W || p.y >= t.H) return vec4(0.f);          // undefined in GL; robust-access result
+  const float* q = t.f32 + ((size_t)p.y * t.W + p.x) * 4;
+  return vec4(q[0], q[1], q[2], q[3]);
+}
+
+struct image2D {                                      // layout(r32f) image2D, write-only
+  float* data = nullptr;
+  int W = 0, H = 0;
+};
+inline void imageStore(image2D& img, const ivec2& p, const vec4& v) {
+  if (p.x < 0 || p.y < 0 || p.x >= img.W || p.y >= img.H) return;
+  img.data[(size_t)p.y * img.W + p.x] = v.x;
+}
+
+// ---- mat4 (column-major, m[c] is column c) -----------------------------------------------------------------------------
+struct mat4 {
+  vec4 c[4];
+  mat4() { c[0] = vec4(1.f, 0.f, 0.f, 0.f); c[1] = vec4(0.f, 1.f, 0.f, 0.f); c[2] = vec4(0.f, 0.f, 1.f, 0.f); c[3] = vec4(0.f, 0.f, 0.f, 1.f); }
+  explicit mat4(const float* m16) { for (int i = 0; i < 4; ++i) c[i] = vec4(m16[i * 4], m16[i * 4 + 1], m16[i * 4 + 2], m16[i * 4 + 3]); }
+  vec4& operator[](int i) { return c[i]; }
+  const vec4& operator[](int i) const { return c[i]; }
+};
+// GLSL 5.9: linear-algebraic products, written out as sums of column * component
+inline vec4 operator*(const mat4& m, const vec4& v) { return m.c[0] * v.x + m.c[1] * v.y + m.c[2] * v.z + m.c[3] * v.w; }
+inline mat4 operator*(const mat4& a, const mat4& b) {
+  mat4 r;
+  for (int i = 0; i < 4; ++i) r.c[i] = a * b.c[i];
+  return r;
+}
+// inverse(): precision is implementation-defined in GLSL; cofactor expansion in binary32 here
+inline mat4 inverse(const mat4& M) {
+  float m[16], inv[16];
+  for (int c = 0; c < 4; ++c) for (int r = 0; r < 4; ++r) m[c * 4 + r] = M.c[c][r];
+  inv[0] = m[5] * m[10] * m[15] - m[5] * m[11] * m[14] - m[9] * m[6] * m[15] + m[9] * m[7] * m[14] + m[13] * m[6] * m[11] - m[13] * m[7] * m[10];
+  inv[4] = -m[4] * m[10] * m[15] + m[4] * m[11] * m[14] + m[8] * m[6] * m[15] - m[8] * m[7] * m[14] - m[12] * m[6] * m[11] + m[12] * m[7] * m[10];
+  inv[8] = m[4] * m[9] * m[15] - m[4] * m[11] * m[13] - m[8] * m[5] * m[15] + m[8] * m[7] * m[13] + m[12] * m[5] * m[11] - m[12] * m[7] * m[9];
+  inv[12] = -m[4] * m[9] * m[14] + m[4] * m[10] * m[13] + m[8] * m[5] * m[14] - m[8] * m[6] * m[13] - m[12] * m[5] * m[10] + m[12] * m[6] * m[9];
+  inv[1] = -m[1] * m[10] * m[15] + m[1] * m[11] * m[14] + m[9] * m[2] * m[15] - m[9] * m[3] * m[14] - m[13] * m[2] * m[11] + m[13] * m[3] * m[10];
+  inv[5] = m[0] * m[10] * m[15] - m[0] * m[11] * m[14] - m[8] * m[2] * m[15] + m[8] * m[3] * m[14] + m[12] * m[2] * m[11] - m[12] * m[3] * m[10];
+  inv[9] = -m[0] * m[9] * m[15] + m[0] * m[11] * m[13] + m[8] * m[1] * m[15] - m[8] * m[3] * m[13] - m[12] * m[1] * m[11] + m[12] * m[3] * m[9];
+  inv[13] = m[0] * m[9] * m[14] - m[0] * m[10] * m[13] - m[8] * m[1] * m[14] + m[8] * m[2] * m[13] + m[12] * m[1] * m[10] - m[12] * m[2] * m[9];
+  inv[2] = m[1] * m[6] * m[15] - m[1] * m[7] * m[14] - m[5] * m[2] * m[15] + m[5] * m[3] * m[14] + m[13] * m[2] * m[7] - m[13] * m[3] * m[6];
+  inv[6] = -m[0] * m[6] * m[15] + m[0] * m[7] * m[14] + m[4] * m[2] * m[15] - m[4] * m[3] * m[14] - m[12] * m[2] * m[7] + m[12] * m[3] * m[6];
+  inv[10] = m[0] * m[5] * m[15] - m[0] * m[7] * m[13] - m[4] * m[1] * m[15] + m[4] * m[3] * m[13] + m[12] * m[1] * m[7] - m[12] * m[3] * m[5];
+  inv[14] = -m[0] * m[5] * m[14] + m[0] * m[6] * m[13] + m[4] * m[1] * m[14] - m[4] * m[2] * m[13] - m[12] * m[1] * m[6] + m[12] * m[2] * m[5];
+  inv[3] = -m[1] * m[6] * m[11] + m[1] * m[7] * m[10] + m[5] * m[2] * m[11] - m[5] * m[3] * m[10] - m[9] * m[2] * m[7] + m[9] * m[3] * m[6];
+  inv[7] = m[0] * m[6] * m[11] - m[0] * m[7] * m[10] - m[4] * m[2] * m[11] + m[4] * m[3] * m[10] + m[8] * m[2] * m[7] - m[8] * m[3] * m[6];
+  inv[11] = -m[0] * m[5] * m[11] + m[0] * m[7] * m[9] + m[4] * m[1] * m[11] - m[4] * m[3] * m[9] - m[8] * m[1] * m[7] + m[8] * m[3] * m[5];
+  inv[15] = m[0] * m[5] * m[10] - m[0] * m[6] * m[9] - m[4] * m[1] * m[10] + m[4] * m[2] * m[9] + m[8] * m[1] * m[6] - m[8] * m[2] * m[5];
+  const float det = m[0] * inv[0] + m[1] * inv[4] + m[2] * inv[8] + m[3] * inv[12];
+  const float id = 1.0f / det;
+  for (int i = 0; i < 16; ++i) inv[i] *= id;
+  return mat4(inv);
+}
 
 struct image3D {                                      // layout(r32f) image3D, write-only
   float* data = nullptr;

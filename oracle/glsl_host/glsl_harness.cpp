@@ -34,6 +34,13 @@ struct S_pre_quality {
 struct S_tsdf_integration {
 #include "tsdf_integration.inc"
 };
+struct S_tsdf_raymarch {
+  // fragment-shader built-ins the source refers to
+  vec4 gl_FragCoord;
+  struct { float near, far, diff; } gl_DepthRange = {0.0f, 1.0f, 1.0f};       // glDepthRange defaults
+  bool discarded = false;
+#include "tsdf_raymarch.inc"
+};
 }  // namespace glsl
 
 using namespace glsl;
@@ -214,6 +221,70 @@ void rg_integrate(int N, const float* inv, const int32_t* inv_res, const float* 
       run(r[0], r[1], r[2], r[3], r[4], r[5]);
     }
   }
+}
+
+// ReconIntegration::draw (framework/reconstruction/recon_integration.cpp:177-241): one fragment per covered pixel of the cube
+// proxy. pass_Position is a point of the pixel's ray in volume space (the rasteriser would interpolate the cube's surface
+// point; the shader only uses normalize(pass_Position - CameraPos)). uniforms16 = gl_ModelViewMatrix, gl_ProjectionMatrix,
+// gl_NormalMatrix, NormalMatrix, vol_to_world, img_to_eye_curr (column-major, 16 floats each). depth_peels may be null
+// (skipSpace off). Outputs: rgba, gl_FragDepth, the num-samples image, and a hit flag (0 = discarded / not covered).
+void rg_raymarch(const float* tsdf, const uint32_t* res, float limit, int N, const float* inv, const int32_t* inv_res,
+                 const float* cv_uv, const int32_t* cv_res, const uint8_t* color, int CW, int CH, const float* depth_b,
+                 const float* quality, const float* normals, int W, int H, const float* bbox_min, const float* bbox_max,
+                 const float* uniforms16, const float* camera_pos, int vw, int vh, int shade_mode, const float* pass_position,
+                 const uint8_t* covered, const float* depth_peels, float* out_rgba, float* out_depth, float* out_samples,
+                 uint8_t* out_hit) {
+  if (N > 5) return;
+  S_tsdf_raymarch proto{};
+  sampler2DArray col;
+  col.u8 = color; col.W = CW; col.H = CH; col.L = N; col.C = 3; col.linear = true;
+  proto.kinect_colors = col;
+  sampler2DArray d = tex2d(depth_b, W, H, 2, false), q = tex2d(quality, W, H, 1, true), nr = tex2d(normals, W, H, 3, true);
+  d.L = q.L = nr.L = N;
+  proto.kinect_depths = d; proto.kinect_qualities = q; proto.kinect_normals = nr;
+  const size_t inv_vox = (size_t)inv_res[0] * inv_res[1] * inv_res[2], cv_vox = (size_t)cv_res[0] * cv_res[1] * cv_res[2];
+  for (int i = 0; i < N; ++i) {
+    proto.cv_xyz_inv[i] = tex3d(inv + (size_t)i * inv_vox * 4, inv_res[0], inv_res[1], inv_res[2], 4);
+    proto.cv_uv[i] = tex3d(cv_uv + (size_t)i * cv_vox * 2, cv_res[0], cv_res[1], cv_res[2], 2);
+  }
+  proto.num_kinects = (uint)N;
+  proto.limit = limit;
+  proto.sampleDistance = limit * 0.5f;             // the global's initialiser reads the uniform (tsdf_raymarch.fs:33)
+  proto.gl_ModelViewMatrix = mat4(uniforms16); proto.gl_ProjectionMatrix = mat4(uniforms16 + 16);
+  proto.gl_NormalMatrix = mat4(uniforms16 + 32); proto.NormalMatrix = mat4(uniforms16 + 48);
+  proto.vol_to_world = mat4(uniforms16 + 64); proto.img_to_eye_curr = mat4(uniforms16 + 80);
+  proto.volume_tsdf = tex3d(tsdf, (int)res[0], (int)res[1], (int)res[2], 1);
+  proto.CameraPos = vec3(camera_pos[0], camera_pos[1], camera_pos[2]);
+  proto.skipSpace = depth_peels != nullptr;
+  sampler2D peels;
+  peels.f32 = depth_peels; peels.W = vw; peels.H = vh;
+  proto.depth_peels = peels;
+  proto.viewport_offset = vec2(0.0f, 0.0f);
+  image2D ns;
+  ns.data = out_samples; ns.W = vw; ns.H = vh;
+  proto.tex_num_samples = ns;
+  proto.g_shade_mode = shade_mode;
+  proto.bbox_min = vec3(bbox_min[0], bbox_min[1], bbox_min[2]);
+  proto.bbox_max = vec3(bbox_max[0], bbox_max[1], bbox_max[2]);
+#pragma omp parallel for schedule(dynamic, 4)
+  for (int y = 0; y < vh; ++y)
+    for (int x = 0; x < vw; ++x) {
+      const size_t o = (size_t)y * vw + x;
+      out_rgba[o * 4] = out_rgba[o * 4 + 1] = out_rgba[o * 4 + 2] = out_rgba[o * 4 + 3] = 0.0f;   // glClearColor(0,0,0,0)
+      out_depth[o] = 1.0f;                                                                          // glClearDepth(1)
+      out_samples[o] = 0.0f;
+      out_hit[o] = 0;
+      if (!covered[o]) continue;
+      S_tsdf_raymarch s(proto);
+      s.gl_FragCoord = vec4((float)x + 0.5f, (float)y + 0.5f, 0.0f, 1.0f);
+      s.pass_Position = vec3(pass_position[o * 3], pass_position[o * 3 + 1], pass_position[o * 3 + 2]);
+      s.gl_FragDepth = 1.0f;
+      s.main();
+      if (s.discarded) continue;
+      out_rgba[o * 4] = s.out_Color.x; out_rgba[o * 4 + 1] = s.out_Color.y; out_rgba[o * 4 + 2] = s.out_Color.z; out_rgba[o * 4 + 3] = s.out_Color.w;
+      out_depth[o] = s.gl_FragDepth;
+      out_hit[o] = 1;
+    }
 }
 
 }  // extern "C"

@@ -14,15 +14,18 @@ cannot parse:
     declarations are removed (globals become struct members); interface blocks lose their braces (their members are
     global names in GLSL too); parameter qualifiers `in` / `const in` are removed;
   * GLSL array declarators `T[n] name` become `T name[n]`, an unsized SSBO array `T[] name` becomes `T* name`;
-  * swizzles `.xy .rg .xyz .rgb` become calls (`.xy()` ...), the only multi-component swizzles these shaders use,
-    always as r-values.
+  * swizzles `.xy .rg .xyz .rgb .xx .yz` become calls (`.xy()` ...), the only multi-component swizzles these shaders
+    use, always as r-values;
+  * function prototypes are dropped (class members need none), `out` / `inout` parameters become references,
+    `T[5]` array values become `arr5<T>`, `discard;` sets a flag and returns.
 Everything else - every expression, constant, loop and branch - is compiled as the reference wrote it.
 """
 import os
 import re
 import sys
 
-NAMED = {"/bricks.glsl": "inc_bricks.glsl", "/inc_bbox_test.glsl": "inc_bbox_test.glsl", "/inc_color.glsl": "inc_color.glsl"}
+NAMED = {"/bricks.glsl": "inc_bricks.glsl", "/inc_bbox_test.glsl": "inc_bbox_test.glsl", "/inc_color.glsl": "inc_color.glsl",
+         "/shading.glsl": "shading.glsl"}          # reconstruction.cpp:24 registers glsl/shading.glsl under this name
 
 
 def load(glsl_dir, name, seen):
@@ -75,14 +78,24 @@ def transpile(lines):
                 in_block = False
                 out.append("// " + l.strip())
                 continue
+        # function prototypes (GLSL needs them for forward references; members of a C++ class do not, and may not repeat)
+        if depth == 0 and re.match(r"^\s*[\w\[\]]+\s+\w+\s*\([^()=]*\)\s*;\s*(//.*)?$", code):
+            out.append("// " + l.strip())
+            continue
+        code = re.sub(r"\bdiscard\s*;", "{ discarded = true; return; }", code)
         # parameter qualifiers
         code = re.sub(r"([(,]\s*)const\s+in\s+", r"\1const ", code)
         code = re.sub(r"([(,]\s*)in\s+", r"\1", code)
+        code = re.sub(r"([(,]\s*)(?:out|inout)\s+(\w+)\s+", r"\1\2& ", code)
+        # first-class arrays of 5: T[5] f(...) / T[5] name = ... / T name[5] = T[5](...)
+        code = re.sub(r"\b(\w+)\s+(\w+)\[5\]\s*=", r"arr5<\1> \2 =", code)
+        code = re.sub(r"\b(\w+)\[5\]\s+(\w+)\s*(=|\()", r"arr5<\1> \2 \3", code)
+        code = re.sub(r"\b(\w+)\[5\]\s*\(", r"arr5<\1>(", code)
         # array declarators: T[n] name; -> T name[n];   T[] name; -> T* name;
         code = re.sub(r"\b(\w+)\[(\d+)\]\s+(\w+)\s*;", r"\1 \3[\2];", code)
         code = re.sub(r"\b(\w+)\[\]\s+(\w+)\s*;", r"\1* \2;", code)
         # r-value swizzles
-        code = re.sub(r"\.(xyz|rgb|xy|rg)\b(?!\s*\()", r".\1()", code)
+        code = re.sub(r"\.(xyz|rgb|xy|rg|xx|yz)\b(?!\s*\()", r".\1()", code)
         if not in_block:
             depth += code.count("{") - code.count("}")
         out.append(code)

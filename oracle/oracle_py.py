@@ -68,6 +68,7 @@ def lib():
     L.ro_raymarch.argtypes = [f32p, u32p, C.c_float, C.c_int, f32p, i32p, f32p, i32p, u8p, C.c_int, C.c_int, f32p, f32p, C.c_int, C.c_int,
                               f32p, f32p, f32p, f32p, C.c_int, C.c_int, C.c_int, C.c_int, u32p, C.c_uint32, u32p, C.c_float,
                               f32p, f32p, f32p, f32p]
+    L.ro_raymarch_rays.argtypes = [f32p, f32p, f32p, f32p, C.c_int, C.c_int, C.c_float, f32p, u8p]
     L.ro_decode_dxt1.argtypes = [u8p, C.c_int, C.c_int, u8p]
     L.ro_depth8_to_float.argtypes = [u8p, C.c_size_t, f32p]
     L.ro_fill_num_lods.argtypes = [C.c_int, C.c_int]
@@ -220,6 +221,16 @@ def raymarch(tsdf, limit, inv, scene, pre, grid, occupied, modelview, projection
                       np.ascontiguousarray(projection, np.float32).reshape(16), int(width), int(height), int(shade_mode), int(skip_space),
                       occ, len(occupied), grid["res_bricks"], grid["brick_size"], out["rgba"], out["depth"], out["samples"], out["pos"])
     return out
+
+
+def raymarch_rays(modelview, projection, bbox_min, bbox_max, width, height, limit):
+    """Per pixel the ray's target point in volume space and whether the cube proxy covers the pixel."""
+    pts = np.zeros((height, width, 3), np.float32)
+    cov = np.zeros((height, width), np.uint8)
+    lib().ro_raymarch_rays(np.ascontiguousarray(modelview, np.float32).reshape(16), np.ascontiguousarray(projection, np.float32).reshape(16),
+                           np.ascontiguousarray(bbox_min, np.float32), np.ascontiguousarray(bbox_max, np.float32), int(width), int(height),
+                           np.float32(limit), pts, cov)
+    return pts, cov
 
 
 def raymarch_uniforms(modelview, projection, bbox_min, bbox_max, width, height):

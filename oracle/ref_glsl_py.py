@@ -85,3 +85,49 @@ def integrate(inv, pre, grid, limit, use_bricks, occupied):
                        np.ascontiguousarray(pre["depth_b"]), np.ascontiguousarray(pre["quality"]), W, H, np.float32(limit), res,
                        int(use_bricks), grid["ranges"], occ, len(occupied), tsdf)
     return tsdf
+
+
+def raymarch(tsdf, limit, inv, scene, pre, modelview, projection, width, height, shade_mode=0, depth_peels=None):
+    """ReconIntegration::draw with the reference's glsl/tsdf_raymarch.fs + shading.glsl, one fragment per pixel the cube
+    proxy covers (skipSpace off unless depth_peels [h][w][4] is given). Host-side uniforms (NormalMatrix, vol_to_world,
+    img_to_eye_curr, CameraPos) and the per-pixel ray targets come from the oracle's restatement of
+    recon_integration.cpp:177-206, which is pinned separately (tests/golden/ref_draw_uniforms.npz).
+    Returns dict(rgba, depth, samples, hit)."""
+    import oracle_py as O
+    L = lib()
+    if not hasattr(L, "_rm"):
+        L.rg_raymarch.argtypes = [f32p, u32p, C.c_float, C.c_int, f32p, i32p, f32p, i32p, u8p, C.c_int, C.c_int, f32p, f32p, f32p,
+                                  C.c_int, C.c_int, f32p, f32p, f32p, f32p, C.c_int, C.c_int, C.c_int, f32p, u8p, C.c_void_p,
+                                  f32p, f32p, f32p, u8p]
+        L._rm = True
+    N, IZ, IY, IX, _ = inv.shape
+    X, Y, Z = scene.cv_res
+    _, H, W = pre["quality"].shape
+    res = np.array([tsdf.shape[2], tsdf.shape[1], tsdf.shape[0]], np.uint32)
+    mv = np.ascontiguousarray(modelview, np.float32).reshape(16)
+    pr = np.ascontiguousarray(projection, np.float32).reshape(16)
+    bmin = np.ascontiguousarray(scene.bbox_min, np.float32)
+    bmax = np.ascontiguousarray(scene.bbox_max, np.float32)
+    u = O.raymarch_uniforms(mv, pr, bmin, bmax, width, height)
+    # gl_NormalMatrix: inverse transpose of the model-view's upper 3x3 (column-major storage), embedded in a mat4
+    m3 = mv.reshape(4, 4).T[:3, :3].astype(np.float64)              # row-major 3x3
+    n3 = np.linalg.inv(m3).T
+    gln = np.eye(4, dtype=np.float64)
+    gln[:3, :3] = n3
+    gl_normal = np.ascontiguousarray(gln.T.reshape(16), np.float32)  # back to column-major
+    v2w = np.zeros(16, np.float32)
+    d = (bmax - bmin).astype(np.float32)
+    v2w[0], v2w[5], v2w[10], v2w[15] = d[0], d[1], d[2], 1.0
+    v2w[12:15] = bmin
+    uniforms = np.ascontiguousarray(np.concatenate([mv, pr, gl_normal, u[64:80], v2w, u[0:16]]), np.float32)
+    cam = np.ascontiguousarray(u[80:83], np.float32)
+    pts, cov = O.raymarch_rays(mv, pr, bmin, bmax, width, height, limit)
+    out = dict(rgba=np.zeros((height, width, 4), np.float32), depth=np.zeros((height, width), np.float32),
+               samples=np.zeros((height, width), np.float32), hit=np.zeros((height, width), np.uint8), covered=cov)
+    peels = np.ascontiguousarray(depth_peels, np.float32) if depth_peels is not None else None
+    L.rg_raymarch(np.ascontiguousarray(tsdf), res, np.float32(limit), N, np.ascontiguousarray(inv), np.array([IX, IY, IZ], np.int32),
+                  np.ascontiguousarray(scene.cv_uv), np.array([X, Y, Z], np.int32), np.ascontiguousarray(scene.color), scene.CW, scene.CH,
+                  np.ascontiguousarray(pre["depth_b"]), np.ascontiguousarray(pre["quality"]), np.ascontiguousarray(pre["normal"]), W, H,
+                  bmin, bmax, uniforms, cam, int(width), int(height), int(shade_mode), pts, cov,
+                  peels.ctypes.data if peels is not None else None, out["rgba"], out["depth"], out["samples"], out["hit"])
+    return out

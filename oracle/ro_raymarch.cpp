@@ -1,4 +1,6 @@
-// ORACLE (test infrastructure, NOT product code) — parity unpinned by the reference's own tests (none exist).
+// ORACLE (test infrastructure, NOT product code). The reference ships no tests; the march, shading and colour blending are pinned
+// against the reference's own glsl/tsdf_raymarch.fs + shading.glsl compiled as C++ and run on the CPU (oracle/glsl_host/,
+// tests/golden/ref_glsl_raymarch.npz). The space-skipping hull (a rasteriser in the reference) is this file's definition.
 // Scalar restatement of the TSDF raymarcher: ReconIntegration::draw / drawDepthLimits
 // (framework/reconstruction/recon_integration.cpp:177-241, 409-429), glsl/tsdf_raymarch.{vs,fs}, glsl/shading.glsl,
 // glsl/bricks.{vs,gs,fs}.
@@ -257,6 +259,29 @@ void ro_raymarch_uniforms(const float* mv, const float* proj, const float* bmin,
   const M4* ms[5] = {&f.img_to_eye, &f.inv_mv, &f.inv_v2w, &f.mv_v2w, &f.normal_matrix};
   for (int k = 0; k < 5; ++k) for (int i = 0; i < 16; ++i) out[k * 16 + i] = ms[k]->m[i];
   out[80] = f.camera_pos.x; out[81] = f.camera_pos.y; out[82] = f.camera_pos.z;
+}
+
+// Per pixel: the point screenToVol(vec3(frag.xy, 1.0)) the march aims at (any point of the pixel's ray serves as the
+// cube fragment's pass_Position) and whether the ray meets the unit cube in front of the camera, i.e. whether the cube
+// proxy produces a fragment there. Used to drive the reference's own tsdf_raymarch.fs on the CPU (oracle/glsl_host).
+void ro_raymarch_rays(const float* modelview, const float* projection, const float* bbox_min, const float* bbox_max, int vw, int vh,
+                      float limit, float* out_points, uint8_t* out_covered) {
+  const Frame f = derive(modelview, projection, bbox_min, bbox_max, vw, vh);
+  const float sd = limit * 0.5f;
+  for (int py = 0; py < vh; ++py)
+    for (int px = 0; px < vw; ++px) {
+      const size_t o = (size_t)py * vw + px;
+      V4 pc = mulv(f.img_to_eye, V4{(float)px + 0.5f, (float)py + 0.5f, 1.0f, 1.0f});
+      V4 es{pc.x / pc.w, pc.y / pc.w, pc.z / pc.w, 1.0f};
+      V4 ws = mulv(f.inv_mv, es);
+      V4 pv = mulv(f.inv_v2w, ws);
+      out_points[o * 3] = pv.x; out_points[o * 3 + 1] = pv.y; out_points[o * 3 + 2] = pv.z;
+      const V3 cam = f.camera_pos;
+      const V3 step = normalize3(V3{pv.x, pv.y, pv.z} - cam) * sd;
+      const V3 invs{1.0f / step.x, 1.0f / step.y, 1.0f / step.z};
+      float c0, c1;
+      out_covered[o] = (slab(cam, invs, V3{0, 0, 0}, V3{1, 1, 1}, c0, c1) && !(c1 < 0.0f)) ? 1 : 0;
+    }
 }
 
 void ro_raymarch(const float* tsdf, const uint32_t* res, float limit, int N, const float* inv, const int32_t* inv_res,

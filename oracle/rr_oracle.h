@@ -2,8 +2,8 @@
  * steppobeck/rgbd-recon's volumetric-fusion path. Loaded with ctypes by tests/, __graft_entry__.smoke() and
  * bench.py's cpu_baseline / --impl reference legs ONLY. The reference ships no tests; the
  * restatement is pinned against reference code compiled into oracle/_ref: C++ sources (libref_harness.so, see ro_math.h) and
- * the pre-processing / integration SHADERS run on the CPU (libref_glsl.so, oracle/glsl_host/). The raymarch and colour-fill
- * restatements (ro_raymarch.cpp, ro_colorfill.cpp) remain unpinned. */
+ * the pre-processing / integration / raymarch SHADERS run on the CPU (libref_glsl.so, oracle/glsl_host/). The space-skipping
+ * hull of ro_raymarch.cpp (a rasteriser in the reference) and ro_colorfill.cpp remain unpinned. */
 #ifndef RR_ORACLE_H
 #define RR_ORACLE_H
 #include <stddef.h>
@@ -53,6 +53,8 @@ void ro_calib_invert(const float* cv_xyz, int X, int Y, int Z, const float* bbox
                      const uint32_t* out_res, float* out, uint32_t* neigh_out, int brute);
 
 void ro_raymarch_uniforms(const float* mv, const float* proj, const float* bmin, const float* bmax, int vw, int vh, float* out);
+void ro_raymarch_rays(const float* modelview, const float* projection, const float* bbox_min, const float* bbox_max, int vw, int vh,
+                      float limit, float* out_points, uint8_t* out_covered);
 void ro_raymarch(const float* tsdf, const uint32_t* res, float limit, int N, const float* inv, const int32_t* inv_res,
                  const float* cv_uv, const int32_t* cv_res, const uint8_t* color, int CW, int CH,
                  const float* depth_b, const float* quality, int W, int H, const float* bbox_min, const float* bbox_max,

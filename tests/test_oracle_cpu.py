@@ -288,6 +288,62 @@ def test_oracle_against_reference_shader_goldens(O):
         _assert_stage(key, got, g[key], 2e-5 * 0.01)
 
 
+def _assert_raymarch(got, want_rgba, want_depth, want_samples, want_hit, what, proj):
+    """Oracle raymarch vs the reference's tsdf_raymarch.fs: same fragments kept, same sample counts; surface depth within
+    0.1 mm in eye space (BASELINE's bar is 1 mm) and 1e-5 in window depth; colours within 2e-3 (bilinear RGB8 lookups and
+    gradient normals amplify the ~1e-7 differences of the hit position)."""
+    hit = got["depth"] < 1.0
+    assert np.array_equal(hit, want_hit > 0), f"{what}: hit masks differ on {(hit != (want_hit > 0)).sum()} pixels"
+    assert hit.sum() > 100
+    assert np.array_equal(got["samples"], want_samples), f"{what}: sample counts differ"
+    assert np.abs(got["depth"] - want_depth).max() <= 1e-5, what
+    p22, p32 = np.float64(proj.reshape(16)[10]), np.float64(proj.reshape(16)[14])
+
+    def eye_z(d):                                                       # inverse of gl_FragDepth = ((p22 z + p32) / -z) / 2 + 1/2
+        return p32 / (-(2.0 * d.astype(np.float64) - 1.0) - p22)
+
+    dz_mm = np.abs(eye_z(got["depth"][hit]) - eye_z(want_depth[hit])) * 1000.0
+    assert dz_mm.max() <= 0.1, f"{what}: surface differs by {dz_mm.max():.4f} mm"
+    assert (np.isnan(got["rgba"]) == np.isnan(want_rgba)).all(), what
+    ok = np.isfinite(got["rgba"]) & np.isfinite(want_rgba)
+    assert np.abs(got["rgba"][ok] - want_rgba[ok]).max() <= 2e-3, what
+
+
+def test_oracle_raymarch_matches_the_reference_shader_run_on_cpu(O, small_scene, small_frame):
+    import ref_glsl_py as G
+    if not G.available():
+        pytest.skip("oracle/_ref/libref_glsl.so not built (needs the reference tree at build time)")
+    from rrpy import synth
+    sc = small_scene
+    grid, pre, occ, inv, tsdf = (small_frame[k] for k in ("grid", "pre", "occ", "inv", "tsdf"))
+    VW, VH = 160, 90
+    for eye in ((1.6, 1.5, 2.2), (0.7, 1.3, 0.75)):                    # outside the volume, and inside it
+        mv, pr = synth.look_at(eye, (0.0, 1.1, 0.0)), synth.perspective(50.0, VW / VH, 0.1, 10.0)
+        for mode in range(4):
+            want = G.raymarch(tsdf, 0.01, inv, sc, pre, mv, pr, VW, VH, mode)
+            got = O.raymarch(tsdf, 0.01, inv, sc, pre, grid, occ, mv, pr, VW, VH, mode, skip_space=False)
+            _assert_raymarch(got, want["rgba"], want["depth"], want["samples"], want["hit"], f"eye {eye} mode {mode}", np.asarray(pr))
+
+
+def test_oracle_raymarch_against_reference_shader_golden(O):
+    """tests/golden/ref_glsl_raymarch.npz: the reference's raymarch shader on the oracle's volume of the golden scene."""
+    from rrpy import synth
+    g = gold("ref_glsl_raymarch.npz")
+    sc = synth.make_scene(N=1, W=128, H=106, CW=160, CH=135, cv_res=(24, 24, 48), seed=77)    # tools/make_golden.py::glsl_scene
+    voxel = float(g["voxel"])
+    grid = O.brick_grid(sc.bbox_min, sc.bbox_max, voxel, 0.1)
+    cams = [O.frustum(sc.cv_xyz[i])[1] for i in range(sc.N)]
+    pre = O.preprocess(sc, grid, cams)
+    inv = synth.analytic_inverse(sc, (20, 22, 20))
+    occ = O.occupied_bricks(pre["bricks"], 10)
+    tsdf = O.integrate(inv, pre, grid, 0.01, True, occ)
+    assert hashlib.sha256(np.ascontiguousarray(tsdf).tobytes()).hexdigest() == str(g["tsdf_sha"]), "the golden's input volume changed"
+    mv, pr = synth.look_at((1.2, 1.4, 1.6), (0.0, 1.1, 0.0)), synth.perspective(50.0, 160 / 90, 0.1, 10.0)   # make_golden.py::RM_VIEW
+    for mode in range(4):
+        got = O.raymarch(tsdf, 0.01, inv, sc, pre, grid, occ, mv, pr, 160, 90, mode, skip_space=False)
+        _assert_raymarch(got, g[f"rgba{mode}"], g["depth"], g["samples"], g["hit"], f"golden mode {mode}", np.asarray(pr))
+
+
 # ------------------------------------------------------------------------------------------------ arithmetic pins
 
 def test_gl_sampling_known_answers(O):

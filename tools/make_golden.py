@@ -68,6 +68,31 @@ def golden_glsl():
                         tsdf_bricks=tsdf_bricks, tsdf_dense=tsdf_dense, **{"pre_" + k: v for k, v in pre.items()})
 
 
+RM_VIEW = dict(eye=(1.2, 1.4, 1.6), at=(0.0, 1.1, 0.0), fovy=50.0, w=160, h=90)
+
+
+def golden_glsl_raymarch():
+    """glsl/tsdf_raymarch.fs + shading.glsl run on the CPU (cube-proxy march, skipSpace off) on the ORACLE's stages and volume
+    of glsl_scene(): inputs every machine can regenerate bit for bit, outputs of the reference's shader."""
+    import ref_glsl_py as G
+    sc = glsl_scene()
+    voxel = 0.035
+    grid = O.brick_grid(sc.bbox_min, sc.bbox_max, voxel, 0.1)
+    cams = [O.frustum(sc.cv_xyz[i])[1] for i in range(sc.N)]
+    pre = O.preprocess(sc, grid, cams)
+    inv = synth.analytic_inverse(sc, (20, 22, 20))
+    occ = O.occupied_bricks(pre["bricks"], 10)
+    tsdf = O.integrate(inv, pre, grid, 0.01, True, occ)
+    mv = synth.look_at(RM_VIEW["eye"], RM_VIEW["at"])
+    pr = synth.perspective(RM_VIEW["fovy"], RM_VIEW["w"] / RM_VIEW["h"], 0.1, 10.0)
+    out = {}
+    for mode in range(4):
+        r = G.raymarch(tsdf, 0.01, inv, sc, pre, mv, pr, RM_VIEW["w"], RM_VIEW["h"], mode)
+        out[f"rgba{mode}"] = r["rgba"]
+        out["depth"], out["samples"], out["hit"] = r["depth"], r["samples"], r["hit"]
+    np.savez_compressed(os.path.join(OUT, "ref_glsl_raymarch.npz"), voxel=np.float32(voxel), tsdf_sha=np.array(sha(tsdf)), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     assert R.available(), "build oracle/_ref first (make -C oracle all)"
@@ -76,9 +101,11 @@ def main():
         return
     if "--only-glsl" in sys.argv:
         golden_glsl()
+        golden_glsl_raymarch()
         return
     golden_dxt1()
     golden_glsl()
+    golden_glsl_raymarch()
     sc = golden_scene()
     xyz = sc.cv_xyz[0]
     # --- calibration inversion + frustum (real calibration_inverter.cpp / frustum.cpp)
