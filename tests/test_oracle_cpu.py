@@ -344,6 +344,27 @@ def test_oracle_raymarch_against_reference_shader_golden(O):
         _assert_raymarch(got, g[f"rgba{mode}"], g["depth"], g["samples"], g["hit"], f"golden mode {mode}", np.asarray(pr))
 
 
+def test_space_skipping_hull_agrees_with_the_cube_march(O, small_scene, small_frame):
+    """The space-skipping start (analytic ray / occupied-brick hull here, rasterised depth peels in the reference) is the one
+    part of the raymarch no reference code pins. It changes the sampling phase, so hits are not identical to the pinned cube
+    march; they must agree statistically: > 95 % of the cube march's hits are found, median distance between the two
+    surface points < 0.5 mm."""
+    from rrpy import synth
+    sc = small_scene
+    grid, pre, occ, inv, tsdf = (small_frame[k] for k in ("grid", "pre", "occ", "inv", "tsdf"))
+    VW, VH = 320, 180
+    dims = (sc.bbox_max - sc.bbox_min).astype(np.float64)
+    for eye in ((1.6, 1.5, 2.2), (0.7, 1.3, 0.75), (-2.0, 1.0, 1.2)):
+        mv, pr = synth.look_at(eye, (0.0, 1.1, 0.0)), synth.perspective(50.0, VW / VH, 0.1, 10.0)
+        a = O.raymarch(tsdf, 0.01, inv, sc, pre, grid, occ, mv, pr, VW, VH, 0, skip_space=True)
+        b = O.raymarch(tsdf, 0.01, inv, sc, pre, grid, occ, mv, pr, VW, VH, 0, skip_space=False)
+        ha, hb = a["depth"] < 1.0, b["depth"] < 1.0
+        both = ha & hb
+        assert hb.sum() > 1000 and both.sum() >= 0.95 * hb.sum() and (ha & ~hb).sum() <= 0.01 * hb.sum()
+        dmm = np.linalg.norm((a["pos"].astype(np.float64) - b["pos"]) * dims, axis=-1)[both] * 1000.0
+        assert np.median(dmm) < 0.5
+
+
 # ------------------------------------------------------------------------------------------------ arithmetic pins
 
 def test_gl_sampling_known_answers(O):
