@@ -35,6 +35,8 @@ struct vec2 {
   vec2() : x(0.f), y(0.f) {}
   explicit vec2(float v) : x(v), y(v) {}
   template <typename A, typename B> vec2(A a, B b) : x((float)a), y((float)b) {}
+  inline vec2(const struct ivec2& v);   // GLSL converts ivec2 / uvec2 to vec2 implicitly
+  inline vec2(const struct uvec2& v);
   vec2 xy() const { return *this; }
   vec2 rg() const { return *this; }
   float& operator[](int i) { return i == 0 ? x : y; }
@@ -82,8 +84,17 @@ struct ivec2 {
   int x, y;
   ivec2() : x(0), y(0) {}
   template <typename A, typename B> ivec2(A a, B b) : x((int)a), y((int)b) {}
+  explicit ivec2(int v) : x(v), y(v) {}
   explicit ivec2(const vec2& v) : x((int)v.x), y((int)v.y) {}     // truncation toward zero
+  inline explicit ivec2(const uvec2& v);
 };
+
+struct uvec2 {
+  uint x, y;
+  uvec2() : x(0u), y(0u) {}
+  template <typename A, typename B> uvec2(A a, B b) : x((uint)a), y((uint)b) {}
+};
+inline uvec2 operator+(const uvec2& a, const uvec2& b) { return uvec2(a.x + b.x, a.y + b.y); }
 
 // T[5] as a value (GLSL arrays are first-class: returned from functions, assigned)
 template <typename T> struct arr5 {
@@ -112,6 +123,10 @@ struct uvec3 {
   explicit uvec3(const ivec3& v) : x((uint)v.x), y((uint)v.y), z((uint)v.z) {}
 };
 
+inline ivec2::ivec2(const uvec2& v) : x((int)v.x), y((int)v.y) {}
+inline vec2::vec2(const ivec2& v) : x((float)v.x), y((float)v.y) {}
+inline vec2::vec2(const uvec2& v) : x((float)v.x), y((float)v.y) {}
+inline ivec2 operator+(const ivec2& a, const ivec2& b) { return ivec2(a.x + b.x, a.y + b.y); }
 inline vec3::vec3(const uvec3& v) : x((float)v.x), y((float)v.y), z((float)v.z) {}
 inline vec3::vec3(const ivec3& v) : x((float)v.x), y((float)v.y), z((float)v.z) {}
 inline ivec3::ivec3(const uvec3& v) : x((int)v.x), y((int)v.y), z((int)v.z) {}
@@ -141,6 +156,8 @@ inline vec3& operator-=(vec3& a, const vec3& b) { a = a - b; return a; }
 inline vec3& operator*=(vec3& a, float s) { a = a * s; return a; }
 inline vec3& operator/=(vec3& a, float s) { a = a / s; return a; }
 inline vec2& operator+=(vec2& a, const vec2& b) { a = a + b; return a; }
+inline vec2 operator+(const vec2& a, float s) { return vec2(a.x + s, a.y + s); }
+inline vec2 operator-(const vec2& a, float s) { return vec2(a.x - s, a.y - s); }
 inline vec3 operator/(float s, const vec3& a) { return vec3(s / a.x, s / a.y, s / a.z); }
 inline vec4 operator+(const vec4& a, const vec4& b) { return vec4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 inline vec4 operator*(const vec4& a, float s) { return vec4(a.x * s, a.y * s, a.z * s, a.w * s); }
@@ -167,8 +184,10 @@ inline float sign(float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); }
 inline vec3 sign(const vec3& v) { return vec3(sign(v.x), sign(v.y), sign(v.z)); }
 inline float sqrt(float x) { return std::sqrt(x); }
 inline float ceil(float x) { return std::ceil(x); }
+inline vec2 floor(const vec2& v) { return vec2(std::floor(v.x), std::floor(v.y)); }
 inline vec2 min(const vec2& a, const vec2& b) { return vec2(min(a.x, b.x), min(a.y, b.y)); }
 inline vec2 max(const vec2& a, const vec2& b) { return vec2(max(a.x, b.x), max(a.y, b.y)); }
+inline vec2 clamp(const vec2& v, const vec2& lo, const vec2& hi) { return min(max(v, lo), hi); }   // GLSL 8.3: min(max(x, minVal), maxVal)
 inline vec3 min(const vec3& a, const vec3& b) { return vec3(min(a.x, b.x), min(a.y, b.y), min(a.z, b.z)); }
 inline vec3 max(const vec3& a, const vec3& b) { return vec3(max(a.x, b.x), max(a.y, b.y), max(a.z, b.z)); }
 inline float dot(const vec2& a, const vec2& b) { return a.x * b.x + a.y * b.y; }
@@ -268,12 +287,33 @@ inline vec4 texture(const sampler3D& t, const vec3& p) {
 // ("gauss") and never samples it
 struct sampler2D {
   const float* f32 = nullptr;
-  int W = 0, H = 0;
+  int W = 0, H = 0, C = 4;                            // C = 1: a depth texture (r = depth)
 };
 inline vec4 texelFetch(const sampler2D& t, const ivec2& p, int) {
-  if (p.x < 0 || p.y < 0 || p.x >= t.W || p.y >= t.H) return vec4(0.f);          // undefined in GL; robust-access result
-  const float* q = t.f32 + ((size_t)p.y * t.W + p.x) * 4;
-  return vec4(q[0], q[1], q[2], q[3]);
+  if (p.x < 0 || p.y < 0 || p.x >= t.W || p.y >= t.H) return vec4(0.f);          // undefined in GL; robust-access result (zeros)
+  const float* q = t.f32 + ((size_t)p.y * t.W + p.x) * t.C;
+  return t.C == 4 ? vec4(q[0], q[1], q[2], q[3]) : vec4(q[0], 0.f, 0.f, 1.f);
+}
+// LINEAR + MIRRORED_REPEAT (GL 4.4 table 8.20: mirror(a) = a >= 0 ? a : -(1 + a); i -> (size - 1) - mirror((i mod 2 size) - size))
+inline int mirrored_repeat(int i, int size) {
+  int m = i % (2 * size);
+  if (m < 0) m += 2 * size;
+  int a = m - size;
+  if (a < 0) a = -(1 + a);
+  return (size - 1) - a;
+}
+inline vec4 texture(const sampler2D& t, const vec2& p) {
+  const float u = p.x * (float)t.W - 0.5f, v = p.y * (float)t.H - 0.5f;
+  const float fu = std::floor(u), fv = std::floor(v);
+  const float a = u - fu, b = v - fv;
+  const int i0 = mirrored_repeat((int)fu, t.W), i1 = mirrored_repeat((int)fu + 1, t.W);
+  const int j0 = mirrored_repeat((int)fv, t.H), j1 = mirrored_repeat((int)fv + 1, t.H);
+  float o[4];
+  for (int c = 0; c < 4; ++c) {
+    auto tx = [&](int j, int i) { return t.f32[((size_t)j * t.W + i) * 4 + c]; };
+    o[c] = mix(mix(tx(j0, i0), tx(j0, i1), a), mix(tx(j1, i0), tx(j1, i1), a), b);
+  }
+  return vec4(o[0], o[1], o[2], o[3]);
 }
 
 struct image2D {                                      // layout(r32f) image2D, write-only

@@ -10,7 +10,9 @@
 //   tsdf_integration: ReconIntegration::integrate (framework/reconstruction/recon_integration.cpp:243-270), one vertex
 //     per voxel centre (framework/rendering/volume_sampler.cpp:33-48).
 // Built only where the reference tree is present; output oracle/_ref/libref_glsl.so (git-ignored).
+#include <cmath>
 #include <cstdint>
+#include <cstring>
 #include <vector>
 
 #include "glsl_compat.hpp"
@@ -40,6 +42,15 @@ struct S_tsdf_raymarch {
   struct { float near, far, diff; } gl_DepthRange = {0.0f, 1.0f, 1.0f};       // glDepthRange defaults
   bool discarded = false;
 #include "tsdf_raymarch.inc"
+};
+struct S_framebuffer_transfer {
+#include "framebuffer_transfer.inc"
+};
+struct S_tsdf_inpaint {
+#include "tsdf_inpaint.inc"
+};
+struct S_tsdf_colorfill {
+#include "tsdf_colorfill.inc"
 };
 }  // namespace glsl
 
@@ -284,6 +295,106 @@ void rg_raymarch(const float* tsdf, const uint32_t* res, float limit, int N, con
       out_rgba[o * 4] = s.out_Color.x; out_rgba[o * 4 + 1] = s.out_Color.y; out_rgba[o * 4 + 2] = s.out_Color.z; out_rgba[o * 4 + 3] = s.out_Color.w;
       out_depth[o] = s.gl_FragDepth;
       out_hit[o] = 1;
+    }
+}
+
+// ReconIntegration::fillColors (recon_integration.cpp:280-339) with the reference's framebuffer_transfer.fs, tsdf_inpaint.fs
+// and tsdf_colorfill.fs. The harness plays the host: the two ViewLod atlases (1.5 W x H, RGBA32F + depth; view_lod.cpp:24-52
+// for the lod viewports), ViewLod::enable's viewport and clears (:61-81), the ping-pong of :282-312, glDepthFunc(GL_ALWAYS)
+// inside and GL_LESS against a cleared depth buffer for the final pass. Same I/O convention as ro_fill_colors.
+void rg_fill_colors(const float* rgba, const float* depth, int W, int H, float* out_rgba, float* atlas_rgba, float* atlas_depth) {
+  const int FW = (int)((float)W * 1.5f);
+  int n = 1 + (int)std::floor(std::log2((float)(W < H ? W : H)));
+  if (n > 20) n = 20;
+  uvec2 off[20], res[20];
+  int oy = H;
+  for (int i = 0; i < n; ++i) {
+    res[i] = uvec2((uint)std::floor((float)W / std::pow(2.0f, (float)i)), (uint)std::floor((float)H / std::pow(2.0f, (float)i)));
+    if (i > 0) { oy -= (int)res[i].y; off[i] = uvec2((uint)W, (uint)oy); }
+  }
+  const size_t npx = (size_t)FW * H;
+  std::vector<float> col[2], dep[2];
+  for (int k = 0; k < 2; ++k) { col[k].assign(npx * 4, 0.0f); dep[k].assign(npx, 1.0f); }
+  auto clear = [&](int k) {                                          // glClearColor(0,1,0,0), glClearDepth(1)
+    for (size_t i = 0; i < npx; ++i) { col[k][i * 4] = 0.f; col[k][i * 4 + 1] = 1.f; col[k][i * 4 + 2] = 0.f; col[k][i * 4 + 3] = 0.f; dep[k][i] = 1.0f; }
+  };
+  // draw(): atlas 0 cleared, raymarch fragments that were not discarded and pass GL_LESS
+  clear(0);
+  for (int y = 0; y < H; ++y)
+    for (int x = 0; x < W; ++x) {
+      const float* p = rgba + ((size_t)y * W + x) * 4;
+      const float d = depth[(size_t)y * W + x];
+      if (p[3] != 0.0f && d < 1.0f) {
+        for (int c = 0; c < 4; ++c) col[0][((size_t)y * FW + x) * 4 + c] = p[c];
+        dep[0][(size_t)y * FW + x] = d;
+      }
+    }
+  auto samplers = [&](int k, sampler2D& c, sampler2D& d) {
+    c.f32 = col[k].data(); c.W = FW; c.H = H; c.C = 4;
+    d.f32 = dep[k].data(); d.W = FW; d.H = H; d.C = 1;
+  };
+  int cur = 0;                                                        // m_view_inpaint; 1 - cur = m_view_inpaint2
+  auto transfer = [&]() {
+    const int dst = 1 - cur;
+    clear(dst);                                                       // enable(0): clears the whole attachment
+    S_framebuffer_transfer proto{};
+    samplers(cur, proto.texture_color, proto.texture_depth);
+    proto.resolution_tex = uvec2((uint)FW, (uint)H);                  // resolution_full (:511)
+    proto.lod = 0;
+    for (int y = 0; y < H; ++y)                                       // viewport (0, 0, W, H)
+      for (int x = 0; x < W; ++x) {
+        S_framebuffer_transfer s(proto);
+        s.pass_TexCoord = vec2(((float)x + 0.5f) / (float)W, ((float)y + 0.5f) / (float)H);
+        s.main();
+        float* o = col[dst].data() + ((size_t)y * FW + x) * 4;
+        o[0] = s.out_FragColor.x; o[1] = s.out_FragColor.y; o[2] = s.out_FragColor.z; o[3] = s.out_FragColor.w;
+        dep[dst][(size_t)y * FW + x] = s.gl_FragDepth;
+      }
+    cur = dst;                                                        // std::swap(m_view_inpaint, m_view_inpaint2)
+  };
+  transfer();
+  for (int i = 1; i < n; ++i) {
+    const int dst = 1 - cur;
+    S_tsdf_inpaint proto{};
+    samplers(cur, proto.texture_color, proto.texture_depth);
+    proto.resolution_inv = vec2(1.0f / (float)FW, 1.0f / (float)H);
+    proto.lod = i - 1;
+    for (int k = 0; k < n; ++k) { proto.texture_offsets[k] = off[k]; proto.texture_resolutions[k] = res[k]; }
+    proto.viewport_offset = vec2(0.0f, 0.0f);
+    const int vx = (int)off[i].x, vy = (int)off[i].y, vw = (int)res[i].x, vh = (int)res[i].y;   // enable(i, false, false)
+    for (int y = vy; y < vy + vh; ++y)
+      for (int x = vx; x < vx + vw; ++x) {
+        if (x < 0 || y < 0 || x >= FW || y >= H) continue;
+        S_tsdf_inpaint s(proto);
+        s.gl_FragCoord = vec4((float)x, (float)y, 0.0f, 1.0f);      // layout(pixel_center_integer)
+        s.pass_TexCoord = vec2(((float)(x - vx) + 0.5f) / (float)vw, ((float)(y - vy) + 0.5f) / (float)vh);
+        s.main();
+        float* o = col[dst].data() + ((size_t)y * FW + x) * 4;
+        o[0] = s.out_FragColor.x; o[1] = s.out_FragColor.y; o[2] = s.out_FragColor.z; o[3] = s.out_FragColor.w;
+        dep[dst][(size_t)y * FW + x] = s.gl_FragDepth;                // GL_ALWAYS
+      }
+    cur = dst;
+    transfer();
+  }
+  const int F = 1 - cur;                                              // m_view_inpaint2 after the last swap: the atlas with every lod
+  if (atlas_rgba) std::memcpy(atlas_rgba, col[F].data(), npx * 4 * sizeof(float));
+  if (atlas_depth) std::memcpy(atlas_depth, dep[F].data(), npx * sizeof(float));
+  S_tsdf_colorfill proto{};
+  samplers(F, proto.texture_color, proto.texture_depth);
+  proto.resolution_inv = vec2(1.0f / (float)FW, 1.0f / (float)H);
+  proto.num_lods = n;
+  for (int k = 0; k < n; ++k) { proto.texture_offsets[k] = off[k]; proto.texture_resolutions[k] = res[k]; }
+  proto.viewport_offset = vec2(0.0f, 0.0f);
+  for (int y = 0; y < H; ++y)
+    for (int x = 0; x < W; ++x) {
+      S_tsdf_colorfill s(proto);
+      s.gl_FragCoord = vec4((float)x, (float)y, 0.0f, 1.0f);
+      s.pass_TexCoord = vec2(((float)x + 0.5f) / (float)W, ((float)y + 0.5f) / (float)H);
+      s.main();
+      float* o = out_rgba + ((size_t)y * W + x) * 4;
+      const float* in = rgba + ((size_t)y * W + x) * 4;
+      if (s.gl_FragDepth < 1.0f) { o[0] = s.out_FragColor.x; o[1] = s.out_FragColor.y; o[2] = s.out_FragColor.z; o[3] = s.out_FragColor.w; }
+      else { o[0] = in[0]; o[1] = in[1]; o[2] = in[2]; o[3] = in[3]; }   // GL_LESS against the cleared depth buffer
     }
 }
 

@@ -16,6 +16,7 @@ cannot parse:
   * GLSL array declarators `T[n] name` become `T name[n]`, an unsized SSBO array `T[] name` becomes `T* name`;
   * swizzles `.xy .rg .xyz .rgb .xx .yz` become calls (`.xy()` ...), the only multi-component swizzles these shaders
     use, always as r-values;
+  * global `const int` become `static constexpr int` (they size arrays);
   * function prototypes are dropped (class members need none), `out` / `inout` parameters become references,
     `T[5]` array values become `arr5<T>`, `discard;` sets a flag and returns.
 Everything else - every expression, constant, loop and branch - is compiled as the reference wrote it.
@@ -78,6 +79,9 @@ def transpile(lines):
                 in_block = False
                 out.append("// " + l.strip())
                 continue
+        # integer constants that size arrays must be constant expressions in C++ too
+        if depth == 0:
+            code = re.sub(r"^(\s*)const\s+int\s+(\w+\s*=)", r"\1static constexpr int \2", code)
         # function prototypes (GLSL needs them for forward references; members of a C++ class do not, and may not repeat)
         if depth == 0 and re.match(r"^\s*[\w\[\]]+\s+\w+\s*\([^()=]*\)\s*;\s*(//.*)?$", code):
             out.append("// " + l.strip())

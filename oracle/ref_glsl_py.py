@@ -131,3 +131,24 @@ def raymarch(tsdf, limit, inv, scene, pre, modelview, projection, width, height,
                   bmin, bmax, uniforms, cam, int(width), int(height), int(shade_mode), pts, cov,
                   peels.ctypes.data if peels is not None else None, out["rgba"], out["depth"], out["samples"], out["hit"])
     return out
+
+
+def fill_colors(rgba, depth, want_atlas=False):
+    """ReconIntegration::fillColors with the reference's framebuffer_transfer.fs / tsdf_inpaint.fs / tsdf_colorfill.fs
+    (same conventions as oracle_py.fill_colors)."""
+    L = lib()
+    if not hasattr(L, "_fc"):
+        L.rg_fill_colors.argtypes = [f32p, f32p, C.c_int, C.c_int, f32p, C.c_void_p, C.c_void_p]
+        L._fc = True
+    rgba = np.ascontiguousarray(rgba, np.float32)
+    depth = np.ascontiguousarray(depth, np.float32)
+    H, W, _ = rgba.shape
+    out = np.zeros_like(rgba)
+    if not want_atlas:
+        L.rg_fill_colors(rgba, depth, W, H, out, None, None)
+        return out
+    FW = int(np.float32(W) * np.float32(1.5))
+    ac = np.zeros((H, FW, 4), np.float32)
+    ad = np.zeros((H, FW), np.float32)
+    L.rg_fill_colors(rgba, depth, W, H, out, ac.ctypes.data, ad.ctypes.data)
+    return out, ac, ad

@@ -1,4 +1,5 @@
-// ORACLE (test infrastructure, NOT product code) — parity unpinned by the reference's own tests (none exist).
+// ORACLE (test infrastructure, NOT product code). The reference ships no tests; this file is pinned against the reference's own
+// framebuffer_transfer.fs / tsdf_inpaint.fs / tsdf_colorfill.fs run on the CPU (oracle/glsl_host/, tests/golden/ref_glsl_colorfill.npz).
 // Scalar restatement of the colour hole filling that follows the raymarch when m_fill_holes is set (the default,
 // framework/reconstruction/recon_integration.cpp:54): ReconIntegration::fillColors (recon_integration.cpp:280-339),
 // the ViewLod mip atlas (framework/rendering/view_lod.cpp:24-61), glsl/framebuffer_transfer.fs, glsl/tsdf_inpaint.fs

@@ -2,10 +2,9 @@
   * golden vectors produced by REAL reference code (tests/golden/ref_*.npz, made by tools/make_golden.py from oracle/_ref),
   * the live oracle/_ref library when it is present (build container only),
   * known answers of the arithmetic pins (GL filtering equations, deterministic pow),
-  * the reference's OWN shaders for pre-processing and integration, compiled as C++ and run on the CPU
-    (oracle/_ref/libref_glsl.so, oracle/glsl_host/) - live where built, and as tests/golden/ref_glsl_stages.npz elsewhere,
-  * self-regression pins of the shader restatement (the raymarch / colour-fill shaders are not yet run this way; the
-    reference ships no tests of its own).
+  * the reference's OWN shaders (pre-processing, integration, raymarch + shading, colour fill), compiled as C++ and run on
+    the CPU (oracle/_ref/libref_glsl.so, oracle/glsl_host/) - live where built, and as tests/golden/ref_glsl_*.npz elsewhere,
+  * self-regression pins of the restatement (the reference ships no tests of its own).
 """
 import hashlib
 import os
@@ -342,6 +341,36 @@ def test_oracle_raymarch_against_reference_shader_golden(O):
     for mode in range(4):
         got = O.raymarch(tsdf, 0.01, inv, sc, pre, grid, occ, mv, pr, 160, 90, mode, skip_space=False)
         _assert_raymarch(got, g[f"rgba{mode}"], g["depth"], g["samples"], g["hit"], f"golden mode {mode}", np.asarray(pr))
+
+
+def _assert_colorfill(O, rgba, depth, want_filled, want_atlas_c, want_atlas_d, what):
+    got, ac, ad = O.fill_colors(rgba, depth, want_atlas=True)
+    assert bits_equal(ac, want_atlas_c).all() and bits_equal(ad, want_atlas_d).all(), f"{what}: the mip atlas (transfer + inpaint passes) must be identical"
+    assert (np.isnan(got) == np.isnan(want_filled)).all()
+    ok = np.isfinite(got) & np.isfinite(want_filled)
+    assert np.abs(got[ok] - want_filled[ok]).max() <= 5e-7, f"{what}: filled colours (two bilinear fetches blended)"
+    assert (got != rgba).any(axis=-1).sum() > 50, f"{what}: the fill must change pixels"
+
+
+def test_oracle_colorfill_matches_the_reference_shaders_run_on_cpu(O, small_scene, small_frame):
+    """fillColors: framebuffer_transfer.fs, tsdf_inpaint.fs and tsdf_colorfill.fs of the reference run on the CPU under a harness
+    that plays ViewLod / ReconIntegration::fillColors (oracle/glsl_host/glsl_harness.cpp) vs ro_colorfill.cpp."""
+    import ref_glsl_py as G
+    if not G.available():
+        pytest.skip("oracle/_ref/libref_glsl.so not built (needs the reference tree at build time)")
+    from rrpy import synth
+    sc = small_scene
+    grid, pre, occ, inv, tsdf = (small_frame[k] for k in ("grid", "pre", "occ", "inv", "tsdf"))
+    for VW, VH in ((320, 180), (161, 97)):                             # odd sizes: truncated lod resolutions
+        mv, pr = synth.look_at((1.6, 1.5, 2.2), (0.0, 1.1, 0.0)), synth.perspective(50.0, VW / VH, 0.1, 10.0)
+        rm = O.raymarch(tsdf, 0.01, inv, sc, pre, grid, occ, mv, pr, VW, VH, 0, skip_space=True)
+        want, ac, ad = G.fill_colors(rm["rgba"], rm["depth"], want_atlas=True)
+        _assert_colorfill(O, rm["rgba"], rm["depth"], want, ac, ad, f"{VW}x{VH}")
+
+
+def test_oracle_colorfill_against_reference_shader_golden(O):
+    g = gold("ref_glsl_colorfill.npz")
+    _assert_colorfill(O, g["rgba"], g["depth"], g["filled"], g["atlas_color"], g["atlas_depth"], "golden")
 
 
 def test_space_skipping_hull_agrees_with_the_cube_march(O, small_scene, small_frame):

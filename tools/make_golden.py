@@ -91,6 +91,10 @@ def golden_glsl_raymarch():
         out[f"rgba{mode}"] = r["rgba"]
         out["depth"], out["samples"], out["hit"] = r["depth"], r["samples"], r["hit"]
     np.savez_compressed(os.path.join(OUT, "ref_glsl_raymarch.npz"), voxel=np.float32(voxel), tsdf_sha=np.array(sha(tsdf)), **out)
+    # colour hole filling (framebuffer_transfer.fs, tsdf_inpaint.fs, tsdf_colorfill.fs) on the shaded image above
+    filled, atlas_c, atlas_d = G.fill_colors(out["rgba1"], out["depth"], want_atlas=True)
+    np.savez_compressed(os.path.join(OUT, "ref_glsl_colorfill.npz"), rgba=out["rgba1"], depth=out["depth"], filled=filled,
+                        atlas_color=atlas_c, atlas_depth=atlas_d)
 
 
 def main():
