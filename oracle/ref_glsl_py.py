@@ -152,3 +152,58 @@ def fill_colors(rgba, depth, want_atlas=False):
     ad = np.zeros((H, FW), np.float32)
     L.rg_fill_colors(rgba, depth, W, H, out, ac.ctypes.data, ad.ctypes.data)
     return out, ac, ad
+
+
+def depth_peels(scene, grid, occupied, modelview, projection, width, height, limit):
+    """What ReconIntegration::drawDepthLimits leaves in the depth-peel texture (recon_integration.cpp:409-429, bricks.vs/fs,
+    GL_MIN blending over the clear colour (1, 0, 1, 0)): per pixel (nearest face z, -farthest face z, nearest BACK face z, .)
+    in window space, for the full brick_size cube of every occupied brick (bricks.vs:18-19). A rasteriser samples faces at
+    pixel centres, which is the intersection of the pixel's ray with the cube; faces in front of the near plane are clipped.
+    bricks.gs only drops faces between two occupied bricks, which never hold the per-pixel minimum or maximum. float64."""
+    import oracle_py as O
+    mv = np.asarray(modelview, np.float64).reshape(4, 4).T              # column-major storage -> row-major matrix
+    pr = np.asarray(projection, np.float64).reshape(4, 4).T
+    bmin = np.asarray(scene.bbox_min, np.float64)
+    dims = np.asarray(scene.bbox_max, np.float64) - bmin
+    v2w = np.eye(4)
+    v2w[:3, :3] = np.diag(dims)
+    v2w[:3, 3] = bmin
+    pvm = pr @ mv @ v2w
+    u = O.raymarch_uniforms(modelview, projection, scene.bbox_min, scene.bbox_max, width, height)
+    cam = u[80:83].astype(np.float64)
+    pts, _ = O.raymarch_rays(modelview, projection, scene.bbox_min, scene.bbox_max, width, height, limit)
+    d = pts.astype(np.float64) - cam
+    d /= np.linalg.norm(d, axis=-1, keepdims=True)
+    rb = [int(v) for v in grid["res_bricks"]]
+    bs = float(grid["brick_size"])
+    peels = np.zeros((height, width, 4), np.float64)
+    peels[..., 0] = 1.0
+    peels[..., 2] = 1.0
+
+    def window_z(t):
+        p = cam + d * t[..., None]
+        clip = p @ pvm[:, :3].T + pvm[:, 3]
+        visible = clip[..., 2] >= -clip[..., 3]                          # not clipped by the near plane
+        return clip[..., 2] / clip[..., 3] * 0.5 + 0.5, visible
+
+    with np.errstate(divide="ignore", invalid="ignore"):
+        inv_d = 1.0 / d
+        for bid in np.asarray(occupied, np.int64):
+            iz, rem = divmod(int(bid), rb[0] * rb[1])
+            iy, ix = divmod(rem, rb[0])
+            lo = np.array([ix, iy, iz], np.float64) * bs / dims
+            hi = np.array([ix + 1, iy + 1, iz + 1], np.float64) * bs / dims
+            ta, tb = (lo - cam) * inv_d, (hi - cam) * inv_d
+            t0 = np.minimum(ta, tb).max(axis=-1)
+            t1 = np.maximum(ta, tb).min(axis=-1)
+            hit = t0 <= t1
+            z0, vis0 = window_z(t0)                                      # entry: a front face
+            z1, vis1 = window_z(t1)                                      # exit: a back face
+            f = hit & vis0 & (t0 > 0)
+            b = hit & vis1 & (t1 > 0)
+            peels[..., 0] = np.where(f, np.minimum(peels[..., 0], z0), peels[..., 0])
+            peels[..., 1] = np.where(f, np.minimum(peels[..., 1], -z0), peels[..., 1])
+            peels[..., 0] = np.where(b, np.minimum(peels[..., 0], z1), peels[..., 0])
+            peels[..., 1] = np.where(b, np.minimum(peels[..., 1], -z1), peels[..., 1])
+            peels[..., 2] = np.where(b, np.minimum(peels[..., 2], z1), peels[..., 2])
+    return peels.astype(np.float32)

@@ -1,6 +1,7 @@
 // ORACLE (test infrastructure, NOT product code). The reference ships no tests; the march, shading and colour blending are pinned
 // against the reference's own glsl/tsdf_raymarch.fs + shading.glsl compiled as C++ and run on the CPU (oracle/glsl_host/,
-// tests/golden/ref_glsl_raymarch.npz). The space-skipping hull (a rasteriser in the reference) is this file's definition.
+// tests/golden/ref_glsl_raymarch.npz), including the skipSpace branch on depth peels as a rasteriser leaves them
+// (oracle/ref_glsl_py.py::depth_peels).
 // Scalar restatement of the TSDF raymarcher: ReconIntegration::draw / drawDepthLimits
 // (framework/reconstruction/recon_integration.cpp:177-241, 409-429), glsl/tsdf_raymarch.{vs,fs}, glsl/shading.glsl,
 // glsl/bricks.{vs,gs,fs}.

@@ -2,8 +2,9 @@
  * steppobeck/rgbd-recon's volumetric-fusion path. Loaded with ctypes by tests/, __graft_entry__.smoke() and
  * bench.py's cpu_baseline / --impl reference legs ONLY. The reference ships no tests; the
  * restatement is pinned against reference code compiled into oracle/_ref: C++ sources (libref_harness.so, see ro_math.h) and
- * the pre-processing / integration / raymarch / colour-fill SHADERS run on the CPU (libref_glsl.so, oracle/glsl_host/). Only the
- * space-skipping hull of ro_raymarch.cpp (a rasteriser in the reference) remains this restatement's own definition. */
+ * the pre-processing / integration / raymarch / colour-fill SHADERS run on the CPU (libref_glsl.so, oracle/glsl_host/). The
+ * space-skipping hull of ro_raymarch.cpp (a rasteriser in the reference) is checked through the shader's skipSpace branch on
+ * depth peels stated by ref_glsl_py.depth_peels. */
 #ifndef RR_ORACLE_H
 #define RR_ORACLE_H
 #include <stddef.h>

@@ -287,14 +287,14 @@ def test_oracle_against_reference_shader_goldens(O):
         _assert_stage(key, got, g[key], 2e-5 * 0.01)
 
 
-def _assert_raymarch(got, want_rgba, want_depth, want_samples, want_hit, what, proj):
+def _assert_raymarch(got, want_rgba, want_depth, want_samples, want_hit, what, proj, sample_flips=0.0):
     """Oracle raymarch vs the reference's tsdf_raymarch.fs: same fragments kept, same sample counts; surface depth within
     0.1 mm in eye space (BASELINE's bar is 1 mm) and 1e-5 in window depth; colours within 2e-3 (bilinear RGB8 lookups and
     gradient normals amplify the ~1e-7 differences of the hit position)."""
     hit = got["depth"] < 1.0
     assert np.array_equal(hit, want_hit > 0), f"{what}: hit masks differ on {(hit != (want_hit > 0)).sum()} pixels"
     assert hit.sum() > 100
-    assert np.array_equal(got["samples"], want_samples), f"{what}: sample counts differ"
+    assert (got["samples"] != want_samples).mean() <= sample_flips, f"{what}: sample counts differ on {(got['samples'] != want_samples).sum()} pixels"
     assert np.abs(got["depth"] - want_depth).max() <= 1e-5, what
     p22, p32 = np.float64(proj.reshape(16)[10]), np.float64(proj.reshape(16)[14])
 
@@ -324,6 +324,26 @@ def test_oracle_raymarch_matches_the_reference_shader_run_on_cpu(O, small_scene,
             _assert_raymarch(got, want["rgba"], want["depth"], want["samples"], want["hit"], f"eye {eye} mode {mode}", np.asarray(pr))
 
 
+def test_oracle_space_skipping_matches_the_reference_shader_on_rasterised_peels(O, small_scene, small_frame):
+    """The skipSpace branch of tsdf_raymarch.fs (getStartPos, screenToVol) fed the depth peels drawDepthLimits' rasteriser
+    would leave (ref_glsl_py.depth_peels: pixel-centre ray / brick-cube intersections in window space, float64) against the
+    oracle's analytic hull: same fragments, surface within 0.1 mm, colours within 2e-3; ceil() of the march length may flip
+    the sample count of a few pixels."""
+    import ref_glsl_py as G
+    if not G.available():
+        pytest.skip("oracle/_ref/libref_glsl.so not built (needs the reference tree at build time)")
+    from rrpy import synth
+    sc = small_scene
+    grid, pre, occ, inv, tsdf = (small_frame[k] for k in ("grid", "pre", "occ", "inv", "tsdf"))
+    VW, VH = 240, 135
+    for eye in ((1.6, 1.5, 2.2), (-2.0, 1.0, 1.2), (0.7, 1.3, 0.75)):   # the last one sits inside the volume
+        mv, pr = synth.look_at(eye, (0.0, 1.1, 0.0)), synth.perspective(50.0, VW / VH, 0.1, 10.0)
+        peels = G.depth_peels(sc, grid, occ, mv, pr, VW, VH, 0.01)
+        want = G.raymarch(tsdf, 0.01, inv, sc, pre, mv, pr, VW, VH, 1, depth_peels=peels)
+        got = O.raymarch(tsdf, 0.01, inv, sc, pre, grid, occ, mv, pr, VW, VH, 1, skip_space=True)
+        _assert_raymarch(got, want["rgba"], want["depth"], want["samples"], want["hit"], f"skipSpace eye {eye}", np.asarray(pr), sample_flips=0.01)
+
+
 def test_oracle_raymarch_against_reference_shader_golden(O):
     """tests/golden/ref_glsl_raymarch.npz: the reference's raymarch shader on the oracle's volume of the golden scene."""
     from rrpy import synth
@@ -341,6 +361,8 @@ def test_oracle_raymarch_against_reference_shader_golden(O):
     for mode in range(4):
         got = O.raymarch(tsdf, 0.01, inv, sc, pre, grid, occ, mv, pr, 160, 90, mode, skip_space=False)
         _assert_raymarch(got, g[f"rgba{mode}"], g["depth"], g["samples"], g["hit"], f"golden mode {mode}", np.asarray(pr))
+    got = O.raymarch(tsdf, 0.01, inv, sc, pre, grid, occ, mv, pr, 160, 90, 1, skip_space=True)
+    _assert_raymarch(got, g["skip_rgba"], g["skip_depth"], g["skip_samples"], g["skip_hit"], "golden skipSpace", np.asarray(pr), sample_flips=0.01)
 
 
 def _assert_colorfill(O, rgba, depth, want_filled, want_atlas_c, want_atlas_d, what):

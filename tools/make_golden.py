@@ -90,6 +90,10 @@ def golden_glsl_raymarch():
         r = G.raymarch(tsdf, 0.01, inv, sc, pre, mv, pr, RM_VIEW["w"], RM_VIEW["h"], mode)
         out[f"rgba{mode}"] = r["rgba"]
         out["depth"], out["samples"], out["hit"] = r["depth"], r["samples"], r["hit"]
+    # the skipSpace branch (getStartPos / screenToVol) on depth peels as drawDepthLimits' rasteriser leaves them
+    peels = G.depth_peels(sc, grid, occ, mv, pr, RM_VIEW["w"], RM_VIEW["h"], 0.01)
+    r = G.raymarch(tsdf, 0.01, inv, sc, pre, mv, pr, RM_VIEW["w"], RM_VIEW["h"], 1, depth_peels=peels)
+    out.update(skip_rgba=r["rgba"], skip_depth=r["depth"], skip_samples=r["samples"], skip_hit=r["hit"])
     np.savez_compressed(os.path.join(OUT, "ref_glsl_raymarch.npz"), voxel=np.float32(voxel), tsdf_sha=np.array(sha(tsdf)), **out)
     # colour hole filling (framebuffer_transfer.fs, tsdf_inpaint.fs, tsdf_colorfill.fs) on the shaded image above
     filled, atlas_c, atlas_d = G.fill_colors(out["rgba1"], out["depth"], want_atlas=True)
