@@ -153,6 +153,9 @@ int rr_integrate(rr_ctx* ctx);
  * (frame slot, flags) as a CUDA graph and replayed, so a frame costs one launch on the host; any rr_configure /
  * rr_set_slab / rr_set_frame_format / calibration upload / rr_set_tunable drops the captured graphs. Same results. */
 int rr_fuse_frame(rr_ctx* ctx, int filter_textures, int use_processed_depth, int refine_boundary);
+/* ReconIntegration::numBricks / occupiedRatio (recon_integration.hpp:58-60) for the last rr_bricks_update / rr_fuse_frame:
+ * waits for the context's stream, then returns the occupied-brick count and count / number of bricks. No launch. */
+int rr_bricks_count(rr_ctx* ctx, uint32_t* out_num_occupied, float* out_ratio);
 /* ReconIntegration::drawF/draw (recon_integration.cpp:151-241) + glsl/tsdf_raymarch.fs, bricks.{vs,gs,fs}.
  * out_rgba float32 [h][w][4], out_depth float32 [h][w] (gl_FragDepth, 1.0 where no surface), both host, may be NULL. */
 int rr_raymarch(rr_ctx* ctx, const rr_view* view, float* out_rgba, float* out_depth);

@@ -554,6 +554,16 @@ int rr_fuse_frame(rr_ctx* c, int filter_textures, int use_processed_depth, int r
   return check(c, cudaGraphLaunch(exec, c->stream), "frame graph launch");
 }
 
+int rr_bricks_count(rr_ctx* c, uint32_t* out_num, float* out_ratio) {
+  if (!c) return RR_ERR_INVALID;
+  RR_REQUIRE(c, c->configured, "rr_bricks_count: call rr_configure first");
+  RR_SET_DEVICE(c);
+  RR_TRY(check(c, cudaStreamSynchronize(c->stream), "bricks count sync"));
+  if (out_num) *out_num = *c->h_num_occ;
+  if (out_ratio) *out_ratio = float(*c->h_num_occ) / float(c->bricks.num);
+  return RR_OK;
+}
+
 static int ensure_view(rr_ctx* c, int w, int h) {
   if (w == c->view_w && h == c->view_h) return RR_OK;
   RR_TRY(check(c, cudaStreamSynchronize(c->stream), "raymarch resize sync"));

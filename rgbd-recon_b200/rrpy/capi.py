@@ -75,6 +75,7 @@ def lib():
     L.rr_bricks_update.argtypes = [vp, u32, f32]
     L.rr_integrate.argtypes = [vp]
     L.rr_fuse_frame.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+    L.rr_bricks_count.argtypes = [vp, u32, f32]
     L.rr_raymarch.argtypes = [vp, C.POINTER(View), f32, f32]
     L.rr_raymarch_partial.argtypes = [vp, C.POINTER(View), vp]
     L.rr_composite.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, f32, f32]
@@ -316,6 +317,13 @@ class Fusion:
     def fuse_frame(self, filter_textures=True, use_processed_depth=True, refine=True):
         """frame() as ONE call (rr_fuse_frame): replays a captured CUDA graph when stage timing is off."""
         self._ck(self.L.rr_fuse_frame(self.h, int(filter_textures), int(use_processed_depth), int(refine)))
+
+    def bricks_count(self):
+        """(occupied bricks, occupied ratio) of the last bricks_update / fuse_frame; waits for the stream, no launch."""
+        n = C.c_uint32()
+        r = C.c_float()
+        self._ck(self.L.rr_bricks_count(self.h, C.byref(n), C.byref(r)))
+        return int(n.value), float(r.value)
 
     # read-back
     def synchronize(self):

@@ -232,6 +232,7 @@ def test_fuse_frame_graph_replay(small_scene):
                 tsdf = fu.download_tsdf()
                 counters, occupied = fu.download_bricks()
                 assert np.array_equal(counters, want[k][1]) and np.array_equal(occupied, want[k][2])
+                assert fu.bricks_count()[0] == len(want[k][2])
                 assert bits_equal(tsdf, want[k][0]).all(), mismatch_report(f"tsdf frame {i} voxel {voxel}", tsdf, want[k][0])
             assert fu.launch_count() > l0
             capi.set_tunable("zchunk", 13)
