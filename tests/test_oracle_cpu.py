@@ -261,6 +261,53 @@ def test_oracle_matches_the_reference_shaders_run_on_cpu(O):
     assert n_occ > 20 and max(worst, worst2) < 1e-7
 
 
+@pytest.mark.parametrize("flags,depth8", [((False, True, True), False), ((True, False, True), False), ((True, True, False), False),
+                                          ((True, False, True), True)])
+def test_oracle_matches_the_reference_shaders_flag_variants(O, flags, depth8):
+    """filterTextures / useProcessedDepths / refineBoundary off, and the 8-bit sqrt-compressed depth stream (pre_depth.fs
+    `uncompress`, NetKinectArray.cpp:345-351): the oracle's chain vs the reference shaders' chain, stage by stage, each stage
+    fed the oracle's previous stage."""
+    import dataclasses
+    import ref_glsl_py as G
+    if not G.available():
+        pytest.skip("oracle/_ref/libref_glsl.so not built (needs the reference tree at build time)")
+    from rrpy import synth
+    sc = synth.make_scene(N=1, W=128, H=106, CW=160, CH=136, cv_res=(24, 24, 48), seed=5)
+    compress = None
+    if depth8:
+        d8 = synth.encode_depth8(sc.depth[0], 0.5, 4.5)
+        sc = dataclasses.replace(sc, depth=O.depth8_to_float(d8[None]))
+        compress = np.float32([[0.5, 4.5]])
+    grid = O.brick_grid(sc.bbox_min, sc.bbox_max, 0.04, 0.1)
+    cams = [O.frustum(sc.cv_xyz[0])[1]]
+    a = O.preprocess(sc, grid, cams, *flags, compress=compress)
+    # the shaders' chain from the same raw frame; then every stage again on the oracle's inputs
+    b = G.preprocess(sc, grid, cams, *flags, compress=compress)
+    assert bits_equal(a["morph"], b["morph"]).all() and np.array_equal(a["bricks"], b["bricks"])
+    assert bits_equal(a["sil"], b["sil"]).all()
+    for k in ("depth", "lab", "depth_b", "normal", "quality"):
+        _assert_stage(k, a[k], b[k], 4 * STAGE_TOL[k])
+    assert (a["sil"] > 0).sum() > 200, "the variant must keep a surface"
+
+
+def test_oracle_integration_matches_the_reference_shader_with_five_sensors(O):
+    """`uniform sampler3D[5] cv_xyz_inv`: the reference's sensor limit, running mean over five sensors in order."""
+    import ref_glsl_py as G
+    if not G.available():
+        pytest.skip("oracle/_ref/libref_glsl.so not built (needs the reference tree at build time)")
+    from rrpy import synth
+    sc = synth.make_scene(N=5, W=96, H=80, CW=128, CH=108, cv_res=(24, 24, 48), seed=21)
+    grid = O.brick_grid(sc.bbox_min, sc.bbox_max, 0.03, 0.1)
+    cams = [O.frustum(sc.cv_xyz[i])[1] for i in range(sc.N)]
+    pre = O.preprocess(sc, grid, cams)
+    inv = synth.analytic_inverse(sc, (40, 44, 40))
+    occ = O.occupied_bricks(pre["bricks"], 10)
+    want, weight = O.integrate(inv, pre, grid, 0.01, True, occ, want_weight=True)
+    got = G.integrate(inv, pre, grid, 0.01, True, occ)
+    assert len(occ) > 20 and (weight > 0).sum() > 1000
+    _assert_stage("tsdf_integration.vs, 5 sensors", got, want, 1e-5 * 0.01, max_flips=2)
+
+
 def test_oracle_against_reference_shader_goldens(O):
     """Same pin for machines without oracle/_ref: tests/golden/ref_glsl_stages.npz holds what the reference's shaders computed
     (full chain, every stage fed by the shaders' own previous stage). The oracle's own chain must stay within rounding:
