@@ -207,8 +207,7 @@ def run_ours(args):
                 fb.issue(packed=h_packed[k])
             consume_broadcast()
             fb.issue(packed=h_packed[k1])                            # next set's host->device copy + broadcast run beside this set's kernels
-            fu.fuse_frame()
-            n = fu.bricks_count()                                    # the per-frame count read, when the frame set is done
+            fu.bricks_clear(); fu.preprocess(); n = fu.bricks_update(sync=True); fu.integrate()
         elif step_host.fused:
             # one graph launch per frame set; the occupied-brick count the reference reads every frame is read when the frame
             # set is done (rr_bricks_count: a 4-byte device->host read behind a stream sync)
@@ -274,8 +273,7 @@ def run_ours(args):
     # the closing swap makes the compute stream (and so the end event) wait for the last staged copy: all K host->device
     # copies issued inside the timed region are also completed inside it
     ms_e2e = timed(step_host, args.steps, max(50, args.warmup), False, finish=(fu.swap_frames if world == 1 else None))   # >= 50 untimed steps: lets the PCIe link leave its idle state
-    e2e_path = ("call by call (rr_bricks_clear, rr_preprocess, rr_bricks_update with the count read mid-frame, rr_integrate)" if world == 1
-                else "rr_fuse_frame + rr_bricks_count behind the pipelined broadcast")
+    e2e_path = "call by call (rr_bricks_clear, rr_preprocess, rr_bricks_update with the count read mid-frame, rr_integrate)"
     e2e_other = None
     if world == 1:
         # the same end-to-end step through rr_fuse_frame + rr_bricks_count (one graph launch, count read at the end of the frame
