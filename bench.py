@@ -492,7 +492,11 @@ def cpu_baseline(scene, inv, voxel, bricks, budget_s):
         if (time.perf_counter() - t_start >= budget_s and len(times) >= 2) or len(times) >= 200:
             break
     fps = 1.0 / float(np.mean(times))
+    # SURVEY.md 8d also asks for the single-threaded figure: one whole frame set on one thread
+    tp1, ti1, _, _ = cpu_frame(scene, inv, voxel, True, 1, 1.0)
+    O.set_threads(cores)
     return {"value": round(R ** 3 * fps / 1e9, 5), "unit": "Gvoxel-updates/s", "frames_per_s": round(fps, 4), "cores": cores, "kind": "port",
+            "single_thread_frames_per_s": round(1.0 / (tp1 + ti1), 4),
             "sample": f"{len(times)} whole 4-sensor frame sets at {R}^3 ({sum(times):.1f} s of wall time on {cores} threads): per frame all 5 "
                       f"pre-process passes on every pixel ({np.mean(tps) * 1e3:.0f} ms) + brick integration of all {n_occ} occupied bricks "
                       f"({np.mean(tis) * 1e3:.0f} ms); oracle port (-O2, OpenMP), bricks mode"}
