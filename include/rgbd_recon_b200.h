@@ -35,9 +35,10 @@ typedef enum rr_status {
   RR_ERR_UNSUPPORTED = -4
 } rr_status;
 
-/* Runtime knobs of ReconIntegration (framework/reconstruction/recon_integration.cpp:30-60, kinect_client.cpp:87-93). */
+/* How a voxel is stored (rr_config.store_weight). */
 enum rr_voxel_format { RR_VOXELS_F32 = 0, RR_VOXELS_F32_WEIGHT = 1, RR_VOXELS_HALF2 = 2 };
 
+/* Runtime knobs of ReconIntegration (framework/reconstruction/recon_integration.cpp:30-60, kinect_client.cpp:87-93). */
 typedef struct rr_config {
   float limit;                    /* TSDF truncation in normalised sensor-depth units (setTsdfLimit)            */
   float voxel_size;               /* metres (setVoxelSize, :341-354)                                            */
