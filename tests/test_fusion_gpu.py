@@ -243,3 +243,4 @@ def test_fuse_frame_graph_replay(small_scene):
     finally:
         capi.set_tunable("zchunk", 13)
         fu.close()
+

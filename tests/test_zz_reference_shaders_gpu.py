@@ -1,0 +1,47 @@
+"""GPU vs the reference's own shaders, directly (no oracle in between). Runs last in the suite (file name) so that its
+looser, formulation-dependent bars can never mask a result of the bit-exact parity tests."""
+import numpy as np
+import pytest
+
+from conftest import bits_equal
+
+pytestmark = pytest.mark.gpu
+
+
+def test_kernels_against_the_reference_shaders_directly(small_scene):
+    """The CUDA path against the reference's OWN shaders run on the CPU (oracle/_ref/libref_glsl.so: glsl/pre_*.fs,
+    inc_*.glsl, tsdf_integration.vs compiled as C++, see oracle/glsl_host/), full chain on both sides, no oracle in between.
+    The shader host environment uses a different float formulation (mix() without fma, libm pow), so the bars are BASELINE's:
+    brick counters and occupied list bit-exact, silhouettes identical, normals within 2e-4 absolute (unit vectors),
+    TSDF within 2e-5 of the truncation distance over the whole chained pipeline."""
+    import oracle_py as O
+    import ref_glsl_py as G
+    if not G.available():
+        pytest.skip("oracle/_ref/libref_glsl.so not built (needs the reference tree at build time)")
+    from rrpy import capi, synth
+    sc = small_scene
+    inv = synth.analytic_inverse(sc, (50, 55, 50))
+    fu = capi.Fusion(sc.N, sc.W, sc.H, sc.CW, sc.CH)
+    capi.load_scene(fu, sc, inv)
+    fu.configure(limit=0.01, voxel_size=0.02, brick_size=0.1, min_voxels=10, use_bricks=True)
+    fu.upload_frames(sc.color, sc.depth)
+    fu.frame(sync_bricks=True)
+    got = {k: fu.download_stage(k) for k in ("morph", "depth", "lab", "depth_b", "sil", "normal", "quality")}
+    counters, occupied = fu.download_bricks()
+    tsdf = fu.download_tsdf()
+    fu.close()
+
+    grid = O.brick_grid(sc.bbox_min, sc.bbox_max, 0.02, 0.1)       # host geometry (pinned against volume_sampler.cpp)
+    cams = [O.frustum(sc.cv_xyz[i])[1] for i in range(sc.N)]
+    ref = G.preprocess(sc, grid, cams)
+    ref_occ = O.occupied_bricks(ref["bricks"], 10)
+    ref_tsdf = G.integrate(inv, ref, grid, 0.01, True, ref_occ)
+    assert np.array_equal(counters, ref["bricks"]) and np.array_equal(occupied, ref_occ) and len(ref_occ) > 50
+    assert bits_equal(got["morph"], ref["morph"]).all() and bits_equal(got["sil"], ref["sil"]).all()
+    for k, tol in dict(depth=2e-6, lab=2e-4, depth_b=2e-6, normal=2e-4, quality=4e-5).items():
+        assert ((got[k] != got[k]) == (ref[k] != ref[k])).all(), k
+        ok = np.isfinite(got[k]) & np.isfinite(ref[k])
+        assert np.abs(got[k][ok] - ref[k][ok]).max() <= tol, f"{k}: {np.abs(got[k][ok] - ref[k][ok]).max()}"
+    assert (np.isnan(tsdf) == np.isnan(ref_tsdf)).all()
+    ok = np.isfinite(tsdf) & np.isfinite(ref_tsdf)
+    assert np.abs(tsdf[ok].astype(np.float64) - ref_tsdf[ok]).max() <= 2e-5 * 0.01
