@@ -45,3 +45,37 @@ def test_kernels_against_the_reference_shaders_directly(small_scene):
     assert (np.isnan(tsdf) == np.isnan(ref_tsdf)).all()
     ok = np.isfinite(tsdf) & np.isfinite(ref_tsdf)
     assert np.abs(tsdf[ok].astype(np.float64) - ref_tsdf[ok]).max() <= 2e-5 * 0.01
+
+
+@pytest.mark.parametrize("eye,mode", [((-2.0, 1.0, 1.2), 0), ((1.6, 1.5, 2.2), 1)])
+def test_raymarch_kernel_against_the_reference_shader_directly(small_scene, eye, mode):
+    """rr_raymarch (cube-proxy march, space skipping off) against glsl/tsdf_raymarch.fs + shading.glsl run on the CPU on the
+    volume the kernels integrated: same fragments, same sample counts, window depth within 1e-5 (BASELINE: 1 mm), colours
+    within 2e-3."""
+    import oracle_py as O
+    import ref_glsl_py as G
+    if not G.available():
+        pytest.skip("oracle/_ref/libref_glsl.so not built (needs the reference tree at build time)")
+    from rrpy import capi, synth
+    sc = small_scene
+    VW, VH = 320, 180
+    inv = synth.analytic_inverse(sc, (50, 55, 50))
+    fu = capi.Fusion(sc.N, sc.W, sc.H, sc.CW, sc.CH)
+    capi.load_scene(fu, sc, inv)
+    fu.configure(limit=0.01, voxel_size=0.02, brick_size=0.1, min_voxels=10, use_bricks=True, skip_space=False)
+    fu.upload_frames(sc.color, sc.depth)
+    fu.frame(sync_bricks=True)
+    tsdf = fu.download_tsdf()
+    pre = {k: fu.download_stage(k) for k in ("depth_b", "quality", "normal")}
+    mv, pr = synth.look_at(eye, (0.0, 1.1, 0.0)), synth.perspective(50.0, VW / VH, 0.1, 10.0)
+    rgba, depth = fu.raymarch(mv, pr, VW, VH, shade_mode=mode)
+    samples = fu.download_num_samples(VW, VH)
+    fu.close()
+    want = G.raymarch(tsdf, 0.01, inv, sc, pre, mv, pr, VW, VH, mode)
+    hit = depth < 1.0
+    assert np.array_equal(hit, want["hit"] > 0) and hit.sum() > 1000
+    assert np.array_equal(samples, want["samples"])
+    assert np.abs(depth - want["depth"]).max() <= 1e-5
+    assert (np.isnan(rgba) == np.isnan(want["rgba"])).all()
+    ok = np.isfinite(rgba) & np.isfinite(want["rgba"])
+    assert np.abs(rgba[ok] - want["rgba"][ok]).max() <= 2e-3
