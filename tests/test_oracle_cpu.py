@@ -391,6 +391,30 @@ def test_oracle_space_skipping_matches_the_reference_shader_on_rasterised_peels(
         _assert_raymarch(got, want["rgba"], want["depth"], want["samples"], want["hit"], f"skipSpace eye {eye}", np.asarray(pr), sample_flips=0.01)
 
 
+def test_reference_cube_proxy_faces_are_front_facing_outward():
+    """ref_glsl_py.depth_peels takes a brick's entry face as gl_FrontFacing and its exit face as back-facing (bricks.fs keeps the
+    nearest BACK face in .b). That holds iff the reference's unit-cube triangle strip (unit_cube.cpp:21-30, 53-62) is wound
+    counter-clockwise seen from outside; checked on the reference's own numbers where the tree is present."""
+    import re
+    path = "/root/reference/framework/rendering/unit_cube.cpp"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present")
+    src = open(path).read()
+    verts = re.search(r"std::vector<float> vertices\{(.*?)\};", src, re.S).group(1)
+    V = np.array([float(x.rstrip("f")) for x in re.findall(r"[-0-9.]+f", verts)], np.float64).reshape(-1, 3)
+    body = src[src.index("void UnitCube::drawInstanced"):]
+    idx = [int(x) for x in re.search(r"indices \{(.*?)\};", body, re.S).group(1).replace("\n", " ").split(",")]
+    assert V.shape == (8, 3) and len(idx) == 14
+    faces = 0
+    for i in range(len(idx) - 2):
+        a, b, c = (idx[i], idx[i + 1], idx[i + 2]) if i % 2 == 0 else (idx[i + 1], idx[i], idx[i + 2])   # strip winding rule
+        n = np.cross(V[b] - V[a], V[c] - V[a])
+        assert np.abs(n).sum() > 0, "degenerate strip triangle"
+        assert np.dot(n, (V[a] + V[b] + V[c]) / 3.0 - 0.5) > 0, "triangle wound clockwise seen from outside"
+        faces += 1
+    assert faces == 12
+
+
 def test_oracle_raymarch_against_reference_shader_golden(O):
     """tests/golden/ref_glsl_raymarch.npz: the reference's raymarch shader on the oracle's volume of the golden scene."""
     from rrpy import synth
