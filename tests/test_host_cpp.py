@@ -41,6 +41,15 @@ def test_host_file_and_wire_formats(tmp_path):
     assert r.returncode == 0 and "host_selftest ok" in r.stdout, r.stderr
 
 
+def test_natural_neighbour_interpolator_properties():
+    """SURVEY.md row a13: kinect::NaturalNeighbourInterpolator without CGAL (host C++). Sibson coordinates are checked through
+    what defines them: an affine field is reproduced to float rounding on scattered samples AND on a regular grid (every
+    Delaunay cell degenerate), the coordinates reproduce the query position, a cell centre gets its eight corners with weight
+    1/8, a sample returns itself, outside the hull there are no coordinates, and the volumes match a Monte Carlo count."""
+    r = subprocess.run([os.path.join(BIN, "nni_selftest")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "nni_selftest ok" in r.stdout, r.stderr[-2000:]
+
+
 def test_programs_are_built_and_report_usage():
     for name in ("calib_inverter", "fusion_playback", "host_selftest"):
         exe = os.path.join(BIN, name)
