@@ -96,6 +96,16 @@ struct uvec2 {
 };
 inline uvec2 operator+(const uvec2& a, const uvec2& b) { return uvec2(a.x + b.x, a.y + b.y); }
 
+// An unsized buffer array (SSBO member `T name[]`). Out-of-range accesses are undefined in GLSL and do happen on this path
+// (index_3d + ivec3(-1) at the brick-grid border, bricks.gs:28; a filtered point that left the bbox, inc_bricks.glsl:52,57):
+// reads return 0, writes are dropped - the robust-buffer-access behaviour.
+template <typename T> struct ssbo_array {
+  T* p = nullptr;
+  size_t n = 0;
+  T sink = T();
+  T& operator[](size_t i) { if (i < n) return p[i]; sink = T(); return sink; }
+};
+
 // T[5] as a value (GLSL arrays are first-class: returned from functions, assigned)
 template <typename T> struct arr5 {
   T v[5];
@@ -166,6 +176,7 @@ inline ivec3 operator+(const ivec3& a, const ivec3& b) { return ivec3(a.x + b.x,
 inline ivec3 operator-(const ivec3& a, const ivec3& b) { return ivec3(a.x - b.x, a.y - b.y, a.z - b.z); }
 inline uvec3 operator-(const uvec3& a, uint s) { return uvec3(a.x - s, a.y - s, a.z - s); }
 inline uvec3 operator+(const uvec3& a, const uvec3& b) { return uvec3(a.x + b.x, a.y + b.y, a.z + b.z); }
+inline uvec3 operator+(const uvec3& a, const ivec3& b) { return uvec3(a.x + (uint)b.x, a.y + (uint)b.y, a.z + (uint)b.z); }   // int -> uint, wraps
 
 // ---- built-in functions (GLSL 4.30 section 8) --------------------------------------------------------------------------
 inline float min(float x, float y) { return y < x ? y : x; }

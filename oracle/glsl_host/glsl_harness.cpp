@@ -10,6 +10,7 @@
 //   tsdf_integration: ReconIntegration::integrate (framework/reconstruction/recon_integration.cpp:243-270), one vertex
 //     per voxel centre (framework/rendering/volume_sampler.cpp:33-48).
 // Built only where the reference tree is present; output oracle/_ref/libref_glsl.so (git-ignored).
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -42,6 +43,23 @@ struct S_tsdf_raymarch {
   struct { float near, far, diff; } gl_DepthRange = {0.0f, 1.0f, 1.0f};       // glDepthRange defaults
   bool discarded = false;
 #include "tsdf_raymarch.inc"
+};
+struct S_bricks_vs {
+  int gl_InstanceID = 0;
+  vec4 gl_Position;
+#include "bricks_vs.inc"
+};
+struct S_bricks_gs {
+  struct { vec4 gl_Position; } gl_in[3];
+  vec4 gl_Position;
+  std::vector<vec4> emitted;
+  void EmitVertex() { emitted.push_back(gl_Position); }
+#include "bricks_gs.inc"
+};
+struct S_bricks_fs {
+  vec4 gl_FragCoord;
+  bool gl_FrontFacing = true;
+#include "bricks_fs.inc"
 };
 struct S_framebuffer_transfer {
 #include "framebuffer_transfer.inc"
@@ -144,7 +162,6 @@ void rg_pre_boundary(const float* depth_rg, const float* lab, int W, int H, int 
 
 void rg_pre_normal(const float* depth_b, int W, int H, const float* cv_xyz, int CX, int CY, int CZ, const float* bbox_min,
                    float brick_size, const uint32_t* brick_res, uint32_t num_bricks, uint32_t* bricks, float* out_normal) {
-  (void)num_bricks;
   S_pre_normal proto{};
   proto.layer = 0u;
   proto.kinect_depths = tex2d(depth_b, W, H, 2, false);
@@ -155,8 +172,7 @@ void rg_pre_normal(const float* depth_b, int W, int H, const float* cv_xyz, int 
   proto.bbox_max = vec3(0.f);
   proto.brick_size = brick_size;
   proto.resolution = uvec3(brick_res[0], brick_res[1], brick_res[2]);
-  proto.bricks = bricks;
-  proto.bricks_occupied = nullptr;
+  proto.bricks.p = bricks; proto.bricks.n = num_bricks;
 #pragma omp parallel for schedule(dynamic, 4)
   for (int y = 0; y < H; ++y)
     for (int x = 0; x < W; ++x) {
@@ -212,7 +228,6 @@ void rg_integrate(int N, const float* inv, const int32_t* inv_res, const float* 
   proto.limit = limit;
   proto.num_kinects = (uint)N;
   proto.res_tsdf = uvec3(res[0], res[1], res[2]);
-  proto.bricks = nullptr; proto.bricks_occupied = nullptr;
   auto run = [&](int x0, int x1, int y0, int y1, int z0, int z1) {
 #pragma omp parallel for schedule(dynamic, 1)
     for (int z = z0; z < z1; ++z)
@@ -396,6 +411,93 @@ void rg_fill_colors(const float* rgba, const float* depth, int W, int H, float* 
       if (s.gl_FragDepth < 1.0f) { o[0] = s.out_FragColor.x; o[1] = s.out_FragColor.y; o[2] = s.out_FragColor.z; o[3] = s.out_FragColor.w; }
       else { o[0] = in[0]; o[1] = in[1]; o[2] = in[2]; o[3] = in[3]; }   // GL_LESS against the cleared depth buffer
     }
+}
+
+// ReconIntegration::drawDepthLimits (recon_integration.cpp:409-429): UnitCube::drawInstanced (one triangle strip per occupied
+// brick, the reference's vertices and strip order passed in) through bricks.vs -> bricks.gs -> a rasteriser -> bricks.fs, GL_MIN
+// blending over the clear colour (1, 0, 1, 0) (:144), face culling off. The rasteriser is the OpenGL 4.4 pipeline in fp64:
+// clipping against the near and far planes (section 13.5), perspective divide and viewport transform (13.6), fragments where
+// the pixel centre lies inside the projected polygon (14.6.1), window z interpolated affinely, facing from the sign of the
+// window-space area (14.6.1, CCW = front). out_peels [vh][vw][4].
+void rg_depth_peels(const float* modelview, const float* projection, const float* bbox_min, float brick_size, const uint32_t* brick_res,
+                    uint32_t* bricks, uint32_t num_bricks, uint32_t* occupied, uint32_t n_occ, const float* cube_vertices,
+                    const uint8_t* strip, int strip_len, int vw, int vh, float* out_peels) {
+  for (size_t i = 0; i < (size_t)vw * vh; ++i) { out_peels[i * 4] = 1.f; out_peels[i * 4 + 1] = 0.f; out_peels[i * 4 + 2] = 1.f; out_peels[i * 4 + 3] = 0.f; }
+  S_bricks_vs vs{};
+  vs.gl_ModelViewMatrix = mat4(modelview); vs.gl_ProjectionMatrix = mat4(projection);
+  vs.bbox_min = vec3(bbox_min[0], bbox_min[1], bbox_min[2]); vs.bbox_max = vec3(0.f);
+  vs.brick_size = brick_size; vs.resolution = uvec3(brick_res[0], brick_res[1], brick_res[2]);
+  vs.bricks.p = bricks; vs.bricks.n = num_bricks; vs.bricks_occupied.p = occupied; vs.bricks_occupied.n = n_occ;
+  S_bricks_gs gs_proto{};
+  gs_proto.bbox_min = vs.bbox_min; gs_proto.bbox_max = vs.bbox_max; gs_proto.brick_size = brick_size; gs_proto.resolution = vs.resolution;
+  gs_proto.bricks.p = bricks; gs_proto.bricks.n = num_bricks; gs_proto.bricks_occupied.p = occupied; gs_proto.bricks_occupied.n = n_occ;
+  struct H4 { double x, y, z, w; };
+  auto lerp4 = [](const H4& a, const H4& b, double t) { return H4{a.x + (b.x - a.x) * t, a.y + (b.y - a.y) * t, a.z + (b.z - a.z) * t, a.w + (b.w - a.w) * t}; };
+  for (uint32_t inst = 0; inst < n_occ; ++inst) {
+    vec4 pos[8]; vec3 gpos[8]; uint gid[8];
+    for (int v = 0; v < 8; ++v) {
+      S_bricks_vs s(vs);
+      s.gl_InstanceID = (int)inst;
+      s.in_Position = vec3(cube_vertices[v * 3], cube_vertices[v * 3 + 1], cube_vertices[v * 3 + 2]);
+      s.main();
+      pos[v] = s.gl_Position; gpos[v] = s.geo_Position; gid[v] = s.geo_Id;
+    }
+    for (int t = 0; t + 2 < strip_len; ++t) {
+      // GL_TRIANGLE_STRIP: odd triangles swap their first two vertices so that every triangle keeps the strip's winding
+      const int i0 = (t & 1) ? strip[t + 1] : strip[t], i1 = (t & 1) ? strip[t] : strip[t + 1], i2 = strip[t + 2];
+      if (i0 == i1 || i1 == i2 || i0 == i2) continue;
+      S_bricks_gs g(gs_proto);
+      const int idx[3] = {i0, i1, i2};
+      for (int k = 0; k < 3; ++k) { g.geo_Position[k] = gpos[idx[k]]; g.geo_Id[k] = gid[idx[k]]; g.gl_in[k].gl_Position = pos[idx[k]]; }
+      g.main();
+      if (g.emitted.size() < 3) continue;
+      std::vector<H4> poly;
+      for (int k = 0; k < 3; ++k) poly.push_back(H4{g.emitted[k].x, g.emitted[k].y, g.emitted[k].z, g.emitted[k].w});
+      for (int plane = 0; plane < 2; ++plane) {                      // near: z >= -w, far: z <= w
+        std::vector<H4> outp;
+        auto dist = [&](const H4& p) { return plane == 0 ? p.z + p.w : p.w - p.z; };
+        for (size_t a = 0; a < poly.size(); ++a) {
+          const H4& A = poly[a]; const H4& B = poly[(a + 1) % poly.size()];
+          const double da = dist(A), db = dist(B);
+          if (da >= 0) outp.push_back(A);
+          if ((da >= 0) != (db >= 0)) outp.push_back(lerp4(A, B, da / (da - db)));
+        }
+        poly.swap(outp);
+        if (poly.size() < 3) break;
+      }
+      if (poly.size() < 3) continue;
+      std::vector<double> wx(poly.size()), wy(poly.size()), wz(poly.size());
+      for (size_t a = 0; a < poly.size(); ++a) {
+        wx[a] = (poly[a].x / poly[a].w + 1.0) * 0.5 * vw; wy[a] = (poly[a].y / poly[a].w + 1.0) * 0.5 * vh; wz[a] = (poly[a].z / poly[a].w + 1.0) * 0.5;
+      }
+      double area2 = 0.0;
+      for (size_t a = 0; a < poly.size(); ++a) { const size_t b = (a + 1) % poly.size(); area2 += wx[a] * wy[b] - wx[b] * wy[a]; }
+      if (area2 == 0.0) continue;
+      const bool front = area2 > 0.0;
+      for (size_t f = 1; f + 1 < poly.size(); ++f) {                 // fan of the clipped polygon
+        const double x0 = wx[0], y0 = wy[0], x1 = wx[f], y1 = wy[f], x2 = wx[f + 1], y2 = wy[f + 1];
+        const double den = (x1 - x0) * (y2 - y0) - (x2 - x0) * (y1 - y0);
+        if (den == 0.0) continue;
+        const int px0 = std::max(0, (int)std::floor(std::min({x0, x1, x2}) - 0.5)), px1 = std::min(vw - 1, (int)std::ceil(std::max({x0, x1, x2}) - 0.5));
+        const int py0 = std::max(0, (int)std::floor(std::min({y0, y1, y2}) - 0.5)), py1 = std::min(vh - 1, (int)std::ceil(std::max({y0, y1, y2}) - 0.5));
+        for (int py = py0; py <= py1; ++py)
+          for (int px = px0; px <= px1; ++px) {
+            const double cx = px + 0.5, cy = py + 0.5;
+            const double b1 = ((cx - x0) * (y2 - y0) - (x2 - x0) * (cy - y0)) / den;
+            const double b2 = ((x1 - x0) * (cy - y0) - (cx - x0) * (y1 - y0)) / den;
+            const double b0 = 1.0 - b1 - b2;
+            if (b0 < 0.0 || b1 < 0.0 || b2 < 0.0) continue;
+            S_bricks_fs fs{};
+            fs.gl_FragCoord = vec4((float)cx, (float)cy, (float)(b0 * wz[0] + b1 * wz[f] + b2 * wz[f + 1]), 1.0f);
+            fs.gl_FrontFacing = front;
+            fs.main();
+            float* o = out_peels + ((size_t)py * vw + px) * 4;       // glBlendEquation(GL_MIN)
+            o[0] = std::min(o[0], fs.out_Color.x); o[1] = std::min(o[1], fs.out_Color.y);
+            o[2] = std::min(o[2], fs.out_Color.z); o[3] = std::min(o[3], fs.out_Color.w);
+          }
+      }
+    }
+  }
 }
 
 }  // extern "C"

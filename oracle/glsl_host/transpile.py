@@ -13,7 +13,9 @@ cannot parse:
   * `layout(...)`, `noperspective`, and the storage qualifiers `uniform` / `in` / `out` / `buffer` of global
     declarations are removed (globals become struct members); interface blocks lose their braces (their members are
     global names in GLSL too); parameter qualifiers `in` / `const in` are removed;
-  * GLSL array declarators `T[n] name` become `T name[n]`, an unsized SSBO array `T[] name` becomes `T* name`;
+  * GLSL array declarators `T[n] name` become `T name[n]`, an unsized SSBO array `T[] name` becomes `ssbo_array<T> name`
+    (bounds-checked: the shaders index it out of range at the brick-grid border), a geometry shader's `in T name[]` becomes
+    `T name[3]`;
   * swizzles `.xy .rg .xyz .rgb .xx .yz` become calls (`.xy()` ...), the only multi-component swizzles these shaders
     use, always as r-values;
   * global `const int` become `static constexpr int` (they size arrays);
@@ -67,6 +69,9 @@ def transpile(lines):
             continue
         code = l
         code = re.sub(r"layout\s*\([^)]*\)\s*", "", code)
+        if re.match(r"^\s*(in|out)\s*;\s*$", code):             # geometry shader: layout(triangles) in; / layout(...) out;
+            out.append("// " + l.strip())
+            continue
         if depth == 0 and not in_block:
             if re.match(r"\s*(uniform|buffer)\s+\w+\s*\{\s*$", code):
                 in_block = True
@@ -97,7 +102,8 @@ def transpile(lines):
         code = re.sub(r"\b(\w+)\[5\]\s*\(", r"arr5<\1>(", code)
         # array declarators: T[n] name; -> T name[n];   T[] name; -> T* name;
         code = re.sub(r"\b(\w+)\[(\d+)\]\s+(\w+)\s*;", r"\1 \3[\2];", code)
-        code = re.sub(r"\b(\w+)\[\]\s+(\w+)\s*;", r"\1* \2;", code)
+        code = re.sub(r"\b(\w+)\[\]\s+(\w+)\s*;", r"ssbo_array<\1> \2;", code)
+        code = re.sub(r"\b(\w+)\s+(\w+)\[\]\s*;", r"\1 \2[3];", code)      # geometry-shader inputs: one entry per triangle vertex
         # r-value swizzles
         code = re.sub(r"\.(xyz|rgb|xy|rg|xx|yz)\b(?!\s*\()", r".\1()", code)
         if not in_block:
@@ -110,7 +116,8 @@ def main():
     glsl_dir, out_dir = sys.argv[1], sys.argv[2]
     os.makedirs(out_dir, exist_ok=True)
     for name in sys.argv[3:]:
-        stem = os.path.splitext(name)[0]
+        name, _, stem = name.partition(":")                       # "bricks.vs:bricks_vs" names the output; default = the file's stem
+        stem = stem or os.path.splitext(name)[0]
         body = transpile(load(glsl_dir, name, set()))
         with open(os.path.join(out_dir, stem + ".inc"), "w") as f:
             f.write(f"// GENERATED from the reference's glsl/{name} by oracle/glsl_host/transpile.py - do not commit\n")

@@ -207,3 +207,37 @@ def depth_peels(scene, grid, occupied, modelview, projection, width, height, lim
             peels[..., 1] = np.where(b, np.minimum(peels[..., 1], -z1), peels[..., 1])
             peels[..., 2] = np.where(b, np.minimum(peels[..., 2], z1), peels[..., 2])
     return peels.astype(np.float32)
+
+
+def reference_cube_strip(path="/root/reference/framework/rendering/unit_cube.cpp"):
+    """The reference's unit-cube vertices [8][3] and the triangle strip UnitCube::drawInstanced draws (unit_cube.cpp:21-30,
+    53-62), parsed from its source where the tree is present; None otherwise."""
+    import re
+    if not os.path.exists(path):
+        return None
+    src = open(path).read()
+    verts = re.search(r"std::vector<float> vertices\{(.*?)\};", src, re.S).group(1)
+    V = np.array([float(x.rstrip("f")) for x in re.findall(r"[-0-9.]+f", verts)], np.float32).reshape(-1, 3)
+    body = src[src.index("void UnitCube::drawInstanced"):]
+    idx = np.array([int(x) for x in re.search(r"indices \{(.*?)\};", body, re.S).group(1).replace("\n", " ").split(",")], np.uint8)
+    return V, idx
+
+
+def depth_peels_rasterised(scene, grid, counters, occupied, modelview, projection, width, height, cube=None):
+    """ReconIntegration::drawDepthLimits with the reference's bricks.vs / bricks.gs / bricks.fs and a rasteriser
+    (glsl_harness.cpp::rg_depth_peels). cube = (vertices [8][3], strip indices); default: parsed from the reference tree."""
+    L = lib()
+    if not hasattr(L, "_dp"):
+        L.rg_depth_peels.argtypes = [f32p, f32p, f32p, C.c_float, u32p, u32p, C.c_uint32, u32p, C.c_uint32, f32p, u8p, C.c_int,
+                                     C.c_int, C.c_int, f32p]
+        L._dp = True
+    cube = cube or reference_cube_strip()
+    assert cube is not None, "the unit-cube strip comes from the reference tree"
+    V, idx = cube
+    out = np.zeros((height, width, 4), np.float32)
+    occ = np.ascontiguousarray(occupied, np.uint32) if len(occupied) else np.zeros(1, np.uint32)
+    L.rg_depth_peels(np.ascontiguousarray(modelview, np.float32).reshape(16), np.ascontiguousarray(projection, np.float32).reshape(16),
+                     np.ascontiguousarray(scene.bbox_min, np.float32), np.float32(grid["brick_size"]), grid["res_bricks"],
+                     np.ascontiguousarray(counters, np.uint32), len(counters), occ, len(occupied), np.ascontiguousarray(V, np.float32),
+                     np.ascontiguousarray(idx, np.uint8), len(idx), int(width), int(height), out)
+    return out

@@ -3,8 +3,8 @@
  * bench.py's cpu_baseline / --impl reference legs ONLY. The reference ships no tests; the
  * restatement is pinned against reference code compiled into oracle/_ref: C++ sources (libref_harness.so, see ro_math.h) and
  * the pre-processing / integration / raymarch / colour-fill SHADERS run on the CPU (libref_glsl.so, oracle/glsl_host/). The
- * space-skipping hull of ro_raymarch.cpp (a rasteriser in the reference) is checked through the shader's skipSpace branch on
- * depth peels stated by ref_glsl_py.depth_peels. */
+ * space-skipping hull of ro_raymarch.cpp is checked through the shader's skipSpace branch on depth peels produced by the
+ * reference's bricks.vs/gs/fs and a rasteriser (glsl_harness.cpp::rg_depth_peels). */
 #ifndef RR_ORACLE_H
 #define RR_ORACLE_H
 #include <stddef.h>

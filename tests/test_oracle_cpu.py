@@ -371,6 +371,29 @@ def test_oracle_raymarch_matches_the_reference_shader_run_on_cpu(O, small_scene,
             _assert_raymarch(got, want["rgba"], want["depth"], want["samples"], want["hit"], f"eye {eye} mode {mode}", np.asarray(pr))
 
 
+def test_depth_peels_from_the_reference_brick_shaders_and_a_rasteriser(O, small_scene, small_frame):
+    """drawDepthLimits with the reference's bricks.vs / bricks.gs / bricks.fs and a rasteriser (glsl_harness.cpp::rg_depth_peels;
+    the cube strip is read from unit_cube.cpp) against the ray-cast statement ref_glsl_py.depth_peels: same coverage, nearest and
+    farthest face depth to rounding; the nearest BACK face differs where bricks.gs dropped faces between occupied bricks, which
+    never changes getStartPos' `r >= b` decision."""
+    import ref_glsl_py as G
+    if not G.available() or G.reference_cube_strip() is None:
+        pytest.skip("needs oracle/_ref/libref_glsl.so and the reference tree (unit-cube strip)")
+    from rrpy import synth
+    sc = small_scene
+    grid, pre, occ = (small_frame[k] for k in ("grid", "pre", "occ"))
+    VW, VH = 240, 135
+    for eye in ((1.6, 1.5, 2.2), (-2.0, 1.0, 1.2), (0.7, 1.3, 0.75)):
+        mv, pr = synth.look_at(eye, (0.0, 1.1, 0.0)), synth.perspective(50.0, VW / VH, 0.1, 10.0)
+        cast = G.depth_peels(sc, grid, occ, mv, pr, VW, VH, 0.01)
+        rast = G.depth_peels_rasterised(sc, grid, pre["bricks"], occ, mv, pr, VW, VH)
+        cov = cast[..., 0] < 1.0
+        assert np.array_equal(cov, rast[..., 0] < 1.0) and cov.sum() > 1000
+        assert np.abs(cast[..., 0] - rast[..., 0]).max() <= 5e-7 and np.abs(cast[..., 1] - rast[..., 1]).max() <= 5e-7
+        assert (rast[..., 2] >= cast[..., 2] - 5e-7).all(), "dropping internal faces can only move the nearest back face away"
+        assert np.array_equal(cast[..., 0] >= cast[..., 2], rast[..., 0] >= rast[..., 2]), "getStartPos' front-face-culled decision"
+
+
 def test_oracle_space_skipping_matches_the_reference_shader_on_rasterised_peels(O, small_scene, small_frame):
     """The skipSpace branch of tsdf_raymarch.fs (getStartPos, screenToVol) fed the depth peels drawDepthLimits' rasteriser
     would leave (ref_glsl_py.depth_peels: pixel-centre ray / brick-cube intersections in window space, float64) against the
@@ -385,7 +408,9 @@ def test_oracle_space_skipping_matches_the_reference_shader_on_rasterised_peels(
     VW, VH = 240, 135
     for eye in ((1.6, 1.5, 2.2), (-2.0, 1.0, 1.2), (0.7, 1.3, 0.75)):   # the last one sits inside the volume
         mv, pr = synth.look_at(eye, (0.0, 1.1, 0.0)), synth.perspective(50.0, VW / VH, 0.1, 10.0)
-        peels = G.depth_peels(sc, grid, occ, mv, pr, VW, VH, 0.01)
+        # the reference's own brick shaders + rasteriser where its cube strip can be read, the ray-cast statement otherwise
+        peels = (G.depth_peels_rasterised(sc, grid, pre["bricks"], occ, mv, pr, VW, VH) if G.reference_cube_strip() is not None
+                 else G.depth_peels(sc, grid, occ, mv, pr, VW, VH, 0.01))
         want = G.raymarch(tsdf, 0.01, inv, sc, pre, mv, pr, VW, VH, 1, depth_peels=peels)
         got = O.raymarch(tsdf, 0.01, inv, sc, pre, grid, occ, mv, pr, VW, VH, 1, skip_space=True)
         _assert_raymarch(got, want["rgba"], want["depth"], want["samples"], want["hit"], f"skipSpace eye {eye}", np.asarray(pr), sample_flips=0.01)

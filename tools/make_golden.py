@@ -90,8 +90,8 @@ def golden_glsl_raymarch():
         r = G.raymarch(tsdf, 0.01, inv, sc, pre, mv, pr, RM_VIEW["w"], RM_VIEW["h"], mode)
         out[f"rgba{mode}"] = r["rgba"]
         out["depth"], out["samples"], out["hit"] = r["depth"], r["samples"], r["hit"]
-    # the skipSpace branch (getStartPos / screenToVol) on depth peels as drawDepthLimits' rasteriser leaves them
-    peels = G.depth_peels(sc, grid, occ, mv, pr, RM_VIEW["w"], RM_VIEW["h"], 0.01)
+    # the skipSpace branch (getStartPos / screenToVol) on the depth peels of drawDepthLimits (the reference's brick shaders)
+    peels = G.depth_peels_rasterised(sc, grid, pre["bricks"], occ, mv, pr, RM_VIEW["w"], RM_VIEW["h"])    # bricks.vs/gs/fs + rasteriser
     r = G.raymarch(tsdf, 0.01, inv, sc, pre, mv, pr, RM_VIEW["w"], RM_VIEW["h"], 1, depth_peels=peels)
     out.update(skip_rgba=r["rgba"], skip_depth=r["depth"], skip_samples=r["samples"], skip_hit=r["hit"])
     np.savez_compressed(os.path.join(OUT, "ref_glsl_raymarch.npz"), voxel=np.float32(voxel), tsdf_sha=np.array(sha(tsdf)), **out)
