@@ -308,6 +308,34 @@ def test_oracle_integration_matches_the_reference_shader_with_five_sensors(O):
     _assert_stage("tsdf_integration.vs, 5 sensors", got, want, 1e-5 * 0.01, max_flips=2)
 
 
+def test_empty_frame_set_oracle_and_reference_shaders(O):
+    """No depth returns at all: no silhouette, no brick marks, an empty occupied list, a volume that is -limit everywhere
+    (bricks mode only clears), and a raymarch without a single sample - in the oracle and in the reference's shaders."""
+    import dataclasses
+    import ref_glsl_py as G
+    from rrpy import synth
+    sc = synth.make_scene(N=2, W=96, H=80, CW=128, CH=108, cv_res=(24, 24, 48), seed=3)
+    sc = dataclasses.replace(sc, depth=np.zeros_like(sc.depth))
+    grid = O.brick_grid(sc.bbox_min, sc.bbox_max, 0.04, 0.1)
+    cams = [O.frustum(sc.cv_xyz[i])[1] for i in range(sc.N)]
+    pre = O.preprocess(sc, grid, cams)
+    assert not pre["sil"].any() and not pre["bricks"].any() and not pre["quality"].any() and not pre["normal"].any()
+    occ = O.occupied_bricks(pre["bricks"], 10)
+    assert len(occ) == 0
+    inv = synth.analytic_inverse(sc, (30, 33, 30))
+    tsdf = O.integrate(inv, pre, grid, 0.01, True, occ)
+    assert (tsdf == np.float32(-0.01)).all()
+    mv, pr = synth.look_at((1.6, 1.5, 2.2), (0.0, 1.1, 0.0)), synth.perspective(50.0, 16 / 9, 0.1, 10.0)
+    rm = O.raymarch(tsdf, 0.01, inv, sc, pre, grid, occ, mv, pr, 96, 54, 1, skip_space=True)
+    assert (rm["depth"] == 1.0).all() and not rm["samples"].any() and not rm["rgba"].any()
+    if G.available():
+        ref = G.preprocess(sc, grid, cams)
+        for k in ("morph", "depth", "lab", "depth_b", "sil", "normal", "quality"):
+            _assert_stage(k, pre[k], ref[k], 4 * STAGE_TOL.get(k, 0.0))
+        assert not ref["bricks"].any()
+        assert bits_equal(G.integrate(inv, ref, grid, 0.01, True, occ), tsdf).all()
+
+
 def test_oracle_against_reference_shader_goldens(O):
     """Same pin for machines without oracle/_ref: tests/golden/ref_glsl_stages.npz holds what the reference's shaders computed
     (full chain, every stage fed by the shaders' own previous stage). The oracle's own chain must stay within rounding:

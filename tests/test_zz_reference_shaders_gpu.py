@@ -79,3 +79,38 @@ def test_raymarch_kernel_against_the_reference_shader_directly(small_scene, eye,
     assert (np.isnan(rgba) == np.isnan(want["rgba"])).all()
     ok = np.isfinite(rgba) & np.isfinite(want["rgba"])
     assert np.abs(rgba[ok] - want["rgba"][ok]).max() <= 2e-3
+
+
+def test_empty_frame_set_on_the_gpu():
+    """Edge case: a frame set without a single depth return. No brick marks, an empty occupied list, a volume that is -limit
+    everywhere, a raymarch without samples - bit-identical to the oracle (whose empty-frame behaviour is checked against the
+    reference's shaders in tests/test_oracle_cpu.py::test_empty_frame_set_oracle_and_reference_shaders)."""
+    import dataclasses
+    import oracle_py as O
+    from rrpy import capi, synth
+    sc = synth.make_scene(N=2, W=96, H=80, CW=128, CH=108, cv_res=(24, 24, 48), seed=3)
+    sc = dataclasses.replace(sc, depth=np.zeros_like(sc.depth))
+    inv = synth.analytic_inverse(sc, (30, 33, 30))
+    fu = capi.Fusion(sc.N, sc.W, sc.H, sc.CW, sc.CH)
+    capi.load_scene(fu, sc, inv)
+    fu.configure(limit=0.01, voxel_size=0.04, brick_size=0.1, min_voxels=10, use_bricks=True, skip_space=True)
+    fu.upload_frames(sc.color, sc.depth)
+    n_occ, ratio = fu.frame(sync_bricks=True)
+    got = {k: fu.download_stage(k) for k in ("morph", "depth", "lab", "depth_b", "sil", "normal", "quality")}
+    counters, occupied = fu.download_bricks()
+    tsdf = fu.download_tsdf()
+    mv, pr = synth.look_at((1.6, 1.5, 2.2), (0.0, 1.1, 0.0)), synth.perspective(50.0, 16 / 9, 0.1, 10.0)
+    rgba, depth = fu.raymarch(mv, pr, 96, 54, shade_mode=1)
+    samples = fu.download_num_samples(96, 54)
+    fu.fuse_frame(); fu.fuse_frame()                      # the graph path on an empty occupied list
+    assert fu.bricks_count()[0] == 0
+    tsdf2 = fu.download_tsdf()
+    fu.close()
+    grid = O.brick_grid(sc.bbox_min, sc.bbox_max, 0.04, 0.1)
+    cams = [O.frustum(sc.cv_xyz[i])[1] for i in range(sc.N)]
+    pre = O.preprocess(sc, grid, cams)
+    assert n_occ == 0 and ratio == 0.0 and len(occupied) == 0 and not counters.any()
+    for k in got:
+        assert bits_equal(got[k], pre[k]).all(), k
+    assert (tsdf == np.float32(-0.01)).all() and (tsdf2 == np.float32(-0.01)).all()
+    assert (depth == 1.0).all() and not samples.any() and not rgba.any()
