@@ -433,6 +433,9 @@ def run_ours(args):
                 "bound": (f"host->device link: {cb + db} B/step at the measured {link_gbs:.1f} GB/s caps e2e at {link_gbs * 1e9 / (cb + db):.0f} frames/s" if link_gbs else None),
                 "dxt1_stream": e2e_dxt1},
         "gpu_launches": int(gpu_launches), "host_enqueue_ms_per_step": round(host_enqueue_ms, 5),
+        # beside voxel-updates/s, the evaluations actually performed (this rank's slab for N > 1)
+        "occupied_voxel_updates_per_s": round(float(n_occ_vox if bricks else R ** 3 * slab_frac) * frames_s, 1),
+        "voxel_sensor_evaluations_per_s": round(float(n_occ_vox if bricks else R ** 3 * slab_frac) * N_SENSORS * frames_s, 1),
         "stages_ms": {"1preprocess": round(pre_ms / max(1, pre_n), 5), "2integrate": round(int_avg_ms, 5),
                       "how": f"CUDA-event stage timers over {stage_steps} further steps of the same loop with direct launches "
                              f"({ms_stage_pass / stage_steps:.5f} ms/step); `value` is timed with the frame replayed as one CUDA graph"},
