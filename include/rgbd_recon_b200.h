@@ -205,9 +205,18 @@ int rr_get_stage_stats(rr_ctx* ctx, const char* name, float* total_ms, uint32_t*
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 uint64_t rr_launch_count(const rr_ctx* ctx);
 /* Launch-shape knob of the integrator, process-wide (no reference counterpart; the reference's draw-call structure is
- * fixed). Names: "fused", "zchunk", "fill_rows", "fill_warps", "ctas", "threads", "chunk", "brick_grid".
+ * fixed). Names: "fused", "zchunk", "fill_rows", "fill_warps", "ctas", "threads", "chunk", "brick_grid",
+ * "ldg256", "graph", "staged", "stage_zchunk", "stage_ychunk", "stage_tile", "stage_fwarps", "stage_fill_rows".
  * Results never depend on these. Returns RR_ERR_INVALID for an unknown name. */
 int rr_set_tunable(const char* name, int value);
+/* Which integrator the bricks mode of this context runs and with what geometry (no reference counterpart; diagnostics for
+ * bench.py and the tests). Waits for the stream. out[16]:
+ *  [0] 1 = the TMA-staged kernel is selected (0: the direct kernels), [1] tile edge (pixels), [2..4] staged inverse-volume
+ *  box (coarse texels), [5] y-chunk, [6] z-chunk (voxels per work item), [7] y-chunks per brick, [8] z-chunks per brick,
+ *  [9] bricks left to the direct kernel (footprint larger than the tile), [10] shared memory per CTA (bytes),
+ *  [11] consumer warps, [12] fill warps, [13] device-side consistency flags (0 = healthy: bit 0 box overflow, bit 1 barrier
+ *  time-out), [14..15] reserved. */
+int rr_integrator_info(rr_ctx* ctx, uint32_t* out);
 /* Library/ABI version. */
 int rr_version(void);
 

@@ -121,12 +121,15 @@ int rr_create(rr_ctx** out, int device, int num_sensors, int depth_w, int depth_
   if (rc == RR_OK) rc = dev_alloc(c, &c->d_normal, px, "normal");
   if (rc == RR_OK) rc = dev_alloc(c, &c->d_quality, px, "quality");
   if (rc == RR_OK) rc = dev_alloc(c, &c->d_gather, (size_t)c->N * (c->W + 1) * (c->H + 1) * 2, "gather");
+  c->pair_pitch = (c->W + 3) & ~1;
+  if (rc == RR_OK) rc = dev_alloc(c, &c->d_pairs, (size_t)c->N * (c->H + 2) * c->pair_pitch, "pair image");
   if (rc == RR_OK) rc = dev_alloc(c, &c->d_flags, 4, "flags");
   if (rc == RR_OK) rc = dev_alloc(c, &c->d_num_occ, 1, "num_occ");
   if (rc == RR_OK) rc = dev_alloc(c, &c->d_work, 4, "work counters");
   if (rc == RR_OK) rc = check(c, cudaMallocHost((void**)&c->h_num_occ, sizeof(uint32_t)), "pinned count");
   if (rc == RR_OK) {
     cudaMemsetAsync(c->d_flags, 0, 4 * sizeof(uint32_t), c->stream);
+    cudaMemsetAsync(c->d_pairs, 0, (size_t)c->N * (c->H + 2) * c->pair_pitch * sizeof(float2), c->stream);
     cudaMemsetAsync(c->d_num_occ, 0, sizeof(uint32_t), c->stream);
     for (int b = 0; b < 2; ++b) {
       cudaMemsetAsync(c->d_color_slot[b], 0, (size_t)c->N * c->CW * c->CH * 3, c->stream);
@@ -153,6 +156,8 @@ void rr_destroy(rr_ctx* c) {
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   cudaFree(c->d_inv); cudaFree(c->d_morph); cudaFree(c->d_depth);
   cudaFree(c->d_lab); cudaFree(c->d_depth_b); cudaFree(c->d_sil); cudaFree(c->d_normal); cudaFree(c->d_quality);
+  staged_release(c);
+  cudaFree(c->d_pairs);
   cudaFree(c->d_gather); cudaFree(c->d_flags); cudaFree(c->d_ranges); cudaFree(c->d_counters); cudaFree(c->d_occupied);
   cudaFree(c->d_num_occ); cudaFree(c->d_work); cudaFree(c->d_ztab); cudaFree(c->d_rowmask); cudaFree(c->d_rowany); cudaFree(c->d_cand_y); cudaFree(c->d_cand_z); cudaFree(c->d_near_occ); cudaFree(c->d_occ_mask); cudaFree(c->d_pos); cudaFree(c->d_step); cudaFree(c->d_tsdf); cudaFree(c->d_weight);
   cudaFree(c->d_rgba); cudaFree(c->d_zbuf); cudaFree(c->d_nsamples);
@@ -242,6 +247,7 @@ int rr_calib_upload_inv(rr_ctx* c, int sensor, const float* inv, const uint32_t 
   RR_TRY(check(c, cudaMemcpyAsync(c->d_inv + n * sensor, inv, n * sizeof(float4), cudaMemcpyHostToDevice, c->stream), "inv upload"));
   RR_TRY(check(c, cudaStreamSynchronize(c->stream), "inv upload sync"));
   c->have_inv[sensor] = true;
+  c->sti.dirty = true;
   return RR_OK;
 }
 
@@ -328,6 +334,7 @@ int rr_configure(rr_ctx* c, const rr_config* cfg) {
   }
   c->cfg = *cfg;
   c->configured = true;
+  c->sti.dirty = true;
   return RR_OK;
 }
 
@@ -518,6 +525,7 @@ int rr_fuse_frame(rr_ctx* c, int filter_textures, int use_processed_depth, int r
   RR_TRY(require_ready(c, true));
   RR_SET_DEVICE(c);
   const int f = filter_textures ? 1 : 0, p = use_processed_depth ? 1 : 0, r = refine_boundary ? 1 : 0;
+  RR_TRY(staged_prepare(c));       // table rebuilds synchronise: never inside a capture
   // capture needs a launch sequence without allocations or event timers: the z table exists (first frame ran direct)
   // and stage timing is off
   const bool ready = rr::tunables().graph != 0 && !c->graphs_broken && c->timing == 0 && c->d_ztab &&
@@ -669,7 +677,7 @@ int rr_calib_invert(rr_ctx* c, int sensor, const uint32_t out_res[3], float* hos
   if (rc == RR_OK && host_out) rc = check(c, cudaMemcpyAsync(host_out, d_out, n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream), "inverse download");
   if (rc == RR_OK) rc = check(c, cudaStreamSynchronize(c->stream), "invert sync");
   if (own) cudaFree(d_out);
-  if (rc == RR_OK && keep) c->have_inv[sensor] = true;
+  if (rc == RR_OK && keep) { c->have_inv[sensor] = true; c->sti.dirty = true; }
   return rc;
 }
 
@@ -815,6 +823,25 @@ int rr_get_stage_stats(rr_ctx* c, const char* name, float* total_ms, uint32_t* c
 
 uint64_t rr_launch_count(const rr_ctx* c) { return c ? c->launches : 0; }
 
+int rr_integrator_info(rr_ctx* c, uint32_t* out) {
+  if (!c || !out) return RR_ERR_INVALID;
+  RR_SET_DEVICE(c);
+  RR_TRY(staged_prepare(c));
+  const auto& s = c->sti;
+  std::memset(out, 0, 16 * sizeof(uint32_t));
+  out[0] = staged_selected(c) ? 1u : 0u;
+  out[1] = (uint32_t)s.T; out[2] = (uint32_t)s.BX; out[3] = (uint32_t)s.BY; out[4] = (uint32_t)s.BZ;
+  out[5] = (uint32_t)s.cy; out[6] = (uint32_t)s.cz; out[7] = (uint32_t)s.n_yc; out[8] = (uint32_t)s.n_zc;
+  out[9] = s.n_legacy; out[10] = s.smem_bytes; out[11] = (uint32_t)s.cwarps; out[12] = (uint32_t)s.fwarps;
+  if (s.d_err) {
+    uint32_t e[4] = {0, 0, 0, 0};
+    RR_TRY(check(c, cudaStreamSynchronize(c->stream), "integrator info sync"));
+    RR_TRY(check(c, cudaMemcpy(e, s.d_err, sizeof(e), cudaMemcpyDeviceToHost), "integrator flags"));
+    out[13] = (e[0] ? 1u : 0u) | (e[1] ? 2u : 0u);
+  }
+  return RR_OK;
+}
+
 int rr_set_tunable(const char* name, int value) {
   if (!name) return RR_ERR_INVALID;
   Tunables& t = tunables();
@@ -829,6 +856,13 @@ int rr_set_tunable(const char* name, int value) {
   else if (n == "brick_grid") t.brick_grid = value;
   else if (n == "ldg256") t.ldg256 = value;
   else if (n == "graph") t.graph = value;
+  else if (n == "staged") t.staged = value;
+  else if (n == "stage_zchunk") t.stage_zchunk = value;
+  else if (n == "stage_ychunk") t.stage_ychunk = value;
+  else if (n == "stage_tile") t.stage_tile = value;
+  else if (n == "stage_fwarps") t.stage_fwarps = value;
+  else if (n == "stage_fill_rows") t.stage_fill_rows = value;
+  else if (n == "stage_debug") t.stage_debug = value;
   else return RR_ERR_INVALID;
   ++t.generation;              // captured frame graphs bake the launch shapes in: stale keys never match again
   return RR_OK;

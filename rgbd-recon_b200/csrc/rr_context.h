@@ -10,9 +10,14 @@
 //              taps (silhouette in the sign bit) = one 32-byte sector per voxel-sensor lookup in the integrator
 //   bricks     uint32 counters[nb], occupied[nb], count; int32 ranges[nb][6]; uint8 near_occupied[nb], occ_mask[nb];
 //              uint32 rowmask[nbz][nby][ceil(X/32)], uint8 rowany[nbz][nby], int16 cand_y[Y][2], cand_z[Z][2]
+//   pairs      float2[N][H+2][pitch]: (depth_b.x, quality with the silhouette in the sign bit) per pixel, one replicated
+//              border pixel on every side (CLAMP_TO_EDGE) - the image the staged integrator tiles into shared memory by TMA
+//   footprints uint32[bricks * y-chunks * z-chunks][N]: origin of the pair-image tile each work item of the staged
+//              integrator needs per sensor (fixed by calibration + brick grid, built once by k_footprints)
 //   volume     tsdf float[Z][Y][X] (+ weight float[Z][Y][X] when rr_config.store_weight)
 #pragma once
 
+#include <cuda.h>            // CUtensorMap (types only; the encoder is fetched with cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -98,6 +103,8 @@ struct rr_ctx {
   float4* d_normal = nullptr;
   float* d_quality = nullptr;
   float4* d_gather = nullptr;
+  float2* d_pairs = nullptr;       // [N][H+2][pair_pitch]
+  int pair_pitch = 0;              // W+2 rounded up to even (TMA strides are multiples of 16 bytes)
   uint32_t* d_flags = nullptr;     // [0] pack-encoding violation counter
 
   // settings + bricks + volume
@@ -128,6 +135,23 @@ struct rr_ctx {
   struct FrameGraph { uint64_t key; cudaGraphExec_t exec; uint64_t launches; };
   std::vector<FrameGraph> frame_graphs;
   bool graphs_broken = false;      // a capture failed once: stay on direct launches
+  // staged (TMA) integrator, rr_integrate_staged.cu. `dirty` is set by everything its tables depend on (inverse volumes,
+  // volume / brick grid, tunables); they are rebuilt lazily by the next integrate or pre-process call.
+  struct StagedIntegrator {
+    bool dirty = true;             // tables below do not match the current calibration / configuration
+    bool ok = false;               // the configuration fits the staged kernel
+    unsigned generation = 0;       // key of the tunables the tables were built for (staged_key)
+    int cy = 0, cz = 0, n_yc = 0, n_zc = 0;   // work item = brick x y-chunk x z-chunk (voxels per chunk, chunks per brick)
+    int BX = 0, BY = 0, BZ = 0;    // inverse-volume box staged per item (coarse texels)
+    int T = 0;                     // pair-image tile edge staged per item and sensor (pixels, even)
+    int cwarps = 0, fwarps = 0;    // consumer / fill warps per CTA
+    uint32_t inv_bytes = 0, tile_bytes = 0, inv_span = 0, tile_span = 0, stage_bytes = 0, smem_bytes = 0;
+    uint32_t* d_fp = nullptr;      // [items][N]: tile origin tx0 | ty0 << 16
+    uint8_t* d_legacy = nullptr;   // [num_bricks]: 1 = a footprint of this brick exceeds the tile, left to k_integrate_bricks
+    uint32_t n_legacy = 0;         // bricks flagged in d_legacy
+    uint32_t* d_err = nullptr;     // [4] device-side consistency flags (must stay 0)
+    CUtensorMap map_inv, map_pairs;
+  } sti;
   uint32_t* h_num_occ = nullptr;   // pinned
   float* d_tsdf = nullptr;
   float* d_weight = nullptr;
@@ -161,6 +185,13 @@ struct Tunables {
   int brick_grid = 6;   // grid multiple of the unfused brick kernel
   int ldg256 = 1;       // gather texels with one 256-bit load (0: two 128-bit loads)
   int graph = 1;        // rr_fuse_frame replays a captured CUDA graph (0: direct launches)
+  int staged = 1;       // bricks mode uses the TMA-staged integrator when the configuration fits (0: direct kernels)
+  int stage_zchunk = 9; // staged integrator: voxels of a brick's z extent per work item
+  int stage_ychunk = 0; // ... and of its y extent (0: chosen so that an item's columns fill the consumer threads)
+  int stage_tile = 0;   // pair-image tile edge in pixels (0: chosen from the footprint statistics and the smem budget)
+  int stage_fwarps = 2; // fill warps per CTA
+  int stage_fill_rows = 16;   // voxel rows per fill item
+  int stage_debug = 0;  // measurement only, results are WRONG: bit 0 skips the clear stream, bit 1 the brick evaluation
   unsigned generation = 0;   // bumped by every rr_set_tunable (invalidates captured graphs)
 };
 Tunables& tunables();
@@ -182,6 +213,9 @@ int launch_composite(rr_ctx* c, const float4* d_rec, int n_parts);
 int launch_fill_colors(rr_ctx* c);
 int launch_unpack_frames(rr_ctx* c, int slot);
 int launch_calib_invert(rr_ctx* c, int sensor, const uint32_t out_res[3], float4* d_out);
+int staged_prepare(rr_ctx* c);        // (re)builds the staged integrator's tables when dirty; RR_OK also when it declines
+void staged_release(rr_ctx* c);
+bool staged_selected(const rr_ctx* c); // after staged_prepare: the next bricks-mode integrate runs the staged kernel
 void drop_frame_graphs(rr_ctx* c);
 
 // host geometry (rr_host_geom.cpp)
@@ -192,6 +226,8 @@ uint32_t host_divide_box(const float bmin[3], const float bmax[3], float brick_s
                          uint32_t res_bricks[3], std::vector<int32_t>* ranges);
 
 }  // namespace rr
+
+#define RR_TRY_RC(expr) do { int rc__ = (expr); if (rc__ != RR_OK) return rc__; } while (0)
 
 #define RR_LAUNCH_CHECK(c, what)                                   \
   do {                                                             \

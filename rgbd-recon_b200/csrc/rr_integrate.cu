@@ -8,10 +8,7 @@
 // coarse plane per sensor; consecutive lanes are consecutive x, so the R32F stores are 128-byte coalesced rows.
 // Silhouette (bilinear), depth (nearest) and quality (bilinear) come from ONE 32-byte gather texel per voxel-sensor
 // (see k_pack_gather). HBM-bound integer/float gather work: no tensor-core path applies.
-#include "rr_context.h"
-#include "rr_math.cuh"
-
-#include <cuda_fp16.h>
+#include "rr_integrate.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -19,23 +16,6 @@
 #include <cstring>
 
 namespace rr {
-
-struct IntegrateParams {
-  const float4* inv;      // [N][IZ][IY][IX]
-  const float4* gather;   // [N][H+1][W+1][2]
-  const float4* ztab;     // [Z]: per fine z the coarse plane pair and weight of the z filter tap: (k0, k1, g, 1-g)
-  float* tsdf;
-  float* weight;
-  const int32_t* ranges;  // [num_bricks][6]
-  const uint32_t* occupied;
-  const uint32_t* num_occupied;
-  int IX, IY, IZ, W, H, X, Y, Z;
-  float fW, fH, exmax, eymax;   // (float)W, (float)H, (float)(W-1), (float)(H-1)
-  int z_begin, z_end;     // slab
-  int z_chunk;
-  float limit;
-  int wide_loads;         // tunable ldg256: gather texels with one 256-bit load
-};
 
 // lin_coord of every fine z against the inverse volume's z axis, evaluated once per (Z, IZ) pair with the same
 // float operations march_column used to repeat per voxel (identical results, ~25 instructions saved per voxel).
@@ -66,7 +46,7 @@ struct Tap {
 // One (x, y) column, z in [zb, ze). All index arithmetic is 32-bit (sizes are validated on the host).
 // z (hence the coarse plane pair) is uniform across a warp wherever the callers keep a warp inside one brick / one
 // dense tile, so the plane-advance branches below do not diverge.
-template <int N, int MODE>
+template <int N, int MODE, bool PAIRS = false>
 __device__ __forceinline__ void march_column(const IntegrateParams& p, int x, int y, int zb, int ze) {
   const float stepX = 1.0f / (float)p.X, stepY = 1.0f / (float)p.Y;
   const float px = ((float)x + 0.5f) * stepX, py = ((float)y + 0.5f) * stepY;
@@ -85,11 +65,7 @@ __device__ __forceinline__ void march_column(const IntegrateParams& p, int x, in
   auto plane = [&](int s, int k) -> float3 {
     const float4* base = p.inv + (unsigned)(s * p.IZ + k) * plane_sz;
     const float4 p00 = __ldg(base + o00), p10 = __ldg(base + o10), p01 = __ldg(base + o01), p11 = __ldg(base + o11);
-    float3 r;
-    r.x = fmaf(b, fmaf(a, p11.x, oma * p01.x), omb * fmaf(a, p10.x, oma * p00.x));
-    r.y = fmaf(b, fmaf(a, p11.y, oma * p01.y), omb * fmaf(a, p10.y, oma * p00.y));
-    r.z = fmaf(b, fmaf(a, p11.z, oma * p01.z), omb * fmaf(a, p10.z, oma * p00.z));
-    return r;
+    return plane_reduce(p00, p10, p01, p11, a, oma, b, omb);
   };
 
   unsigned o = (unsigned)((zb * p.Y + y) * p.X + x);
@@ -123,49 +99,23 @@ __device__ __forceinline__ void march_column(const IntegrateParams& p, int x, in
     // z filter tap, bilinear footprint (silhouette, quality) at (u, v) and the gather loads for sensor s
     auto fetch = [&](int s) -> Tap {
       Tap t;
-      const float u = fmaf(g, B[s].x, omg * A[s].x), v = fmaf(g, B[s].y, omg * A[s].y);
-      t.d = fmaf(g, B[s].z, omg * A[s].z);
-      // lower-left texel floor(u*W - 0.5), weights (wa, wb)
-      const float uu = u * p.fW - 0.5f, vv = v * p.fH - 0.5f;
-      const float fu = floorf(uu), fv = floorf(vv);
-      t.wa = uu - fu; t.wb = vv - fv;
-      // gather-texel index = clamp(footprint, -1, W-1) + 1; fmaxf/fminf drop a NaN operand, so NaN -> entry 0
-      const int ex = (int)fminf(fmaxf(fu, -1.0f), p.exmax) + 1, ey = (int)fminf(fmaxf(fv, -1.0f), p.eymax) + 1;
+      int ex, ey;
+      tap_coords(A[s], B[s], g, omg, p.fW, p.fH, p.exmax, p.eymax, t.wa, t.wb, t.d, ex, ey);
+      ex += 1; ey += 1;
+      if (PAIRS) {
+        // the pair image the staged integrator tiles (same taps, 8 bytes per pixel): footprint (ex, ey) = pixels ex, ex+1 of rows ey, ey+1
+        const float2* q = p.pairs + ((unsigned)(s * (p.H + 2) + ey) * (unsigned)p.pair_pitch + (unsigned)ex);
+        const float2 t00 = __ldg(q), t10 = __ldg(q + 1), t01 = __ldg(q + p.pair_pitch), t11 = __ldg(q + p.pair_pitch + 1);
+        t.lo = make_float4(t00.x, t10.x, t01.x, t11.x);
+        t.hi = make_float4(t00.y, t10.y, t01.y, t11.y);
+        return t;
+      }
       const float4* g4 = p.gather + ((unsigned)s * gstride + ((unsigned)ey * grow + (unsigned)ex) * 2u);
       if (p.wide_loads) ldg_texel(g4, t.lo, t.hi); else { t.lo = __ldg(g4); t.hi = __ldg(g4 + 1); }
       return t;
     };
-    // tsdf_integration.vs:30-55 for one sensor
     auto fuse = [&](const Tap& t) {
-      // silhouette < 1 ? The four taps are exactly 0 or 1 (sign bits of hi). lerp(1,1,t) == 1 and lerp(0,0,t) == 0
-      // exactly for every finite t, so uniform footprints need no arithmetic; NaN weights compare false either way.
-      const uint32_t bx = __float_as_uint(t.hi.x), by = __float_as_uint(t.hi.y), bz = __float_as_uint(t.hi.z), bw = __float_as_uint(t.hi.w);
-      const uint32_t all1 = (bx & by & bz & bw) >> 31, any1 = (bx | by | bz | bw) >> 31;
-      bool sil_lt1;
-      if (all1) {
-        sil_lt1 = false;
-      } else if (!any1) {
-        sil_lt1 = (t.wa == t.wa) && (t.wb == t.wb);
-      } else {
-        const float s00 = (int)bx < 0 ? 1.0f : 0.0f, s10 = (int)by < 0 ? 1.0f : 0.0f;
-        const float s01 = (int)bz < 0 ? 1.0f : 0.0f, s11 = (int)bw < 0 ? 1.0f : 0.0f;
-        sil_lt1 = lerpf(lerpf(s00, s10, t.wa), lerpf(s01, s11, t.wa), t.wb) < 1.0f;
-      }
-      if (sil_lt1 && weighted_tsd >= limit) { weighted_tsd = neg_limit; return; }
-      // NEAREST depth tap = upper tap of the footprint iff the bilinear weight is >= 0.5 (floor(t) == floor(t-0.5)+1);
-      // where the subtraction t-0.5 can round (t < 0.5) both taps are the same clamped texel.
-      const bool selx = t.wa >= 0.5f, sely = t.wb >= 0.5f;
-      const float depth = sely ? (selx ? t.lo.w : t.lo.z) : (selx ? t.lo.y : t.lo.x);
-      const float sdist = t.d - depth;
-      if (sdist <= neg_limit) {
-        weighted_tsd = neg_limit;
-      } else if (sdist >= limit) {
-      } else {
-        const float q00 = fabsf(t.hi.x), q10 = fabsf(t.hi.y), q01 = fabsf(t.hi.z), q11 = fabsf(t.hi.w);
-        const float w = lerpf(lerpf(q00, q10, t.wa), lerpf(q01, q11, t.wa), t.wb);
-        weighted_tsd = (weighted_tsd * total_weight + w * sdist) / (total_weight + w);
-        total_weight += w;
-      }
+      fuse_tap(t.wa, t.wb, t.d, t.lo.x, t.lo.y, t.lo.z, t.lo.w, t.hi.x, t.hi.y, t.hi.z, t.hi.w, limit, neg_limit, weighted_tsd, total_weight);
     };
     // two sensors' gathers are in flight before the first decision chain runs
 #pragma unroll
@@ -175,14 +125,7 @@ __device__ __forceinline__ void march_column(const IntegrateParams& p, int x, in
       fuse(t1);
     }
     if (N & 1) { const Tap t = fetch(N - 1); fuse(t); }
-    if (MODE == 2) {
-      // half2 voxel: (tsdf, weight) rounded to nearest-even half, one 4-byte store
-      const __half2 h = __floats2half2_rn(weighted_tsd, total_weight);
-      reinterpret_cast<uint32_t*>(p.tsdf)[o] = *reinterpret_cast<const uint32_t*>(&h);
-    } else {
-      p.tsdf[o] = weighted_tsd;
-      if (MODE == 1) p.weight[o] = total_weight;
-    }
+    store_voxel<MODE>(p, o, weighted_tsd, total_weight);
   }
 }
 
@@ -201,8 +144,8 @@ __global__ void __launch_bounds__(256) k_integrate_dense(const __grid_constant__
 // Bricks may overlap or leave one-voxel gaps (float rounding in divideBox/containedVoxels): overlapping voxels are
 // written twice with the same value, gaps keep the cleared -limit.
 #define BRICK_MAX_THREADS 320
-template <int N, int MODE, int MINB>
-__global__ void __launch_bounds__(BRICK_MAX_THREADS, MINB) k_integrate_bricks(const __grid_constant__ IntegrateParams p, int max_cols, int max_nz, int BRICK_ZCHUNK) {
+template <int N, int MODE, int MINB, bool PAIRS>
+__global__ void __launch_bounds__(BRICK_MAX_THREADS, MINB) k_integrate_bricks(const __grid_constant__ IntegrateParams p, int max_cols, int max_nz, int BRICK_ZCHUNK, const uint8_t* __restrict__ only) {
   const unsigned n_occ = *p.num_occupied;
   const unsigned col_blocks = ((unsigned)max_cols + blockDim.x - 1u) / blockDim.x;
   const unsigned z_blocks = (unsigned)(max_nz + BRICK_ZCHUNK - 1) / BRICK_ZCHUNK;
@@ -211,14 +154,16 @@ __global__ void __launch_bounds__(BRICK_MAX_THREADS, MINB) k_integrate_bricks(co
   for (unsigned w = blockIdx.x; w < items; w += gridDim.x) {
     const unsigned b = w / per_brick, r = w - b * per_brick;
     const unsigned zc = r / col_blocks, cc = r - zc * col_blocks;
-    const int32_t* rg = p.ranges + (size_t)p.occupied[b] * 6;
+    const uint32_t brick = p.occupied[b];
+    if (only && !only[brick]) continue;         // `only`: the bricks the staged integrator left to this kernel
+    const int32_t* rg = p.ranges + (size_t)brick * 6;
     const int x0 = rg[0], nx = rg[1] - rg[0], y0 = rg[2], ny = rg[3] - rg[2];
     const int zb = max(rg[4] + (int)zc * BRICK_ZCHUNK, p.z_begin);
     const int ze = min(min(rg[4] + (int)(zc + 1) * BRICK_ZCHUNK, rg[5]), p.z_end);
     const int ci = (int)(cc * blockDim.x + threadIdx.x);
     if (zb >= ze || ci >= nx * ny) continue;
     const int cy = ci / nx, cx = ci - cy * nx;
-    march_column<N, MODE>(p, x0 + cx, y0 + cy, zb, ze);
+    march_column<N, MODE, PAIRS>(p, x0 + cx, y0 + cy, zb, ze);
   }
 }
 
@@ -232,95 +177,6 @@ __global__ void __launch_bounds__(BRICK_MAX_THREADS, MINB) k_integrate_bricks(co
 //   compute item = 32 consecutive columns of the flattened (occupied brick, column) space x one z-chunk.
 // The first `fill_warps` warps of a CTA start on fill items, the others on compute items; a warp that runs out of its
 // own kind helps with the other, so the kernel ends when both counters are exhausted.
-struct FusedParams {
-  IntegrateParams ip;
-  const uint32_t* rowmask; const uint8_t* rowany; const int16_t* cand_y; const int16_t* cand_z;
-  int mask_words, nby;
-  uint32_t* work;              // [0] compute items handed out, [1] fill items handed out
-  int max_cols, max_nz, zchunk, n_zchunks;
-  int fill_rows; uint32_t fill_items; uint32_t row_begin, row_end;   // fill_rows <= 32
-  int fill_warps;
-  int chunk;                   // compute items a CTA draws from the global counter at a time
-  float fill_value;
-};
-
-// One fill item: rows [row0, row1), at most 32. Lane r classifies row row0 + r (which brick rows cover it, does any of
-// them hold an occupied brick); rows without occupied bricks are streamed with 16-byte stores, the others consult the
-// row bitmask per 4-voxel group.
-template <bool WEIGHT>
-__device__ __forceinline__ void fill_rows(const FusedParams& p, uint32_t row0, uint32_t row1, int lane) {
-  const int X = p.ip.X, Y = p.ip.Y;
-  const float4 v4 = make_float4(p.fill_value, p.fill_value, p.fill_value, p.fill_value);
-  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  const bool vec = (X & 3) == 0;
-  int br0 = -1, br1 = -1, br2 = -1, br3 = -1;
-  bool any = false;
-  if (row0 + (uint32_t)lane < row1) {
-    const uint32_t row = row0 + (uint32_t)lane;
-    const int z = (int)(row / (uint32_t)Y), y = (int)(row - (uint32_t)z * (uint32_t)Y);
-    const int cy0 = p.cand_y[2 * y], cy1 = p.cand_y[2 * y + 1], cz0 = p.cand_z[2 * z], cz1 = p.cand_z[2 * z + 1];
-    br0 = (cy0 >= 0 && cz0 >= 0) ? cz0 * p.nby + cy0 : -1;
-    br1 = (cy1 >= 0 && cz0 >= 0) ? cz0 * p.nby + cy1 : -1;
-    br2 = (cy0 >= 0 && cz1 >= 0) ? cz1 * p.nby + cy0 : -1;
-    br3 = (cy1 >= 0 && cz1 >= 0) ? cz1 * p.nby + cy1 : -1;
-    any = (br0 >= 0 && p.rowany[br0]) || (br1 >= 0 && p.rowany[br1]) || (br2 >= 0 && p.rowany[br2]) || (br3 >= 0 && p.rowany[br3]);
-  }
-  const uint32_t anymask = __ballot_sync(0xffffffffu, any);
-  const int nrows = (int)(row1 - row0);
-  for (int r = 0; r < nrows; ++r) {
-    float* trow = p.ip.tsdf + (size_t)(row0 + (uint32_t)r) * X;
-    float* wrow = WEIGHT ? p.ip.weight + (size_t)(row0 + (uint32_t)r) * X : nullptr;
-    if (!((anymask >> r) & 1u)) {
-      if (vec) {
-        for (int x4 = lane; x4 * 4 < X; x4 += 32) {
-          __stcs(reinterpret_cast<float4*>(trow) + x4, v4);
-          if (WEIGHT) __stcs(reinterpret_cast<float4*>(wrow) + x4, z4);
-        }
-      } else {
-        for (int x = lane; x < X; x += 32) { trow[x] = p.fill_value; if (WEIGHT) wrow[x] = 0.0f; }
-      }
-      continue;
-    }
-    const int b0 = __shfl_sync(0xffffffffu, br0, r), b1 = __shfl_sync(0xffffffffu, br1, r);
-    const int b2 = __shfl_sync(0xffffffffu, br2, r), b3 = __shfl_sync(0xffffffffu, br3, r);
-    for (int chunk = 0; chunk * 1024 < X; ++chunk) {
-      uint32_t comb = 0;
-      const int w = chunk * 32 + lane;
-      if (w < p.mask_words) {
-        if (b0 >= 0) comb |= __ldg(p.rowmask + (size_t)b0 * p.mask_words + w);
-        if (b1 >= 0) comb |= __ldg(p.rowmask + (size_t)b1 * p.mask_words + w);
-        if (b2 >= 0) comb |= __ldg(p.rowmask + (size_t)b2 * p.mask_words + w);
-        if (b3 >= 0) comb |= __ldg(p.rowmask + (size_t)b3 * p.mask_words + w);
-      }
-      const int xbase = chunk * 1024;
-      if (vec) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t word = __shfl_sync(0xffffffffu, comb, j * 4 + (lane >> 3));
-          const int x = xbase + (j * 32 + lane) * 4;
-          if (x >= X) continue;
-          const uint32_t nib = (word >> ((lane & 7) * 4)) & 15u;
-          if (nib == 0) {
-            __stcs(reinterpret_cast<float4*>(trow + x), v4);
-            if (WEIGHT) __stcs(reinterpret_cast<float4*>(wrow + x), z4);
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (!((nib >> e) & 1u)) { trow[x + e] = p.fill_value; if (WEIGHT) wrow[x + e] = 0.0f; }
-          }
-        }
-      } else {
-        for (int i = 0; i < 32; ++i) {
-          const uint32_t word = __shfl_sync(0xffffffffu, comb, i);
-          const int x = xbase + i * 32 + lane;
-          if (x >= X) continue;
-          if (!((word >> lane) & 1u)) { trow[x] = p.fill_value; if (WEIGHT) wrow[x] = 0.0f; }
-        }
-      }
-    }
-  }
-}
-
 // Compute items are handed out to a CTA in chunks of `chunk` consecutive items (one global atomic per chunk) and to
 // its warps one at a time from a shared counter, so the warps of a CTA work on neighbouring column blocks of the same
 // brick at the same time: their inverse-volume corners and gather texels hit the SM's L1 instead of L2.
@@ -390,18 +246,22 @@ __global__ void __launch_bounds__(THREADS, 2) k_integrate_fused(const __grid_con
 }
 
 // glClearTexImage(-limit) (recon_integration.cpp:250-251): 16-byte streaming stores over the slab.
+// A slab may start at any voxel (odd plane sizes): scalar stores up to the first 16-byte boundary, vectors after it.
 __global__ void __launch_bounds__(256) k_fill(float* __restrict__ dst, size_t n, float value) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t n4 = n / 4;
-  float4* d4 = reinterpret_cast<float4*>(dst);
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t head = min(n, (size_t)((4u - (unsigned)((reinterpret_cast<uintptr_t>(dst) >> 2) & 3u)) & 3u));
+  if (i < head) dst[i] = value;
+  float* body = dst + head;
+  const size_t nb = n - head, n4 = nb / 4;
+  float4* d4 = reinterpret_cast<float4*>(body);
   const float4 v = make_float4(value, value, value, value);
   for (size_t j = i; j < n4; j += stride) __stcs(d4 + j, v);
-  for (size_t j = n4 * 4 + i; j < n; j += stride) dst[j] = value;
+  for (size_t j = n4 * 4 + i; j < nb; j += stride) body[j] = value;
 }
 
 // The cleared voxel as the 4 bytes the fill stores write: -limit (R32F), or half2(-limit, 0) for half2 voxels.
-static float cleared_voxel(int mode, float limit) {
+float cleared_voxel(int mode, float limit) {
   if (mode != 2) return -limit;
   const __half2 h = __floats2half2_rn(-limit, 0.0f);
   float f;
@@ -424,9 +284,77 @@ Tunables& tunables() {
     v.brick_grid = env("RR_BRICK_GRID", v.brick_grid);
     v.ldg256 = env("RR_LDG256", v.ldg256);
     v.graph = env("RR_GRAPH", v.graph);
+    v.staged = env("RR_STAGED", v.staged);
+    v.stage_zchunk = env("RR_STAGE_ZCHUNK", v.stage_zchunk);
+    v.stage_ychunk = env("RR_STAGE_YCHUNK", v.stage_ychunk);
+    v.stage_tile = env("RR_STAGE_TILE", v.stage_tile);
+    v.stage_fwarps = env("RR_STAGE_FWARPS", v.stage_fwarps);
+    v.stage_fill_rows = env("RR_STAGE_FILL_ROWS", v.stage_fill_rows);
     return v;
   }();
   return t;
+}
+
+void setup_fill(const rr_ctx* c, const IntegrateParams& p, int mode, int fill_rows, FusedParams& f) {
+  f.ip = p;
+  f.rowmask = c->d_rowmask; f.rowany = c->d_rowany; f.cand_y = c->d_cand_y; f.cand_z = c->d_cand_z;
+  f.mask_words = c->mask_words; f.nby = (int)c->bricks.res[1];
+  f.work = c->d_work;
+  f.fill_rows = std::min(32, std::max(1, fill_rows));
+  f.row_begin = (uint32_t)p.z_begin * (uint32_t)p.Y; f.row_end = (uint32_t)p.z_end * (uint32_t)p.Y;
+  f.fill_items = (f.row_end - f.row_begin + (uint32_t)f.fill_rows - 1u) / (uint32_t)f.fill_rows;
+  f.fill_value = cleared_voxel(mode, p.limit);
+}
+
+static void brick_extents(const rr_ctx* c, int& max_cols, int& max_nz) {
+  max_cols = max_nz = 0;
+  for (size_t i = 0; i + 5 < c->h_ranges.size(); i += 6) {
+    max_cols = std::max(max_cols, (c->h_ranges[i + 1] - c->h_ranges[i]) * (c->h_ranges[i + 3] - c->h_ranges[i + 2]));
+    max_nz = std::max(max_nz, c->h_ranges[i + 5] - c->h_ranges[i + 4]);
+  }
+}
+
+// k_integrate_bricks over the occupied bricks (`only` != nullptr: just those flagged in the per-brick mask)
+template <int N>
+static int launch_bricks_n(rr_ctx* c, const IntegrateParams& p, int mode, const uint8_t* only) {
+  int max_cols, max_nz;
+  brick_extents(c, max_cols, max_nz);
+  if (max_cols == 0 || max_nz == 0) return RR_OK;
+  // block size: the multiple of 32 (128..320) that wastes the fewest lanes on a brick's column count
+  int threads = 256;
+  double best = 1e9;
+  for (int t = 128; t <= BRICK_MAX_THREADS; t += 32) {
+    const double waste = double((max_cols + t - 1) / t * t) / double(max_cols);
+    if (waste < best - 1e-9 || (waste < best + 1e-9 && t > threads)) { best = waste; threads = t; }
+  }
+  const int zchunk = 9;
+  const dim3 grd(148 * std::max(1, tunables().brick_grid), 1, 1);
+  // the masked launch serves the staged integrator, whose frames carry the pair image instead of the gather texels
+  if (only) {
+    if (mode == 1) k_integrate_bricks<N, 1, 2, true><<<grd, threads, 0, c->stream>>>(p, max_cols, max_nz, zchunk, only);
+    else if (mode == 2) k_integrate_bricks<N, 2, 2, true><<<grd, threads, 0, c->stream>>>(p, max_cols, max_nz, zchunk, only);
+    else k_integrate_bricks<N, 0, 2, true><<<grd, threads, 0, c->stream>>>(p, max_cols, max_nz, zchunk, only);
+  } else {
+    if (mode == 1) k_integrate_bricks<N, 1, 2, false><<<grd, threads, 0, c->stream>>>(p, max_cols, max_nz, zchunk, only);
+    else if (mode == 2) k_integrate_bricks<N, 2, 2, false><<<grd, threads, 0, c->stream>>>(p, max_cols, max_nz, zchunk, only);
+    else k_integrate_bricks<N, 0, 2, false><<<grd, threads, 0, c->stream>>>(p, max_cols, max_nz, zchunk, only);
+  }
+  RR_LAUNCH_CHECK(c, "k_integrate_bricks");
+  return RR_OK;
+}
+
+int launch_bricks_masked(rr_ctx* c, const IntegrateParams& p, int mode, const uint8_t* only) {
+  switch (c->N) {
+    case 1: return launch_bricks_n<1>(c, p, mode, only);
+    case 2: return launch_bricks_n<2>(c, p, mode, only);
+    case 3: return launch_bricks_n<3>(c, p, mode, only);
+    case 4: return launch_bricks_n<4>(c, p, mode, only);
+    case 5: return launch_bricks_n<5>(c, p, mode, only);
+    case 6: return launch_bricks_n<6>(c, p, mode, only);
+    case 7: return launch_bricks_n<7>(c, p, mode, only);
+    case 8: return launch_bricks_n<8>(c, p, mode, only);
+  }
+  return fail(c, RR_ERR_UNSUPPORTED, "integrate: 1..8 sensors supported");
 }
 
 template <int N>
@@ -434,28 +362,19 @@ static int launch_n(rr_ctx* c, const IntegrateParams& p, bool bricks, int mode, 
   const dim3 blk(32, 8, 1);
   const Tunables& tn = tunables();
   if (bricks) {
-    int max_cols = 0, max_nz = 0;
-    for (size_t i = 0; i + 5 < c->h_ranges.size(); i += 6) {
-      max_cols = std::max(max_cols, (c->h_ranges[i + 1] - c->h_ranges[i]) * (c->h_ranges[i + 3] - c->h_ranges[i + 2]));
-      max_nz = std::max(max_nz, c->h_ranges[i + 5] - c->h_ranges[i + 4]);
-    }
+    int max_cols, max_nz;
+    brick_extents(c, max_cols, max_nz);
     if (max_cols == 0 || max_nz == 0) return RR_OK;
     if (fused) {
       // z-chunks: split a brick's z extent into pieces of ~zchunk voxels of equal size
       const int want = std::max(1, tn.zchunk);
       const int n_zchunks = std::max(1, (max_nz + want - 1) / want);
       FusedParams f{};
-      f.ip = p;
-      f.rowmask = c->d_rowmask; f.rowany = c->d_rowany; f.cand_y = c->d_cand_y; f.cand_z = c->d_cand_z;
-      f.mask_words = c->mask_words; f.nby = (int)c->bricks.res[1];
-      f.work = c->d_work;
+      setup_fill(c, p, mode, tn.fill_rows, f);
       f.max_cols = max_cols; f.max_nz = max_nz; f.n_zchunks = n_zchunks; f.zchunk = (max_nz + n_zchunks - 1) / n_zchunks;
-      f.fill_rows = std::min(32, std::max(1, tn.fill_rows)); f.fill_warps = tn.fill_warps;
+      f.fill_warps = tn.fill_warps;
       // chunk <= 0: one z-chunk of one brick (all its column blocks) per draw
       f.chunk = tn.chunk > 0 ? tn.chunk : (max_cols + 31) / 32;
-      f.row_begin = (uint32_t)p.z_begin * (uint32_t)p.Y; f.row_end = (uint32_t)p.z_end * (uint32_t)p.Y;
-      f.fill_items = (f.row_end - f.row_begin + (uint32_t)f.fill_rows - 1u) / (uint32_t)f.fill_rows;
-      f.fill_value = cleared_voxel(mode, p.limit);
       cudaMemsetAsync(c->d_work, 0, 4 * sizeof(uint32_t), c->stream);
       const dim3 grd(148 * std::min(2, std::max(1, tn.ctas)), 1, 1);
       if constexpr (N > 4) {
@@ -472,18 +391,7 @@ static int launch_n(rr_ctx* c, const IntegrateParams& p, bool bricks, int mode, 
       RR_LAUNCH_CHECK(c, "k_integrate_fused");
       return RR_OK;
     }
-    // block size: the multiple of 32 (128..320) that wastes the fewest lanes on a brick's column count
-    int threads = 256;
-    double best = 1e9;
-    for (int t = 128; t <= BRICK_MAX_THREADS; t += 32) {
-      const double waste = double((max_cols + t - 1) / t * t) / double(max_cols);
-      if (waste < best - 1e-9 || (waste < best + 1e-9 && t > threads)) { best = waste; threads = t; }
-    }
-    const int zchunk = 9;
-    const dim3 grd(148 * std::max(1, tn.brick_grid), 1, 1);
-    if (mode == 1) k_integrate_bricks<N, 1, 2><<<grd, threads, 0, c->stream>>>(p, max_cols, max_nz, zchunk);
-    else if (mode == 2) k_integrate_bricks<N, 2, 2><<<grd, threads, 0, c->stream>>>(p, max_cols, max_nz, zchunk);
-    else k_integrate_bricks<N, 0, 2><<<grd, threads, 0, c->stream>>>(p, max_cols, max_nz, zchunk);
+    return launch_bricks_n<N>(c, p, mode, nullptr);
   } else {
     const int nz = p.z_end - p.z_begin;
     const dim3 grd((p.X + 31) / 32, (p.Y + 7) / 8, (nz + p.z_chunk - 1) / p.z_chunk);
@@ -492,6 +400,18 @@ static int launch_n(rr_ctx* c, const IntegrateParams& p, bool bricks, int mode, 
     else k_integrate_dense<N, 0><<<grd, blk, 0, c->stream>>>(p);
   }
   RR_LAUNCH_CHECK(c, "k_integrate");
+  return RR_OK;
+}
+
+// (k0, k1, g, 1-g) of every fine z against the inverse volume's z axis; rebuilt when either resolution changes
+int build_ztab(rr_ctx* c) {
+  const int Z = (int)c->res[2], IZ = (int)c->ires[2];
+  if (c->d_ztab && c->ztab_Z == Z && c->ztab_IZ == IZ) return RR_OK;
+  if (c->d_ztab) { cudaStreamSynchronize(c->stream); cudaFree(c->d_ztab); c->d_ztab = nullptr; }
+  if (cudaMalloc((void**)&c->d_ztab, sizeof(float4) * (size_t)Z) != cudaSuccess) return fail(c, RR_ERR_CUDA, "integrate: z table allocation failed");
+  k_build_ztab<<<(Z + 127) / 128, 128, 0, c->stream>>>(c->d_ztab, Z, IZ);
+  RR_LAUNCH_CHECK(c, "k_build_ztab");
+  c->ztab_Z = Z; c->ztab_IZ = IZ;
   return RR_OK;
 }
 
@@ -512,14 +432,9 @@ int launch_integrate(rr_ctx* c) {
   }
   p.z_chunk = 32;
   p.fW = (float)c->W; p.fH = (float)c->H; p.exmax = (float)(c->W - 1); p.eymax = (float)(c->H - 1);
-  if (!c->d_ztab || c->ztab_Z != p.Z || c->ztab_IZ != p.IZ) {
-    if (c->d_ztab) { cudaStreamSynchronize(c->stream); cudaFree(c->d_ztab); c->d_ztab = nullptr; }
-    if (cudaMalloc((void**)&c->d_ztab, sizeof(float4) * (size_t)p.Z) != cudaSuccess) return fail(c, RR_ERR_CUDA, "integrate: z table allocation failed");
-    k_build_ztab<<<(p.Z + 127) / 128, 128, 0, c->stream>>>(c->d_ztab, p.Z, p.IZ);
-    RR_LAUNCH_CHECK(c, "k_build_ztab");
-    c->ztab_Z = p.Z; c->ztab_IZ = p.IZ;
-  }
+  RR_TRY_RC(build_ztab(c));
   p.ztab = c->d_ztab;
+  p.pairs = c->d_pairs; p.pair_pitch = c->pair_pitch;
   p.limit = c->cfg.limit;
   p.wide_loads = tunables().ldg256;
   const int mode = c->cfg.store_weight == RR_VOXELS_HALF2 ? 2 : (c->cfg.store_weight != 0 ? 1 : 0);
@@ -530,27 +445,34 @@ int launch_integrate(rr_ctx* c) {
   const size_t nslab = plane * (size_t)(p.z_end - p.z_begin);
   // tunable fused=0 selects the two-kernel path (k_fill, then k_integrate_bricks) for A/B measurements
   const bool fused = bricks && tunables().fused != 0 && c->fused_ok;
-  if (bricks && !fused && nslab) {
-    // dense mode overwrites every voxel, so only the brick path needs the clear
-    k_fill<<<148 * 8, 256, 0, c->stream>>>(c->d_tsdf + plane * p.z_begin, nslab, cleared_voxel(mode, p.limit));
-    RR_LAUNCH_CHECK(c, "k_fill");
-    if (weight) {
-      k_fill<<<148 * 8, 256, 0, c->stream>>>(c->d_weight + plane * p.z_begin, nslab, 0.0f);
-      RR_LAUNCH_CHECK(c, "k_fill");
-    }
-  }
   int rc = RR_OK;
-  if (nslab) {
-    switch (c->N) {
-      case 1: rc = launch_n<1>(c, p, bricks, mode, fused); break;
-      case 2: rc = launch_n<2>(c, p, bricks, mode, fused); break;
-      case 3: rc = launch_n<3>(c, p, bricks, mode, fused); break;
-      case 4: rc = launch_n<4>(c, p, bricks, mode, fused); break;
-      case 5: rc = launch_n<5>(c, p, bricks, mode, fused); break;
-      case 6: rc = launch_n<6>(c, p, bricks, mode, fused); break;
-      case 7: rc = launch_n<7>(c, p, bricks, mode, fused); break;
-      case 8: rc = launch_n<8>(c, p, bricks, mode, fused); break;
-      default: return fail(c, RR_ERR_UNSUPPORTED, "integrate: 1..8 sensors supported");
+  bool done = false;
+  // first choice in bricks mode: the TMA-staged persistent kernel (rr_integrate_staged.cu); it declines (done = false) when
+  // the configuration does not fit its shared-memory stages, and the direct kernels below take over
+  if (fused && nslab && tunables().staged != 0) rc = launch_integrate_staged(c, p, mode, &done);
+  if (!done && rc == RR_OK) {
+    if (bricks && !fused && nslab) {
+      // dense mode overwrites every voxel, so only the brick path needs the clear
+      float* t0 = c->d_tsdf + plane * p.z_begin;
+      k_fill<<<148 * 8, 256, 0, c->stream>>>(t0, nslab, cleared_voxel(mode, p.limit));
+      RR_LAUNCH_CHECK(c, "k_fill");
+      if (weight) {
+        k_fill<<<148 * 8, 256, 0, c->stream>>>(c->d_weight + plane * p.z_begin, nslab, 0.0f);
+        RR_LAUNCH_CHECK(c, "k_fill");
+      }
+    }
+    if (nslab) {
+      switch (c->N) {
+        case 1: rc = launch_n<1>(c, p, bricks, mode, fused); break;
+        case 2: rc = launch_n<2>(c, p, bricks, mode, fused); break;
+        case 3: rc = launch_n<3>(c, p, bricks, mode, fused); break;
+        case 4: rc = launch_n<4>(c, p, bricks, mode, fused); break;
+        case 5: rc = launch_n<5>(c, p, bricks, mode, fused); break;
+        case 6: rc = launch_n<6>(c, p, bricks, mode, fused); break;
+        case 7: rc = launch_n<7>(c, p, bricks, mode, fused); break;
+        case 8: rc = launch_n<8>(c, p, bricks, mode, fused); break;
+        default: return fail(c, RR_ERR_UNSUPPORTED, "integrate: 1..8 sensors supported");
+      }
     }
   }
   timer_end(c, "2integrate");

@@ -1,0 +1,657 @@
+// TSDF integration of the occupied bricks with TMA-staged operands (sm_100a): the per-voxel work of
+// glsl/tsdf_integration.vs:23-59 driven like ReconIntegration::integrate (recon_integration.cpp:243-270), fused with the
+// clear of the volume (glClearTexImage, :250-251) as in rr_integrate.cu's k_integrate_fused - same arithmetic (the device
+// functions of rr_integrate.cuh), same results bit for bit, different data movement.
+//
+// Both operands of a voxel-sensor evaluation have addresses that do not depend on frame data:
+//   * the inverse calibration volume (cv_xyz_inv) is sampled at the voxel centre: for a box of voxels the eight-corner
+//     gathers cover an axis-aligned box of coarse texels, an affine function of the voxel range;
+//   * the depth / quality / silhouette taps sit where the calibration projects the voxel: for a box of voxels they cover a
+//     small rectangle of each sensor's image, fixed by calibration + brick grid and computed once (k_footprints).
+// So a work item = (occupied brick, y-chunk, z-chunk) is served by 1 + N bulk tensor copies (cp.async.bulk.tensor, TMA):
+// a 5-D box {xyzw, BX, BY, BZ, N} of the inverse volumes and one T x T tile per sensor of the "pair image"
+// (depth_b.x, quality | silhouette sign; 8 bytes per pixel, border replicated so CLAMP_TO_EDGE needs no clamping).
+// A persistent CTA per SM runs a two-stage mbarrier pipeline: one producer thread draws items from a global counter and
+// issues the copies for item i+1 while CWARPS consumer warps evaluate item i out of shared memory (LDS only, no global
+// loads in the voxel loop); FWARPS warps stream the clear (-limit) over every voxel outside the occupied bricks the whole
+// time, and every warp that runs out of its own work helps with the clear.
+#include "rr_integrate.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+namespace rr {
+
+struct StagedParams {
+  FusedParams f;            // integrate parameters + clear stream
+  int cy, cz, n_yc, n_zc;   // work item = brick x y-chunk x z-chunk (voxels per chunk, chunks per brick)
+  int BX, BY, BZ, T;        // staged inverse-volume box (coarse texels) and pair-image tile edge (pixels)
+  const uint32_t* fp;       // [bricks * n_yc * n_zc][N]: tile origin tx0 | ty0 << 16
+  const uint8_t* legacy;    // [bricks]: 1 = left to k_integrate_bricks (a footprint exceeds the tile); may be nullptr
+  uint32_t inv_bytes, tile_bytes;    // bytes one item's copies deliver (box, one tile)
+  uint32_t inv_span, tile_span, stage_bytes;   // smem regions: TMA destinations are 128-byte aligned
+  uint32_t* err;            // [0] box overflow, [1] barrier time-out
+  int debug;
+};
+
+// first 128 bytes of a stage, written by the producer before it arms the stage's full barrier
+struct ItemHdr {
+  int valid;                // 0: no more items
+  int x0, nx, y0, ny, zb, ze;
+  int ixlo, iylo, izlo;     // origin of the staged inverse-volume box
+  uint32_t pad[2];
+  uint32_t tb[RR_MAX_SENSORS];   // byte offset (from the dynamic smem base) of pair texel (0, 0) of sensor s: tile start - tile origin
+};
+// stage layout: [0,128) ItemHdr | [128, 128 + 16*ZT_MAX) the item's slice of the z table | inverse-volume box | N pair tiles
+#define ITEM_HDR_BYTES 128
+#define ZT_MAX 56
+#define STAGE_HDR_BYTES (ITEM_HDR_BYTES + 16 * ZT_MAX)
+static_assert(sizeof(ItemHdr) <= ITEM_HDR_BYTES, "item header must fit its slot");
+static_assert(STAGE_HDR_BYTES % 128 == 0, "TMA destinations are 128-byte aligned");
+
+// ---- PTX: mbarrier + TMA ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+// try_wait suspends the thread in hardware until the phase completes or the time hint (ns) runs out: a waiting warp
+// issues one instruction per hint period instead of spinning
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* b, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(smem_u32(b)), "r"(parity), "r"(100000u) : "memory");
+  return ok != 0;
+}
+// A wait that never completes would hang the GPU, so a pipeline bug gives up after ~0.3 s of wall time, raises err[1]
+// (rr_integrator_info reports it) and lets the role run out instead.
+__device__ __forceinline__ bool mbar_wait(uint64_t* b, uint32_t parity, uint32_t* err) {
+  if (mbar_try_wait(b, parity)) return true;
+  unsigned long long t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while (!mbar_try_wait(b, parity)) {
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (t - t0 > 300000000ull) {
+      atomicOr(err + 1, 1u);
+      return false;
+    }
+  }
+  return true;
+}
+// plain bulk copy global -> shared (1-D TMA): src, dst and size multiples of 16 bytes
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+               ::"r"(dst), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(dst), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+
+// ---- one (x, y) column of a staged item ---------------------------------------------------------------------------
+// Same plane / tap / decision arithmetic as march_column (rr_integrate.cu), operands read from the stage:
+//   inverse-volume corners: float4 at inv_off + ((s*BZ + k-izlo)*BY + y-iylo)*BX + x-ixlo
+//   pair texels of the footprint (ex, ey): float2 at tb[s] + (ey*T + ex)*8, +8, +T*8, +T*8+8
+template <int N, int MODE>
+__device__ __forceinline__ void march_staged(const IntegrateParams& p, const uint8_t* __restrict__ smem, uint32_t inv_off,
+                                             const ItemHdr* __restrict__ h, int BX, int BY, int BZ, int T, int x, int y, int zb, int ze) {
+  const float stepX = 1.0f / (float)p.X, stepY = 1.0f / (float)p.Y;
+  const float px = ((float)x + 0.5f) * stepX, py = ((float)y + 0.5f) * stepY;
+  int x0, x1, y0, y1; float a, b;
+  lin_coord(px, p.IX, x0, x1, a);
+  lin_coord(py, p.IY, y0, y1, b);
+  const float oma = 1.0f - a, omb = 1.0f - b;
+  const int ixlo = h->ixlo, iylo = h->iylo, izlo = h->izlo;
+  const uint32_t r0 = (uint32_t)((y0 - iylo) * BX), r1 = (uint32_t)((y1 - iylo) * BX);
+  const uint32_t c00 = inv_off + ((r0 + (uint32_t)(x0 - ixlo)) << 4), c10 = inv_off + ((r0 + (uint32_t)(x1 - ixlo)) << 4);
+  const uint32_t c01 = inv_off + ((r1 + (uint32_t)(x0 - ixlo)) << 4), c11 = inv_off + ((r1 + (uint32_t)(x1 - ixlo)) << 4);
+  const uint32_t ps = (uint32_t)(BX * BY) << 4, ss = ps * (uint32_t)BZ;
+  const uint32_t trow = (uint32_t)T << 3;
+  uint32_t tb[N];
+#pragma unroll
+  for (int s = 0; s < N; ++s) tb[s] = h->tb[s];
+  const float limit = p.limit, neg_limit = -p.limit;
+  float3 A[N], B[N];
+  int ck0 = -1, ck1 = -1;
+
+  auto plane = [&](int s, int k) -> float3 {
+    const uint32_t off = (uint32_t)s * ss + (uint32_t)(k - izlo) * ps;
+    const float4 p00 = *reinterpret_cast<const float4*>(smem + c00 + off), p10 = *reinterpret_cast<const float4*>(smem + c10 + off);
+    const float4 p01 = *reinterpret_cast<const float4*>(smem + c01 + off), p11 = *reinterpret_cast<const float4*>(smem + c11 + off);
+    return plane_reduce(p00, p10, p01, p11, a, oma, b, omb);
+  };
+
+  unsigned o = (unsigned)((zb * p.Y + y) * p.X + x);
+  const unsigned ostep = (unsigned)(p.X * p.Y);
+  const float4* ztab = reinterpret_cast<const float4*>(smem + inv_off - STAGE_HDR_BYTES + ITEM_HDR_BYTES) - zb;   // the item's slice, staged
+  for (int z = zb; z < ze; ++z, o += ostep) {
+    const float4 zt = ztab[z];
+    const int k0 = __float_as_int(zt.x), k1 = __float_as_int(zt.y);
+    const float g = zt.z, omg = zt.w;
+    if (k0 != ck0) {
+      if (k0 == ck1) {
+#pragma unroll
+        for (int s = 0; s < N; ++s) A[s] = B[s];
+      } else {
+#pragma unroll
+        for (int s = 0; s < N; ++s) A[s] = plane(s, k0);
+      }
+      ck0 = k0;
+    }
+    if (k1 != ck1) {
+      if (k1 == k0) {
+#pragma unroll
+        for (int s = 0; s < N; ++s) B[s] = A[s];
+      } else {
+#pragma unroll
+        for (int s = 0; s < N; ++s) B[s] = plane(s, k1);
+      }
+      ck1 = k1;
+    }
+    float weighted_tsd = limit, total_weight = 0.0f;
+    struct Tap { float wa, wb, d; float2 t00, t10, t01, t11; };
+    auto fetch = [&](int s) -> Tap {
+      Tap t;
+      int ex, ey;                // lower-left texel clamped to [-1, W-1]; the + 1 of the footprint index lives in tb[s]
+      tap_coords(A[s], B[s], g, omg, p.fW, p.fH, p.exmax, p.eymax, t.wa, t.wb, t.d, ex, ey);
+      const uint32_t off = tb[s] + ((uint32_t)(ey * T + ex) << 3);
+      t.t00 = *reinterpret_cast<const float2*>(smem + off);
+      t.t10 = *reinterpret_cast<const float2*>(smem + off + 8u);
+      t.t01 = *reinterpret_cast<const float2*>(smem + off + trow);
+      t.t11 = *reinterpret_cast<const float2*>(smem + off + trow + 8u);
+      return t;
+    };
+    auto fuse = [&](const Tap& t) {
+      fuse_tap(t.wa, t.wb, t.d, t.t00.x, t.t10.x, t.t01.x, t.t11.x, t.t00.y, t.t10.y, t.t01.y, t.t11.y, limit, neg_limit, weighted_tsd, total_weight);
+    };
+#pragma unroll
+    for (int s = 0; s + 1 < N; s += 2) {
+      const Tap t0 = fetch(s), t1 = fetch(s + 1);
+      fuse(t0);
+      fuse(t1);
+    }
+    if (N & 1) { const Tap t = fetch(N - 1); fuse(t); }
+    store_voxel<MODE>(p, o, weighted_tsd, total_weight);
+  }
+}
+
+// ---- the kernel ------------------------------------------------------------------------------------------------------
+// warps [0, CWARPS): consumers; warp CWARPS: producer (lane 0); warps above: clear stream.
+template <int N, int MODE, int CWARPS, int FWARPS>
+__global__ void __launch_bounds__((CWARPS + FWARPS + 1) * 32, 1)
+k_integrate_staged(const __grid_constant__ StagedParams p, const __grid_constant__ CUtensorMap map_inv, const __grid_constant__ CUtensorMap map_pairs) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t s_full[2], s_empty[2];
+  // TMA destinations must be 128-byte aligned; the dynamic window's own alignment is only guaranteed to 16
+  uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
+    mbar_init(&s_empty[0], CWARPS); mbar_init(&s_empty[1], CWARPS);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  const IntegrateParams& ip = p.f.ip;
+
+  if (warp == CWARPS) {                      // ---- producer
+    if (lane == 0) {
+      tma_prefetch_desc(&map_inv);
+      tma_prefetch_desc(&map_pairs);
+      const uint32_t n_occ = *ip.num_occupied;
+      // occupied bricks that intersect the slab: the list ascends in brick id, hence in brick z, so they are one run [lo, hi)
+      uint32_t lo = 0, hi = n_occ;
+      if (ip.z_begin > 0) {
+        uint32_t a = 0, b = n_occ;
+        while (a < b) { const uint32_t m = (a + b) >> 1; if (ip.ranges[(size_t)ip.occupied[m] * 6 + 5] > ip.z_begin) b = m; else a = m + 1; }
+        lo = a;
+      }
+      if (ip.z_end < ip.Z) {
+        uint32_t a = lo, b = n_occ;
+        while (a < b) { const uint32_t m = (a + b) >> 1; if (ip.ranges[(size_t)ip.occupied[m] * 6 + 4] >= ip.z_end) b = m; else a = m + 1; }
+        hi = a;
+      }
+      const uint32_t per_brick = (uint32_t)(p.n_yc * p.n_zc);
+      const uint32_t total = (p.debug & 2) ? 0u : (hi - lo) * per_brick;
+      const float stepX = 1.0f / (float)ip.X, stepY = 1.0f / (float)ip.Y;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (;;) {
+        const uint32_t it = atomicAdd(p.f.work, 1u);
+        uint8_t* st = smem + (uint32_t)stage * p.stage_bytes;
+        ItemHdr* h = reinterpret_cast<ItemHdr*>(st);
+        if (it >= total) {
+          if (!mbar_wait(&s_empty[stage], phase ^ 1u, p.err)) break;
+          h->valid = 0;
+          mbar_arrive(&s_full[stage]);
+          break;
+        }
+        const uint32_t bi = it / per_brick, r = it - bi * per_brick;
+        const int yc = (int)(r / (uint32_t)p.n_zc), zc = (int)(r - (uint32_t)yc * (uint32_t)p.n_zc);
+        const uint32_t brick = ip.occupied[lo + bi];
+        if (p.legacy && p.legacy[brick]) continue;
+        const int32_t* rg = ip.ranges + (size_t)brick * 6;
+        const int x0 = rg[0], x1 = rg[1];
+        const int yb = rg[2] + yc * p.cy, ye = min(yb + p.cy, rg[3]);
+        const int zb = max(rg[4] + zc * p.cz, ip.z_begin), ze = min(min(rg[4] + (zc + 1) * p.cz, rg[5]), ip.z_end);
+        if (x0 >= x1 || yb >= ye || zb >= ze) continue;
+        // coarse box of the item: lin_coord is monotone, so the first / last voxel bound every corner index
+        int i0, i1, ixlo, ixhi, iylo, iyhi; float w;
+        lin_coord(((float)x0 + 0.5f) * stepX, ip.IX, ixlo, i1, w);
+        lin_coord(((float)(x1 - 1) + 0.5f) * stepX, ip.IX, i0, ixhi, w);
+        lin_coord(((float)yb + 0.5f) * stepY, ip.IY, iylo, i1, w);
+        lin_coord(((float)(ye - 1) + 0.5f) * stepY, ip.IY, i0, iyhi, w);
+        const int izlo = __float_as_int(ip.ztab[zb].x), izhi = __float_as_int(ip.ztab[ze - 1].y);
+        if (ixhi - ixlo >= p.BX || iyhi - iylo >= p.BY || izhi - izlo >= p.BZ) { atomicOr(p.err, 1u); continue; }
+        if (!mbar_wait(&s_empty[stage], phase ^ 1u, p.err)) break;
+        h->valid = 1;
+        h->x0 = x0; h->nx = x1 - x0; h->y0 = yb; h->ny = ye - yb; h->zb = zb; h->ze = ze;
+        h->ixlo = ixlo; h->iylo = iylo; h->izlo = izlo;
+        const uint32_t* fp = p.fp + ((size_t)(brick * (uint32_t)p.n_yc + (uint32_t)yc) * (uint32_t)p.n_zc + (uint32_t)zc) * N;
+        const uint32_t base = (uint32_t)stage * p.stage_bytes + STAGE_HDR_BYTES;
+        uint32_t org[N];
+#pragma unroll
+        for (int s = 0; s < N; ++s) {
+          org[s] = fp[s];
+          h->tb[s] = base + p.inv_span + (uint32_t)s * p.tile_span + ((uint32_t)(p.T + 1) << 3) -
+                     ((((org[s] >> 16) * (uint32_t)p.T) + (org[s] & 0xffffu)) << 3);
+        }
+        const uint32_t zt_bytes = (uint32_t)(ze - zb) * 16u;
+        mbar_expect_tx(&s_full[stage], p.inv_bytes + (uint32_t)N * p.tile_bytes + zt_bytes);
+        bulk_load(smem_u32(st) + ITEM_HDR_BYTES, ip.ztab + zb, zt_bytes, &s_full[stage]);
+        const uint32_t dst = smem_u32(st) + STAGE_HDR_BYTES;
+        tma_load_5d(dst, &map_inv, &s_full[stage], 0, ixlo, iylo, izlo, 0);
+#pragma unroll
+        for (int s = 0; s < N; ++s)
+          tma_load_3d(dst + p.inv_span + (uint32_t)s * p.tile_span, &map_pairs, &s_full[stage], (int)(org[s] & 0xffffu), (int)(org[s] >> 16), s);
+        stage ^= 1;
+        phase ^= (stage == 0) ? 1u : 0u;
+      }
+    }
+    __syncwarp();
+  } else if (warp < CWARPS) {                // ---- consumers
+    int stage = 0;
+    uint32_t phase = 0;
+    for (;;) {
+      if (!mbar_wait(&s_full[stage], phase, p.err)) break;
+      const uint32_t sbase = (uint32_t)stage * p.stage_bytes;
+      const ItemHdr* h = reinterpret_cast<const ItemHdr*>(smem + sbase);
+      if (!h->valid) break;
+      const int x0 = h->x0, nx = h->nx, y0 = h->y0, zb = h->zb, ze = h->ze;
+      const int cols = nx * h->ny;
+      for (int col = (int)threadIdx.x; col < cols; col += CWARPS * 32) {
+        const int cyv = col / nx, cxv = col - cyv * nx;
+        march_staged<N, MODE>(ip, smem, sbase + STAGE_HDR_BYTES, h, p.BX, p.BY, p.BZ, p.T, x0 + cxv, y0 + cyv, zb, ze);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[stage]);
+      stage ^= 1;
+      phase ^= (stage == 0) ? 1u : 0u;
+    }
+  }
+  // ---- clear stream: the fill warps from the start, everybody else once their own work is done
+  fill_loop<MODE == 1>(p.f, lane);
+}
+
+// ---- footprints ------------------------------------------------------------------------------------------------------
+// One block per (brick, y-chunk, z-chunk) of the WHOLE brick grid (occupancy changes per frame, the footprints do not):
+// every voxel of the item runs the plane / tap arithmetic of the integrator and the block reduces the footprint indices
+// (ex, ey) per sensor to their bounding rectangle. out[item][s] = (exmin, eymin, exmax, eymax); empty item: exmax < exmin.
+template <int N>
+__global__ void __launch_bounds__(256) k_footprints(const __grid_constant__ IntegrateParams p, int cy, int cz, int n_yc, int n_zc, int4* __restrict__ out) {
+  __shared__ int s_red[8][RR_MAX_SENSORS][4];
+  const uint32_t item = blockIdx.x;
+  const uint32_t per_brick = (uint32_t)(n_yc * n_zc);
+  const uint32_t brick = item / per_brick, r = item - brick * per_brick;
+  const int yc = (int)(r / (uint32_t)n_zc), zc = (int)(r - (uint32_t)yc * (uint32_t)n_zc);
+  const int32_t* rg = p.ranges + (size_t)brick * 6;
+  const int x0 = rg[0], nx = rg[1] - rg[0];
+  const int yb = rg[2] + yc * cy, ye = min(yb + cy, rg[3]);
+  const int zb = rg[4] + zc * cz, ze = min(zb + cz, rg[5]);
+  int mn_x[N], mn_y[N], mx_x[N], mx_y[N];
+#pragma unroll
+  for (int s = 0; s < N; ++s) { mn_x[s] = mn_y[s] = 0x7fffffff; mx_x[s] = mx_y[s] = -1; }
+  const int cols = (nx > 0 && ye > yb && ze > zb) ? nx * (ye - yb) : 0;
+  const float stepX = 1.0f / (float)p.X, stepY = 1.0f / (float)p.Y;
+  const unsigned plane_sz = (unsigned)(p.IX * p.IY);
+  for (int col = (int)threadIdx.x; col < cols; col += (int)blockDim.x) {
+    const int cyv = col / nx, cxv = col - cyv * nx;
+    const float px = ((float)(x0 + cxv) + 0.5f) * stepX, py = ((float)(yb + cyv) + 0.5f) * stepY;
+    int cx0, cx1, cy0, cy1; float a, b;
+    lin_coord(px, p.IX, cx0, cx1, a);
+    lin_coord(py, p.IY, cy0, cy1, b);
+    const float oma = 1.0f - a, omb = 1.0f - b;
+    const unsigned o00 = cy0 * p.IX + cx0, o10 = cy0 * p.IX + cx1, o01 = cy1 * p.IX + cx0, o11 = cy1 * p.IX + cx1;
+    for (int z = zb; z < ze; ++z) {
+      const float4 zt = __ldg(p.ztab + z);
+      const int k0 = __float_as_int(zt.x), k1 = __float_as_int(zt.y);
+#pragma unroll
+      for (int s = 0; s < N; ++s) {
+        const float4* b0 = p.inv + (unsigned)(s * p.IZ + k0) * plane_sz;
+        const float4* b1 = p.inv + (unsigned)(s * p.IZ + k1) * plane_sz;
+        const float3 A = plane_reduce(__ldg(b0 + o00), __ldg(b0 + o10), __ldg(b0 + o01), __ldg(b0 + o11), a, oma, b, omb);
+        const float3 B = plane_reduce(__ldg(b1 + o00), __ldg(b1 + o10), __ldg(b1 + o01), __ldg(b1 + o11), a, oma, b, omb);
+        float wa, wb, d; int ex, ey;
+        tap_coords(A, B, zt.z, zt.w, p.fW, p.fH, p.exmax, p.eymax, wa, wb, d, ex, ey);
+        ex += 1; ey += 1;
+        mn_x[s] = min(mn_x[s], ex); mx_x[s] = max(mx_x[s], ex);
+        mn_y[s] = min(mn_y[s], ey); mx_y[s] = max(mx_y[s], ey);
+      }
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int s = 0; s < N; ++s) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      mn_x[s] = min(mn_x[s], __shfl_xor_sync(0xffffffffu, mn_x[s], d)); mn_y[s] = min(mn_y[s], __shfl_xor_sync(0xffffffffu, mn_y[s], d));
+      mx_x[s] = max(mx_x[s], __shfl_xor_sync(0xffffffffu, mx_x[s], d)); mx_y[s] = max(mx_y[s], __shfl_xor_sync(0xffffffffu, mx_y[s], d));
+    }
+    if (lane == 0) { s_red[warp][s][0] = mn_x[s]; s_red[warp][s][1] = mn_y[s]; s_red[warp][s][2] = mx_x[s]; s_red[warp][s][3] = mx_y[s]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < N) {
+    const int s = threadIdx.x;
+    int4 v = make_int4(0x7fffffff, 0x7fffffff, -1, -1);
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+      v.x = min(v.x, s_red[w][s][0]); v.y = min(v.y, s_red[w][s][1]); v.z = max(v.z, s_red[w][s][2]); v.w = max(v.w, s_red[w][s][3]);
+    }
+    out[(size_t)item * N + s] = v;
+  }
+}
+
+// ---- host ------------------------------------------------------------------------------------------------------------
+// lin_coord (rr_math.cuh) on the host: same float operations (this file is compiled with -ffp-contract=off)
+static void h_lin_coord(float s, int W, int& i0, int& i1) {
+  const float u = s * (float)W - 0.5f;
+  const float f = floorf(u);
+  auto cl = [&](float v) { return !(v >= 0.0f) ? 0 : (v >= (float)(W - 1) ? W - 1 : (int)v); };
+  i0 = cl(f);
+  i1 = cl(f + 1.0f);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+    cudaGetLastError();
+    return (EncodeTiledFn)f;
+  }();
+  return fn;
+}
+
+template <int N, int CWARPS, int FWARPS>
+static int launch_staged_nf(rr_ctx* c, const StagedParams& sp, int mode) {
+  const auto& st = c->sti;
+  const dim3 grd(148, 1, 1), blk((CWARPS + FWARPS + 1) * 32, 1, 1);
+  auto go = [&](auto kern) -> int {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st.smem_bytes);
+    if (e != cudaSuccess) return check(c, e, "k_integrate_staged shared memory");
+    kern<<<grd, blk, st.smem_bytes, c->stream>>>(sp, st.map_inv, st.map_pairs);
+    return RR_OK;
+  };
+  int rc;
+  if (mode == 1) rc = go(k_integrate_staged<N, 1, CWARPS, FWARPS>);
+  else if (mode == 2) rc = go(k_integrate_staged<N, 2, CWARPS, FWARPS>);
+  else rc = go(k_integrate_staged<N, 0, CWARPS, FWARPS>);
+  if (rc != RR_OK) return rc;
+  RR_LAUNCH_CHECK(c, "k_integrate_staged");
+  return RR_OK;
+}
+
+template <int N, int CWARPS>
+static int launch_staged_n(rr_ctx* c, const StagedParams& sp, int mode) {
+  return c->sti.fwarps == 1 ? launch_staged_nf<N, CWARPS, 1>(c, sp, mode) : launch_staged_nf<N, CWARPS, 2>(c, sp, mode);
+}
+
+// consumer warps per CTA: up to four sensors run 22 warps (a 26 x 26 brick's 676 columns in one pass) at 80 registers,
+// more sensors keep 6 more registers of plane state each and run 11 warps at 144
+static int consumer_warps(int N) { return N <= 4 ? 22 : 11; }
+
+static int footprints(rr_ctx* c, const IntegrateParams& p, int cy, int cz, int n_yc, int n_zc, int4* d_out, uint32_t items) {
+  switch (c->N) {
+    case 1: k_footprints<1><<<items, 256, 0, c->stream>>>(p, cy, cz, n_yc, n_zc, d_out); break;
+    case 2: k_footprints<2><<<items, 256, 0, c->stream>>>(p, cy, cz, n_yc, n_zc, d_out); break;
+    case 3: k_footprints<3><<<items, 256, 0, c->stream>>>(p, cy, cz, n_yc, n_zc, d_out); break;
+    case 4: k_footprints<4><<<items, 256, 0, c->stream>>>(p, cy, cz, n_yc, n_zc, d_out); break;
+    case 5: k_footprints<5><<<items, 256, 0, c->stream>>>(p, cy, cz, n_yc, n_zc, d_out); break;
+    case 6: k_footprints<6><<<items, 256, 0, c->stream>>>(p, cy, cz, n_yc, n_zc, d_out); break;
+    case 7: k_footprints<7><<<items, 256, 0, c->stream>>>(p, cy, cz, n_yc, n_zc, d_out); break;
+    case 8: k_footprints<8><<<items, 256, 0, c->stream>>>(p, cy, cz, n_yc, n_zc, d_out); break;
+    default: return fail(c, RR_ERR_UNSUPPORTED, "integrate: 1..8 sensors supported");
+  }
+  RR_LAUNCH_CHECK(c, "k_footprints");
+  return RR_OK;
+}
+
+void staged_release(rr_ctx* c) {
+  cudaFree(c->sti.d_fp); cudaFree(c->sti.d_legacy); cudaFree(c->sti.d_err);
+  c->sti.d_fp = nullptr; c->sti.d_legacy = nullptr; c->sti.d_err = nullptr;
+  c->sti.ok = false; c->sti.dirty = true;
+}
+
+// the tunables the staged tables depend on, as one key (other knobs change launch shapes of the direct kernels only)
+static unsigned staged_key() {
+  const Tunables& tn = tunables();
+  unsigned k = 2166136261u;
+  for (int v : {tn.staged, tn.fused, tn.stage_zchunk, tn.stage_ychunk, tn.stage_tile, tn.stage_fwarps}) k = (k ^ (unsigned)v) * 16777619u;
+  return k;
+}
+
+bool staged_selected(const rr_ctx* c) {
+  const Tunables& tn = tunables();
+  return c->configured && c->cfg.use_bricks && c->fused_ok && tn.fused && tn.staged && c->sti.ok && !c->sti.dirty &&
+         c->sti.generation == staged_key();
+}
+
+int build_ztab(rr_ctx* c);   // rr_integrate.cu
+
+// Everything the staged kernel needs that depends only on calibration + configuration: item geometry, box and tile sizes,
+// the footprint table, the tensor maps. Synchronises the stream (never called inside a graph capture: rr_fuse_frame runs
+// it before capturing).
+int staged_prepare(rr_ctx* c) {
+  auto& st = c->sti;
+  const Tunables& tn = tunables();
+  if (!st.dirty && st.generation == staged_key()) return RR_OK;
+  st.ok = false;
+  st.n_legacy = 0;
+  if (!c->configured || !c->cfg.use_bricks || !c->fused_ok || !tn.staged || !tn.fused || !c->d_inv) return RR_OK;
+  for (int i = 0; i < c->N; ++i) if (!c->have_inv[i]) return RR_OK;
+  st.dirty = false;
+  st.generation = staged_key();
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) return RR_OK;                       // driver without tensor maps: the direct kernels run
+  const int N = c->N, X = (int)c->res[0], Y = (int)c->res[1], Z = (int)c->res[2];
+  const int IX = (int)c->ires[0], IY = (int)c->ires[1], IZ = (int)c->ires[2];
+  int max_nx = 0, max_ny = 0, max_nz = 0;
+  const size_t nb = c->h_ranges.size() / 6;
+  for (size_t i = 0; i < nb; ++i) {
+    const int32_t* r = c->h_ranges.data() + i * 6;
+    max_nx = std::max(max_nx, r[1] - r[0]); max_ny = std::max(max_ny, r[3] - r[2]); max_nz = std::max(max_nz, r[5] - r[4]);
+  }
+  if (max_nx <= 0 || max_ny <= 0 || max_nz <= 0) return RR_OK;
+  st.cwarps = consumer_warps(N);
+  st.fwarps = tn.stage_fwarps == 1 ? 1 : 2;
+  const int CT = st.cwarps * 32;
+  // y-chunk: as many brick rows as fill the consumer threads best (ties: the larger chunk, fewer items)
+  int cy = tn.stage_ychunk > 0 ? std::min(tn.stage_ychunk, max_ny) : 0;
+  if (cy == 0) {
+    double best = -1.0;
+    for (int t = 1; t <= max_ny; ++t) {
+      const int cols = max_nx * t;
+      const double eff = double(cols) / double((cols + CT - 1) / CT * CT);
+      if (eff >= best - 0.02) { if (eff > best) best = eff; cy = t; }
+    }
+  }
+  const int n_yc = (max_ny + cy - 1) / cy;
+  const int n_zc = std::max(1, (max_nz + std::max(1, tn.stage_zchunk) - 1) / std::max(1, tn.stage_zchunk));
+  const int cz = (max_nz + n_zc - 1) / n_zc;
+  // staged inverse-volume box: the largest coarse extent any item needs, from the same coordinate arithmetic as the device
+  int BX = 1, BY = 1, BZ = 1;
+  const float stepX = 1.0f / (float)X, stepY = 1.0f / (float)Y, stepZ = 1.0f / (float)Z;
+  for (size_t i = 0; i < nb; ++i) {
+    const int32_t* r = c->h_ranges.data() + i * 6;
+    int lo, hi, t;
+    if (r[1] > r[0]) {
+      h_lin_coord(((float)r[0] + 0.5f) * stepX, IX, lo, t); h_lin_coord(((float)(r[1] - 1) + 0.5f) * stepX, IX, t, hi);
+      BX = std::max(BX, hi - lo + 1);
+    }
+    for (int yb = r[2]; yb < r[3]; yb += cy) {
+      const int ye = std::min(yb + cy, r[3]);
+      h_lin_coord(((float)yb + 0.5f) * stepY, IY, lo, t); h_lin_coord(((float)(ye - 1) + 0.5f) * stepY, IY, t, hi);
+      BY = std::max(BY, hi - lo + 1);
+    }
+    for (int zb = r[4]; zb < r[5]; zb += cz) {
+      const int ze = std::min(zb + cz, r[5]);
+      h_lin_coord(((float)zb + 0.5f) * stepZ, IZ, lo, t); h_lin_coord(((float)(ze - 1) + 0.5f) * stepZ, IZ, t, hi);
+      BZ = std::max(BZ, hi - lo + 1);
+    }
+  }
+  if (BX > 256 || BY > 256 || BZ > 256 || cz > ZT_MAX) return RR_OK;
+  int smem_max = 0;
+  cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device);
+  const long budget = ((long)smem_max - 1024) / 2 - STAGE_HDR_BYTES;           // per stage, after the header
+  const long inv_bytes = (long)N * BZ * BY * BX * 16, inv_span = (inv_bytes + 127) & ~127L;
+  long t_budget = (long)std::floor(std::sqrt(std::max(0.0, double(budget - inv_span - 128 * N) / (8.0 * N))));
+  t_budget = std::min(t_budget & ~1L, 256L);
+  if (t_budget < 8) return RR_OK;
+
+  // footprints of every item of the brick grid
+  IntegrateParams p{};
+  p.inv = c->d_inv; p.ranges = c->d_ranges;
+  p.IX = IX; p.IY = IY; p.IZ = IZ; p.W = c->W; p.H = c->H; p.X = X; p.Y = Y; p.Z = Z;
+  p.fW = (float)c->W; p.fH = (float)c->H; p.exmax = (float)(c->W - 1); p.eymax = (float)(c->H - 1);
+  RR_TRY_RC(build_ztab(c));
+  p.ztab = c->d_ztab;
+  const size_t items = nb * (size_t)n_yc * n_zc;
+  if (items == 0 || items > 0x7fffffffull) return RR_OK;
+  int4* d_ext = nullptr;
+  if (cudaMalloc((void**)&d_ext, items * N * sizeof(int4)) != cudaSuccess) { cudaGetLastError(); return RR_OK; }
+  int rc = footprints(c, p, cy, cz, n_yc, n_zc, d_ext, (uint32_t)items);
+  std::vector<int4> ext(items * N);
+  if (rc == RR_OK) rc = check(c, cudaMemcpyAsync(ext.data(), d_ext, ext.size() * sizeof(int4), cudaMemcpyDeviceToHost, c->stream), "footprint download");
+  if (rc == RR_OK) rc = check(c, cudaStreamSynchronize(c->stream), "footprint sync");
+  cudaFree(d_ext);
+  if (rc != RR_OK) return rc;
+  // tile edge: cover every footprint if that is affordable, else the bulk of them (the rest goes to k_integrate_bricks)
+  std::vector<int> need;
+  need.reserve(ext.size());
+  for (const int4& e : ext)
+    if (e.z >= e.x) need.push_back(std::max(e.z - (e.x & ~1), e.w - e.y) + 2);
+  if (need.empty()) return RR_OK;
+  std::sort(need.begin(), need.end());
+  auto even = [](long v) { return (v + 1) & ~1L; };
+  long T;
+  if (tn.stage_tile > 0) {
+    T = std::min<long>(even(tn.stage_tile), t_budget);
+  } else {
+    const long t_all = even(need.back()), t_bulk = even(need[(size_t)((need.size() - 1) * 0.98)]);
+    T = (t_all <= t_budget && t_all <= std::max(48L, t_bulk + 8)) ? t_all : std::min(t_budget, std::max(16L, t_bulk));
+  }
+  T = std::max(T, 8L);
+  std::vector<uint32_t> fp(items * N, 0u);
+  std::vector<uint8_t> legacy(nb, 0);
+  const size_t per_brick = (size_t)n_yc * n_zc;
+  for (size_t i = 0; i < items; ++i)
+    for (int s = 0; s < N; ++s) {
+      const int4& e = ext[i * N + s];
+      if (e.z < e.x) continue;
+      if (std::max(e.z - (e.x & ~1), e.w - e.y) + 2 > T || e.x > 0xffff || e.y > 0xffff) legacy[i / per_brick] = 1;
+      fp[i * N + s] = (uint32_t)(e.x & ~1) | ((uint32_t)e.y << 16);
+    }
+  for (uint8_t v : legacy) st.n_legacy += v;
+  staged_release(c);
+  st.dirty = false;
+  RR_TRY_RC(check(c, cudaMalloc((void**)&st.d_fp, fp.size() * sizeof(uint32_t)), "footprint table"));
+  RR_TRY_RC(check(c, cudaMalloc((void**)&st.d_legacy, nb), "legacy brick mask"));
+  RR_TRY_RC(check(c, cudaMalloc((void**)&st.d_err, 4 * sizeof(uint32_t)), "staged flags"));
+  cudaMemcpyAsync(st.d_fp, fp.data(), fp.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+  cudaMemcpyAsync(st.d_legacy, legacy.data(), nb, cudaMemcpyHostToDevice, c->stream);
+  cudaMemsetAsync(st.d_err, 0, 4 * sizeof(uint32_t), c->stream);
+  RR_TRY_RC(check(c, cudaStreamSynchronize(c->stream), "staged tables upload"));
+
+  // tensor maps: inverse volumes as (xyzw, IX, IY, IZ, N) float32, pair image as (pitch, H+2, N) 8-byte pixels.
+  // The innermost start coordinate of a tile must be a multiple of 16 bytes (measured: tools/tma_probe.cu), so tile origins are even pixels.
+  {
+    const cuuint64_t dims[5] = {4, (cuuint64_t)IX, (cuuint64_t)IY, (cuuint64_t)IZ, (cuuint64_t)N};
+    const cuuint64_t strides[4] = {16, (cuuint64_t)IX * 16, (cuuint64_t)IX * IY * 16, (cuuint64_t)IX * IY * IZ * 16};
+    const cuuint32_t box[5] = {4, (cuuint32_t)BX, (cuuint32_t)BY, (cuuint32_t)BZ, (cuuint32_t)N};
+    const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    if (enc(&st.map_inv, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, c->d_inv, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return RR_OK;
+  }
+  {
+    const cuuint64_t dims[3] = {(cuuint64_t)c->pair_pitch, (cuuint64_t)(c->H + 2), (cuuint64_t)N};
+    const cuuint64_t strides[2] = {(cuuint64_t)c->pair_pitch * 8, (cuuint64_t)c->pair_pitch * (c->H + 2) * 8};
+    const cuuint32_t box[3] = {(cuuint32_t)T, (cuuint32_t)T, 1};
+    const cuuint32_t es[3] = {1, 1, 1};
+    if (enc(&st.map_pairs, CU_TENSOR_MAP_DATA_TYPE_INT64, 3, c->d_pairs, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return RR_OK;
+  }
+  st.cy = cy; st.cz = cz; st.n_yc = n_yc; st.n_zc = n_zc;
+  st.BX = BX; st.BY = BY; st.BZ = BZ; st.T = (int)T;
+  st.inv_bytes = (uint32_t)inv_bytes;
+  st.tile_bytes = (uint32_t)(T * T * 8);
+  st.inv_span = (uint32_t)inv_span;
+  st.tile_span = (st.tile_bytes + 127u) & ~127u;
+  st.stage_bytes = STAGE_HDR_BYTES + st.inv_span + (uint32_t)N * st.tile_span;
+  st.smem_bytes = 2 * st.stage_bytes + 128;
+  st.ok = true;
+  return RR_OK;
+}
+
+int launch_integrate_staged(rr_ctx* c, const IntegrateParams& p, int mode, bool* done) {
+  *done = false;
+  RR_TRY_RC(staged_prepare(c));
+  const auto& st = c->sti;
+  if (!staged_selected(c)) return RR_OK;
+  StagedParams sp{};
+  setup_fill(c, p, mode, tunables().stage_fill_rows, sp.f);
+  sp.cy = st.cy; sp.cz = st.cz; sp.n_yc = st.n_yc; sp.n_zc = st.n_zc;
+  sp.BX = st.BX; sp.BY = st.BY; sp.BZ = st.BZ; sp.T = st.T;
+  sp.fp = st.d_fp; sp.legacy = st.n_legacy ? st.d_legacy : nullptr;
+  sp.inv_bytes = st.inv_bytes; sp.tile_bytes = st.tile_bytes; sp.stage_bytes = st.stage_bytes;
+  sp.inv_span = st.inv_span; sp.tile_span = st.tile_span;
+  sp.err = st.d_err;
+  if (tunables().stage_debug & 1) sp.f.fill_items = 0;
+  sp.debug = tunables().stage_debug;
+  cudaMemsetAsync(c->d_work, 0, 4 * sizeof(uint32_t), c->stream);
+  int rc;
+  switch (c->N) {
+    case 1: rc = launch_staged_n<1, 22>(c, sp, mode); break;
+    case 2: rc = launch_staged_n<2, 22>(c, sp, mode); break;
+    case 3: rc = launch_staged_n<3, 22>(c, sp, mode); break;
+    case 4: rc = launch_staged_n<4, 22>(c, sp, mode); break;
+    case 5: rc = launch_staged_n<5, 11>(c, sp, mode); break;
+    case 6: rc = launch_staged_n<6, 11>(c, sp, mode); break;
+    case 7: rc = launch_staged_n<7, 11>(c, sp, mode); break;
+    case 8: rc = launch_staged_n<8, 11>(c, sp, mode); break;
+    default: return fail(c, RR_ERR_UNSUPPORTED, "integrate: 1..8 sensors supported");
+  }
+  if (rc != RR_OK) return rc;
+  // bricks whose footprint exceeds the tile (close to a sensor, or outside its frustum) go through the direct kernel; it
+  // reads the same pair image from global memory
+  if (st.n_legacy) RR_TRY_RC(launch_bricks_masked(c, p, mode, st.d_legacy));
+  *done = true;
+  return RR_OK;
+}
+
+}  // namespace rr

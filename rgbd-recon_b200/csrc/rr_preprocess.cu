@@ -277,7 +277,8 @@ __global__ void __launch_bounds__(256) k_normal(const float2* __restrict__ depth
 // ------------------------------------------------------------------------------------------------ pre_quality
 // glsl/pre_quality.fs:65-119 (13x13 support count + range weights, pow 6, 1/(6.5 d), angle^2); :115's colour loop is dead.
 __global__ void __launch_bounds__(256) k_quality(const float2* __restrict__ depth_b, const float4* __restrict__ normals,
-                                                 float* __restrict__ out_quality, int W, int H,
+                                                 float* __restrict__ out_quality, const float* __restrict__ sil, float2* __restrict__ pairs,
+                                                 int pair_pitch, uint32_t* __restrict__ flags, int W, int H,
                                                  const __grid_constant__ SensorTables st) {
   // as in k_bilateral: samples outside (0, 1) are stored as +inf so that the range comparison alone rejects them
   __shared__ float tile[SM_H][SM_W];
@@ -295,7 +296,36 @@ __global__ void __launch_bounds__(256) k_quality(const float2* __restrict__ dept
   if (px >= W || py >= H) return;
   const size_t o = base + (size_t)py * W + px;
   const float depth = depth_b[o].x;
-  if ((depth <= 0.0f) || (depth >= 1.0f)) { out_quality[o] = 0.0f; return; }     // a NaN centre passes, as in the shader
+  // The pair image the staged integrator tiles into shared memory (rr_integrate_staged.cu): per pixel (depth_b.x, quality
+  // with the silhouette - exactly 0 or 1, pre_boundary.fs:88-108 - in the sign bit), one replicated border pixel on every
+  // side so that a CLAMP_TO_EDGE footprint is pixels (e, e+1) of the padded image. quality is never negative (a product
+  // of pow() results and positive divisors), so the sign bit is free; violations are counted in flags[0].
+  auto emit = [&](float q) {
+    out_quality[o] = q;
+    if (!pairs) return;
+    uint32_t bits = __float_as_uint(q);
+    if ((bits >> 31) && !(q != q) && q != 0.0f) atomicAdd(flags, 1u);
+    bits &= 0x7fffffffu;
+    if (sil[o] >= 1.0f) bits |= 0x80000000u;
+    const float2 v = make_float2(depth, __uint_as_float(bits));
+    float2* img = pairs + (size_t)layer * (H + 2) * pair_pitch;
+    const int xs0 = px + 1, xs1 = (px == 0) ? 0 : ((px == W - 1) ? W + 1 : -1);
+    const int ys0 = py + 1, ys1 = (py == 0) ? 0 : ((py == H - 1) ? H + 1 : -1);
+    img[(size_t)ys0 * pair_pitch + xs0] = v;
+    if (xs1 >= 0) img[(size_t)ys0 * pair_pitch + xs1] = v;
+    if (ys1 >= 0) img[(size_t)ys1 * pair_pitch + xs0] = v;
+    if (xs1 >= 0 && ys1 >= 0) img[(size_t)ys1 * pair_pitch + xs1] = v;
+    if (W == 1 && px == 0) {               // a one-pixel-wide image is its own left and right border
+      img[(size_t)ys0 * pair_pitch + 2] = v;
+      if (ys1 >= 0) img[(size_t)ys1 * pair_pitch + 2] = v;
+    }
+    if (H == 1 && py == 0) {
+      img[(size_t)2 * pair_pitch + xs0] = v;
+      if (xs1 >= 0) img[(size_t)2 * pair_pitch + xs1] = v;
+      if (W == 1) img[(size_t)2 * pair_pitch + 2] = v;
+    }
+  };
+  if ((depth <= 0.0f) || (depth >= 1.0f)) { emit(0.0f); return; }     // a NaN centre passes, as in the shader
   const float dist_range_max = 0.35f * (depth / 1.0f);
   const float dist_range_max_inv = 1.0f / dist_range_max;
   float w_range = 0.0f, border = 0.0f;
@@ -331,7 +361,7 @@ __global__ void __launch_bounds__(256) k_quality(const float2* __restrict__ dept
   const float3 cam = make_float3(st.cam[layer][0], st.cam[layer][1], st.cam[layer][2]);
   const float angle = dot3(normalize3(cam - world_pos), make_float3(n4.x, n4.y, n4.z));
   q *= gpow(angle, 2.0f);
-  out_quality[o] = q;
+  emit(q);
 }
 
 // ------------------------------------------------------------------------------------------------ gather texels
@@ -369,6 +399,7 @@ int launch_preprocess(rr_ctx* c, int filter_textures, int use_processed_depth, i
   const dim3 grd((W + TILE_X - 1) / TILE_X, (H + TILE_Y - 1) / TILE_Y, N);
   const SensorTables st = sensor_tables(c);
   cudaStream_t s = c->stream;
+  RR_TRY_RC(staged_prepare(c));            // decides which integrator the frame set is packed for (no-op unless settings changed)
   timer_begin(c, "1preprocess");
 
   timer_begin(c, "morph");
@@ -407,11 +438,16 @@ int launch_preprocess(rr_ctx* c, int filter_textures, int use_processed_depth, i
   timer_end(c, "normal");
 
   timer_begin(c, "quality");
-  k_quality<<<grd, blk, 0, s>>>(c->d_depth_b, c->d_normal, c->d_quality, W, H, st);
+  // The staged integrator reads the pair image k_quality writes on its way out; the 32-byte gather texels of the direct
+  // kernels (dense mode, configurations the staged kernel declines) cost one more pass and are built only when needed.
+  const bool staged = staged_selected(c);
+  k_quality<<<grd, blk, 0, s>>>(c->d_depth_b, c->d_normal, c->d_quality, c->d_sil, c->d_pairs, c->pair_pitch, c->d_flags, W, H, st);
   RR_LAUNCH_CHECK(c, "k_quality");
-  const dim3 grd_g((W + 1 + TILE_X - 1) / TILE_X, (H + 1 + TILE_Y - 1) / TILE_Y, N);
-  k_pack_gather<<<grd_g, blk, 0, s>>>(c->d_depth_b, c->d_quality, c->d_sil, c->d_gather, c->d_flags, W, H);
-  RR_LAUNCH_CHECK(c, "k_pack_gather");
+  if (!staged) {
+    const dim3 grd_g((W + 1 + TILE_X - 1) / TILE_X, (H + 1 + TILE_Y - 1) / TILE_Y, N);
+    k_pack_gather<<<grd_g, blk, 0, s>>>(c->d_depth_b, c->d_quality, c->d_sil, c->d_gather, c->d_flags, W, H);
+    RR_LAUNCH_CHECK(c, "k_pack_gather");
+  }
   timer_end(c, "quality");
 
   timer_end(c, "1preprocess");

@@ -90,6 +90,7 @@ def lib():
     L.rr_set_timing.argtypes = [vp, C.c_int]
     L.rr_get_stage_ms.argtypes = [vp, C.c_char_p, f32]
     L.rr_get_stage_stats.argtypes = [vp, C.c_char_p, f32, u32]
+    L.rr_integrator_info.argtypes = [vp, u32]
     L.rr_launch_count.argtypes = [vp]
     L.rr_launch_count.restype = C.c_uint64
     L.rr_version.restype = C.c_int
@@ -379,6 +380,14 @@ class Fusion:
         ms = C.c_float()
         self._ck(self.L.rr_get_stage_ms(self.h, name.encode(), C.byref(ms)))
         return float(ms.value)
+
+    def integrator_info(self):
+        """rr_integrator_info as a dict (which integrator bricks mode runs, staged geometry, device flags)."""
+        out = np.zeros(16, np.uint32)
+        self._ck(self.L.rr_integrator_info(self.h, _u32(out)))
+        keys = ("staged", "tile", "box_x", "box_y", "box_z", "ychunk", "zchunk", "n_ychunks", "n_zchunks", "legacy_bricks",
+                "smem_bytes", "consumer_warps", "fill_warps", "flags")
+        return {k: int(v) for k, v in zip(keys, out)}
 
     def launch_count(self):
         return int(self.L.rr_launch_count(self.h))

@@ -29,6 +29,10 @@ for l in lines[start + 1:]:
         addr2line[int(m.group(1), 16)] = cur
 rows = list(csv.reader(open(src_csv)))
 hdr, data = rows[1], rows[2:]
+for i, r in enumerate(data):            # several captured launches: keep the first one's table
+    if r and r[0] == "Kernel Name":
+        data = data[:i]
+        break
 ia, ins, iex = hdr.index("Address"), hdr.index("# Samples"), hdr.index("Instructions Executed")
 base = int(data[0][ia], 16)
 by, bys = collections.Counter(), collections.Counter()

@@ -17,7 +17,8 @@ sys.path.insert(0, os.path.join(ROOT, "rgbd-recon_b200"))
 import bench  # noqa: E402
 from rrpy import capi  # noqa: E402
 
-DEFAULTS = dict(fused=1, zchunk=13, fill_rows=16, fill_warps=2, ctas=2, threads=512, chunk=1, ldg256=1)
+DEFAULTS = dict(fused=1, zchunk=13, fill_rows=16, fill_warps=2, ctas=2, threads=512, chunk=1, ldg256=1,
+                staged=1, stage_zchunk=9, stage_ychunk=0, stage_tile=0, stage_fwarps=2, stage_fill_rows=16, stage_debug=0)
 
 
 def main():
@@ -34,8 +35,13 @@ def main():
             if item:
                 k, v = item.split("=")
                 kv[k] = int(v)
+        # non-tunable keys: min_voxels (occupancy threshold; huge = empty occupied list = pure clear), z0/z1 (slab)
+        mv = kv.pop("min_voxels", bench.MIN_VOX)
+        z0, z1 = kv.pop("z0", 0), kv.pop("z1", bench.R)
         for k, v in kv.items():
             capi.set_tunable(k, v)
+        fu.configure(limit=bench.LIMIT, voxel_size=voxel, brick_size=bench.BRICK, min_voxels=mv, use_bricks=True)
+        fu.set_slab(z0, z1)
         for _ in range(5):
             fu.frame()
         fu.synchronize()
@@ -50,7 +56,8 @@ def main():
         h = hashlib.sha1(fu.download_tsdf().tobytes()).hexdigest()[:12]
         if ref_hash is None:
             ref_hash = h
-        print(json.dumps({"config": spec, "integrate_ms": round(ms / n, 5), "preprocess_ms": round(pms / max(1, pn), 5),
+        info = fu.integrator_info()
+        print(json.dumps({"config": spec, "integrator": info, "integrate_ms": round(ms / n, 5), "preprocess_ms": round(pms / max(1, pn), 5),
                           "tsdf_sha1": h, "same_as_first": h == ref_hash}), flush=True)
     fu.close()
 
