@@ -2,7 +2,7 @@
 // (framework/reconstruction/recon_integration.cpp:272-278, 431-446) without the GPU->CPU->GPU round trip.
 // The occupied list must equal the CPU loop's order (ascending brick id), so the compaction is an ORDERED
 // ballot + prefix scan by a single 1024-thread block (a brick grid is ~10^4 counters: one block is latency-optimal).
-#include "rr_context.h"
+#include "rr_integrate.cuh"
 
 namespace rr {
 
@@ -52,8 +52,21 @@ __global__ void __launch_bounds__(1024) k_bricks_update(const uint32_t* __restri
                                                         uint32_t rz, uint32_t min_voxels, const int32_t* __restrict__ ranges, int mask_words,
                                                         uint32_t* __restrict__ occupied, uint32_t* __restrict__ num_occupied,
                                                         uint8_t* __restrict__ near_occ, uint8_t* __restrict__ occ_mask,
-                                                        uint32_t* __restrict__ rowmask, uint8_t* __restrict__ rowany) {
-  if (blockIdx.x == 0) { bricks_compact_block(counters, num_bricks, min_voxels, occupied, num_occupied); return; }
+                                                        uint32_t* __restrict__ rowmask, uint8_t* __restrict__ rowany,
+                                                        uint32_t* __restrict__ work, uint32_t mask_blocks, const __grid_constant__ ClassifyParams cq) {
+  if (blockIdx.x == 0) {
+    if (threadIdx.x < 4) work[threadIdx.x] = 0;          // work counters of the persistent integrators (this frame's launch)
+    bricks_compact_block(counters, num_bricks, min_voxels, occupied, num_occupied);
+    return;
+  }
+  if (blockIdx.x > mask_blocks) {
+    // verdict blocks (staged integrator): one warp per work item of every brick, idle unless the brick is occupied
+    const uint32_t w = (blockIdx.x - 1 - mask_blocks) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t brick = w / (uint32_t)cq.per_brick;
+    if (brick >= num_bricks || counters[brick] < min_voxels) return;
+    classify_item(cq, brick, w - brick * (uint32_t)cq.per_brick, threadIdx.x & 31);
+    return;
+  }
   if (near_occ == nullptr) return;
   const uint32_t i = (blockIdx.x - 1) * blockDim.x + threadIdx.x;
   if (i < rx * ry * rz) {
@@ -94,9 +107,16 @@ int launch_bricks_update(rr_ctx* c) {
   const bool grid_ok = nb == c->bricks.res[0] * c->bricks.res[1] * c->bricks.res[2];
   const uint32_t rows_words = (grid_ok && c->fused_ok) ? c->bricks.res[1] * c->bricks.res[2] * (uint32_t)c->mask_words : 0u;
   const uint32_t threads = grid_ok ? (nb > rows_words ? nb : rows_words) : 0u;
-  k_bricks_update<<<1 + (threads + 1023) / 1024, 1024, 0, c->stream>>>(
+  const uint32_t mask_blocks = (threads + 1023) / 1024;
+  // the staged integrator's per-frame verdicts ride along (the pair image is complete: k_quality ran before this)
+  ClassifyParams cq{};
+  RR_TRY_RC(staged_prepare(c));
+  const bool classify = staged_classify_params(c, cq);
+  const uint32_t cls_blocks = classify ? (nb * (uint32_t)cq.per_brick + 31u) / 32u : 0u;
+  k_bricks_update<<<1 + mask_blocks + cls_blocks, 1024, 0, c->stream>>>(
       c->d_counters, nb, c->bricks.res[0], c->bricks.res[1], c->bricks.res[2], c->cfg.min_voxels_per_brick, c->d_ranges, c->mask_words,
-      c->d_occupied, c->d_num_occ, grid_ok ? c->d_near_occ : nullptr, c->d_occ_mask, (grid_ok && c->fused_ok) ? c->d_rowmask : nullptr, c->d_rowany);
+      c->d_occupied, c->d_num_occ, grid_ok ? c->d_near_occ : nullptr, c->d_occ_mask, (grid_ok && c->fused_ok) ? c->d_rowmask : nullptr, c->d_rowany,
+      c->d_work, mask_blocks, cq);
   RR_LAUNCH_CHECK(c, "k_bricks_update");
   cudaError_t e = cudaMemcpyAsync(c->h_num_occ, c->d_num_occ, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
   return check(c, e, "bricks count copy");

@@ -146,9 +146,11 @@ struct rr_ctx {
     int T = 0;                     // pair-image tile edge staged per item and sensor (pixels, even)
     int cwarps = 0, fwarps = 0;    // consumer / fill warps per CTA
     uint32_t inv_bytes = 0, tile_bytes = 0, inv_span = 0, tile_span = 0, stage_bytes = 0, smem_bytes = 0;
-    uint32_t* d_fp = nullptr;      // [items][N]: tile origin tx0 | ty0 << 16
-    uint8_t* d_legacy = nullptr;   // [num_bricks]: 1 = a footprint of this brick exceeds the tile, left to k_integrate_bricks
+    uint2* d_fp = nullptr;         // [items][N]: tile origin tx0 | ty0 << 16, footprint rectangle inside the tile
+    uint8_t* d_legacy = nullptr;   // [num_bricks]: 1 = a footprint of this brick exceeds the tile: evaluated from global memory
     uint32_t n_legacy = 0;         // bricks flagged in d_legacy
+    float2* d_zr = nullptr;        // [items][N]: exact range of pos_calib.z over the item (k_footprints)
+    uint32_t* d_cls = nullptr;     // [items]: this frame's per-sensor verdicts (k_classify)
     uint32_t* d_err = nullptr;     // [4] device-side consistency flags (must stay 0)
     CUtensorMap map_inv, map_pairs;
   } sti;
@@ -191,6 +193,7 @@ struct Tunables {
   int stage_tile = 0;   // pair-image tile edge in pixels (0: chosen from the footprint statistics and the smem budget)
   int stage_fwarps = 2; // fill warps per CTA
   int stage_fill_rows = 16;   // voxel rows per fill item
+  int stage_cwarps = 0; // consumer warps per CTA: 0 = 22 up to four sensors (80 registers), 11 = half of that at 144 registers
   int stage_debug = 0;  // measurement only, results are WRONG: bit 0 skips the clear stream, bit 1 the brick evaluation
   unsigned generation = 0;   // bumped by every rr_set_tunable (invalidates captured graphs)
 };

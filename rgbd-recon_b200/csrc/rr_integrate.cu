@@ -29,106 +29,6 @@ __global__ void k_build_ztab(float4* __restrict__ ztab, int Z, int IZ) {
   ztab[z] = make_float4(__int_as_float(k0), __int_as_float(k1), g, 1.0f - g);
 }
 
-// One 32-byte gather texel with a single 256-bit load (LDG.E.256, sm_100+): half the load instructions and L1 requests
-// of two LDG.128 on the same sector.
-__device__ __forceinline__ void ldg_texel(const float4* p, float4& lo, float4& hi) {
-  asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
-               : "l"(p));
-}
-
-// One sensor's lookup for one voxel: bilinear weights, interpolated depth coordinate and the 32-byte gather texel.
-struct Tap {
-  float wa, wb, d;
-  float4 lo, hi;
-};
-
-// One (x, y) column, z in [zb, ze). All index arithmetic is 32-bit (sizes are validated on the host).
-// z (hence the coarse plane pair) is uniform across a warp wherever the callers keep a warp inside one brick / one
-// dense tile, so the plane-advance branches below do not diverge.
-template <int N, int MODE, bool PAIRS = false>
-__device__ __forceinline__ void march_column(const IntegrateParams& p, int x, int y, int zb, int ze) {
-  const float stepX = 1.0f / (float)p.X, stepY = 1.0f / (float)p.Y;
-  const float px = ((float)x + 0.5f) * stepX, py = ((float)y + 0.5f) * stepY;
-  int x0, x1, y0, y1; float a, b;
-  lin_coord(px, p.IX, x0, x1, a);
-  lin_coord(py, p.IY, y0, y1, b);
-  const float oma = 1.0f - a, omb = 1.0f - b;            // lerp(v0, v1, t) = fma(t, v1, (1 - t) * v0)
-  const unsigned o00 = y0 * p.IX + x0, o10 = y0 * p.IX + x1, o01 = y1 * p.IX + x0, o11 = y1 * p.IX + x1;
-  const unsigned plane_sz = (unsigned)(p.IX * p.IY);
-  const unsigned gstride = (unsigned)((p.W + 1) * (p.H + 1) * 2);
-  const unsigned grow = (unsigned)(p.W + 1);
-  const float limit = p.limit, neg_limit = -p.limit;
-  float3 A[N], B[N];
-  int ck0 = -1, ck1 = -1;
-
-  auto plane = [&](int s, int k) -> float3 {
-    const float4* base = p.inv + (unsigned)(s * p.IZ + k) * plane_sz;
-    const float4 p00 = __ldg(base + o00), p10 = __ldg(base + o10), p01 = __ldg(base + o01), p11 = __ldg(base + o11);
-    return plane_reduce(p00, p10, p01, p11, a, oma, b, omb);
-  };
-
-  unsigned o = (unsigned)((zb * p.Y + y) * p.X + x);
-  const unsigned ostep = (unsigned)(p.X * p.Y);
-  for (int z = zb; z < ze; ++z, o += ostep) {
-    const float4 zt = __ldg(p.ztab + z);
-    const int k0 = __float_as_int(zt.x), k1 = __float_as_int(zt.y);
-    const float g = zt.z, omg = zt.w;
-    if (k0 != ck0) {
-      if (k0 == ck1) {
-#pragma unroll
-        for (int s = 0; s < N; ++s) A[s] = B[s];
-      } else {
-#pragma unroll
-        for (int s = 0; s < N; ++s) A[s] = plane(s, k0);
-      }
-      ck0 = k0;
-    }
-    if (k1 != ck1) {
-      if (k1 == k0) {
-#pragma unroll
-        for (int s = 0; s < N; ++s) B[s] = A[s];
-      } else {
-#pragma unroll
-        for (int s = 0; s < N; ++s) B[s] = plane(s, k1);
-      }
-      ck1 = k1;
-    }
-    float weighted_tsd = limit, total_weight = 0.0f;
-
-    // z filter tap, bilinear footprint (silhouette, quality) at (u, v) and the gather loads for sensor s
-    auto fetch = [&](int s) -> Tap {
-      Tap t;
-      int ex, ey;
-      tap_coords(A[s], B[s], g, omg, p.fW, p.fH, p.exmax, p.eymax, t.wa, t.wb, t.d, ex, ey);
-      ex += 1; ey += 1;
-      if (PAIRS) {
-        // the pair image the staged integrator tiles (same taps, 8 bytes per pixel): footprint (ex, ey) = pixels ex, ex+1 of rows ey, ey+1
-        const float2* q = p.pairs + ((unsigned)(s * (p.H + 2) + ey) * (unsigned)p.pair_pitch + (unsigned)ex);
-        const float2 t00 = __ldg(q), t10 = __ldg(q + 1), t01 = __ldg(q + p.pair_pitch), t11 = __ldg(q + p.pair_pitch + 1);
-        t.lo = make_float4(t00.x, t10.x, t01.x, t11.x);
-        t.hi = make_float4(t00.y, t10.y, t01.y, t11.y);
-        return t;
-      }
-      const float4* g4 = p.gather + ((unsigned)s * gstride + ((unsigned)ey * grow + (unsigned)ex) * 2u);
-      if (p.wide_loads) ldg_texel(g4, t.lo, t.hi); else { t.lo = __ldg(g4); t.hi = __ldg(g4 + 1); }
-      return t;
-    };
-    auto fuse = [&](const Tap& t) {
-      fuse_tap(t.wa, t.wb, t.d, t.lo.x, t.lo.y, t.lo.z, t.lo.w, t.hi.x, t.hi.y, t.hi.z, t.hi.w, limit, neg_limit, weighted_tsd, total_weight);
-    };
-    // two sensors' gathers are in flight before the first decision chain runs
-#pragma unroll
-    for (int s = 0; s + 1 < N; s += 2) {
-      const Tap t0 = fetch(s), t1 = fetch(s + 1);
-      fuse(t0);
-      fuse(t1);
-    }
-    if (N & 1) { const Tap t = fetch(N - 1); fuse(t); }
-    store_voxel<MODE>(p, o, weighted_tsd, total_weight);
-  }
-}
-
 template <int N, int MODE>
 __global__ void __launch_bounds__(256) k_integrate_dense(const __grid_constant__ IntegrateParams p) {
   const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
@@ -144,8 +44,8 @@ __global__ void __launch_bounds__(256) k_integrate_dense(const __grid_constant__
 // Bricks may overlap or leave one-voxel gaps (float rounding in divideBox/containedVoxels): overlapping voxels are
 // written twice with the same value, gaps keep the cleared -limit.
 #define BRICK_MAX_THREADS 320
-template <int N, int MODE, int MINB, bool PAIRS>
-__global__ void __launch_bounds__(BRICK_MAX_THREADS, MINB) k_integrate_bricks(const __grid_constant__ IntegrateParams p, int max_cols, int max_nz, int BRICK_ZCHUNK, const uint8_t* __restrict__ only) {
+template <int N, int MODE, int MINB>
+__global__ void __launch_bounds__(BRICK_MAX_THREADS, MINB) k_integrate_bricks(const __grid_constant__ IntegrateParams p, int max_cols, int max_nz, int BRICK_ZCHUNK) {
   const unsigned n_occ = *p.num_occupied;
   const unsigned col_blocks = ((unsigned)max_cols + blockDim.x - 1u) / blockDim.x;
   const unsigned z_blocks = (unsigned)(max_nz + BRICK_ZCHUNK - 1) / BRICK_ZCHUNK;
@@ -154,16 +54,14 @@ __global__ void __launch_bounds__(BRICK_MAX_THREADS, MINB) k_integrate_bricks(co
   for (unsigned w = blockIdx.x; w < items; w += gridDim.x) {
     const unsigned b = w / per_brick, r = w - b * per_brick;
     const unsigned zc = r / col_blocks, cc = r - zc * col_blocks;
-    const uint32_t brick = p.occupied[b];
-    if (only && !only[brick]) continue;         // `only`: the bricks the staged integrator left to this kernel
-    const int32_t* rg = p.ranges + (size_t)brick * 6;
+    const int32_t* rg = p.ranges + (size_t)p.occupied[b] * 6;
     const int x0 = rg[0], nx = rg[1] - rg[0], y0 = rg[2], ny = rg[3] - rg[2];
     const int zb = max(rg[4] + (int)zc * BRICK_ZCHUNK, p.z_begin);
     const int ze = min(min(rg[4] + (int)(zc + 1) * BRICK_ZCHUNK, rg[5]), p.z_end);
     const int ci = (int)(cc * blockDim.x + threadIdx.x);
     if (zb >= ze || ci >= nx * ny) continue;
     const int cy = ci / nx, cx = ci - cy * nx;
-    march_column<N, MODE, PAIRS>(p, x0 + cx, y0 + cy, zb, ze);
+    march_column<N, MODE>(p, x0 + cx, y0 + cy, zb, ze);
   }
 }
 
@@ -314,9 +212,8 @@ static void brick_extents(const rr_ctx* c, int& max_cols, int& max_nz) {
   }
 }
 
-// k_integrate_bricks over the occupied bricks (`only` != nullptr: just those flagged in the per-brick mask)
 template <int N>
-static int launch_bricks_n(rr_ctx* c, const IntegrateParams& p, int mode, const uint8_t* only) {
+static int launch_bricks_n(rr_ctx* c, const IntegrateParams& p, int mode) {
   int max_cols, max_nz;
   brick_extents(c, max_cols, max_nz);
   if (max_cols == 0 || max_nz == 0) return RR_OK;
@@ -329,32 +226,11 @@ static int launch_bricks_n(rr_ctx* c, const IntegrateParams& p, int mode, const 
   }
   const int zchunk = 9;
   const dim3 grd(148 * std::max(1, tunables().brick_grid), 1, 1);
-  // the masked launch serves the staged integrator, whose frames carry the pair image instead of the gather texels
-  if (only) {
-    if (mode == 1) k_integrate_bricks<N, 1, 2, true><<<grd, threads, 0, c->stream>>>(p, max_cols, max_nz, zchunk, only);
-    else if (mode == 2) k_integrate_bricks<N, 2, 2, true><<<grd, threads, 0, c->stream>>>(p, max_cols, max_nz, zchunk, only);
-    else k_integrate_bricks<N, 0, 2, true><<<grd, threads, 0, c->stream>>>(p, max_cols, max_nz, zchunk, only);
-  } else {
-    if (mode == 1) k_integrate_bricks<N, 1, 2, false><<<grd, threads, 0, c->stream>>>(p, max_cols, max_nz, zchunk, only);
-    else if (mode == 2) k_integrate_bricks<N, 2, 2, false><<<grd, threads, 0, c->stream>>>(p, max_cols, max_nz, zchunk, only);
-    else k_integrate_bricks<N, 0, 2, false><<<grd, threads, 0, c->stream>>>(p, max_cols, max_nz, zchunk, only);
-  }
+  if (mode == 1) k_integrate_bricks<N, 1, 2><<<grd, threads, 0, c->stream>>>(p, max_cols, max_nz, zchunk);
+  else if (mode == 2) k_integrate_bricks<N, 2, 2><<<grd, threads, 0, c->stream>>>(p, max_cols, max_nz, zchunk);
+  else k_integrate_bricks<N, 0, 2><<<grd, threads, 0, c->stream>>>(p, max_cols, max_nz, zchunk);
   RR_LAUNCH_CHECK(c, "k_integrate_bricks");
   return RR_OK;
-}
-
-int launch_bricks_masked(rr_ctx* c, const IntegrateParams& p, int mode, const uint8_t* only) {
-  switch (c->N) {
-    case 1: return launch_bricks_n<1>(c, p, mode, only);
-    case 2: return launch_bricks_n<2>(c, p, mode, only);
-    case 3: return launch_bricks_n<3>(c, p, mode, only);
-    case 4: return launch_bricks_n<4>(c, p, mode, only);
-    case 5: return launch_bricks_n<5>(c, p, mode, only);
-    case 6: return launch_bricks_n<6>(c, p, mode, only);
-    case 7: return launch_bricks_n<7>(c, p, mode, only);
-    case 8: return launch_bricks_n<8>(c, p, mode, only);
-  }
-  return fail(c, RR_ERR_UNSUPPORTED, "integrate: 1..8 sensors supported");
 }
 
 template <int N>
@@ -391,7 +267,7 @@ static int launch_n(rr_ctx* c, const IntegrateParams& p, bool bricks, int mode, 
       RR_LAUNCH_CHECK(c, "k_integrate_fused");
       return RR_OK;
     }
-    return launch_bricks_n<N>(c, p, mode, nullptr);
+    return launch_bricks_n<N>(c, p, mode);
   } else {
     const int nz = p.z_end - p.z_begin;
     const dim3 grd((p.X + 31) / 32, (p.Y + 7) / 8, (nz + p.z_chunk - 1) / p.z_chunk);
@@ -422,6 +298,7 @@ int launch_integrate(rr_ctx* c) {
   p.IX = (int)c->ires[0]; p.IY = (int)c->ires[1]; p.IZ = (int)c->ires[2];
   p.W = c->W; p.H = c->H; p.X = (int)c->res[0]; p.Y = (int)c->res[1]; p.Z = (int)c->res[2];
   p.z_begin = (int)c->slab_z0; p.z_end = (int)c->slab_z1;
+  p.plane_elems = (unsigned)(c->res[0] * c->res[1]);
   if (c->slab_z0 > 0 || c->slab_z1 < c->res[2]) {
     // a slab owner also computes a read-only halo: the raymarcher's refinement and gradient taps reach at most
     // 2 * (limit/2) * Z voxels (+1 for the trilinear tap) past the owned samples; integration is pure, so the halo is

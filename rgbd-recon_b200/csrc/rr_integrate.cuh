@@ -25,6 +25,7 @@ struct IntegrateParams {
   int IX, IY, IZ, W, H, X, Y, Z;
   float fW, fH, exmax, eymax;   // (float)W, (float)H, (float)(W-1), (float)(H-1)
   int z_begin, z_end;     // slab
+  unsigned plane_elems;   // X * Y
   int z_chunk;
   float limit;
   int wide_loads;         // tunable ldg256: gather texels with one 256-bit load
@@ -114,6 +115,106 @@ __device__ __forceinline__ void store_voxel(const IntegrateParams& p, unsigned o
   } else {
     p.tsdf[o] = weighted_tsd;
     if (MODE == 1) p.weight[o] = total_weight;
+  }
+}
+
+// One 32-byte gather texel with a single 256-bit load (LDG.E.256, sm_100+): half the load instructions and L1 requests
+// of two LDG.128 on the same sector.
+__device__ __forceinline__ void ldg_texel(const float4* p, float4& lo, float4& hi) {
+  asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
+               : "l"(p));
+}
+
+// One sensor's lookup for one voxel: bilinear weights, interpolated depth coordinate and the 32-byte gather texel.
+struct GatherTap {
+  float wa, wb, d;
+  float4 lo, hi;
+};
+
+// One (x, y) column, z in [zb, ze). All index arithmetic is 32-bit (sizes are validated on the host).
+// z (hence the coarse plane pair) is uniform across a warp wherever the callers keep a warp inside one brick / one
+// dense tile, so the plane-advance branches below do not diverge.
+template <int N, int MODE, bool PAIRS = false>
+__device__ __forceinline__ void march_column(const IntegrateParams& p, int x, int y, int zb, int ze) {
+  const float stepX = 1.0f / (float)p.X, stepY = 1.0f / (float)p.Y;
+  const float px = ((float)x + 0.5f) * stepX, py = ((float)y + 0.5f) * stepY;
+  int x0, x1, y0, y1; float a, b;
+  lin_coord(px, p.IX, x0, x1, a);
+  lin_coord(py, p.IY, y0, y1, b);
+  const float oma = 1.0f - a, omb = 1.0f - b;            // lerp(v0, v1, t) = fma(t, v1, (1 - t) * v0)
+  const unsigned o00 = y0 * p.IX + x0, o10 = y0 * p.IX + x1, o01 = y1 * p.IX + x0, o11 = y1 * p.IX + x1;
+  const unsigned plane_sz = (unsigned)(p.IX * p.IY);
+  const unsigned gstride = (unsigned)((p.W + 1) * (p.H + 1) * 2);
+  const unsigned grow = (unsigned)(p.W + 1);
+  const float limit = p.limit, neg_limit = -p.limit;
+  float3 A[N], B[N];
+  int ck0 = -1, ck1 = -1;
+
+  auto plane = [&](int s, int k) -> float3 {
+    const float4* base = p.inv + (unsigned)(s * p.IZ + k) * plane_sz;
+    const float4 p00 = __ldg(base + o00), p10 = __ldg(base + o10), p01 = __ldg(base + o01), p11 = __ldg(base + o11);
+    return plane_reduce(p00, p10, p01, p11, a, oma, b, omb);
+  };
+
+  unsigned o = (unsigned)((zb * p.Y + y) * p.X + x);
+  const unsigned ostep = (unsigned)(p.X * p.Y);
+  for (int z = zb; z < ze; ++z, o += ostep) {
+    const float4 zt = __ldg(p.ztab + z);
+    const int k0 = __float_as_int(zt.x), k1 = __float_as_int(zt.y);
+    const float g = zt.z, omg = zt.w;
+    if (k0 != ck0) {
+      if (k0 == ck1) {
+#pragma unroll
+        for (int s = 0; s < N; ++s) A[s] = B[s];
+      } else {
+#pragma unroll
+        for (int s = 0; s < N; ++s) A[s] = plane(s, k0);
+      }
+      ck0 = k0;
+    }
+    if (k1 != ck1) {
+      if (k1 == k0) {
+#pragma unroll
+        for (int s = 0; s < N; ++s) B[s] = A[s];
+      } else {
+#pragma unroll
+        for (int s = 0; s < N; ++s) B[s] = plane(s, k1);
+      }
+      ck1 = k1;
+    }
+    float weighted_tsd = limit, total_weight = 0.0f;
+
+    // z filter tap, bilinear footprint (silhouette, quality) at (u, v) and the gather loads for sensor s
+    auto fetch = [&](int s) -> GatherTap {
+      GatherTap t;
+      int ex, ey;
+      tap_coords(A[s], B[s], g, omg, p.fW, p.fH, p.exmax, p.eymax, t.wa, t.wb, t.d, ex, ey);
+      ex += 1; ey += 1;
+      if (PAIRS) {
+        // the pair image the staged integrator tiles (same taps, 8 bytes per pixel): footprint (ex, ey) = pixels ex, ex+1 of rows ey, ey+1
+        const float2* q = p.pairs + ((unsigned)(s * (p.H + 2) + ey) * (unsigned)p.pair_pitch + (unsigned)ex);
+        const float2 t00 = __ldg(q), t10 = __ldg(q + 1), t01 = __ldg(q + p.pair_pitch), t11 = __ldg(q + p.pair_pitch + 1);
+        t.lo = make_float4(t00.x, t10.x, t01.x, t11.x);
+        t.hi = make_float4(t00.y, t10.y, t01.y, t11.y);
+        return t;
+      }
+      const float4* g4 = p.gather + ((unsigned)s * gstride + ((unsigned)ey * grow + (unsigned)ex) * 2u);
+      if (p.wide_loads) ldg_texel(g4, t.lo, t.hi); else { t.lo = __ldg(g4); t.hi = __ldg(g4 + 1); }
+      return t;
+    };
+    auto fuse = [&](const GatherTap& t) {
+      fuse_tap(t.wa, t.wb, t.d, t.lo.x, t.lo.y, t.lo.z, t.lo.w, t.hi.x, t.hi.y, t.hi.z, t.hi.w, limit, neg_limit, weighted_tsd, total_weight);
+    };
+    // two sensors' gathers are in flight before the first decision chain runs
+#pragma unroll
+    for (int s = 0; s + 1 < N; s += 2) {
+      const GatherTap t0 = fetch(s), t1 = fetch(s + 1);
+      fuse(t0);
+      fuse(t1);
+    }
+    if (N & 1) { const GatherTap t = fetch(N - 1); fuse(t); }
+    store_voxel<MODE>(p, o, weighted_tsd, total_weight);
   }
 }
 
@@ -225,12 +326,61 @@ __device__ __forceinline__ void fill_loop(const FusedParams& p, int lane) {
   }
 }
 
+// ---- per-frame verdicts of the staged integrator ---------------------------------------------------------------------
+// One warp per work item (brick x y-chunk x z-chunk) of an occupied brick: per sensor, scan the footprint rectangle of the
+// item in the pair image (are all silhouette taps 1, what is the range of depth_b.x) and compare with the item's exact range
+// of pos_calib.z (k_footprints): sdist = pos_calib.z - depth is monotone in both operands and rounding is monotone, so
+//   zlo - dmax >= limit  =>  sdist >= limit for every voxel of the item   (tsdf_integration.vs:45: nothing happens)
+//   zhi - dmin <= -limit =>  sdist <= -limit for every voxel              (:41: weighted_tsd = -limit)
+// and with every silhouette tap 1 the silhouette test (:32) never fires. Such (item, sensor) pairs need no per-voxel work.
+// Returns skip mask | front mask << 8. Non-finite values keep a sensor on the voxel-by-voxel path (NaN patterns unchanged).
+struct ClassifyParams {
+  const uint2* fp;          // [items][N]: tile origin tx0 | ty0 << 16, footprint rectangle x offset | width << 8 | height << 20
+  const float2* zr;         // [items][N]: exact range of pos_calib.z over the item
+  const float2* pairs; int pair_pitch, H2;
+  const uint8_t* legacy;    // [bricks] or nullptr: bricks evaluated from global memory (no verdicts)
+  uint32_t* cls;            // [items] out
+  int per_brick, N;
+  float limit;
+};
+
+__device__ __forceinline__ void classify_item(const ClassifyParams& q, uint32_t brick, uint32_t sub, int lane) {
+  if (q.legacy && q.legacy[brick]) return;
+  const size_t item = (size_t)brick * q.per_brick + sub;
+  const float inf = __int_as_float(0x7f800000);
+  uint32_t skip = 0, front = 0;
+#pragma unroll 1
+  for (int s = 0; s < q.N; ++s) {
+    const uint2 f = q.fp[item * q.N + s];
+    const float2 z = q.zr[item * q.N + s];
+    const int rw = (int)((f.y >> 8) & 4095u), rh = (int)(f.y >> 20);
+    if (rw * rh == 0 || !(z.x <= z.y)) continue;
+    const float2* img = q.pairs + ((size_t)s * q.H2 + (f.x >> 16)) * q.pair_pitch + (f.x & 0xffffu) + (f.y & 255u);
+    float dlo = inf, dhi = -inf;
+    bool ok = true;
+    for (int i = lane; i < rw * rh; i += 32) {
+      const int ty = i / rw, tx = i - ty * rw;
+      const float2 t = __ldg(img + (size_t)ty * q.pair_pitch + tx);
+      ok = ok && ((int)__float_as_uint(t.y) < 0) && (fabsf(t.x) < inf);
+      dlo = fminf(dlo, t.x); dhi = fmaxf(dhi, t.x);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      dlo = fminf(dlo, __shfl_xor_sync(0xffffffffu, dlo, d)); dhi = fmaxf(dhi, __shfl_xor_sync(0xffffffffu, dhi, d));
+    }
+    if (!__all_sync(0xffffffffu, ok)) continue;
+    if (z.x - dhi >= q.limit) skip |= 1u << s;
+    else if (z.y - dlo <= -q.limit) front |= 1u << s;
+  }
+  if (lane == 0) q.cls[item] = skip | (front << 8);
+}
+
 // The cleared voxel as the 4 bytes the fill stores write: -limit (R32F), or half2(-limit, 0) for half2 voxels.
 float cleared_voxel(int mode, float limit);
 // fills the clear-stream half of FusedParams for the current slab (row range, item count, masks)
 void setup_fill(const rr_ctx* c, const IntegrateParams& p, int mode, int fill_rows, FusedParams& f);
-// k_integrate_bricks over the occupied bricks flagged in the per-brick mask `only` (nullptr: all of them)
-int launch_bricks_masked(rr_ctx* c, const IntegrateParams& p, int mode, const uint8_t* only);
+// classification parameters of the current configuration; false when the staged integrator is not selected
+bool staged_classify_params(const rr_ctx* c, ClassifyParams& q);
 // staged (TMA) integrator: returns RR_OK and sets *done = true when it handled the launch
 int launch_integrate_staged(rr_ctx* c, const IntegrateParams& p, int mode, bool* done);
 

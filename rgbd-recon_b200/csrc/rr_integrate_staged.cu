@@ -28,8 +28,9 @@ struct StagedParams {
   FusedParams f;            // integrate parameters + clear stream
   int cy, cz, n_yc, n_zc;   // work item = brick x y-chunk x z-chunk (voxels per chunk, chunks per brick)
   int BX, BY, BZ, T;        // staged inverse-volume box (coarse texels) and pair-image tile edge (pixels)
-  const uint32_t* fp;       // [bricks * n_yc * n_zc][N]: tile origin tx0 | ty0 << 16
-  const uint8_t* legacy;    // [bricks]: 1 = left to k_integrate_bricks (a footprint exceeds the tile); may be nullptr
+  const uint2* fp;          // [bricks * n_yc * n_zc][N]: .x = tile origin tx0 | ty0 << 16, .y = footprint rectangle (ItemHdr::rect)
+  const uint8_t* legacy;    // [bricks]: 1 = a footprint exceeds the tile: evaluated from global memory (march_column); may be nullptr
+  const uint32_t* cls;      // [bricks * n_yc * n_zc]: this frame's per-sensor verdicts (k_classify): skip | front << 8
   uint32_t inv_bytes, tile_bytes;    // bytes one item's copies deliver (box, one tile)
   uint32_t inv_span, tile_span, stage_bytes;   // smem regions: TMA destinations are 128-byte aligned
   uint32_t* err;            // [0] box overflow, [1] barrier time-out
@@ -38,11 +39,17 @@ struct StagedParams {
 
 // first 128 bytes of a stage, written by the producer before it arms the stage's full barrier
 struct ItemHdr {
-  int valid;                // 0: no more items
+  int valid;                // 0: no more items, 1: staged item, 2: direct item (operands stay in global memory)
   int x0, nx, y0, ny, zb, ze;
   int ixlo, iylo, izlo;     // origin of the staged inverse-volume box
-  uint32_t pad[2];
-  uint32_t tb[RR_MAX_SENSORS];   // byte offset (from the dynamic smem base) of pair texel (0, 0) of sensor s: tile start - tile origin
+  int nbx, nby, nbz;        // ... and the part of it this item uses
+  // Per-sensor verdict of k_classify for this frame: bit s of `skip` = every voxel of the
+  // item lies at least `limit` behind everything sensor s sees in its footprint (tsdf_integration.vs:45 "do nothing"), bit s
+  // of `front` = at least `limit` in front of it (:41 weighted_tsd = -limit); neither = evaluate voxel by voxel.
+  uint32_t skip, front;
+  uint32_t pad;
+  uint32_t tb[RR_MAX_SENSORS];   // byte offset (from the dynamic smem base) of pair texel (-1, -1) of sensor s: tile start - tile origin
+  uint32_t rect[RR_MAX_SENSORS]; // footprint rectangle inside the tile: x offset | width << 8 | height << 20 (pixels)
 };
 // stage layout: [0,128) ItemHdr | [128, 128 + 16*ZT_MAX) the item's slice of the z table | inverse-volume box | N pair tiles
 #define ITEM_HDR_BYTES 128
@@ -108,39 +115,43 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 //   inverse-volume corners: float4 at inv_off + ((s*BZ + k-izlo)*BY + y-iylo)*BX + x-ixlo
 //   pair texels of the footprint (ex, ey): float2 at tb[s] + (ey*T + ex)*8, +8, +T*8, +T*8+8
 template <int N, int MODE>
-__device__ __forceinline__ void march_staged(const IntegrateParams& p, const uint8_t* __restrict__ smem, uint32_t inv_off,
-                                             const ItemHdr* __restrict__ h, int BX, int BY, int BZ, int T, int x, int y, int zb, int ze) {
-  const float stepX = 1.0f / (float)p.X, stepY = 1.0f / (float)p.Y;
-  const float px = ((float)x + 0.5f) * stepX, py = ((float)y + 0.5f) * stepY;
-  int x0, x1, y0, y1; float a, b;
-  lin_coord(px, p.IX, x0, x1, a);
-  lin_coord(py, p.IY, y0, y1, b);
-  const float oma = 1.0f - a, omb = 1.0f - b;
-  const int ixlo = h->ixlo, iylo = h->iylo, izlo = h->izlo;
-  const uint32_t r0 = (uint32_t)((y0 - iylo) * BX), r1 = (uint32_t)((y1 - iylo) * BX);
-  const uint32_t c00 = inv_off + ((r0 + (uint32_t)(x0 - ixlo)) << 4), c10 = inv_off + ((r0 + (uint32_t)(x1 - ixlo)) << 4);
-  const uint32_t c01 = inv_off + ((r1 + (uint32_t)(x0 - ixlo)) << 4), c11 = inv_off + ((r1 + (uint32_t)(x1 - ixlo)) << 4);
-  const uint32_t ps = (uint32_t)(BX * BY) << 4, ss = ps * (uint32_t)BZ;
-  const uint32_t trow = (uint32_t)T << 3;
-  uint32_t tb[N];
-#pragma unroll
-  for (int s = 0; s < N; ++s) tb[s] = h->tb[s];
-  const float limit = p.limit, neg_limit = -p.limit;
+__device__ __forceinline__ void march_staged(const IntegrateParams& p, const uint8_t* __restrict__ smem, uint32_t sbase,
+                                             const ItemHdr* __restrict__ h, int BX, uint32_t ps, uint32_t ss, int T, int x, int y) {
+  // Register budget: 80 per thread with 768 threads per CTA. Everything warp-uniform that is needed once per voxel or less
+  // (tile bases, z range, verdict masks) stays in the stage header and is re-read by LDS (a broadcast) where it is used.
+  float a, b;
+  uint32_t c00, dX, dY;            // byte offset of the (x0, y0) corner in plane 0 of sensor 0; +dX: x1, +dY: y1
+  {
+    const float stepX = 1.0f / (float)p.X, stepY = 1.0f / (float)p.Y;
+    const float px = ((float)x + 0.5f) * stepX, py = ((float)y + 0.5f) * stepY;
+    int x0, x1, y0, y1;
+    lin_coord(px, p.IX, x0, x1, a);
+    lin_coord(py, p.IY, y0, y1, b);
+    // plane k of sensor s starts at sbase + STAGE_HDR_BYTES + s * ss + (k - izlo) * ps: fold izlo into the base
+    c00 = sbase + STAGE_HDR_BYTES - (uint32_t)h->izlo * ps + ((uint32_t)((y0 - h->iylo) * BX + (x0 - h->ixlo)) << 4);
+    dX = (uint32_t)(x1 - x0) << 4;
+    dY = (uint32_t)((y1 - y0) * BX) << 4;
+  }
+  const uint32_t masks = h->skip | h->front | (h->front << 8);     // bits 0-7: no per-voxel work, bits 8-15: front
   float3 A[N], B[N];
+#pragma unroll
+  for (int s = 0; s < N; ++s) A[s] = B[s] = make_float3(0.f, 0.f, 0.f);
   int ck0 = -1, ck1 = -1;
 
   auto plane = [&](int s, int k) -> float3 {
-    const uint32_t off = (uint32_t)s * ss + (uint32_t)(k - izlo) * ps;
-    const float4 p00 = *reinterpret_cast<const float4*>(smem + c00 + off), p10 = *reinterpret_cast<const float4*>(smem + c10 + off);
-    const float4 p01 = *reinterpret_cast<const float4*>(smem + c01 + off), p11 = *reinterpret_cast<const float4*>(smem + c11 + off);
-    return plane_reduce(p00, p10, p01, p11, a, oma, b, omb);
+    if ((masks >> s) & 1u) return make_float3(0.f, 0.f, 0.f);
+    const uint8_t* q = smem + (c00 + (uint32_t)s * ss + (uint32_t)k * ps);
+    const float4 p00 = *reinterpret_cast<const float4*>(q), p10 = *reinterpret_cast<const float4*>(q + dX);
+    const float4 p01 = *reinterpret_cast<const float4*>(q + dY), p11 = *reinterpret_cast<const float4*>(q + dY + dX);
+    return plane_reduce(p00, p10, p01, p11, a, 1.0f - a, b, 1.0f - b);
   };
 
+  const int zb = h->zb;
   unsigned o = (unsigned)((zb * p.Y + y) * p.X + x);
-  const unsigned ostep = (unsigned)(p.X * p.Y);
-  const float4* ztab = reinterpret_cast<const float4*>(smem + inv_off - STAGE_HDR_BYTES + ITEM_HDR_BYTES) - zb;   // the item's slice, staged
-  for (int z = zb; z < ze; ++z, o += ostep) {
-    const float4 zt = ztab[z];
+  const float4* zt_ptr = reinterpret_cast<const float4*>(smem + sbase + ITEM_HDR_BYTES);       // the item's slice of the z table
+  const float4* zt_end = zt_ptr + (h->ze - zb);
+  for (; zt_ptr < zt_end; ++zt_ptr, o += p.plane_elems) {
+    const float4 zt = *zt_ptr;
     const int k0 = __float_as_int(zt.x), k1 = __float_as_int(zt.y);
     const float g = zt.z, omg = zt.w;
     if (k0 != ck0) {
@@ -163,31 +174,29 @@ __device__ __forceinline__ void march_staged(const IntegrateParams& p, const uin
       }
       ck1 = k1;
     }
-    float weighted_tsd = limit, total_weight = 0.0f;
-    struct Tap { float wa, wb, d; float2 t00, t10, t01, t11; };
-    auto fetch = [&](int s) -> Tap {
-      Tap t;
-      int ex, ey;                // lower-left texel clamped to [-1, W-1]; the + 1 of the footprint index lives in tb[s]
-      tap_coords(A[s], B[s], g, omg, p.fW, p.fH, p.exmax, p.eymax, t.wa, t.wb, t.d, ex, ey);
-      const uint32_t off = tb[s] + ((uint32_t)(ey * T + ex) << 3);
-      t.t00 = *reinterpret_cast<const float2*>(smem + off);
-      t.t10 = *reinterpret_cast<const float2*>(smem + off + 8u);
-      t.t01 = *reinterpret_cast<const float2*>(smem + off + trow);
-      t.t11 = *reinterpret_cast<const float2*>(smem + off + trow + 8u);
-      return t;
-    };
-    auto fuse = [&](const Tap& t) {
-      fuse_tap(t.wa, t.wb, t.d, t.t00.x, t.t10.x, t.t01.x, t.t11.x, t.t00.y, t.t10.y, t.t01.y, t.t11.y, limit, neg_limit, weighted_tsd, total_weight);
-    };
+    float weighted_tsd = p.limit, total_weight = 0.0f;
 #pragma unroll
-    for (int s = 0; s + 1 < N; s += 2) {
-      const Tap t0 = fetch(s), t1 = fetch(s + 1);
-      fuse(t0);
-      fuse(t1);
+    for (int s = 0; s < N; ++s) {
+      if (!((masks >> s) & 1u)) {
+        float wa, wb, d;
+        int ex, ey;                // lower-left texel clamped to [-1, W-1]; the + 1 of the footprint index lives in tb[s]
+        tap_coords(A[s], B[s], g, omg, p.fW, p.fH, p.exmax, p.eymax, wa, wb, d, ex, ey);
+        const uint8_t* q = smem + (h->tb[s] + ((uint32_t)(ey * T + ex) << 3));
+        const float2 t00 = *reinterpret_cast<const float2*>(q), t10 = *reinterpret_cast<const float2*>(q + 8);
+        const float2 t01 = *reinterpret_cast<const float2*>(q + (T << 3)), t11 = *reinterpret_cast<const float2*>(q + (T << 3) + 8);
+        fuse_tap(wa, wb, d, t00.x, t10.x, t01.x, t11.x, t00.y, t10.y, t01.y, t11.y, p.limit, -p.limit, weighted_tsd, total_weight);
+      } else if ((masks >> (8 + s)) & 1u) {
+        weighted_tsd = -p.limit;
+      }
     }
-    if (N & 1) { const Tap t = fetch(N - 1); fuse(t); }
     store_voxel<MODE>(p, o, weighted_tsd, total_weight);
   }
+}
+
+// Cold path of the kernel below, kept out of line so that its register needs do not shape the staged loop's allocation.
+template <int N, int MODE>
+__device__ __noinline__ void march_direct(const IntegrateParams& p, int x, int y, int zb, int ze) {
+  march_column<N, MODE, true>(p, x, y, zb, ze);
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------------------------
@@ -196,25 +205,27 @@ template <int N, int MODE, int CWARPS, int FWARPS>
 __global__ void __launch_bounds__((CWARPS + FWARPS + 1) * 32, 1)
 k_integrate_staged(const __grid_constant__ StagedParams p, const __grid_constant__ CUtensorMap map_inv, const __grid_constant__ CUtensorMap map_pairs) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t s_full[2], s_empty[2];
+  __shared__ __align__(8) uint64_t s_full[2], s_ready[2], s_empty[2];
   // TMA destinations must be 128-byte aligned; the dynamic window's own alignment is only guaranteed to 16
   uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
+    mbar_init(&s_ready[0], 1); mbar_init(&s_ready[1], 1);
     mbar_init(&s_empty[0], CWARPS); mbar_init(&s_empty[1], CWARPS);
     mbar_fence_init();
   }
   __syncthreads();
   const IntegrateParams& ip = p.f.ip;
 
-  if (warp == CWARPS) {                      // ---- producer
+  if (warp == CWARPS) {                      // ---- producer: lane 0 draws items and issues the copies, the warp classifies
+    uint32_t lo = 0, total = 0;
     if (lane == 0) {
       tma_prefetch_desc(&map_inv);
       tma_prefetch_desc(&map_pairs);
       const uint32_t n_occ = *ip.num_occupied;
       // occupied bricks that intersect the slab: the list ascends in brick id, hence in brick z, so they are one run [lo, hi)
-      uint32_t lo = 0, hi = n_occ;
+      uint32_t hi = n_occ;
       if (ip.z_begin > 0) {
         uint32_t a = 0, b = n_occ;
         while (a < b) { const uint32_t m = (a + b) >> 1; if (ip.ranges[(size_t)ip.occupied[m] * 6 + 5] > ip.z_begin) b = m; else a = m + 1; }
@@ -225,77 +236,106 @@ k_integrate_staged(const __grid_constant__ StagedParams p, const __grid_constant
         while (a < b) { const uint32_t m = (a + b) >> 1; if (ip.ranges[(size_t)ip.occupied[m] * 6 + 4] >= ip.z_end) b = m; else a = m + 1; }
         hi = a;
       }
-      const uint32_t per_brick = (uint32_t)(p.n_yc * p.n_zc);
-      const uint32_t total = (p.debug & 2) ? 0u : (hi - lo) * per_brick;
-      const float stepX = 1.0f / (float)ip.X, stepY = 1.0f / (float)ip.Y;
-      int stage = 0;
-      uint32_t phase = 0;
-      for (;;) {
-        const uint32_t it = atomicAdd(p.f.work, 1u);
-        uint8_t* st = smem + (uint32_t)stage * p.stage_bytes;
-        ItemHdr* h = reinterpret_cast<ItemHdr*>(st);
-        if (it >= total) {
-          if (!mbar_wait(&s_empty[stage], phase ^ 1u, p.err)) break;
-          h->valid = 0;
-          mbar_arrive(&s_full[stage]);
-          break;
-        }
-        const uint32_t bi = it / per_brick, r = it - bi * per_brick;
-        const int yc = (int)(r / (uint32_t)p.n_zc), zc = (int)(r - (uint32_t)yc * (uint32_t)p.n_zc);
-        const uint32_t brick = ip.occupied[lo + bi];
-        if (p.legacy && p.legacy[brick]) continue;
-        const int32_t* rg = ip.ranges + (size_t)brick * 6;
-        const int x0 = rg[0], x1 = rg[1];
-        const int yb = rg[2] + yc * p.cy, ye = min(yb + p.cy, rg[3]);
-        const int zb = max(rg[4] + zc * p.cz, ip.z_begin), ze = min(min(rg[4] + (zc + 1) * p.cz, rg[5]), ip.z_end);
-        if (x0 >= x1 || yb >= ye || zb >= ze) continue;
-        // coarse box of the item: lin_coord is monotone, so the first / last voxel bound every corner index
-        int i0, i1, ixlo, ixhi, iylo, iyhi; float w;
-        lin_coord(((float)x0 + 0.5f) * stepX, ip.IX, ixlo, i1, w);
-        lin_coord(((float)(x1 - 1) + 0.5f) * stepX, ip.IX, i0, ixhi, w);
-        lin_coord(((float)yb + 0.5f) * stepY, ip.IY, iylo, i1, w);
-        lin_coord(((float)(ye - 1) + 0.5f) * stepY, ip.IY, i0, iyhi, w);
-        const int izlo = __float_as_int(ip.ztab[zb].x), izhi = __float_as_int(ip.ztab[ze - 1].y);
-        if (ixhi - ixlo >= p.BX || iyhi - iylo >= p.BY || izhi - izlo >= p.BZ) { atomicOr(p.err, 1u); continue; }
-        if (!mbar_wait(&s_empty[stage], phase ^ 1u, p.err)) break;
-        h->valid = 1;
-        h->x0 = x0; h->nx = x1 - x0; h->y0 = yb; h->ny = ye - yb; h->zb = zb; h->ze = ze;
-        h->ixlo = ixlo; h->iylo = iylo; h->izlo = izlo;
-        const uint32_t* fp = p.fp + ((size_t)(brick * (uint32_t)p.n_yc + (uint32_t)yc) * (uint32_t)p.n_zc + (uint32_t)zc) * N;
-        const uint32_t base = (uint32_t)stage * p.stage_bytes + STAGE_HDR_BYTES;
-        uint32_t org[N];
-#pragma unroll
-        for (int s = 0; s < N; ++s) {
-          org[s] = fp[s];
-          h->tb[s] = base + p.inv_span + (uint32_t)s * p.tile_span + ((uint32_t)(p.T + 1) << 3) -
-                     ((((org[s] >> 16) * (uint32_t)p.T) + (org[s] & 0xffffu)) << 3);
-        }
-        const uint32_t zt_bytes = (uint32_t)(ze - zb) * 16u;
-        mbar_expect_tx(&s_full[stage], p.inv_bytes + (uint32_t)N * p.tile_bytes + zt_bytes);
-        bulk_load(smem_u32(st) + ITEM_HDR_BYTES, ip.ztab + zb, zt_bytes, &s_full[stage]);
-        const uint32_t dst = smem_u32(st) + STAGE_HDR_BYTES;
-        tma_load_5d(dst, &map_inv, &s_full[stage], 0, ixlo, iylo, izlo, 0);
-#pragma unroll
-        for (int s = 0; s < N; ++s)
-          tma_load_3d(dst + p.inv_span + (uint32_t)s * p.tile_span, &map_pairs, &s_full[stage], (int)(org[s] & 0xffffu), (int)(org[s] >> 16), s);
-        stage ^= 1;
-        phase ^= (stage == 0) ? 1u : 0u;
-      }
+      total = (p.debug & 2) ? 0u : (hi - lo) * (uint32_t)(p.n_yc * p.n_zc);
     }
-    __syncwarp();
+    const uint32_t per_brick = (uint32_t)(p.n_yc * p.n_zc);
+    const float stepX = 1.0f / (float)ip.X, stepY = 1.0f / (float)ip.Y;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (;;) {
+      uint8_t* st = smem + (uint32_t)stage * p.stage_bytes;
+      ItemHdr* h = reinterpret_cast<ItemHdr*>(st);
+      int state = 0;                           // 1: item issued, 2: no more items, 3: give up (barrier time-out)
+      if (lane == 0) {
+        while (state == 0) {
+          const uint32_t it = atomicAdd(p.f.work, 1u);
+          if (it >= total) {
+            state = mbar_wait(&s_empty[stage], phase ^ 1u, p.err) ? 2 : 3;
+            if (state == 2) { h->valid = 0; mbar_arrive(&s_ready[stage]); }
+            break;
+          }
+          const uint32_t bi = it / per_brick, r = it - bi * per_brick;
+          const int yc = (int)(r / (uint32_t)p.n_zc), zc = (int)(r - (uint32_t)yc * (uint32_t)p.n_zc);
+          const uint32_t brick = ip.occupied[lo + bi];
+          const bool direct = p.legacy && p.legacy[brick];     // a footprint of this brick exceeds the tile: global-memory path
+          const int32_t* rg = ip.ranges + (size_t)brick * 6;
+          const int x0 = rg[0], x1 = rg[1];
+          const int yb = rg[2] + yc * p.cy, ye = min(yb + p.cy, rg[3]);
+          const int zb = max(rg[4] + zc * p.cz, ip.z_begin), ze = min(min(rg[4] + (zc + 1) * p.cz, rg[5]), ip.z_end);
+          if (x0 >= x1 || yb >= ye || zb >= ze) continue;
+          if (direct) {
+            if (!mbar_wait(&s_empty[stage], phase ^ 1u, p.err)) { state = 3; break; }
+            h->valid = 2;
+            h->x0 = x0; h->nx = x1 - x0; h->y0 = yb; h->ny = ye - yb; h->zb = zb; h->ze = ze;
+            mbar_arrive(&s_full[stage]);           // nothing to copy: the phase completes at once
+            state = 1;
+            break;
+          }
+          // coarse box of the item: lin_coord is monotone, so the first / last voxel bound every corner index
+          int i0, i1, ixlo, ixhi, iylo, iyhi; float w;
+          lin_coord(((float)x0 + 0.5f) * stepX, ip.IX, ixlo, i1, w);
+          lin_coord(((float)(x1 - 1) + 0.5f) * stepX, ip.IX, i0, ixhi, w);
+          lin_coord(((float)yb + 0.5f) * stepY, ip.IY, iylo, i1, w);
+          lin_coord(((float)(ye - 1) + 0.5f) * stepY, ip.IY, i0, iyhi, w);
+          const int izlo = __float_as_int(ip.ztab[zb].x), izhi = __float_as_int(ip.ztab[ze - 1].y);
+          if (ixhi - ixlo >= p.BX || iyhi - iylo >= p.BY || izhi - izlo >= p.BZ) { atomicOr(p.err, 1u); continue; }
+          if (!mbar_wait(&s_empty[stage], phase ^ 1u, p.err)) { state = 3; break; }
+          h->valid = 1;
+          h->x0 = x0; h->nx = x1 - x0; h->y0 = yb; h->ny = ye - yb; h->zb = zb; h->ze = ze;
+          h->ixlo = ixlo; h->iylo = iylo; h->izlo = izlo;
+          h->nbx = ixhi - ixlo + 1; h->nby = iyhi - iylo + 1; h->nbz = izhi - izlo + 1;
+          const size_t item = (size_t)(brick * (uint32_t)p.n_yc + (uint32_t)yc) * (uint32_t)p.n_zc + (uint32_t)zc;
+          const uint32_t verdict = (p.debug & 4) ? 0u : p.cls[item];
+          h->skip = verdict & 255u; h->front = verdict >> 8;
+          const uint2* fp = p.fp + item * N;
+          const uint32_t base = (uint32_t)stage * p.stage_bytes + STAGE_HDR_BYTES;
+          uint32_t org[N];
+#pragma unroll
+          for (int s = 0; s < N; ++s) {
+            const uint2 f = fp[s];
+            org[s] = f.x;
+            h->rect[s] = f.y;
+            h->tb[s] = base + p.inv_span + (uint32_t)s * p.tile_span + ((uint32_t)(p.T + 1) << 3) -
+                       ((((org[s] >> 16) * (uint32_t)p.T) + (org[s] & 0xffffu)) << 3);
+          }
+          const uint32_t zt_bytes = (uint32_t)(ze - zb) * 16u;
+          mbar_expect_tx(&s_full[stage], p.inv_bytes + (uint32_t)N * p.tile_bytes + zt_bytes);
+          bulk_load(smem_u32(st) + ITEM_HDR_BYTES, ip.ztab + zb, zt_bytes, &s_full[stage]);
+          const uint32_t dst = smem_u32(st) + STAGE_HDR_BYTES;
+          tma_load_5d(dst, &map_inv, &s_full[stage], 0, ixlo, iylo, izlo, 0);
+#pragma unroll
+          for (int s = 0; s < N; ++s)
+            tma_load_3d(dst + p.inv_span + (uint32_t)s * p.tile_span, &map_pairs, &s_full[stage], (int)(org[s] & 0xffffu), (int)(org[s] >> 16), s);
+          state = 1;
+        }
+      }
+      state = __shfl_sync(0xffffffffu, state, 0);
+      if (state != 1) break;
+      // the copies of this item have landed (lane 0 observes the barrier, the warp follows it): classify, then hand the
+      // stage to the consumers
+      bool ok = true;
+      if (lane == 0) ok = mbar_wait(&s_full[stage], phase, p.err);
+      ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
+      if (!ok) break;
+      if (lane == 0) mbar_arrive(&s_ready[stage]);
+      stage ^= 1;
+      phase ^= (stage == 0) ? 1u : 0u;
+    }
   } else if (warp < CWARPS) {                // ---- consumers
     int stage = 0;
     uint32_t phase = 0;
     for (;;) {
-      if (!mbar_wait(&s_full[stage], phase, p.err)) break;
+      if (!mbar_wait(&s_ready[stage], phase, p.err)) break;
       const uint32_t sbase = (uint32_t)stage * p.stage_bytes;
       const ItemHdr* h = reinterpret_cast<const ItemHdr*>(smem + sbase);
       if (!h->valid) break;
-      const int x0 = h->x0, nx = h->nx, y0 = h->y0, zb = h->zb, ze = h->ze;
-      const int cols = nx * h->ny;
-      for (int col = (int)threadIdx.x; col < cols; col += CWARPS * 32) {
-        const int cyv = col / nx, cxv = col - cyv * nx;
-        march_staged<N, MODE>(ip, smem, sbase + STAGE_HDR_BYTES, h, p.BX, p.BY, p.BZ, p.T, x0 + cxv, y0 + cyv, zb, ze);
+      const uint32_t ps = (uint32_t)(p.BX * p.BY) << 4, ss = ps * (uint32_t)p.BZ;
+      // one column per thread: the host sizes the y-chunk so that an item's columns fit the consumer threads
+      const int nx = h->nx, col = (int)threadIdx.x;
+      if (col < nx * h->ny) {
+        const int cyv = col / nx, x = h->x0 + (col - cyv * nx), y = h->y0 + cyv;
+        if (h->valid == 2) march_direct<N, MODE>(ip, x, y, h->zb, h->ze);      // oversize footprint: operands from global memory
+        else march_staged<N, MODE>(ip, smem, sbase, h, p.BX, ps, ss, p.T, x, y);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[stage]);
@@ -312,8 +352,10 @@ k_integrate_staged(const __grid_constant__ StagedParams p, const __grid_constant
 // every voxel of the item runs the plane / tap arithmetic of the integrator and the block reduces the footprint indices
 // (ex, ey) per sensor to their bounding rectangle. out[item][s] = (exmin, eymin, exmax, eymax); empty item: exmax < exmin.
 template <int N>
-__global__ void __launch_bounds__(256) k_footprints(const __grid_constant__ IntegrateParams p, int cy, int cz, int n_yc, int n_zc, int4* __restrict__ out) {
+__global__ void __launch_bounds__(256) k_footprints(const __grid_constant__ IntegrateParams p, int cy, int cz, int n_yc, int n_zc, int4* __restrict__ out,
+                                                    float2* __restrict__ out_z) {
   __shared__ int s_red[8][RR_MAX_SENSORS][4];
+  __shared__ float s_redz[8][RR_MAX_SENSORS][2];
   const uint32_t item = blockIdx.x;
   const uint32_t per_brick = (uint32_t)(n_yc * n_zc);
   const uint32_t brick = item / per_brick, r = item - brick * per_brick;
@@ -323,8 +365,10 @@ __global__ void __launch_bounds__(256) k_footprints(const __grid_constant__ Inte
   const int yb = rg[2] + yc * cy, ye = min(yb + cy, rg[3]);
   const int zb = rg[4] + zc * cz, ze = min(zb + cz, rg[5]);
   int mn_x[N], mn_y[N], mx_x[N], mx_y[N];
+  float zlo[N], zhi[N];              // range of pos_calib.z over the item; any non-finite value widens it to (-inf, inf)
+  const float inf = __int_as_float(0x7f800000);
 #pragma unroll
-  for (int s = 0; s < N; ++s) { mn_x[s] = mn_y[s] = 0x7fffffff; mx_x[s] = mx_y[s] = -1; }
+  for (int s = 0; s < N; ++s) { mn_x[s] = mn_y[s] = 0x7fffffff; mx_x[s] = mx_y[s] = -1; zlo[s] = inf; zhi[s] = -inf; }
   const int cols = (nx > 0 && ye > yb && ze > zb) ? nx * (ye - yb) : 0;
   const float stepX = 1.0f / (float)p.X, stepY = 1.0f / (float)p.Y;
   const unsigned plane_sz = (unsigned)(p.IX * p.IY);
@@ -350,6 +394,7 @@ __global__ void __launch_bounds__(256) k_footprints(const __grid_constant__ Inte
         ex += 1; ey += 1;
         mn_x[s] = min(mn_x[s], ex); mx_x[s] = max(mx_x[s], ex);
         mn_y[s] = min(mn_y[s], ey); mx_y[s] = max(mx_y[s], ey);
+        if (fabsf(d) < inf) { zlo[s] = fminf(zlo[s], d); zhi[s] = fmaxf(zhi[s], d); } else { zlo[s] = -inf; zhi[s] = inf; }
       }
     }
   }
@@ -361,7 +406,14 @@ __global__ void __launch_bounds__(256) k_footprints(const __grid_constant__ Inte
       mn_x[s] = min(mn_x[s], __shfl_xor_sync(0xffffffffu, mn_x[s], d)); mn_y[s] = min(mn_y[s], __shfl_xor_sync(0xffffffffu, mn_y[s], d));
       mx_x[s] = max(mx_x[s], __shfl_xor_sync(0xffffffffu, mx_x[s], d)); mx_y[s] = max(mx_y[s], __shfl_xor_sync(0xffffffffu, mx_y[s], d));
     }
-    if (lane == 0) { s_red[warp][s][0] = mn_x[s]; s_red[warp][s][1] = mn_y[s]; s_red[warp][s][2] = mx_x[s]; s_red[warp][s][3] = mx_y[s]; }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      zlo[s] = fminf(zlo[s], __shfl_xor_sync(0xffffffffu, zlo[s], d)); zhi[s] = fmaxf(zhi[s], __shfl_xor_sync(0xffffffffu, zhi[s], d));
+    }
+    if (lane == 0) {
+      s_red[warp][s][0] = mn_x[s]; s_red[warp][s][1] = mn_y[s]; s_red[warp][s][2] = mx_x[s]; s_red[warp][s][3] = mx_y[s];
+      s_redz[warp][s][0] = zlo[s]; s_redz[warp][s][1] = zhi[s];
+    }
   }
   __syncthreads();
   if (threadIdx.x < N) {
@@ -371,6 +423,9 @@ __global__ void __launch_bounds__(256) k_footprints(const __grid_constant__ Inte
       v.x = min(v.x, s_red[w][s][0]); v.y = min(v.y, s_red[w][s][1]); v.z = max(v.z, s_red[w][s][2]); v.w = max(v.w, s_red[w][s][3]);
     }
     out[(size_t)item * N + s] = v;
+    float2 zr = make_float2(inf, -inf);
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { zr.x = fminf(zr.x, s_redz[w][s][0]); zr.y = fmaxf(zr.y, s_redz[w][s][1]); }
+    out_z[(size_t)item * N + s] = zr;
   }
 }
 
@@ -424,18 +479,18 @@ static int launch_staged_n(rr_ctx* c, const StagedParams& sp, int mode) {
 
 // consumer warps per CTA: up to four sensors run 22 warps (a 26 x 26 brick's 676 columns in one pass) at 80 registers,
 // more sensors keep 6 more registers of plane state each and run 11 warps at 144
-static int consumer_warps(int N) { return N <= 4 ? 22 : 11; }
+static int consumer_warps(int N) { return (N <= 4 && tunables().stage_cwarps != 11) ? 22 : 11; }
 
-static int footprints(rr_ctx* c, const IntegrateParams& p, int cy, int cz, int n_yc, int n_zc, int4* d_out, uint32_t items) {
+static int footprints(rr_ctx* c, const IntegrateParams& p, int cy, int cz, int n_yc, int n_zc, int4* d_out, float2* d_z, uint32_t items) {
   switch (c->N) {
-    case 1: k_footprints<1><<<items, 256, 0, c->stream>>>(p, cy, cz, n_yc, n_zc, d_out); break;
-    case 2: k_footprints<2><<<items, 256, 0, c->stream>>>(p, cy, cz, n_yc, n_zc, d_out); break;
-    case 3: k_footprints<3><<<items, 256, 0, c->stream>>>(p, cy, cz, n_yc, n_zc, d_out); break;
-    case 4: k_footprints<4><<<items, 256, 0, c->stream>>>(p, cy, cz, n_yc, n_zc, d_out); break;
-    case 5: k_footprints<5><<<items, 256, 0, c->stream>>>(p, cy, cz, n_yc, n_zc, d_out); break;
-    case 6: k_footprints<6><<<items, 256, 0, c->stream>>>(p, cy, cz, n_yc, n_zc, d_out); break;
-    case 7: k_footprints<7><<<items, 256, 0, c->stream>>>(p, cy, cz, n_yc, n_zc, d_out); break;
-    case 8: k_footprints<8><<<items, 256, 0, c->stream>>>(p, cy, cz, n_yc, n_zc, d_out); break;
+    case 1: k_footprints<1><<<items, 256, 0, c->stream>>>(p, cy, cz, n_yc, n_zc, d_out, d_z); break;
+    case 2: k_footprints<2><<<items, 256, 0, c->stream>>>(p, cy, cz, n_yc, n_zc, d_out, d_z); break;
+    case 3: k_footprints<3><<<items, 256, 0, c->stream>>>(p, cy, cz, n_yc, n_zc, d_out, d_z); break;
+    case 4: k_footprints<4><<<items, 256, 0, c->stream>>>(p, cy, cz, n_yc, n_zc, d_out, d_z); break;
+    case 5: k_footprints<5><<<items, 256, 0, c->stream>>>(p, cy, cz, n_yc, n_zc, d_out, d_z); break;
+    case 6: k_footprints<6><<<items, 256, 0, c->stream>>>(p, cy, cz, n_yc, n_zc, d_out, d_z); break;
+    case 7: k_footprints<7><<<items, 256, 0, c->stream>>>(p, cy, cz, n_yc, n_zc, d_out, d_z); break;
+    case 8: k_footprints<8><<<items, 256, 0, c->stream>>>(p, cy, cz, n_yc, n_zc, d_out, d_z); break;
     default: return fail(c, RR_ERR_UNSUPPORTED, "integrate: 1..8 sensors supported");
   }
   RR_LAUNCH_CHECK(c, "k_footprints");
@@ -443,8 +498,8 @@ static int footprints(rr_ctx* c, const IntegrateParams& p, int cy, int cz, int n
 }
 
 void staged_release(rr_ctx* c) {
-  cudaFree(c->sti.d_fp); cudaFree(c->sti.d_legacy); cudaFree(c->sti.d_err);
-  c->sti.d_fp = nullptr; c->sti.d_legacy = nullptr; c->sti.d_err = nullptr;
+  cudaFree(c->sti.d_fp); cudaFree(c->sti.d_legacy); cudaFree(c->sti.d_err); cudaFree(c->sti.d_zr); cudaFree(c->sti.d_cls);
+  c->sti.d_fp = nullptr; c->sti.d_legacy = nullptr; c->sti.d_err = nullptr; c->sti.d_zr = nullptr; c->sti.d_cls = nullptr;
   c->sti.ok = false; c->sti.dirty = true;
 }
 
@@ -452,7 +507,7 @@ void staged_release(rr_ctx* c) {
 static unsigned staged_key() {
   const Tunables& tn = tunables();
   unsigned k = 2166136261u;
-  for (int v : {tn.staged, tn.fused, tn.stage_zchunk, tn.stage_ychunk, tn.stage_tile, tn.stage_fwarps}) k = (k ^ (unsigned)v) * 16777619u;
+  for (int v : {tn.staged, tn.fused, tn.stage_zchunk, tn.stage_ychunk, tn.stage_tile, tn.stage_fwarps, tn.stage_cwarps}) k = (k ^ (unsigned)v) * 16777619u;
   return k;
 }
 
@@ -460,6 +515,15 @@ bool staged_selected(const rr_ctx* c) {
   const Tunables& tn = tunables();
   return c->configured && c->cfg.use_bricks && c->fused_ok && tn.fused && tn.staged && c->sti.ok && !c->sti.dirty &&
          c->sti.generation == staged_key();
+}
+
+bool staged_classify_params(const rr_ctx* c, ClassifyParams& q) {
+  if (!staged_selected(c)) return false;
+  const auto& st = c->sti;
+  q.fp = st.d_fp; q.zr = st.d_zr; q.pairs = c->d_pairs; q.pair_pitch = c->pair_pitch; q.H2 = c->H + 2;
+  q.legacy = st.n_legacy ? st.d_legacy : nullptr;
+  q.cls = st.d_cls; q.per_brick = st.n_yc * st.n_zc; q.N = c->N; q.limit = c->cfg.limit;
+  return true;
 }
 
 int build_ztab(rr_ctx* c);   // rr_integrate.cu
@@ -501,6 +565,8 @@ int staged_prepare(rr_ctx* c) {
       if (eff >= best - 0.02) { if (eff > best) best = eff; cy = t; }
     }
   }
+  while (cy > 1 && max_nx * cy > CT) --cy;
+  if (max_nx * cy > CT) return RR_OK;           // a single brick row exceeds the consumer threads: the direct kernels run
   const int n_yc = (max_ny + cy - 1) / cy;
   const int n_zc = std::max(1, (max_nz + std::max(1, tn.stage_zchunk) - 1) / std::max(1, tn.stage_zchunk));
   const int cz = (max_nz + n_zc - 1) / n_zc;
@@ -544,19 +610,21 @@ int staged_prepare(rr_ctx* c) {
   const size_t items = nb * (size_t)n_yc * n_zc;
   if (items == 0 || items > 0x7fffffffull) return RR_OK;
   int4* d_ext = nullptr;
+  float2* d_zr = nullptr;
   if (cudaMalloc((void**)&d_ext, items * N * sizeof(int4)) != cudaSuccess) { cudaGetLastError(); return RR_OK; }
-  int rc = footprints(c, p, cy, cz, n_yc, n_zc, d_ext, (uint32_t)items);
+  if (cudaMalloc((void**)&d_zr, items * N * sizeof(float2)) != cudaSuccess) { cudaGetLastError(); cudaFree(d_ext); return RR_OK; }
+  int rc = footprints(c, p, cy, cz, n_yc, n_zc, d_ext, d_zr, (uint32_t)items);
   std::vector<int4> ext(items * N);
   if (rc == RR_OK) rc = check(c, cudaMemcpyAsync(ext.data(), d_ext, ext.size() * sizeof(int4), cudaMemcpyDeviceToHost, c->stream), "footprint download");
   if (rc == RR_OK) rc = check(c, cudaStreamSynchronize(c->stream), "footprint sync");
   cudaFree(d_ext);
-  if (rc != RR_OK) return rc;
+  if (rc != RR_OK) { cudaFree(d_zr); return rc; }
   // tile edge: cover every footprint if that is affordable, else the bulk of them (the rest goes to k_integrate_bricks)
   std::vector<int> need;
   need.reserve(ext.size());
   for (const int4& e : ext)
     if (e.z >= e.x) need.push_back(std::max(e.z - (e.x & ~1), e.w - e.y) + 2);
-  if (need.empty()) return RR_OK;
+  if (need.empty()) { cudaFree(d_zr); return RR_OK; }
   std::sort(need.begin(), need.end());
   auto even = [](long v) { return (v + 1) & ~1L; };
   long T;
@@ -567,23 +635,28 @@ int staged_prepare(rr_ctx* c) {
     T = (t_all <= t_budget && t_all <= std::max(48L, t_bulk + 8)) ? t_all : std::min(t_budget, std::max(16L, t_bulk));
   }
   T = std::max(T, 8L);
-  std::vector<uint32_t> fp(items * N, 0u);
+  std::vector<uint2> fp(items * N, make_uint2(0u, 0u));
   std::vector<uint8_t> legacy(nb, 0);
   const size_t per_brick = (size_t)n_yc * n_zc;
   for (size_t i = 0; i < items; ++i)
     for (int s = 0; s < N; ++s) {
       const int4& e = ext[i * N + s];
       if (e.z < e.x) continue;
-      if (std::max(e.z - (e.x & ~1), e.w - e.y) + 2 > T || e.x > 0xffff || e.y > 0xffff) legacy[i / per_brick] = 1;
-      fp[i * N + s] = (uint32_t)(e.x & ~1) | ((uint32_t)e.y << 16);
+      if (std::max(e.z - (e.x & ~1), e.w - e.y) + 2 > T || e.x > 0xffff || e.y > 0xffff) { legacy[i / per_brick] = 1; continue; }
+      // tile origin (even x: TMA start coordinates are multiples of 16 bytes) and the footprint rectangle inside the tile
+      const uint32_t rx = (uint32_t)(e.x & 1), rw = (uint32_t)(e.z - e.x + 2), rh = (uint32_t)(e.w - e.y + 2);
+      fp[i * N + s] = make_uint2((uint32_t)(e.x & ~1) | ((uint32_t)e.y << 16), rx | (rw << 8) | (rh << 20));
     }
   for (uint8_t v : legacy) st.n_legacy += v;
   staged_release(c);
   st.dirty = false;
-  RR_TRY_RC(check(c, cudaMalloc((void**)&st.d_fp, fp.size() * sizeof(uint32_t)), "footprint table"));
+  st.d_zr = d_zr;
+  RR_TRY_RC(check(c, cudaMalloc((void**)&st.d_cls, items * sizeof(uint32_t)), "verdict table"));
+  cudaMemsetAsync(st.d_cls, 0, items * sizeof(uint32_t), c->stream);
+  RR_TRY_RC(check(c, cudaMalloc((void**)&st.d_fp, fp.size() * sizeof(uint2)), "footprint table"));
   RR_TRY_RC(check(c, cudaMalloc((void**)&st.d_legacy, nb), "legacy brick mask"));
   RR_TRY_RC(check(c, cudaMalloc((void**)&st.d_err, 4 * sizeof(uint32_t)), "staged flags"));
-  cudaMemcpyAsync(st.d_fp, fp.data(), fp.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+  cudaMemcpyAsync(st.d_fp, fp.data(), fp.size() * sizeof(uint2), cudaMemcpyHostToDevice, c->stream);
   cudaMemcpyAsync(st.d_legacy, legacy.data(), nb, cudaMemcpyHostToDevice, c->stream);
   cudaMemsetAsync(st.d_err, 0, 4 * sizeof(uint32_t), c->stream);
   RR_TRY_RC(check(c, cudaStreamSynchronize(c->stream), "staged tables upload"));
@@ -628,18 +701,19 @@ int launch_integrate_staged(rr_ctx* c, const IntegrateParams& p, int mode, bool*
   sp.cy = st.cy; sp.cz = st.cz; sp.n_yc = st.n_yc; sp.n_zc = st.n_zc;
   sp.BX = st.BX; sp.BY = st.BY; sp.BZ = st.BZ; sp.T = st.T;
   sp.fp = st.d_fp; sp.legacy = st.n_legacy ? st.d_legacy : nullptr;
+  sp.cls = st.d_cls;
   sp.inv_bytes = st.inv_bytes; sp.tile_bytes = st.tile_bytes; sp.stage_bytes = st.stage_bytes;
   sp.inv_span = st.inv_span; sp.tile_span = st.tile_span;
   sp.err = st.d_err;
   if (tunables().stage_debug & 1) sp.f.fill_items = 0;
   sp.debug = tunables().stage_debug;
-  cudaMemsetAsync(c->d_work, 0, 4 * sizeof(uint32_t), c->stream);
+  // the work counters were reset and this frame's verdicts written by k_bricks_update (launch_bricks_update)
   int rc;
   switch (c->N) {
     case 1: rc = launch_staged_n<1, 22>(c, sp, mode); break;
     case 2: rc = launch_staged_n<2, 22>(c, sp, mode); break;
     case 3: rc = launch_staged_n<3, 22>(c, sp, mode); break;
-    case 4: rc = launch_staged_n<4, 22>(c, sp, mode); break;
+    case 4: rc = st.cwarps == 11 ? launch_staged_n<4, 11>(c, sp, mode) : launch_staged_n<4, 22>(c, sp, mode); break;
     case 5: rc = launch_staged_n<5, 11>(c, sp, mode); break;
     case 6: rc = launch_staged_n<6, 11>(c, sp, mode); break;
     case 7: rc = launch_staged_n<7, 11>(c, sp, mode); break;
@@ -647,9 +721,6 @@ int launch_integrate_staged(rr_ctx* c, const IntegrateParams& p, int mode, bool*
     default: return fail(c, RR_ERR_UNSUPPORTED, "integrate: 1..8 sensors supported");
   }
   if (rc != RR_OK) return rc;
-  // bricks whose footprint exceeds the tile (close to a sensor, or outside its frustum) go through the direct kernel; it
-  // reads the same pair image from global memory
-  if (st.n_legacy) RR_TRY_RC(launch_bricks_masked(c, p, mode, st.d_legacy));
   *done = true;
   return RR_OK;
 }

@@ -18,7 +18,7 @@ import bench  # noqa: E402
 from rrpy import capi  # noqa: E402
 
 DEFAULTS = dict(fused=1, zchunk=13, fill_rows=16, fill_warps=2, ctas=2, threads=512, chunk=1, ldg256=1,
-                staged=1, stage_zchunk=9, stage_ychunk=0, stage_tile=0, stage_fwarps=2, stage_fill_rows=16, stage_debug=0)
+                staged=1, stage_zchunk=9, stage_ychunk=0, stage_tile=0, stage_fwarps=2, stage_fill_rows=16, stage_debug=0, stage_cwarps=0)
 
 
 def main():
@@ -57,7 +57,8 @@ def main():
         if ref_hash is None:
             ref_hash = h
         info = fu.integrator_info()
-        print(json.dumps({"config": spec, "integrator": info, "integrate_ms": round(ms / n, 5), "preprocess_ms": round(pms / max(1, pn), 5),
+        info = {k: info[k] for k in ("staged", "tile", "zchunk", "legacy_bricks", "smem_bytes", "fill_warps", "flags")}
+        print(json.dumps({"config": spec, "integrate_ms": round(ms / n, 5), "integrator": info, "preprocess_ms": round(pms / max(1, pn), 5),
                           "tsdf_sha1": h, "same_as_first": h == ref_hash}), flush=True)
     fu.close()
 
