@@ -32,6 +32,19 @@ EXTENT = 2.048
 BBOX = ((-EXTENT / 2, 1.1 - EXTENT / 2, -EXTENT / 2), (EXTENT / 2, 1.1 + EXTENT / 2, EXTENT / 2))
 LIMIT, BRICK, MIN_VOX = 0.01, 0.1, 10
 N_FRAMES = 2                  # distinct synthetic frame sets cycled through the steps
+# one description of the workload for both arms (the driver compares the strings)
+WORKLOAD = (f"4 Kinect-v2 sensors 512x424 depth + 1280x1080 RGB8, {R}^3 R32F TSDF ({EXTENT} m cube), inverse calibration volumes "
+            f"128x128x256, step = clear bricks + 5 pre-process passes + brick update + integrate")
+INTEGRATION = {True: "occupied bricks (reference default m_use_bricks=true)", False: "dense (every voxel x every sensor)"}
+
+
+def host_cores():
+    """Host threads this process may use. torch.distributed.run exports OMP_NUM_THREADS=1 to its workers, so the OpenMP
+    default is not the box's core count there: the CPU arms set their thread count from the affinity mask instead."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 def peaks():
@@ -420,9 +433,7 @@ def run_ours(args):
         "value": round(value, 3), "unit": "Gvoxel-updates/s", "frames_per_s": round(frames_s, 2),
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 5),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"4 Kinect-v2 sensors 512x424 depth + 1280x1080 RGB8, {R}^3 R32F TSDF ({EXTENT} m cube), "
-                               f"inverse calibration volumes 128x128x256, step = clear bricks + 5 pre-process passes + brick update + integrate",
-                   "integration": "occupied bricks (reference default m_use_bricks=true)" if bricks else "dense (every voxel x every sensor)",
+        "config": {"workload": WORKLOAD, "integration": INTEGRATION[bricks],
                    "parallelism": f"z-slabs x{world}" if world > 1 else "single GPU", "slabs": slab_how,
                    "l2": "inputs+outputs per step (268 MB inverse volumes, 537 MB TSDF) exceed the 126 MB L2; no explicit flush",
                    "occupied_bricks": int(n_occ), "occupied_ratio": round(float(ratio), 4), "frames_cycled": N_FRAMES},
@@ -485,7 +496,8 @@ def cpu_baseline(scene, inv, voxel, bricks, budget_s):
     (all pixels, all occupied bricks) repeated until ~budget_s seconds of CPU work are spent."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_py as O
-    cores = O.max_threads()
+    cores = host_cores()
+    O.set_threads(cores)
     times, tps, tis = [], [], []
     t_start = time.perf_counter()
     n_occ = 0
@@ -514,7 +526,8 @@ def run_reference(args):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_py as O
     scenes, inv, voxel = make_inputs()
-    cores = O.max_threads()
+    cores = host_cores()                 # every host thread of the box, whatever OMP_NUM_THREADS the launcher exported
+    O.set_threads(cores)
     frac = 1.0
     times = []
     n_occ = n_sub = 0
@@ -559,8 +572,7 @@ def run_reference(args):
            "value": round(value, 5), "unit": "Gvoxel-updates/s", "frames_per_s": round(fps, 4), "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": round(t * 1e3, 2), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
-           "config": {"workload": f"4 Kinect-v2 sensors 512x424 depth + 1280x1080 RGB8, {R}^3 R32F TSDF, same inputs as the GPU arm",
-                      "integration": "occupied bricks (reference default m_use_bricks=true)"},
+           "config": {"workload": WORKLOAD, "integration": INTEGRATION[True]},
            "cpu_baseline": {"value": round(value, 5), "unit": "Gvoxel-updates/s", "cores": cores, "kind": "port",
                             "sample": f"per step: full pre-processing of 4x512x424 pixels + integration of {n_sub} of {n_occ} occupied bricks, "
                                       f"integration time scaled to all occupied bricks"},

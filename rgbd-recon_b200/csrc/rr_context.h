@@ -145,7 +145,7 @@ struct rr_ctx {
     int BX = 0, BY = 0, BZ = 0;    // inverse-volume box staged per item (coarse texels)
     int T = 0;                     // pair-image tile edge staged per item and sensor (pixels, even)
     int cwarps = 0, fwarps = 0;    // consumer / fill warps per CTA
-    uint32_t inv_bytes = 0, tile_bytes = 0, inv_span = 0, tile_span = 0, stage_bytes = 0, smem_bytes = 0;
+    uint32_t inv_bytes = 0, tile_bytes = 0, inv_span = 0, tile_span = 0, stage_bytes = 0, smem_bytes = 0, fill_src_bytes = 0, tables_off = 0;
     uint2* d_fp = nullptr;         // [items][N]: tile origin tx0 | ty0 << 16, footprint rectangle inside the tile
     uint8_t* d_legacy = nullptr;   // [num_bricks]: 1 = a footprint of this brick exceeds the tile: evaluated from global memory
     uint32_t n_legacy = 0;         // bricks flagged in d_legacy
@@ -188,12 +188,13 @@ struct Tunables {
   int ldg256 = 1;       // gather texels with one 256-bit load (0: two 128-bit loads)
   int graph = 1;        // rr_fuse_frame replays a captured CUDA graph (0: direct launches)
   int staged = 1;       // bricks mode uses the TMA-staged integrator when the configuration fits (0: direct kernels)
-  int stage_zchunk = 9; // staged integrator: voxels of a brick's z extent per work item
+  int stage_zchunk = 13; // staged integrator: voxels of a brick's z extent per work item
   int stage_ychunk = 0; // ... and of its y extent (0: chosen so that an item's columns fill the consumer threads)
   int stage_tile = 0;   // pair-image tile edge in pixels (0: chosen from the footprint statistics and the smem budget)
-  int stage_fwarps = 2; // fill warps per CTA
   int stage_fill_rows = 16;   // voxel rows per fill item
   int stage_cwarps = 0; // consumer warps per CTA: 0 = 22 up to four sensors (80 registers), 11 = half of that at 144 registers
+  int stage_bulk_fill = 16;   // KB of cleared voxels in shared memory as the source of the clear's TMA bulk stores (0: per-lane stores)
+  int stage_fill_batch = 1;   // fill items drawn per atomic
   int stage_debug = 0;  // measurement only, results are WRONG: bit 0 skips the clear stream, bit 1 the brick evaluation
   unsigned generation = 0;   // bumped by every rr_set_tunable (invalidates captured graphs)
 };

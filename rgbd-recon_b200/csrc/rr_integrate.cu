@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_integrate_fused(const __grid_con
         it = __shfl_sync(0xffffffffu, it, 0);
         if (it >= p.fill_items) break;
         const uint32_t r0 = p.row_begin + it * (uint32_t)p.fill_rows;
-        fill_rows<MODE == 1>(p, r0, min(r0 + (uint32_t)p.fill_rows, p.row_end), lane);
+        fill_rows<MODE == 1>(p, FillTables{p.cand_y, p.cand_z, p.rowany}, r0, min(r0 + (uint32_t)p.fill_rows, p.row_end), lane);
       }
     } else {
       for (;;) {
@@ -186,7 +186,6 @@ Tunables& tunables() {
     v.stage_zchunk = env("RR_STAGE_ZCHUNK", v.stage_zchunk);
     v.stage_ychunk = env("RR_STAGE_YCHUNK", v.stage_ychunk);
     v.stage_tile = env("RR_STAGE_TILE", v.stage_tile);
-    v.stage_fwarps = env("RR_STAGE_FWARPS", v.stage_fwarps);
     v.stage_fill_rows = env("RR_STAGE_FILL_ROWS", v.stage_fill_rows);
     return v;
   }();

@@ -33,6 +33,9 @@ struct StagedParams {
   const uint32_t* cls;      // [bricks * n_yc * n_zc]: this frame's per-sensor verdicts (k_classify): skip | front << 8
   uint32_t inv_bytes, tile_bytes;    // bytes one item's copies deliver (box, one tile)
   uint32_t inv_span, tile_span, stage_bytes;   // smem regions: TMA destinations are 128-byte aligned
+  uint32_t fill_src_off, fill_src_bytes;   // buffer of cleared voxels behind the stages (source of the clear's bulk stores); 0 bytes: none
+  uint32_t tables_off;      // shared-memory copies of cand_y [2Y], cand_z [2Z] (int16) and rowany [nby*nbz] behind that
+  uint32_t n_rowany, fill_batch;
   uint32_t* err;            // [0] box overflow, [1] barrier time-out
   int debug;
 };
@@ -200,9 +203,30 @@ __device__ __noinline__ void march_direct(const IntegrateParams& p, int x, int y
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------------------------
-// warps [0, CWARPS): consumers; warp CWARPS: producer (lane 0); warps above: clear stream.
-template <int N, int MODE, int CWARPS, int FWARPS>
-__global__ void __launch_bounds__((CWARPS + FWARPS + 1) * 32, 1)
+// The CTA is launched as whole warpgroups: the CWARPS consumer warps rounded up to warpgroups, then two auxiliary
+// warpgroups = one producer warp per pipeline stage + six clear warps. It starts at 65536 / threads registers per thread;
+// the auxiliary warpgroups then give registers back (setmaxnreg.dec to 40) and the consumer warpgroups take them
+// (setmaxnreg.inc to 72 with 22 consumer warps, 144 with 11): the clear gets enough warps to keep HBM busy - a warp streams
+// only ~4 B/clk of stores - while the brick evaluation keeps its register budget.
+// Each stage has its own producer (lane 0 of its warp): it draws an item from the global counter, gathers its metadata,
+// waits until the consumers have left the stage, issues the copies and, when they have landed, hands the stage over. Two
+// producers keep two items in preparation at any time, so the chain of dependent loads behind one item is never on the
+// consumers' critical path. Consumers visit the stages alternately until both have signalled the end.
+template <int CWARPS> struct StagedShape {
+  static constexpr int kConsumerWG = (CWARPS + 3) / 4;
+  static constexpr int kThreads = (kConsumerWG + 2) * 128;
+  static constexpr int kProducerWarp = kConsumerWG * 4;     // and kProducerWarp + 1
+  static constexpr int kAuxRegs = 40;
+  // setmaxnreg needs the kernel's register count declared (.maxnreg)
+  static constexpr int kLaunchRegs = (65536 / kThreads) / 8 * 8;
+  // the CTA's pool is what it was launched with: the consumers can take what the auxiliary warpgroups give back, no more
+  // (asking for more would block forever)
+  static constexpr int kConsumerRegs = ((kThreads * kLaunchRegs - 256 * kAuxRegs) / (kConsumerWG * 128)) / 8 * 8;
+  static_assert(kConsumerRegs >= kLaunchRegs && kConsumerRegs <= 255 && kAuxRegs <= kLaunchRegs, "register reallocation plan");
+};
+
+template <int N, int MODE, int CWARPS>
+__global__ void __maxnreg__((StagedShape<CWARPS>::kLaunchRegs))
 k_integrate_staged(const __grid_constant__ StagedParams p, const __grid_constant__ CUtensorMap map_inv, const __grid_constant__ CUtensorMap map_pairs) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t s_full[2], s_ready[2], s_empty[2];
@@ -215,121 +239,123 @@ k_integrate_staged(const __grid_constant__ StagedParams p, const __grid_constant
     mbar_init(&s_empty[0], CWARPS); mbar_init(&s_empty[1], CWARPS);
     mbar_fence_init();
   }
+  // the clear's bulk-store source: fill_src_bytes of cleared voxels (then as many zero bytes for a separate weight volume)
+  for (uint32_t i = threadIdx.x * 4u; i < p.fill_src_bytes * (MODE == 1 ? 2u : 1u); i += blockDim.x * 4u)
+    *reinterpret_cast<float*>(smem + p.fill_src_off + i) = i < p.fill_src_bytes ? p.f.fill_value : 0.0f;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the async proxy (TMA reads)
+  // the clear's row tables, once per CTA
+  int16_t* s_cand_y = reinterpret_cast<int16_t*>(smem + p.tables_off);
+  int16_t* s_cand_z = s_cand_y + 2 * p.f.ip.Y;
+  uint8_t* s_rowany = reinterpret_cast<uint8_t*>(s_cand_z + 2 * p.f.ip.Z);
+  for (int i = threadIdx.x; i < 2 * p.f.ip.Y; i += blockDim.x) s_cand_y[i] = p.f.cand_y[i];
+  for (int i = threadIdx.x; i < 2 * p.f.ip.Z; i += blockDim.x) s_cand_z[i] = p.f.cand_z[i];
+  for (uint32_t i = threadIdx.x; i < p.n_rowany; i += blockDim.x) s_rowany[i] = p.f.rowany[i];
   __syncthreads();
+  const FillTables ft{s_cand_y, s_cand_z, s_rowany};
   const IntegrateParams& ip = p.f.ip;
+  using Shape = StagedShape<CWARPS>;
+  constexpr int PWARP = Shape::kProducerWarp;
+  const FillSource fs{p.fill_src_bytes ? smem_u32(smem + p.fill_src_off) : 0u, p.fill_src_bytes};
 
-  if (warp == CWARPS) {                      // ---- producer: lane 0 draws items and issues the copies, the warp classifies
-    uint32_t lo = 0, total = 0;
-    if (lane == 0) {
-      tma_prefetch_desc(&map_inv);
-      tma_prefetch_desc(&map_pairs);
-      const uint32_t n_occ = *ip.num_occupied;
-      // occupied bricks that intersect the slab: the list ascends in brick id, hence in brick z, so they are one run [lo, hi)
-      uint32_t hi = n_occ;
-      if (ip.z_begin > 0) {
-        uint32_t a = 0, b = n_occ;
-        while (a < b) { const uint32_t m = (a + b) >> 1; if (ip.ranges[(size_t)ip.occupied[m] * 6 + 5] > ip.z_begin) b = m; else a = m + 1; }
-        lo = a;
-      }
-      if (ip.z_end < ip.Z) {
-        uint32_t a = lo, b = n_occ;
-        while (a < b) { const uint32_t m = (a + b) >> 1; if (ip.ranges[(size_t)ip.occupied[m] * 6 + 4] >= ip.z_end) b = m; else a = m + 1; }
-        hi = a;
-      }
-      total = (p.debug & 2) ? 0u : (hi - lo) * (uint32_t)(p.n_yc * p.n_zc);
+  // ---- producer of one stage (one thread)
+  auto producer = [&](const int stage) {
+    tma_prefetch_desc(&map_inv);
+    tma_prefetch_desc(&map_pairs);
+    const uint32_t n_occ = *ip.num_occupied;
+    // occupied bricks that intersect the slab: the list ascends in brick id, hence in brick z, so they are one run [lo, hi)
+    uint32_t lo = 0, hi = n_occ;
+    if (ip.z_begin > 0) {
+      uint32_t a = 0, b = n_occ;
+      while (a < b) { const uint32_t m = (a + b) >> 1; if (ip.ranges[(size_t)ip.occupied[m] * 6 + 5] > ip.z_begin) b = m; else a = m + 1; }
+      lo = a;
+    }
+    if (ip.z_end < ip.Z) {
+      uint32_t a = lo, b = n_occ;
+      while (a < b) { const uint32_t m = (a + b) >> 1; if (ip.ranges[(size_t)ip.occupied[m] * 6 + 4] >= ip.z_end) b = m; else a = m + 1; }
+      hi = a;
     }
     const uint32_t per_brick = (uint32_t)(p.n_yc * p.n_zc);
+    const uint32_t total = (p.debug & 2) ? 0u : (hi - lo) * per_brick;
     const float stepX = 1.0f / (float)ip.X, stepY = 1.0f / (float)ip.Y;
-    int stage = 0;
+    uint8_t* st = smem + (uint32_t)stage * p.stage_bytes;
+    ItemHdr* h = reinterpret_cast<ItemHdr*>(st);
     uint32_t phase = 0;
     for (;;) {
-      uint8_t* st = smem + (uint32_t)stage * p.stage_bytes;
-      ItemHdr* h = reinterpret_cast<ItemHdr*>(st);
-      int state = 0;                           // 1: item issued, 2: no more items, 3: give up (barrier time-out)
-      if (lane == 0) {
-        while (state == 0) {
-          const uint32_t it = atomicAdd(p.f.work, 1u);
-          if (it >= total) {
-            state = mbar_wait(&s_empty[stage], phase ^ 1u, p.err) ? 2 : 3;
-            if (state == 2) { h->valid = 0; mbar_arrive(&s_ready[stage]); }
-            break;
-          }
-          const uint32_t bi = it / per_brick, r = it - bi * per_brick;
-          const int yc = (int)(r / (uint32_t)p.n_zc), zc = (int)(r - (uint32_t)yc * (uint32_t)p.n_zc);
-          const uint32_t brick = ip.occupied[lo + bi];
-          const bool direct = p.legacy && p.legacy[brick];     // a footprint of this brick exceeds the tile: global-memory path
-          const int32_t* rg = ip.ranges + (size_t)brick * 6;
-          const int x0 = rg[0], x1 = rg[1];
-          const int yb = rg[2] + yc * p.cy, ye = min(yb + p.cy, rg[3]);
-          const int zb = max(rg[4] + zc * p.cz, ip.z_begin), ze = min(min(rg[4] + (zc + 1) * p.cz, rg[5]), ip.z_end);
-          if (x0 >= x1 || yb >= ye || zb >= ze) continue;
-          if (direct) {
-            if (!mbar_wait(&s_empty[stage], phase ^ 1u, p.err)) { state = 3; break; }
-            h->valid = 2;
-            h->x0 = x0; h->nx = x1 - x0; h->y0 = yb; h->ny = ye - yb; h->zb = zb; h->ze = ze;
-            mbar_arrive(&s_full[stage]);           // nothing to copy: the phase completes at once
-            state = 1;
-            break;
-          }
-          // coarse box of the item: lin_coord is monotone, so the first / last voxel bound every corner index
-          int i0, i1, ixlo, ixhi, iylo, iyhi; float w;
-          lin_coord(((float)x0 + 0.5f) * stepX, ip.IX, ixlo, i1, w);
-          lin_coord(((float)(x1 - 1) + 0.5f) * stepX, ip.IX, i0, ixhi, w);
-          lin_coord(((float)yb + 0.5f) * stepY, ip.IY, iylo, i1, w);
-          lin_coord(((float)(ye - 1) + 0.5f) * stepY, ip.IY, i0, iyhi, w);
-          const int izlo = __float_as_int(ip.ztab[zb].x), izhi = __float_as_int(ip.ztab[ze - 1].y);
-          if (ixhi - ixlo >= p.BX || iyhi - iylo >= p.BY || izhi - izlo >= p.BZ) { atomicOr(p.err, 1u); continue; }
-          if (!mbar_wait(&s_empty[stage], phase ^ 1u, p.err)) { state = 3; break; }
-          h->valid = 1;
-          h->x0 = x0; h->nx = x1 - x0; h->y0 = yb; h->ny = ye - yb; h->zb = zb; h->ze = ze;
-          h->ixlo = ixlo; h->iylo = iylo; h->izlo = izlo;
-          h->nbx = ixhi - ixlo + 1; h->nby = iyhi - iylo + 1; h->nbz = izhi - izlo + 1;
-          const size_t item = (size_t)(brick * (uint32_t)p.n_yc + (uint32_t)yc) * (uint32_t)p.n_zc + (uint32_t)zc;
-          const uint32_t verdict = (p.debug & 4) ? 0u : p.cls[item];
-          h->skip = verdict & 255u; h->front = verdict >> 8;
-          const uint2* fp = p.fp + item * N;
-          const uint32_t base = (uint32_t)stage * p.stage_bytes + STAGE_HDR_BYTES;
-          uint32_t org[N];
-#pragma unroll
-          for (int s = 0; s < N; ++s) {
-            const uint2 f = fp[s];
-            org[s] = f.x;
-            h->rect[s] = f.y;
-            h->tb[s] = base + p.inv_span + (uint32_t)s * p.tile_span + ((uint32_t)(p.T + 1) << 3) -
-                       ((((org[s] >> 16) * (uint32_t)p.T) + (org[s] & 0xffffu)) << 3);
-          }
-          const uint32_t zt_bytes = (uint32_t)(ze - zb) * 16u;
-          mbar_expect_tx(&s_full[stage], p.inv_bytes + (uint32_t)N * p.tile_bytes + zt_bytes);
-          bulk_load(smem_u32(st) + ITEM_HDR_BYTES, ip.ztab + zb, zt_bytes, &s_full[stage]);
-          const uint32_t dst = smem_u32(st) + STAGE_HDR_BYTES;
-          tma_load_5d(dst, &map_inv, &s_full[stage], 0, ixlo, iylo, izlo, 0);
-#pragma unroll
-          for (int s = 0; s < N; ++s)
-            tma_load_3d(dst + p.inv_span + (uint32_t)s * p.tile_span, &map_pairs, &s_full[stage], (int)(org[s] & 0xffffu), (int)(org[s] >> 16), s);
-          state = 1;
-        }
+      const uint32_t it = atomicAdd(p.f.work, 1u);
+      if (it >= total) {
+        if (mbar_wait(&s_empty[stage], phase ^ 1u, p.err)) { h->valid = 0; mbar_arrive(&s_ready[stage]); }
+        return;
       }
-      state = __shfl_sync(0xffffffffu, state, 0);
-      if (state != 1) break;
-      // the copies of this item have landed (lane 0 observes the barrier, the warp follows it): classify, then hand the
-      // stage to the consumers
-      bool ok = true;
-      if (lane == 0) ok = mbar_wait(&s_full[stage], phase, p.err);
-      ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
-      if (!ok) break;
-      if (lane == 0) mbar_arrive(&s_ready[stage]);
-      stage ^= 1;
-      phase ^= (stage == 0) ? 1u : 0u;
+      const uint32_t bi = it / per_brick, r = it - bi * per_brick;
+      const int yc = (int)(r / (uint32_t)p.n_zc), zc = (int)(r - (uint32_t)yc * (uint32_t)p.n_zc);
+      const uint32_t brick = ip.occupied[lo + bi];
+      const bool direct = p.legacy && p.legacy[brick];     // a footprint of this brick exceeds the tile: global-memory path
+      const int32_t* rg = ip.ranges + (size_t)brick * 6;
+      const int x0 = rg[0], x1 = rg[1];
+      const int yb = rg[2] + yc * p.cy, ye = min(yb + p.cy, rg[3]);
+      const int zb = max(rg[4] + zc * p.cz, ip.z_begin), ze = min(min(rg[4] + (zc + 1) * p.cz, rg[5]), ip.z_end);
+      if (x0 >= x1 || yb >= ye || zb >= ze) continue;
+      if (direct) {
+        if (!mbar_wait(&s_empty[stage], phase ^ 1u, p.err)) return;
+        h->valid = 2;
+        h->x0 = x0; h->nx = x1 - x0; h->y0 = yb; h->ny = ye - yb; h->zb = zb; h->ze = ze;
+        mbar_arrive(&s_ready[stage]);            // nothing to copy
+        phase ^= 1u;
+        continue;
+      }
+      // coarse box of the item: lin_coord is monotone, so the first / last voxel bound every corner index
+      int i0, i1, ixlo, ixhi, iylo, iyhi; float w;
+      lin_coord(((float)x0 + 0.5f) * stepX, ip.IX, ixlo, i1, w);
+      lin_coord(((float)(x1 - 1) + 0.5f) * stepX, ip.IX, i0, ixhi, w);
+      lin_coord(((float)yb + 0.5f) * stepY, ip.IY, iylo, i1, w);
+      lin_coord(((float)(ye - 1) + 0.5f) * stepY, ip.IY, i0, iyhi, w);
+      const int izlo = __float_as_int(ip.ztab[zb].x), izhi = __float_as_int(ip.ztab[ze - 1].y);
+      if (ixhi - ixlo >= p.BX || iyhi - iylo >= p.BY || izhi - izlo >= p.BZ) { atomicOr(p.err, 1u); continue; }
+      const size_t item = (size_t)(brick * (uint32_t)p.n_yc + (uint32_t)yc) * (uint32_t)p.n_zc + (uint32_t)zc;
+      const uint32_t verdict = (p.debug & 4) ? 0u : p.cls[item];
+      const uint2* fp = p.fp + item * N;
+      uint2 f[N];
+#pragma unroll
+      for (int s = 0; s < N; ++s) f[s] = fp[s];
+      // everything above overlapped the consumers' work on this stage's previous item; now the stage itself is needed
+      if (!mbar_wait(&s_empty[stage], phase ^ 1u, p.err)) return;
+      h->valid = 1;
+      h->x0 = x0; h->nx = x1 - x0; h->y0 = yb; h->ny = ye - yb; h->zb = zb; h->ze = ze;
+      h->ixlo = ixlo; h->iylo = iylo; h->izlo = izlo;
+      h->nbx = ixhi - ixlo + 1; h->nby = iyhi - iylo + 1; h->nbz = izhi - izlo + 1;
+      h->skip = verdict & 255u; h->front = verdict >> 8;
+      const uint32_t base = (uint32_t)stage * p.stage_bytes + STAGE_HDR_BYTES;
+#pragma unroll
+      for (int s = 0; s < N; ++s) {
+        h->rect[s] = f[s].y;
+        h->tb[s] = base + p.inv_span + (uint32_t)s * p.tile_span + ((uint32_t)(p.T + 1) << 3) -
+                   ((((f[s].x >> 16) * (uint32_t)p.T) + (f[s].x & 0xffffu)) << 3);
+      }
+      const uint32_t zt_bytes = (uint32_t)(ze - zb) * 16u;
+      mbar_expect_tx(&s_full[stage], p.inv_bytes + (uint32_t)N * p.tile_bytes + zt_bytes);
+      bulk_load(smem_u32(st) + ITEM_HDR_BYTES, ip.ztab + zb, zt_bytes, &s_full[stage]);
+      const uint32_t dst = smem_u32(st) + STAGE_HDR_BYTES;
+      tma_load_5d(dst, &map_inv, &s_full[stage], 0, ixlo, iylo, izlo, 0);
+#pragma unroll
+      for (int s = 0; s < N; ++s)
+        tma_load_3d(dst + p.inv_span + (uint32_t)s * p.tile_span, &map_pairs, &s_full[stage], (int)(f[s].x & 0xffffu), (int)(f[s].x >> 16), s);
+      // the copies have landed: hand the stage to the consumers
+      if (!mbar_wait(&s_full[stage], phase, p.err)) return;
+      mbar_arrive(&s_ready[stage]);
+      phase ^= 1u;
     }
-  } else if (warp < CWARPS) {                // ---- consumers
-    int stage = 0;
-    uint32_t phase = 0;
-    for (;;) {
-      if (!mbar_wait(&s_ready[stage], phase, p.err)) break;
+  };
+  // ---- consumers: stages alternately, each until its producer signals the end
+  auto consumer = [&]() {
+    const uint32_t ps = (uint32_t)(p.BX * p.BY) << 4, ss = ps * (uint32_t)p.BZ;
+    uint32_t phase[2] = {0u, 0u};
+    bool live[2] = {true, true};
+    for (int stage = 0; live[0] || live[1]; stage ^= 1) {
+      if (!live[stage]) continue;
+      if (!mbar_wait(&s_ready[stage], phase[stage], p.err)) return;
       const uint32_t sbase = (uint32_t)stage * p.stage_bytes;
       const ItemHdr* h = reinterpret_cast<const ItemHdr*>(smem + sbase);
-      if (!h->valid) break;
-      const uint32_t ps = (uint32_t)(p.BX * p.BY) << 4, ss = ps * (uint32_t)p.BZ;
+      if (!h->valid) { live[stage] = false; continue; }
       // one column per thread: the host sizes the y-chunk so that an item's columns fit the consumer threads
       const int nx = h->nx, col = (int)threadIdx.x;
       if (col < nx * h->ny) {
@@ -339,12 +365,27 @@ k_integrate_staged(const __grid_constant__ StagedParams p, const __grid_constant
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[stage]);
-      stage ^= 1;
-      phase ^= (stage == 0) ? 1u : 0u;
+      phase[stage] ^= 1u;
+    }
+  };
+  // ---- clear stream: the clear warps from the start, everybody else once their own work is done
+  auto clear = [&]() { fill_loop<MODE == 1>(p.f, ft, lane, fs, p.fill_batch); };
+  const bool helpers_clear = !(p.debug & 16);
+  // each role's code sits behind its own setmaxnreg, so that ptxas allocates it against that budget
+  if (warp < PWARP) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Shape::kConsumerRegs));
+    if (warp < CWARPS) consumer();
+    if (helpers_clear) clear();
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Shape::kAuxRegs));
+    if (warp <= PWARP + 1) {
+      if (lane == 0) producer(warp - PWARP);
+      __syncwarp();
+      if (helpers_clear) clear();
+    } else {
+      clear();
     }
   }
-  // ---- clear stream: the fill warps from the start, everybody else once their own work is done
-  fill_loop<MODE == 1>(p.f, lane);
 }
 
 // ---- footprints ------------------------------------------------------------------------------------------------------
@@ -453,10 +494,10 @@ static EncodeTiledFn encode_tiled() {
   return fn;
 }
 
-template <int N, int CWARPS, int FWARPS>
-static int launch_staged_nf(rr_ctx* c, const StagedParams& sp, int mode) {
+template <int N, int CWARPS>
+static int launch_staged_n(rr_ctx* c, const StagedParams& sp, int mode) {
   const auto& st = c->sti;
-  const dim3 grd(148, 1, 1), blk((CWARPS + FWARPS + 1) * 32, 1, 1);
+  const dim3 grd(148, 1, 1), blk(StagedShape<CWARPS>::kThreads, 1, 1);
   auto go = [&](auto kern) -> int {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st.smem_bytes);
     if (e != cudaSuccess) return check(c, e, "k_integrate_staged shared memory");
@@ -464,20 +505,15 @@ static int launch_staged_nf(rr_ctx* c, const StagedParams& sp, int mode) {
     return RR_OK;
   };
   int rc;
-  if (mode == 1) rc = go(k_integrate_staged<N, 1, CWARPS, FWARPS>);
-  else if (mode == 2) rc = go(k_integrate_staged<N, 2, CWARPS, FWARPS>);
-  else rc = go(k_integrate_staged<N, 0, CWARPS, FWARPS>);
+  if (mode == 1) rc = go(k_integrate_staged<N, 1, CWARPS>);
+  else if (mode == 2) rc = go(k_integrate_staged<N, 2, CWARPS>);
+  else rc = go(k_integrate_staged<N, 0, CWARPS>);
   if (rc != RR_OK) return rc;
   RR_LAUNCH_CHECK(c, "k_integrate_staged");
   return RR_OK;
 }
 
-template <int N, int CWARPS>
-static int launch_staged_n(rr_ctx* c, const StagedParams& sp, int mode) {
-  return c->sti.fwarps == 1 ? launch_staged_nf<N, CWARPS, 1>(c, sp, mode) : launch_staged_nf<N, CWARPS, 2>(c, sp, mode);
-}
-
-// consumer warps per CTA: up to four sensors run 22 warps (a 26 x 26 brick's 676 columns in one pass) at 80 registers,
+// consumer warps per CTA: up to four sensors run 22 warps (a 26 x 26 brick's 676 columns in one pass) at 72 registers,
 // more sensors keep 6 more registers of plane state each and run 11 warps at 144
 static int consumer_warps(int N) { return (N <= 4 && tunables().stage_cwarps != 11) ? 22 : 11; }
 
@@ -507,7 +543,7 @@ void staged_release(rr_ctx* c) {
 static unsigned staged_key() {
   const Tunables& tn = tunables();
   unsigned k = 2166136261u;
-  for (int v : {tn.staged, tn.fused, tn.stage_zchunk, tn.stage_ychunk, tn.stage_tile, tn.stage_fwarps, tn.stage_cwarps}) k = (k ^ (unsigned)v) * 16777619u;
+  for (int v : {tn.staged, tn.fused, tn.stage_zchunk, tn.stage_ychunk, tn.stage_tile, tn.stage_cwarps, tn.stage_bulk_fill}) k = (k ^ (unsigned)v) * 16777619u;
   return k;
 }
 
@@ -553,7 +589,7 @@ int staged_prepare(rr_ctx* c) {
   }
   if (max_nx <= 0 || max_ny <= 0 || max_nz <= 0) return RR_OK;
   st.cwarps = consumer_warps(N);
-  st.fwarps = tn.stage_fwarps == 1 ? 1 : 2;
+  st.fwarps = 6;
   const int CT = st.cwarps * 32;
   // y-chunk: as many brick rows as fill the consumer threads best (ties: the larger chunk, fewer items)
   int cy = tn.stage_ychunk > 0 ? std::min(tn.stage_ychunk, max_ny) : 0;
@@ -594,7 +630,10 @@ int staged_prepare(rr_ctx* c) {
   if (BX > 256 || BY > 256 || BZ > 256 || cz > ZT_MAX) return RR_OK;
   int smem_max = 0;
   cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device);
-  const long budget = ((long)smem_max - 1024) / 2 - STAGE_HDR_BYTES;           // per stage, after the header
+  const int weight_mode = c->cfg.store_weight == RR_VOXELS_F32_WEIGHT ? 2 : 1;
+  const long fill_buf = tn.stage_bulk_fill > 0 ? (long)tn.stage_bulk_fill * 1024 : 0;      // bytes of cleared voxels for the bulk stores
+  const long tables = ((long)(4 * (Y + Z)) + (long)c->bricks.res[1] * c->bricks.res[2] + 127) & ~127L;      // cand_y, cand_z, rowany
+  const long budget = ((long)smem_max - 1024 - fill_buf * weight_mode - tables) / 2 - STAGE_HDR_BYTES;           // per stage, after the header
   const long inv_bytes = (long)N * BZ * BY * BX * 16, inv_span = (inv_bytes + 127) & ~127L;
   long t_budget = (long)std::floor(std::sqrt(std::max(0.0, double(budget - inv_span - 128 * N) / (8.0 * N))));
   t_budget = std::min(t_budget & ~1L, 256L);
@@ -686,7 +725,9 @@ int staged_prepare(rr_ctx* c) {
   st.inv_span = (uint32_t)inv_span;
   st.tile_span = (st.tile_bytes + 127u) & ~127u;
   st.stage_bytes = STAGE_HDR_BYTES + st.inv_span + (uint32_t)N * st.tile_span;
-  st.smem_bytes = 2 * st.stage_bytes + 128;
+  st.fill_src_bytes = (uint32_t)fill_buf;
+  st.smem_bytes = 2 * st.stage_bytes + 128 + (uint32_t)(fill_buf * weight_mode) + (uint32_t)tables;
+  st.tables_off = 2 * st.stage_bytes + (uint32_t)(fill_buf * weight_mode);
   st.ok = true;
   return RR_OK;
 }
@@ -705,8 +746,12 @@ int launch_integrate_staged(rr_ctx* c, const IntegrateParams& p, int mode, bool*
   sp.inv_bytes = st.inv_bytes; sp.tile_bytes = st.tile_bytes; sp.stage_bytes = st.stage_bytes;
   sp.inv_span = st.inv_span; sp.tile_span = st.tile_span;
   sp.err = st.d_err;
+  sp.fill_src_off = 2 * st.stage_bytes; sp.fill_src_bytes = st.fill_src_bytes;
+  sp.tables_off = st.tables_off; sp.n_rowany = c->bricks.res[1] * c->bricks.res[2];
+  sp.fill_batch = (uint32_t)std::max(1, tunables().stage_fill_batch);
   if (tunables().stage_debug & 1) sp.f.fill_items = 0;
   sp.debug = tunables().stage_debug;
+  sp.f.store_flavour = (tunables().stage_debug >> 8) & 3;
   // the work counters were reset and this frame's verdicts written by k_bricks_update (launch_bricks_update)
   int rc;
   switch (c->N) {
