@@ -864,7 +864,6 @@ int rr_set_tunable(const char* name, int value) {
   else if (n == "stage_debug") t.stage_debug = value;
   else if (n == "stage_cwarps") t.stage_cwarps = value;
   else if (n == "stage_bulk_fill") t.stage_bulk_fill = value;
-  else if (n == "stage_fill_batch") t.stage_fill_batch = value;
   else return RR_ERR_INVALID;
   ++t.generation;              // captured frame graphs bake the launch shapes in: stale keys never match again
   return RR_OK;

@@ -193,8 +193,7 @@ struct Tunables {
   int stage_tile = 0;   // pair-image tile edge in pixels (0: chosen from the footprint statistics and the smem budget)
   int stage_fill_rows = 16;   // voxel rows per fill item
   int stage_cwarps = 0; // consumer warps per CTA: 0 = 22 up to four sensors (80 registers), 11 = half of that at 144 registers
-  int stage_bulk_fill = 16;   // KB of cleared voxels in shared memory as the source of the clear's TMA bulk stores (0: per-lane stores)
-  int stage_fill_batch = 1;   // fill items drawn per atomic
+  int stage_bulk_fill = 16;   // KB of cleared voxels in shared memory, the source of the clear's TMA bulk stores
   int stage_debug = 0;  // measurement only, results are WRONG: bit 0 skips the clear stream, bit 1 the brick evaluation
   unsigned generation = 0;   // bumped by every rr_set_tunable (invalidates captured graphs)
 };

@@ -42,7 +42,6 @@ struct FusedParams {
   int fill_warps;
   int chunk;                   // compute items a CTA draws from the global counter at a time
   float fill_value;
-  int store_flavour;           // experiment knob of the clear's per-lane stores: 0 streaming (.cs), 1 plain, 2 32-byte
 };
 
 // x/y part of the trilinear inverse-volume fetch for one coarse plane: lerp(v0, v1, t) = fma(t, v1, (1 - t) * v0),
@@ -219,47 +218,47 @@ __device__ __forceinline__ void march_column(const IntegrateParams& p, int x, in
   }
 }
 
-// TMA bulk stores (shared -> global) for the clear stream: one instruction moves up to a whole buffer of cleared voxels,
-// asynchronously, so the issuing warp is not held by the store queue the way per-lane stores hold it.
-__device__ __forceinline__ void bulk_store(void* dst, uint32_t src_smem, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-
-// Source of the bulk stores: a shared-memory buffer holding `bytes` of cleared voxels (and, for a separate weight volume,
-// as many zero bytes behind it). src == 0: no buffer, per-lane stores.
-struct FillSource { uint32_t src, bytes; };
-// 32-byte store (one lane, two float4): fewer store instructions per byte for the clear's streams (sm_100: STG.256)
-__device__ __forceinline__ void st_v8(float4* p, const float4& v) {
-  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
 // The small per-axis tables the clear consults per row (cand_y, cand_z, rowany): global by default, the staged kernel
 // keeps a copy in shared memory so that classifying a fill item costs no global round trips.
 struct FillTables { const int16_t* cand_y; const int16_t* cand_z; const uint8_t* rowany; };
 
-// One fill item: rows [row0, row1), at most 32. Lane r classifies row row0 + r (which brick rows cover it, does any of
-// them hold an occupied brick); rows without occupied bricks are streamed with 16-byte stores, the others consult the
-// row bitmask per 4-voxel group.
+// Lane r of a fill item classifies row row0 + r: the (at most four) brick rows that cover it and whether any of them holds
+// an occupied brick.
+__device__ __forceinline__ bool classify_row(const FusedParams& p, const FillTables& ft, uint32_t row0, uint32_t row1, int lane,
+                                             int& br0, int& br1, int& br2, int& br3) {
+  br0 = br1 = br2 = br3 = -1;
+  if (row0 + (uint32_t)lane >= row1) return false;
+  const uint32_t row = row0 + (uint32_t)lane;
+  const int Y = p.ip.Y;
+  const int z = (int)(row / (uint32_t)Y), y = (int)(row - (uint32_t)z * (uint32_t)Y);
+  const int cy0 = ft.cand_y[2 * y], cy1 = ft.cand_y[2 * y + 1], cz0 = ft.cand_z[2 * z], cz1 = ft.cand_z[2 * z + 1];
+  br0 = (cy0 >= 0 && cz0 >= 0) ? cz0 * p.nby + cy0 : -1;
+  br1 = (cy1 >= 0 && cz0 >= 0) ? cz0 * p.nby + cy1 : -1;
+  br2 = (cy0 >= 0 && cz1 >= 0) ? cz1 * p.nby + cy0 : -1;
+  br3 = (cy1 >= 0 && cz1 >= 0) ? cz1 * p.nby + cy1 : -1;
+  return (br0 >= 0 && ft.rowany[br0]) || (br1 >= 0 && ft.rowany[br1]) || (br2 >= 0 && ft.rowany[br2]) || (br3 >= 0 && ft.rowany[br3]);
+}
+
+// x mask of a row covered by brick rows b0..b3 (bit set = voxel inside an occupied brick), word `w` of it
+__device__ __forceinline__ uint32_t row_mask_word(const FusedParams& p, int b0, int b1, int b2, int b3, int w) {
+  uint32_t comb = 0;
+  if (b0 >= 0) comb |= __ldg(p.rowmask + (size_t)b0 * p.mask_words + w);
+  if (b1 >= 0) comb |= __ldg(p.rowmask + (size_t)b1 * p.mask_words + w);
+  if (b2 >= 0) comb |= __ldg(p.rowmask + (size_t)b2 * p.mask_words + w);
+  if (b3 >= 0) comb |= __ldg(p.rowmask + (size_t)b3 * p.mask_words + w);
+  return comb;
+}
+
+// One fill item with per-lane stores (k_integrate_fused): rows [row0, row1), at most 32. Runs of rows without occupied
+// bricks are streamed with 16-byte stores, the others consult the row bitmask per 4-voxel group.
 template <bool WEIGHT>
-__device__ __forceinline__ void fill_rows(const FusedParams& p, const FillTables& ft, uint32_t row0, uint32_t row1, int lane,
-                                          FillSource fs = FillSource{0u, 0u}) {
-  const int X = p.ip.X, Y = p.ip.Y;
+__device__ __forceinline__ void fill_rows(const FusedParams& p, const FillTables& ft, uint32_t row0, uint32_t row1, int lane) {
+  const int X = p.ip.X;
   const float4 v4 = make_float4(p.fill_value, p.fill_value, p.fill_value, p.fill_value);
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
   const bool vec = (X & 3) == 0;
-  int br0 = -1, br1 = -1, br2 = -1, br3 = -1;
-  bool any = false;
-  if (row0 + (uint32_t)lane < row1) {
-    const uint32_t row = row0 + (uint32_t)lane;
-    const int z = (int)(row / (uint32_t)Y), y = (int)(row - (uint32_t)z * (uint32_t)Y);
-    const int cy0 = ft.cand_y[2 * y], cy1 = ft.cand_y[2 * y + 1], cz0 = ft.cand_z[2 * z], cz1 = ft.cand_z[2 * z + 1];
-    br0 = (cy0 >= 0 && cz0 >= 0) ? cz0 * p.nby + cy0 : -1;
-    br1 = (cy1 >= 0 && cz0 >= 0) ? cz0 * p.nby + cy1 : -1;
-    br2 = (cy0 >= 0 && cz1 >= 0) ? cz1 * p.nby + cy0 : -1;
-    br3 = (cy1 >= 0 && cz1 >= 0) ? cz1 * p.nby + cy1 : -1;
-    any = (br0 >= 0 && ft.rowany[br0]) || (br1 >= 0 && ft.rowany[br1]) || (br2 >= 0 && ft.rowany[br2]) || (br3 >= 0 && ft.rowany[br3]);
-  }
+  int br0, br1, br2, br3;
+  const bool any = classify_row(p, ft, row0, row1, lane, br0, br1, br2, br3);
   uint32_t anymask = __ballot_sync(0xffffffffu, any);
   const int nrows = (int)(row1 - row0);
   if (nrows < 32) anymask |= ~0u << nrows;          // rows past the item count as "not clean": they end every run
@@ -272,31 +271,11 @@ __device__ __forceinline__ void fill_rows(const FusedParams& p, const FillTables
       float* t0 = p.ip.tsdf + (size_t)(row0 + (uint32_t)r) * X;
       float* w0 = WEIGHT ? p.ip.weight + (size_t)(row0 + (uint32_t)r) * X : nullptr;
       const int n = len * X;
-      if (vec && fs.src) {
-        // a run of clean rows is contiguous and 16-byte aligned: lanes issue one bulk store per buffer-sized piece
-        const uint32_t nbytes = (uint32_t)n * 4u;
-        for (uint32_t off = (uint32_t)lane * fs.bytes; off < nbytes; off += 32u * fs.bytes) {
-          const uint32_t sz = min(fs.bytes, nbytes - off);
-          bulk_store(reinterpret_cast<uint8_t*>(t0) + off, fs.src, sz);
-          if (WEIGHT) bulk_store(reinterpret_cast<uint8_t*>(w0) + off, fs.src + fs.bytes, sz);
-        }
-        bulk_commit();
-      } else if (vec) {
+      if (vec) {
         float4* t4 = reinterpret_cast<float4*>(t0) + lane;
         float4* w4 = WEIGHT ? reinterpret_cast<float4*>(w0) + lane : nullptr;
         const int n4 = n >> 2;
         int i = lane;
-        if (p.store_flavour == 1 && !WEIGHT) {
-          // experiment: plain (write-back) stores
-          for (; i + 96 < n4; i += 128, t4 += 128) { t4[0] = v4; t4[32] = v4; t4[64] = v4; t4[96] = v4; }
-        } else if (p.store_flavour == 2 && !WEIGHT) {
-          // experiment: 32-byte stores, lane covers float4 pair (2*lane, 2*lane+1)
-          float4* q = reinterpret_cast<float4*>(t0) + 2 * lane;
-          int j = 2 * lane;
-          for (; j + 192 + 1 < n4; j += 256, q += 256) { st_v8(q, v4); st_v8(q + 64, v4); st_v8(q + 128, v4); st_v8(q + 192, v4); }
-          for (; j + 1 < n4; j += 64, q += 64) st_v8(q, v4);
-          i = n4; 
-        }
         for (; i + 96 < n4; i += 128, t4 += 128) {
           __stcs(t4, v4); __stcs(t4 + 32, v4); __stcs(t4 + 64, v4); __stcs(t4 + 96, v4);
           if (WEIGHT) { __stcs(w4, z4); __stcs(w4 + 32, z4); __stcs(w4 + 64, z4); __stcs(w4 + 96, z4); w4 += 128; }
@@ -313,78 +292,12 @@ __device__ __forceinline__ void fill_rows(const FusedParams& p, const FillTables
     }
     const int b0 = __shfl_sync(0xffffffffu, br0, r), b1 = __shfl_sync(0xffffffffu, br1, r);
     const int b2 = __shfl_sync(0xffffffffu, br2, r), b3 = __shfl_sync(0xffffffffu, br3, r);
-    if (vec && fs.src && X <= 1024 && (uint32_t)X * 4u <= fs.bytes) {
-      // Bulk path for rows that cross occupied bricks. Consecutive rows covered by the same brick rows share one x mask:
-      // its runs of voxels to clear are found once (lane k keeps run k) and every row of the group then costs one bulk
-      // store per run for the 16-byte aligned interior plus up to six scalar stores at its ragged ends.
-      const uint32_t same = __ballot_sync(0xffffffffu, any && br0 == b0 && br1 == b1 && br2 == b2 && br3 == b3) >> r;
-      const int glen = min((same == 0xffffffffu) ? 32 : __ffs((int)~same) - 1, nrows - r);
-      uint32_t comb = 0xffffffffu;                         // words past the row count as occupied
-      if (lane < p.mask_words) {
-        comb = 0;
-        if (b0 >= 0) comb |= __ldg(p.rowmask + (size_t)b0 * p.mask_words + lane);
-        if (b1 >= 0) comb |= __ldg(p.rowmask + (size_t)b1 * p.mask_words + lane);
-        if (b2 >= 0) comb |= __ldg(p.rowmask + (size_t)b2 * p.mask_words + lane);
-        if (b3 >= 0) comb |= __ldg(p.rowmask + (size_t)b3 * p.mask_words + lane);
-        if (lane * 32 + 32 > X) comb |= ~0u << (X - lane * 32);      // bits past the last voxel of the row
-      }
-      // transitions: a run to clear starts where a 0 follows a 1 (or the row begins), and ends where a 1 follows a 0
-      uint32_t prev = __shfl_up_sync(0xffffffffu, comb >> 31, 1);
-      if (lane == 0) prev = 1u;
-      const uint32_t t = comb ^ ((comb << 1) | prev);
-      uint32_t starts = t & ~comb, ends = t & comb;
-      int ra = 0, rb = 0, nruns = 0;
-      for (;;) {
-        const uint32_t bs = __ballot_sync(0xffffffffu, starts != 0u);
-        if (bs == 0u) break;
-        const int ls = __ffs((int)bs) - 1;
-        const uint32_t sw = __shfl_sync(0xffffffffu, starts, ls);
-        const int s_pos = ls * 32 + __ffs((int)sw) - 1;
-        if (lane == ls) starts &= starts - 1u;
-        const uint32_t be = __ballot_sync(0xffffffffu, ends != 0u);
-        int e_pos = X;                                     // a run that reaches a 1024-voxel row's end has no closing transition
-        if (be != 0u) {
-          const int le = __ffs((int)be) - 1;
-          const uint32_t ew = __shfl_sync(0xffffffffu, ends, le);
-          e_pos = le * 32 + __ffs((int)ew) - 1;
-          if (lane == le) ends &= ends - 1u;
-        }
-        if (lane == (nruns & 31)) { ra = s_pos; rb = e_pos; }
-        ++nruns;
-        if (nruns == 32) break;
-      }
-      if (nruns < 32 || __ballot_sync(0xffffffffu, starts != 0u) == 0u) {
-        const int a4 = min((ra + 3) & ~3, rb), b4 = max(rb & ~3, a4);       // aligned interior [a4, b4)
-        for (int g = 0; g < glen; ++g) {
-          float* trow = p.ip.tsdf + (size_t)(row0 + (uint32_t)(r + g)) * X;
-          float* wrow = WEIGHT ? p.ip.weight + (size_t)(row0 + (uint32_t)(r + g)) * X : nullptr;
-          if (lane < nruns) {
-            if (b4 > a4) {
-              bulk_store(trow + a4, fs.src, (uint32_t)(b4 - a4) * 4u);
-              if (WEIGHT) bulk_store(wrow + a4, fs.src + fs.bytes, (uint32_t)(b4 - a4) * 4u);
-            }
-            for (int x = ra; x < a4; ++x) { trow[x] = p.fill_value; if (WEIGHT) wrow[x] = 0.0f; }
-            for (int x = b4; x < rb; ++x) { trow[x] = p.fill_value; if (WEIGHT) wrow[x] = 0.0f; }
-          }
-        }
-        bulk_commit();
-        r += glen;
-        continue;
-      }
-      // more than 32 runs in one row: the per-group path below
-    }
     float* trow = p.ip.tsdf + (size_t)(row0 + (uint32_t)r) * X;
     float* wrow = WEIGHT ? p.ip.weight + (size_t)(row0 + (uint32_t)r) * X : nullptr;
     ++r;
     for (int chunk = 0; chunk * 1024 < X; ++chunk) {
-      uint32_t comb = 0;
       const int w = chunk * 32 + lane;
-      if (w < p.mask_words) {
-        if (b0 >= 0) comb |= __ldg(p.rowmask + (size_t)b0 * p.mask_words + w);
-        if (b1 >= 0) comb |= __ldg(p.rowmask + (size_t)b1 * p.mask_words + w);
-        if (b2 >= 0) comb |= __ldg(p.rowmask + (size_t)b2 * p.mask_words + w);
-        if (b3 >= 0) comb |= __ldg(p.rowmask + (size_t)b3 * p.mask_words + w);
-      }
+      const uint32_t comb = w < p.mask_words ? row_mask_word(p, b0, b1, b2, b3, w) : 0u;
       const int xbase = chunk * 1024;
       if (vec) {
         const int jn = min(8, groups - chunk * 8);
@@ -414,22 +327,132 @@ __device__ __forceinline__ void fill_rows(const FusedParams& p, const FillTables
   }
 }
 
-// Draw fill items from the global counter until the slab's rows are exhausted (whole warp).
-// `batch` items are drawn per atomic: the round trip to the counter is the latency of a fill item once its stores are
-// asynchronous.
+// ---- the clear by TMA bulk stores (staged integrator) ---------------------------------------------------------------
+// cp.async.bulk shared -> global: one instruction moves up to a whole buffer of cleared voxels, asynchronously, so the
+// issuing warp is not held by the store queue the way per-lane stores hold it (a warp streams only ~4 B/clk of those).
+__device__ __forceinline__ void bulk_store(void* dst, uint32_t src_smem, uint32_t bytes, uint64_t policy) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst), "r"(src_smem), "r"(bytes), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// Source of the bulk stores: a shared-memory buffer holding `bytes` of cleared voxels (and, for a separate weight volume,
+// as many zero bytes behind it); policy: their L2 cache hint (evict_first); drop: measurement hook, nothing is stored.
+struct FillSource { uint32_t src, bytes; bool drop; uint64_t policy; };
+
+// One fill item, rows [row0, row1), at most 32; requires X % 4 == 0, X <= 1024 and a buffer of at least one row.
+// A run of rows without occupied bricks is contiguous, 16-byte aligned memory: one bulk store per buffer-sized piece.
+// Consecutive rows that cross occupied bricks and are covered by the same brick rows share one x mask: its runs of
+// voxels to clear are found once (lane k keeps run k) and every row of the group then costs one bulk store per run for
+// the 16-byte aligned interior plus up to six scalar stores at its ragged ends.
 template <bool WEIGHT>
-__device__ __forceinline__ void fill_loop(const FusedParams& p, const FillTables& ft, int lane, FillSource fs = FillSource{0u, 0u}, unsigned batch = 1u) {
-  for (;;) {
-    unsigned it0 = 0;
-    if (lane == 0) it0 = atomicAdd(p.work + 1, batch);
-    it0 = __shfl_sync(0xffffffffu, it0, 0);
-    if (it0 >= p.fill_items) break;
-    for (unsigned it = it0; it < min(it0 + batch, p.fill_items); ++it) {
-      const uint32_t r0 = p.row_begin + it * (uint32_t)p.fill_rows;
-      fill_rows<WEIGHT>(p, ft, r0, min(r0 + (uint32_t)p.fill_rows, p.row_end), lane, fs);
+__device__ __forceinline__ void fill_rows_bulk(const FusedParams& p, const FillTables& ft, uint32_t row0, uint32_t row1, int lane, const FillSource& fs) {
+  const int X = p.ip.X;
+  int br0, br1, br2, br3;
+  const bool any = classify_row(p, ft, row0, row1, lane, br0, br1, br2, br3);
+  uint32_t anymask = __ballot_sync(0xffffffffu, any);
+  const int nrows = (int)(row1 - row0);
+  if (nrows < 32) anymask |= ~0u << nrows;          // rows past the item count as "not clean": they end every run
+  for (int r = 0; r < nrows;) {
+    if (!((anymask >> r) & 1u)) {
+      const int run = min(__ffs((int)(anymask >> r)) - 1, nrows - r);
+      const int len = (anymask >> r) ? run : nrows - r;
+      uint8_t* t0 = reinterpret_cast<uint8_t*>(p.ip.tsdf + (size_t)(row0 + (uint32_t)r) * X);
+      uint8_t* w0 = WEIGHT ? reinterpret_cast<uint8_t*>(p.ip.weight + (size_t)(row0 + (uint32_t)r) * X) : nullptr;
+      const uint32_t nbytes = (uint32_t)(len * X) * 4u;
+      for (uint32_t off = (uint32_t)lane * fs.bytes; off < nbytes; off += 32u * fs.bytes) {
+        if (fs.drop) continue;
+        const uint32_t sz = min(fs.bytes, nbytes - off);
+        bulk_store(t0 + off, fs.src, sz, fs.policy);
+        if (WEIGHT) bulk_store(w0 + off, fs.src + fs.bytes, sz, fs.policy);
+      }
+      bulk_commit();
+      r += len;
+      continue;
     }
+    const int b0 = __shfl_sync(0xffffffffu, br0, r), b1 = __shfl_sync(0xffffffffu, br1, r);
+    const int b2 = __shfl_sync(0xffffffffu, br2, r), b3 = __shfl_sync(0xffffffffu, br3, r);
+    const uint32_t same = __ballot_sync(0xffffffffu, any && br0 == b0 && br1 == b1 && br2 == b2 && br3 == b3) >> r;
+    const int glen = min((same == 0xffffffffu) ? 32 : __ffs((int)~same) - 1, nrows - r);
+    uint32_t comb = 0xffffffffu;                         // words past the row count as occupied
+    if (lane < p.mask_words) {
+      comb = row_mask_word(p, b0, b1, b2, b3, lane);
+      if (lane * 32 + 32 > X) comb |= ~0u << (X - lane * 32);      // bits past the last voxel of the row
+    }
+    // transitions: a run to clear starts where a 0 follows a 1 (or the row begins), and ends where a 1 follows a 0
+    uint32_t prev = __shfl_up_sync(0xffffffffu, comb >> 31, 1);
+    if (lane == 0) prev = 1u;
+    const uint32_t t = comb ^ ((comb << 1) | prev);
+    uint32_t starts = t & ~comb, ends = t & comb;
+    int ra = 0, rb = 0, nruns = 0;
+    for (;;) {
+      const uint32_t bs = __ballot_sync(0xffffffffu, starts != 0u);
+      if (bs == 0u) break;
+      const int ls = __ffs((int)bs) - 1;
+      const uint32_t sw = __shfl_sync(0xffffffffu, starts, ls);
+      const int s_pos = ls * 32 + __ffs((int)sw) - 1;
+      if (lane == ls) starts &= starts - 1u;
+      const uint32_t be = __ballot_sync(0xffffffffu, ends != 0u);
+      int e_pos = X;                                     // a run that reaches a 1024-voxel row's end has no closing transition
+      if (be != 0u) {
+        const int le = __ffs((int)be) - 1;
+        const uint32_t ew = __shfl_sync(0xffffffffu, ends, le);
+        e_pos = le * 32 + __ffs((int)ew) - 1;
+        if (lane == le) ends &= ends - 1u;
+      }
+      if (nruns >= 32) {
+        // more runs than lanes (a row alternating faster than 32 bricks): the rest with per-lane scalar stores
+        for (int g = 0; g < glen; ++g) {
+          float* trow = p.ip.tsdf + (size_t)(row0 + (uint32_t)(r + g)) * X;
+          float* wrow = WEIGHT ? p.ip.weight + (size_t)(row0 + (uint32_t)(r + g)) * X : nullptr;
+          for (int x = s_pos + lane; x < e_pos; x += 32) { trow[x] = p.fill_value; if (WEIGHT) wrow[x] = 0.0f; }
+        }
+      } else if (lane == nruns) {
+        ra = s_pos; rb = e_pos;
+      }
+      ++nruns;
+    }
+    const int a4 = min((ra + 3) & ~3, rb), b4 = max(rb & ~3, a4);       // aligned interior [a4, b4) of this lane's run
+    for (int g = 0; g < glen; ++g) {
+      float* trow = p.ip.tsdf + (size_t)(row0 + (uint32_t)(r + g)) * X;
+      float* wrow = WEIGHT ? p.ip.weight + (size_t)(row0 + (uint32_t)(r + g)) * X : nullptr;
+      if (lane < nruns) {
+        if (b4 > a4 && !fs.drop) {
+          bulk_store(trow + a4, fs.src, (uint32_t)(b4 - a4) * 4u, fs.policy);
+          if (WEIGHT) bulk_store(wrow + a4, fs.src + fs.bytes, (uint32_t)(b4 - a4) * 4u, fs.policy);
+        }
+        for (int x = ra; x < a4; ++x) { trow[x] = p.fill_value; if (WEIGHT) wrow[x] = 0.0f; }
+        for (int x = b4; x < rb; ++x) { trow[x] = p.fill_value; if (WEIGHT) wrow[x] = 0.0f; }
+      }
+    }
+    bulk_commit();
+    r += glen;
   }
-  if (fs.src) bulk_wait_all();      // the buffer must outlive the copies that read it
+}
+
+// Draw fill items from the global counter until the slab's rows are exhausted (whole warp).
+template <bool WEIGHT>
+__device__ __forceinline__ void fill_loop(const FusedParams& p, const FillTables& ft, int lane) {
+  for (;;) {
+    unsigned it = 0;
+    if (lane == 0) it = atomicAdd(p.work + 1, 1u);
+    it = __shfl_sync(0xffffffffu, it, 0);
+    if (it >= p.fill_items) break;
+    const uint32_t r0 = p.row_begin + it * (uint32_t)p.fill_rows;
+    fill_rows<WEIGHT>(p, ft, r0, min(r0 + (uint32_t)p.fill_rows, p.row_end), lane);
+  }
+}
+template <bool WEIGHT>
+__device__ __forceinline__ void fill_loop_bulk(const FusedParams& p, const FillTables& ft, int lane, const FillSource& fs) {
+  for (;;) {
+    unsigned it = 0;
+    if (lane == 0) it = atomicAdd(p.work + 1, 1u);
+    it = __shfl_sync(0xffffffffu, it, 0);
+    if (it >= p.fill_items) break;
+    const uint32_t r0 = p.row_begin + it * (uint32_t)p.fill_rows;
+    fill_rows_bulk<WEIGHT>(p, ft, r0, min(r0 + (uint32_t)p.fill_rows, p.row_end), lane, fs);
+  }
+  bulk_wait_all();      // the buffer must outlive the copies that read it
 }
 
 // ---- per-frame verdicts of the staged integrator ---------------------------------------------------------------------

@@ -35,7 +35,7 @@ struct StagedParams {
   uint32_t inv_span, tile_span, stage_bytes;   // smem regions: TMA destinations are 128-byte aligned
   uint32_t fill_src_off, fill_src_bytes;   // buffer of cleared voxels behind the stages (source of the clear's bulk stores); 0 bytes: none
   uint32_t tables_off;      // shared-memory copies of cand_y [2Y], cand_z [2Z] (int16) and rowany [nby*nbz] behind that
-  uint32_t n_rowany, fill_batch;
+  uint32_t n_rowany;
   uint32_t* err;            // [0] box overflow, [1] barrier time-out
   int debug;
 };
@@ -101,13 +101,25 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
-  asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-               ::"r"(dst), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+// L2 policies: the integrator's operands (a few tens of MB per frame) are re-read every frame and should survive the
+// 0.5 GB of clear traffic that streams through L2 in the same kernel, so loads ask for evict_last, the clear for evict_first.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
 }
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-               ::"r"(dst), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, int c4, uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;"
+               ::"r"(dst), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+               ::"r"(dst), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(policy) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
@@ -255,12 +267,13 @@ k_integrate_staged(const __grid_constant__ StagedParams p, const __grid_constant
   const IntegrateParams& ip = p.f.ip;
   using Shape = StagedShape<CWARPS>;
   constexpr int PWARP = Shape::kProducerWarp;
-  const FillSource fs{p.fill_src_bytes ? smem_u32(smem + p.fill_src_off) : 0u, p.fill_src_bytes};
+  const FillSource fs{p.fill_src_bytes ? smem_u32(smem + p.fill_src_off) : 0u, p.fill_src_bytes, (p.debug & 32) != 0, l2_policy_evict_first()};
 
   // ---- producer of one stage (one thread)
   auto producer = [&](const int stage) {
     tma_prefetch_desc(&map_inv);
     tma_prefetch_desc(&map_pairs);
+    const uint64_t keep = l2_policy_evict_last();
     const uint32_t n_occ = *ip.num_occupied;
     // occupied bricks that intersect the slab: the list ascends in brick id, hence in brick z, so they are one run [lo, hi)
     uint32_t lo = 0, hi = n_occ;
@@ -335,10 +348,10 @@ k_integrate_staged(const __grid_constant__ StagedParams p, const __grid_constant
       mbar_expect_tx(&s_full[stage], p.inv_bytes + (uint32_t)N * p.tile_bytes + zt_bytes);
       bulk_load(smem_u32(st) + ITEM_HDR_BYTES, ip.ztab + zb, zt_bytes, &s_full[stage]);
       const uint32_t dst = smem_u32(st) + STAGE_HDR_BYTES;
-      tma_load_5d(dst, &map_inv, &s_full[stage], 0, ixlo, iylo, izlo, 0);
+      tma_load_5d(dst, &map_inv, &s_full[stage], 0, ixlo, iylo, izlo, 0, keep);
 #pragma unroll
       for (int s = 0; s < N; ++s)
-        tma_load_3d(dst + p.inv_span + (uint32_t)s * p.tile_span, &map_pairs, &s_full[stage], (int)(f[s].x & 0xffffu), (int)(f[s].x >> 16), s);
+        tma_load_3d(dst + p.inv_span + (uint32_t)s * p.tile_span, &map_pairs, &s_full[stage], (int)(f[s].x & 0xffffu), (int)(f[s].x >> 16), s, keep);
       // the copies have landed: hand the stage to the consumers
       if (!mbar_wait(&s_full[stage], phase, p.err)) return;
       mbar_arrive(&s_ready[stage]);
@@ -369,7 +382,7 @@ k_integrate_staged(const __grid_constant__ StagedParams p, const __grid_constant
     }
   };
   // ---- clear stream: the clear warps from the start, everybody else once their own work is done
-  auto clear = [&]() { fill_loop<MODE == 1>(p.f, ft, lane, fs, p.fill_batch); };
+  auto clear = [&]() { fill_loop_bulk<MODE == 1>(p.f, ft, lane, fs); };
   const bool helpers_clear = !(p.debug & 16);
   // each role's code sits behind its own setmaxnreg, so that ptxas allocates it against that budget
   if (warp < PWARP) {
@@ -588,6 +601,9 @@ int staged_prepare(rr_ctx* c) {
     max_nx = std::max(max_nx, r[1] - r[0]); max_ny = std::max(max_ny, r[3] - r[2]); max_nz = std::max(max_nz, r[5] - r[4]);
   }
   if (max_nx <= 0 || max_ny <= 0 || max_nz <= 0) return RR_OK;
+  // the clear's bulk stores need 16-byte aligned rows, a row mask of at most 32 words and a buffer of at least one row
+  const long fill_buf = std::max(4L, (long)tn.stage_bulk_fill) * 1024;
+  if ((X & 3) != 0 || X > 1024 || (long)X * 4 > fill_buf) return RR_OK;
   st.cwarps = consumer_warps(N);
   st.fwarps = 6;
   const int CT = st.cwarps * 32;
@@ -631,7 +647,6 @@ int staged_prepare(rr_ctx* c) {
   int smem_max = 0;
   cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device);
   const int weight_mode = c->cfg.store_weight == RR_VOXELS_F32_WEIGHT ? 2 : 1;
-  const long fill_buf = tn.stage_bulk_fill > 0 ? (long)tn.stage_bulk_fill * 1024 : 0;      // bytes of cleared voxels for the bulk stores
   const long tables = ((long)(4 * (Y + Z)) + (long)c->bricks.res[1] * c->bricks.res[2] + 127) & ~127L;      // cand_y, cand_z, rowany
   const long budget = ((long)smem_max - 1024 - fill_buf * weight_mode - tables) / 2 - STAGE_HDR_BYTES;           // per stage, after the header
   const long inv_bytes = (long)N * BZ * BY * BX * 16, inv_span = (inv_bytes + 127) & ~127L;
@@ -748,10 +763,8 @@ int launch_integrate_staged(rr_ctx* c, const IntegrateParams& p, int mode, bool*
   sp.err = st.d_err;
   sp.fill_src_off = 2 * st.stage_bytes; sp.fill_src_bytes = st.fill_src_bytes;
   sp.tables_off = st.tables_off; sp.n_rowany = c->bricks.res[1] * c->bricks.res[2];
-  sp.fill_batch = (uint32_t)std::max(1, tunables().stage_fill_batch);
   if (tunables().stage_debug & 1) sp.f.fill_items = 0;
   sp.debug = tunables().stage_debug;
-  sp.f.store_flavour = (tunables().stage_debug >> 8) & 3;
   // the work counters were reset and this frame's verdicts written by k_bricks_update (launch_bricks_update)
   int rc;
   switch (c->N) {
