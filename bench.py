@@ -9,8 +9,12 @@ depth frames inside the timed region, D2H of the occupied-brick count the refere
 
   python bench.py --gpus N --steps K --warmup W          # our arm (torchrun launches N ranks for N > 1)
   python bench.py --impl reference ...                   # the reference's algorithm on the host cores (oracle port)
-"""
+
+Beside the headline the line carries sub-records measured in the same run: `dense` (setUseBricks(false)), `config5`
+(BASELINE.json configs[4]: 8 sensors, 1024^3 half2 voxels, the same slab code at every N), the view path, and for N > 1
+`verified` (every rank's slab and the composited view compared bit for bit with a single-context run on rank 0)."""
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -32,6 +36,7 @@ EXTENT = 2.048
 BBOX = ((-EXTENT / 2, 1.1 - EXTENT / 2, -EXTENT / 2), (EXTENT / 2, 1.1 + EXTENT / 2, EXTENT / 2))
 LIMIT, BRICK, MIN_VOX = 0.01, 0.1, 10
 N_FRAMES = 2                  # distinct synthetic frame sets cycled through the steps
+VW, VH = 1280, 720            # view of the raymarch sub-record
 # one description of the workload for both arms (the driver compares the strings)
 WORKLOAD = (f"4 Kinect-v2 sensors 512x424 depth + 1280x1080 RGB8, {R}^3 R32F TSDF ({EXTENT} m cube), inverse calibration volumes "
             f"128x128x256, step = clear bricks + 5 pre-process passes + brick update + integrate")
@@ -66,11 +71,11 @@ def measured_traffic(bricks):
     return int(t["dram_bytes_read"] + t["dram_bytes_write"]), t.get("source")
 
 
-def make_inputs(res=R):
+def make_inputs(res=R, n_sensors=N_SENSORS, n_frames=N_FRAMES):
     from rrpy import synth
     voxel = EXTENT / res
-    scenes = [synth.make_scene(N=N_SENSORS, W=W, H=H, CW=CW, CH=CH, cv_res=CV_RES, bbox=BBOX, frame=0, seed=1234)]
-    scenes += [synth.rerender(scenes[0], 7 * t) for t in range(1, N_FRAMES)]
+    scenes = [synth.make_scene(N=n_sensors, W=W, H=H, CW=CW, CH=CH, cv_res=CV_RES, bbox=BBOX, frame=0, seed=1234)]
+    scenes += [synth.rerender(scenes[0], 7 * t) for t in range(1, n_frames)]
     inv = synth.analytic_inverse(scenes[0], INV_RES)
     return scenes, inv, np.float32(voxel)
 
@@ -118,17 +123,240 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def algorithmic_bytes(res, n_occ_vox, covered_inv_vox, nbricks, bricks):
-    """bytes one integrate launch must move."""
+def algorithmic_bytes(res, n_occ_vox, covered_inv_vox, nbricks, bricks, n_sensors=N_SENSORS, slab_frac=1.0):
+    """bytes one integrate launch must move. Bricked: 4·XYZ (clear) + 4·V_occ (overwrite) +
+    16·covered·N (inverse volumes where occupied bricks cover them) + 16·P·N (depth_b 8 + quality 4 + silhouette 4 per
+    pixel) + 4·#bricks. Dense: 4·XYZ + 16·V_inv·N + 16·P·N."""
     P = W * H
+    vinv = INV_RES[0] * INV_RES[1] * INV_RES[2]
     if not bricks:
-        return 4 * res ** 3 + 16 * INV_RES[0] * INV_RES[1] * INV_RES[2] * N_SENSORS + 16 * P * N_SENSORS
-    return 4 * res ** 3 + 4 * n_occ_vox + 16 * covered_inv_vox * N_SENSORS + 16 * P * N_SENSORS + 4 * nbricks
+        return int(4 * res ** 3 * slab_frac + 16 * vinv * n_sensors * slab_frac + 16 * P * n_sensors)
+    return int(4 * res ** 3 * slab_frac + 4 * n_occ_vox + 16 * covered_inv_vox * n_sensors + 16 * P * n_sensors + 4 * nbricks)
+
+
+class Rig:
+    """One rank of one configuration: a context, its frame sets (pinned host + device), the slab, the broadcast
+    pipeline for N > 1, and the timed loops."""
+
+    def __init__(self, torch, dist, rank, world, local, scenes, inv, voxel, n_sensors, res, bricks, fmt):
+        from rrpy import capi, multigpu
+        self.torch, self.dist, self.rank, self.world, self.local = torch, dist, rank, world, local
+        self.capi, self.multigpu = capi, multigpu
+        self.res, self.bricks, self.n_sensors = res, bricks, n_sensors
+        self.dev = torch.device("cuda", local)
+        fu = self.fu = capi.Fusion(n_sensors, W, H, CW, CH, device=local)
+        capi.load_scene(fu, scenes[0], inv)
+        fu.configure(limit=LIMIT, voxel_size=voxel, brick_size=BRICK, min_voxels=MIN_VOX, use_bricks=bricks, store_weight=fmt)
+        assert tuple(int(v) for v in fu.volume_res()) == (res, res, res), fu.volume_res()
+        # z-slab of this rank: contiguous slices, remainder spread over the first ranks
+        self.z0, self.z1 = multigpu.slab_range(rank, world, res)
+        self.slab_how = "single volume"
+        self.slabs = [(0, res)]
+        if world > 1 and bricks:
+            # slab boundaries balanced on the brick occupancy of one pre-processed frame set (every rank computes the same
+            # counters, so every rank derives the same boundaries): equal-thickness slabs leave the outer ranks idle
+            fu.upload_frames(scenes[0].color, scenes[0].depth)
+            fu.bricks_clear(); fu.preprocess(); fu.bricks_update(sync=True)
+            _, occ0 = fu.download_bricks()
+            self.slabs = multigpu.balanced_slabs(world, res, res * res, fu.brick_ranges(), occ0)
+            self.z0, self.z1 = self.slabs[rank]
+            self.slab_how = f"z-slabs balanced on occupied-brick cost: {self.slabs}"
+        elif world > 1:
+            self.slabs = [multigpu.slab_range(r, world, res) for r in range(world)]
+            self.slab_how = "equal z-slabs"
+        fu.set_slab(self.z0, self.z1)
+        halo = multigpu.halo(LIMIT, res) if world > 1 else 0
+        self.zc0, self.zc1 = max(0, self.z0 - halo), min(res, self.z1 + halo)     # slices this rank actually writes (slab + halo)
+        self.stream = torch.cuda.ExternalStream(fu.stream(), device=self.dev)
+        # frame sets: pinned host copies (e2e) and device copies (value)
+        self.h_color = [torch.from_numpy(s.color).pin_memory() for s in scenes]
+        self.h_depth = [torch.from_numpy(s.depth).pin_memory() for s in scenes]
+        self.d_color = [t.to(self.dev) for t in self.h_color]
+        self.d_depth = [t.to(self.dev) for t in self.h_depth]
+        self.cb, self.db = self.h_color[0].numel(), self.h_depth[0].numel() * 4
+        self.h_src_c, self.h_src_d, self.h_src_cb, self.h_src_db = self.h_color, self.h_depth, self.cb, self.db
+        self.nf = len(scenes)
+        # N > 1: one packed broadcast per frame set, double-buffered (the broadcast of set i+1 overlaps the fusion of set i)
+        self.fb = multigpu.FrameBroadcaster(dist, self.dev, self.cb, self.db, src=0) if world > 1 else None
+        if world > 1 and rank == 0:
+            # the ingest rank holds every frame set packed like a server message (colour bytes then depth bytes)
+            self.d_packed = [torch.cat([c.reshape(-1), d.reshape(-1).view(torch.uint8)]) for c, d in zip(self.d_color, self.d_depth)]
+            self.h_packed = [torch.cat([c.reshape(-1), d.reshape(-1).view(torch.uint8)]).pin_memory() for c, d in zip(self.h_color, self.h_depth)]
+        else:
+            self.d_packed = self.h_packed = [None] * self.nf
+
+    def consume_broadcast(self):
+        packed, slot = self.fb.consume(self.stream)
+        self.fu.upload_frames_ptr(packed.data_ptr(), self.cb, packed.data_ptr() + self.cb, self.db, device=True)   # into the current frame slot, on the compute stream
+        self.fb.release(slot, self.stream)
+
+    def step_device(self, i):
+        k = i % self.nf
+        fu, fb = self.fu, self.fb
+        if self.world > 1:
+            # each frame set arrives on rank 0 and is broadcast over NVLink (NCCL) before every GPU pre-processes it
+            if fb.in_flight() == 0:
+                fb.issue(packed=self.d_packed[k])                         # pipeline prologue (first step only)
+            self.consume_broadcast()
+            # the next set's broadcast is enqueued BEFORE this set's kernels: NCCL's CTAs then share the SMs with the small
+            # pre-processing kernels instead of queueing behind the persistent integrate kernel, which fills every SM
+            fb.issue(packed=self.d_packed[(i + 1) % self.nf])
+            fu.fuse_frame()
+        else:
+            fu.upload_frames_ptr(self.d_color[k].data_ptr(), self.cb, self.d_depth[k].data_ptr(), self.db, device=True)
+            fu.fuse_frame()                  # one call; a captured CUDA graph while stage timing is off, direct launches otherwise
+
+    def step_host(self, i):
+        """The reference's ingest is double-buffered (reader thread fills the back PBO while the front one is drawn,
+        double_pixel_buffer.cpp): frame set i was staged during step i-1; this step swaps it in, starts the host->device
+        copy of frame set i+1 on the copy stream, and runs the fused frame on set i: one rr_fuse_frame (a CUDA-graph launch)
+        plus rr_bricks_count, the 4-byte device->host read of the occupied-brick count the reference does every frame.
+        Every step issues one host->device copy of a whole frame set, all inside the timed region."""
+        k, k1 = i % self.nf, (i + 1) % self.nf
+        fu, fb = self.fu, self.fb
+        if self.world > 1:
+            # rank 0 copies the pinned host frame set into the broadcast slot (its host->device copy), then one broadcast
+            if fb.in_flight() == 0:
+                fb.issue(packed=self.h_packed[k])
+            self.consume_broadcast()
+            fb.issue(packed=self.h_packed[k1])                            # next set's host->device copy + broadcast run beside this set's kernels
+            fu.fuse_frame()
+            return fu.bricks_count()
+        fu.swap_frames()
+        fu.stage_frames_ptr(self.h_src_c[k1].data_ptr(), self.h_src_cb, self.h_src_d[k1].data_ptr(), self.h_src_db)
+        fu.fuse_frame()
+        return fu.bricks_count()
+
+    def barrier(self):
+        if self.fb is not None:
+            while self.fb.in_flight():                     # drain the pipeline: every rank consumes what every rank issued
+                self.consume_broadcast()
+        self.fu.synchronize()
+        self.torch.cuda.synchronize(self.dev)
+        if self.world > 1:
+            self.dist.barrier()
+
+    def timed(self, step, steps, warmup, with_stage_timers=False, finish=None):
+        torch, fu = self.torch, self.fu
+        for i in range(warmup):
+            step(i)
+        self.barrier()
+        fu.set_timing(1 if with_stage_timers else 0)
+        fu.stage_stats("2integrate"); fu.stage_stats("1preprocess")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = fu.launch_count()
+        e0.record(self.stream)
+        h0 = time.perf_counter()
+        for i in range(steps):
+            step(warmup + i)
+        self.host_ms = (time.perf_counter() - h0) * 1e3 / steps      # host time to ENQUEUE one step (diagnostic)
+        if finish:
+            finish()
+        e1.record(self.stream)
+        self.barrier()
+        self.launches = fu.launch_count() - l0
+        ms = e0.elapsed_time(e1)
+        fu.set_timing(0)
+        return self.max_over_ranks(ms)
+
+    def max_over_ranks(self, v):
+        if self.world > 1:
+            t = self.torch.tensor([v], device=self.dev)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            return float(t.item())
+        return float(v)
+
+    def occupancy(self):
+        """Occupied bricks of the last frame and the voxels of them this rank evaluates (slab + halo)."""
+        n_occ, ratio = self.fu.bricks_update(sync=True)
+        counters, occ = self.fu.download_bricks()
+        rr = self.fu.brick_ranges()[occ]
+        vox = int(((rr[:, 1] - rr[:, 0]) * (rr[:, 3] - rr[:, 2]) *
+                   (np.clip(rr[:, 5], self.zc0, self.zc1) - np.clip(rr[:, 4], self.zc0, self.zc1)).clip(0)).sum()) if len(occ) else 0
+        return int(n_occ), float(ratio), vox, len(counters)
+
+    def roofline(self, int_avg_ms, n_occ_vox, nbricks):
+        slab_frac = (self.zc1 - self.zc0) / self.res
+        covered = int(INV_RES[0] * INV_RES[1] * INV_RES[2] * min(1.0, n_occ_vox / max(1, self.res ** 3 * slab_frac)) * slab_frac)
+        abytes = algorithmic_bytes(self.res, n_occ_vox, covered, nbricks, self.bricks, self.n_sensors, slab_frac)
+        achieved = abytes / (int_avg_ms / 1e3) / 1e9 if int_avg_ms > 0 else 0.0
+        peak, peak_src = peaks()
+        return abytes, achieved, peak, peak_src
+
+    def close(self):
+        self.fu.close()
+
+
+def integrate_kernel_name(bricks, info):
+    if not bricks:
+        return "k_integrate_dense"
+    if info.get("staged"):
+        return ("k_integrate_staged (clear + occupied-brick integration, TMA-staged operands, one launch = the 2integrate stage; "
+                f"tile {info['tile']} px, z-chunk {info['zchunk']}, {info['smem_bytes']} B smem)")
+    return "k_integrate_fused (clear + occupied-brick integration, direct gathers)"
+
+
+def sub_record(torch, dist, rank, world, local, what, n_sensors, res, bricks, fmt, steps, scenes=None, inv=None, voxel=None):
+    """A secondary configuration through the same code path: frames device-resident (broadcast from rank 0 for N > 1),
+    one rr_fuse_frame per step, CUDA events over `steps` steps after 5 warm-up steps, stage timers in a second pass."""
+    if scenes is None:
+        scenes, inv, voxel = make_inputs(res, n_sensors, 1)
+    rig = Rig(torch, dist, rank, world, local, scenes, inv, voxel, n_sensors, res, bricks, fmt)
+    ms = rig.timed(rig.step_device, steps, 5) / steps
+    rig.timed(rig.step_device, max(10, steps // 2), 3, with_stage_timers=True)
+    int_ms, int_n = rig.fu.stage_stats("2integrate")
+    pre_ms, pre_n = rig.fu.stage_stats("1preprocess")
+    int_avg = int_ms / max(1, int_n)
+    n_occ, ratio, vox, nbricks = rig.occupancy()
+    abytes, achieved, peak, _ = rig.roofline(int_avg, vox, nbricks)
+    info = rig.fu.integrator_info()
+    out = {"what": what, "value": round(res ** 3 / ms / 1e6, 3), "unit": "Gvoxel-updates/s", "frames_per_s": round(1e3 / ms, 2),
+           "ms_per_step": round(ms, 5), "steps": steps,
+           "stages_ms": {"1preprocess": round(pre_ms / max(1, pre_n), 5), "2integrate": round(int_avg, 5)},
+           "roofline": {"achieved": round(achieved, 1), "frac": round(achieved / peak, 4), "algorithmic_bytes_per_launch": int(abytes),
+                        "kernel": integrate_kernel_name(bricks, info)},
+           "occupied_bricks": n_occ, "slabs": rig.slab_how if world > 1 else None}
+    rig.close()
+    return out
+
+
+def verify_against_single_context(torch, dist, rig, scenes, inv, voxel, bricks, mv, pr, records, view_once):
+    """Run once, untimed: every rank fuses frame set 0 into its slab and hashes the slices it owns; rank 0 also fuses the whole
+    volume on a second, unsharded context and hashes the same slice ranges, marches the same view there, and compares the
+    composited image of the sharded run with it bit for bit. True only if every slab and the view agree."""
+    from rrpy import capi
+    fu, dev, rank, world = rig.fu, rig.dev, rig.rank, rig.world
+    fu.upload_frames(scenes[0].color, scenes[0].depth)
+    fu.frame()
+    mine = fu.download_tsdf()[rig.z0:rig.z1]
+    digest = np.frombuffer(hashlib.sha256(mine.tobytes()).digest(), np.uint8).copy()
+    all_digests = [torch.empty(32, dtype=torch.uint8, device=dev) for _ in range(world)]
+    dist.all_gather(all_digests, torch.from_numpy(digest).to(dev))
+    view_once()
+    rig.barrier()
+    ok = True
+    if rank == 0:
+        rgba_s, depth_s = fu.composite(records.data_ptr(), 1, VW, VH, download=True)
+        ref = capi.Fusion(N_SENSORS, W, H, CW, CH, device=rig.local)
+        capi.load_scene(ref, scenes[0], inv)
+        ref.configure(limit=LIMIT, voxel_size=voxel, brick_size=BRICK, min_voxels=MIN_VOX, use_bricks=bricks)
+        ref.upload_frames(scenes[0].color, scenes[0].depth)
+        ref.frame()
+        full = ref.download_tsdf()
+        for r, (z0, z1) in enumerate(rig.slabs):
+            want = hashlib.sha256(full[z0:z1].tobytes()).digest()
+            ok = ok and bytes(all_digests[r].cpu().numpy().tobytes()) == want
+        rgba_r, depth_r = ref.raymarch(mv, pr, VW, VH, shade_mode=1)
+        ok = ok and np.array_equal(rgba_s.view(np.uint32), rgba_r.view(np.uint32)) and np.array_equal(depth_s.view(np.uint32), depth_r.view(np.uint32))
+        ref.close()
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.broadcast(flag, 0)
+    return bool(flag.item())
 
 
 def run_ours(args):
     import torch
-    from rrpy import capi
+    from rrpy import capi, multigpu, synth
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -141,247 +369,105 @@ def run_ours(args):
             os.environ["NCCL_DEBUG"] = "WARN"        # keeps NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         torch.cuda.set_device(local)
         import datetime
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=300))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    bricks = args.mode == "bricks"
 
     scenes, inv, voxel = make_inputs()
-    fu = capi.Fusion(N_SENSORS, W, H, CW, CH, device=local)
-    capi.load_scene(fu, scenes[0], inv)
-    bricks = args.mode == "bricks"
-    fu.configure(limit=LIMIT, voxel_size=voxel, brick_size=BRICK, min_voxels=MIN_VOX, use_bricks=bricks)
-    res = fu.volume_res()
-    assert tuple(int(v) for v in res) == (R, R, R), res
-    # z-slab of this rank: contiguous slices, remainder spread over the first ranks
-    from rrpy import multigpu
-    z0, z1 = multigpu.slab_range(rank, world, R)
-    slab_how = "single volume"
-    if world > 1 and bricks:
-        # slab boundaries balanced on the brick occupancy of one pre-processed frame set (every rank computes the same
-        # counters, so every rank derives the same boundaries): equal-thickness slabs leave the outer ranks idle
-        fu.upload_frames(scenes[0].color, scenes[0].depth)
-        fu.bricks_clear(); fu.preprocess(); fu.bricks_update(sync=True)
-        _, occ0 = fu.download_bricks()
-        slabs = multigpu.balanced_slabs(world, R, R * R, fu.brick_ranges(), occ0)
-        z0, z1 = slabs[rank]
-        slab_how = f"z-slabs balanced on occupied-brick cost: {slabs}"
-    elif world > 1:
-        slab_how = "equal z-slabs"
-    fu.set_slab(z0, z1)
-    halo = multigpu.halo(LIMIT, R) if world > 1 else 0
-    zc0, zc1 = max(0, z0 - halo), min(R, z1 + halo)          # slices this rank actually writes (slab + halo)
-
-    stream = torch.cuda.ExternalStream(fu.stream(), device=dev)
-    # frame sets: pinned host copies (e2e) and device copies (value)
-    h_color = [torch.from_numpy(s.color).pin_memory() for s in scenes]
-    h_depth = [torch.from_numpy(s.depth).pin_memory() for s in scenes]
-    d_color = [t.to(dev) for t in h_color]
-    d_depth = [t.to(dev) for t in h_depth]
-    cb, db = h_color[0].numel(), h_depth[0].numel() * 4
-    # N > 1: one packed broadcast per frame set, double-buffered (the broadcast of set i+1 overlaps the fusion of set i)
-    fb = multigpu.FrameBroadcaster(dist, dev, cb, db, src=0) if world > 1 else None
-    if world > 1 and rank == 0:
-        # the ingest rank holds every frame set packed like a server message (colour bytes then depth bytes): one copy per set
-        d_packed = [torch.cat([c.reshape(-1), d.reshape(-1).view(torch.uint8)]) for c, d in zip(d_color, d_depth)]
-        h_packed = [torch.cat([c.reshape(-1), d.reshape(-1).view(torch.uint8)]).pin_memory() for c, d in zip(h_color, h_depth)]
-    else:
-        d_packed = h_packed = [None] * N_FRAMES
-
-    def consume_broadcast():
-        packed, slot = fb.consume(stream)
-        fu.upload_frames_ptr(packed.data_ptr(), cb, packed.data_ptr() + cb, db, device=True)    # into the current frame slot, on the compute stream
-        fb.release(slot, stream)
-
-    def step_device(i):
-        k = i % N_FRAMES
-        if world > 1:
-            # each frame set arrives on rank 0 and is broadcast over NVLink (NCCL) before every GPU pre-processes it
-            if fb.in_flight() == 0:
-                fb.issue(packed=d_packed[k])                         # pipeline prologue (first step only)
-            consume_broadcast()
-            # the next set's broadcast is enqueued BEFORE this set's kernels: NCCL's CTAs then share the SMs with the small
-            # pre-processing kernels instead of queueing behind the persistent integrate kernel, which fills every SM
-            fb.issue(packed=d_packed[(i + 1) % N_FRAMES])
-            fu.fuse_frame()
-        else:
-            fu.upload_frames_ptr(d_color[k].data_ptr(), cb, d_depth[k].data_ptr(), db, device=True)
-            fu.fuse_frame()                  # one call; a captured CUDA graph while stage timing is off, direct launches otherwise
-
-    def step_host(i):
-        # the reference's ingest is double-buffered (reader thread fills the back PBO while the front one is drawn,
-        # double_pixel_buffer.cpp): frame set i was staged during step i-1; this step swaps it in, starts the host->device
-        # copy of frame set i+1 on the copy stream, and runs the fused frame on set i. Every step issues one 20 MB
-        # host->device copy and one 4-byte device->host read, all inside the timed region.
-        k = i % N_FRAMES
-        k1 = (i + 1) % N_FRAMES
-        if world > 1:
-            # rank 0 copies the pinned host frame set into the broadcast slot (its host->device copy), then one broadcast
-            if fb.in_flight() == 0:
-                fb.issue(packed=h_packed[k])
-            consume_broadcast()
-            fb.issue(packed=h_packed[k1])                            # next set's host->device copy + broadcast run beside this set's kernels
-            fu.bricks_clear(); fu.preprocess(); n = fu.bricks_update(sync=True); fu.integrate()
-        elif step_host.fused:
-            # one graph launch per frame set; the occupied-brick count the reference reads every frame is read when the frame
-            # set is done (rr_bricks_count: a 4-byte device->host read behind a stream sync)
-            fu.swap_frames()
-            fu.stage_frames_ptr(h_color[k1].data_ptr(), cb, h_depth[k1].data_ptr(), db)
-            fu.fuse_frame()
-            n = fu.bricks_count()
-        else:
-            fu.swap_frames()
-            fu.stage_frames_ptr(h_color[k1].data_ptr(), cb, h_depth[k1].data_ptr(), db)
-            fu.bricks_clear(); fu.preprocess(); n = fu.bricks_update(sync=True); fu.integrate()
-        return n
-
-    step_host.fused = False
-
-    def barrier():
-        if fb is not None:
-            while fb.in_flight():                     # drain the pipeline: every rank consumes what every rank issued
-                consume_broadcast()
-        fu.synchronize()
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-
-    def timed(step, steps, warmup, with_stage_timers, finish=None):
-        for i in range(warmup):
-            step(i)
-        barrier()
-        fu.set_timing(1 if with_stage_timers else 0)
-        fu.stage_stats("2integrate"); fu.stage_stats("1preprocess")
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = fu.launch_count()
-        e0.record(stream)
-        h0 = time.perf_counter()
-        for i in range(steps):
-            step(warmup + i)
-        timed.host_ms = (time.perf_counter() - h0) * 1e3 / steps      # host time to ENQUEUE one step (diagnostic)
-        if finish:
-            finish()
-        e1.record(stream)
-        barrier()
-        timed.launches = fu.launch_count() - l0
-        ms = e0.elapsed_time(e1)
-        fu.set_timing(0)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+    rig = Rig(torch, dist, rank, world, local, scenes, inv, voxel, N_SENSORS, R, bricks, capi.VOXELS_F32)
+    fu, stream = rig.fu, rig.stream
+    cb, db = rig.cb, rig.db
 
     sampler = ClockSampler(local, args.clock_ms) if (rank == 0 and args.clock_ms > 0) else None
-    ms_total = timed(step_device, args.steps, args.warmup, False)
-    gpu_launches = timed.launches
-    host_enqueue_ms = timed.host_ms
+    ms_total = rig.timed(rig.step_device, args.steps, args.warmup)
+    gpu_launches, host_enqueue_ms = rig.launches, rig.host_ms
     # stage breakdown and the dominant kernel's launch duration: the same steps again with CUDA-event stage timers on the
     # context's stream (timers need direct launches, so this pass is not the one `value` comes from)
     stage_steps = max(10, min(args.steps, 100))
-    ms_stage_pass = timed(step_device, stage_steps, 3, True)
+    ms_stage_pass = rig.timed(rig.step_device, stage_steps, 3, with_stage_timers=True)
     int_ms, int_n = fu.stage_stats("2integrate")
     pre_ms, pre_n = fu.stage_stats("1preprocess")
+
+    # ---- end to end from pinned host buffers ------------------------------------------------------------------------
+    e2e_warm = max(50, args.warmup)                 # >= 50 untimed steps: lets the PCIe link leave its idle state
     if world == 1:
-        fu.stage_frames_ptr(h_color[0].data_ptr(), cb, h_depth[0].data_ptr(), db)     # prologue of the ingest pipeline
+        fu.stage_frames_ptr(rig.h_color[0].data_ptr(), cb, rig.h_depth[0].data_ptr(), db)     # prologue of the ingest pipeline
     # the closing swap makes the compute stream (and so the end event) wait for the last staged copy: all K host->device
     # copies issued inside the timed region are also completed inside it
-    ms_e2e = timed(step_host, args.steps, max(50, args.warmup), False, finish=(fu.swap_frames if world == 1 else None))   # >= 50 untimed steps: lets the PCIe link leave its idle state
-    e2e_path = "call by call (rr_bricks_clear, rr_preprocess, rr_bricks_update with the count read mid-frame, rr_integrate)"
-    e2e_other = None
-    if world == 1:
-        # the same end-to-end step through rr_fuse_frame + rr_bricks_count (one graph launch, count read at the end of the frame
-        # set); both are public-API paths over the same host buffers - the headline e2e is the faster one, the other is kept beside it
-        step_host.fused = True
-        fu.stage_frames_ptr(h_color[0].data_ptr(), cb, h_depth[0].data_ptr(), db)
-        ms_fused = timed(step_host, args.steps, max(50, args.warmup), False, finish=fu.swap_frames)
-        step_host.fused = False
-        slow, fast = max(ms_e2e, ms_fused), min(ms_e2e, ms_fused)
-        fused_wins = ms_fused <= ms_e2e
-        e2e_other = {"path": e2e_path if fused_wins else "rr_fuse_frame + rr_bricks_count",
-                     "frames_per_s": round(args.steps / (slow / 1e3), 2)}
-        if fused_wins:
-            e2e_path = "rr_fuse_frame (one CUDA-graph launch per frame set) + rr_bricks_count (count read when the frame set is done)"
-        ms_e2e = fast
-    # what bounds e2e: the host->device link. Bandwidth of the same 20 MB pinned copy alone (CUDA events, copy stream idle).
+    ms_e2e = rig.timed(rig.step_host, args.steps, e2e_warm, finish=(fu.swap_frames if world == 1 else None))
+    e2e_path = ("rr_stage_frames / rr_swap_frames (20 MB host->device per step on a copy stream) + rr_fuse_frame (one CUDA-graph launch) + "
+                "rr_bricks_count (4-byte read when the frame set is done)") if world == 1 else \
+               "rank 0: pinned host -> broadcast slot, NCCL broadcast, every rank rr_fuse_frame + rr_bricks_count"
     link_gbs = None
-    e2e_dxt1 = None
+    e2e_streams = {}
     if world == 1:
+        # what bounds e2e: the host->device link. Bandwidth of the same 20 MB pinned copy alone (CUDA events, copy stream idle).
         l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n_copies = 50
         for _ in range(5):
-            d_color[0].copy_(h_color[0], non_blocking=True); d_depth[0].copy_(h_depth[0], non_blocking=True)
+            rig.d_color[0].copy_(rig.h_color[0], non_blocking=True); rig.d_depth[0].copy_(rig.h_depth[0], non_blocking=True)
         torch.cuda.synchronize(dev)
         l0.record()
         for _ in range(n_copies):
-            d_color[0].copy_(h_color[0], non_blocking=True); d_depth[0].copy_(h_depth[0], non_blocking=True)
+            rig.d_color[0].copy_(rig.h_color[0], non_blocking=True); rig.d_depth[0].copy_(rig.h_depth[0], non_blocking=True)
         l1.record()
         torch.cuda.synchronize(dev)
         link_gbs = (cb + db) * n_copies / (l0.elapsed_time(l1) / 1e3) / 1e9
-        # the same step fed the reference's default stream format (compress_rgb: 1, KinectCalibrationFile.cpp:94): DXT1
-        # colour blocks decoded on the device (rr_set_frame_format), float32 depth. Reported beside the RGB8 headline.
-        from rrpy import synth as synth_
-        h_dxt = [torch.from_numpy(np.stack([synth_.encode_dxt1(s.color[i]) for i in range(N_SENSORS)])).pin_memory() for s in scenes]
-        xb = h_dxt[0].numel()
-        fu.synchronize()
-        fu.set_frame_format(dxt1_color=True)
-
-        def step_host_dxt1(i):
-            k1 = (i + 1) % N_FRAMES
-            fu.swap_frames()
-            fu.stage_frames_ptr(h_dxt[k1].data_ptr(), xb, h_depth[k1].data_ptr(), db)
-            fu.bricks_clear(); fu.preprocess(); n = fu.bricks_update(sync=True); fu.integrate()
-            return n
-
-        fu.stage_frames_ptr(h_dxt[0].data_ptr(), xb, h_depth[0].data_ptr(), db)
-        ms_dxt = timed(step_host_dxt1, args.steps, max(50, args.warmup), False, finish=fu.swap_frames)
-        fps_dxt = args.steps / (ms_dxt / 1e3)
-        e2e_dxt1 = {"value": round(R ** 3 * fps_dxt / 1e9, 3), "unit": "Gvoxel-updates/s", "frames_per_s": round(fps_dxt, 2),
-                    "h2d_bytes_per_step": int(xb + db), "d2h_bytes_per_step": 4,
-                    "what": "same step, colour streamed as DXT1 blocks (the reference's default stream format) and decoded on the device"}
+        # the same step fed the reference's stream formats (compress_rgb: 1 is its default, KinectCalibrationFile.cpp:94):
+        # DXT1 colour blocks, and DXT1 + 8-bit sqrt-compressed depth, decoded on the device inside the captured frame graph
+        h_dxt = [torch.from_numpy(np.stack([synth.encode_dxt1(s.color[i]) for i in range(N_SENSORS)])).pin_memory() for s in scenes]
+        near_far = np.tile(np.array([0.5, 4.5], np.float32), (N_SENSORS, 1))
+        h_d8 = [torch.from_numpy(np.stack([synth.encode_depth8(s.depth[i], 0.5, 4.5) for i in range(N_SENSORS)])).pin_memory() for s in scenes]
+        for key, dxt1, d8 in (("dxt1_stream", True, False), ("dxt1_depth8_stream", True, True)):
+            fu.synchronize()
+            fu.set_frame_format(dxt1_color=dxt1, depth8=d8, near_far=near_far if d8 else None)
+            rig.h_src_c, rig.h_src_cb = h_dxt, h_dxt[0].numel()
+            rig.h_src_d, rig.h_src_db = (h_d8, h_d8[0].numel()) if d8 else (rig.h_depth, db)
+            fu.stage_frames_ptr(rig.h_src_c[0].data_ptr(), rig.h_src_cb, rig.h_src_d[0].data_ptr(), rig.h_src_db)
+            ms_s = rig.timed(rig.step_host, args.steps, e2e_warm, finish=fu.swap_frames)
+            fps_s = args.steps / (ms_s / 1e3)
+            e2e_streams[key] = {"value": round(R ** 3 * fps_s / 1e9, 3), "unit": "Gvoxel-updates/s", "frames_per_s": round(fps_s, 2),
+                                "h2d_bytes_per_step": int(rig.h_src_cb + rig.h_src_db), "d2h_bytes_per_step": 4,
+                                "what": "same step through rr_fuse_frame, colour streamed as DXT1 blocks" + (" and depth as 8-bit sqrt-compressed bytes" if d8 else "") +
+                                        ", decoded on the device (different input precision than the RGB8 / float32 headline)"}
         fu.synchronize()
         fu.set_frame_format(dxt1_color=False)
-        fu.upload_frames_ptr(d_color[0].data_ptr(), cb, d_depth[0].data_ptr(), db, device=True)
+        rig.h_src_c, rig.h_src_d, rig.h_src_cb, rig.h_src_db = rig.h_color, rig.h_depth, cb, db
+        fu.upload_frames_ptr(rig.d_color[0].data_ptr(), cb, rig.d_depth[0].data_ptr(), db, device=True)
     bcast_ms = None
     if world > 1:
         # the broadcast alone (nothing else on the GPUs): what the pipelined step hides, or is bound by
-        barrier()
+        rig.barrier()
         b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for _ in range(3):
-            fb.issue(packed=d_packed[0]); fb.consume(stream)
+            rig.fb.issue(packed=rig.d_packed[0]); rig.fb.consume(stream)
         torch.cuda.synchronize(dev)
         b0.record()
         for _ in range(20):
-            fb.issue(packed=d_packed[0]); fb.consume(stream)
+            rig.fb.issue(packed=rig.d_packed[0]); rig.fb.consume(stream)
         b1.record()
         torch.cuda.synchronize(dev)
-        t = torch.tensor([b0.elapsed_time(b1) / 20], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        bcast_ms = float(t.item())
+        bcast_ms = rig.max_over_ranks(b0.elapsed_time(b1) / 20)
     # keep the GPU busy until nvidia-smi has a few samples under load (the timed region can be < 100 ms). Every rank
     # runs the same number of extra steps (derived from the all-reduced step time), since steps contain collectives.
     n_extra = int(min(20000, max(64, 1200.0 / max(1e-3, ms_total / args.steps))))
     for i in range(n_extra):
-        step_device(i)
+        rig.step_device(i)
         if i % 64 == 63:
             fu.synchronize()
-    barrier()
+    rig.barrier()
     clocks = sampler.stop() if sampler else None
 
-    # occupancy statistics of the last frame for the algorithmic-bytes figure
-    n_occ, ratio = fu.bricks_update(sync=True)
-    counters, occ = fu.download_bricks()
-    ranges = fu.brick_ranges()
-    rr = ranges[occ]
-    n_occ_vox = int(((rr[:, 1] - rr[:, 0]) * (rr[:, 3] - rr[:, 2]) * (np.clip(rr[:, 5], zc0, zc1) - np.clip(rr[:, 4], zc0, zc1)).clip(0)).sum()) if len(occ) else 0
+    n_occ, ratio, n_occ_vox, nbricks = rig.occupancy()
+    info = fu.integrator_info()
 
-    # the view path (reported beside the headline, not part of it): raymarch at 1280x720; for N > 1 every rank marches
-    # its slab into partial records, ONE gather brings them to rank 0, which composites
-    from rrpy import synth
-    VW, VH = 1280, 720
+    # ---- the view path (reported beside the headline and combined with it): raymarch at 1280x720 + colour hole filling; for
+    # N > 1 every rank marches its slab into partial records and two reductions composite them on rank 0
     mv = synth.look_at((1.7, 1.6, 2.3), (0.0, 1.1, 0.0))
     pr = synth.perspective(50.0, VW / VH, 0.1, 10.0)
     records = torch.empty((VW * VH, multigpu.RECORD_FLOATS), dtype=torch.float32, device=dev)
-    gathered = torch.empty((world, VW * VH, multigpu.RECORD_FLOATS), dtype=torch.float32, device=dev) if (world > 1 and rank == 0) else None
+    keys = torch.empty((VW * VH,), dtype=torch.int64, device=dev)
 
     def view_once():
         if world == 1:
@@ -389,79 +475,86 @@ def run_ours(args):
             fu.fill_colors(download=False)          # m_fill_holes is on by default (recon_integration.cpp:54)
             return
         fu.raymarch_partial(mv, pr, VW, VH, records.data_ptr(), shade_mode=1)
-        torch.cuda.current_stream(dev).wait_stream(stream)
-        out = multigpu.gather_records(dist, records, dst=0, out=gathered)
-        stream.wait_stream(torch.cuda.current_stream(dev))      # the next march may not overwrite `records` before the gather read it
+        multigpu.reduce_records(dist, fu, records, keys, dst=0, stream=stream)
         if rank == 0:
-            fu.composite(out.data_ptr(), world, VW, VH, download=False)
+            fu.composite(records.data_ptr(), 1, VW, VH, download=False)
             fu.fill_colors(download=False)
 
     for _ in range(3):
         view_once()
-    barrier()
+    rig.barrier()
     v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n_views = 20
     v0.record(stream)
     for _ in range(n_views):
         view_once()
     v1.record(stream)
-    barrier()
-    view_ms = v0.elapsed_time(v1) / n_views
+    rig.barrier()
+    view_ms = rig.max_over_ranks(v0.elapsed_time(v1) / n_views)
+
+    # ---- N > 1: this run's slabs and composited view against a single-context run, bit for bit ---------------------------
+    verified = None
     if world > 1:
-        t = torch.tensor([view_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        view_ms = float(t.item())
+        verified = verify_against_single_context(torch, dist, rig, scenes, inv, voxel, bricks, mv, pr, records, view_once)
 
     frames_s = args.steps / (ms_total / 1e3)
     value = R ** 3 * frames_s / 1e9
     e2e_frames_s = args.steps / (ms_e2e / 1e3)
-    peak, peak_src = peaks()
-    slab_frac = (zc1 - zc0) / R
-    if bricks:
-        # fused clear+integrate: every voxel of the slab is written once (4 B), the inverse volumes are read where occupied
-        # bricks cover them, the packed depth/quality/silhouette texels once, the brick tables once
-        covered_inv = int(INV_RES[0] * INV_RES[1] * INV_RES[2] * min(1.0, n_occ_vox / max(1, R ** 3 * slab_frac)) * slab_frac)
-        abytes = (4 * R ** 3 * slab_frac + 16 * covered_inv * N_SENSORS + 32 * (W + 1) * (H + 1) * N_SENSORS + 4 * len(counters))
-    else:
-        abytes = 4 * R ** 3 * slab_frac + 16 * INV_RES[0] * INV_RES[1] * INV_RES[2] * N_SENSORS * slab_frac + 32 * (W + 1) * (H + 1) * N_SENSORS
     int_avg_ms = int_ms / max(1, int_n)
-    achieved = abytes / (int_avg_ms / 1e3) / 1e9 if int_avg_ms > 0 else 0.0
-
+    abytes, achieved, peak, peak_src = rig.roofline(int_avg_ms, n_occ_vox, nbricks)
     traffic, traffic_src = measured_traffic(bricks) if world == 1 else (None, None)
+    ms_step = ms_total / args.steps
+    slab_vox = R ** 3 * (rig.zc1 - rig.zc0) / R
+    rig.close()
+
+    # ---- sub-records through the same code (device-resident frames, rr_fuse_frame): dense mode and BASELINE config 5 -----
+    dense = config5 = None
+    if args.subrecords:
+        if bricks:
+            dense = sub_record(torch, dist, rank, world, local, "same workload with setUseBricks(false): every voxel x every sensor",
+                               N_SENSORS, R, False, capi.VOXELS_F32, 20, scenes[:1], inv, voxel)
+        config5 = sub_record(torch, dist, rank, world, local,
+                             "BASELINE.json configs[4]: 8 sensors 512x424, 1024^3 TSDF with half2 (tsdf, weight) voxels, occupied bricks, "
+                             "same z-slab code (one NCCL broadcast of the 40 MB frame set per step for N > 1)", 8, 1024, True, capi.VOXELS_HALF2, 30)
+
     out = {
         "metric": "4-sensor TSDF Gvoxel-updates/s at 512^3 (fused frames/s in frames_per_s)",
         "value": round(value, 3), "unit": "Gvoxel-updates/s", "frames_per_s": round(frames_s, 2),
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 5),
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 5),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "integration": INTEGRATION[bricks],
-                   "parallelism": f"z-slabs x{world}" if world > 1 else "single GPU", "slabs": slab_how,
+                   "parallelism": f"z-slabs x{world}" if world > 1 else "single GPU", "slabs": rig.slab_how,
                    "l2": "inputs+outputs per step (268 MB inverse volumes, 537 MB TSDF) exceed the 126 MB L2; no explicit flush",
-                   "occupied_bricks": int(n_occ), "occupied_ratio": round(float(ratio), 4), "frames_cycled": N_FRAMES},
+                   "occupied_bricks": int(n_occ), "occupied_ratio": round(float(ratio), 4), "frames_cycled": N_FRAMES, "integrator": info},
         "e2e": {"value": round(R ** 3 * e2e_frames_s / 1e9, 3), "unit": "Gvoxel-updates/s", "frames_per_s": round(e2e_frames_s, 2),
-                "h2d_bytes_per_step": int(cb + db), "d2h_bytes_per_step": 4,
-                "path": e2e_path, "other_path": e2e_other,
+                "h2d_bytes_per_step": int(cb + db), "d2h_bytes_per_step": 4, "path": e2e_path,
                 "h2d_link_gbs": round(link_gbs, 2) if link_gbs else None,
                 "bound": (f"host->device link: {cb + db} B/step at the measured {link_gbs:.1f} GB/s caps e2e at {link_gbs * 1e9 / (cb + db):.0f} frames/s" if link_gbs else None),
-                "dxt1_stream": e2e_dxt1},
+                **e2e_streams},
         "gpu_launches": int(gpu_launches), "host_enqueue_ms_per_step": round(host_enqueue_ms, 5),
         # beside voxel-updates/s, the evaluations actually performed (this rank's slab for N > 1)
-        "occupied_voxel_updates_per_s": round(float(n_occ_vox if bricks else R ** 3 * slab_frac) * frames_s, 1),
-        "voxel_sensor_evaluations_per_s": round(float(n_occ_vox if bricks else R ** 3 * slab_frac) * N_SENSORS * frames_s, 1),
+        "occupied_voxel_updates_per_s": round(float(n_occ_vox if bricks else slab_vox) * frames_s, 1),
+        "voxel_sensor_evaluations_per_s": round(float(n_occ_vox if bricks else slab_vox) * N_SENSORS * frames_s, 1),
         "stages_ms": {"1preprocess": round(pre_ms / max(1, pre_n), 5), "2integrate": round(int_avg_ms, 5),
                       "how": f"CUDA-event stage timers over {stage_steps} further steps of the same loop with direct launches "
                              f"({ms_stage_pass / stage_steps:.5f} ms/step); `value` is timed with the frame replayed as one CUDA graph"},
-        "view": {"ms_per_view": round(view_ms, 4), "resolution": [VW, VH], "what": "tsdf_raymarch (shaded, brick space skipping) + colour hole filling" + (f" per slab + 1 gather of {multigpu.RECORD_FLOATS * 4}-byte records + composite" if world > 1 else "")},
-        "roofline": {"bound": "hbm", "kernel": "k_integrate_fused (clear + occupied-brick integration, one launch = the 2integrate stage)" if bricks else "k_integrate_dense",
+        "view": {"ms_per_view": round(view_ms, 4), "resolution": [VW, VH],
+                 "what": "tsdf_raymarch (shaded, brick space skipping) + colour hole filling" +
+                         (" per slab, MIN all-reduce of the first-hit keys + integer SUM reduce of the winners' records onto rank 0, composite" if world > 1 else "")},
+        # SURVEY.md 8d "reported separately and combined": one fused frame set followed by one view
+        "combined_frames_per_s": round(1e3 / (ms_step + view_ms), 2),
+        "roofline": {"bound": "hbm", "kernel": integrate_kernel_name(bricks, info),
                      "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                     "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": int(abytes), "peak_source": peak_src},
+                     "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": int(abytes), "peak_source": peak_src,
+                     "algorithmic_bytes": "SURVEY.md 8d: 4*XYZ + 4*V_occ + 16*covered_inverse_voxels*N + 16*pixels*N + 4*bricks"},
+        "dense": dense, "config5": config5,
         "clocks": clocks,
     }
     if world > 1:
+        out["verified"] = verified
         out["broadcast"] = {"bytes": int(cb + db), "ms_alone": round(bcast_ms, 4), "gbs": round((cb + db) / bcast_ms / 1e6, 1),
                             "what": "one packed NCCL broadcast per frame set, double-buffered beside the previous set's kernels",
                             "nccl_min_nchannels": os.environ.get("NCCL_MIN_NCHANNELS")}
-    fu.close()
-    if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
@@ -589,6 +682,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="bricks", choices=["bricks", "dense"])
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--no-subrecords", dest="subrecords", action="store_false", help="skip the dense and config5 sub-records")
     ap.add_argument("--clock-ms", type=int, default=100, help="nvidia-smi sampling period during the timed regions (0 = off)")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup

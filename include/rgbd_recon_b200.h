@@ -179,6 +179,16 @@ int rr_upload_view(rr_ctx* ctx, int width, int height, const float* rgba, const 
 #define RR_PARTIAL_RECORD_BYTES 32
 int rr_raymarch_partial(rr_ctx* ctx, const rr_view* view, void* d_records);
 int rr_composite(rr_ctx* ctx, const void* d_records, int n_parts, int width, int height, float* out_rgba, float* out_depth);
+/* The same compositing by two reductions instead of a gather, so that the display GPU does not receive one record image
+ * per slab (tsdf_raymarch.fs:92-142 finds ONE first hit per ray; so does this):
+ *   rr_partial_keys         d_keys[i] (int64, DEVICE, w*h) = first_hit_step << 8 | rank for the records of the last
+ *                           rr_raymarch_partial; an all-reduce MIN over the ranks names every pixel's winner (smallest
+ *                           step, lowest rank on ties - exactly rr_composite's choice);
+ *   rr_partial_keep_winners zeroes this rank's record wherever it is not the winner; an integer SUM reduce of the records
+ *                           (8 x uint32 per pixel) onto the display GPU then yields the winner's record bit for bit, and
+ *                           rr_composite(..., n_parts = 1) turns it into the view. */
+int rr_partial_keys(rr_ctx* ctx, const void* d_records, int rank, void* d_keys);
+int rr_partial_keep_winners(rr_ctx* ctx, void* d_records, const void* d_keys_min, int rank);
 
 /* ---- read-back (tests, debug views) ------------------------------------------------------------------------ */
 int rr_download_tsdf(rr_ctx* ctx, float* out);

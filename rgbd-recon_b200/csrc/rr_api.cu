@@ -633,6 +633,20 @@ int rr_raymarch_partial(rr_ctx* c, const rr_view* view, void* d_records) {
   return launch_pack_partial(c, (float4*)d_records);
 }
 
+int rr_partial_keys(rr_ctx* c, const void* d_records, int rank, void* d_keys) {
+  if (!c) return RR_ERR_INVALID;
+  RR_REQUIRE(c, d_records && d_keys && rank >= 0 && rank < 256 && c->view_w > 0, "rr_partial_keys: bad arguments (march a view first; ranks 0..255)");
+  RR_SET_DEVICE(c);
+  return launch_partial_keys(c, (const float4*)d_records, rank, (long long*)d_keys);
+}
+
+int rr_partial_keep_winners(rr_ctx* c, void* d_records, const void* d_keys_min, int rank) {
+  if (!c) return RR_ERR_INVALID;
+  RR_REQUIRE(c, d_records && d_keys_min && rank >= 0 && rank < 256 && c->view_w > 0, "rr_partial_keep_winners: bad arguments");
+  RR_SET_DEVICE(c);
+  return launch_partial_keep(c, (float4*)d_records, (const long long*)d_keys_min, rank);
+}
+
 int rr_composite(rr_ctx* c, const void* d_records, int n_parts, int width, int height, float* out_rgba, float* out_depth) {
   if (!c) return RR_ERR_INVALID;
   RR_REQUIRE(c, d_records && n_parts >= 1 && width > 0 && height > 0, "rr_composite: bad arguments");

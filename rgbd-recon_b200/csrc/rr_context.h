@@ -213,6 +213,8 @@ int launch_integrate(rr_ctx* c);
 int launch_raymarch(rr_ctx* c, const rr_view* v);
 int launch_pack_partial(rr_ctx* c, float4* d_rec);
 int launch_composite(rr_ctx* c, const float4* d_rec, int n_parts);
+int launch_partial_keys(rr_ctx* c, const float4* d_rec, int rank, long long* d_keys);
+int launch_partial_keep(rr_ctx* c, float4* d_rec, const long long* d_keys_min, int rank);
 int launch_fill_colors(rr_ctx* c);
 int launch_unpack_frames(rr_ctx* c, int slot);
 int launch_calib_invert(rr_ctx* c, int sensor, const uint32_t out_res[3], float4* d_out);

@@ -359,6 +359,37 @@ __global__ void __launch_bounds__(256) k_composite(const float4* __restrict__ re
   rgba[i] = best_a; depth[i] = best_b.x; step[i] = best_step; nsamp[i] = best_b.z;
 }
 
+// Compositing by two reductions instead of a gather (the display GPU would otherwise receive n_parts record images):
+//   key = first_hit_step << 8 | rank   ->  MIN all-reduce: the winner of every pixel (smallest step, lowest rank on ties,
+//                                          exactly k_composite's choice)
+//   records of non-winners zeroed       ->  integer SUM reduce onto the display GPU: x + 0 + ... + 0 is x bit for bit
+__global__ void __launch_bounds__(256) k_partial_keys(const float4* __restrict__ rec, long long rank, long long* __restrict__ keys, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  keys[i] = ((long long)__float_as_uint(rec[2 * i + 1].y) << 8) | rank;
+}
+
+__global__ void __launch_bounds__(256) k_partial_keep(float4* __restrict__ rec, const long long* __restrict__ keys_min, long long rank, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long mine = ((long long)__float_as_uint(rec[2 * i + 1].y) << 8) | rank;
+  if (keys_min[i] != mine) { rec[2 * i] = make_float4(0.f, 0.f, 0.f, 0.f); rec[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f); }
+}
+
+int launch_partial_keys(rr_ctx* c, const float4* d_rec, int rank, long long* d_keys) {
+  const int n = c->view_w * c->view_h;
+  k_partial_keys<<<(n + 255) / 256, 256, 0, c->stream>>>(d_rec, (long long)rank, d_keys, n);
+  RR_LAUNCH_CHECK(c, "k_partial_keys");
+  return RR_OK;
+}
+
+int launch_partial_keep(rr_ctx* c, float4* d_rec, const long long* d_keys_min, int rank) {
+  const int n = c->view_w * c->view_h;
+  k_partial_keep<<<(n + 255) / 256, 256, 0, c->stream>>>(d_rec, d_keys_min, (long long)rank, n);
+  RR_LAUNCH_CHECK(c, "k_partial_keep");
+  return RR_OK;
+}
+
 int launch_pack_partial(rr_ctx* c, float4* d_rec) {
   const int n = c->view_w * c->view_h;
   k_pack_partial<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_rgba, c->d_zbuf, c->d_step, c->d_nsamples, d_rec, n);

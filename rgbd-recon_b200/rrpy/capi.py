@@ -79,6 +79,8 @@ def lib():
     L.rr_raymarch.argtypes = [vp, C.POINTER(View), f32, f32]
     L.rr_raymarch_partial.argtypes = [vp, C.POINTER(View), vp]
     L.rr_composite.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, f32, f32]
+    L.rr_partial_keys.argtypes = [vp, vp, C.c_int, vp]
+    L.rr_partial_keep_winners.argtypes = [vp, vp, vp, C.c_int]
     L.rr_fill_colors.argtypes = [vp, f32]
     L.rr_upload_view.argtypes = [vp, C.c_int, C.c_int, f32, f32]
     L.rr_download_tsdf.argtypes = [vp, f32]
@@ -296,6 +298,12 @@ class Fusion:
         """Slab march into a DEVICE record buffer (width*height*32 bytes), see rr_raymarch_partial."""
         v = self._view(modelview, projection, width, height, shade_mode)
         self._ck(self.L.rr_raymarch_partial(self.h, C.byref(v), d_records_ptr))
+
+    def partial_keys(self, d_records_ptr, rank, d_keys_ptr):
+        self._ck(self.L.rr_partial_keys(self.h, d_records_ptr, int(rank), d_keys_ptr))
+
+    def partial_keep_winners(self, d_records_ptr, d_keys_min_ptr, rank):
+        self._ck(self.L.rr_partial_keep_winners(self.h, d_records_ptr, d_keys_min_ptr, int(rank)))
 
     def composite(self, d_records_ptr, n_parts, width, height, download=True):
         self._vw, self._vh = int(width), int(height)

@@ -137,6 +137,29 @@ def gather_records(dist, records, dst=0, out=None):
     return None
 
 
+def reduce_records(dist, fu, records, keys, dst=0, stream=None):
+    """Compositing by two reductions (rr_partial_keys / rr_partial_keep_winners): an all-reduce MIN of the int64 keys names
+    every pixel's winner, every rank zeroes the records it lost, and an integer SUM reduce brings the winners' records to
+    `dst` bit for bit. `records` [h*w][8] float32 and `keys` [h*w] int64 are device tensors of this rank; both are
+    overwritten. On `dst`, `records` then holds the composited record image (rr_composite with n_parts = 1)."""
+    import torch
+    rank = dist.get_rank()
+    cur = torch.cuda.current_stream(records.device) if records.is_cuda else None
+    fu.partial_keys(records.data_ptr(), rank, keys.data_ptr())
+    if cur is not None:
+        cur.wait_stream(stream)
+    dist.all_reduce(keys, op=dist.ReduceOp.MIN)
+    if cur is not None:
+        stream.wait_stream(cur)
+    fu.partial_keep_winners(records.data_ptr(), keys.data_ptr(), rank)
+    if cur is not None:
+        cur.wait_stream(stream)
+    dist.reduce(records.view(torch.int32), dst=dst, op=dist.ReduceOp.SUM)
+    if cur is not None:
+        stream.wait_stream(cur)
+    return records
+
+
 def composite_reference(parts: np.ndarray):
     """Pure-numpy statement of k_composite for tests of the gather layout: parts [P][n][8] -> (records [n][8], winner)."""
     steps = parts[..., 5].view(np.uint32) if parts.dtype == np.float32 else parts[..., 5]

@@ -134,27 +134,31 @@ def wall_sdf(p, frame=0, centre=(0.0, 1.1, 0.0)):
 
 
 def render_depth(sen: Sensor, sdf, frame, seed, noise_sigma=0.0015, dropout=0.01):
+    """Sphere-traced z-depth map. Only rays still marching are evaluated each step (same values as marching every pixel
+    every step - the SDF is evaluated per point - at a tenth of the time)."""
     W, H = sen.W, sen.H
     px, py = np.meshgrid(np.arange(W) + 0.5, np.arange(H) + 0.5)
     ray = (sen.fwd[None, None, :] + ((px - sen.cx) / sen.fx)[..., None] * sen.right + ((py - sen.cy) / sen.fy)[..., None] * sen.down)
     rl = np.linalg.norm(ray, axis=-1)
-    d = ray / rl[..., None]
-    t = np.full((H, W), 0.3)
-    alive = np.ones((H, W), bool)
-    hit = np.zeros((H, W), bool)
+    d = (ray / rl[..., None]).reshape(-1, 3)
+    t = np.full(H * W, 0.3)
+    hit = np.zeros(H * W, bool)
+    idx = np.arange(H * W)
     for _ in range(96):
-        p = sen.pos + t[..., None] * d
-        dist = sdf(p, frame)
-        hit |= alive & (dist < 2e-4)
-        alive &= ~hit & (t < 6.0)
-        t = np.where(alive, t + np.maximum(dist, 1e-4), t)
-        if not alive.any():
+        ti = t[idx]
+        dist = sdf(sen.pos + ti[:, None] * d[idx], frame)
+        h = dist < 2e-4
+        hit[idx[h]] = True
+        keep = ~h & (ti < 6.0)
+        idx = idx[keep]
+        t[idx] = ti[keep] + np.maximum(dist[keep], 1e-4)
+        if idx.size == 0:
             break
-    z = t / rl                                              # z-depth along the optical axis
+    z = t.reshape(H, W) / rl                                # z-depth along the optical axis
     rng = np.random.default_rng(seed)
     z = z + rng.normal(0.0, noise_sigma, size=z.shape)
     drop = rng.uniform(size=z.shape) < dropout
-    z = np.where(hit & ~drop, z, 0.0)
+    z = np.where(hit.reshape(H, W) & ~drop, z, 0.0)
     return z.astype(np.float32)
 
 

@@ -59,6 +59,7 @@ def run(name, steps=100, warmup=5):
     pm, pn = fu.stage_stats("1preprocess")
     fu.set_timing(0)
     n_occ, ratio = fu.bricks_update(sync=True)
+    info = fu.integrator_info()
     VW, VH = 1280, 720
     mv = synth.look_at((1.7, 1.6, 2.3), (0.0, 1.1, 0.0))
     pr = synth.perspective(50.0, VW / VH, 0.1, 10.0)
@@ -74,7 +75,7 @@ def run(name, steps=100, warmup=5):
     fu.close()
     out = {"config": name, "what": cfg["what"], "frames_per_s": round(1e3 / ms, 2), "gvoxel_updates_per_s": round(R ** 3 / ms / 1e6, 3),
            "ms_per_step": round(ms, 5), "stages_ms": {"1preprocess": round(pm / max(1, pn), 5), "2integrate": round(im / max(1, inn), 5)},
-           "occupied_bricks": int(n_occ), "occupied_ratio": round(float(ratio), 4),
+           "occupied_bricks": int(n_occ), "occupied_ratio": round(float(ratio), 4), "integrator": info,
            "view_ms": round(v0.elapsed_time(v1) / 20, 4), "view": "raymarch 1280x720 (shaded, brick space skipping) + colour hole filling",
            "steps": steps, "warmup": warmup, "data": "synthetic (same generators as bench.py)"}
     print(json.dumps(out), flush=True)
