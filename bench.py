@@ -355,18 +355,18 @@ def verify_against_single_context(torch, dist, rig, scenes, inv, voxel, bricks, 
 
 
 def run_ours(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 and os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"            # keeps NCCL's version banner off stdout: rank 0 prints exactly one JSON line
     import torch
     from rrpy import capi, multigpu, synth
     rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"        # keeps NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         torch.cuda.set_device(local)
         import datetime
         dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=300))

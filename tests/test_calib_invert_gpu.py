@@ -84,3 +84,22 @@ def test_inverted_volume_feeds_integration(small_scene):
     want = O.integrate(inv, pre, grid, 0.01, True, occ)
     assert bits_equal(tsdf, want).all(), mismatch_report("tsdf", tsdf, want)
     assert ((want > -0.01) & (want < 0.01)).sum() > 1000
+
+
+def test_inversion_at_baseline_size_matches_the_oracle():
+    """BASELINE config 1 at its own size: one 128 x 128 x 256 calibration volume inverted over the default bounding box at
+    7 mm (286 x 315 x 286 output voxels), every output voxel bit-identical to the oracle port (a few seconds on the host
+    cores with the reference's own parallelisation)."""
+    import oracle_py as O
+    from rrpy import capi, synth
+    sc = synth.make_scene(N=1, W=64, H=53, CW=80, CH=68, cv_res=(128, 128, 256))
+    res = tuple(int(np.ceil((sc.bbox_max[i] - sc.bbox_min[i]) / np.float32(0.007))) for i in range(3))
+    assert res == (286, 315, 286)
+    fu = capi.Fusion(1, sc.W, sc.H, sc.CW, sc.CH)
+    capi.load_scene(fu, sc)
+    got = fu.calib_invert(0, res)
+    fu.close()
+    O.set_threads(max(1, len(os.sched_getaffinity(0))))
+    want = O.calib_invert(sc.cv_xyz[0], sc.bbox_min, sc.bbox_max, res)
+    assert (want[..., 3] > 0).mean() > 0.2
+    assert bits_equal(got, want).all(), f"{(~bits_equal(got, want)).sum()} values differ"

@@ -75,6 +75,43 @@ def test_fullsize_paths_agree(full, monkeypatch):
         assert bits_equal(fused[sl], want[sl]).all()
 
 
+def test_fullsize_whole_frame_matches_the_oracle(full):
+    """BASELINE's headline configuration against the oracle IN FULL: all seven stage images of the 4 x 512 x 424 pre-processing,
+    the brick counters, the occupied list and every voxel of the 512^3 volume, bit for bit (the oracle needs ~0.5 s for the
+    whole chain on the host cores), then the 1280x720 raymarch of config 2 on that volume."""
+    import oracle_py as O
+    from rrpy import capi, synth
+    b, sc = full["bench"], full["scene"]
+    fu = _ctx(full)
+    n_occ, _ = fu.frame(sync_bricks=True)
+    info = fu.integrator_info()
+    assert info["staged"] == 1 and info["flags"] == 0, info          # the TMA-staged integrator is the one that ran, and it is healthy
+    got = {k: fu.download_stage(k) for k in capi.STAGES}
+    counters, occupied = fu.download_bricks()
+    tsdf = fu.download_tsdf()
+    grid = O.brick_grid(sc.bbox_min, sc.bbox_max, full["voxel"], b.BRICK)
+    cams = [O.frustum(sc.cv_xyz[i])[1] for i in range(sc.N)]
+    pre = O.preprocess(sc, grid, cams)
+    occ = O.occupied_bricks(pre["bricks"], b.MIN_VOX)
+    for k in ("morph", "depth", "lab", "depth_b", "sil", "normal", "quality"):
+        assert bits_equal(got[k], pre[k]).all(), f"stage {k}: {(~bits_equal(got[k], pre[k])).sum()} values differ"
+    assert np.array_equal(counters, pre["bricks"]), "brick counters differ"
+    assert np.array_equal(occupied, occ) and n_occ == len(occ), "occupied brick list differs"
+    want = O.integrate(full["inv"], pre, grid, b.LIMIT, True, occ)
+    assert bits_equal(tsdf, want).all(), f"{(~bits_equal(tsdf, want)).sum()} of 512^3 voxels differ from the oracle"
+    assert ((want > -b.LIMIT) & (want < b.LIMIT)).sum() > 100000
+    # config 2's view size on this volume
+    VW, VH = 1280, 720
+    mv, pr = synth.look_at((1.7, 1.6, 2.3), (0.0, 1.1, 0.0)), synth.perspective(50.0, VW / VH, 0.1, 10.0)
+    for shade_mode in (0, 1):
+        rgba, depth = fu.raymarch(mv, pr, VW, VH, shade_mode=shade_mode)
+        ns = fu.download_num_samples(VW, VH)
+        w = O.raymarch(want, b.LIMIT, full["inv"], sc, pre, grid, occ, mv, pr, VW, VH, shade_mode, skip_space=True)
+        assert (w["depth"] < 1.0).sum() > 20000
+        assert bits_equal(depth, w["depth"]).all() and bits_equal(rgba, w["rgba"]).all() and bits_equal(ns, w["samples"]).all()
+    fu.close()
+
+
 def test_fullsize_slabs_agree(full):
     import torch
     from rrpy import multigpu as M, synth
