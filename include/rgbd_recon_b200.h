@@ -223,10 +223,18 @@ int rr_set_tunable(const char* name, int value);
  * bench.py and the tests). Waits for the stream. out[16]:
  *  [0] 1 = the TMA-staged kernel is selected (0: the direct kernels), [1] tile edge (pixels), [2..4] staged inverse-volume
  *  box (coarse texels), [5] y-chunk, [6] z-chunk (voxels per work item), [7] y-chunks per brick, [8] z-chunks per brick,
- *  [9] bricks left to the direct kernel (footprint larger than the tile), [10] shared memory per CTA (bytes),
- *  [11] consumer warps, [12] fill warps, [13] device-side consistency flags (0 = healthy: bit 0 box overflow, bit 1 barrier
- *  time-out), [14..15] reserved. */
+ *  [9] (item, sensor) pairs of the brick grid whose footprint exceeds the tile (read from global memory when occupied and
+ *  not settled by a verdict), [10] shared memory per CTA (bytes), [11] consumer warps, [12] clear warps, [13] device-side
+ *  consistency flags (0 = healthy: bit 0 box overflow, bit 1 barrier time-out), [14] operand slots in the ring, [15] bytes per slot. */
 int rr_integrator_info(rr_ctx* ctx, uint32_t* out);
+/* Cycle counters of the staged integrator's warp roles, accumulated while the tunable "stage_debug" has bit 7 set and reset
+ * by this call (diagnostics, no reference counterpart). out[16], SM clock cycles summed over warps / producer threads:
+ *  [0] consumer warps waiting for a staged item, [1] evaluating one, [2] items a consumer warp had no columns of,
+ *  [4] producers gathering item metadata, [5] waiting for a free stage, [6] issuing + waiting for the copies,
+ *  [7] staged items, [8] direct items, [9] clear warps in the clear, [10] other warps helping with the clear,
+ *  [11] longest CTA (cycles), [12] sum over warps of their lifetime, [3] sensors evaluated voxel by voxel summed over items,
+ *  [13] largest tile edge a staged (item, evaluated sensor) needed, [14] / [15] items needing at most 30 / 36 pixels. */
+int rr_integrator_profile(rr_ctx* ctx, uint64_t* out);
 /* Library/ABI version. */
 int rr_version(void);
 

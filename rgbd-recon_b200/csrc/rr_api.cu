@@ -293,7 +293,7 @@ int rr_configure(rr_ctx* c, const rr_config* cfg) {
     c->bricks.brick_size = bs; c->bricks.num = nb;
     for (int a = 0; a < 3; ++a) c->bricks.res[a] = rb[a];
     RR_TRY(dev_alloc(c, &c->d_ranges, (size_t)nb * 6, "brick ranges"));
-    RR_TRY(dev_alloc(c, &c->d_counters, nb, "brick counters"));
+    RR_TRY(dev_alloc(c, &c->d_counters, (size_t)nb + RR_CLASS_COUNTERS, "brick counters"));
     RR_TRY(dev_alloc(c, &c->d_occupied, nb, "occupied list"));
     RR_TRY(dev_alloc(c, &c->d_near_occ, nb, "near-occupied mask"));
     RR_TRY(dev_alloc(c, &c->d_occ_mask, nb, "occupied mask"));
@@ -325,7 +325,7 @@ int rr_configure(rr_ctx* c, const rr_config* cfg) {
     cudaMemsetAsync(c->d_rowmask, 0, (size_t)rb[2] * rb[1] * c->mask_words * sizeof(uint32_t), c->stream);
     cudaMemsetAsync(c->d_rowany, 0, (size_t)rb[2] * rb[1], c->stream);
     cudaMemcpyAsync(c->d_ranges, c->h_ranges.data(), (size_t)nb * 6 * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream);
-    cudaMemsetAsync(c->d_counters, 0, nb * sizeof(uint32_t), c->stream);
+    cudaMemsetAsync(c->d_counters, 0, ((size_t)nb + RR_CLASS_COUNTERS) * sizeof(uint32_t), c->stream);
     cudaMemsetAsync(c->d_near_occ, 0, nb, c->stream);
     cudaMemsetAsync(c->d_occ_mask, 0, nb, c->stream);
     cudaMemsetAsync(c->d_num_occ, 0, sizeof(uint32_t), c->stream);
@@ -846,13 +846,24 @@ int rr_integrator_info(rr_ctx* c, uint32_t* out) {
   out[0] = staged_selected(c) ? 1u : 0u;
   out[1] = (uint32_t)s.T; out[2] = (uint32_t)s.BX; out[3] = (uint32_t)s.BY; out[4] = (uint32_t)s.BZ;
   out[5] = (uint32_t)s.cy; out[6] = (uint32_t)s.cz; out[7] = (uint32_t)s.n_yc; out[8] = (uint32_t)s.n_zc;
-  out[9] = s.n_legacy; out[10] = s.smem_bytes; out[11] = (uint32_t)s.cwarps; out[12] = (uint32_t)s.fwarps;
+  out[9] = s.n_oversize; out[10] = s.smem_bytes; out[11] = (uint32_t)s.cwarps; out[12] = (uint32_t)s.fwarps; out[14] = s.n_slots; out[15] = s.slot_bytes;
   if (s.d_err) {
     uint32_t e[4] = {0, 0, 0, 0};
     RR_TRY(check(c, cudaStreamSynchronize(c->stream), "integrator info sync"));
     RR_TRY(check(c, cudaMemcpy(e, s.d_err, sizeof(e), cudaMemcpyDeviceToHost), "integrator flags"));
     out[13] = (e[0] ? 1u : 0u) | (e[1] ? 2u : 0u);
   }
+  return RR_OK;
+}
+
+int rr_integrator_profile(rr_ctx* c, uint64_t* out) {
+  if (!c || !out) return RR_ERR_INVALID;
+  RR_SET_DEVICE(c);
+  std::memset(out, 0, 16 * sizeof(uint64_t));
+  if (!c->sti.d_err) return RR_OK;
+  RR_TRY(check(c, cudaStreamSynchronize(c->stream), "integrator profile sync"));
+  RR_TRY(check(c, cudaMemcpy(out, c->sti.d_err + 4, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost), "integrator profile"));
+  RR_TRY(check(c, cudaMemset(c->sti.d_err + 4, 0, 16 * sizeof(uint64_t)), "integrator profile reset"));
   return RR_OK;
 }
 
@@ -876,6 +887,8 @@ int rr_set_tunable(const char* name, int value) {
   else if (n == "stage_tile") t.stage_tile = value;
   else if (n == "stage_fill_rows") t.stage_fill_rows = value;
   else if (n == "stage_debug") t.stage_debug = value;
+  else if (n == "stage_fill_depth") t.stage_fill_depth = value;
+  else if (n == "stage_fill_lsu") t.stage_fill_lsu = value;
   else if (n == "stage_cwarps") t.stage_cwarps = value;
   else if (n == "stage_bulk_fill") t.stage_bulk_fill = value;
   else return RR_ERR_INVALID;

@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(1024) k_bricks_update(const uint32_t* __restri
 }
 
 int launch_bricks_clear(rr_ctx* c) {
-  cudaError_t e = cudaMemsetAsync(c->d_counters, 0, sizeof(uint32_t) * c->bricks.num, c->stream);
+  cudaError_t e = cudaMemsetAsync(c->d_counters, 0, sizeof(uint32_t) * ((size_t)c->bricks.num + RR_CLASS_COUNTERS), c->stream);
   return check(c, e, "bricks clear");
 }
 
@@ -118,6 +118,7 @@ int launch_bricks_update(rr_ctx* c) {
       c->d_occupied, c->d_num_occ, grid_ok ? c->d_near_occ : nullptr, c->d_occ_mask, (grid_ok && c->fused_ok) ? c->d_rowmask : nullptr, c->d_rowany,
       c->d_work, mask_blocks, cq);
   RR_LAUNCH_CHECK(c, "k_bricks_update");
+  c->work_fresh = true;
   cudaError_t e = cudaMemcpyAsync(c->h_num_occ, c->d_num_occ, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
   return check(c, e, "bricks count copy");
 }

@@ -45,6 +45,8 @@ struct BrickGrid {
   uint32_t num;
 };
 
+#define RR_CLASS_COUNTERS 16      // >= RR_MAX_SENSORS + 1
+
 struct StageTimer {            // one CUDA-event pair per recorded interval; summed and recycled by rr_get_stage_stats
   std::vector<cudaEvent_t> beg, end;
   size_t used = 0;             // intervals recorded since the last reset
@@ -115,7 +117,7 @@ struct rr_ctx {
   rr::BrickGrid bricks{};
   std::vector<int32_t> h_ranges;
   int32_t* d_ranges = nullptr;
-  uint32_t* d_counters = nullptr;
+  uint32_t* d_counters = nullptr;  // [bricks.num] voxels seen per brick, then RR_CLASS_COUNTERS item-class counters of the staged integrator
   uint32_t* d_occupied = nullptr;
   uint32_t* d_num_occ = nullptr;
   uint8_t* d_near_occ = nullptr;
@@ -127,6 +129,7 @@ struct rr_ctx {
   int16_t* d_cand_y = nullptr;     // [Y][2], -1 = none
   int16_t* d_cand_z = nullptr;     // [Z][2]
   uint32_t* d_work = nullptr;      // [4] work-item counters of the persistent fused kernel
+  bool work_fresh = false;         // k_bricks_update has reset them and no integrate launch has drawn from them since
   int mask_words = 0;
   float4* d_ztab = nullptr;        // [Z] (k0, k1, g, 1-g) of the z filter tap against the inverse volume (k_build_ztab)
   int ztab_Z = 0, ztab_IZ = 0;
@@ -145,12 +148,13 @@ struct rr_ctx {
     int BX = 0, BY = 0, BZ = 0;    // inverse-volume box staged per item (coarse texels)
     int T = 0;                     // pair-image tile edge staged per item and sensor (pixels, even)
     int cwarps = 0, fwarps = 0;    // consumer / fill warps per CTA
-    uint32_t inv_bytes = 0, tile_bytes = 0, inv_span = 0, tile_span = 0, stage_bytes = 0, smem_bytes = 0, fill_src_bytes = 0, tables_off = 0;
-    uint2* d_fp = nullptr;         // [items][N]: tile origin tx0 | ty0 << 16, footprint rectangle inside the tile
-    uint8_t* d_legacy = nullptr;   // [num_bricks]: 1 = a footprint of this brick exceeds the tile: evaluated from global memory
-    uint32_t n_legacy = 0;         // bricks flagged in d_legacy
+    uint32_t inv_bytes = 0, tile_bytes = 0, inv_span = 0, smem_bytes = 0, fill_src_bytes = 0, fill_src_off = 0, tables_off = 0;
+    uint32_t slot_bytes = 0, n_slots = 0, slots_off = 0;   // ring of per-sensor operand slots (inverse-volume box + tile)
+    uint2* d_fp = nullptr;         // [items][N]: tile origin tx0 | ty0 << 16, footprint rectangle inside the tile (bit 7 of .y: exceeds the tile)
+    uint32_t n_oversize = 0;       // (item, sensor) pairs of the whole brick grid whose footprint exceeds the tile
+    uint2* d_list = nullptr;       // [N + 1][list_stride]: this frame's occupied items by cost class (item, verdict), k_bricks_update
+    uint32_t list_stride = 0;
     float2* d_zr = nullptr;        // [items][N]: exact range of pos_calib.z over the item (k_footprints)
-    uint32_t* d_cls = nullptr;     // [items]: this frame's per-sensor verdicts (k_classify)
     uint32_t* d_err = nullptr;     // [4] device-side consistency flags (must stay 0)
     CUtensorMap map_inv, map_pairs;
   } sti;
@@ -193,7 +197,9 @@ struct Tunables {
   int stage_tile = 0;   // pair-image tile edge in pixels (0: chosen from the footprint statistics and the smem budget)
   int stage_fill_rows = 16;   // voxel rows per fill item
   int stage_cwarps = 0; // consumer warps per CTA: 0 = 22 up to four sensors (80 registers), 11 = half of that at 144 registers
-  int stage_bulk_fill = 16;   // KB of cleared voxels in shared memory, the source of the clear's TMA bulk stores
+  int stage_bulk_fill = 4;    // KB of cleared voxels in shared memory, the source of the clear's TMA bulk stores
+  int stage_fill_depth = 0;   // bulk-store groups a clear lane may leave pending (-1: unbounded)
+  int stage_fill_lsu = 0;     // 1: rows without occupied bricks are cleared by per-lane stores instead of bulk stores
   int stage_debug = 0;  // measurement only, results are WRONG: bit 0 skips the clear stream, bit 1 the brick evaluation
   unsigned generation = 0;   // bumped by every rr_set_tunable (invalidates captured graphs)
 };

@@ -338,7 +338,16 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 
 // Source of the bulk stores: a shared-memory buffer holding `bytes` of cleared voxels (and, for a separate weight volume,
 // as many zero bytes behind it); policy: their L2 cache hint (evict_first); drop: measurement hook, nothing is stored.
-struct FillSource { uint32_t src, bytes; bool drop; uint64_t policy; };
+struct FillSource { uint32_t src, bytes; bool drop; uint64_t policy; int depth; bool lsu; };
+// Bound on the bulk-store groups a lane leaves pending (tunable stage_fill_depth; < 0: none): the TMA unit serves the
+// integrator's tile loads and the clear's stores from one queue, so a deep backlog of stores delays every load behind it.
+__device__ __forceinline__ void bulk_throttle(int depth) {
+  if (depth < 0) return;
+  if (depth == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  else if (depth == 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+  else if (depth == 2) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+  else asm volatile("cp.async.bulk.wait_group.read 4;" ::: "memory");
+}
 
 // One fill item, rows [row0, row1), at most 32; requires X % 4 == 0, X <= 1024 and a buffer of at least one row.
 // A run of rows without occupied bricks is contiguous, 16-byte aligned memory: one bulk store per buffer-sized piece.
@@ -360,6 +369,16 @@ __device__ __forceinline__ void fill_rows_bulk(const FusedParams& p, const FillT
       uint8_t* t0 = reinterpret_cast<uint8_t*>(p.ip.tsdf + (size_t)(row0 + (uint32_t)r) * X);
       uint8_t* w0 = WEIGHT ? reinterpret_cast<uint8_t*>(p.ip.weight + (size_t)(row0 + (uint32_t)r) * X) : nullptr;
       const uint32_t nbytes = (uint32_t)(len * X) * 4u;
+      if (fs.lsu) {
+        // per-lane streaming stores (experiment: keeps the clear out of the TMA unit's queue)
+        const float4 v4 = make_float4(p.fill_value, p.fill_value, p.fill_value, p.fill_value), z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (uint32_t off = (uint32_t)lane * 16u; off < nbytes; off += 512u) {
+          __stcs(reinterpret_cast<float4*>(t0 + off), v4);
+          if (WEIGHT) __stcs(reinterpret_cast<float4*>(w0 + off), z4);
+        }
+        r += len;
+        continue;
+      }
       for (uint32_t off = (uint32_t)lane * fs.bytes; off < nbytes; off += 32u * fs.bytes) {
         if (fs.drop) continue;
         const uint32_t sz = min(fs.bytes, nbytes - off);
@@ -367,6 +386,7 @@ __device__ __forceinline__ void fill_rows_bulk(const FusedParams& p, const FillT
         if (WEIGHT) bulk_store(w0 + off, fs.src + fs.bytes, sz, fs.policy);
       }
       bulk_commit();
+      bulk_throttle(fs.depth);
       r += len;
       continue;
     }
@@ -426,6 +446,7 @@ __device__ __forceinline__ void fill_rows_bulk(const FusedParams& p, const FillT
       }
     }
     bulk_commit();
+    bulk_throttle(fs.depth);
     r += glen;
   }
 }
@@ -462,29 +483,35 @@ __device__ __forceinline__ void fill_loop_bulk(const FusedParams& p, const FillT
 //   zlo - dmax >= limit  =>  sdist >= limit for every voxel of the item   (tsdf_integration.vs:45: nothing happens)
 //   zhi - dmin <= -limit =>  sdist <= -limit for every voxel              (:41: weighted_tsd = -limit)
 // and with every silhouette tap 1 the silhouette test (:32) never fires. Such (item, sensor) pairs need no per-voxel work.
-// Returns skip mask | front mask << 8. Non-finite values keep a sensor on the voxel-by-voxel path (NaN patterns unchanged).
+// Verdict = skip mask | front mask << 8. Non-finite values keep a sensor on the voxel-by-voxel path (NaN patterns unchanged).
+// The item is appended, with its verdict, to this frame's work list of its cost class = number of sensors left to evaluate
+// voxel by voxel (an item with an oversize footprint counts as the most expensive class): the integrator hands out the
+// expensive items first, so the last ones to finish are the short ones.
 struct ClassifyParams {
-  const uint2* fp;          // [items][N]: tile origin tx0 | ty0 << 16, footprint rectangle x offset | width << 8 | height << 20
+  const uint2* fp;          // [items][N]: tile origin tx0 | ty0 << 16, footprint rectangle x offset | oversize << 7 | width << 8 | height << 20
   const float2* zr;         // [items][N]: exact range of pos_calib.z over the item
   const float2* pairs; int pair_pitch, H2;
-  const uint8_t* legacy;    // [bricks] or nullptr: bricks evaluated from global memory (no verdicts)
-  uint32_t* cls;            // [items] out
+  uint2* list;              // [N + 1][list_stride] out: (item, verdict) by class
+  uint32_t* class_count;    // [N + 1] in/out: entries per class (cleared with the brick counters)
+  uint32_t list_stride;
   int per_brick, N;
   float limit;
 };
 
 __device__ __forceinline__ void classify_item(const ClassifyParams& q, uint32_t brick, uint32_t sub, int lane) {
-  if (q.legacy && q.legacy[brick]) return;
   const size_t item = (size_t)brick * q.per_brick + sub;
   const float inf = __int_as_float(0x7f800000);
-  uint32_t skip = 0, front = 0;
+  uint32_t skip = 0, front = 0, oversize = 0, voxels = 0;
 #pragma unroll 1
   for (int s = 0; s < q.N; ++s) {
     const uint2 f = q.fp[item * q.N + s];
     const float2 z = q.zr[item * q.N + s];
     const int rw = (int)((f.y >> 8) & 4095u), rh = (int)(f.y >> 20);
-    if (rw * rh == 0 || !(z.x <= z.y)) continue;
-    const float2* img = q.pairs + ((size_t)s * q.H2 + (f.x >> 16)) * q.pair_pitch + (f.x & 0xffffu) + (f.y & 255u);
+    if (rw * rh == 0) continue;
+    voxels = 1;
+    if (f.y & 128u) oversize |= 1u << s;
+    if (!(z.x <= z.y)) continue;
+    const float2* img = q.pairs + ((size_t)s * q.H2 + (f.x >> 16)) * q.pair_pitch + (f.x & 0xffffu) + (f.y & 127u);
     float dlo = inf, dhi = -inf;
     bool ok = true;
     for (int i = lane; i < rw * rh; i += 32) {
@@ -501,7 +528,12 @@ __device__ __forceinline__ void classify_item(const ClassifyParams& q, uint32_t 
     if (z.x - dhi >= q.limit) skip |= 1u << s;
     else if (z.y - dlo <= -q.limit) front |= 1u << s;
   }
-  if (lane == 0) q.cls[item] = skip | (front << 8);
+  if (lane == 0 && voxels) {
+    const uint32_t off = skip | front;
+    const int cls = (oversize & ~off) ? q.N : q.N - __popc(off);
+    const uint32_t idx = atomicAdd(q.class_count + cls, 1u);
+    if (idx < q.list_stride) q.list[(size_t)cls * q.list_stride + idx] = make_uint2((uint32_t)item, skip | (front << 8));
+  }
 }
 
 // The cleared voxel as the 4 bytes the fill stores write: -limit (R32F), or half2(-limit, 0) for half2 voxels.

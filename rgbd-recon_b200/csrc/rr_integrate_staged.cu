@@ -22,44 +22,56 @@
 #include <cstring>
 #include <vector>
 
+// Role-level cycle counters (rr_integrator_profile): compiled in only for `make prof` (librr_b200_prof.so), so that the
+// shipped kernel's register allocation is not shaped by them.
+#ifdef RR_STAGE_PROF
+#define RR_PROF(...) __VA_ARGS__
+#else
+#define RR_PROF(...)
+#endif
+
 namespace rr {
 
 struct StagedParams {
   FusedParams f;            // integrate parameters + clear stream
   int cy, cz, n_yc, n_zc;   // work item = brick x y-chunk x z-chunk (voxels per chunk, chunks per brick)
-  int BX, BY, BZ, T;        // staged inverse-volume box (coarse texels) and pair-image tile edge (pixels)
-  const uint2* fp;          // [bricks * n_yc * n_zc][N]: .x = tile origin tx0 | ty0 << 16, .y = footprint rectangle (ItemHdr::rect)
-  const uint8_t* legacy;    // [bricks]: 1 = a footprint exceeds the tile: evaluated from global memory (march_column); may be nullptr
-  const uint32_t* cls;      // [bricks * n_yc * n_zc]: this frame's per-sensor verdicts (k_classify): skip | front << 8
-  uint32_t inv_bytes, tile_bytes;    // bytes one item's copies deliver (box, one tile)
-  uint32_t inv_span, tile_span, stage_bytes;   // smem regions: TMA destinations are 128-byte aligned
-  uint32_t fill_src_off, fill_src_bytes;   // buffer of cleared voxels behind the stages (source of the clear's bulk stores); 0 bytes: none
+  int BX, BY, BZ, T;        // staged inverse-volume box per sensor (coarse texels) and pair-image tile edge (pixels)
+  const uint2* fp;          // [bricks * n_yc * n_zc][N]: .x = tile origin tx0 | ty0 << 16, .y = footprint rectangle (bit 7: exceeds the tile)
+  const uint2* list;        // [N + 1][list_stride]: this frame's items by cost class (.x item, .y verdict), written by k_bricks_update
+  const uint32_t* class_count;   // [N + 1]
+  uint32_t list_stride;
+  uint32_t inv_bytes, tile_bytes;    // bytes one sensor's copies deliver (box, tile)
+  uint32_t inv_span;        // offset of the tile inside a slot (TMA destinations are 128-byte aligned)
+  uint32_t slot_bytes, n_slots, slots_off;   // ring of per-sensor operand slots behind the item headers
+  uint32_t fill_src_off, fill_src_bytes;   // buffer of cleared voxels (source of the clear's bulk stores)
   uint32_t tables_off;      // shared-memory copies of cand_y [2Y], cand_z [2Z] (int16) and rowany [nby*nbz] behind that
   uint32_t n_rowany;
   uint32_t* err;            // [0] box overflow, [1] barrier time-out
+  int fill_depth, fill_lsu; // tunables stage_fill_depth / stage_fill_lsu (FillSource)
+  unsigned long long* prof; // stage_debug bit 7: cycle counters per role (rr_integrator_profile), else nullptr
   int debug;
 };
 
-// first 128 bytes of a stage, written by the producer before it arms the stage's full barrier
+// An item in flight = one header of the header ring + one operand slot per sensor that is evaluated voxel by voxel.
+// The first 128 bytes of a header are written by the producer before it arms the header's full barrier; the item's slice
+// of the z table follows (bulk copy).
 struct ItemHdr {
   int valid;                // 0: no more items, 1: staged item, 2: direct item (operands stay in global memory)
   int x0, nx, y0, ny, zb, ze;
-  int ixlo, iylo, izlo;     // origin of the staged inverse-volume box
-  int nbx, nby, nbz;        // ... and the part of it this item uses
-  // Per-sensor verdict of k_classify for this frame: bit s of `skip` = every voxel of the
-  // item lies at least `limit` behind everything sensor s sees in its footprint (tsdf_integration.vs:45 "do nothing"), bit s
-  // of `front` = at least `limit` in front of it (:41 weighted_tsd = -limit); neither = evaluate voxel by voxel.
+  // Per-sensor verdict of k_bricks_update for this frame: bit s of `skip` = every voxel of the item lies at least `limit`
+  // behind everything sensor s sees in its footprint (tsdf_integration.vs:45 "do nothing"), bit s of `front` = at least
+  // `limit` in front of it (:41 weighted_tsd = -limit); neither = evaluate voxel by voxel.
   uint32_t skip, front;
-  uint32_t pad;
-  uint32_t tb[RR_MAX_SENSORS];   // byte offset (from the dynamic smem base) of pair texel (-1, -1) of sensor s: tile start - tile origin
-  uint32_t rect[RR_MAX_SENSORS]; // footprint rectangle inside the tile: x offset | width << 8 | height << 20 (pixels)
+  uint32_t nslots;          // operand slots the item holds (returned to the ring when every consumer warp has left it)
+  uint32_t ib[RR_MAX_SENSORS];   // byte offset (from the dynamic smem base) of inverse-volume texel (0, 0, 0) of sensor s, were the whole volume staged
+  uint32_t tb[RR_MAX_SENSORS];   // ... and of pair texel (-1, -1) of sensor s: tile start - tile origin
 };
-// stage layout: [0,128) ItemHdr | [128, 128 + 16*ZT_MAX) the item's slice of the z table | inverse-volume box | N pair tiles
 #define ITEM_HDR_BYTES 128
 #define ZT_MAX 56
-#define STAGE_HDR_BYTES (ITEM_HDR_BYTES + 16 * ZT_MAX)
+#define HDR_BYTES (ITEM_HDR_BYTES + 16 * ZT_MAX)
+#define NH 8                // headers = items in flight per CTA at most
 static_assert(sizeof(ItemHdr) <= ITEM_HDR_BYTES, "item header must fit its slot");
-static_assert(STAGE_HDR_BYTES % 128 == 0, "TMA destinations are 128-byte aligned");
+static_assert(HDR_BYTES % 128 == 0, "TMA destinations are 128-byte aligned");
 
 // ---- PTX: mbarrier + TMA ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -126,24 +138,23 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 }
 
 // ---- one (x, y) column of a staged item ---------------------------------------------------------------------------
-// Same plane / tap / decision arithmetic as march_column (rr_integrate.cu), operands read from the stage:
-//   inverse-volume corners: float4 at inv_off + ((s*BZ + k-izlo)*BY + y-iylo)*BX + x-ixlo
+// Same plane / tap / decision arithmetic as march_column (rr_integrate.cuh), operands read from the item's slots:
+//   inverse-volume corners: float4 at ib[s] + ((k*BY + y)*BX + x) * 16
 //   pair texels of the footprint (ex, ey): float2 at tb[s] + (ey*T + ex)*8, +8, +T*8, +T*8+8
 template <int N, int MODE>
-__device__ __forceinline__ void march_staged(const IntegrateParams& p, const uint8_t* __restrict__ smem, uint32_t sbase,
-                                             const ItemHdr* __restrict__ h, int BX, uint32_t ps, uint32_t ss, int T, int x, int y) {
-  // Register budget: 80 per thread with 768 threads per CTA. Everything warp-uniform that is needed once per voxel or less
-  // (tile bases, z range, verdict masks) stays in the stage header and is re-read by LDS (a broadcast) where it is used.
+__device__ __forceinline__ void march_staged(const IntegrateParams& p, const uint8_t* __restrict__ smem, const ItemHdr* __restrict__ h,
+                                             int BX, uint32_t ps, int T, int x, int y) {
+  // Register budget: 72 per thread with 22 consumer warps. Everything warp-uniform that is needed once per voxel or less
+  // (slot bases, z range, verdict masks) stays in the item header and is re-read by LDS (a broadcast) where it is used.
   float a, b;
-  uint32_t c00, dX, dY;            // byte offset of the (x0, y0) corner in plane 0 of sensor 0; +dX: x1, +dY: y1
+  uint32_t cxy, dX, dY;            // byte offset of the (x0, y0) corner inside a coarse plane; +dX: x1, +dY: y1
   {
     const float stepX = 1.0f / (float)p.X, stepY = 1.0f / (float)p.Y;
     const float px = ((float)x + 0.5f) * stepX, py = ((float)y + 0.5f) * stepY;
     int x0, x1, y0, y1;
     lin_coord(px, p.IX, x0, x1, a);
     lin_coord(py, p.IY, y0, y1, b);
-    // plane k of sensor s starts at sbase + STAGE_HDR_BYTES + s * ss + (k - izlo) * ps: fold izlo into the base
-    c00 = sbase + STAGE_HDR_BYTES - (uint32_t)h->izlo * ps + ((uint32_t)((y0 - h->iylo) * BX + (x0 - h->ixlo)) << 4);
+    cxy = (uint32_t)(y0 * BX + x0) << 4;
     dX = (uint32_t)(x1 - x0) << 4;
     dY = (uint32_t)((y1 - y0) * BX) << 4;
   }
@@ -155,7 +166,7 @@ __device__ __forceinline__ void march_staged(const IntegrateParams& p, const uin
 
   auto plane = [&](int s, int k) -> float3 {
     if ((masks >> s) & 1u) return make_float3(0.f, 0.f, 0.f);
-    const uint8_t* q = smem + (c00 + (uint32_t)s * ss + (uint32_t)k * ps);
+    const uint8_t* q = smem + (h->ib[s] + (uint32_t)k * ps + cxy);
     const float4 p00 = *reinterpret_cast<const float4*>(q), p10 = *reinterpret_cast<const float4*>(q + dX);
     const float4 p01 = *reinterpret_cast<const float4*>(q + dY), p11 = *reinterpret_cast<const float4*>(q + dY + dX);
     return plane_reduce(p00, p10, p01, p11, a, 1.0f - a, b, 1.0f - b);
@@ -163,7 +174,7 @@ __device__ __forceinline__ void march_staged(const IntegrateParams& p, const uin
 
   const int zb = h->zb;
   unsigned o = (unsigned)((zb * p.Y + y) * p.X + x);
-  const float4* zt_ptr = reinterpret_cast<const float4*>(smem + sbase + ITEM_HDR_BYTES);       // the item's slice of the z table
+  const float4* zt_ptr = reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(h) + ITEM_HDR_BYTES);   // the item's slice of the z table
   const float4* zt_end = zt_ptr + (h->ze - zb);
   for (; zt_ptr < zt_end; ++zt_ptr, o += p.plane_elems) {
     const float4 zt = *zt_ptr;
@@ -216,18 +227,22 @@ __device__ __noinline__ void march_direct(const IntegrateParams& p, int x, int y
 
 // ---- the kernel ------------------------------------------------------------------------------------------------------
 // The CTA is launched as whole warpgroups: the CWARPS consumer warps rounded up to warpgroups, then two auxiliary
-// warpgroups = one producer warp per pipeline stage + six clear warps. It starts at 65536 / threads registers per thread;
-// the auxiliary warpgroups then give registers back (setmaxnreg.dec to 40) and the consumer warpgroups take them
-// (setmaxnreg.inc to 72 with 22 consumer warps, 144 with 11): the clear gets enough warps to keep HBM busy - a warp streams
-// only ~4 B/clk of stores - while the brick evaluation keeps its register budget.
-// Each stage has its own producer (lane 0 of its warp): it draws an item from the global counter, gathers its metadata,
-// waits until the consumers have left the stage, issues the copies and, when they have landed, hands the stage over. Two
-// producers keep two items in preparation at any time, so the chain of dependent loads behind one item is never on the
-// consumers' critical path. Consumers visit the stages alternately until both have signalled the end.
+// warpgroups = the producer warp + seven clear warps. It starts at 65536 / threads registers per thread; the auxiliary
+// warpgroups then give registers back (setmaxnreg.dec to 40) and the consumer warpgroups take them (setmaxnreg.inc to 72
+// with 22 consumer warps, 144 with 11): the clear gets enough warps to keep HBM busy while the brick evaluation keeps its
+// register budget.
+//
+// Items flow through a ring of NH headers and a ring of operand slots (one slot = one sensor's inverse-volume box + its
+// pair-image tile). The producer (one thread) draws an item from this frame's class-sorted list, takes a header and as
+// many slots as the item has sensors to evaluate voxel by voxel - sensors a verdict has settled need no operands - and
+// issues the copies against the header's `full` barrier without waiting for them: an average item of the bench workload
+// holds 3 of 10 slots, so three to four items are in flight and a consumer warp that finishes early runs ahead instead of
+// waiting. Consumer warps walk the headers in order; the last one to leave an item completes its `empty` barrier, which
+// is what the producer waits on (oldest item first) when it needs a header or slots back.
 template <int CWARPS> struct StagedShape {
   static constexpr int kConsumerWG = (CWARPS + 3) / 4;
   static constexpr int kThreads = (kConsumerWG + 2) * 128;
-  static constexpr int kProducerWarp = kConsumerWG * 4;     // and kProducerWarp + 1
+  static constexpr int kProducerWarp = kConsumerWG * 4;
   static constexpr int kAuxRegs = 40;
   // setmaxnreg needs the kernel's register count declared (.maxnreg)
   static constexpr int kLaunchRegs = (65536 / kThreads) / 8 * 8;
@@ -241,14 +256,12 @@ template <int N, int MODE, int CWARPS>
 __global__ void __maxnreg__((StagedShape<CWARPS>::kLaunchRegs))
 k_integrate_staged(const __grid_constant__ StagedParams p, const __grid_constant__ CUtensorMap map_inv, const __grid_constant__ CUtensorMap map_pairs) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t s_full[2], s_ready[2], s_empty[2];
+  __shared__ __align__(8) uint64_t s_full[NH], s_empty[NH];
   // TMA destinations must be 128-byte aligned; the dynamic window's own alignment is only guaranteed to 16
   uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
-    mbar_init(&s_ready[0], 1); mbar_init(&s_ready[1], 1);
-    mbar_init(&s_empty[0], CWARPS); mbar_init(&s_empty[1], CWARPS);
+    for (int i = 0; i < NH; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], CWARPS); }
     mbar_fence_init();
   }
   // the clear's bulk-store source: fill_src_bytes of cleared voxels (then as many zero bytes for a separate weight volume)
@@ -263,126 +276,170 @@ k_integrate_staged(const __grid_constant__ StagedParams p, const __grid_constant
   for (int i = threadIdx.x; i < 2 * p.f.ip.Z; i += blockDim.x) s_cand_z[i] = p.f.cand_z[i];
   for (uint32_t i = threadIdx.x; i < p.n_rowany; i += blockDim.x) s_rowany[i] = p.f.rowany[i];
   __syncthreads();
+  RR_PROF(const long long t_start = clock64();)
   const FillTables ft{s_cand_y, s_cand_z, s_rowany};
   const IntegrateParams& ip = p.f.ip;
   using Shape = StagedShape<CWARPS>;
   constexpr int PWARP = Shape::kProducerWarp;
-  const FillSource fs{p.fill_src_bytes ? smem_u32(smem + p.fill_src_off) : 0u, p.fill_src_bytes, (p.debug & 32) != 0, l2_policy_evict_first()};
+  const FillSource fs{smem_u32(smem + p.fill_src_off), p.fill_src_bytes, (p.debug & 32) != 0, l2_policy_evict_first(), p.fill_depth, p.fill_lsu != 0};
 
-  // ---- producer of one stage (one thread)
-  auto producer = [&](const int stage) {
+  // ---- producer (one thread)
+  auto producer = [&]() {
     tma_prefetch_desc(&map_inv);
     tma_prefetch_desc(&map_pairs);
     const uint64_t keep = l2_policy_evict_last();
-    const uint32_t n_occ = *ip.num_occupied;
-    // occupied bricks that intersect the slab: the list ascends in brick id, hence in brick z, so they are one run [lo, hi)
-    uint32_t lo = 0, hi = n_occ;
-    if (ip.z_begin > 0) {
-      uint32_t a = 0, b = n_occ;
-      while (a < b) { const uint32_t m = (a + b) >> 1; if (ip.ranges[(size_t)ip.occupied[m] * 6 + 5] > ip.z_begin) b = m; else a = m + 1; }
-      lo = a;
-    }
-    if (ip.z_end < ip.Z) {
-      uint32_t a = lo, b = n_occ;
-      while (a < b) { const uint32_t m = (a + b) >> 1; if (ip.ranges[(size_t)ip.occupied[m] * 6 + 4] >= ip.z_end) b = m; else a = m + 1; }
-      hi = a;
-    }
+    uint32_t cnt[N + 1];
+#pragma unroll
+    for (int k = 0; k <= N; ++k) cnt[k] = (p.debug & 2) ? 0u : min(p.class_count[k], p.list_stride);
     const uint32_t per_brick = (uint32_t)(p.n_yc * p.n_zc);
-    const uint32_t total = (p.debug & 2) ? 0u : (hi - lo) * per_brick;
     const float stepX = 1.0f / (float)ip.X, stepY = 1.0f / (float)ip.Y;
-    uint8_t* st = smem + (uint32_t)stage * p.stage_bytes;
-    ItemHdr* h = reinterpret_cast<ItemHdr*>(st);
-    uint32_t phase = 0;
+    uint32_t j = 0, tail = 0, slots_free = p.n_slots, slot_head = 0;      // items pushed / retired, the slot ring
+    auto hdr = [&](uint32_t k) { return reinterpret_cast<ItemHdr*>(smem + (k % NH) * HDR_BYTES); };
+    // wait until the oldest item in flight has been consumed; its slots return to the ring
+    auto retire = [&]() -> bool {
+      if (!mbar_wait(&s_empty[tail % NH], (tail / NH) & 1u, p.err)) return false;
+      slots_free += hdr(tail)->nslots;
+      ++tail;
+      return true;
+    };
+    RR_PROF(long long tp0 = clock64(); long long tp1 = 0; long long t_meta = 0; long long t_empty = 0; long long n_staged = 0; long long n_direct = 0;)
     for (;;) {
       const uint32_t it = atomicAdd(p.f.work, 1u);
-      if (it >= total) {
-        if (mbar_wait(&s_empty[stage], phase ^ 1u, p.err)) { h->valid = 0; mbar_arrive(&s_ready[stage]); }
+      // the most expensive class first
+      int cls = -1;
+      uint32_t idx = it;
+#pragma unroll
+      for (int k = N; k >= 0; --k)
+        if (cls < 0) { if (idx < cnt[k]) cls = k; else idx -= cnt[k]; }
+      if (cls < 0) {
+        while (j - tail >= NH) if (!retire()) return;
+        ItemHdr* h = hdr(j);
+        h->valid = 0; h->nslots = 0;
+        mbar_arrive(&s_full[j % NH]);
+        RR_PROF(if (p.prof) {
+          atomicAdd(p.prof + 4, (unsigned long long)t_meta); atomicAdd(p.prof + 5, (unsigned long long)t_empty);
+          atomicAdd(p.prof + 7, (unsigned long long)n_staged); atomicAdd(p.prof + 8, (unsigned long long)n_direct);
+        })
         return;
       }
-      const uint32_t bi = it / per_brick, r = it - bi * per_brick;
+      const uint2 e = p.list[(size_t)cls * p.list_stride + idx];
+      const uint32_t item = e.x;
+      const uint32_t brick = item / per_brick, r = item - brick * per_brick;
       const int yc = (int)(r / (uint32_t)p.n_zc), zc = (int)(r - (uint32_t)yc * (uint32_t)p.n_zc);
-      const uint32_t brick = ip.occupied[lo + bi];
-      const bool direct = p.legacy && p.legacy[brick];     // a footprint of this brick exceeds the tile: global-memory path
       const int32_t* rg = ip.ranges + (size_t)brick * 6;
       const int x0 = rg[0], x1 = rg[1];
       const int yb = rg[2] + yc * p.cy, ye = min(yb + p.cy, rg[3]);
       const int zb = max(rg[4] + zc * p.cz, ip.z_begin), ze = min(min(rg[4] + (zc + 1) * p.cz, rg[5]), ip.z_end);
       if (x0 >= x1 || yb >= ye || zb >= ze) continue;
-      if (direct) {
-        if (!mbar_wait(&s_empty[stage], phase ^ 1u, p.err)) return;
-        h->valid = 2;
-        h->x0 = x0; h->nx = x1 - x0; h->y0 = yb; h->ny = ye - yb; h->zb = zb; h->ze = ze;
-        mbar_arrive(&s_ready[stage]);            // nothing to copy
-        phase ^= 1u;
-        continue;
-      }
-      // coarse box of the item: lin_coord is monotone, so the first / last voxel bound every corner index
-      int i0, i1, ixlo, ixhi, iylo, iyhi; float w;
-      lin_coord(((float)x0 + 0.5f) * stepX, ip.IX, ixlo, i1, w);
-      lin_coord(((float)(x1 - 1) + 0.5f) * stepX, ip.IX, i0, ixhi, w);
-      lin_coord(((float)yb + 0.5f) * stepY, ip.IY, iylo, i1, w);
-      lin_coord(((float)(ye - 1) + 0.5f) * stepY, ip.IY, i0, iyhi, w);
-      const int izlo = __float_as_int(ip.ztab[zb].x), izhi = __float_as_int(ip.ztab[ze - 1].y);
-      if (ixhi - ixlo >= p.BX || iyhi - iylo >= p.BY || izhi - izlo >= p.BZ) { atomicOr(p.err, 1u); continue; }
-      const size_t item = (size_t)(brick * (uint32_t)p.n_yc + (uint32_t)yc) * (uint32_t)p.n_zc + (uint32_t)zc;
-      const uint32_t verdict = (p.debug & 4) ? 0u : p.cls[item];
-      const uint2* fp = p.fp + item * N;
+      const uint32_t verdict = (p.debug & 4) ? 0u : e.y;
+      const uint32_t off = (verdict | (verdict >> 8)) & ((1u << N) - 1u);      // sensors a verdict has settled
+      const uint2* fp = p.fp + (size_t)item * N;
       uint2 f[N];
 #pragma unroll
       for (int s = 0; s < N; ++s) f[s] = fp[s];
-      // everything above overlapped the consumers' work on this stage's previous item; now the stage itself is needed
-      if (!mbar_wait(&s_empty[stage], phase ^ 1u, p.err)) return;
-      h->valid = 1;
-      h->x0 = x0; h->nx = x1 - x0; h->y0 = yb; h->ny = ye - yb; h->zb = zb; h->ze = ze;
-      h->ixlo = ixlo; h->iylo = iylo; h->izlo = izlo;
-      h->nbx = ixhi - ixlo + 1; h->nby = iyhi - iylo + 1; h->nbz = izhi - izlo + 1;
-      h->skip = verdict & 255u; h->front = verdict >> 8;
-      const uint32_t base = (uint32_t)stage * p.stage_bytes + STAGE_HDR_BYTES;
+      bool direct = false;                     // a footprint that has to be read exceeds the tile: global-memory path
 #pragma unroll
-      for (int s = 0; s < N; ++s) {
-        h->rect[s] = f[s].y;
-        h->tb[s] = base + p.inv_span + (uint32_t)s * p.tile_span + ((uint32_t)(p.T + 1) << 3) -
-                   ((((f[s].x >> 16) * (uint32_t)p.T) + (f[s].x & 0xffffu)) << 3);
+      for (int s = 0; s < N; ++s) direct = direct || (!((off >> s) & 1u) && (f[s].y & 128u));
+      const uint32_t act = direct ? 0u : (uint32_t)N - (uint32_t)__popc(off);
+      // coarse box of the item: lin_coord is monotone, so the first / last voxel bound every corner index
+      int ixlo = 0, iylo = 0, izlo = 0;
+      if (!direct) {
+        int i0, i1, ixhi, iyhi; float w;
+        lin_coord(((float)x0 + 0.5f) * stepX, ip.IX, ixlo, i1, w);
+        lin_coord(((float)(x1 - 1) + 0.5f) * stepX, ip.IX, i0, ixhi, w);
+        lin_coord(((float)yb + 0.5f) * stepY, ip.IY, iylo, i1, w);
+        lin_coord(((float)(ye - 1) + 0.5f) * stepY, ip.IY, i0, iyhi, w);
+        izlo = __float_as_int(ip.ztab[zb].x);
+        const int izhi = __float_as_int(ip.ztab[ze - 1].y);
+        if (ixhi - ixlo >= p.BX || iyhi - iylo >= p.BY || izhi - izlo >= p.BZ) { atomicOr(p.err, 1u); continue; }
       }
-      const uint32_t zt_bytes = (uint32_t)(ze - zb) * 16u;
-      mbar_expect_tx(&s_full[stage], p.inv_bytes + (uint32_t)N * p.tile_bytes + zt_bytes);
-      bulk_load(smem_u32(st) + ITEM_HDR_BYTES, ip.ztab + zb, zt_bytes, &s_full[stage]);
-      const uint32_t dst = smem_u32(st) + STAGE_HDR_BYTES;
-      tma_load_5d(dst, &map_inv, &s_full[stage], 0, ixlo, iylo, izlo, 0, keep);
+      // everything above overlapped the consumers' work; now a header and the item's slots are needed
+      RR_PROF(tp1 = clock64(); t_meta += tp1 - tp0;)
+      while (j - tail >= NH || slots_free < act) if (!retire()) return;
+      RR_PROF(tp0 = clock64(); t_empty += tp0 - tp1;)
+      const uint32_t hs = j % NH;
+      ItemHdr* h = hdr(j);
+      h->valid = direct ? 2 : 1;
+      h->x0 = x0; h->nx = x1 - x0; h->y0 = yb; h->ny = ye - yb; h->zb = zb; h->ze = ze;
+      h->skip = verdict & 255u; h->front = (verdict >> 8) & 255u;
+      h->nslots = act;
+      if (direct) {
+        mbar_arrive(&s_full[hs]);              // nothing to copy
+        RR_PROF(++n_direct;)
+      } else {
+        const uint32_t first = slot_head;
+        const uint32_t vol0 = (uint32_t)((izlo * p.BY + iylo) * p.BX + ixlo) << 4;
 #pragma unroll
-      for (int s = 0; s < N; ++s)
-        tma_load_3d(dst + p.inv_span + (uint32_t)s * p.tile_span, &map_pairs, &s_full[stage], (int)(f[s].x & 0xffffu), (int)(f[s].x >> 16), s, keep);
-      // the copies have landed: hand the stage to the consumers
-      if (!mbar_wait(&s_full[stage], phase, p.err)) return;
-      mbar_arrive(&s_ready[stage]);
-      phase ^= 1u;
+        for (int s = 0; s < N; ++s) {
+          if ((off >> s) & 1u) continue;
+          const uint32_t slot = p.slots_off + slot_head * p.slot_bytes;
+          slot_head = slot_head + 1u == p.n_slots ? 0u : slot_head + 1u;
+          h->ib[s] = slot - vol0;
+          h->tb[s] = slot + p.inv_span + ((uint32_t)(p.T + 1) << 3) - ((((f[s].x >> 16) * (uint32_t)p.T) + (f[s].x & 0xffffu)) << 3);
+        }
+        const uint32_t zt_bytes = (uint32_t)(ze - zb) * 16u;
+        mbar_expect_tx(&s_full[hs], zt_bytes + act * (p.inv_bytes + p.tile_bytes));
+        const uint32_t base = smem_u32(smem);
+        bulk_load(base + hs * HDR_BYTES + ITEM_HDR_BYTES, ip.ztab + zb, zt_bytes, &s_full[hs]);
+        uint32_t sl = first;
+#pragma unroll
+        for (int s = 0; s < N; ++s) {
+          if ((off >> s) & 1u) continue;
+          const uint32_t dst = base + p.slots_off + sl * p.slot_bytes;
+          sl = sl + 1u == p.n_slots ? 0u : sl + 1u;
+          tma_load_5d(dst, &map_inv, &s_full[hs], 0, ixlo, iylo, izlo, s, keep);
+          tma_load_3d(dst + p.inv_span, &map_pairs, &s_full[hs], (int)(f[s].x & 0xffffu), (int)(f[s].x >> 16), s, keep);
+        }
+        RR_PROF(++n_staged; if (p.prof) {
+          uint32_t need = 0;
+          for (int s = 0; s < N; ++s)
+            if (!((off >> s) & 1u)) need = max(need, max((f[s].y & 127u) + ((f[s].y >> 8) & 4095u), f[s].y >> 20));
+          atomicMax(p.prof + 13, (unsigned long long)need); atomicAdd(p.prof + 3, (unsigned long long)act);
+          if (need <= 30u) atomicAdd(p.prof + 14, 1ull);
+          if (need <= 36u) atomicAdd(p.prof + 15, 1ull);
+        })
+      }
+      slots_free -= act;
+      ++j;
+      RR_PROF(tp0 = clock64();)
     }
   };
-  // ---- consumers: stages alternately, each until its producer signals the end
+  // ---- consumers: the headers in order, until the producer signals the end
   auto consumer = [&]() {
-    const uint32_t ps = (uint32_t)(p.BX * p.BY) << 4, ss = ps * (uint32_t)p.BZ;
-    uint32_t phase[2] = {0u, 0u};
-    bool live[2] = {true, true};
-    for (int stage = 0; live[0] || live[1]; stage ^= 1) {
-      if (!live[stage]) continue;
-      if (!mbar_wait(&s_ready[stage], phase[stage], p.err)) return;
-      const uint32_t sbase = (uint32_t)stage * p.stage_bytes;
-      const ItemHdr* h = reinterpret_cast<const ItemHdr*>(smem + sbase);
-      if (!h->valid) { live[stage] = false; continue; }
+    const uint32_t ps = (uint32_t)(p.BX * p.BY) << 4;
+    RR_PROF(long long tc0 = clock64(); long long t_wait = 0; long long t_work = 0; long long t_idle = 0;)
+    for (uint32_t j = 0;; ++j) {
+      const uint32_t hs = j % NH;
+      if (!mbar_wait(&s_full[hs], (j / NH) & 1u, p.err)) return;
+      RR_PROF({ const long long t = clock64(); t_wait += t - tc0; tc0 = t; })
+      const ItemHdr* h = reinterpret_cast<const ItemHdr*>(smem + hs * HDR_BYTES);
+      if (!h->valid) break;
       // one column per thread: the host sizes the y-chunk so that an item's columns fit the consumer threads
       const int nx = h->nx, col = (int)threadIdx.x;
       if (col < nx * h->ny) {
         const int cyv = col / nx, x = h->x0 + (col - cyv * nx), y = h->y0 + cyv;
         if (h->valid == 2) march_direct<N, MODE>(ip, x, y, h->zb, h->ze);      // oversize footprint: operands from global memory
-        else march_staged<N, MODE>(ip, smem, sbase, h, p.BX, ps, ss, p.T, x, y);
+        else march_staged<N, MODE>(ip, smem, h, p.BX, ps, p.T, x, y);
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[stage]);
-      phase[stage] ^= 1u;
+      RR_PROF({ const long long t = clock64(); if (col - lane < nx * h->ny) t_work += t - tc0; else t_idle += 1; tc0 = t; })
+      if (lane == 0) mbar_arrive(&s_empty[hs]);
     }
+    RR_PROF(if (p.prof && lane == 0) {
+      atomicAdd(p.prof + 0, (unsigned long long)t_wait); atomicAdd(p.prof + 1, (unsigned long long)t_work);
+      atomicAdd(p.prof + 2, (unsigned long long)t_idle);
+    })
   };
   // ---- clear stream: the clear warps from the start, everybody else once their own work is done
-  auto clear = [&]() { fill_loop_bulk<MODE == 1>(p.f, ft, lane, fs); };
+  auto clear = [&]() {
+    RR_PROF(const long long t0 = clock64();)
+    fill_loop_bulk<MODE == 1>(p.f, ft, lane, fs);
+    RR_PROF(if (p.prof && lane == 0) {
+      atomicAdd(p.prof + (warp > PWARP ? 9 : 10), (unsigned long long)(clock64() - t0));
+      atomicMax(p.prof + 11, (unsigned long long)(clock64() - t_start));
+      atomicAdd(p.prof + 12, (unsigned long long)(clock64() - t_start));
+    })
+  };
   const bool helpers_clear = !(p.debug & 16);
   // each role's code sits behind its own setmaxnreg, so that ptxas allocates it against that budget
   if (warp < PWARP) {
@@ -391,8 +448,8 @@ k_integrate_staged(const __grid_constant__ StagedParams p, const __grid_constant
     if (helpers_clear) clear();
   } else {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Shape::kAuxRegs));
-    if (warp <= PWARP + 1) {
-      if (lane == 0) producer(warp - PWARP);
+    if (warp == PWARP) {
+      if (lane == 0) producer();
       __syncwarp();
       if (helpers_clear) clear();
     } else {
@@ -547,8 +604,8 @@ static int footprints(rr_ctx* c, const IntegrateParams& p, int cy, int cz, int n
 }
 
 void staged_release(rr_ctx* c) {
-  cudaFree(c->sti.d_fp); cudaFree(c->sti.d_legacy); cudaFree(c->sti.d_err); cudaFree(c->sti.d_zr); cudaFree(c->sti.d_cls);
-  c->sti.d_fp = nullptr; c->sti.d_legacy = nullptr; c->sti.d_err = nullptr; c->sti.d_zr = nullptr; c->sti.d_cls = nullptr;
+  cudaFree(c->sti.d_fp); cudaFree(c->sti.d_list); cudaFree(c->sti.d_err); cudaFree(c->sti.d_zr);
+  c->sti.d_fp = nullptr; c->sti.d_list = nullptr; c->sti.d_err = nullptr; c->sti.d_zr = nullptr;
   c->sti.ok = false; c->sti.dirty = true;
 }
 
@@ -570,8 +627,8 @@ bool staged_classify_params(const rr_ctx* c, ClassifyParams& q) {
   if (!staged_selected(c)) return false;
   const auto& st = c->sti;
   q.fp = st.d_fp; q.zr = st.d_zr; q.pairs = c->d_pairs; q.pair_pitch = c->pair_pitch; q.H2 = c->H + 2;
-  q.legacy = st.n_legacy ? st.d_legacy : nullptr;
-  q.cls = st.d_cls; q.per_brick = st.n_yc * st.n_zc; q.N = c->N; q.limit = c->cfg.limit;
+  q.list = st.d_list; q.class_count = c->d_counters + c->bricks.num; q.list_stride = st.list_stride;
+  q.per_brick = st.n_yc * st.n_zc; q.N = c->N; q.limit = c->cfg.limit;
   return true;
 }
 
@@ -585,7 +642,7 @@ int staged_prepare(rr_ctx* c) {
   const Tunables& tn = tunables();
   if (!st.dirty && st.generation == staged_key()) return RR_OK;
   st.ok = false;
-  st.n_legacy = 0;
+  st.n_oversize = 0;
   if (!c->configured || !c->cfg.use_bricks || !c->fused_ok || !tn.staged || !tn.fused || !c->d_inv) return RR_OK;
   for (int i = 0; i < c->N; ++i) if (!c->have_inv[i]) return RR_OK;
   st.dirty = false;
@@ -603,9 +660,9 @@ int staged_prepare(rr_ctx* c) {
   if (max_nx <= 0 || max_ny <= 0 || max_nz <= 0) return RR_OK;
   // the clear's bulk stores need 16-byte aligned rows, a row mask of at most 32 words and a buffer of at least one row
   const long fill_buf = std::max(4L, (long)tn.stage_bulk_fill) * 1024;
-  if ((X & 3) != 0 || X > 1024 || (long)X * 4 > fill_buf) return RR_OK;
+  if ((X & 3) != 0 || X > 1024 || (long)X * 4 > fill_buf || c->W > 0xffff || c->H > 0xffff) return RR_OK;
   st.cwarps = consumer_warps(N);
-  st.fwarps = 6;
+  st.fwarps = 7;
   const int CT = st.cwarps * 32;
   // y-chunk: as many brick rows as fill the consumer threads best (ties: the larger chunk, fewer items)
   int cy = tn.stage_ychunk > 0 ? std::min(tn.stage_ychunk, max_ny) : 0;
@@ -648,11 +705,17 @@ int staged_prepare(rr_ctx* c) {
   cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device);
   const int weight_mode = c->cfg.store_weight == RR_VOXELS_F32_WEIGHT ? 2 : 1;
   const long tables = ((long)(4 * (Y + Z)) + (long)c->bricks.res[1] * c->bricks.res[2] + 127) & ~127L;      // cand_y, cand_z, rowany
-  const long budget = ((long)smem_max - 1024 - fill_buf * weight_mode - tables) / 2 - STAGE_HDR_BYTES;           // per stage, after the header
-  const long inv_bytes = (long)N * BZ * BY * BX * 16, inv_span = (inv_bytes + 127) & ~127L;
-  long t_budget = (long)std::floor(std::sqrt(std::max(0.0, double(budget - inv_span - 128 * N) / (8.0 * N))));
-  t_budget = std::min(t_budget & ~1L, 256L);
-  if (t_budget < 8) return RR_OK;
+  const long budget = (long)smem_max - 1024 - (long)NH * HDR_BYTES - fill_buf * weight_mode - tables;       // the slot ring
+  const long inv_bytes = (long)BZ * BY * BX * 16, inv_span = (inv_bytes + 127) & ~127L;
+  auto slot_bytes_for = [&](long T) { return inv_span + ((T * T * 8 + 127) & ~127L); };
+  // largest tile that still leaves `slots` slots
+  auto tile_for_slots = [&](long slots) {
+    long T = 256;
+    while (T >= 8 && slot_bytes_for(T) * slots > budget) T -= 2;
+    return T;
+  };
+  const long t_min_slots = tile_for_slots(N);            // every sensor of one item must fit the ring
+  if (t_min_slots < 8) return RR_OK;
 
   // footprints of every item of the brick grid
   IntegrateParams p{};
@@ -662,7 +725,7 @@ int staged_prepare(rr_ctx* c) {
   RR_TRY_RC(build_ztab(c));
   p.ztab = c->d_ztab;
   const size_t items = nb * (size_t)n_yc * n_zc;
-  if (items == 0 || items > 0x7fffffffull) return RR_OK;
+  if (items == 0 || items > 0x3fffffffull) return RR_OK;
   int4* d_ext = nullptr;
   float2* d_zr = nullptr;
   if (cudaMalloc((void**)&d_ext, items * N * sizeof(int4)) != cudaSuccess) { cudaGetLastError(); return RR_OK; }
@@ -673,7 +736,9 @@ int staged_prepare(rr_ctx* c) {
   if (rc == RR_OK) rc = check(c, cudaStreamSynchronize(c->stream), "footprint sync");
   cudaFree(d_ext);
   if (rc != RR_OK) { cudaFree(d_zr); return rc; }
-  // tile edge: cover every footprint if that is affordable, else the bulk of them (the rest goes to k_integrate_bricks)
+  // Tile edge: a smaller tile leaves more slots in the ring (more items in flight), a larger one sends fewer (item, sensor)
+  // pairs to the global-memory path, which costs several times a staged item: the largest tile that keeps two items' worth
+  // of slots plus one, and no larger than the largest footprint of the grid.
   std::vector<int> need;
   need.reserve(ext.size());
   for (const int4& e : ext)
@@ -683,44 +748,44 @@ int staged_prepare(rr_ctx* c) {
   auto even = [](long v) { return (v + 1) & ~1L; };
   long T;
   if (tn.stage_tile > 0) {
-    T = std::min<long>(even(tn.stage_tile), t_budget);
+    T = std::min<long>(even(tn.stage_tile), t_min_slots);
   } else {
-    const long t_all = even(need.back()), t_bulk = even(need[(size_t)((need.size() - 1) * 0.98)]);
-    T = (t_all <= t_budget && t_all <= std::max(48L, t_bulk + 8)) ? t_all : std::min(t_budget, std::max(16L, t_bulk));
+    T = std::min(even(need.back()), std::max(tile_for_slots(2 * N + 1), std::min(t_min_slots, 24L)));
   }
   T = std::max(T, 8L);
+  const long slot_bytes = slot_bytes_for(T);
+  const long n_slots = std::min(budget / slot_bytes, 64L);
+  if (n_slots < N) { cudaFree(d_zr); return RR_OK; }
   std::vector<uint2> fp(items * N, make_uint2(0u, 0u));
-  std::vector<uint8_t> legacy(nb, 0);
-  const size_t per_brick = (size_t)n_yc * n_zc;
   for (size_t i = 0; i < items; ++i)
     for (int s = 0; s < N; ++s) {
       const int4& e = ext[i * N + s];
       if (e.z < e.x) continue;
-      if (std::max(e.z - (e.x & ~1), e.w - e.y) + 2 > T || e.x > 0xffff || e.y > 0xffff) { legacy[i / per_brick] = 1; continue; }
-      // tile origin (even x: TMA start coordinates are multiples of 16 bytes) and the footprint rectangle inside the tile
-      const uint32_t rx = (uint32_t)(e.x & 1), rw = (uint32_t)(e.z - e.x + 2), rh = (uint32_t)(e.w - e.y + 2);
-      fp[i * N + s] = make_uint2((uint32_t)(e.x & ~1) | ((uint32_t)e.y << 16), rx | (rw << 8) | (rh << 20));
+      // tile origin (even x: TMA start coordinates are multiples of 16 bytes) and the footprint rectangle inside the tile;
+      // bit 7: the footprint exceeds the tile (the item then reads its operands from global memory, if this sensor is read at all)
+      const uint32_t over = std::max(e.z - (e.x & ~1), e.w - e.y) + 2 > T ? 128u : 0u;
+      const uint32_t rx = (uint32_t)(e.x & 1), rw = (uint32_t)std::min(e.z - e.x + 2, 4095), rh = (uint32_t)std::min(e.w - e.y + 2, 4095);
+      fp[i * N + s] = make_uint2((uint32_t)(e.x & ~1) | ((uint32_t)e.y << 16), rx | over | (rw << 8) | (rh << 20));
+      st.n_oversize += over ? 1u : 0u;
     }
-  for (uint8_t v : legacy) st.n_legacy += v;
   staged_release(c);
   st.dirty = false;
   st.d_zr = d_zr;
-  RR_TRY_RC(check(c, cudaMalloc((void**)&st.d_cls, items * sizeof(uint32_t)), "verdict table"));
-  cudaMemsetAsync(st.d_cls, 0, items * sizeof(uint32_t), c->stream);
+  st.list_stride = (uint32_t)items;
+  RR_TRY_RC(check(c, cudaMalloc((void**)&st.d_list, (size_t)(N + 1) * items * sizeof(uint2)), "item lists"));
   RR_TRY_RC(check(c, cudaMalloc((void**)&st.d_fp, fp.size() * sizeof(uint2)), "footprint table"));
-  RR_TRY_RC(check(c, cudaMalloc((void**)&st.d_legacy, nb), "legacy brick mask"));
-  RR_TRY_RC(check(c, cudaMalloc((void**)&st.d_err, 4 * sizeof(uint32_t)), "staged flags"));
+  RR_TRY_RC(check(c, cudaMalloc((void**)&st.d_err, 4 * sizeof(uint32_t) + 16 * sizeof(unsigned long long)), "staged flags"));
   cudaMemcpyAsync(st.d_fp, fp.data(), fp.size() * sizeof(uint2), cudaMemcpyHostToDevice, c->stream);
-  cudaMemcpyAsync(st.d_legacy, legacy.data(), nb, cudaMemcpyHostToDevice, c->stream);
-  cudaMemsetAsync(st.d_err, 0, 4 * sizeof(uint32_t), c->stream);
+  cudaMemsetAsync(st.d_err, 0, 4 * sizeof(uint32_t) + 16 * sizeof(unsigned long long), c->stream);
+  cudaMemsetAsync(c->d_counters + nb, 0, RR_CLASS_COUNTERS * sizeof(uint32_t), c->stream);
   RR_TRY_RC(check(c, cudaStreamSynchronize(c->stream), "staged tables upload"));
 
-  // tensor maps: inverse volumes as (xyzw, IX, IY, IZ, N) float32, pair image as (pitch, H+2, N) 8-byte pixels.
+  // tensor maps: inverse volumes as (xyzw, IX, IY, IZ, N) float32 with a one-sensor box, pair image as (pitch, H+2, N) 8-byte pixels.
   // The innermost start coordinate of a tile must be a multiple of 16 bytes (measured: tools/tma_probe.cu), so tile origins are even pixels.
   {
     const cuuint64_t dims[5] = {4, (cuuint64_t)IX, (cuuint64_t)IY, (cuuint64_t)IZ, (cuuint64_t)N};
     const cuuint64_t strides[4] = {16, (cuuint64_t)IX * 16, (cuuint64_t)IX * IY * 16, (cuuint64_t)IX * IY * IZ * 16};
-    const cuuint32_t box[5] = {4, (cuuint32_t)BX, (cuuint32_t)BY, (cuuint32_t)BZ, (cuuint32_t)N};
+    const cuuint32_t box[5] = {4, (cuuint32_t)BX, (cuuint32_t)BY, (cuuint32_t)BZ, 1};
     const cuuint32_t es[5] = {1, 1, 1, 1, 1};
     if (enc(&st.map_inv, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, c->d_inv, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return RR_OK;
@@ -738,11 +803,13 @@ int staged_prepare(rr_ctx* c) {
   st.inv_bytes = (uint32_t)inv_bytes;
   st.tile_bytes = (uint32_t)(T * T * 8);
   st.inv_span = (uint32_t)inv_span;
-  st.tile_span = (st.tile_bytes + 127u) & ~127u;
-  st.stage_bytes = STAGE_HDR_BYTES + st.inv_span + (uint32_t)N * st.tile_span;
+  st.slot_bytes = (uint32_t)slot_bytes;
+  st.n_slots = (uint32_t)n_slots;
+  st.slots_off = (uint32_t)NH * HDR_BYTES;
   st.fill_src_bytes = (uint32_t)fill_buf;
-  st.smem_bytes = 2 * st.stage_bytes + 128 + (uint32_t)(fill_buf * weight_mode) + (uint32_t)tables;
-  st.tables_off = 2 * st.stage_bytes + (uint32_t)(fill_buf * weight_mode);
+  st.fill_src_off = st.slots_off + st.n_slots * st.slot_bytes;
+  st.tables_off = st.fill_src_off + (uint32_t)(fill_buf * weight_mode);
+  st.smem_bytes = st.tables_off + (uint32_t)tables + 128;
   st.ok = true;
   return RR_OK;
 }
@@ -756,16 +823,21 @@ int launch_integrate_staged(rr_ctx* c, const IntegrateParams& p, int mode, bool*
   setup_fill(c, p, mode, tunables().stage_fill_rows, sp.f);
   sp.cy = st.cy; sp.cz = st.cz; sp.n_yc = st.n_yc; sp.n_zc = st.n_zc;
   sp.BX = st.BX; sp.BY = st.BY; sp.BZ = st.BZ; sp.T = st.T;
-  sp.fp = st.d_fp; sp.legacy = st.n_legacy ? st.d_legacy : nullptr;
-  sp.cls = st.d_cls;
-  sp.inv_bytes = st.inv_bytes; sp.tile_bytes = st.tile_bytes; sp.stage_bytes = st.stage_bytes;
-  sp.inv_span = st.inv_span; sp.tile_span = st.tile_span;
+  sp.fp = st.d_fp;
+  sp.list = st.d_list; sp.class_count = c->d_counters + c->bricks.num; sp.list_stride = st.list_stride;
+  sp.inv_bytes = st.inv_bytes; sp.tile_bytes = st.tile_bytes; sp.inv_span = st.inv_span;
+  sp.slot_bytes = st.slot_bytes; sp.n_slots = st.n_slots; sp.slots_off = st.slots_off;
   sp.err = st.d_err;
-  sp.fill_src_off = 2 * st.stage_bytes; sp.fill_src_bytes = st.fill_src_bytes;
+  sp.prof = (tunables().stage_debug & 128) ? reinterpret_cast<unsigned long long*>(st.d_err + 4) : nullptr;
+  sp.fill_src_off = st.fill_src_off; sp.fill_src_bytes = st.fill_src_bytes;
   sp.tables_off = st.tables_off; sp.n_rowany = c->bricks.res[1] * c->bricks.res[2];
   if (tunables().stage_debug & 1) sp.f.fill_items = 0;
   sp.debug = tunables().stage_debug;
-  // the work counters were reset and this frame's verdicts written by k_bricks_update (launch_bricks_update)
+  sp.fill_depth = tunables().stage_fill_depth; sp.fill_lsu = tunables().stage_fill_lsu;
+  // The work counters are reset and this frame's item lists written by k_bricks_update; a second integrate of the same
+  // frame set (another slab, a repeated call) finds the lists intact and only needs fresh counters.
+  if (!c->work_fresh) cudaMemsetAsync(c->d_work, 0, 4 * sizeof(uint32_t), c->stream);
+  c->work_fresh = false;
   int rc;
   switch (c->N) {
     case 1: rc = launch_staged_n<1, 22>(c, sp, mode); break;

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "librr_b200.so")
+LIB_PATH = os.environ.get("RR_B200_LIB") or os.path.join(os.path.dirname(_HERE), "librr_b200.so")   # RR_B200_LIB: the profiling build (make prof)
 HEADER_PATH = os.path.join(os.path.dirname(os.path.dirname(_HERE)), "include", "rgbd_recon_b200.h")
 
 STAGES = dict(morph=0, depth=1, lab=2, depth_b=3, sil=4, normal=5, quality=6)
@@ -93,6 +93,7 @@ def lib():
     L.rr_get_stage_ms.argtypes = [vp, C.c_char_p, f32]
     L.rr_get_stage_stats.argtypes = [vp, C.c_char_p, f32, u32]
     L.rr_integrator_info.argtypes = [vp, u32]
+    L.rr_integrator_profile.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.rr_launch_count.argtypes = [vp]
     L.rr_launch_count.restype = C.c_uint64
     L.rr_version.restype = C.c_int
@@ -393,9 +394,17 @@ class Fusion:
         """rr_integrator_info as a dict (which integrator bricks mode runs, staged geometry, device flags)."""
         out = np.zeros(16, np.uint32)
         self._ck(self.L.rr_integrator_info(self.h, _u32(out)))
-        keys = ("staged", "tile", "box_x", "box_y", "box_z", "ychunk", "zchunk", "n_ychunks", "n_zchunks", "legacy_bricks",
-                "smem_bytes", "consumer_warps", "fill_warps", "flags")
+        keys = ("staged", "tile", "box_x", "box_y", "box_z", "ychunk", "zchunk", "n_ychunks", "n_zchunks", "oversize_pairs",
+                "smem_bytes", "consumer_warps", "fill_warps", "flags", "slots", "slot_bytes")
         return {k: int(v) for k, v in zip(keys, out)}
+
+    def integrator_profile(self):
+        """rr_integrator_profile: cycle counters of the staged integrator's roles (stage_debug bit 7), reset on read."""
+        out = np.zeros(16, np.uint64)
+        self._ck(self.L.rr_integrator_profile(self.h, out.ctypes.data_as(C.POINTER(C.c_uint64))))
+        keys = ("consumer_wait", "consumer_work", "consumer_idle_items", "active_sensor_items", "producer_meta", "producer_wait_empty", "producer_copy",
+                "staged_items", "direct_items", "clear_warps", "clear_helpers", "cta_max", "warp_life_sum", "tile_need_max", "need_le30_items", "need_le36_items")
+        return {k: int(v) for k, v in zip(keys, out) if not k.startswith("_")}
 
     def launch_count(self):
         return int(self.L.rr_launch_count(self.h))

@@ -18,7 +18,7 @@ import bench  # noqa: E402
 from rrpy import capi  # noqa: E402
 
 DEFAULTS = dict(fused=1, zchunk=13, fill_rows=16, fill_warps=2, ctas=2, threads=512, chunk=1, ldg256=1,
-                staged=1, stage_zchunk=13, stage_ychunk=0, stage_tile=0, stage_fill_rows=16, stage_debug=0, stage_cwarps=0, stage_bulk_fill=16)
+                staged=1, stage_zchunk=13, stage_ychunk=0, stage_tile=0, stage_fill_rows=16, stage_debug=0, stage_cwarps=0, stage_bulk_fill=4, stage_fill_depth=0, stage_fill_lsu=0)
 
 
 def main():
@@ -47,6 +47,7 @@ def main():
         fu.synchronize()
         fu.set_timing(1)
         fu.stage_stats("2integrate"); fu.stage_stats("1preprocess")
+        fu.integrator_profile()          # reset (counts only with the profiling build: RR_B200_LIB=.../librr_b200_prof.so, stage_debug bit 7)
         for _ in range(40):
             fu.frame()
         fu.synchronize()
@@ -57,9 +58,14 @@ def main():
         if ref_hash is None:
             ref_hash = h
         info = fu.integrator_info()
-        info = {k: info[k] for k in ("staged", "tile", "zchunk", "legacy_bricks", "smem_bytes", "fill_warps", "flags")}
-        print(json.dumps({"config": spec, "integrate_ms": round(ms / n, 5), "integrator": info, "preprocess_ms": round(pms / max(1, pn), 5),
-                          "tsdf_sha1": h, "same_as_first": h == ref_hash}), flush=True)
+        info = {k: info[k] for k in ("staged", "tile", "zchunk", "oversize_pairs", "smem_bytes", "fill_warps", "flags", "slots", "slot_bytes")}
+        rec = {"config": spec, "integrate_ms": round(ms / n, 5), "integrator": info, "preprocess_ms": round(pms / max(1, pn), 5),
+               "tsdf_sha1": h, "same_as_first": h == ref_hash}
+        prof = fu.integrator_profile()
+        if any(prof.values()):
+            # per frame; cycle sums in kilocycles
+            rec["roles_per_frame"] = {k: (v if k.endswith("max") else round(v / 40.0, 1) if k.endswith("items") else round(v / 40.0 / 1e3, 1)) for k, v in prof.items()}
+        print(json.dumps(rec), flush=True)
     fu.close()
 
 
