@@ -889,6 +889,7 @@ int rr_set_tunable(const char* name, int value) {
   else if (n == "stage_debug") t.stage_debug = value;
   else if (n == "stage_fill_depth") t.stage_fill_depth = value;
   else if (n == "stage_fill_lsu") t.stage_fill_lsu = value;
+  else if (n == "stage_tail_cap") t.stage_tail_cap = value;
   else if (n == "stage_cwarps") t.stage_cwarps = value;
   else if (n == "stage_bulk_fill") t.stage_bulk_fill = value;
   else return RR_ERR_INVALID;

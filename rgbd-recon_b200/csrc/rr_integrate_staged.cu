@@ -48,6 +48,7 @@ struct StagedParams {
   uint32_t n_rowany;
   uint32_t* err;            // [0] box overflow, [1] barrier time-out
   int fill_depth, fill_lsu; // tunables stage_fill_depth / stage_fill_lsu (FillSource)
+  int tail_cap;             // tunable stage_tail_cap: items in flight per CTA once the list runs out (0: no limit)
   unsigned long long* prof; // stage_debug bit 7: cycle counters per role (rr_integrator_profile), else nullptr
   int debug;
 };
@@ -303,8 +304,19 @@ k_integrate_staged(const __grid_constant__ StagedParams p, const __grid_constant
       return true;
     };
     RR_PROF(long long tp0 = clock64(); long long tp1 = 0; long long t_meta = 0; long long t_empty = 0; long long n_staged = 0; long long n_direct = 0;)
+    uint32_t total = 0, seen = 0;             // items of this frame, and the last index this producer drew
+#pragma unroll
+    for (int k = 0; k <= N; ++k) total += cnt[k];
     for (;;) {
+      // Items drawn early are items other CTAs cannot take: towards the end of the list the run-ahead shrinks with what is
+      // left per CTA (down to one item at a time), so that the last items spread over all SMs instead of queueing in a few.
+      if (p.tail_cap > 0) {
+        const uint32_t left = total > seen ? (total - seen) / gridDim.x : 0u;
+        const uint32_t cap = min(max(left, (uint32_t)p.tail_cap), (uint32_t)NH);
+        while (j - tail >= cap) if (!retire()) return;
+      }
       const uint32_t it = atomicAdd(p.f.work, 1u);
+      seen = it;
       // the most expensive class first
       int cls = -1;
       uint32_t idx = it;
@@ -834,6 +846,7 @@ int launch_integrate_staged(rr_ctx* c, const IntegrateParams& p, int mode, bool*
   if (tunables().stage_debug & 1) sp.f.fill_items = 0;
   sp.debug = tunables().stage_debug;
   sp.fill_depth = tunables().stage_fill_depth; sp.fill_lsu = tunables().stage_fill_lsu;
+  sp.tail_cap = tunables().stage_tail_cap;
   // The work counters are reset and this frame's item lists written by k_bricks_update; a second integrate of the same
   // frame set (another slab, a repeated call) finds the lists intact and only needs fresh counters.
   if (!c->work_fresh) cudaMemsetAsync(c->d_work, 0, 4 * sizeof(uint32_t), c->stream);
