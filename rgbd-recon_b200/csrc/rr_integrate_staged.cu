@@ -595,9 +595,14 @@ static int launch_staged_n(rr_ctx* c, const StagedParams& sp, int mode) {
   return RR_OK;
 }
 
-// consumer warps per CTA: up to four sensors run 22 warps (a 26 x 26 brick's 676 columns in one pass) at 72 registers,
-// more sensors keep 6 more registers of plane state each and run 11 warps at 144
-static int consumer_warps(int N) { return (N <= 4 && tunables().stage_cwarps != 11) ? 22 : 11; }
+// consumer warps per CTA: up to four sensors run 22 warps (a 26 x 26 brick's 676 columns in one pass) at 72 registers;
+// more sensors keep 6 more registers of plane state each: 16 warps at 96 registers (tunable stage_cwarps = 11: 11 at 144).
+// Measured on 8 sensors / 1024^3 (profiles/r2_g_c5.log): 11 warps 2.50 ms, 16 warps 1.86 ms, 20 warps at 80 registers 2.25 ms
+// (spills), pairs of sensors in flight 2.87 ms (spills).
+static int consumer_warps(int N) {
+  if (tunables().stage_cwarps == 11) return 11;
+  return N <= 4 ? 22 : 16;
+}
 
 static int footprints(rr_ctx* c, const IntegrateParams& p, int cy, int cz, int n_yc, int n_zc, int4* d_out, float2* d_z, uint32_t items) {
   switch (c->N) {
@@ -857,10 +862,10 @@ int launch_integrate_staged(rr_ctx* c, const IntegrateParams& p, int mode, bool*
     case 2: rc = launch_staged_n<2, 22>(c, sp, mode); break;
     case 3: rc = launch_staged_n<3, 22>(c, sp, mode); break;
     case 4: rc = st.cwarps == 11 ? launch_staged_n<4, 11>(c, sp, mode) : launch_staged_n<4, 22>(c, sp, mode); break;
-    case 5: rc = launch_staged_n<5, 11>(c, sp, mode); break;
-    case 6: rc = launch_staged_n<6, 11>(c, sp, mode); break;
-    case 7: rc = launch_staged_n<7, 11>(c, sp, mode); break;
-    case 8: rc = launch_staged_n<8, 11>(c, sp, mode); break;
+    case 5: rc = st.cwarps == 11 ? launch_staged_n<5, 11>(c, sp, mode) : launch_staged_n<5, 16>(c, sp, mode); break;
+    case 6: rc = st.cwarps == 11 ? launch_staged_n<6, 11>(c, sp, mode) : launch_staged_n<6, 16>(c, sp, mode); break;
+    case 7: rc = st.cwarps == 11 ? launch_staged_n<7, 11>(c, sp, mode) : launch_staged_n<7, 16>(c, sp, mode); break;
+    case 8: rc = st.cwarps == 11 ? launch_staged_n<8, 11>(c, sp, mode) : launch_staged_n<8, 16>(c, sp, mode); break;
     default: return fail(c, RR_ERR_UNSUPPORTED, "integrate: 1..8 sensors supported");
   }
   if (rc != RR_OK) return rc;

@@ -48,6 +48,7 @@ def run(name, steps=100, warmup=5):
     fu.synchronize()
     fu.set_timing(1)
     fu.stage_stats("2integrate"); fu.stage_stats("1preprocess")
+    fu.integrator_profile()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(steps):
@@ -58,6 +59,7 @@ def run(name, steps=100, warmup=5):
     im, inn = fu.stage_stats("2integrate")
     pm, pn = fu.stage_stats("1preprocess")
     fu.set_timing(0)
+    prof = fu.integrator_profile()       # counts only with the profiling build (RR_B200_LIB) and stage_debug bit 7
     n_occ, ratio = fu.bricks_update(sync=True)
     info = fu.integrator_info()
     VW, VH = 1280, 720
@@ -78,9 +80,17 @@ def run(name, steps=100, warmup=5):
            "occupied_bricks": int(n_occ), "occupied_ratio": round(float(ratio), 4), "integrator": info,
            "view_ms": round(v0.elapsed_time(v1) / 20, 4), "view": "raymarch 1280x720 (shaded, brick space skipping) + colour hole filling",
            "steps": steps, "warmup": warmup, "data": "synthetic (same generators as bench.py)"}
+    if os.environ.get("RR_TUNE"):
+        out["tunables"] = os.environ["RR_TUNE"]
+    if any(prof.values()):
+        out["roles_per_frame"] = {k: (v if k.endswith("max") else round(v / steps, 1) if k.endswith("items") else round(v / steps / 1e3, 1)) for k, v in prof.items()}
     print(json.dumps(out), flush=True)
 
 
 if __name__ == "__main__":
+    # RR_TUNE="stage_debug=128,stage_tile=36": integrator tunables for A/B runs
+    for kv in filter(None, os.environ.get("RR_TUNE", "").split(",")):
+        k, v = kv.split("=")
+        capi.set_tunable(k, int(v))
     for n in (sys.argv[1:] or ["c2", "c3", "c5"]):
         run(n)
