@@ -8,7 +8,10 @@
  *
  * Conventions: every call returns 0 on success or a negative rr_status; rr_last_error(ctx) gives the text.
  * A context is single-caller (the reference issues everything from its one GL thread) and owns one CUDA stream
- * on one device. Host pointers passed in stay owned by the caller. Arrays are C-contiguous:
+ * on one device. The one exception mirrors the reference's reader thread (NetKinectArray::readLoop): rr_stage_frames and
+ * rr_stage_sync may be called from a second thread while the first one runs the per-frame calls, provided the two threads
+ * order rr_stage_frames against rr_swap_frames themselves (the reference's m_mutex_pbo); rr_last_error returns a per-thread
+ * copy of the text. Host pointers passed in stay owned by the caller. Arrays are C-contiguous:
  *   depth  float32 [N][H][W]        metres, 0 = no return       (NetKinectArray.cpp:135-142)
  *   colour uint8   [N][CH][CW][3]   RGB8                        (NetKinectArray.cpp:120-131)
  *   cv_xyz float32 [Z][Y][X][3], cv_uv float32 [Z][Y][X][2], cv_xyz_inv float32 [Z][Y][X][4]
@@ -124,12 +127,15 @@ int rr_set_slab(rr_ctx* ctx, uint32_t z0, uint32_t z1);
  *   rr_upload_frames = rr_stage_frames + rr_swap_frames (no overlap; the simple path). */
 int rr_stage_frames(rr_ctx* ctx, const void* color, size_t color_bytes, const void* depth, size_t depth_bytes);
 /* Stream formats of the reference (KinectCalibrationFile compress_rgb / compress_depth; NetKinectArray.cpp:120-142,
- * 149-159,170-175): colour RGB8 [N][CH][CW][3] or DXT1 blocks (CW*CH/2 bytes per sensor, CW and CH multiples of 4);
+ * 149-159,170-175): colour RGB8 [N][CH][CW][3], DXT1 blocks (compress_rgb == 1: CW*CH/2 bytes per sensor) or DXT5 blocks
+ * (compress_rgb == 5, :125-128,153-156: CW*CH bytes per sensor - the reference hard-codes 307200 = 640*480; the alpha half of a
+ * block is not sampled downstream and is skipped); CW and CH multiples of 4 for both block formats;
  * depth float32 metres [N][H][W] or 8-bit sqrt-compressed [N][H][W] with per-sensor (near, far) of the calibration file
  * (near_far float [N][2]; pre_depth.fs uncompress(), :51-61, with scale = far - near). Sets the sizes the upload calls
  * expect; packed frame sets are expanded on the device. Default: RGB8 + float32. */
 #define RR_COLOR_RGB8 0
 #define RR_COLOR_DXT1 1
+#define RR_COLOR_DXT5 5
 #define RR_DEPTH_F32 0
 #define RR_DEPTH_U8 1
 int rr_set_frame_format(rr_ctx* ctx, int color_format, int depth_format, const float* near_far);

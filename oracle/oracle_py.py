@@ -70,6 +70,7 @@ def lib():
                               f32p, f32p, f32p, f32p]
     L.ro_raymarch_rays.argtypes = [f32p, f32p, f32p, f32p, C.c_int, C.c_int, C.c_float, f32p, u8p]
     L.ro_decode_dxt1.argtypes = [u8p, C.c_int, C.c_int, u8p]
+    L.ro_decode_dxt5.argtypes = [u8p, C.c_int, C.c_int, u8p]
     L.ro_depth8_to_float.argtypes = [u8p, C.c_size_t, f32p]
     L.ro_fill_num_lods.argtypes = [C.c_int, C.c_int]
     L.ro_fill_num_lods.restype = C.c_int
@@ -136,6 +137,13 @@ def calib_invert(cv_xyz_one, bbox_min, bbox_max, out_res, want_neighbours=False,
 
 
 # ---------------------------------------------------------------------------------------------- frame
+
+def decode_dxt5(blocks, W, H):
+    """DXT5 block bytes (16 per 4x4 block) -> uint8 [H][W][3]; the alpha half of a block is not sampled downstream."""
+    out = np.zeros((H, W, 3), np.uint8)
+    lib().ro_decode_dxt5(np.ascontiguousarray(blocks, np.uint8), W, H, out)
+    return out
+
 
 def decode_dxt1(blocks, W, H):
     """DXT1 block bytes -> uint8 [H][W][3] (what the GL sampler returns as .rgb * 255)."""

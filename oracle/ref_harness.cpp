@@ -43,6 +43,14 @@ void ref_squish_decompress_dxt1(const unsigned char* blocks, int w, int h, unsig
   squish::DecompressImage(rgba, w, h, blocks, squish::kDxt1);
 }
 int ref_squish_storage_dxt1(int w, int h) { return squish::GetStorageRequirements(w, h, squish::kDxt1); }
+// the same for DXT5 streams (compress_rgb == 5, NetKinectArray.cpp:125-128)
+void ref_squish_compress_dxt5(const unsigned char* rgba, int w, int h, unsigned char* blocks) {
+  squish::CompressImage(rgba, w, h, blocks, squish::kDxt5 | squish::kColourRangeFit);
+}
+void ref_squish_decompress_dxt5(const unsigned char* blocks, int w, int h, unsigned char* rgba) {
+  squish::DecompressImage(rgba, w, h, blocks, squish::kDxt5);
+}
+int ref_squish_storage_dxt5(int w, int h) { return squish::GetStorageRequirements(w, h, squish::kDxt5); }
 
 // kinect::Frustum (frustum.cpp): planes float[6][4], camera position float[3]
 void ref_frustum(const float* corners, float* planes_out, float* cam_out) {

@@ -46,6 +46,11 @@ def lib():
         L.ref_squish_decompress_dxt1.argtypes = [u8p, C.c_int, C.c_int, u8p]
         L.ref_squish_storage_dxt1.argtypes = [C.c_int, C.c_int]
         L.ref_squish_storage_dxt1.restype = C.c_int
+        if hasattr(L, "ref_squish_storage_dxt5"):
+            L.ref_squish_compress_dxt5.argtypes = [u8p, C.c_int, C.c_int, u8p]
+            L.ref_squish_decompress_dxt5.argtypes = [u8p, C.c_int, C.c_int, u8p]
+            L.ref_squish_storage_dxt5.argtypes = [C.c_int, C.c_int]
+            L.ref_squish_storage_dxt5.restype = C.c_int
         _LIB = L
     return _LIB
 
@@ -137,6 +142,23 @@ def squish_compress_dxt1(rgb):
     rgba = np.concatenate([rgb, np.full((H, W, 1), 255, np.uint8)], axis=2)
     out = np.zeros(lib().ref_squish_storage_dxt1(W, H), np.uint8)
     lib().ref_squish_compress_dxt1(np.ascontiguousarray(rgba), W, H, out)
+    return out
+
+
+def squish_compress_dxt5(rgb, alpha=None):
+    """external/squish CompressImage (kDxt5 | kColourRangeFit) of uint8 [H][W][3] (+ optional alpha [H][W]) -> block bytes."""
+    H, W, _ = rgb.shape
+    a = np.full((H, W, 1), 255, np.uint8) if alpha is None else np.asarray(alpha, np.uint8).reshape(H, W, 1)
+    rgba = np.concatenate([rgb, a], axis=2)
+    out = np.zeros(lib().ref_squish_storage_dxt5(W, H), np.uint8)
+    lib().ref_squish_compress_dxt5(np.ascontiguousarray(rgba), W, H, out)
+    return out
+
+
+def squish_decompress_dxt5(blocks, W, H):
+    """external/squish DecompressImage (kDxt5) -> uint8 [H][W][4]."""
+    out = np.zeros((H, W, 4), np.uint8)
+    lib().ref_squish_decompress_dxt5(np.ascontiguousarray(blocks, np.uint8), W, H, out)
     return out
 
 

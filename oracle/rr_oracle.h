@@ -66,6 +66,7 @@ void ro_raymarch(const float* tsdf, const uint32_t* res, float limit, int N, con
 
 /* Compressed ingest: DXT1 colour blocks -> uint8 [H][W][3]; 8-bit depth -> byte/255. */
 void ro_decode_dxt1(const uint8_t* blocks, int W, int H, uint8_t* out_rgb);
+void ro_decode_dxt5(const uint8_t* blocks, int W, int H, uint8_t* out_rgb);   /* 16-byte blocks: alpha (skipped) + colour */
 void ro_depth8_to_float(const uint8_t* in, size_t n, float* out);
 
 /* Colour hole filling after the raymarch (ReconIntegration::fillColors + ViewLod + framebuffer_transfer / tsdf_inpaint /

@@ -10,7 +10,10 @@
 namespace rr {
 
 int fail(rr_ctx* c, int code, const std::string& msg) {
-  if (c) c->error = msg;
+  if (c) {
+    std::lock_guard<std::mutex> lock(c->error_mutex);
+    c->error = msg;
+  }
   return code;
 }
 
@@ -31,6 +34,17 @@ static bool timer_is_top(const char* name) { return name[0] >= '0' && name[0] <=
 void timer_begin(rr_ctx* c, const char* name) {
   if (c->timing == 0 || (c->timing == 1 && !timer_is_top(name))) return;
   StageTimer& t = c->timers[name];
+  if (t.used >= StageTimer::kMaxPending) {
+    // fold the pending intervals (long since complete) into the running sum and reuse their events
+    for (size_t i = 0; i < t.used; ++i) {
+      float ms = 0.0f;
+      if (cudaEventSynchronize(t.end[i]) == cudaSuccess && cudaEventElapsedTime(&ms, t.beg[i], t.end[i]) == cudaSuccess) {
+        t.folded_ms += ms; ++t.folded_n; t.last_ms = ms;
+      }
+    }
+    cudaGetLastError();
+    t.used = 0;
+  }
   if (t.used == t.beg.size()) {
     cudaEvent_t b, e;
     cudaEventCreate(&b); cudaEventCreate(&e);
@@ -171,7 +185,16 @@ void rr_destroy(rr_ctx* c) {
   delete c;
 }
 
-const char* rr_last_error(const rr_ctx* c) { return c ? c->error.c_str() : "null context"; }
+const char* rr_last_error(const rr_ctx* c) {
+  if (!c) return "null context";
+  // a copy per calling thread: the text stays valid for the caller while another thread's call fails
+  thread_local std::string text;
+  {
+    std::lock_guard<std::mutex> lock(const_cast<rr_ctx*>(c)->error_mutex);
+    text = c->error;
+  }
+  return text.c_str();
+}
 
 int rr_synchronize(rr_ctx* c) {
   if (!c) return RR_ERR_INVALID;
@@ -275,6 +298,10 @@ int rr_configure(rr_ctx* c, const rr_config* cfg) {
   uint32_t res[3];
   host_volume_res(c->bbox_min, c->bbox_max, cfg->voxel_size, res);
   RR_REQUIRE(c, res[0] && res[1] && res[2], "rr_configure: empty volume");
+  // The kernels index voxels with 32-bit arithmetic (march_column / march_staged offsets, sample_tsdf's z0 * X * Y): a
+  // volume of 2^31 voxels or more (about 1290^3; 8 GB of R32F, which HBM would hold) is refused instead of wrapping.
+  if ((unsigned long long)res[0] * res[1] * res[2] >= (1ull << 31))
+    return fail(c, RR_ERR_UNSUPPORTED, "rr_configure: volumes of 2^31 voxels or more are not supported (32-bit voxel indices)");
   const float bs = host_adjust_brick_size(cfg->voxel_size, cfg->brick_size);
   RR_REQUIRE(c, bs > 0.0f, "rr_configure: brick size rounds to zero voxels");
   const bool new_volume = !c->configured || res[0] != c->res[0] || res[1] != c->res[1] || res[2] != c->res[2] ||
@@ -368,7 +395,9 @@ int rr_set_slab(rr_ctx* c, uint32_t z0, uint32_t z1) {
 }
 
 static size_t color_bytes_of(const rr_ctx* c) {
-  return c->color_format == RR_COLOR_DXT1 ? (size_t)c->N * c->CW * c->CH / 2 : (size_t)c->N * c->CW * c->CH * 3;
+  if (c->color_format == RR_COLOR_DXT1) return (size_t)c->N * c->CW * c->CH / 2;       // 8 bytes per 4x4 block
+  if (c->color_format == RR_COLOR_DXT5) return (size_t)c->N * c->CW * c->CH;           // 16 bytes per 4x4 block
+  return (size_t)c->N * c->CW * c->CH * 3;
 }
 static size_t depth_bytes_of(const rr_ctx* c) {
   return (size_t)c->N * c->W * c->H * (c->depth_format == RR_DEPTH_U8 ? 1 : sizeof(float));
@@ -383,9 +412,9 @@ static int check_frame_sizes(rr_ctx* c, const void* color, size_t cb, const void
 int rr_set_frame_format(rr_ctx* c, int color_format, int depth_format, const float* near_far) {
   if (!c) return RR_ERR_INVALID;
   drop_frame_graphs(c);
-  RR_REQUIRE(c, color_format == RR_COLOR_RGB8 || color_format == RR_COLOR_DXT1, "rr_set_frame_format: unknown colour format (DXT5 streams are not supported)");
+  RR_REQUIRE(c, color_format == RR_COLOR_RGB8 || color_format == RR_COLOR_DXT1 || color_format == RR_COLOR_DXT5, "rr_set_frame_format: unknown colour format");
   RR_REQUIRE(c, depth_format == RR_DEPTH_F32 || depth_format == RR_DEPTH_U8, "rr_set_frame_format: unknown depth format");
-  RR_REQUIRE(c, color_format != RR_COLOR_DXT1 || ((c->CW % 4) == 0 && (c->CH % 4) == 0), "rr_set_frame_format: DXT1 needs colour width and height that are multiples of 4");
+  RR_REQUIRE(c, color_format == RR_COLOR_RGB8 || ((c->CW % 4) == 0 && (c->CH % 4) == 0), "rr_set_frame_format: DXT1 / DXT5 need colour width and height that are multiples of 4");
   RR_REQUIRE(c, depth_format != RR_DEPTH_U8 || near_far, "rr_set_frame_format: 8-bit depth needs the per-sensor (near, far) range");
   RR_SET_DEVICE(c);
   RR_TRY(check(c, cudaStreamSynchronize(c->copy_stream), "format sync"));
@@ -393,7 +422,8 @@ int rr_set_frame_format(rr_ctx* c, int color_format, int depth_format, const flo
   c->staged = false;
   c->color_format = color_format; c->depth_format = depth_format;
   for (int b = 0; b < 2; ++b) {
-    if (color_format == RR_COLOR_DXT1 && !c->d_color_packed[b]) RR_TRY(dev_alloc(c, &c->d_color_packed[b], (size_t)c->N * c->CW * c->CH / 2, "packed colour"));
+    // sized for the larger block format (DXT5, 16 bytes per 4x4 block), so a later format switch needs no reallocation
+    if (color_format != RR_COLOR_RGB8 && !c->d_color_packed[b]) RR_TRY(dev_alloc(c, &c->d_color_packed[b], (size_t)c->N * c->CW * c->CH, "packed colour"));
     if (depth_format == RR_DEPTH_U8 && !c->d_depth_packed[b]) RR_TRY(dev_alloc(c, &c->d_depth_packed[b], (size_t)c->N * c->W * c->H, "packed depth"));
   }
   for (int i = 0; i < c->N; ++i) {
@@ -411,7 +441,7 @@ int rr_stage_frames(rr_ctx* c, const void* color, size_t cb, const void* depth, 
   // the slot may still be read by kernels launched while it was current
   if (c->free_recorded[t]) RR_TRY(check(c, cudaStreamWaitEvent(c->copy_stream, c->ev_free[t], 0), "stage wait"));
   void* dd = c->depth_format == RR_DEPTH_U8 ? (void*)c->d_depth_packed[t] : (void*)c->d_depth_slot[t];
-  void* dc = c->color_format == RR_COLOR_DXT1 ? (void*)c->d_color_packed[t] : (void*)c->d_color_slot[t];
+  void* dc = c->color_format != RR_COLOR_RGB8 ? (void*)c->d_color_packed[t] : (void*)c->d_color_slot[t];
   RR_TRY(check(c, cudaMemcpyAsync(dd, depth, db, cudaMemcpyHostToDevice, c->copy_stream), "depth upload"));
   if (color) RR_TRY(check(c, cudaMemcpyAsync(dc, color, cb, cudaMemcpyHostToDevice, c->copy_stream), "colour upload"));
   c->staged_color = color != nullptr;
@@ -460,7 +490,7 @@ int rr_upload_frames_device(rr_ctx* c, const void* color, size_t cb, const void*
   // current slot, on the compute stream
   const int t = c->cur_slot;
   void* dd = c->depth_format == RR_DEPTH_U8 ? (void*)c->d_depth_packed[t] : (void*)c->d_depth_slot[t];
-  void* dc = c->color_format == RR_COLOR_DXT1 ? (void*)c->d_color_packed[t] : (void*)c->d_color_slot[t];
+  void* dc = c->color_format != RR_COLOR_RGB8 ? (void*)c->d_color_packed[t] : (void*)c->d_color_slot[t];
   RR_TRY(check(c, cudaMemcpyAsync(dd, depth, db, cudaMemcpyDeviceToDevice, c->stream), "depth upload"));
   if (color) RR_TRY(check(c, cudaMemcpyAsync(dc, color, cb, cudaMemcpyDeviceToDevice, c->stream), "colour upload"));
   const int keep_color = c->color_format;
@@ -810,7 +840,8 @@ int rr_set_timing(rr_ctx* c, int level) {
 int rr_get_stage_ms(rr_ctx* c, const char* name, float* ms) {
   if (!c || !name || !ms) return RR_ERR_INVALID;
   auto it = c->timers.find(name);
-  RR_REQUIRE(c, it != c->timers.end() && it->second.used > 0, "rr_get_stage_ms: stage has not run with timing enabled");
+  RR_REQUIRE(c, it != c->timers.end() && (it->second.used > 0 || it->second.folded_n > 0), "rr_get_stage_ms: stage has not run with timing enabled");
+  if (it->second.used == 0) { *ms = it->second.last_ms; return RR_OK; }
   RR_SET_DEVICE(c);
   const size_t i = it->second.used - 1;
   RR_TRY(check(c, cudaEventSynchronize(it->second.end[i]), "stage timer sync"));
@@ -830,8 +861,9 @@ int rr_get_stage_stats(rr_ctx* c, const char* name, float* total_ms, uint32_t* c
     RR_TRY(check(c, cudaEventElapsedTime(&ms, t.beg[i], t.end[i]), "stage timer"));
     *total_ms += ms;
   }
-  *count = (uint32_t)t.used;
-  t.used = 0;
+  *total_ms += (float)t.folded_ms;
+  *count = (uint32_t)t.used + t.folded_n;
+  t.used = 0; t.folded_ms = 0.0; t.folded_n = 0;
   return RR_OK;
 }
 

@@ -22,6 +22,7 @@
 #include <stdint.h>
 
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -49,8 +50,14 @@ struct BrickGrid {
 
 struct StageTimer {            // one CUDA-event pair per recorded interval; summed and recycled by rr_get_stage_stats
   std::vector<cudaEvent_t> beg, end;
-  size_t used = 0;             // intervals recorded since the last reset
+  size_t used = 0;             // intervals recorded since the last reset / fold
   bool open = false;
+  // O(1) state for callers that only ever ask for the mean at exit (TimerDatabase::mean): once kMaxPending intervals are
+  // pending they are folded into a running sum, so the event vectors stop growing
+  static constexpr size_t kMaxPending = 256;
+  double folded_ms = 0.0;
+  uint32_t folded_n = 0;
+  float last_ms = 0.0f;        // the newest folded interval (rr_get_stage_ms right after a fold)
 };
 
 }  // namespace rr
@@ -59,7 +66,8 @@ struct rr_ctx {
   int device = 0;
   int N = 0, W = 0, H = 0, CW = 0, CH = 0;
   cudaStream_t stream = nullptr;
-  std::string error;
+  std::string error;           // text of the last failing call; written under error_mutex (a reader thread may stage frames)
+  std::mutex error_mutex;
   uint64_t launches = 0;
   int timing = 0;              // 0 off, 1 top-level stages, 2 every pass
   std::map<std::string, rr::StageTimer> timers;

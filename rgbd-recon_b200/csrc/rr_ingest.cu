@@ -9,12 +9,15 @@ namespace rr {
 // S3TC DXT1 (BC1) block -> 4x4 RGB8 texels; same integer arithmetic as the reference's CPU codec external/squish
 // (colourblock.cpp:160-214): 565 endpoints expanded by bit replication, (2a+b)/3 and (a+2b)/3 in four-colour mode,
 // (a+b)/2 and black in three-colour mode (endpoint0 <= endpoint1). Alpha is not sampled downstream.
-__global__ void __launch_bounds__(256) k_decode_dxt1(const uint2* __restrict__ blocks, uint8_t* __restrict__ rgb, int W, int H) {
+// DXT5 (BC3, GL_COMPRESSED_RGBA_S3TC_DXT5_EXT, NetKinectArray.cpp:125-128,153-156): 16-byte blocks, the colour block sits
+// behind 8 bytes of alpha and is always in four-colour mode (squish DecompressColour with isDxt1 = false).
+template <bool DXT5>
+__global__ void __launch_bounds__(256) k_decode_dxt(const uint2* __restrict__ blocks, uint8_t* __restrict__ rgb, int W, int H) {
   const int bw = W >> 2, bh = H >> 2;
   const int bx = blockIdx.x * 32 + threadIdx.x, by = blockIdx.y * 8 + threadIdx.y;
   if (bx >= bw || by >= bh) return;
   const size_t layer = blockIdx.z;
-  const uint2 blk = __ldg(blocks + (layer * bh + by) * bw + bx);
+  const uint2 blk = __ldg(blocks + ((layer * bh + by) * bw + bx) * (DXT5 ? 2 : 1) + (DXT5 ? 1 : 0));
   const int a = (int)(blk.x & 0xffffu), b = (int)(blk.x >> 16);
   int code[4][3];
   code[0][0] = ((a >> 11) << 3) | (a >> 13);            code[1][0] = ((b >> 11) << 3) | (b >> 13);
@@ -23,7 +26,7 @@ __global__ void __launch_bounds__(256) k_decode_dxt1(const uint2* __restrict__ b
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     const int c = code[0][i], d = code[1][i];
-    if (a <= b) { code[2][i] = (c + d) / 2; code[3][i] = 0; }
+    if (!DXT5 && a <= b) { code[2][i] = (c + d) / 2; code[3][i] = 0; }
     else { code[2][i] = (2 * c + d) / 3; code[3][i] = (c + 2 * d) / 3; }
   }
   uint8_t* img = rgb + layer * (size_t)W * H * 3;
@@ -53,10 +56,12 @@ __global__ void __launch_bounds__(256) k_depth8(const uint8_t* __restrict__ in, 
 
 // expand the packed layers of frame slot `slot` into its RGB8 / float32 buffers, on the compute stream
 int launch_unpack_frames(rr_ctx* c, int slot) {
-  if (c->color_format == RR_COLOR_DXT1) {
+  if (c->color_format == RR_COLOR_DXT1 || c->color_format == RR_COLOR_DXT5) {
     const dim3 blk(32, 8, 1), grd((c->CW / 4 + 31) / 32, (c->CH / 4 + 7) / 8, c->N);
-    k_decode_dxt1<<<grd, blk, 0, c->stream>>>(reinterpret_cast<const uint2*>(c->d_color_packed[slot]), c->d_color_slot[slot], c->CW, c->CH);
-    RR_LAUNCH_CHECK(c, "k_decode_dxt1");
+    const uint2* src = reinterpret_cast<const uint2*>(c->d_color_packed[slot]);
+    if (c->color_format == RR_COLOR_DXT5) k_decode_dxt<true><<<grd, blk, 0, c->stream>>>(src, c->d_color_slot[slot], c->CW, c->CH);
+    else k_decode_dxt<false><<<grd, blk, 0, c->stream>>>(src, c->d_color_slot[slot], c->CW, c->CH);
+    RR_LAUNCH_CHECK(c, "k_decode_dxt");
   }
   if (c->depth_format == RR_DEPTH_U8) {
     const size_t n = (size_t)c->N * c->W * c->H;

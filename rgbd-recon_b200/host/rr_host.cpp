@@ -162,6 +162,13 @@ CalibrationFiles::CalibrationFiles(std::vector<std::string> const& calib_filenam
     throw std::invalid_argument("calibration file " + calib_filenames[0] + " lacks rgb_size: / depth_size:");
   m_compressed_rgb = first.isCompressedRGB(); m_compressed_d = first.isCompressedDepth();
   m_near = first.getNear(); m_far = first.getFar(); m_min_length = first.min_length;
+  // every sensor's own depth range (the reference keeps a KinectCalibrationFile per sensor, calibration_files.cpp:12-20)
+  m_near_far.assign(1, std::make_pair(m_near, m_far));
+  for (std::size_t i = 1; i < calib_filenames.size(); ++i) {
+    KinectCalibrationFile f(calib_filenames[i]);
+    if (!f.parse()) throw std::invalid_argument("cannot open calibration file " + calib_filenames[i]);
+    m_near_far.push_back(std::make_pair(f.getNear(), f.getFar()));
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------- NetKinectArray
@@ -191,14 +198,17 @@ void NetKinectArray::pushMessage(void const* data, std::size_t bytes) {
 NetKinectArray::NetKinectArray(std::string const& serverport, std::string const& slaveport, CalibrationFiles const* calibs, CalibVolumes const* vols, bool readfromfile)
     : m_resolution_color(calibs->getWidthC(), calibs->getHeightC()), m_resolution_depth(calibs->getWidth(), calibs->getHeight()),
       m_numLayers(calibs->num()), m_serverport(serverport), m_slaveport(slaveport), m_calib_files(calibs), m_calib_vols(vols) {
-  if (calibs->isCompressedRGB() > 1) throw std::runtime_error("DXT5 colour streams are not supported (DXT1 and RGB8 are)");
-  // NetKinectArray.cpp:120-142: DXT1 = w*h/2 bytes, RGB8 = w*h*3; depth 1 byte (sqrt-compressed) or a float per texel
-  m_colorsize = calibs->isCompressedRGB() == 1 ? (std::size_t)m_resolution_color.x * m_resolution_color.y / 2
-                                               : (std::size_t)m_resolution_color.x * m_resolution_color.y * 3;
+  // NetKinectArray.cpp:120-142: DXT1 = w*h/2 bytes, DXT5 = w*h (the reference's 307200 at 640x480), RGB8 = w*h*3;
+  // depth 1 byte (sqrt-compressed) or a float per texel
+  const unsigned crgb = calibs->isCompressedRGB();
+  if (crgb != 0 && crgb != 1 && crgb != 5) throw std::runtime_error("compress_rgb must be 0 (RGB8), 1 (DXT1) or 5 (DXT5)");
+  const std::size_t cpx = (std::size_t)m_resolution_color.x * m_resolution_color.y;
+  m_colorsize = crgb == 1 ? cpx / 2 : (crgb == 5 ? cpx : cpx * 3);
   m_depthsize = (std::size_t)m_resolution_depth.x * m_resolution_depth.y * (calibs->isCompressedDepth() ? 1 : sizeof(float));
   std::vector<float> near_far;
-  for (unsigned i = 0; i < m_numLayers; ++i) { near_far.push_back(calibs->getNear()); near_far.push_back(calibs->getFar()); }
-  ck(rr_set_frame_format(ctx(), calibs->isCompressedRGB() == 1 ? RR_COLOR_DXT1 : RR_COLOR_RGB8,
+  // per sensor, as the reference reads them (getCalibs()[i].getNear() / getFar(), NetKinectArray.cpp:345-351)
+  for (unsigned i = 0; i < m_numLayers; ++i) { near_far.push_back(calibs->getNear(i)); near_far.push_back(calibs->getFar(i)); }
+  ck(rr_set_frame_format(ctx(), crgb == 1 ? RR_COLOR_DXT1 : (crgb == 5 ? RR_COLOR_DXT5 : RR_COLOR_RGB8),
                          calibs->isCompressedDepth() ? RR_DEPTH_U8 : RR_DEPTH_F32, near_far.data()), "rr_set_frame_format");
   for (int b = 0; b < 2; ++b)
     if (cudaMallocHost((void**)&m_staging[b], (m_colorsize + m_depthsize) * m_numLayers) != cudaSuccess) throw std::runtime_error("pinned staging allocation failed");

@@ -13,6 +13,7 @@
 #define RR_HOST_HPP
 
 #include <array>
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <map>
@@ -21,6 +22,7 @@
 #include <stdexcept>
 #include <string>
 #include <thread>
+#include <utility>
 #include <vector>
 
 #include "../../include/rgbd_recon_b200.h"
@@ -121,15 +123,19 @@ class CalibrationFiles {
   unsigned isCompressedRGB() const { return m_compressed_rgb; }
   bool isCompressedDepth() const { return m_compressed_d; }
   float minLength() const { return m_min_length; }
-  // KinectCalibrationFile::getNear / getFar (the range of the 8-bit depth stream), the same for every sensor here
-  void setDepthRange(float near_, float far_) { m_near = near_; m_far = far_; }
+  // KinectCalibrationFile::getNear / getFar (the range of the 8-bit depth stream), per sensor as in the reference
+  // (getCalibs()[i].getNear()); setDepthRange sets one range for every sensor (synthetic scenes)
+  void setDepthRange(float near_, float far_) { m_near = near_; m_far = far_; m_near_far.clear(); }
   float getNear() const { return m_near; }
   float getFar() const { return m_far; }
+  float getNear(unsigned i) const { return i < m_near_far.size() ? m_near_far[i].first : m_near; }
+  float getFar(unsigned i) const { return i < m_near_far.size() ? m_near_far[i].second : m_far; }
   std::vector<std::string> const& getFileNames() const { return m_filenames; }
  private:
   unsigned m_width, m_widthc, m_height, m_heightc, m_compressed_rgb;
   bool m_compressed_d;
   float m_near = 0.5f, m_far = 4.5f, m_min_length = 0.0125f;
+  std::vector<std::pair<float, float>> m_near_far;       // (near, far) of every sensor's .yml; empty: m_near / m_far for all
   std::vector<std::string> m_filenames;
 };
 
@@ -235,10 +241,10 @@ class NetKinectArray {
   std::size_t m_colorsize, m_depthsize;            // per sensor
   uint8_t* m_staging[2] = {nullptr, nullptr};      // pinned, [colour N | depth N]
   int m_back = 0;
-  bool m_dirty = false;
+  std::atomic<bool> m_dirty{false};            // written by the reader thread, read by update()
   std::mutex m_mutex_pbo;
   std::unique_ptr<std::thread> m_readThread;
-  bool m_running = false;
+  std::atomic<bool> m_running{false};
   bool m_filter_textures = true, m_refine_bound = true, m_use_processed_depth = true;
   std::string m_serverport, m_slaveport;
   std::size_t m_num_frame = 0;

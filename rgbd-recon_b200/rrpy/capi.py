@@ -210,11 +210,11 @@ class Fusion:
     def set_slab(self, z0, z1):
         self._ck(self.L.rr_set_slab(self.h, int(z0), int(z1)))
 
-    def set_frame_format(self, dxt1_color=False, depth8=False, near_far=None):
-        """Stream formats (rr_set_frame_format): DXT1 colour blocks and / or 8-bit sqrt-compressed depth."""
+    def set_frame_format(self, dxt1_color=False, depth8=False, near_far=None, dxt5_color=False):
+        """Stream formats (rr_set_frame_format): DXT1 / DXT5 colour blocks and / or 8-bit sqrt-compressed depth."""
         nf = np.ascontiguousarray(near_far, np.float32) if near_far is not None else None
         self._depth8 = bool(depth8)
-        self._ck(self.L.rr_set_frame_format(self.h, 1 if dxt1_color else 0, 1 if depth8 else 0, _f32(nf) if nf is not None else None))
+        self._ck(self.L.rr_set_frame_format(self.h, 5 if dxt5_color else (1 if dxt1_color else 0), 1 if depth8 else 0, _f32(nf) if nf is not None else None))
 
     # per frame
     def upload_frames(self, color, depth):

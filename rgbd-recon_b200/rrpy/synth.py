@@ -259,6 +259,15 @@ def encode_depth8(depth_m, near, far):
     return b.astype(np.uint8)
 
 
+def encode_dxt5(rgb, seed=0):
+    """DXT5 (BC3) stream blocks: 8 alpha bytes (arbitrary here: the path never samples alpha) + the colour block of
+    encode_dxt1. In a BC3 block the colour half is always read in four-colour mode, whatever the endpoint order.
+    uint8 [H][W][3] -> block bytes (16 per 4x4 block)."""
+    c = encode_dxt1(rgb).reshape(-1, 8)
+    a = np.random.default_rng(seed).integers(0, 256, size=c.shape, dtype=np.uint8)
+    return np.concatenate([a, c], axis=1).reshape(-1)
+
+
 def encode_dxt1(rgb):
     """Minimal DXT1 (BC1) encoder for synthetic streams: per 4x4 block the endpoints are the corners of the colour
     bounding box in 5:6:5, four-colour mode, nearest palette entry per texel. uint8 [H][W][3] -> block bytes."""

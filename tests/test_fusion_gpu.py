@@ -244,3 +244,16 @@ def test_fuse_frame_graph_replay(small_scene):
         capi.set_tunable("zchunk", 13)
         fu.close()
 
+
+
+def test_configure_refuses_volumes_beyond_32_bit_voxel_indices(small_scene):
+    """rr_configure: 2^31 voxels or more would wrap the kernels' 32-bit voxel offsets (the allocation itself would fit HBM),
+    so the configuration is refused with RR_ERR_UNSUPPORTED before anything is allocated."""
+    from rrpy import capi
+    sc = small_scene[0] if isinstance(small_scene, tuple) else small_scene
+    fu = capi.Fusion(sc.N, sc.W, sc.H, sc.CW, sc.CH)
+    fu.set_bbox(sc.bbox_min, sc.bbox_max)
+    ext = float(np.max(np.asarray(sc.bbox_max) - np.asarray(sc.bbox_min)))
+    with pytest.raises(capi.RRError, match="2\\^31"):
+        fu.configure(limit=0.01, voxel_size=ext / 1400.0, brick_size=0.1, min_voxels=10, use_bricks=True)
+    fu.close()

@@ -20,6 +20,40 @@ def packed_scene():
     return sc, dxt, d8
 
 
+def test_dxt5_ingest_matches_oracle(packed_scene):
+    """compress_rgb == 5 (NetKinectArray.cpp:125-128,153-156): 16-byte blocks whose colour half is decoded in four-colour mode
+    whatever the endpoint order (the swapped copy below decodes differently as DXT1); the alpha half is skipped."""
+    import oracle_py as O
+    from rrpy import capi, synth
+    sc, _, _ = packed_scene
+    inv = synth.analytic_inverse(sc, (40, 44, 40))
+    blocks = []
+    for i in range(sc.N):
+        b = synth.encode_dxt5(sc.color[i], seed=i).reshape(-1, 16).copy()
+        b[::3, 8:12] = b[::3, [10, 11, 8, 9]]           # every third block: endpoints swapped (c0 <= c1), indices kept
+        blocks.append(b.reshape(-1))
+    dxt5 = np.stack(blocks)
+    fu = capi.Fusion(sc.N, sc.W, sc.H, sc.CW, sc.CH)
+    capi.load_scene(fu, sc, inv)
+    fu.configure(limit=0.01, voxel_size=0.025, brick_size=0.1, min_voxels=10, use_bricks=True)
+    fu.set_frame_format(dxt5_color=True)
+    with pytest.raises(capi.RRError):
+        fu.upload_frames(dxt5[:, : dxt5.shape[1] // 2], sc.depth)      # DXT1-sized colour while DXT5 is expected
+    fu.upload_frames(dxt5, sc.depth)
+    fu.frame(sync_bricks=True)
+    got_lab, got_tsdf = fu.download_stage("lab"), fu.download_tsdf()
+    fu.close()
+    color = np.stack([O.decode_dxt5(dxt5[i], sc.CW, sc.CH) for i in range(sc.N)])
+    assert not np.array_equal(color[0], O.decode_dxt1(dxt5[0].reshape(-1, 16)[:, 8:].reshape(-1), sc.CW, sc.CH))
+    osc = dataclasses.replace(sc, color=color)
+    grid = O.brick_grid(sc.bbox_min, sc.bbox_max, 0.025, 0.1)
+    cams = [O.frustum(sc.cv_xyz[i])[1] for i in range(sc.N)]
+    pre = O.preprocess(osc, grid, cams, True, True, True)
+    want = O.integrate(inv, pre, grid, 0.01, True, O.occupied_bricks(pre["bricks"], 10))
+    assert bits_equal(got_lab, pre["lab"]).all(), mismatch_report("lab", got_lab, pre["lab"])
+    assert bits_equal(got_tsdf, want).all(), mismatch_report("tsdf", got_tsdf, want)
+
+
 @pytest.mark.parametrize("dxt1,depth8", [(True, False), (False, True), (True, True)])
 def test_compressed_ingest_matches_oracle(packed_scene, dxt1, depth8):
     import oracle_py as O

@@ -724,6 +724,19 @@ def test_colorfill_oracle_properties(O):
     assert np.isin(out2[hit].reshape(-1, 4).view(np.uint32), clean.view(np.uint32)).all()
 
 
+def test_dxt5_decoder_against_reference_squish(O):
+    """DXT5 colour ingest (compress_rgb == 5): the oracle's decoder against blocks compressed AND decoded by the reference's
+    own codec external/squish (tests/golden/ref_dxt5.npz), including arbitrary block bytes (both endpoint orders: a BC3
+    colour block stays in four-colour mode)."""
+    g = gold("ref_dxt5.npz")
+    H, W = g["image"].shape[:2]
+    assert np.array_equal(O.decode_dxt5(g["blocks"], W, H), g["decoded"][..., :3])
+    assert np.array_equal(O.decode_dxt5(g["random_blocks"], W, H), g["random_decoded"][..., :3])
+    import ref_py as R
+    if R.available() and hasattr(R.lib(), "ref_squish_storage_dxt5"):
+        assert np.array_equal(R.squish_decompress_dxt5(g["blocks"], W, H), g["decoded"])
+
+
 def test_dxt1_decoder_against_reference_squish(O):
     """DXT1 colour ingest: the oracle's BC1 decoder against blocks compressed AND decoded by the reference's own codec
     external/squish (tests/golden/ref_dxt1.npz, made by tools/make_golden.py through oracle/_ref), including arbitrary

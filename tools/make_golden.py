@@ -49,6 +49,22 @@ def golden_dxt1():
                         random_decoded=rnd_decoded)
 
 
+def golden_dxt5():
+    """DXT5 colour ingest (compress_rgb == 5): blocks made and decoded by external/squish, plus arbitrary block bytes."""
+    rng = np.random.default_rng(12)
+    H, W = 48, 64
+    yy, xx = np.mgrid[0:H, 0:W]
+    img = np.stack([(xx * 3 + yy) % 256, (yy * 5) % 256, ((xx // 4 + yy // 8) % 2) * 180 + 40], axis=2).astype(np.int32)
+    img = np.clip(img + rng.integers(-12, 13, size=img.shape), 0, 255).astype(np.uint8)
+    alpha = rng.integers(0, 256, size=(H, W), dtype=np.uint8)
+    blocks = R.squish_compress_dxt5(img, alpha)
+    decoded = R.squish_decompress_dxt5(blocks, W, H)
+    rnd = rng.integers(0, 256, size=(W // 4) * (H // 4) * 16, dtype=np.uint8)
+    rnd_decoded = R.squish_decompress_dxt5(rnd, W, H)
+    np.savez_compressed(os.path.join(OUT, "ref_dxt5.npz"), image=img, blocks=blocks, decoded=decoded, random_blocks=rnd,
+                        random_decoded=rnd_decoded)
+
+
 def golden_glsl():
     """The reference's OWN shaders (glsl/pre_*.fs, inc_*.glsl, tsdf_integration.vs) compiled as C++ and run on the CPU
     (oracle/_ref/libref_glsl.so, oracle/glsl_host/): every pre-processing stage and the integrated volume on the golden
@@ -106,12 +122,14 @@ def main():
     assert R.available(), "build oracle/_ref first (make -C oracle all)"
     if "--only-dxt" in sys.argv:
         golden_dxt1()
+        golden_dxt5()
         return
     if "--only-glsl" in sys.argv:
         golden_glsl()
         golden_glsl_raymarch()
         return
     golden_dxt1()
+    golden_dxt5()
     golden_glsl()
     golden_glsl_raymarch()
     sc = golden_scene()
