@@ -196,6 +196,50 @@ int rr_composite(rr_ctx* ctx, const void* d_records, int n_parts, int width, int
 int rr_partial_keys(rr_ctx* ctx, const void* d_records, int rank, void* d_keys);
 int rr_partial_keep_winners(rr_ctx* ctx, void* d_records, const void* d_keys_min, int rank);
 
+/* ---- one process, several GPUs (no reference counterpart - the reference owns one GL context) ---------- */
+/* A group = one rr_ctx per device; the TSDF volume is split into contiguous z-slabs, one per member. Every call below is the
+ * group form of the per-context call of the same name and has the same meaning and error behaviour; setup is replicated,
+ * a frame set goes host -> member 0 (the ingest and display device) -> the other members by peer copies over NVLink on
+ * their copy streams (double-buffered like rr_stage_frames), pre-processing and brick tables are replicated, each member
+ * integrates its slab, and a view is marched per slab and composited by ONE kernel on member 0 that reads the other
+ * members' first-hit keys and the winners' pixels through peer memory. Results equal the single-context ones bit for bit
+ * (tests/test_group_gpu.py). A group of one device is a plain pass-through. Single caller, like a context.
+ * rr_group_last_error gives the text of the last failing group call (naming the member). */
+typedef struct rr_group rr_group;
+int rr_group_create(rr_group** out, const int* devices, int n_devices, int num_sensors, int depth_w, int depth_h, int color_w, int color_h);
+void rr_group_destroy(rr_group* g);
+int rr_group_size(const rr_group* g);
+rr_ctx* rr_group_member(rr_group* g, int i);      /* for per-context queries and read-backs (member 0: brick tables, timers, view) */
+const char* rr_group_last_error(const rr_group* g);
+int rr_group_synchronize(rr_group* g);
+int rr_group_set_bbox(rr_group* g, const float bbox_min[3], const float bbox_max[3]);
+int rr_group_calib_upload(rr_group* g, int sensor, const float* cv_xyz, const float* cv_uv, const uint32_t res[3], const float depth_limits[2]);
+int rr_group_calib_upload_inv(rr_group* g, int sensor, const float* cv_xyz_inv, const uint32_t res[3]);
+int rr_group_set_frame_format(rr_group* g, int color_format, int depth_format, const float* near_far);
+int rr_group_set_timing(rr_group* g, int level);
+/* rr_configure on every member, then equal-thickness slabs (rr_set_slab). */
+int rr_group_configure(rr_group* g, const rr_config* cfg);
+/* Explicit slab boundaries z_bounds[n + 1] (ascending, tiling [0, Z)); rr_group_get_slabs reads them back. */
+int rr_group_set_slabs(rr_group* g, const uint32_t* z_bounds);
+int rr_group_get_slabs(const rr_group* g, uint32_t* z_bounds);
+/* Slabs of equal integrate cost (clear stream + compute_to_fill x voxels of occupied bricks per slice; <= 0: the measured 45)
+ * from the occupied bricks of the last fused frame set. Synchronises; for occasional use. */
+int rr_group_balance_slabs(rr_group* g, float compute_to_fill);
+int rr_group_stage_frames(rr_group* g, const void* color, size_t color_bytes, const void* depth, size_t depth_bytes);
+int rr_group_swap_frames(rr_group* g);
+int rr_group_stage_sync(rr_group* g);
+int rr_group_upload_frames(rr_group* g, const void* color, size_t color_bytes, const void* depth, size_t depth_bytes);
+int rr_group_bricks_clear(rr_group* g);
+int rr_group_preprocess(rr_group* g, int filter_textures, int use_processed_depth, int refine_boundary);
+int rr_group_bricks_update(rr_group* g, uint32_t* out_num_occupied, float* out_ratio);
+int rr_group_integrate(rr_group* g);
+int rr_group_fuse_frame(rr_group* g, int filter_textures, int use_processed_depth, int refine_boundary);
+int rr_group_bricks_count(rr_group* g, uint32_t* out_num_occupied, float* out_ratio);
+int rr_group_raymarch(rr_group* g, const rr_view* view, float* out_rgba, float* out_depth);
+int rr_group_fill_colors(rr_group* g, float* out_rgba);
+/* The whole volume assembled from the slices each member owns: float32 [Z][Y][X] (4-byte voxels of any format). */
+int rr_group_download_tsdf(rr_group* g, float* out);
+
 /* ---- read-back (tests, debug views) ------------------------------------------------------------------------ */
 int rr_download_tsdf(rr_ctx* ctx, float* out);
 int rr_download_weight(rr_ctx* ctx, float* out);

@@ -94,6 +94,38 @@ def lib():
     L.rr_get_stage_stats.argtypes = [vp, C.c_char_p, f32, u32]
     L.rr_integrator_info.argtypes = [vp, u32]
     L.rr_integrator_profile.argtypes = [vp, C.POINTER(C.c_uint64)]
+    # one process, several GPUs
+    L.rr_group_create.argtypes = [C.POINTER(vp), i32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.rr_group_destroy.argtypes = [vp]
+    L.rr_group_destroy.restype = None
+    L.rr_group_size.argtypes = [vp]
+    L.rr_group_member.argtypes = [vp, C.c_int]
+    L.rr_group_member.restype = vp
+    L.rr_group_last_error.argtypes = [vp]
+    L.rr_group_last_error.restype = C.c_char_p
+    L.rr_group_synchronize.argtypes = [vp]
+    L.rr_group_set_bbox.argtypes = [vp, f32, f32]
+    L.rr_group_calib_upload.argtypes = [vp, C.c_int, f32, f32, u32, f32]
+    L.rr_group_calib_upload_inv.argtypes = [vp, C.c_int, f32, u32]
+    L.rr_group_set_frame_format.argtypes = [vp, C.c_int, C.c_int, f32]
+    L.rr_group_set_timing.argtypes = [vp, C.c_int]
+    L.rr_group_configure.argtypes = [vp, C.POINTER(Config)]
+    L.rr_group_set_slabs.argtypes = [vp, u32]
+    L.rr_group_get_slabs.argtypes = [vp, u32]
+    L.rr_group_balance_slabs.argtypes = [vp, C.c_float]
+    L.rr_group_stage_frames.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t]
+    L.rr_group_swap_frames.argtypes = [vp]
+    L.rr_group_stage_sync.argtypes = [vp]
+    L.rr_group_upload_frames.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t]
+    L.rr_group_bricks_clear.argtypes = [vp]
+    L.rr_group_preprocess.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+    L.rr_group_bricks_update.argtypes = [vp, u32, f32]
+    L.rr_group_integrate.argtypes = [vp]
+    L.rr_group_fuse_frame.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+    L.rr_group_bricks_count.argtypes = [vp, u32, f32]
+    L.rr_group_raymarch.argtypes = [vp, C.POINTER(View), f32, f32]
+    L.rr_group_fill_colors.argtypes = [vp, f32]
+    L.rr_group_download_tsdf.argtypes = [vp, f32]
     L.rr_launch_count.argtypes = [vp]
     L.rr_launch_count.restype = C.c_uint64
     L.rr_version.restype = C.c_int
@@ -411,6 +443,148 @@ class Fusion:
 
     def stream(self):
         return self.L.rr_stream(self.h)
+
+
+class Group:
+    """Thin object wrapper of an rr_group: one process, one rr_ctx per device, z-slabs (include/rgbd_recon_b200.h)."""
+
+    def __init__(self, devices, N, W, H, CW, CH):
+        self.L = lib()
+        self.h = C.c_void_p()
+        self.N, self.W, self.H, self.CW, self.CH = N, W, H, CW, CH
+        dev = np.ascontiguousarray(devices, np.int32)
+        rc = self.L.rr_group_create(C.byref(self.h), dev.ctypes.data_as(C.POINTER(C.c_int32)), len(dev), N, W, H, CW, CH)
+        if rc != 0:
+            raise RRError(f"rr_group_create failed with status {rc}")
+        self.n = len(dev)
+
+    def close(self):
+        if self.h:
+            self.L.rr_group_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise RRError(f"status {rc}: {self.L.rr_group_last_error(self.h).decode()}")
+
+    def member(self, i):
+        """The i-th member as a (non-owning) Fusion, for queries and read-backs."""
+        fu = Fusion.__new__(Fusion)
+        fu.L, fu.h = self.L, C.c_void_p(self.L.rr_group_member(self.h, i))
+        fu.N, fu.W, fu.H, fu.CW, fu.CH = self.N, self.W, self.H, self.CW, self.CH
+        fu.close = lambda: None
+        return fu
+
+    def set_bbox(self, bmin, bmax):
+        bmin = np.ascontiguousarray(bmin, np.float32)
+        bmax = np.ascontiguousarray(bmax, np.float32)
+        self._ck(self.L.rr_group_set_bbox(self.h, _f32(bmin), _f32(bmax)))
+
+    def calib_upload(self, sensor, cv_xyz, cv_uv, depth_limits=(0.5, 4.5)):
+        Z, Y, X, _ = cv_xyz.shape
+        xyz = np.ascontiguousarray(cv_xyz, np.float32)
+        uv = np.ascontiguousarray(cv_uv, np.float32)
+        res = np.array([X, Y, Z], np.uint32)
+        dl = np.array(depth_limits, np.float32)
+        self._ck(self.L.rr_group_calib_upload(self.h, sensor, _f32(xyz), _f32(uv), _u32(res), _f32(dl)))
+
+    def calib_upload_inv(self, sensor, inv):
+        Z, Y, X, _ = inv.shape
+        a = np.ascontiguousarray(inv, np.float32)
+        res = np.array([X, Y, Z], np.uint32)
+        self._ck(self.L.rr_group_calib_upload_inv(self.h, sensor, _f32(a), _u32(res)))
+
+    def configure(self, limit=0.01, voxel_size=0.01, brick_size=0.1, min_voxels=10, use_bricks=True, skip_space=True, store_weight=False):
+        cfg = Config(limit, voxel_size, brick_size, min_voxels, int(use_bricks), int(skip_space), int(store_weight))
+        self._ck(self.L.rr_group_configure(self.h, C.byref(cfg)))
+
+    def set_frame_format(self, dxt1_color=False, depth8=False, near_far=None, dxt5_color=False):
+        nf = np.ascontiguousarray(near_far, np.float32) if near_far is not None else None
+        self._ck(self.L.rr_group_set_frame_format(self.h, 5 if dxt5_color else (1 if dxt1_color else 0), 1 if depth8 else 0,
+                                                  _f32(nf) if nf is not None else None))
+
+    def set_slabs(self, bounds):
+        b = np.ascontiguousarray(bounds, np.uint32)
+        assert len(b) == self.n + 1
+        self._ck(self.L.rr_group_set_slabs(self.h, _u32(b)))
+
+    def slabs(self):
+        b = np.zeros(self.n + 1, np.uint32)
+        self._ck(self.L.rr_group_get_slabs(self.h, _u32(b)))
+        return [int(v) for v in b]
+
+    def balance_slabs(self, compute_to_fill=0.0):
+        self._ck(self.L.rr_group_balance_slabs(self.h, float(compute_to_fill)))
+
+    def upload_frames(self, color, depth):
+        color = np.ascontiguousarray(color) if color is not None else None
+        depth = np.ascontiguousarray(depth)
+        self._ck(self.L.rr_group_upload_frames(self.h, color.ctypes.data if color is not None else None, color.nbytes if color is not None else 0,
+                                               depth.ctypes.data, depth.nbytes))
+
+    def stage_frames_ptr(self, color_ptr, color_bytes, depth_ptr, depth_bytes):
+        self._ck(self.L.rr_group_stage_frames(self.h, color_ptr, color_bytes, depth_ptr, depth_bytes))
+
+    def swap_frames(self):
+        self._ck(self.L.rr_group_swap_frames(self.h))
+
+    def stage_sync(self):
+        self._ck(self.L.rr_group_stage_sync(self.h))
+
+    def frame(self, filter_textures=True, use_processed_depth=True, refine=True):
+        """The per-frame sequence call by call (kinect_client.cpp:572-600) on every member; returns (occupied, ratio)."""
+        self._ck(self.L.rr_group_bricks_clear(self.h))
+        self._ck(self.L.rr_group_preprocess(self.h, int(filter_textures), int(use_processed_depth), int(refine)))
+        n, r = C.c_uint32(), C.c_float()
+        self._ck(self.L.rr_group_bricks_update(self.h, C.byref(n), C.byref(r)))
+        self._ck(self.L.rr_group_integrate(self.h))
+        return int(n.value), float(r.value)
+
+    def fuse_frame(self, filter_textures=True, use_processed_depth=True, refine=True):
+        self._ck(self.L.rr_group_fuse_frame(self.h, int(filter_textures), int(use_processed_depth), int(refine)))
+
+    def bricks_count(self):
+        n, r = C.c_uint32(), C.c_float()
+        self._ck(self.L.rr_group_bricks_count(self.h, C.byref(n), C.byref(r)))
+        return int(n.value), float(r.value)
+
+    def raymarch(self, modelview, projection, width, height, shade_mode=0, download=True):
+        v = View()
+        v.modelview[:] = [float(x) for x in np.asarray(modelview, np.float32).reshape(16)]
+        v.projection[:] = [float(x) for x in np.asarray(projection, np.float32).reshape(16)]
+        v.viewport[:] = [0, 0, int(width), int(height)]
+        v.shade_mode = int(shade_mode)
+        self._vw, self._vh = int(width), int(height)
+        if not download:
+            self._ck(self.L.rr_group_raymarch(self.h, C.byref(v), None, None))
+            return None
+        rgba = np.zeros((height, width, 4), np.float32)
+        depth = np.zeros((height, width), np.float32)
+        self._ck(self.L.rr_group_raymarch(self.h, C.byref(v), _f32(rgba), _f32(depth)))
+        return rgba, depth
+
+    def fill_colors(self, download=True):
+        if not download:
+            self._ck(self.L.rr_group_fill_colors(self.h, None))
+            return None
+        out = np.zeros((self._vh, self._vw, 4), np.float32)
+        self._ck(self.L.rr_group_fill_colors(self.h, _f32(out)))
+        return out
+
+    def synchronize(self):
+        self._ck(self.L.rr_group_synchronize(self.h))
+
+    def download_tsdf(self):
+        r = self.member(0).volume_res()
+        out = np.zeros((int(r[2]), int(r[1]), int(r[0])), np.float32)
+        self._ck(self.L.rr_group_download_tsdf(self.h, _f32(out)))
+        return out
 
 
 def load_scene(fu: "Fusion", scene, inv=None):
