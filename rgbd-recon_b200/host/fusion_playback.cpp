@@ -3,6 +3,10 @@
 // raymarches it. Prints the TimerDatabase stage means; optionally dumps the last TSDF volume and image.
 //   fusion_playback <file.ks> (--streams "s0;s1;..." | --messages file) [--depth W H --color CW CH] [--frames K] [--voxel m]
 //                   [--limit l] [--eye x y z | --matrices file] [--view W H] [--shade m] [--dump-tsdf file] [--dump-image file] [--dense]
+//                   [--gpus N | --devices a,b,...]
+// --gpus N / --devices: the volume is split into z-slabs over several devices in this one process (rr_group: frame sets by
+// peer copies from the first device, per-slab integration, the view composited on the first device); after the first frame
+// the slabs are re-cut to equal integrate cost. A device may be named more than once (slabs sharing a GPU).
 // Without --depth/--color the sizes and stream formats (DXT1 colour, 8-bit depth, near/far) come from the sensors' .yml
 // files like in the reference (CalibrationFiles, calibration_files.cpp:7-34). --messages plays a file of back-to-back
 // server messages (the ZMQ payload layout of NetKinectArray::readLoop, :511-538) through NetKinectArray::pushMessage.
@@ -43,6 +47,7 @@ int main(int argc, char** argv) {
   int frames = 10, shade = 1;
   float voxel = 0.01f, limit = 0.01f, eye[3] = {1.6f, 1.5f, 2.2f};
   bool dense = false;
+  std::vector<int> devices(1, 0);
   for (int i = 1; i < argc; ++i) {
     auto next = [&](int k) { return std::atof(argv[i + k]); };
     if (!std::strcmp(argv[i], "--depth")) { W = (unsigned)next(1); H = (unsigned)next(2); i += 2; explicit_sizes = true; }
@@ -58,6 +63,11 @@ int main(int argc, char** argv) {
     else if (!std::strcmp(argv[i], "--dump-tsdf")) dump_tsdf = argv[++i];
     else if (!std::strcmp(argv[i], "--dump-image")) dump_image = argv[++i];
     else if (!std::strcmp(argv[i], "--dense")) dense = true;
+    else if (!std::strcmp(argv[i], "--gpus")) { devices.clear(); for (int d = 0, n = std::atoi(argv[++i]); d < n; ++d) devices.push_back(d); }
+    else if (!std::strcmp(argv[i], "--devices")) {
+      devices.clear();
+      for (char* tok = std::strtok(argv[++i], ","); tok; tok = std::strtok(nullptr, ",")) devices.push_back(std::atoi(tok));
+    }
     else if (!std::strcmp(argv[i], "--matrices")) matrices = argv[++i];     // 32 floats: modelview, projection (column-major)
     else ks = argv[i];
   }
@@ -70,7 +80,9 @@ int main(int argc, char** argv) {
       std::cout << "streams: depth " << calib_files.getWidth() << "x" << calib_files.getHeight() << (calib_files.isCompressedDepth() ? " 8-bit" : " float32")
                 << ", colour " << calib_files.getWidthC() << "x" << calib_files.getHeightC() << (calib_files.isCompressedRGB() == 1 ? " DXT1" : " RGB8")
                 << ", near/far " << calib_files.getNear() << " " << calib_files.getFar() << std::endl;
-    gpu::Context gpu(0, calib_files);                                                  // stands where the GL context stood
+    if (devices.empty()) throw std::runtime_error("--gpus / --devices name no device");
+    gpu::Context gpu(devices, calib_files);                                            // stands where the GL context stood
+    if (devices.size() > 1) std::cout << "z-slabs over " << devices.size() << " devices" << std::endl;
     CalibVolumes cv(sc.calib_filenames, sc.bbox);                                      // :241
     NetKinectArray nka(streams, "", &calib_files, &cv, !streams.empty());              // :242
     std::ifstream msg_file;
@@ -115,6 +127,7 @@ int main(int argc, char** argv) {
       recon.updateOccupiedBricks();
       recon.integrate();
       recon.drawF();
+      if (done == 0 && devices.size() > 1) gpu.balanceSlabs();                        // occupied bricks cluster around the subject
       ++done;
     }
     if (!messages.empty()) std::cout << "last frame time " << nka.getCurrentFrameTime() << std::endl;

@@ -16,14 +16,17 @@ namespace kinect {
 namespace gpu {
 static Context* g_current = nullptr;
 
-Context::Context(int device, CalibrationFiles const& cfs) : m_ctx(nullptr) {
-  const int rc = rr_create(&m_ctx, device, (int)cfs.num(), (int)cfs.getWidth(), (int)cfs.getHeight(), (int)cfs.getWidthC(), (int)cfs.getHeightC());
-  if (rc != RR_OK) throw std::runtime_error("rr_create failed with status " + std::to_string(rc) + " (a CUDA device is required; there is no CPU fallback)");
+Context::Context(int device, CalibrationFiles const& cfs) : Context(std::vector<int>(1, device), cfs) {}
+Context::Context(std::vector<int> const& devices, CalibrationFiles const& cfs) : m_group(nullptr), m_ctx(nullptr) {
+  const int rc = rr_group_create(&m_group, devices.data(), (int)devices.size(), (int)cfs.num(), (int)cfs.getWidth(), (int)cfs.getHeight(),
+                                 (int)cfs.getWidthC(), (int)cfs.getHeightC());
+  if (rc != RR_OK) throw std::runtime_error("rr_group_create failed with status " + std::to_string(rc) + " (CUDA devices are required; there is no CPU fallback)");
+  m_ctx = rr_group_member(m_group, 0);
   g_current = this;
 }
 Context::~Context() {
   if (g_current == this) g_current = nullptr;
-  rr_destroy(m_ctx);
+  rr_group_destroy(m_group);
 }
 Context& Context::current() {
   if (!g_current) throw std::runtime_error("no kinect::gpu::Context: create one before CalibVolumes / NetKinectArray / ReconIntegration");
@@ -32,10 +35,17 @@ Context& Context::current() {
 void Context::check(int status, char const* what) const {
   if (status != RR_OK) throw std::runtime_error(std::string(what) + ": " + rr_last_error(m_ctx));
 }
+void Context::checkGroup(int status, char const* what) const {
+  if (status != RR_OK) throw std::runtime_error(std::string(what) + ": " + rr_group_last_error(m_group));
+}
 }  // namespace gpu
 
+// member 0 of the device group: queries, read-backs, timers (brick tables and calibration are identical on every member)
 static rr_ctx* ctx() { return gpu::Context::current().handle(); }
 static void ck(int status, char const* what) { gpu::Context::current().check(status, what); }
+// everything that changes state goes to the whole group (one device: a pass-through)
+static rr_group* grp() { return gpu::Context::current().group(); }
+static void gk(int status, char const* what) { gpu::Context::current().checkGroup(status, what); }
 
 // basefile = calib_file minus its 3-character extension (CalibVolumes.cpp:34-39, calibration_inverter.cpp:17-21)
 static std::string strip_ext3(std::string const& f) {
@@ -52,7 +62,7 @@ CalibVolumes::CalibVolumes(std::vector<std::string> const& calib_volume_files, g
   }
   const float mn[3] = {bbox.getPMin()[0], bbox.getPMin()[1], bbox.getPMin()[2]};
   const float mx[3] = {bbox.getPMax()[0], bbox.getPMax()[1], bbox.getPMax()[2]};
-  ck(rr_set_bbox(ctx(), mn, mx), "rr_set_bbox");
+  gk(rr_group_set_bbox(grp(), mn, mx), "rr_set_bbox");
   m_res.resize(num()); m_limits.resize(num()); m_frustums.resize(num());
   for (unsigned i = 0; i < num(); ++i) addVolume(i, m_cv_xyz_filenames[i], m_cv_uv_filenames[i]);
 }
@@ -63,7 +73,7 @@ void CalibVolumes::addVolume(unsigned i, std::string const& filename_xyz, std::s
   if (vx.res() != vu.res()) throw std::runtime_error("cv_xyz / cv_uv resolutions differ: " + filename_xyz);
   const uint32_t res[3] = {vx.res().x, vx.res().y, vx.res().z};
   const float lim[2] = {vx.depthLimits().x, vx.depthLimits().y};
-  ck(rr_calib_upload(ctx(), (int)i, reinterpret_cast<float const*>(vx.volume().data()), reinterpret_cast<float const*>(vu.volume().data()), res, lim), "rr_calib_upload");
+  gk(rr_group_calib_upload(grp(), (int)i, reinterpret_cast<float const*>(vx.volume().data()), reinterpret_cast<float const*>(vu.volume().data()), res, lim), "rr_calib_upload");
   m_res[i] = vx.res();
   m_limits[i] = vx.depthLimits();
   float planes[24], cams[RR_HOST_MAX_SENSORS * 3];
@@ -79,7 +89,7 @@ void CalibVolumes::loadInverseCalibs(std::string const& path) {
     const std::string name = path + basename_of(m_cv_xyz_filenames[i]) + "_inv";
     CalibrationVolume<glm::fvec4> v{name};
     const uint32_t res[3] = {v.res().x, v.res().y, v.res().z};
-    ck(rr_calib_upload_inv(ctx(), (int)i, reinterpret_cast<float const*>(v.volume().data()), res), "rr_calib_upload_inv");
+    gk(rr_group_calib_upload_inv(grp(), (int)i, reinterpret_cast<float const*>(v.volume().data()), res), "rr_calib_upload_inv");
     m_res_inv = v.res();
   }
 }
@@ -97,14 +107,14 @@ CalibrationInverter::CalibrationInverter(std::vector<std::string> const& calib_v
   for (auto const& f : calib_volume_files) m_cv_xyz_filenames.push_back(strip_ext3(f) + "cv_xyz");
   const float mn[3] = {bbox.getPMin()[0], bbox.getPMin()[1], bbox.getPMin()[2]};
   const float mx[3] = {bbox.getPMax()[0], bbox.getPMax()[1], bbox.getPMax()[2]};
-  ck(rr_set_bbox(ctx(), mn, mx), "rr_set_bbox");
+  gk(rr_group_set_bbox(grp(), mn, mx), "rr_set_bbox");
   for (unsigned i = 0; i < m_cv_xyz_filenames.size(); ++i) {
     std::cerr << "loading " << m_cv_xyz_filenames[i] << std::endl;
     CalibrationVolume<xyz> vx{m_cv_xyz_filenames[i]};
     std::vector<float> no_uv((std::size_t)vx.numVoxels() * 2, 0.0f);     // the inverter needs cv_xyz only
     const uint32_t res[3] = {vx.res().x, vx.res().y, vx.res().z};
     const float lim[2] = {vx.depthLimits().x, vx.depthLimits().y};
-    ck(rr_calib_upload(ctx(), (int)i, reinterpret_cast<float const*>(vx.volume().data()), no_uv.data(), res, lim), "rr_calib_upload");
+    gk(rr_group_calib_upload(grp(), (int)i, reinterpret_cast<float const*>(vx.volume().data()), no_uv.data(), res, lim), "rr_calib_upload");
   }
 }
 
@@ -208,7 +218,7 @@ NetKinectArray::NetKinectArray(std::string const& serverport, std::string const&
   std::vector<float> near_far;
   // per sensor, as the reference reads them (getCalibs()[i].getNear() / getFar(), NetKinectArray.cpp:345-351)
   for (unsigned i = 0; i < m_numLayers; ++i) { near_far.push_back(calibs->getNear(i)); near_far.push_back(calibs->getFar(i)); }
-  ck(rr_set_frame_format(ctx(), crgb == 1 ? RR_COLOR_DXT1 : (crgb == 5 ? RR_COLOR_DXT5 : RR_COLOR_RGB8),
+  gk(rr_group_set_frame_format(grp(), crgb == 1 ? RR_COLOR_DXT1 : (crgb == 5 ? RR_COLOR_DXT5 : RR_COLOR_RGB8),
                          calibs->isCompressedDepth() ? RR_DEPTH_U8 : RR_DEPTH_F32, near_far.data()), "rr_set_frame_format");
   for (int b = 0; b < 2; ++b)
     if (cudaMallocHost((void**)&m_staging[b], (m_colorsize + m_depthsize) * m_numLayers) != cudaSuccess) throw std::runtime_error("pinned staging allocation failed");
@@ -221,7 +231,7 @@ NetKinectArray::NetKinectArray(std::string const& serverport, std::string const&
 NetKinectArray::~NetKinectArray() {
   m_running = false;
   if (m_readThread) m_readThread->join();
-  rr_synchronize(ctx());
+  rr_group_synchronize(grp());
   for (int b = 0; b < 2; ++b) cudaFreeHost(m_staging[b]);
 }
 
@@ -229,11 +239,11 @@ void NetKinectArray::pushFrame(void const* color, void const* depth) {
   std::lock_guard<std::mutex> lock(m_mutex_pbo);
   // the reader's side of the double buffer: fill the back pinned buffer and start its copy into the back device slot;
   // the copy overlaps whatever the main thread is still computing on the current slot
-  ck(rr_stage_sync(ctx()), "rr_stage_sync");          // the copy that last read this pinned buffer pair has finished
+  gk(rr_group_stage_sync(grp()), "rr_stage_sync");          // the copy that last read this pinned buffer pair has finished
   uint8_t* dst = m_staging[m_back];
   std::memcpy(dst, color, m_colorsize * m_numLayers);
   std::memcpy(dst + m_colorsize * m_numLayers, depth, m_depthsize * m_numLayers);
-  ck(rr_stage_frames(ctx(), dst, m_colorsize * m_numLayers, dst + m_colorsize * m_numLayers, m_depthsize * m_numLayers), "rr_stage_frames");
+  gk(rr_group_stage_frames(grp(), dst, m_colorsize * m_numLayers, dst + m_colorsize * m_numLayers, m_depthsize * m_numLayers), "rr_stage_frames");
   m_back ^= 1;
   m_dirty = true;
   ++m_num_frame;
@@ -274,13 +284,13 @@ bool NetKinectArray::update() {
   std::lock_guard<std::mutex> lock(m_mutex_pbo);
   if (!m_dirty) return false;
   // swapBuffers (NetKinectArray.cpp:229-236): the staged device slot becomes the one the kernels read
-  ck(rr_swap_frames(ctx()), "rr_swap_frames");
+  gk(rr_group_swap_frames(grp()), "rr_swap_frames");
   m_dirty = false;
   return true;
 }
 
 void NetKinectArray::processTextures() {
-  ck(rr_preprocess(ctx(), m_filter_textures ? 1 : 0, m_use_processed_depth ? 1 : 0, m_refine_bound ? 1 : 0), "rr_preprocess");
+  gk(rr_group_preprocess(grp(), m_filter_textures ? 1 : 0, m_use_processed_depth ? 1 : 0, m_refine_bound ? 1 : 0), "rr_preprocess");
 }
 void NetKinectArray::filterTextures(bool filter) { m_filter_textures = filter; processTextures(); }
 void NetKinectArray::useProcessedDepths(bool filter) { m_use_processed_depth = filter; processTextures(); }
@@ -311,7 +321,7 @@ ReconIntegration::ReconIntegration(CalibrationFiles const& cfs, CalibVolumes con
   m_cfg.use_bricks = 1; m_cfg.skip_space = 1; m_cfg.store_weight = 0;
   setVoxelSize(size);
 }
-void ReconIntegration::configure() { ck(rr_configure(ctx(), &m_cfg), "rr_configure"); }
+void ReconIntegration::configure() { gk(rr_group_configure(grp(), &m_cfg), "rr_configure"); }
 void ReconIntegration::setVoxelSize(float size) {
   m_cfg.voxel_size = size;
   configure();
@@ -331,33 +341,33 @@ void ReconIntegration::setMinVoxelsPerBrick(unsigned i) {
 unsigned ReconIntegration::numBricks() const { uint32_t n = 0; ck(rr_get_brick_info(ctx(), nullptr, nullptr, &n), "rr_get_brick_info"); return n; }
 float ReconIntegration::getBrickSize() const { float s = 0; ck(rr_get_brick_info(ctx(), nullptr, &s, nullptr), "rr_get_brick_info"); return s; }
 glm::uvec3 ReconIntegration::volumeResolution() const { uint32_t r[3]; ck(rr_get_volume_res(ctx(), r), "rr_get_volume_res"); return glm::uvec3(r[0], r[1], r[2]); }
-void ReconIntegration::clearOccupiedBricks() const { ck(rr_bricks_clear(ctx()), "rr_bricks_clear"); }
+void ReconIntegration::clearOccupiedBricks() const { gk(rr_group_bricks_clear(grp()), "rr_bricks_clear"); }
 void ReconIntegration::updateOccupiedBricks() {
   uint32_t n = 0;
-  ck(rr_bricks_update(ctx(), &n, &m_ratio_occupied), "rr_bricks_update");
+  gk(rr_group_bricks_update(grp(), &n, &m_ratio_occupied), "rr_bricks_update");
 }
-void ReconIntegration::integrate() { ck(rr_integrate(ctx()), "rr_integrate"); }
+void ReconIntegration::integrate() { gk(rr_group_integrate(grp()), "rr_integrate"); }
 void ReconIntegration::resize(std::size_t width, std::size_t height) { Reconstruction::resize(width, height); }
 void ReconIntegration::draw() {
   const std::size_t n = (std::size_t)m_view.viewport[2] * m_view.viewport[3];
   m_rgba.resize(n * 4); m_depth.resize(n);
-  ck(rr_raymarch(ctx(), &m_view, m_rgba.data(), m_depth.data()), "rr_raymarch");
+  gk(rr_group_raymarch(grp(), &m_view, m_rgba.data(), m_depth.data()), "rr_raymarch");
 }
 void ReconIntegration::drawF() {
   // drawDepthLimits + draw + fillColors (recon_integration.cpp:151-175): brick space skipping happens inside
   // rr_raymarch; with m_fill_holes (the default) the colour image is the hole-filled one
   Reconstruction::drawF();
-  if (m_fill_holes) ck(rr_fill_colors(ctx(), m_rgba.data()), "rr_fill_colors");
+  if (m_fill_holes) gk(rr_group_fill_colors(grp(), m_rgba.data()), "rr_fill_colors");
 }
 void ReconIntegration::downloadTsdf(std::vector<float>& out) const {
   const glm::uvec3 r = volumeResolution();
   out.resize((std::size_t)r.x * r.y * r.z);
-  ck(rr_download_tsdf(ctx(), out.data()), "rr_download_tsdf");
+  gk(rr_group_download_tsdf(grp(), out.data()), "rr_download_tsdf");
 }
 
 // ---------------------------------------------------------------------------------------------------- TimerDatabase
 TimerDatabase& TimerDatabase::instance() { static TimerDatabase t; return t; }
-void TimerDatabase::enable(int level) const { ck(rr_set_timing(ctx(), level), "rr_set_timing"); }
+void TimerDatabase::enable(int level) const { gk(rr_group_set_timing(grp(), level), "rr_set_timing"); }
 double TimerDatabase::duration(std::string const& name) const {
   float ms = 0.0f;
   ck(rr_get_stage_ms(ctx(), name.c_str(), &ms), "rr_get_stage_ms");

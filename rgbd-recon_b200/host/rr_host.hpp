@@ -144,13 +144,22 @@ namespace gpu {
 class Context {
  public:
   Context(int device, CalibrationFiles const& cfs);
+  // several devices: the TSDF volume is split into z-slabs, one per device (rr_group, include/rgbd_recon_b200.h); frame sets
+  // enter on devices[0] and reach the others by peer copies, the view is composited on devices[0]
+  Context(std::vector<int> const& devices, CalibrationFiles const& cfs);
   ~Context();
   Context(Context const&) = delete;
   Context& operator=(Context const&) = delete;
-  rr_ctx* handle() const { return m_ctx; }
+  rr_ctx* handle() const { return m_ctx; }   // member 0: queries, read-backs, timers
+  rr_group* group() const { return m_group; }
+  unsigned numDevices() const { return (unsigned)rr_group_size(m_group); }
+  // equal-cost slabs from the occupied bricks of the last fused frame set (rr_group_balance_slabs)
+  void balanceSlabs() const { checkGroup(rr_group_balance_slabs(m_group, 0.0f), "rr_group_balance_slabs"); }
   static Context& current();                 // throws if none was created
-  void check(int status, char const* what) const;   // rethrow a C-ABI status
+  void check(int status, char const* what) const;        // rethrow a C-ABI status of member 0
+  void checkGroup(int status, char const* what) const;   // ... of a group call
  private:
+  rr_group* m_group;
   rr_ctx* m_ctx;
 };
 }  // namespace gpu

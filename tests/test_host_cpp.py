@@ -91,8 +91,19 @@ def test_calib_inverter_program_matches_oracle(tmp_path, small_scene):
 
 
 @pytest.mark.gpu
-def test_fusion_playback_program_matches_oracle(tmp_path, small_scene):
+@pytest.mark.parametrize("devices", [None, "0,0,0", "all"])
+def test_fusion_playback_program_matches_oracle(tmp_path, small_scene, devices):
+    """The C++ look-alike program against the oracle; with --devices the same run goes through rr_group (z-slabs over several
+    devices in one process, here also three slabs sharing GPU 0) and must give the same volume and image bit for bit."""
     import oracle_py as O
+    extra = []
+    if devices == "all":
+        import torch
+        if torch.cuda.device_count() < 2:
+            pytest.skip("one GPU: the multi-device run is covered by the shared-device case")
+        extra = ["--gpus", str(min(4, torch.cuda.device_count()))]
+    elif devices:
+        extra = ["--devices", devices]
     from rrpy import synth, volume_io
     sc = small_scene
     ks, streams = write_scene_files(str(tmp_path), sc)
@@ -104,10 +115,11 @@ def test_fusion_playback_program_matches_oracle(tmp_path, small_scene):
     np.concatenate([mv, pr]).astype(np.float32).tofile(str(tmp_path / "view.bin"))
     r = subprocess.run([os.path.join(BIN, "fusion_playback"), ks, "--depth", str(sc.W), str(sc.H), "--color", str(sc.CW), str(sc.CH),
                         "--streams", ";".join(streams), "--frames", "3", "--voxel", "0.02", "--view", str(VW), str(VH), "--shade", "1",
-                        "--matrices", str(tmp_path / "view.bin"), "--dump-tsdf", str(tmp_path / "tsdf.bin"), "--dump-image", str(tmp_path / "img.bin")],
+                        "--matrices", str(tmp_path / "view.bin"), "--dump-tsdf", str(tmp_path / "tsdf.bin"), "--dump-image", str(tmp_path / "img.bin")] + extra,
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
     assert "2integrate mean ms" in r.stdout
+    assert ("z-slabs over" in r.stdout) == bool(extra)
     grid = O.brick_grid(sc.bbox_min, sc.bbox_max, 0.02, 0.1)
     cams = [O.frustum(sc.cv_xyz[i])[1] for i in range(sc.N)]
     pre = O.preprocess(sc, grid, cams)
