@@ -53,44 +53,18 @@ __global__ void __launch_bounds__(1024) k_bricks_update(const uint32_t* __restri
                                                         uint32_t* __restrict__ occupied, uint32_t* __restrict__ num_occupied,
                                                         uint8_t* __restrict__ near_occ, uint8_t* __restrict__ occ_mask,
                                                         uint32_t* __restrict__ rowmask, uint8_t* __restrict__ rowany,
-                                                        uint32_t* __restrict__ work, uint32_t mask_blocks, uint32_t cls_blocks,
-                                                        const __grid_constant__ ClassifyParams cq) {
+                                                        uint32_t* __restrict__ work, uint32_t mask_blocks, const __grid_constant__ ClassifyParams cq) {
   if (blockIdx.x == 0) {
     if (threadIdx.x < 4) work[threadIdx.x] = 0;          // work counters of the persistent integrators (this frame's launch)
     bricks_compact_block(counters, num_bricks, min_voxels, occupied, num_occupied);
     return;
   }
   if (blockIdx.x > mask_blocks) {
-    // verdict blocks (staged integrator): one warp per (work item, sensor) of every brick, idle unless the brick is
-    // occupied; 32 / N items per block, their sensors' bits meet in shared memory
-    __shared__ uint32_t s_bits[32][4];          // per item slot: skip, front, oversize, has voxels
-    const int N = cq.N, per_block = 32 / N;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x < 128) s_bits[threadIdx.x >> 2][threadIdx.x & 3] = 0u;
-    __syncthreads();
-    const int slot = warp / N, s = warp - slot * N;
-    // grid-stride over groups of per_block items of the whole brick grid; a group without an occupied brick costs one barrier
-    const uint32_t groups = (num_bricks * (uint32_t)cq.per_brick + (uint32_t)per_block - 1u) / (uint32_t)per_block;
-    for (uint32_t grp = blockIdx.x - 1 - mask_blocks; grp < groups; grp += cls_blocks) {
-      const uint32_t w = grp * (uint32_t)per_block + (uint32_t)slot;      // item index
-      const uint32_t brick = w / (uint32_t)cq.per_brick;
-      const bool live = slot < per_block && brick < num_bricks && counters[brick] >= min_voxels;
-      if (!__syncthreads_or(live ? 1 : 0)) continue;
-      if (live) {
-        const uint32_t r = classify_sensor(cq, (size_t)w, s, lane);
-        if (lane == 0 && r) {
-          if (r & 1u) atomicOr(&s_bits[slot][0], 1u << s);
-          if (r & 2u) atomicOr(&s_bits[slot][1], 1u << s);
-          if (r & 4u) atomicOr(&s_bits[slot][2], 1u << s);
-          atomicOr(&s_bits[slot][3], 1u);
-        }
-      }
-      __syncthreads();
-      if (live && s == 0 && lane == 0 && s_bits[slot][3]) classify_push(cq, (size_t)w, s_bits[slot][0], s_bits[slot][1], s_bits[slot][2]);
-      __syncthreads();
-      if (threadIdx.x < 128) s_bits[threadIdx.x >> 2][threadIdx.x & 3] = 0u;
-      // the next iteration's __syncthreads_or orders this reset before its atomics
-    }
+    // verdict blocks (staged integrator): one warp per work item of every brick, idle unless the brick is occupied
+    const uint32_t w = (blockIdx.x - 1 - mask_blocks) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t brick = w / (uint32_t)cq.per_brick;
+    if (brick >= num_bricks || counters[brick] < min_voxels) return;
+    classify_item(cq, brick, w - brick * (uint32_t)cq.per_brick, threadIdx.x & 31);
     return;
   }
   if (near_occ == nullptr) return;
@@ -138,14 +112,11 @@ int launch_bricks_update(rr_ctx* c) {
   ClassifyParams cq{};
   RR_TRY_RC(staged_prepare(c));
   const bool classify = staged_classify_params(c, cq);
-  // verdict blocks: 32 / N items per block and step, grid-stride (a wave of two blocks per SM at most)
-  const uint32_t items_per_block = classify ? 32u / (uint32_t)cq.N : 1u;
-  const uint32_t cls_groups = classify ? (nb * (uint32_t)cq.per_brick + items_per_block - 1u) / items_per_block : 0u;
-  const uint32_t cls_blocks = cls_groups < 296u ? cls_groups : 296u;
+  const uint32_t cls_blocks = classify ? (nb * (uint32_t)cq.per_brick + 31u) / 32u : 0u;
   k_bricks_update<<<1 + mask_blocks + cls_blocks, 1024, 0, c->stream>>>(
       c->d_counters, nb, c->bricks.res[0], c->bricks.res[1], c->bricks.res[2], c->cfg.min_voxels_per_brick, c->d_ranges, c->mask_words,
       c->d_occupied, c->d_num_occ, grid_ok ? c->d_near_occ : nullptr, c->d_occ_mask, (grid_ok && c->fused_ok) ? c->d_rowmask : nullptr, c->d_rowany,
-      c->d_work, mask_blocks, cls_blocks, cq);
+      c->d_work, mask_blocks, cq);
   RR_LAUNCH_CHECK(c, "k_bricks_update");
   c->work_fresh = true;
   cudaError_t e = cudaMemcpyAsync(c->h_num_occ, c->d_num_occ, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);

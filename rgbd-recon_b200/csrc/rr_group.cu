@@ -12,6 +12,8 @@
 // The multi-process form of the same path (one rank per GPU, NCCL) is what bench.py drives through rrpy/multigpu.py.
 #include "rr_context.h"
 
+#include <cuda_fp16.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -411,7 +413,8 @@ int rr_group_fill_colors(rr_group* g, float* out_rgba) {
   return rc == RR_OK ? RR_OK : member_fail(g, 0, rc);
 }
 
-// The whole volume, assembled from the slices each member owns. out: float32 [Z][Y][X] (one 4-byte voxel each).
+// The whole volume, assembled from the slices each member owns. out: float32 [Z][Y][X], as rr_download_tsdf returns it
+// (half2 voxels: the tsdf half widened to float).
 int rr_group_download_tsdf(rr_group* g, float* out) {
   if (!g || !out) return RR_ERR_INVALID;
   uint32_t res[3];
@@ -424,7 +427,16 @@ int rr_group_download_tsdf(rr_group* g, float* out) {
     const size_t z0 = g->bounds[i], z1 = g->bounds[i + 1];
     RR_G_TRY(g, cudaMemcpyAsync(out + plane * z0, c->d_tsdf + plane * z0, plane * (z1 - z0) * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   }
-  return rr_group_synchronize(g);
+  const int rc = rr_group_synchronize(g);
+  if (rc != RR_OK || g->m[0]->cfg.store_weight != RR_VOXELS_HALF2) return rc;
+  const size_t n = plane * res[2];
+  for (size_t i = 0; i < n; ++i) {
+    uint32_t u;
+    std::memcpy(&u, out + i, sizeof(u));
+    const __half h = __ushort_as_half((unsigned short)(u & 0xffffu));
+    out[i] = __half2float(h);
+  }
+  return RR_OK;
 }
 
 }  // extern "C"

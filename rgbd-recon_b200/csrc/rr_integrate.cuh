@@ -498,40 +498,42 @@ struct ClassifyParams {
   float limit;
 };
 
-// one warp, one (item, sensor): bit 0 skip, bit 1 front, bit 2 the footprint exceeds the tile, bit 3 the item has voxels
-__device__ __forceinline__ uint32_t classify_sensor(const ClassifyParams& q, size_t item, int s, int lane) {
+__device__ __forceinline__ void classify_item(const ClassifyParams& q, uint32_t brick, uint32_t sub, int lane) {
+  const size_t item = (size_t)brick * q.per_brick + sub;
   const float inf = __int_as_float(0x7f800000);
-  const uint2 f = q.fp[item * q.N + s];
-  const float2 z = q.zr[item * q.N + s];
-  const int rw = (int)((f.y >> 8) & 4095u), rh = (int)(f.y >> 20);
-  if (rw * rh == 0) return 0u;
-  uint32_t r = 8u | ((f.y & 128u) ? 4u : 0u);
-  if (!(z.x <= z.y)) return r;
-  const float2* img = q.pairs + ((size_t)s * q.H2 + (f.x >> 16)) * q.pair_pitch + (f.x & 0xffffu) + (f.y & 127u);
-  float dlo = inf, dhi = -inf;
-  bool ok = true;
-  for (int i = lane; i < rw * rh; i += 32) {
-    const int ty = i / rw, tx = i - ty * rw;
-    const float2 t = __ldg(img + (size_t)ty * q.pair_pitch + tx);
-    ok = ok && ((int)__float_as_uint(t.y) < 0) && (fabsf(t.x) < inf);
-    dlo = fminf(dlo, t.x); dhi = fmaxf(dhi, t.x);
-  }
+  uint32_t skip = 0, front = 0, oversize = 0, voxels = 0;
+#pragma unroll 1
+  for (int s = 0; s < q.N; ++s) {
+    const uint2 f = q.fp[item * q.N + s];
+    const float2 z = q.zr[item * q.N + s];
+    const int rw = (int)((f.y >> 8) & 4095u), rh = (int)(f.y >> 20);
+    if (rw * rh == 0) continue;
+    voxels = 1;
+    if (f.y & 128u) oversize |= 1u << s;
+    if (!(z.x <= z.y)) continue;
+    const float2* img = q.pairs + ((size_t)s * q.H2 + (f.x >> 16)) * q.pair_pitch + (f.x & 0xffffu) + (f.y & 127u);
+    float dlo = inf, dhi = -inf;
+    bool ok = true;
+    for (int i = lane; i < rw * rh; i += 32) {
+      const int ty = i / rw, tx = i - ty * rw;
+      const float2 t = __ldg(img + (size_t)ty * q.pair_pitch + tx);
+      ok = ok && ((int)__float_as_uint(t.y) < 0) && (fabsf(t.x) < inf);
+      dlo = fminf(dlo, t.x); dhi = fmaxf(dhi, t.x);
+    }
 #pragma unroll
-  for (int d = 16; d > 0; d >>= 1) {
-    dlo = fminf(dlo, __shfl_xor_sync(0xffffffffu, dlo, d)); dhi = fmaxf(dhi, __shfl_xor_sync(0xffffffffu, dhi, d));
+    for (int d = 16; d > 0; d >>= 1) {
+      dlo = fminf(dlo, __shfl_xor_sync(0xffffffffu, dlo, d)); dhi = fmaxf(dhi, __shfl_xor_sync(0xffffffffu, dhi, d));
+    }
+    if (!__all_sync(0xffffffffu, ok)) continue;
+    if (z.x - dhi >= q.limit) skip |= 1u << s;
+    else if (z.y - dlo <= -q.limit) front |= 1u << s;
   }
-  if (!__all_sync(0xffffffffu, ok)) return r;
-  if (z.x - dhi >= q.limit) r |= 1u;
-  else if (z.y - dlo <= -q.limit) r |= 2u;
-  return r;
-}
-
-// one thread per item, once every sensor's bits are known: append (item, verdict) to the list of its cost class
-__device__ __forceinline__ void classify_push(const ClassifyParams& q, size_t item, uint32_t skip, uint32_t front, uint32_t oversize) {
-  const uint32_t off = skip | front;
-  const int cls = (oversize & ~off) ? q.N : q.N - __popc(off);
-  const uint32_t idx = atomicAdd(q.class_count + cls, 1u);
-  if (idx < q.list_stride) q.list[(size_t)cls * q.list_stride + idx] = make_uint2((uint32_t)item, skip | (front << 8));
+  if (lane == 0 && voxels) {
+    const uint32_t off = skip | front;
+    const int cls = (oversize & ~off) ? q.N : q.N - __popc(off);
+    const uint32_t idx = atomicAdd(q.class_count + cls, 1u);
+    if (idx < q.list_stride) q.list[(size_t)cls * q.list_stride + idx] = make_uint2((uint32_t)item, skip | (front << 8));
+  }
 }
 
 // The cleared voxel as the 4 bytes the fill stores write: -limit (R32F), or half2(-limit, 0) for half2 voxels.

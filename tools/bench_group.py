@@ -33,6 +33,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--c5", action="store_true", help="BASELINE config 5: 8 sensors, 1024^3, half2 voxels")
     ap.add_argument("--devices", default="", help="explicit device list a,b,... (a device may repeat)")
+    ap.add_argument("--dxt1", action="store_true", help="stream colour as DXT1 blocks and depth as 8-bit bytes (3.6 MB instead of 20 MB per frame set)")
+    ap.add_argument("--count", action="store_true", help="read the occupied-brick count every step (the reference's per-frame read-back)")
     a = ap.parse_args()
     devices = [int(v) for v in a.devices.split(",")] if a.devices else list(range(a.gpus))
     n_s, res, fmt = (8, 1024, capi.VOXELS_HALF2) if a.c5 else (bench.N_SENSORS, bench.R, capi.VOXELS_F32)
@@ -49,20 +51,29 @@ def main():
             capi.load_scene(obj, sc, inv)
         obj.configure(limit=bench.LIMIT, voxel_size=voxel, brick_size=bench.BRICK, min_voxels=bench.MIN_VOX, use_bricks=True, store_weight=fmt)
 
+    near_far = np.float32([[0.5, 4.5]] * n_s)
+    flags = (True, not a.dxt1, True)          # 8-bit depth streams skip pre_morph (it validates metres), as in the reference's use
     g = capi.Group(devices, n_s, bench.W, bench.H, bench.CW, bench.CH)
     setup(g)
-    pinned = [(torch.from_numpy(s.color).pin_memory(), torch.from_numpy(s.depth).pin_memory()) for s in scenes]
+    if a.dxt1:
+        g.set_frame_format(dxt1_color=True, depth8=True, near_far=near_far)
+        packed = [(np.stack([synth.encode_dxt1(s.color[i]) for i in range(n_s)]), np.stack([synth.encode_depth8(s.depth[i], 0.5, 4.5) for i in range(n_s)])) for s in scenes]
+        pinned = [(torch.from_numpy(c).pin_memory(), torch.from_numpy(d).pin_memory()) for c, d in packed]
+    else:
+        pinned = [(torch.from_numpy(s.color).pin_memory(), torch.from_numpy(s.depth).pin_memory()) for s in scenes]
     streams = [torch.cuda.ExternalStream(g.member(i).stream(), device=torch.device("cuda", devices[i])) for i in range(len(devices))]
 
     def stage(k):
         c, d = pinned[k % len(pinned)]
-        g.stage_frames_ptr(c.data_ptr(), c.numel(), d.data_ptr(), d.numel() * 4)
+        g.stage_frames_ptr(c.data_ptr(), c.numel() * c.element_size(), d.data_ptr(), d.numel() * d.element_size())
 
     def run(steps, first):
         for k in range(first, first + steps):
             g.swap_frames()
             stage(k + 1)
-            g.fuse_frame()
+            g.fuse_frame(*flags)
+            if a.count:
+                g.bricks_count()
         return first + steps
 
     stage(0)
@@ -102,8 +113,13 @@ def main():
     g.close()
     fu = capi.Fusion(n_s, bench.W, bench.H, bench.CW, bench.CH, device=devices[0])
     setup(fu)
-    fu.upload_frames(last.color, last.depth)
-    fu.fuse_frame()
+    if a.dxt1:
+        fu.set_frame_format(dxt1_color=True, depth8=True, near_far=near_far)
+        c, d = packed[(k - 1) % len(scenes)]
+        fu.upload_frames(c, d)
+    else:
+        fu.upload_frames(last.color, last.depth)
+    fu.fuse_frame(*flags)
     w_tsdf = fu.download_tsdf()
     w_rgba, w_depth = fu.raymarch(mv, pr, bench.VW, bench.VH, shade_mode=1)
     fu.close()
@@ -112,7 +128,8 @@ def main():
     print(json.dumps({"what": "rr_group (one process): stage (H2D + peer copies) + swap + fuse per frame set, end to end from pinned host memory",
                       "config": "c5: 8 sensors, 1024^3 half2" if a.c5 else bench.WORKLOAD, "devices": devices, "steps": a.steps, "warmup": a.warmup,
                       "ms_per_step": round(ms, 5), "frames_per_s": round(1e3 / ms, 2), "gvoxel_updates_per_s": round(res ** 3 / ms / 1e6, 3),
-                      "h2d_bytes_per_step": int(pinned[0][0].numel() + pinned[0][1].numel() * 4), "view_ms": round(view_ms, 4),
+                      "h2d_bytes_per_step": int(pinned[0][0].numel() * pinned[0][0].element_size() + pinned[0][1].numel() * pinned[0][1].element_size()),
+                      "stream": "DXT1 colour + 8-bit depth" if a.dxt1 else "RGB8 + float32", "view_ms": round(view_ms, 4),
                       "view": f"{bench.VW}x{bench.VH}: per-slab raymarch + peer-memory composite + colour hole filling",
                       "slabs": slabs, "occupied_bricks": n_occ, "verified": verified}), flush=True)
 
