@@ -322,7 +322,7 @@ def sub_record(torch, dist, rank, world, local, what, n_sensors, res, bricks, fm
     return out
 
 
-def verify_against_single_context(torch, dist, rig, scenes, inv, voxel, bricks, mv, pr, records, view_once):
+def verify_against_single_context(torch, dist, rig, scenes, inv, voxel, bricks, mv, pr, view_once):
     """Run once, untimed: every rank fuses frame set 0 into its slab and hashes the slices it owns; rank 0 also fuses the whole
     volume on a second, unsharded context and hashes the same slice ranges, marches the same view there, and compares the
     composited image of the sharded run with it bit for bit. True only if every slab and the view agree."""
@@ -334,11 +334,11 @@ def verify_against_single_context(torch, dist, rig, scenes, inv, voxel, bricks, 
     digest = np.frombuffer(hashlib.sha256(mine.tobytes()).digest(), np.uint8).copy()
     all_digests = [torch.empty(32, dtype=torch.uint8, device=dev) for _ in range(world)]
     dist.all_gather(all_digests, torch.from_numpy(digest).to(dev))
-    view_once()
+    composited = view_once(download=True)
     rig.barrier()
     ok = True
     if rank == 0:
-        rgba_s, depth_s = fu.composite(records.data_ptr(), 1, VW, VH, download=True)
+        rgba_s, depth_s = composited
         ref = capi.Fusion(N_SENSORS, W, H, CW, CH, device=rig.local)
         capi.load_scene(ref, scenes[0], inv)
         ref.configure(limit=LIMIT, voxel_size=voxel, brick_size=BRICK, min_voxels=MIN_VOX, use_bricks=bricks)
@@ -468,19 +468,38 @@ def run_ours(args):
     # N > 1 every rank marches its slab into partial records and two reductions composite them on rank 0
     mv = synth.look_at((1.7, 1.6, 2.3), (0.0, 1.1, 0.0))
     pr = synth.perspective(50.0, VW / VH, 0.1, 10.0)
-    records = torch.empty((VW * VH, multigpu.RECORD_FLOATS), dtype=torch.float32, device=dev)
-    keys = torch.empty((VW * VH,), dtype=torch.int64, device=dev)
+    # N > 1: every rank marches its slab into its own view images; rank 0 composites them with ONE kernel that reads the other
+    # ranks' first-hit keys and the winners' pixels straight out of their memory (CUDA IPC over NVLink: rr_view_export /
+    # rr_composite_peers, the kernel of rr_group_raymarch). Two stream-ordered one-element all-reduces fence the ranks: the
+    # peers' marches are complete before rank 0 reads them, and no peer marches again before rank 0 has finished.
+    peer_handles = []
+    fence = torch.zeros(1, dtype=torch.int32, device=dev) if world > 1 else None
+    if world > 1:
+        fu.raymarch(mv, pr, VW, VH, shade_mode=1, download=False)          # allocates the view images at this size
+        fu.synchronize()
+        blobs = [None] * world
+        dist.all_gather_object(blobs, fu.view_export(VW, VH))
+        peer_handles = [blobs[r] for r in range(world) if r != 0]
 
-    def view_once():
+    def stream_fence():
+        cur = torch.cuda.current_stream(dev)
+        cur.wait_stream(stream)
+        dist.all_reduce(fence)
+        stream.wait_stream(cur)
+
+    def view_once(download=False):
         if world == 1:
             fu.raymarch(mv, pr, VW, VH, shade_mode=1, download=False)
             fu.fill_colors(download=False)          # m_fill_holes is on by default (recon_integration.cpp:54)
-            return
-        fu.raymarch_partial(mv, pr, VW, VH, records.data_ptr(), shade_mode=1)
-        multigpu.reduce_records(dist, fu, records, keys, dst=0, stream=stream)
+            return None
+        fu.raymarch(mv, pr, VW, VH, shade_mode=1, download=False)
+        stream_fence()
+        out = None
         if rank == 0:
-            fu.composite(records.data_ptr(), 1, VW, VH, download=False)
+            out = fu.composite_peers(peer_handles, VW, VH, download=download)
             fu.fill_colors(download=False)
+        stream_fence()
+        return out
 
     for _ in range(3):
         view_once()
@@ -497,7 +516,7 @@ def run_ours(args):
     # ---- N > 1: this run's slabs and composited view against a single-context run, bit for bit ---------------------------
     verified = None
     if world > 1:
-        verified = verify_against_single_context(torch, dist, rig, scenes, inv, voxel, bricks, mv, pr, records, view_once)
+        verified = verify_against_single_context(torch, dist, rig, scenes, inv, voxel, bricks, mv, pr, view_once)
 
     frames_s = args.steps / (ms_total / 1e3)
     value = R ** 3 * frames_s / 1e9
@@ -542,7 +561,7 @@ def run_ours(args):
                              f"({ms_stage_pass / stage_steps:.5f} ms/step); `value` is timed with the frame replayed as one CUDA graph"},
         "view": {"ms_per_view": round(view_ms, 4), "resolution": [VW, VH],
                  "what": "tsdf_raymarch (shaded, brick space skipping) + colour hole filling" +
-                         (" per slab, MIN all-reduce of the first-hit keys + integer SUM reduce of the winners' records onto rank 0, composite" if world > 1 else "")},
+                         (" per slab; one compositing kernel on rank 0 reads the other ranks' first-hit keys and the winners' pixels through CUDA IPC peer memory (rr_composite_peers), fenced by two one-element all-reduces" if world > 1 else "")},
         # SURVEY.md 8d "reported separately and combined": one fused frame set followed by one view
         "combined_frames_per_s": round(1e3 / (ms_step + view_ms), 2),
         "roofline": {"bound": "hbm", "kernel": integrate_kernel_name(bricks, info),

@@ -240,6 +240,15 @@ int rr_group_fill_colors(rr_group* g, float* out_rgba);
 /* The whole volume assembled from the slices each member owns: float32 [Z][Y][X] (4-byte voxels of any format). */
 int rr_group_download_tsdf(rr_group* g, float* out);
 
+/* The group's compositing with one process per GPU (torchrun / MPI): every rank marches its slab with rr_raymarch (no
+ * download), exports its view images once per viewport size (rr_view_export: RR_VIEW_HANDLE_BYTES of CUDA IPC handles, to be
+ * sent to the display rank by any means), and the display rank composites its own view with the peers' directly out of their
+ * memory (rr_composite_peers, the kernel of rr_group_raymarch). The caller orders the ranks: the peers' marches must have
+ * completed before the call (e.g. a stream-ordered NCCL barrier) and the peers must not march again before it has finished. */
+#define RR_VIEW_HANDLE_BYTES 256
+int rr_view_export(rr_ctx* ctx, int width, int height, void* out_handle);
+int rr_composite_peers(rr_ctx* ctx, const void* peer_handles, int n_peers, int width, int height, float* out_rgba, float* out_depth);
+
 /* ---- read-back (tests, debug views) ------------------------------------------------------------------------ */
 int rr_download_tsdf(rr_ctx* ctx, float* out);
 int rr_download_weight(rr_ctx* ctx, float* out);

@@ -171,6 +171,8 @@ void rr_destroy(rr_ctx* c) {
   cudaFree(c->d_inv); cudaFree(c->d_morph); cudaFree(c->d_depth);
   cudaFree(c->d_lab); cudaFree(c->d_depth_b); cudaFree(c->d_sil); cudaFree(c->d_normal); cudaFree(c->d_quality);
   staged_release(c);
+  for (auto& v : c->ipc_views) { cudaIpcCloseMemHandle(v.step); cudaIpcCloseMemHandle(v.rgba); cudaIpcCloseMemHandle(v.zbuf); cudaIpcCloseMemHandle(v.nsamp); }
+  cudaGetLastError();
   cudaFree(c->d_pairs);
   cudaFree(c->d_gather); cudaFree(c->d_flags); cudaFree(c->d_ranges); cudaFree(c->d_counters); cudaFree(c->d_occupied);
   cudaFree(c->d_num_occ); cudaFree(c->d_work); cudaFree(c->d_ztab); cudaFree(c->d_rowmask); cudaFree(c->d_rowany); cudaFree(c->d_cand_y); cudaFree(c->d_cand_z); cudaFree(c->d_near_occ); cudaFree(c->d_occ_mask); cudaFree(c->d_pos); cudaFree(c->d_step); cudaFree(c->d_tsdf); cudaFree(c->d_weight);
@@ -602,7 +604,7 @@ int rr_bricks_count(rr_ctx* c, uint32_t* out_num, float* out_ratio) {
   return RR_OK;
 }
 
-static int ensure_view(rr_ctx* c, int w, int h) {
+int ensure_view(rr_ctx* c, int w, int h) {
   if (w == c->view_w && h == c->view_h) return RR_OK;
   RR_TRY(check(c, cudaStreamSynchronize(c->stream), "raymarch resize sync"));
   RR_TRY(dev_alloc(c, &c->d_rgba, (size_t)w * h, "view rgba"));

@@ -145,6 +145,9 @@ struct rr_ctx {
   // rr_fuse_frame: captured launch sequences, keyed by (frame slot, pre-process flags, tunable generation)
   struct FrameGraph { uint64_t key; cudaGraphExec_t exec; uint64_t launches; };
   std::vector<FrameGraph> frame_graphs;
+  // view images of other processes' contexts opened through CUDA IPC (rr_composite_peers); key = the 256-byte handle blob
+  struct IpcView { std::string key; uint32_t* step; float4* rgba; float* zbuf; float* nsamp; };
+  std::vector<IpcView> ipc_views;
   bool graphs_broken = false;      // a capture failed once: stay on direct launches
   // staged (TMA) integrator, rr_integrate_staged.cu. `dirty` is set by everything its tables depend on (inverse volumes,
   // volume / brick grid, tunables); they are rebuilt lazily by the next integrate or pre-process call.

@@ -413,6 +413,64 @@ int rr_group_fill_colors(rr_group* g, float* out_rgba) {
   return rc == RR_OK ? RR_OK : member_fail(g, 0, rc);
 }
 
+/* ---- the same compositing across processes (one process per GPU): the peers' view images through CUDA IPC --------------- */
+int ensure_view(rr_ctx* c, int w, int h);      // rr_api.cu (same linkage block)
+
+int rr_view_export(rr_ctx* c, int width, int height, void* out_handle) {
+  if (!c) return RR_ERR_INVALID;
+  if (!out_handle || width <= 0 || height <= 0) return rr::fail(c, RR_ERR_INVALID, "rr_view_export: bad arguments");
+  if (cudaSetDevice(c->device) != cudaSuccess) return rr::check(c, cudaGetLastError(), "rr_view_export");
+  RR_TRY_RC(ensure_view(c, width, height));
+  cudaIpcMemHandle_t h[4];
+  static_assert(sizeof(h) == RR_VIEW_HANDLE_BYTES, "four IPC handles");
+  void* ptrs[4] = {c->d_step, c->d_rgba, c->d_zbuf, c->d_nsamples};
+  for (int i = 0; i < 4; ++i) {
+    const cudaError_t e = cudaIpcGetMemHandle(&h[i], ptrs[i]);
+    if (e != cudaSuccess) return rr::check(c, e, "rr_view_export: cudaIpcGetMemHandle");
+  }
+  std::memcpy(out_handle, h, sizeof(h));
+  return RR_OK;
+}
+
+int rr_composite_peers(rr_ctx* c, const void* peer_handles, int n_peers, int width, int height, float* out_rgba, float* out_depth) {
+  if (!c) return RR_ERR_INVALID;
+  if (n_peers < 0 || n_peers >= RR_MAX_GROUP || (n_peers > 0 && !peer_handles) || width != c->view_w || height != c->view_h || !c->d_step)
+    return rr::fail(c, RR_ERR_INVALID, "rr_composite_peers: march this context's own view at this size first; at most 15 peers");
+  if (cudaSetDevice(c->device) != cudaSuccess) return rr::check(c, cudaGetLastError(), "rr_composite_peers");
+  rr::PeerViews pv{};
+  pv.n = n_peers + 1;
+  pv.step[0] = c->d_step; pv.rgba[0] = c->d_rgba; pv.zbuf[0] = c->d_zbuf; pv.nsamp[0] = c->d_nsamples;
+  for (int p = 0; p < n_peers; ++p) {
+    const std::string key(static_cast<const char*>(peer_handles) + (size_t)p * RR_VIEW_HANDLE_BYTES, RR_VIEW_HANDLE_BYTES);
+    const rr_ctx::IpcView* v = nullptr;
+    for (const auto& o : c->ipc_views) if (o.key == key) { v = &o; break; }
+    if (!v) {
+      cudaIpcMemHandle_t h[4];
+      std::memcpy(h, key.data(), sizeof(h));
+      void* ptrs[4] = {nullptr, nullptr, nullptr, nullptr};
+      for (int i = 0; i < 4; ++i) {
+        const cudaError_t e = cudaIpcOpenMemHandle(&ptrs[i], h[i], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+          for (int k = 0; k < i; ++k) cudaIpcCloseMemHandle(ptrs[k]);
+          return rr::check(c, e, "rr_composite_peers: cudaIpcOpenMemHandle (handles come from rr_view_export in ANOTHER process)");
+        }
+      }
+      c->ipc_views.push_back({key, (uint32_t*)ptrs[0], (float4*)ptrs[1], (float*)ptrs[2], (float*)ptrs[3]});
+      v = &c->ipc_views.back();
+    }
+    pv.step[p + 1] = v->step; pv.rgba[p + 1] = v->rgba; pv.zbuf[p + 1] = v->zbuf; pv.nsamp[p + 1] = v->nsamp;
+  }
+  const size_t px = (size_t)width * height;
+  rr::timer_begin(c, "composite");
+  rr::k_composite_peers<<<(unsigned)((px + 255) / 256), 256, 0, c->stream>>>(pv, (int)px, c->d_rgba, c->d_zbuf, c->d_step, c->d_nsamples);
+  RR_LAUNCH_CHECK(c, "k_composite_peers");
+  rr::timer_end(c, "composite");
+  if (out_rgba) RR_TRY_RC(rr::check(c, cudaMemcpyAsync(out_rgba, c->d_rgba, px * sizeof(float4), cudaMemcpyDeviceToHost, c->stream), "rgba download"));
+  if (out_depth) RR_TRY_RC(rr::check(c, cudaMemcpyAsync(out_depth, c->d_zbuf, px * sizeof(float), cudaMemcpyDeviceToHost, c->stream), "depth download"));
+  if (out_rgba || out_depth) RR_TRY_RC(rr::check(c, cudaStreamSynchronize(c->stream), "composite sync"));
+  return RR_OK;
+}
+
 // The whole volume, assembled from the slices each member owns. out: float32 [Z][Y][X], as rr_download_tsdf returns it
 // (half2 voxels: the tsdf half widened to float).
 int rr_group_download_tsdf(rr_group* g, float* out) {

@@ -94,6 +94,8 @@ def lib():
     L.rr_get_stage_stats.argtypes = [vp, C.c_char_p, f32, u32]
     L.rr_integrator_info.argtypes = [vp, u32]
     L.rr_integrator_profile.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.rr_view_export.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.rr_composite_peers.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, f32, f32]
     # one process, several GPUs
     L.rr_group_create.argtypes = [C.POINTER(vp), i32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     L.rr_group_destroy.argtypes = [vp]
@@ -346,6 +348,27 @@ class Fusion:
         rgba = np.zeros((height, width, 4), np.float32)
         depth = np.zeros((height, width), np.float32)
         self._ck(self.L.rr_composite(self.h, d_records_ptr, n_parts, width, height, _f32(rgba), _f32(depth)))
+        return rgba, depth
+
+    def view_export(self, width, height):
+        """rr_view_export: 256 bytes of CUDA IPC handles of this context's view images (for another process' composite_peers)."""
+        buf = (C.c_ubyte * 256)()
+        self._ck(self.L.rr_view_export(self.h, int(width), int(height), C.cast(buf, C.c_void_p)))
+        return bytes(buf)
+
+    def composite_peers(self, peer_handles, width, height, download=True):
+        """rr_composite_peers: this context's view (marched last) composited with the views behind `peer_handles` (a list of
+        view_export blobs of OTHER processes), in place; returns (rgba, depth) when download."""
+        blob = b"".join(peer_handles)
+        buf = (C.c_ubyte * max(1, len(blob))).from_buffer_copy(blob) if blob else None
+        self._vw, self._vh = int(width), int(height)
+        ptr = C.cast(buf, C.c_void_p) if buf is not None else None
+        if not download:
+            self._ck(self.L.rr_composite_peers(self.h, ptr, len(peer_handles), width, height, None, None))
+            return None
+        rgba = np.zeros((height, width, 4), np.float32)
+        depth = np.zeros((height, width), np.float32)
+        self._ck(self.L.rr_composite_peers(self.h, ptr, len(peer_handles), width, height, _f32(rgba), _f32(depth)))
         return rgba, depth
 
     def frame(self, filter_textures=True, use_processed_depth=True, refine=True, sync_bricks=False):
