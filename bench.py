@@ -298,7 +298,7 @@ def integrate_kernel_name(bricks, info):
     return "k_integrate_fused (clear + occupied-brick integration, direct gathers)"
 
 
-def sub_record(torch, dist, rank, world, local, what, n_sensors, res, bricks, fmt, steps, scenes=None, inv=None, voxel=None):
+def sub_record(torch, dist, rank, world, local, what, n_sensors, res, bricks, fmt, steps, scenes=None, inv=None, voxel=None, view=False):
     """A secondary configuration through the same code path: frames device-resident (broadcast from rank 0 for N > 1),
     one rr_fuse_frame per step, CUDA events over `steps` steps after 5 warm-up steps, stage timers in a second pass."""
     if scenes is None:
@@ -318,8 +318,43 @@ def sub_record(torch, dist, rank, world, local, what, n_sensors, res, bricks, fm
            "roofline": {"achieved": round(achieved, 1), "frac": round(achieved / peak, 4), "algorithmic_bytes_per_launch": int(abytes),
                         "kernel": integrate_kernel_name(bricks, info)},
            "occupied_bricks": n_occ, "slabs": rig.slab_how if world > 1 else None}
+    if view and world == 1:
+        from rrpy import synth
+        mv, pr = synth.look_at((1.7, 1.6, 2.3), (0.0, 1.1, 0.0)), synth.perspective(50.0, VW / VH, 0.1, 10.0)
+        for _ in range(3):
+            rig.fu.raymarch(mv, pr, VW, VH, shade_mode=1, download=False); rig.fu.fill_colors(download=False)
+        rig.fu.synchronize()
+        v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        v0.record(rig.stream)
+        for _ in range(10):
+            rig.fu.raymarch(mv, pr, VW, VH, shade_mode=1, download=False); rig.fu.fill_colors(download=False)
+        v1.record(rig.stream)
+        rig.fu.synchronize()
+        out["view_ms"] = round(v0.elapsed_time(v1) / 10, 4)
+        out["view"] = f"raymarch {VW}x{VH} (shaded, brick space skipping) + colour hole filling"
     rig.close()
     return out
+
+
+def invert_record(torch):
+    """BASELINE.json configs[0]: CalibrationInverter on one synthetic 128x128x256 cv_xyz -> inverse volume at ceil(bbox / 0.007 m)
+    (exact 8-NN + inverse-distance weighting + frustum cull, k_invert). GPU time per volume from the context's stage timer;
+    parity of this size against the oracle port is tests/test_calib_invert_gpu.py, the CPU timing tools/bench_invert.py."""
+    from rrpy import capi, synth
+    sc = synth.make_scene(N=1, W=W, H=H, CW=CW, CH=CH, cv_res=CV_RES)
+    res = tuple(int(np.ceil((sc.bbox_max[i] - sc.bbox_min[i]) / np.float32(0.007))) for i in range(3))
+    fu = capi.Fusion(1, W, H, CW, CH)
+    capi.load_scene(fu, sc)
+    fu.set_timing(2)
+    times = []
+    for _ in range(4):
+        fu.calib_invert(0, res, download=False)
+        times.append(fu.stage_ms("calib_invert"))
+    fu.close()
+    ms = float(np.median(times[1:]))
+    nvox = res[0] * res[1] * res[2]
+    return {"what": "BASELINE.json configs[0]: calib_inverter, one 128x128x256 calibration volume -> inverse volume (exact 8-NN + IDW + frustum cull)",
+            "out_res": list(res), "ms_per_volume": round(ms, 3), "mvoxel_per_s": round(nvox / ms / 1e3, 1)}
 
 
 def verify_against_single_context(torch, dist, rig, scenes, inv, voxel, bricks, mv, pr, view_once):
@@ -529,7 +564,14 @@ def run_ours(args):
     rig.close()
 
     # ---- sub-records through the same code (device-resident frames, rr_fuse_frame): dense mode and BASELINE config 5 -----
-    dense = config5 = None
+    dense = config5 = config1 = config2 = config3 = None
+    if args.subrecords and world == 1:
+        # the other BASELINE.json configurations, single GPU (their parity tests are in tests/; bench lines of the same in tools/)
+        config1 = invert_record(torch)
+        config2 = sub_record(torch, dist, rank, world, local, "BASELINE.json configs[1]: 1 sensor 512x424, 128^3 R32F TSDF, occupied bricks, + raymarch",
+                             1, 128, True, capi.VOXELS_F32, 50, view=True)
+        config3 = sub_record(torch, dist, rank, world, local, "BASELINE.json configs[2]: 4 sensors, 256^3 R32F TSDF, brick culling, + raymarch and colour fill",
+                             4, 256, True, capi.VOXELS_F32, 50, view=True)
     if args.subrecords:
         if bricks:
             dense = sub_record(torch, dist, rank, world, local, "same workload with setUseBricks(false): every voxel x every sensor",
@@ -568,7 +610,7 @@ def run_ours(args):
                      "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                      "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": int(abytes), "peak_source": peak_src,
                      "algorithmic_bytes": "SURVEY.md 8d: 4*XYZ + 4*V_occ + 16*covered_inverse_voxels*N + 16*pixels*N + 4*bricks"},
-        "dense": dense, "config5": config5,
+        "dense": dense, "config5": config5, "config1": config1, "config2": config2, "config3": config3,
         "clocks": clocks,
     }
     if world > 1:

@@ -514,16 +514,11 @@ __device__ __forceinline__ void classify_item(const ClassifyParams& q, uint32_t 
     const float2* img = q.pairs + ((size_t)s * q.H2 + (f.x >> 16)) * q.pair_pitch + (f.x & 0xffffu) + (f.y & 127u);
     float dlo = inf, dhi = -inf;
     bool ok = true;
-    // lanes walk the rectangle row-major, 32 pixels apart; four loads in flight per lane
-    int ty = lane / rw, tx = lane - ty * rw;
-    const int n = rw * rh, dy = 32 / rw, dx = 32 - dy * rw;
-#pragma unroll 4
-    for (int i = lane; i < n; i += 32) {
+    for (int i = lane; i < rw * rh; i += 32) {
+      const int ty = i / rw, tx = i - ty * rw;
       const float2 t = __ldg(img + (size_t)ty * q.pair_pitch + tx);
-      ok = ok & ((int)__float_as_uint(t.y) < 0) & (fabsf(t.x) < inf);
+      ok = ok && ((int)__float_as_uint(t.y) < 0) && (fabsf(t.x) < inf);
       dlo = fminf(dlo, t.x); dhi = fmaxf(dhi, t.x);
-      tx += dx; ty += dy;
-      if (tx >= rw) { tx -= rw; ++ty; }
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
