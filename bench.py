@@ -24,7 +24,8 @@ import time
 
 import numpy as np
 
-os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+# rank 0 prints ONE JSON line on stdout: NCCL's own output (the version banner at NCCL_DEBUG >= VERSION, warnings) goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "rgbd-recon_b200"))
@@ -393,8 +394,6 @@ def verify_against_single_context(torch, dist, rig, scenes, inv, voxel, bricks, 
 
 def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if world > 1 and os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"            # keeps NCCL's version banner off stdout: rank 0 prints exactly one JSON line
     import torch
     from rrpy import capi, multigpu, synth
     rank = int(os.environ.get("RANK", "0"))
