@@ -24,8 +24,17 @@ import time
 
 import numpy as np
 
-# rank 0 prints ONE JSON line on stdout: NCCL's own output (the version banner at NCCL_DEBUG >= VERSION, warnings) goes to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+_RESULT_FD = None      # the process' real stdout once main() has pointed fd 1 at stderr (see emit)
+
+
+def emit(record):
+    """The ONE JSON line of the contract. Libraries print to the C-level stdout on their own (NCCL's version banner on the first
+    collective), so main() points fd 1 at stderr for the whole run and the result line alone goes to the real stdout."""
+    line = json.dumps(record) + "\n"
+    if _RESULT_FD is None:
+        sys.stdout.write(line); sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, line.encode())
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "rgbd-recon_b200"))
@@ -652,7 +661,7 @@ def run_ours(args):
     if rank == 0:
         if args.cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(scenes[0], inv, voxel, bricks, budget_s=12.0)
-        print(json.dumps(out), flush=True)
+        emit(out)
 
 
 def cpu_frame(scene, inv, voxel, bricks, threads, int_fraction=1.0):
@@ -763,7 +772,7 @@ def run_reference(args):
                                       f"integration time scaled to all occupied bricks"},
            "e2e": {"value": round(value, 5), "unit": "Gvoxel-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "reference_shaders_on_cpu": shader_harness}
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def main():
@@ -778,6 +787,10 @@ def main():
     ap.add_argument("--clock-ms", type=int, default=100, help="nvidia-smi sampling period during the timed regions (0 = off)")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

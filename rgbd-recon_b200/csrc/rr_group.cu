@@ -123,6 +123,15 @@ int rr_group_create(rr_group** out, const int* devices, int n_devices, int num_s
     }
     cudaGetLastError();
   }
+  // ... and the other way round, so that the members' copies of a staged frame set go device to device over NVLink
+  // (without peer access cudaMemcpyPeerAsync stages through host memory)
+  for (int i = 1; i < n_devices; ++i) {
+    if (devices[i] == devices[0]) continue;
+    cudaSetDevice(devices[i]);
+    int can = 0;
+    if (cudaDeviceCanAccessPeer(&can, devices[i], devices[0]) == cudaSuccess && can) cudaDeviceEnablePeerAccess(devices[0], 0);
+    cudaGetLastError();
+  }
   g->ev_view.assign(n_devices, nullptr);
   for (int i = 0; i < n_devices; ++i) {
     cudaSetDevice(devices[i]);
