@@ -153,4 +153,24 @@ __device__ __forceinline__ float3 tex2d_rgb8(const uint8_t* __restrict__ img, in
   return make_float3(o[0], o[1], o[2]);
 }
 
+// The same fetch with the twelve c/255 divisions read from a 256-entry table the caller built with that very division
+// (lut[c] = (float)c / 255.0f, IEEE: the quotient is the same number wherever it is computed): identical results, a
+// shared-memory load instead of a ~10-instruction division per tap.
+__device__ __forceinline__ float3 tex2d_rgb8_lut(const uint8_t* __restrict__ img, int W, int H, float s, float t, const float* __restrict__ lut) {
+  int x0, x1, y0, y1; float a, b;
+  lin_coord(s, W, x0, x1, a);
+  lin_coord(t, H, y0, y1, b);
+  const uint8_t* p00 = img + ((size_t)y0 * W + x0) * 3;
+  const uint8_t* p10 = img + ((size_t)y0 * W + x1) * 3;
+  const uint8_t* p01 = img + ((size_t)y1 * W + x0) * 3;
+  const uint8_t* p11 = img + ((size_t)y1 * W + x1) * 3;
+  float o[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float v00 = lut[__ldg(p00 + c)], v10 = lut[__ldg(p10 + c)], v01 = lut[__ldg(p01 + c)], v11 = lut[__ldg(p11 + c)];
+    o[c] = lerpf(lerpf(v00, v10, a), lerpf(v01, v11, a), b);
+  }
+  return make_float3(o[0], o[1], o[2]);
+}
+
 }  // namespace rr

@@ -14,6 +14,7 @@ namespace rr {
 #define KS 6
 #define SM_W (TILE_X + 2 * KS)
 #define SM_H (TILE_Y + 2 * KS)
+static_assert(TILE_X * TILE_Y == 256, "k_bilateral fills its 256-entry byte table with one entry per thread");
 
 // ------------------------------------------------------------------------------------------------ pre_morph
 // glsl/pre_morph.fs:73-112 dilate(kernel 1), main mode 0; mode 1 is a copy and is folded away.
@@ -85,10 +86,12 @@ __global__ void __launch_bounds__(256) k_bilateral(const float* __restrict__ dep
   // (is_outside, pre_depth.fs:40-42) is stored as +inf: |inf - depth| = inf exceeds every finite range threshold, so the
   // single range comparison below also rejects it. The centre depth itself is kept in a register, untouched.
   __shared__ float tile[SM_H][SM_W];
+  __shared__ float byte_lut[256];          // c / 255 of the colour fetch (tex2d_rgb8_lut)
   const int layer = blockIdx.z;
   const float* img = depth_in + (size_t)layer * W * H;
   const int bx = blockIdx.x * TILE_X, by = blockIdx.y * TILE_Y;
   const int tid = threadIdx.y * TILE_X + threadIdx.x;
+  byte_lut[tid] = (float)tid / 255.0f;     // TILE_X * TILE_Y == 256 threads
   const bool compress = dp.compress[layer] != 0;
   const float cv_min = st.dmin[layer], cv_max = st.dmax[layer];
   auto decode = [&](float d) -> float {
@@ -111,7 +114,7 @@ __global__ void __launch_bounds__(256) k_bilateral(const float* __restrict__ dep
                       pos_world.x <= dp.bmax[0] && pos_world.y <= dp.bmax[1] && pos_world.z <= dp.bmax[2];
   const float zc = (depth_norm <= 0.0f || depth_norm >= 1.0f) ? 1.0f : depth_norm;
   const float2 cc = tex3d_uv(st.uv[layer], st.cx[layer], st.cy[layer], st.cz[layer], tcx, tcy, zc);
-  const float3 lab = rgb_to_lab(tex2d_rgb8(color + (size_t)layer * CW * CH * 3, CW, CH, cc.x, cc.y));
+  const float3 lab = rgb_to_lab(tex2d_rgb8_lut(color + (size_t)layer * CW * CH * 3, CW, CH, cc.x, cc.y, byte_lut));
   const size_t o = (size_t)layer * W * H + (size_t)py * W + px;
   out_lab[o] = make_float4(lab.x, lab.y, lab.z, 0.0f);
   if (!in_box) { out_depth[o] = make_float2(0.0f, 0.0f); return; }
