@@ -1,8 +1,8 @@
 // rr_group: one process, several GPUs. The reference has no multi-GPU path; its single GL context does the
 // whole of kinect_client.cpp:572-617 per frame. Here the TSDF volume is split into contiguous z-slabs, one rr_ctx per device:
-//   * a frame set goes host -> the ingest device (member 0) -> every other member by peer copies over NVLink
-//     (cudaMemcpyPeerAsync on the members' copy streams, double-buffered like rr_stage_frames: the copies of frame set i+1
-//     overlap the kernels of frame set i);
+//   * a frame set goes host -> the ingest device (member 0) -> every other member by peer copies over NVLink, down a binary
+//     tree of members (cudaMemcpyPeerAsync on the members' copy streams, double-buffered like rr_stage_frames: the copies
+//     of frame set i+1 overlap the kernels of frame set i);
 //   * pre-processing and the brick tables are replicated (identical on every member, no exchange), integration is per slab
 //     (plus a halo recomputed locally, rr_integrate);
 //   * a view is marched per slab; ONE kernel on the display device (member 0) composites it, reading the other members'
@@ -123,13 +123,18 @@ int rr_group_create(rr_group** out, const int* devices, int n_devices, int num_s
     }
     cudaGetLastError();
   }
-  // ... and the other way round, so that the members' copies of a staged frame set go device to device over NVLink
-  // (without peer access cudaMemcpyPeerAsync stages through host memory)
+  // Frame sets travel down a binary tree of members (member i copies from member (i - 1) / 2, so no device serves more than
+  // two copies of a set): peer access in both directions along every edge, so that the copies go device to device over
+  // NVLink (without peer access cudaMemcpyPeerAsync stages through host memory)
   for (int i = 1; i < n_devices; ++i) {
-    if (devices[i] == devices[0]) continue;
-    cudaSetDevice(devices[i]);
+    const int a = devices[i], b = devices[(i - 1) / 2];
+    if (a == b) continue;
     int can = 0;
-    if (cudaDeviceCanAccessPeer(&can, devices[i], devices[0]) == cudaSuccess && can) cudaDeviceEnablePeerAccess(devices[0], 0);
+    cudaSetDevice(a);
+    if (cudaDeviceCanAccessPeer(&can, a, b) == cudaSuccess && can) cudaDeviceEnablePeerAccess(b, 0);
+    cudaGetLastError();
+    cudaSetDevice(b);
+    if (cudaDeviceCanAccessPeer(&can, b, a) == cudaSuccess && can) cudaDeviceEnablePeerAccess(a, 0);
     cudaGetLastError();
   }
   g->ev_view.assign(n_devices, nullptr);
@@ -295,8 +300,9 @@ int rr_group_stage_frames(rr_group* g, const void* color, size_t color_bytes, co
   for (size_t i = 1; i < g->m.size(); ++i) RR_G_TRY(g, cudaStreamWaitEvent(c0->copy_stream, g->m[i]->ev_staged, 0));     // no-op until first recorded
   int rc = rr_stage_frames(c0, color, color_bytes, depth, depth_bytes);
   if (rc != RR_OK) return member_fail(g, 0, rc);
+  // down the tree: a member's copy waits for its parent's (ev_staged of the parent), ascending order issues parents first
   for (size_t i = 1; i < g->m.size(); ++i) {
-    rc = stage_from_peer(g, g->m[i], c0, color != nullptr, color_bytes, depth_bytes);
+    rc = stage_from_peer(g, g->m[i], g->m[(i - 1) / 2], color != nullptr, color_bytes, depth_bytes);
     if (rc != RR_OK) return rc;
   }
   return RR_OK;

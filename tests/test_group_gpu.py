@@ -35,7 +35,7 @@ def _single(sc, inv, voxel, mv, pr, vw, vh, frames):
     return out
 
 
-@pytest.mark.parametrize("n", [1, 2, 3])
+@pytest.mark.parametrize("n", [1, 2, 3, 5])
 def test_group_equals_single_context(n):
     from rrpy import capi, synth
     sc = synth.make_scene(N=2, W=128, H=106, CW=160, CH=136, cv_res=(32, 32, 64))
@@ -113,7 +113,7 @@ def test_group_pipelined_staging_and_compressed_streams():
     fu.configure(limit=0.01, voxel_size=0.02, brick_size=0.1, min_voxels=10, use_bricks=True)
     want = volumes(fu)
     fu.close()
-    g = capi.Group(_devices(2), sc.N, sc.W, sc.H, sc.CW, sc.CH)
+    g = capi.Group(_devices(4), sc.N, sc.W, sc.H, sc.CW, sc.CH)          # four members: the frame sets go down a two-level tree
     g.set_bbox(sc.bbox_min, sc.bbox_max)
     for i in range(sc.N):
         g.calib_upload(i, sc.cv_xyz[i], sc.cv_uv[i])
