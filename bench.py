@@ -170,7 +170,8 @@ class Rig:
             fu.upload_frames(scenes[0].color, scenes[0].depth)
             fu.bricks_clear(); fu.preprocess(); fu.bricks_update(sync=True)
             _, occ0 = fu.download_bricks()
-            self.slabs = multigpu.balanced_slabs(world, res, res * res, fu.brick_ranges(), occ0)
+            # cost of an occupied voxel against a cleared one: 45 at four sensors, proportional to the sensor count
+            self.slabs = multigpu.balanced_slabs(world, res, res * res, fu.brick_ranges(), occ0, compute_to_fill=45.0 * n_sensors / 4.0)
             self.z0, self.z1 = self.slabs[rank]
             self.slab_how = f"z-slabs balanced on occupied-brick cost: {self.slabs}"
         elif world > 1:
@@ -320,12 +321,14 @@ def sub_record(torch, dist, rank, world, local, what, n_sensors, res, bricks, fm
     int_ms, int_n = rig.fu.stage_stats("2integrate")
     pre_ms, pre_n = rig.fu.stage_stats("1preprocess")
     int_avg = int_ms / max(1, int_n)
+    int_slowest = rig.max_over_ranks(int_avg)          # the slab that gates the step (stage timers are per rank)
     n_occ, ratio, vox, nbricks = rig.occupancy()
     abytes, achieved, peak, _ = rig.roofline(int_avg, vox, nbricks)
     info = rig.fu.integrator_info()
     out = {"what": what, "value": round(res ** 3 / ms / 1e6, 3), "unit": "Gvoxel-updates/s", "frames_per_s": round(1e3 / ms, 2),
            "ms_per_step": round(ms, 5), "steps": steps,
-           "stages_ms": {"1preprocess": round(pre_ms / max(1, pre_n), 5), "2integrate": round(int_avg, 5)},
+           "stages_ms": {"1preprocess": round(pre_ms / max(1, pre_n), 5), "2integrate": round(int_avg, 5),
+                         **({"2integrate_slowest_rank": round(int_slowest, 5)} if world > 1 else {})},
            "roofline": {"achieved": round(achieved, 1), "frac": round(achieved / peak, 4), "algorithmic_bytes_per_launch": int(abytes),
                         "kernel": integrate_kernel_name(bricks, info)},
            "occupied_bricks": n_occ, "slabs": rig.slab_how if world > 1 else None}
@@ -408,6 +411,8 @@ def run_ours(args):
     from rrpy import capi, multigpu, synth
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    for kv in filter(None, args.tune.split(",")):
+        capi.set_tunable(kv.split("=")[0], int(kv.split("=")[1]))
     dist = None
     if world > 1:
         import torch.distributed as dist_
@@ -434,6 +439,7 @@ def run_ours(args):
     ms_stage_pass = rig.timed(rig.step_device, stage_steps, 3, with_stage_timers=True)
     int_ms, int_n = fu.stage_stats("2integrate")
     pre_ms, pre_n = fu.stage_stats("1preprocess")
+    int_slowest = rig.max_over_ranks(int_ms / max(1, int_n))      # the slab that gates the step (stage timers are per rank)
 
     # ---- end to end from pinned host buffers ------------------------------------------------------------------------
     e2e_warm = max(50, args.warmup)                 # >= 50 untimed steps: lets the PCIe link leave its idle state
@@ -637,6 +643,7 @@ def run_ours(args):
         "occupied_voxel_updates_per_s": round(float(n_occ_vox if bricks else slab_vox) * frames_s, 1),
         "voxel_sensor_evaluations_per_s": round(float(n_occ_vox if bricks else slab_vox) * N_SENSORS * frames_s, 1),
         "stages_ms": {"1preprocess": round(pre_ms / max(1, pre_n), 5), "2integrate": round(int_avg_ms, 5),
+                      **({"2integrate_slowest_rank": round(int_slowest, 5)} if world > 1 else {}),
                       "how": f"CUDA-event stage timers over {stage_steps} further steps of the same loop with direct launches "
                              f"({ms_stage_pass / stage_steps:.5f} ms/step); `value` is timed with the frame replayed as one CUDA graph"},
         "view": {"ms_per_view": round(view_ms, 4), "resolution": [VW, VH],
@@ -784,6 +791,7 @@ def main():
     ap.add_argument("--mode", default="bricks", choices=["bricks", "dense"])
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--no-subrecords", dest="subrecords", action="store_false", help="skip the dense and config5 sub-records")
+    ap.add_argument("--tune", default="", help="integrator tunables k=v,k=v applied on every rank (A/B measurements; results never depend on them)")
     ap.add_argument("--clock-ms", type=int, default=100, help="nvidia-smi sampling period during the timed regions (0 = off)")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup

@@ -275,7 +275,8 @@ int rr_get_stage_stats(rr_ctx* ctx, const char* name, float* total_ms, uint32_t*
 uint64_t rr_launch_count(const rr_ctx* ctx);
 /* Launch-shape knob of the integrator, process-wide (no reference counterpart; the reference's draw-call structure is
  * fixed). Names: "fused", "zchunk", "fill_rows", "fill_warps", "ctas", "threads", "chunk", "brick_grid",
- * "ldg256", "graph", "staged", "stage_zchunk", "stage_ychunk", "stage_tile", "stage_cwarps", "stage_fill_rows", "stage_bulk_fill", "stage_debug".
+ * "ldg256", "graph", "staged", "stage_zchunk", "stage_ychunk", "stage_tile", "stage_cwarps", "stage_fill_rows", "stage_bulk_fill", "stage_fill_depth",
+ * "stage_tail_cap", "stage_ctas", "stage_fill_lsu", "stage_debug".
  * Results never depend on these. Returns RR_ERR_INVALID for an unknown name. */
 int rr_set_tunable(const char* name, int value);
 /* Which integrator the bricks mode of this context runs and with what geometry (no reference counterpart; diagnostics for

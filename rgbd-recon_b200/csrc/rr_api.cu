@@ -117,6 +117,7 @@ int rr_create(rr_ctx** out, int device, int num_sensors, int depth_w, int depth_
     delete c;
     return RR_ERR_CUDA;
   }
+  if (cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || c->num_sms < 1) c->num_sms = 148;
   const size_t px = (size_t)c->N * c->W * c->H;
   int rc = RR_OK;
   for (int b = 0; b < 2; ++b) {
@@ -924,6 +925,7 @@ int rr_set_tunable(const char* name, int value) {
   else if (n == "stage_fill_depth") t.stage_fill_depth = value;
   else if (n == "stage_fill_lsu") t.stage_fill_lsu = value;
   else if (n == "stage_tail_cap") t.stage_tail_cap = value;
+  else if (n == "stage_ctas") t.stage_ctas = value;
   else if (n == "stage_cwarps") t.stage_cwarps = value;
   else if (n == "stage_bulk_fill") t.stage_bulk_fill = value;
   else return RR_ERR_INVALID;

@@ -69,6 +69,7 @@ struct rr_ctx {
   std::string error;           // text of the last failing call; written under error_mutex (a reader thread may stage frames)
   std::mutex error_mutex;
   uint64_t launches = 0;
+  int num_sms = 148;           // multiprocessors of the device (persistent kernels launch one CTA per SM)
   int timing = 0;              // 0 off, 1 top-level stages, 2 every pass
   std::map<std::string, rr::StageTimer> timers;
 
@@ -211,6 +212,7 @@ struct Tunables {
   int stage_bulk_fill = 4;    // KB of cleared voxels in shared memory, the source of the clear's TMA bulk stores
   int stage_fill_depth = 0;   // bulk-store groups a clear lane may leave pending (-1: unbounded)
  int stage_tail_cap = 2;     // items in flight per CTA towards the end of the item list (0: the ring's capacity throughout)
+  int stage_ctas = 0;         // CTAs of the staged integrator (0: one per SM)
   int stage_fill_lsu = 0;     // 1: rows without occupied bricks are cleared by per-lane stores instead of bulk stores
   int stage_debug = 0;  // measurement only, results are WRONG: bit 0 skips the clear stream, bit 1 the brick evaluation
   unsigned generation = 0;   // bumped by every rr_set_tunable (invalidates captured graphs)

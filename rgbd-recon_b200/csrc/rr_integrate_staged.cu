@@ -579,7 +579,10 @@ static EncodeTiledFn encode_tiled() {
 template <int N, int CWARPS>
 static int launch_staged_n(rr_ctx* c, const StagedParams& sp, int mode) {
   const auto& st = c->sti;
-  const dim3 grd(148, 1, 1), blk(StagedShape<CWARPS>::kThreads, 1, 1);
+  // one persistent CTA per SM; tunable stage_ctas leaves SMs free (a collective library's kernels cannot share an SM with
+  // a CTA that holds its whole register file and shared memory)
+  const int ctas = tunables().stage_ctas > 0 ? std::min(tunables().stage_ctas, c->num_sms) : c->num_sms;
+  const dim3 grd((unsigned)std::max(1, ctas), 1, 1), blk(StagedShape<CWARPS>::kThreads, 1, 1);
   auto go = [&](auto kern) -> int {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st.smem_bytes);
     if (e != cudaSuccess) return check(c, e, "k_integrate_staged shared memory");
