@@ -171,7 +171,8 @@ class Rig:
             fu.bricks_clear(); fu.preprocess(); fu.bricks_update(sync=True)
             _, occ0 = fu.download_bricks()
             # cost of an occupied voxel against a cleared one: 45 at four sensors, proportional to the sensor count
-            self.slabs = multigpu.balanced_slabs(world, res, res * res, fu.brick_ranges(), occ0, compute_to_fill=45.0 * n_sensors / 4.0)
+            self.slabs = multigpu.balanced_slabs(world, res, res * res, fu.brick_ranges(), occ0, compute_to_fill=45.0 * n_sensors / 4.0,
+                                                      halo_slices=multigpu.halo(LIMIT, res))
             self.z0, self.z1 = self.slabs[rank]
             self.slab_how = f"z-slabs balanced on occupied-brick cost: {self.slabs}"
         elif world > 1:

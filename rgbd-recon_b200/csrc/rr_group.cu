@@ -258,14 +258,34 @@ int rr_group_balance_slabs(rr_group* g, float compute_to_fill) {
   }
   std::vector<double> cum(Z + 1, 0.0);
   for (uint32_t z = 0; z < Z; ++z) cum[z + 1] = cum[z] + cost[z];
-  std::vector<uint32_t> b(n + 1, 0);
-  for (uint32_t r = 1; r < n; ++r) {
-    const double target = cum[Z] * r / n;
-    uint32_t z = (uint32_t)(std::lower_bound(cum.begin(), cum.end(), target) - cum.begin());
-    z = std::min(std::max(z, b[r - 1] + 1), Z - (n - r));          // keep every slab non-empty
-    b[r] = z;
+  // A member also integrates a halo on either side of its slab (rr_integrate), which weighs heavily on thin slabs: the cost
+  // of a slab is the cost of slab + halo, and the boundaries minimise the largest one (bisection on the bound, greedy fill).
+  const uint32_t h = (uint32_t)std::ceil(c0->cfg.limit * (float)Z) + 2u;
+  auto slab_cost = [&](uint32_t z0, uint32_t z1) { return cum[std::min(Z, z1 + h)] - cum[z0 > h ? z0 - h : 0u]; };
+  auto fill = [&](double bound, std::vector<uint32_t>& out) {
+    out.assign(1, 0u);
+    while (out.back() < Z) {
+      if (out.size() > n) return false;
+      const uint32_t z0 = out.back();
+      uint32_t z1 = z0 + 1;
+      while (z1 < Z && slab_cost(z0, z1 + 1) <= bound) ++z1;
+      out.push_back(z1);
+    }
+    return true;
+  };
+  double lo = 0.0, hi = cum[Z];
+  std::vector<uint32_t> b;
+  for (int it = 0; it < 60; ++it) {
+    const double mid = 0.5 * (lo + hi);
+    if (fill(mid, b)) hi = mid; else lo = mid;
   }
-  b[n] = Z;
+  fill(hi, b);
+  while (b.size() - 1 < n) {             // fewer slabs than members (tiny volumes): split the thickest
+    size_t k = 0;
+    for (size_t i = 0; i + 1 < b.size(); ++i) if (b[i + 1] - b[i] > b[k + 1] - b[k]) k = i;
+    if (b[k + 1] - b[k] < 2) return gfail(g, RR_ERR_INVALID, "rr_group_balance_slabs: fewer z slices than devices");
+    b.insert(b.begin() + (long)k + 1, (b[k] + b[k + 1]) / 2);
+  }
   return rr_group_set_slabs(g, b.data());
 }
 
