@@ -167,6 +167,20 @@ int rr_bricks_count(rr_ctx* ctx, uint32_t* out_num_occupied, float* out_ratio);
  * out_rgba float32 [h][w][4], out_depth float32 [h][w] (gl_FragDepth, 1.0 where no surface), both host, may be NULL. */
 int rr_raymarch(rr_ctx* ctx, const rr_view* view, float* out_rgba, float* out_depth);
 
+/* The point-drawing consumers of the pre-processed maps, without a rasteriser: one thread per vertex splats
+ * a depth-tested square (64-bit atomicMin of depth | vertex id: the first drawn fragment wins depth ties, as GL_LESS), one
+ * thread per pixel shades the winner. Both write the context's view images like rr_raymarch (rgba float32 [h][w][4] with
+ * alpha 1 on covered pixels and all zeros elsewhere; depth float32 [h][w], 1.0 where nothing was drawn).
+ *   rr_draw_points  ReconPoints::draw (recon_points.cpp:71-111; glsl/points.vs, points.gs, points.fs): every depth pixel of
+ *                   every sensor (the maps of the last rr_preprocess) as a square of (shade mode 3: 4, else 10) / |pos_eye|
+ *                   pixels, shaded from the sensor's colour and normal maps (rr_view.shade_mode as in rr_raymarch).
+ *   rr_draw_calibs  ReconCalibs::draw (recon_calibs.cpp:56-66; glsl/calib_vis.vs, calib_vis.fs; VolumeSampler::sample): every
+ *                   voxel centre of the inverse-volume grid as a one-pixel point coloured by the TSDF there (red outside,
+ *                   green inside, blue at >= limit, nothing at <= -limit). active_kinect only selects lookups whose results
+ *                   the shader never uses; tsdf_limit is ReconCalibs' own limit (setTsdfLimit, default 0.01). */
+int rr_draw_points(rr_ctx* ctx, const rr_view* view, float* out_rgba, float* out_depth);
+int rr_draw_calibs(rr_ctx* ctx, const rr_view* view, int active_kinect, float tsdf_limit, float* out_rgba, float* out_depth);
+
 /* ReconIntegration::fillColors (recon_integration.cpp:280-339; on by default, m_fill_holes, :54) + ViewLod
  * (view_lod.cpp:24-61) + glsl/framebuffer_transfer.fs, tsdf_inpaint.fs, tsdf_colorfill.fs: push-pull colour hole filling
  * of the LAST view (rr_raymarch, rr_composite or rr_upload_view): pixels the raymarch hit but could only colour with the

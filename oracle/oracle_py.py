@@ -231,6 +231,43 @@ def raymarch(tsdf, limit, inv, scene, pre, grid, occupied, modelview, projection
     return out
 
 
+def draw_points(scene, pre, modelview, projection, width, height, shade_mode=0):
+    """ReconPoints::draw on the pre-processed maps of `pre` (depth_b, normal). Returns (rgba [h,w,4], depth [h,w])."""
+    L = lib()
+    if not hasattr(L, "_points"):
+        L.ro_draw_points.argtypes = [C.c_int, C.c_int, C.c_int, f32p, f32p, u8p, C.c_int, C.c_int, f32p, f32p, i32p, f32p, f32p, f32p, f32p,
+                                     C.c_int, C.c_int, C.c_int, f32p, f32p]
+        L.ro_draw_calibs.argtypes = [f32p, u32p, i32p, C.c_float, f32p, f32p, f32p, f32p, C.c_int, C.c_int, f32p, f32p]
+        L._points = True
+    X, Y, Z = scene.cv_res
+    N, H, W = pre["quality"].shape
+    rgba, depth = np.zeros((height, width, 4), np.float32), np.zeros((height, width), np.float32)
+    L.ro_draw_points(N, W, H, np.ascontiguousarray(pre["depth_b"], np.float32), np.ascontiguousarray(pre["normal"], np.float32),
+                     np.ascontiguousarray(scene.color), scene.CW, scene.CH, np.ascontiguousarray(scene.cv_xyz, np.float32),
+                     np.ascontiguousarray(scene.cv_uv, np.float32), np.array([X, Y, Z], np.int32), np.ascontiguousarray(scene.bbox_min, np.float32),
+                     np.ascontiguousarray(scene.bbox_max, np.float32), np.ascontiguousarray(modelview, np.float32).reshape(16),
+                     np.ascontiguousarray(projection, np.float32).reshape(16), int(width), int(height), int(shade_mode), rgba, depth)
+    return rgba, depth
+
+
+def draw_calibs(tsdf, inv_res, limit, bbox_min, bbox_max, modelview, projection, width, height):
+    """ReconCalibs::draw: the voxel centres of the inverse-volume grid (inv_res = (IX, IY, IZ)) coloured by the TSDF there."""
+    draw_points.__doc__  # (argtypes are set by the first draw_points / below)
+    L = lib()
+    if not hasattr(L, "_points"):
+        L.ro_draw_points.argtypes = [C.c_int, C.c_int, C.c_int, f32p, f32p, u8p, C.c_int, C.c_int, f32p, f32p, i32p, f32p, f32p, f32p, f32p,
+                                     C.c_int, C.c_int, C.c_int, f32p, f32p]
+        L.ro_draw_calibs.argtypes = [f32p, u32p, i32p, C.c_float, f32p, f32p, f32p, f32p, C.c_int, C.c_int, f32p, f32p]
+        L._points = True
+    res = np.array([tsdf.shape[2], tsdf.shape[1], tsdf.shape[0]], np.uint32)
+    rgba, depth = np.zeros((height, width, 4), np.float32), np.zeros((height, width), np.float32)
+    L.ro_draw_calibs(np.ascontiguousarray(tsdf, np.float32), res, np.array(inv_res, np.int32), np.float32(limit),
+                     np.ascontiguousarray(bbox_min, np.float32), np.ascontiguousarray(bbox_max, np.float32),
+                     np.ascontiguousarray(modelview, np.float32).reshape(16), np.ascontiguousarray(projection, np.float32).reshape(16),
+                     int(width), int(height), rgba, depth)
+    return rgba, depth
+
+
 def raymarch_rays(modelview, projection, bbox_min, bbox_max, width, height, limit):
     """Per pixel the ray's target point in volume space and whether the cube proxy covers the pixel."""
     pts = np.zeros((height, width, 3), np.float32)

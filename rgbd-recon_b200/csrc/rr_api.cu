@@ -177,7 +177,7 @@ void rr_destroy(rr_ctx* c) {
   cudaFree(c->d_pairs);
   cudaFree(c->d_gather); cudaFree(c->d_flags); cudaFree(c->d_ranges); cudaFree(c->d_counters); cudaFree(c->d_occupied);
   cudaFree(c->d_num_occ); cudaFree(c->d_work); cudaFree(c->d_ztab); cudaFree(c->d_rowmask); cudaFree(c->d_rowany); cudaFree(c->d_cand_y); cudaFree(c->d_cand_z); cudaFree(c->d_near_occ); cudaFree(c->d_occ_mask); cudaFree(c->d_pos); cudaFree(c->d_step); cudaFree(c->d_tsdf); cudaFree(c->d_weight);
-  cudaFree(c->d_rgba); cudaFree(c->d_zbuf); cudaFree(c->d_nsamples);
+  cudaFree(c->d_rgba); cudaFree(c->d_zbuf); cudaFree(c->d_nsamples); cudaFree(c->d_point_keys);
   cudaFree(c->d_fill_fc); cudaFree(c->d_fill_fd); cudaFree(c->d_fill_sc); cudaFree(c->d_fill_sd); cudaFree(c->d_filled);
   if (c->h_num_occ) cudaFreeHost(c->h_num_occ);
   for (auto& kv : c->timers) {
@@ -613,6 +613,7 @@ int ensure_view(rr_ctx* c, int w, int h) {
   RR_TRY(dev_alloc(c, &c->d_nsamples, (size_t)w * h, "view samples"));
   RR_TRY(dev_alloc(c, &c->d_pos, (size_t)w * h, "view positions"));
   RR_TRY(dev_alloc(c, &c->d_step, (size_t)w * h, "view steps"));
+  RR_TRY(dev_alloc(c, &c->d_point_keys, (size_t)w * h, "point keys"));
   c->view_w = w; c->view_h = h;
   return RR_OK;
 }
@@ -630,6 +631,33 @@ int rr_raymarch(rr_ctx* c, const rr_view* view, float* out_rgba, float* out_dept
   if (out_depth) RR_TRY(check(c, cudaMemcpyAsync(out_depth, c->d_zbuf, (size_t)w * h * sizeof(float), cudaMemcpyDeviceToHost, c->stream), "depth download"));
   if (out_rgba || out_depth) RR_TRY(check(c, cudaStreamSynchronize(c->stream), "raymarch sync"));
   return RR_OK;
+}
+
+static int draw_points_common(rr_ctx* c, const rr_view* view, int mode, float limit, float* out_rgba, float* out_depth, const char* who) {
+  RR_REQUIRE(c, view, "draw points: null view");
+  RR_REQUIRE(c, view->viewport[2] > 0 && view->viewport[3] > 0, "draw points: empty viewport");
+  RR_SET_DEVICE(c);
+  const int w = view->viewport[2], h = view->viewport[3];
+  RR_TRY(ensure_view(c, w, h));
+  RR_TRY(launch_draw_points(c, view, mode, limit));
+  if (out_rgba) RR_TRY(check(c, cudaMemcpyAsync(out_rgba, c->d_rgba, (size_t)w * h * sizeof(float4), cudaMemcpyDeviceToHost, c->stream), who));
+  if (out_depth) RR_TRY(check(c, cudaMemcpyAsync(out_depth, c->d_zbuf, (size_t)w * h * sizeof(float), cudaMemcpyDeviceToHost, c->stream), who));
+  if (out_rgba || out_depth) RR_TRY(check(c, cudaStreamSynchronize(c->stream), who));
+  return RR_OK;
+}
+
+int rr_draw_points(rr_ctx* c, const rr_view* view, float* out_rgba, float* out_depth) {
+  if (!c) return RR_ERR_INVALID;
+  for (int i = 0; i < c->N; ++i) RR_REQUIRE(c, c->have_calib[i], "rr_draw_points: upload every sensor's calibration volumes first");
+  return draw_points_common(c, view, 0, 0.0f, out_rgba, out_depth, "rr_draw_points");
+}
+
+int rr_draw_calibs(rr_ctx* c, const rr_view* view, int active_kinect, float tsdf_limit, float* out_rgba, float* out_depth) {
+  if (!c) return RR_ERR_INVALID;
+  RR_TRY(require_ready(c, true));
+  RR_REQUIRE(c, active_kinect >= 0 && active_kinect < c->N, "rr_draw_calibs: no such sensor");
+  RR_REQUIRE(c, tsdf_limit > 0.0f, "rr_draw_calibs: the limit must be positive");
+  return draw_points_common(c, view, 1, tsdf_limit, out_rgba, out_depth, "rr_draw_calibs");
 }
 
 int rr_fill_colors(rr_ctx* c, float* out_rgba) {

@@ -181,6 +181,7 @@ struct rr_ctx {
   float* d_nsamples = nullptr;
   float4* d_pos = nullptr;         // hit position in volume space (w = 1 on a hit)
   uint32_t* d_step = nullptr;      // step index of the hit, 0xFFFFFFFF = none (multi-GPU compositing key)
+  unsigned long long* d_point_keys = nullptr;   // rr_draw_points / rr_draw_calibs: per pixel (depth bits << 32 | vertex id), atomicMin
 
   // colour hole filling (rr_colorfill.cu): atlas right of column W, squeezed copy, filled colour
   int fill_w = 0, fill_h = 0;
@@ -236,6 +237,7 @@ int launch_composite(rr_ctx* c, const float4* d_rec, int n_parts);
 int launch_partial_keys(rr_ctx* c, const float4* d_rec, int rank, long long* d_keys);
 int launch_partial_keep(rr_ctx* c, float4* d_rec, const long long* d_keys_min, int rank);
 int launch_fill_colors(rr_ctx* c);
+int launch_draw_points(rr_ctx* c, const rr_view* v, int mode, float calib_limit);   // rr_points.cu
 int launch_unpack_frames(rr_ctx* c, int slot);
 int launch_calib_invert(rr_ctx* c, int sensor, const uint32_t out_res[3], float4* d_out);
 int staged_prepare(rr_ctx* c);        // (re)builds the staged integrator's tables when dirty; RR_OK also when it declines

@@ -359,6 +359,16 @@ void ReconIntegration::drawF() {
   Reconstruction::drawF();
   if (m_fill_holes) gk(rr_group_fill_colors(grp(), m_rgba.data()), "rr_fill_colors");
 }
+void ReconPoints::draw() {                                   // recon_points.cpp:71-111
+  const std::size_t n = (std::size_t)m_view.viewport[2] * m_view.viewport[3];
+  m_rgba.resize(n * 4); m_depth.resize(n);
+  ck(rr_draw_points(ctx(), &m_view, m_rgba.data(), m_depth.data()), "rr_draw_points");
+}
+void ReconCalibs::draw() {                                   // recon_calibs.cpp:56-66
+  const std::size_t n = (std::size_t)m_view.viewport[2] * m_view.viewport[3];
+  m_rgba.resize(n * 4); m_depth.resize(n);
+  ck(rr_draw_calibs(ctx(), &m_view, (int)m_active_kinect, m_tsdf_limit, m_rgba.data(), m_depth.data()), "rr_draw_calibs");
+}
 void ReconIntegration::downloadTsdf(std::vector<float>& out) const {
   const glm::uvec3 r = volumeResolution();
   out.resize((std::size_t)r.x * r.y * r.z);

@@ -294,7 +294,6 @@ class ReconIntegration : public Reconstruction {
   void setColorFilling(bool active) { m_fill_holes = active; }
   void setUseBricks(bool active);
   void setSpaceSkip(bool active);
-  void setDrawBricks(bool active) { m_draw_bricks = active; }
   void setVoxelSize(float size);
   void setTsdfLimit(float limit);
   void setBrickSize(float size);
@@ -313,8 +312,37 @@ class ReconIntegration : public Reconstruction {
  private:
   void configure();
   rr_config m_cfg;
-  bool m_fill_holes = true, m_draw_bricks = false;
+  bool m_fill_holes = true;
   float m_ratio_occupied = 0.0f;
+  std::vector<float> m_rgba, m_depth;
+};
+
+// ---- framework/reconstruction/recon_points.hpp: every depth pixel of every sensor as a shaded, depth-tested point sprite -----
+// (runs on the first device of the context: the pre-processed maps are replicated on every member)
+class ReconPoints : public Reconstruction {
+ public:
+  ReconPoints(CalibrationFiles const& cfs, CalibVolumes const* cv, gloost::BoundingBox const& bbox) : Reconstruction(cfs, cv, bbox) {}
+  void draw() override;
+  void setShadeMode(int mode) { m_view.shade_mode = mode; }
+  std::vector<float> const& colorImage() const { return m_rgba; }
+  std::vector<float> const& depthImage() const { return m_depth; }
+ private:
+  std::vector<float> m_rgba, m_depth;
+};
+
+// ---- framework/reconstruction/recon_calibs.hpp: the inverse-volume grid's voxel centres coloured by the TSDF (debug view) ----
+// Reads the TSDF volume of the first device; with several devices that member holds its own z-slab only.
+class ReconCalibs : public Reconstruction {
+ public:
+  ReconCalibs(CalibrationFiles const& cfs, CalibVolumes const* cv, gloost::BoundingBox const& bbox) : Reconstruction(cfs, cv, bbox) {}
+  void draw() override;
+  void setActiveKinect(unsigned num_kinect) { m_active_kinect = num_kinect; }
+  void setTsdfLimit(float limit) { m_tsdf_limit = limit; }
+  std::vector<float> const& colorImage() const { return m_rgba; }
+  std::vector<float> const& depthImage() const { return m_depth; }
+ private:
+  unsigned m_active_kinect = 0;
+  float m_tsdf_limit = 0.01f;
   std::vector<float> m_rgba, m_depth;
 };
 

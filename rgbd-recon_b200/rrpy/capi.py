@@ -94,6 +94,8 @@ def lib():
     L.rr_get_stage_stats.argtypes = [vp, C.c_char_p, f32, u32]
     L.rr_integrator_info.argtypes = [vp, u32]
     L.rr_integrator_profile.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.rr_draw_points.argtypes = [vp, C.POINTER(View), f32, f32]
+    L.rr_draw_calibs.argtypes = [vp, C.POINTER(View), C.c_int, C.c_float, f32, f32]
     L.rr_view_export.argtypes = [vp, C.c_int, C.c_int, vp]
     L.rr_composite_peers.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, f32, f32]
     # one process, several GPUs
@@ -304,6 +306,22 @@ class Fusion:
         rgba = np.zeros((height, width, 4), np.float32)
         depth = np.zeros((height, width), np.float32)
         self._ck(self.L.rr_raymarch(self.h, C.byref(v), _f32(rgba), _f32(depth)))
+        return rgba, depth
+
+    def draw_points(self, modelview, projection, width, height, shade_mode=0):
+        """ReconPoints::draw (rr_draw_points) of the maps of the last preprocess; returns (rgba, depth)."""
+        v = self._view(modelview, projection, width, height, shade_mode)
+        self._vw, self._vh = int(width), int(height)
+        rgba, depth = np.zeros((height, width, 4), np.float32), np.zeros((height, width), np.float32)
+        self._ck(self.L.rr_draw_points(self.h, C.byref(v), _f32(rgba), _f32(depth)))
+        return rgba, depth
+
+    def draw_calibs(self, modelview, projection, width, height, active_kinect=0, limit=0.01):
+        """ReconCalibs::draw (rr_draw_calibs): the inverse-volume grid's voxel centres coloured by the TSDF; returns (rgba, depth)."""
+        v = self._view(modelview, projection, width, height, 0)
+        self._vw, self._vh = int(width), int(height)
+        rgba, depth = np.zeros((height, width, 4), np.float32), np.zeros((height, width), np.float32)
+        self._ck(self.L.rr_draw_calibs(self.h, C.byref(v), int(active_kinect), float(limit), _f32(rgba), _f32(depth)))
         return rgba, depth
 
     def fill_colors(self, download=True):
