@@ -72,6 +72,7 @@ struct vec4 {
   explicit vec4(float v) : x(v), y(v), z(v), w(v) {}
   template <typename A, typename B, typename C, typename D> vec4(A a_, B b_, C c, D d) : x((float)a_), y((float)b_), z((float)c), w((float)d) {}
   template <typename D> vec4(const vec3& v, D d) : x(v.x), y(v.y), z(v.z), w((float)d) {}
+  template <typename C, typename D> vec4(const vec2& v, C c, D d) : x(v.x), y(v.y), z((float)c), w((float)d) {}
   vec2 xy() const { return vec2(x, y); }
   vec2 rg() const { return vec2(x, y); }
   vec3 xyz() const { return vec3(x, y, z); }
@@ -270,6 +271,8 @@ inline vec4 texture(const sampler2DArray& t, const vec3& p) {
   }
   return vec4(o[0], o[1], o[2], o[3]);
 }
+
+inline vec4 texture2DArray(const sampler2DArray& t, const vec3& p) { return texture(t, p); }     // GL_EXT_texture_array spelling
 
 struct sampler3D {
   const float* f32 = nullptr;

@@ -61,6 +61,32 @@ struct S_bricks_fs {
   bool gl_FrontFacing = true;
 #include "bricks_fs.inc"
 };
+struct S_points_vs {
+  vec4 gl_Position;
+#include "points_vs.inc"
+};
+struct S_points_gs {
+  struct { vec4 gl_Position; } gl_in[1];
+  vec4 gl_Position;
+  float gl_PointSize = 1.0f;
+  int emitted = 0;
+  void EmitVertex() { ++emitted; }
+#include "points_gs.inc"
+};
+struct S_points_fs {
+  vec4 gl_FragCoord;
+  vec2 gl_PointCoord;
+  bool discarded = false;
+#include "points_fs.inc"
+};
+struct S_calib_vis_vs {
+  vec4 gl_Position;
+#include "calib_vis_vs.inc"
+};
+struct S_calib_vis_fs {
+  bool discarded = false;
+#include "calib_vis_fs.inc"
+};
 struct S_framebuffer_transfer {
 #include "framebuffer_transfer.inc"
 };
@@ -500,4 +526,133 @@ void rg_depth_peels(const float* modelview, const float* projection, const float
   }
 }
 
+
+// ---- the point-drawing reconstructions -------------------------------------------------------------------
+// One point through the fixed-function stages between the last vertex-processing stage and the fragment shader, as OpenGL 4.4
+// prescribes them: clip-volume cull of the point's centre (13.5), perspective divide and viewport transform with depth range
+// [0, 1] (13.6), a fragment for every pixel whose centre lies in the half-open square of side max(size, 1) centred at the
+// window position (14.4.1, point sprites; the shaders run with GL_PROGRAM_POINT_SIZE, kinect_client.cpp:260-261). fp64 for
+// the fixed-function arithmetic. `frag(px, py, zw, inv_w, s, t)` runs the fragment shader and returns false on discard;
+// the depth test is GL_LESS in draw order against out_depth.
+}  // extern "C" (a template cannot have C linkage)
+template <typename Frag>
+static void raster_point_gl(const vec4& clip, double size, int vw, int vh, float* out_rgba, float* out_depth, Frag frag) {
+  if (!(clip.w > 0.0f) || !(std::fabs(clip.x) <= clip.w) || !(std::fabs(clip.y) <= clip.w) || !(std::fabs(clip.z) <= clip.w)) return;
+  const double xw = ((double)clip.x / clip.w * 0.5 + 0.5) * vw, yw = ((double)clip.y / clip.w * 0.5 + 0.5) * vh;
+  const float zw = (float)((double)clip.z / clip.w * 0.5 + 0.5);
+  if (!(size >= 1.0)) size = 1.0;
+  const double h = size * 0.5;
+  const int x0 = std::max(0, (int)std::ceil(xw - h - 0.5)), x1 = std::min(vw, (int)std::ceil(xw + h - 0.5));
+  const int y0 = std::max(0, (int)std::ceil(yw - h - 0.5)), y1 = std::min(vh, (int)std::ceil(yw + h - 0.5));
+  for (int y = y0; y < y1; ++y)
+    for (int x = x0; x < x1; ++x) {
+      const size_t o = (size_t)y * vw + x;
+      // point sprite coordinates (14.4.1, upper-left origin): s = 1/2 + (xf + 1/2 - xw) / size, t = 1/2 - (yf + 1/2 - yw) / size
+      const float ps = (float)(0.5 + ((double)x + 0.5 - xw) / size), pt = (float)(0.5 - ((double)y + 0.5 - yw) / size);
+      vec4 color;
+      if (!frag(x, y, zw, 1.0f / clip.w, ps, pt, color)) continue;
+      if (!(zw < out_depth[o])) continue;                           // GL_LESS
+      out_depth[o] = zw;
+      out_rgba[o * 4] = color.x; out_rgba[o * 4 + 1] = color.y; out_rgba[o * 4 + 2] = color.z; out_rgba[o * 4 + 3] = color.w;
+    }
+}
+
+extern "C" {
+// ReconPoints::draw (recon_points.cpp:46-52,71-111) with the reference's points.vs -> points.gs -> rasteriser -> points.fs.
+// uniforms16: gl_ModelViewMatrix, gl_ProjectionMatrix, gl_NormalMatrix, img_to_eye_curr, projection_inv, modelview_inv.
+void rg_draw_points(int N, int W, int H, const float* depth_b, const float* normals, const uint8_t* color, int CW, int CH,
+                    const float* cv_xyz, const float* cv_uv, const int32_t* cv_res, const float* bbox_min, const float* bbox_max,
+                    const float* uniforms16, int vw, int vh, int shade_mode, float* out_rgba, float* out_depth) {
+  for (size_t i = 0; i < (size_t)vw * vh; ++i) { out_rgba[i * 4] = out_rgba[i * 4 + 1] = out_rgba[i * 4 + 2] = out_rgba[i * 4 + 3] = 0.f; out_depth[i] = 1.f; }
+  if (N > 5) return;
+  sampler2DArray col;
+  col.u8 = color; col.W = CW; col.H = CH; col.L = N; col.C = 3; col.linear = true;
+  sampler2DArray d = tex2d(depth_b, W, H, 2, false), nr = tex2d(normals, W, H, 3, true);
+  d.L = nr.L = N;
+  const size_t cv_vox = (size_t)cv_res[0] * cv_res[1] * cv_res[2];
+  S_points_vs vs{};
+  S_points_gs gs{};
+  S_points_fs fs{};
+  vs.kinect_depths = d; vs.kinect_normals = nr;
+  for (int i = 0; i < N; ++i) {
+    vs.cv_xyz[i] = tex3d(cv_xyz + (size_t)i * cv_vox * 3, cv_res[0], cv_res[1], cv_res[2], 3);
+    vs.cv_uv[i] = tex3d(cv_uv + (size_t)i * cv_vox * 2, cv_res[0], cv_res[1], cv_res[2], 2);
+  }
+  vs.gl_ModelViewMatrix = mat4(uniforms16); vs.gl_ProjectionMatrix = mat4(uniforms16 + 16);
+  gs.g_shade_mode = shade_mode;
+  gs.bbox_min = vec3(bbox_min[0], bbox_min[1], bbox_min[2]); gs.bbox_max = vec3(bbox_max[0], bbox_max[1], bbox_max[2]);
+  fs.kinect_colors = col; fs.kinect_normals = nr;
+  fs.gl_ModelViewMatrix = mat4(uniforms16); fs.gl_ProjectionMatrix = mat4(uniforms16 + 16); fs.gl_NormalMatrix = mat4(uniforms16 + 32);
+  fs.img_to_eye_curr = mat4(uniforms16 + 48); fs.projection_inv = mat4(uniforms16 + 64); fs.modelview_inv = mat4(uniforms16 + 80);
+  fs.viewportSizeInv = vec2(1.0f / (float)vw, 1.0f / (float)vh);
+  fs.epsilon = 0.075f;                                               // recon_points.cpp:40
+  fs.g_shade_mode = shade_mode;
+  const float stepX = 1.0f / (float)W, stepY = 1.0f / (float)H;
+  for (int layer = 0; layer < N; ++layer)
+    for (int y = 0; y < H; ++y)
+      for (int x = 0; x < W; ++x) {
+        S_points_vs v(vs);
+        v.layer = (uint)layer;
+        v.in_position = vec2((float)(((double)x + 0.5) * (double)stepX), (float)(((double)y + 0.5) * (double)stepY));
+        v.main();
+        S_points_gs g(gs);
+        g.geo_texcoord[0] = v.geo_texcoord; g.geo_pos_norm[0] = v.geo_pos_norm; g.geo_pos_es[0] = v.geo_pos_es; g.geo_pos_cs[0] = v.geo_pos_cs;
+        g.geo_depth[0] = v.geo_depth; g.geo_quality[0] = 0.0f;         // points.vs never writes geo_quality; points.fs never uses it
+        g.gl_in[0].gl_Position = v.gl_Position;
+        g.main();
+        if (!g.emitted) continue;
+        raster_point_gl(g.gl_Position, (double)g.gl_PointSize, vw, vh, out_rgba, out_depth,
+                        [&](int px, int py, float zw, float inv_w, float ps, float pt, vec4& out) {
+                          S_points_fs f(fs);
+                          f.layer = (uint)layer;
+                          f.pass_texcoord = g.pass_texcoord; f.pass_pos_norm = g.pass_pos_norm; f.pass_pos_es = g.pass_pos_es; f.pass_pos_cs = g.pass_pos_cs;
+                          f.pass_depth = g.pass_depth; f.pass_quality = g.pass_quality; f.pass_glpos = g.pass_glpos;
+                          f.gl_FragCoord = vec4((float)px + 0.5f, (float)py + 0.5f, zw, inv_w);
+                          f.gl_PointCoord = vec2(ps, pt);
+                          f.main();
+                          out = f.gl_FragColor;
+                          return !f.discarded;
+                        });
+      }
+}
+
+// ReconCalibs::draw (recon_calibs.cpp:39-46,56-66) over VolumeSampler's voxel centres (volume_sampler.cpp:14-23) with the
+// reference's calib_vis.vs -> rasteriser -> calib_vis.fs. The vertex shader does not write gl_PointSize: size 1.
+void rg_draw_calibs(const float* tsdf, const uint32_t* res, int N, const float* inv, const int32_t* inv_res, const float* cv_xyz, const int32_t* cv_res,
+                    int layer, float limit, const float* bbox_min, const float* bbox_max, const float* modelview, const float* projection,
+                    int vw, int vh, float* out_rgba, float* out_depth) {
+  for (size_t i = 0; i < (size_t)vw * vh; ++i) { out_rgba[i * 4] = out_rgba[i * 4 + 1] = out_rgba[i * 4 + 2] = out_rgba[i * 4 + 3] = 0.f; out_depth[i] = 1.f; }
+  if (N > 5) return;
+  const size_t inv_vox = (size_t)inv_res[0] * inv_res[1] * inv_res[2], cv_vox = (size_t)cv_res[0] * cv_res[1] * cv_res[2];
+  S_calib_vis_vs vs{};
+  S_calib_vis_fs fs{};
+  for (int i = 0; i < N; ++i) {
+    vs.cv_xyz_inv[i] = tex3d(inv + (size_t)i * inv_vox * 4, inv_res[0], inv_res[1], inv_res[2], 4);
+    fs.cv_xyz_inv[i] = vs.cv_xyz_inv[i];
+    vs.cv_xyz[i] = tex3d(cv_xyz + (size_t)i * cv_vox * 3, cv_res[0], cv_res[1], cv_res[2], 3);
+  }
+  vs.volume_tsdf = tex3d(tsdf, (int)res[0], (int)res[1], (int)res[2], 1);
+  vs.layer = fs.layer = (uint)layer;
+  vs.limit = fs.limit = limit;
+  vs.gl_ModelViewMatrix = mat4(modelview); vs.gl_ProjectionMatrix = mat4(projection);
+  float v2w[16] = {0};
+  v2w[0] = bbox_max[0] - bbox_min[0]; v2w[5] = bbox_max[1] - bbox_min[1]; v2w[10] = bbox_max[2] - bbox_min[2];
+  v2w[12] = bbox_min[0]; v2w[13] = bbox_min[1]; v2w[14] = bbox_min[2]; v2w[15] = 1.0f;
+  vs.vol_to_world = mat4(v2w);
+  const float stepX = 1.0f / (float)inv_res[0], stepY = 1.0f / (float)inv_res[1], stepZ = 1.0f / (float)inv_res[2];
+  for (int z = 0; z < inv_res[2]; ++z)
+    for (int y = 0; y < inv_res[1]; ++y)
+      for (int x = 0; x < inv_res[0]; ++x) {
+        S_calib_vis_vs v(vs);
+        v.in_Position = vec3(((float)x + 0.5f) * stepX, ((float)y + 0.5f) * stepY, ((float)z + 0.5f) * stepZ);
+        v.main();
+        raster_point_gl(v.gl_Position, 1.0, vw, vh, out_rgba, out_depth, [&](int, int, float, float, float, float, vec4& out) {
+          S_calib_vis_fs f(fs);
+          f.geo_pos_view = v.geo_pos_view; f.geo_pos_world = v.geo_pos_world; f.geo_pos_volume = v.geo_pos_volume; f.geo_distance = v.geo_distance;
+          f.main();
+          out = f.gl_FragColor;
+          return !f.discarded;
+        });
+      }
+}
 }  // extern "C"

@@ -10,7 +10,7 @@ Writes <out_dir>/<stem>.inc (git-ignored, under oracle/_ref/). The shader text i
 cannot parse:
   * `#version` / `#extension` lines are dropped; `#include </name>` is replaced by the named file's text, each file
     once per shader (the names are the ones NetKinectArray.cpp:90,208-209 registers with globjects::NamedString);
-  * `layout(...)`, `noperspective`, and the storage qualifiers `uniform` / `in` / `out` / `buffer` of global
+  * `layout(...)`, `noperspective`, `flat`, `highp`, and the storage qualifiers `uniform` / `in` / `out` / `buffer` of global
     declarations are removed (globals become struct members); interface blocks lose their braces (their members are
     global names in GLSL too); parameter qualifiers `in` / `const in` are removed;
   * GLSL array declarators `T[n] name` become `T name[n]`, an unsized SSBO array `T[] name` becomes `ssbo_array<T> name`
@@ -69,6 +69,8 @@ def transpile(lines):
             continue
         code = l
         code = re.sub(r"layout\s*\([^)]*\)\s*", "", code)
+        code = re.sub(r"\bhighp\s+", "", code)                   # precision qualifiers have no effect on desktop GL
+        code = re.sub(r"^(\s*)flat\s+", r"\1", code)            # interpolation qualifier of a global declaration
         if re.match(r"^\s*(in|out)\s*;\s*$", code):             # geometry shader: layout(triangles) in; / layout(...) out;
             out.append("// " + l.strip())
             continue
@@ -103,7 +105,7 @@ def transpile(lines):
         # array declarators: T[n] name; -> T name[n];   T[] name; -> T* name;
         code = re.sub(r"\b(\w+)\[(\d+)\]\s+(\w+)\s*;", r"\1 \3[\2];", code)
         code = re.sub(r"\b(\w+)\[\]\s+(\w+)\s*;", r"ssbo_array<\1> \2;", code)
-        code = re.sub(r"\b(\w+)\s+(\w+)\[\]\s*;", r"\1 \2[3];", code)      # geometry-shader inputs: one entry per triangle vertex
+        code = re.sub(r"\b(\w+)\s+(\w+)\[\]\s*;", r"\1 \2[3];", code)      # geometry-shader inputs: one entry per primitive vertex (<= 3)
         # r-value swizzles
         code = re.sub(r"\.(xyz|rgb|xy|rg|xx|yz)\b(?!\s*\()", r".\1()", code)
         if not in_block:

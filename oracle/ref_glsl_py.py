@@ -241,3 +241,60 @@ def depth_peels_rasterised(scene, grid, counters, occupied, modelview, projectio
                      np.ascontiguousarray(counters, np.uint32), len(counters), occ, len(occupied), np.ascontiguousarray(V, np.float32),
                      np.ascontiguousarray(idx, np.uint8), len(idx), int(width), int(height), out)
     return out
+
+
+def _gl_normal_matrix(mv):
+    """gl_NormalMatrix: inverse transpose of the model-view's upper 3x3 (column-major storage), embedded in a mat4."""
+    m3 = mv.reshape(4, 4).T[:3, :3].astype(np.float64)
+    gln = np.eye(4, dtype=np.float64)
+    gln[:3, :3] = np.linalg.inv(m3).T
+    return np.ascontiguousarray(gln.T.reshape(16), np.float32)
+
+
+def draw_points(scene, pre, modelview, projection, width, height, shade_mode=0):
+    """ReconPoints::draw with the reference's glsl/points.vs, points.gs, points.fs (+ shading.glsl, inc_bbox_test.glsl) and the
+    fixed-function point pipeline of glsl_harness.cpp::raster_point_gl. Returns (rgba [h,w,4], depth [h,w])."""
+    import oracle_py as O
+    L = lib()
+    if not hasattr(L, "_pts"):
+        L.rg_draw_points.argtypes = [C.c_int, C.c_int, C.c_int, f32p, f32p, u8p, C.c_int, C.c_int, f32p, f32p, i32p, f32p, f32p, f32p,
+                                     C.c_int, C.c_int, C.c_int, f32p, f32p]
+        L.rg_draw_calibs.argtypes = [f32p, u32p, C.c_int, f32p, i32p, f32p, i32p, C.c_int, C.c_float, f32p, f32p, f32p, f32p,
+                                     C.c_int, C.c_int, f32p, f32p]
+        L._pts = True
+    X, Y, Z = scene.cv_res
+    N, H, W = pre["quality"].shape
+    mv = np.ascontiguousarray(modelview, np.float32).reshape(16)
+    pr = np.ascontiguousarray(projection, np.float32).reshape(16)
+    bmin, bmax = np.ascontiguousarray(scene.bbox_min, np.float32), np.ascontiguousarray(scene.bbox_max, np.float32)
+    u = O.raymarch_uniforms(mv, pr, bmin, bmax, width, height)
+    inv4 = lambda m: np.ascontiguousarray(np.linalg.inv(m.reshape(4, 4).T.astype(np.float64)).T.reshape(16), np.float32)     # column-major in and out
+    uniforms = np.ascontiguousarray(np.concatenate([mv, pr, _gl_normal_matrix(mv), u[0:16], inv4(pr), inv4(mv)]), np.float32)
+    rgba, depth = np.zeros((height, width, 4), np.float32), np.zeros((height, width), np.float32)
+    L.rg_draw_points(N, W, H, np.ascontiguousarray(pre["depth_b"], np.float32), np.ascontiguousarray(pre["normal"], np.float32),
+                     np.ascontiguousarray(scene.color), scene.CW, scene.CH, np.ascontiguousarray(scene.cv_xyz, np.float32),
+                     np.ascontiguousarray(scene.cv_uv, np.float32), np.array([X, Y, Z], np.int32), bmin, bmax, uniforms,
+                     int(width), int(height), int(shade_mode), rgba, depth)
+    return rgba, depth
+
+
+def draw_calibs(tsdf, inv, scene, layer, limit, modelview, projection, width, height):
+    """ReconCalibs::draw with the reference's glsl/calib_vis.vs and calib_vis.fs over VolumeSampler's voxel centres."""
+    draw_points.__doc__
+    L = lib()
+    if not hasattr(L, "_pts"):
+        L.rg_draw_points.argtypes = [C.c_int, C.c_int, C.c_int, f32p, f32p, u8p, C.c_int, C.c_int, f32p, f32p, i32p, f32p, f32p, f32p,
+                                     C.c_int, C.c_int, C.c_int, f32p, f32p]
+        L.rg_draw_calibs.argtypes = [f32p, u32p, C.c_int, f32p, i32p, f32p, i32p, C.c_int, C.c_float, f32p, f32p, f32p, f32p,
+                                     C.c_int, C.c_int, f32p, f32p]
+        L._pts = True
+    N, IZ, IY, IX, _ = inv.shape
+    X, Y, Z = scene.cv_res
+    res = np.array([tsdf.shape[2], tsdf.shape[1], tsdf.shape[0]], np.uint32)
+    rgba, depth = np.zeros((height, width, 4), np.float32), np.zeros((height, width), np.float32)
+    L.rg_draw_calibs(np.ascontiguousarray(tsdf, np.float32), res, N, np.ascontiguousarray(inv, np.float32), np.array([IX, IY, IZ], np.int32),
+                     np.ascontiguousarray(scene.cv_xyz, np.float32), np.array([X, Y, Z], np.int32), int(layer), np.float32(limit),
+                     np.ascontiguousarray(scene.bbox_min, np.float32), np.ascontiguousarray(scene.bbox_max, np.float32),
+                     np.ascontiguousarray(modelview, np.float32).reshape(16), np.ascontiguousarray(projection, np.float32).reshape(16),
+                     int(width), int(height), rgba, depth)
+    return rgba, depth

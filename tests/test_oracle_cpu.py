@@ -399,6 +399,60 @@ def test_oracle_raymarch_matches_the_reference_shader_run_on_cpu(O, small_scene,
             _assert_raymarch(got, want["rgba"], want["depth"], want["samples"], want["hit"], f"eye {eye} mode {mode}", np.asarray(pr))
 
 
+def _assert_points(got, want, what):
+    """Point renderings agree when coverage is the same up to a handful of boundary pixels (the fixed-function stage is fp64 in
+    the shader harness, fp32 in the oracle) and, where the same point won, depth to 2e-7 and colour to 2e-5."""
+    (rgba, depth), (w_rgba, w_depth) = got, want
+    cov, w_cov = depth < 1.0, w_depth < 1.0
+    assert w_cov.sum() > 50, what
+    assert (cov != w_cov).sum() <= max(2, int(0.002 * w_cov.sum())), f"{what}: coverage differs on {(cov != w_cov).sum()} pixels"
+    both = cov & w_cov
+    same = both & (np.abs(depth - w_depth) <= 2e-7)
+    assert same.sum() >= 0.995 * both.sum(), f"{what}: another point won on {both.sum() - same.sum()} pixels"
+    assert np.abs(rgba - w_rgba)[same].max() <= 2e-5, what
+
+
+def test_oracle_point_renderers_match_the_reference_shaders_run_on_cpu(O, small_scene, small_frame):
+    """ReconPoints::draw and ReconCalibs::draw (SURVEY.md 8f-4): the oracle's restatement (oracle/ro_points.cpp) against the
+    reference's own points.vs / points.gs / points.fs and calib_vis.vs / calib_vis.fs run on the CPU through the fixed-function
+    point pipeline of OpenGL 4.4 (oracle/glsl_host/glsl_harness.cpp), every shade mode, camera outside and inside the volume."""
+    import ref_glsl_py as G
+    if not G.available() or not hasattr(G.lib(), "rg_draw_points"):
+        pytest.skip("oracle/_ref/libref_glsl.so not built with the point shaders (needs the reference tree at build time)")
+    from rrpy import synth
+    sc = small_scene
+    pre, inv, tsdf = (small_frame[k] for k in ("pre", "inv", "tsdf"))
+    VW, VH = 200, 112
+    for eye in ((1.6, 1.5, 2.2), (0.7, 1.3, 0.75)):
+        mv, pr = synth.look_at(eye, (0.0, 1.1, 0.0)), synth.perspective(50.0, VW / VH, 0.1, 10.0)
+        for mode in range(4):
+            _assert_points(O.draw_points(sc, pre, mv, pr, VW, VH, mode), G.draw_points(sc, pre, mv, pr, VW, VH, mode), f"points eye {eye} mode {mode}")
+        IZ, IY, IX = inv.shape[1:4]
+        for limit in (0.01, 0.005):
+            _assert_points(O.draw_calibs(tsdf, (IX, IY, IZ), limit, sc.bbox_min, sc.bbox_max, mv, pr, VW, VH),
+                           G.draw_calibs(tsdf, inv, sc, 1, limit, mv, pr, VW, VH), f"calibs eye {eye} limit {limit}")
+
+
+def test_oracle_point_renderers_against_the_committed_shader_outputs(O):
+    """The same pin on machines without the reference tree: tests/golden/ref_glsl_points.npz holds what the reference's shaders
+    drew for the golden scene (tools/make_golden.py::golden_glsl_points); the oracle regenerates stages and volume bit for bit."""
+    from rrpy import synth
+    g = gold("ref_glsl_points.npz")
+    sc = synth.make_scene(N=1, W=128, H=106, CW=160, CH=135, cv_res=(24, 24, 48), seed=77)    # tools/make_golden.py::glsl_scene
+    voxel = float(g["voxel"])
+    grid = O.brick_grid(sc.bbox_min, sc.bbox_max, voxel, 0.1)
+    cams = [O.frustum(sc.cv_xyz[i])[1] for i in range(sc.N)]
+    pre = O.preprocess(sc, grid, cams)
+    inv = synth.analytic_inverse(sc, (20, 22, 20))
+    tsdf = O.integrate(inv, pre, grid, 0.01, True, O.occupied_bricks(pre["bricks"], 10))
+    assert hashlib.sha256(np.ascontiguousarray(tsdf).tobytes()).hexdigest() == str(g["tsdf_sha"]), "the golden's input volume changed"
+    V = dict(eye=(1.2, 1.4, 1.6), at=(0.0, 1.1, 0.0), fovy=50.0, w=160, h=90)                  # make_golden.py::RM_VIEW
+    mv, pr = synth.look_at(V["eye"], V["at"]), synth.perspective(V["fovy"], V["w"] / V["h"], 0.1, 10.0)
+    for mode in range(4):
+        _assert_points(O.draw_points(sc, pre, mv, pr, V["w"], V["h"], mode), (g[f"points_rgba{mode}"], g[f"points_depth{mode}"]), f"points mode {mode}")
+    _assert_points(O.draw_calibs(tsdf, (20, 22, 20), 0.01, sc.bbox_min, sc.bbox_max, mv, pr, V["w"], V["h"]), (g["calibs_rgba"], g["calibs_depth"]), "calibs")
+
+
 def test_depth_peels_from_the_reference_brick_shaders_and_a_rasteriser(O, small_scene, small_frame):
     """drawDepthLimits with the reference's bricks.vs / bricks.gs / bricks.fs and a rasteriser (glsl_harness.cpp::rg_depth_peels;
     the cube strip is read from unit_cube.cpp) against the ray-cast statement ref_glsl_py.depth_peels: same coverage, nearest and

@@ -117,9 +117,32 @@ def golden_glsl_raymarch():
                         atlas_color=atlas_c, atlas_depth=atlas_d)
 
 
+def golden_glsl_points():
+    """glsl/points.{vs,gs,fs} and calib_vis.{vs,fs} run on the CPU (oracle/glsl_host: ReconPoints::draw, ReconCalibs::draw with the
+    fixed-function point pipeline of OpenGL 4.4) on the ORACLE's stages and volume of glsl_scene()."""
+    import ref_glsl_py as G
+    sc = glsl_scene()
+    voxel = 0.035
+    grid = O.brick_grid(sc.bbox_min, sc.bbox_max, voxel, 0.1)
+    cams = [O.frustum(sc.cv_xyz[i])[1] for i in range(sc.N)]
+    pre = O.preprocess(sc, grid, cams)
+    inv = synth.analytic_inverse(sc, (20, 22, 20))
+    tsdf = O.integrate(inv, pre, grid, 0.01, True, O.occupied_bricks(pre["bricks"], 10))
+    mv = synth.look_at(RM_VIEW["eye"], RM_VIEW["at"])
+    pr = synth.perspective(RM_VIEW["fovy"], RM_VIEW["w"] / RM_VIEW["h"], 0.1, 10.0)
+    out = {}
+    for mode in range(4):
+        out[f"points_rgba{mode}"], out[f"points_depth{mode}"] = G.draw_points(sc, pre, mv, pr, RM_VIEW["w"], RM_VIEW["h"], mode)
+    out["calibs_rgba"], out["calibs_depth"] = G.draw_calibs(tsdf, inv, sc, 0, 0.01, mv, pr, RM_VIEW["w"], RM_VIEW["h"])
+    np.savez_compressed(os.path.join(OUT, "ref_glsl_points.npz"), voxel=np.float32(voxel), tsdf_sha=np.array(sha(tsdf)), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     assert R.available(), "build oracle/_ref first (make -C oracle all)"
+    if "--only-points" in sys.argv:
+        golden_glsl_points()
+        return
     if "--only-dxt" in sys.argv:
         golden_dxt1()
         golden_dxt5()
@@ -130,6 +153,7 @@ def main():
         return
     golden_dxt1()
     golden_dxt5()
+    golden_glsl_points()
     golden_glsl()
     golden_glsl_raymarch()
     sc = golden_scene()
