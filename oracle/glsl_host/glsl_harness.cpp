@@ -541,6 +541,7 @@ static void raster_point_gl(const vec4& clip, double size, int vw, int vh, float
   const double xw = ((double)clip.x / clip.w * 0.5 + 0.5) * vw, yw = ((double)clip.y / clip.w * 0.5 + 0.5) * vh;
   const float zw = (float)((double)clip.z / clip.w * 0.5 + 0.5);
   if (!(size >= 1.0)) size = 1.0;
+  if (size > 256.0) size = 256.0;                                   // the implementation's point-size range, taken as [1, 256]
   const double h = size * 0.5;
   const int x0 = std::max(0, (int)std::ceil(xw - h - 0.5)), x1 = std::min(vw, (int)std::ceil(xw + h - 0.5));
   const int y0 = std::max(0, (int)std::ceil(yw - h - 0.5)), y1 = std::min(vh, (int)std::ceil(yw + h - 0.5));

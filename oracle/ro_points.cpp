@@ -7,7 +7,8 @@
 //     with glsl/calib_vis.vs (:25-38) and calib_vis.fs (:17-29).
 // Rasterisation follows OpenGL 4.4: a point whose centre is outside the clip volume is culled (§13.5); window coordinates
 // by the viewport transform with depth range [0, 1] (§13.6.1); a point sprite produces a fragment for every pixel whose
-// centre lies inside the square of side gl_PointSize (clamped to >= 1; 1 where the shader does not write it) centred at
+// centre lies inside the square of side gl_PointSize (clamped to the implementation's range, taken as [1, 256]; 1 where the
+// shader does not write it) centred at
 // the point (§14.4.1; the square is taken half-open, [c - s/2, c + s/2)); fragments are depth-tested in draw order, an
 // equal depth fails GL_LESS, so the first drawn fragment keeps the pixel. Depth is kept in binary32.
 // PARITY: the shader stages are pinned against the reference's own shader sources run on the CPU where
@@ -170,7 +171,7 @@ void ro_draw_points(int N, int W, int H, const float* depth_b, const float* norm
         if (!to_window(mulv(proj, es), vw, vh, xw, yw, zw)) continue;
         const float dist = sqrtf(dot3(pos_es, pos_es));
         const float max_size = shade_mode == 3 ? 4.0f : 10.0f;
-        const float size = gl_max(max_size / dist, 1.0f);
+        const float size = gl_min(gl_max(max_size / dist, 1.0f), 256.0f);     // ALIASED_POINT_SIZE_RANGE taken as [1, 256]
         V3 c;
         if (shade_mode == 3) {
           const float* cc = kCameraColors[layer < 5 ? layer : 4];

@@ -11,8 +11,8 @@
 // the fragment shader's arithmetic is applied). Draw order decides depth ties in GL (an equal depth fails GL_LESS);
 // vertex ids ascend in draw order, so the smaller id wins the atomicMin exactly like the first drawn fragment.
 // Rasterisation rule (OpenGL 4.4 §14.4.1, point sprites with program point size): a fragment for every pixel whose centre
-// lies inside the square of side `size` centred at the point's window position, size clamped to >= 1; a point whose centre
-// is outside the clip volume is culled (§13.5).
+// lies inside the square of side `size` centred at the point's window position, size clamped to the implementation's range
+// (taken as [1, 256]); a point whose centre is outside the clip volume is culled (§13.5).
 #include "rr_context.h"
 #include "rr_math.cuh"
 
@@ -148,7 +148,7 @@ __device__ PointVertex point_vertex(const PointParams& p, uint32_t id) {
     if (!to_window(p, clip, v)) return v;
     const float dist = sqrtf(dot3(v.pos_es, v.pos_es));
     const float max_size = p.shade_mode == 3 ? 4.0f : 10.0f;
-    v.size = gmax(max_size / dist, 1.0f);
+    v.size = gmin(gmax(max_size / dist, 1.0f), 256.0f);       // the implementation's point-size range, taken as [1, 256]
     v.alive = true;
     return v;
   }

@@ -277,7 +277,8 @@ def test_staged_integrator_paths_are_bit_identical(n_sensors):
     assert len(occ) > 20
     defaults = dict(stage_tile=0, stage_zchunk=13, stage_ychunk=0, stage_cwarps=0, stage_tail_cap=2, stage_fill_depth=0, stage_bulk_fill=4, stage_fill_rows=16)
     variants = [dict(), dict(stage_tile=8), dict(stage_tile=14, stage_zchunk=4), dict(stage_ychunk=2, stage_zchunk=3), dict(stage_cwarps=11),
-                dict(stage_tail_cap=0, stage_fill_depth=-1, stage_bulk_fill=16), dict(stage_fill_rows=5, stage_tail_cap=1)]
+                dict(stage_tail_cap=0, stage_fill_depth=-1, stage_bulk_fill=16), dict(stage_fill_rows=5, stage_tail_cap=1),
+                dict(stage_ychunk=3), dict(stage_ychunk=7, stage_cwarps=11)]
     fu = capi.Fusion(sc.N, sc.W, sc.H, sc.CW, sc.CH)
     capi.load_scene(fu, sc, inv)
     fu.configure(limit=0.01, voxel_size=0.0125, brick_size=0.1, min_voxels=10, use_bricks=True)
