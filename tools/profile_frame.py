@@ -22,5 +22,12 @@ for i in range(a.frames):
     s = scenes[i % len(scenes)]
     fu.upload_frames(s.color, s.depth)
     print(i, fu.frame(sync_bricks=True))
+# one view of every renderer, so that launch lists and captures also hold the view-path kernels
+from rrpy import synth  # noqa: E402
+mv, pr = synth.look_at((1.7, 1.6, 2.3), (0.0, 1.1, 0.0)), synth.perspective(50.0, bench.VW / bench.VH, 0.1, 10.0)
+fu.raymarch(mv, pr, bench.VW, bench.VH, shade_mode=1, download=False)
+fu.fill_colors(download=False)
+fu.draw_points(mv, pr, bench.VW, bench.VH, shade_mode=1)
+fu.draw_calibs(mv, pr, bench.VW, bench.VH)
 fu.synchronize()
 fu.close()
