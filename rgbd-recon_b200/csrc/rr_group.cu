@@ -31,6 +31,7 @@ struct rr_group {
   std::vector<uint32_t*> f_step; std::vector<float4*> f_rgba; std::vector<float*> f_zbuf; std::vector<float*> f_nsamp;
   size_t f_pixels = 0;
   std::vector<cudaEvent_t> ev_view;    // member i's view (or its fallback copy) is complete
+  std::vector<cudaEvent_t> ev_copied[2];   // [slot][i]: member i has copied its parent's frame slot `slot` (the parent may overwrite it)
   std::vector<uint32_t> bounds;        // slab boundaries [n + 1]
 };
 
@@ -93,6 +94,7 @@ int gcheck(rr_group* g, cudaError_t e, const char* what) {
     }                                                                        \
   } while (0)
 #define RR_G_TRY(g, expr) do { const int rc__ = gcheck((g), (expr), #expr); if (rc__ != RR_OK) return rc__; } while (0)
+#define RR_G_TRY_RC(expr) do { const int rc__ = (expr); if (rc__ != RR_OK) return rc__; } while (0)
 
 extern "C" {
 
@@ -138,9 +140,12 @@ int rr_group_create(rr_group** out, const int* devices, int n_devices, int num_s
     cudaGetLastError();
   }
   g->ev_view.assign(n_devices, nullptr);
+  g->ev_copied[0].assign(n_devices, nullptr); g->ev_copied[1].assign(n_devices, nullptr);
   for (int i = 0; i < n_devices; ++i) {
     cudaSetDevice(devices[i]);
     cudaEventCreateWithFlags(&g->ev_view[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&g->ev_copied[0][i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&g->ev_copied[1][i], cudaEventDisableTiming);
   }
   g->f_step.assign(n_devices, nullptr); g->f_rgba.assign(n_devices, nullptr); g->f_zbuf.assign(n_devices, nullptr); g->f_nsamp.assign(n_devices, nullptr);
   *out = g;
@@ -154,6 +159,7 @@ void rr_group_destroy(rr_group* g) {
     cudaStreamSynchronize(g->m[i]->stream);
     cudaStreamSynchronize(g->m[i]->copy_stream);
     if (g->ev_view[i]) cudaEventDestroy(g->ev_view[i]);
+    for (int b = 0; b < 2; ++b) if (g->ev_copied[b][i]) cudaEventDestroy(g->ev_copied[b][i]);
   }
   cudaSetDevice(g->dev[0]);
   for (size_t i = 0; i < g->m.size(); ++i) { cudaFree(g->f_step[i]); cudaFree(g->f_rgba[i]); cudaFree(g->f_zbuf[i]); cudaFree(g->f_nsamp[i]); }
@@ -292,10 +298,22 @@ int rr_group_balance_slabs(rr_group* g, float compute_to_fill) {
 /* ---- per frame ------------------------------------------------------------------------------------------------- */
 // member c takes the frame set member s has just staged (the same back slot parity everywhere: members are only ever
 // staged and swapped together)
-static int stage_from_peer(rr_group* g, rr_ctx* c, rr_ctx* s, bool color, size_t cb, size_t db) {
+// member `self` is about to overwrite its back slot t: its children in the tree must have finished copying the frame set that
+// slot held (waiting on an event that was never recorded is a no-op)
+static int wait_for_children(rr_group* g, size_t self, int t) {
+  rr_ctx* c = g->m[self];
+  for (size_t child = 2 * self + 1; child <= 2 * self + 2 && child < g->m.size(); ++child)
+    RR_G_TRY(g, cudaStreamWaitEvent(c->copy_stream, g->ev_copied[t][child], 0));
+  return RR_OK;
+}
+
+static int stage_from_peer(rr_group* g, size_t self, bool color, size_t cb, size_t db) {
+  rr_ctx* c = g->m[self];
+  rr_ctx* s = g->m[(self - 1) / 2];
   RR_G_TRY(g, cudaSetDevice(c->device));
   const int t = c->cur_slot ^ 1, ts = s->cur_slot ^ 1;
   if (c->free_recorded[t]) RR_G_TRY(g, cudaStreamWaitEvent(c->copy_stream, c->ev_free[t], 0));
+  RR_G_TRY_RC(wait_for_children(g, self, t));
   RR_G_TRY(g, cudaStreamWaitEvent(c->copy_stream, s->ev_staged, 0));
   void* dd = c->depth_format == RR_DEPTH_U8 ? (void*)c->d_depth_packed[t] : (void*)c->d_depth_slot[t];
   const void* sd = s->depth_format == RR_DEPTH_U8 ? (const void*)s->d_depth_packed[ts] : (const void*)s->d_depth_slot[ts];
@@ -307,6 +325,7 @@ static int stage_from_peer(rr_group* g, rr_ctx* c, rr_ctx* s, bool color, size_t
   }
   c->staged_color = color;
   RR_G_TRY(g, cudaEventRecord(c->ev_staged, c->copy_stream));
+  RR_G_TRY(g, cudaEventRecord(g->ev_copied[ts][self], c->copy_stream));
   c->staged = true;
   return RR_OK;
 }
@@ -314,15 +333,16 @@ static int stage_from_peer(rr_group* g, rr_ctx* c, rr_ctx* s, bool color, size_t
 int rr_group_stage_frames(rr_group* g, const void* color, size_t color_bytes, const void* depth, size_t depth_bytes) {
   if (!g) return RR_ERR_INVALID;
   rr_ctx* c0 = g->m[0];
-  // the ingest device's back slot is the source of the peer copies of the frame set staged before: they must have drained
-  // before it is overwritten (a member's copy stream is in order, so its newest staged event covers the older copies)
-  cudaSetDevice(c0->device);
-  for (size_t i = 1; i < g->m.size(); ++i) RR_G_TRY(g, cudaStreamWaitEvent(c0->copy_stream, g->m[i]->ev_staged, 0));     // no-op until first recorded
-  int rc = rr_stage_frames(c0, color, color_bytes, depth, depth_bytes);
+  // the ingest device's back slot was the source of its children's copies two frame sets ago: they must have drained before
+  // it is overwritten (per slot, so this host->device copy overlaps the deeper levels' copies of the previous frame set)
+  RR_G_TRY(g, cudaSetDevice(c0->device));
+  int rc = wait_for_children(g, 0, c0->cur_slot ^ 1);
+  if (rc != RR_OK) return rc;
+  rc = rr_stage_frames(c0, color, color_bytes, depth, depth_bytes);
   if (rc != RR_OK) return member_fail(g, 0, rc);
   // down the tree: a member's copy waits for its parent's (ev_staged of the parent), ascending order issues parents first
   for (size_t i = 1; i < g->m.size(); ++i) {
-    rc = stage_from_peer(g, g->m[i], g->m[(i - 1) / 2], color != nullptr, color_bytes, depth_bytes);
+    rc = stage_from_peer(g, i, color != nullptr, color_bytes, depth_bytes);
     if (rc != RR_OK) return rc;
   }
   return RR_OK;
