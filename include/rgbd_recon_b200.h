@@ -181,6 +181,19 @@ int rr_raymarch(rr_ctx* ctx, const rr_view* view, float* out_rgba, float* out_de
 int rr_draw_points(rr_ctx* ctx, const rr_view* view, float* out_rgba, float* out_depth);
 int rr_draw_calibs(rr_ctx* ctx, const rr_view* view, int active_kinect, float tsdf_limit, float* out_rgba, float* out_depth);
 
+/* ReconTrigrid::draw (recon_trigrid.cpp:82-149; glsl/trigrid_accum.vs, trigrid_accum.gs, trigrid_accum.fs,
+ * trigrid_normalize.fs), the triangle-mesh consumer of the pre-processed maps: every depth pixel of every
+ * sensor spans two triangles (the grid of :48-61, as written there: cells x < height, y < width); pass 1 keeps the nearest
+ * window depth of the triangles that survive validSurface (no invalid depth, every edge shorter than
+ * min_length * average depth * 4), the bounding box, the colour view's border and back-face culling; pass 2 adds
+ * shade() * quality, quality of every fragment within epsilon = 0.075 (:35) of that surface; pass 3 divides by the summed
+ * quality. A software rasteriser (OpenGL 4.4 clipping, coverage and perspective-correct interpolation in fp64) whose additive
+ * blend is performed in draw order (per-pixel fragment lists summed by ascending triangle id), so the result is deterministic.
+ * min_length: CalibrationFiles::minLength() (the sensor .yml's "min_length:", default 0.0125, KinectCalibrationFile.cpp:96,341).
+ * Writes the context's view images like rr_raymarch: rgba float32 [h][w][4] (alpha 1 where something was drawn, zeros
+ * elsewhere), depth float32 [h][w] (pass 1's depth, 1.0 elsewhere). Synchronises the context's stream once per call. */
+int rr_draw_trigrid(rr_ctx* ctx, const rr_view* view, float min_length, float* out_rgba, float* out_depth);
+
 /* ReconIntegration::fillColors (recon_integration.cpp:280-339; on by default, m_fill_holes, :54) + ViewLod
  * (view_lod.cpp:24-61) + glsl/framebuffer_transfer.fs, tsdf_inpaint.fs, tsdf_colorfill.fs: push-pull colour hole filling
  * of the LAST view (rr_raymarch, rr_composite or rr_upload_view): pixels the raymarch hit but could only colour with the
@@ -290,7 +303,8 @@ uint64_t rr_launch_count(const rr_ctx* ctx);
 /* Launch-shape knob of the integrator, process-wide (no reference counterpart; the reference's draw-call structure is
  * fixed). Names: "fused", "zchunk", "fill_rows", "fill_warps", "ctas", "threads", "chunk", "brick_grid",
  * "ldg256", "graph", "staged", "stage_zchunk", "stage_ychunk", "stage_tile", "stage_cwarps", "stage_fill_rows", "stage_bulk_fill", "stage_fill_depth",
- * "stage_tail_cap", "stage_ctas", "stage_fill_lsu", "stage_debug".
+ * "stage_tail_cap", "stage_ctas", "stage_fill_lsu", "stage_debug", "trigrid_pool" (rr_draw_trigrid: initial fragment-pool
+ * capacity in fragments per 16 view pixels; the pool grows when a view needs more).
  * Results never depend on these. Returns RR_ERR_INVALID for an unknown name. */
 int rr_set_tunable(const char* name, int value);
 /* Which integrator the bricks mode of this context runs and with what geometry (no reference counterpart; diagnostics for

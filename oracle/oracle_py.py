@@ -268,6 +268,25 @@ def draw_calibs(tsdf, inv_res, limit, bbox_min, bbox_max, modelview, projection,
     return rgba, depth
 
 
+def draw_trigrid(scene, pre, modelview, projection, width, height, shade_mode=0, min_length=0.0125, epsilon=0.075, want_passes=False):
+    """ReconTrigrid::draw on the pre-processed maps of `pre` (depth_b, quality). Returns (rgba [h,w,4], depth [h,w]) and, with
+    want_passes, also the accumulation target of pass 2 and the depth buffer of pass 1."""
+    L = lib()
+    L.ro_draw_trigrid.argtypes = [C.c_int, C.c_int, C.c_int, f32p, f32p, u8p, C.c_int, C.c_int, f32p, f32p, i32p, f32p, f32p, f32p, f32p,
+                                  C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, f32p, f32p, C.c_void_p, C.c_void_p]
+    X, Y, Z = scene.cv_res
+    N, H, W = pre["quality"].shape
+    rgba, depth = np.zeros((height, width, 4), np.float32), np.zeros((height, width), np.float32)
+    accum, depth1 = np.zeros((height, width, 4), np.float32), np.zeros((height, width), np.float32)
+    L.ro_draw_trigrid(N, W, H, np.ascontiguousarray(pre["depth_b"], np.float32), np.ascontiguousarray(pre["quality"], np.float32),
+                      np.ascontiguousarray(scene.color), scene.CW, scene.CH, np.ascontiguousarray(scene.cv_xyz, np.float32),
+                      np.ascontiguousarray(scene.cv_uv, np.float32), np.array([X, Y, Z], np.int32), np.ascontiguousarray(scene.bbox_min, np.float32),
+                      np.ascontiguousarray(scene.bbox_max, np.float32), np.ascontiguousarray(modelview, np.float32).reshape(16),
+                      np.ascontiguousarray(projection, np.float32).reshape(16), int(width), int(height), int(shade_mode),
+                      float(min_length), float(epsilon), rgba, depth, accum.ctypes.data, depth1.ctypes.data)
+    return (rgba, depth, accum, depth1) if want_passes else (rgba, depth)
+
+
 def raymarch_rays(modelview, projection, bbox_min, bbox_max, width, height, limit):
     """Per pixel the ray's target point in volume space and whether the cube proxy covers the pixel."""
     pts = np.zeros((height, width, 3), np.float32)

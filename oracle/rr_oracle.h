@@ -71,6 +71,12 @@ void ro_draw_points(int N, int W, int H, const float* depth_b, const float* norm
 void ro_draw_calibs(const float* tsdf, const uint32_t* res, const int32_t* inv_res, float limit, const float* bmin, const float* bmax,
                     const float* mv, const float* proj, int vw, int vh, float* out_rgba, float* out_depth);
 
+/* ReconTrigrid::draw, see ro_trigrid.cpp. out_accum / out_depth1 may be null. */
+void ro_draw_trigrid(int N, int W, int H, const float* depth_b, const float* quality, const uint8_t* color, int CW, int CH,
+                     const float* cv_xyz, const float* cv_uv, const int32_t* cv_res, const float* bmin, const float* bmax,
+                     const float* mv, const float* proj, int vw, int vh, int shade_mode, float min_length, float epsilon,
+                     float* out_rgba, float* out_depth, float* out_accum, float* out_depth1);
+
 /* Compressed ingest: DXT1 colour blocks -> uint8 [H][W][3]; 8-bit depth -> byte/255. */
 void ro_decode_dxt1(const uint8_t* blocks, int W, int H, uint8_t* out_rgb);
 void ro_decode_dxt5(const uint8_t* blocks, int W, int H, uint8_t* out_rgb);   /* 16-byte blocks: alpha (skipped) + colour */

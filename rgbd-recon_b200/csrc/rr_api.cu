@@ -172,6 +172,7 @@ void rr_destroy(rr_ctx* c) {
   cudaFree(c->d_inv); cudaFree(c->d_morph); cudaFree(c->d_depth);
   cudaFree(c->d_lab); cudaFree(c->d_depth_b); cudaFree(c->d_sil); cudaFree(c->d_normal); cudaFree(c->d_quality);
   staged_release(c);
+  trigrid_release(c);
   for (auto& v : c->ipc_views) { cudaIpcCloseMemHandle(v.step); cudaIpcCloseMemHandle(v.rgba); cudaIpcCloseMemHandle(v.zbuf); cudaIpcCloseMemHandle(v.nsamp); }
   cudaGetLastError();
   cudaFree(c->d_pairs);
@@ -660,6 +661,22 @@ int rr_draw_calibs(rr_ctx* c, const rr_view* view, int active_kinect, float tsdf
   return draw_points_common(c, view, 1, tsdf_limit, out_rgba, out_depth, "rr_draw_calibs");
 }
 
+int rr_draw_trigrid(rr_ctx* c, const rr_view* view, float min_length, float* out_rgba, float* out_depth) {
+  if (!c) return RR_ERR_INVALID;
+  RR_REQUIRE(c, view, "rr_draw_trigrid: null view");
+  RR_REQUIRE(c, view->viewport[2] > 0 && view->viewport[3] > 0, "rr_draw_trigrid: empty viewport");
+  RR_REQUIRE(c, min_length > 0.0f, "rr_draw_trigrid: min_length must be positive");
+  for (int i = 0; i < c->N; ++i) RR_REQUIRE(c, c->have_calib[i], "rr_draw_trigrid: upload every sensor's calibration volumes first");
+  RR_SET_DEVICE(c);
+  const int w = view->viewport[2], h = view->viewport[3];
+  RR_TRY(ensure_view(c, w, h));
+  RR_TRY(launch_draw_trigrid(c, view, min_length));
+  if (out_rgba) RR_TRY(check(c, cudaMemcpyAsync(out_rgba, c->d_rgba, (size_t)w * h * sizeof(float4), cudaMemcpyDeviceToHost, c->stream), "rr_draw_trigrid"));
+  if (out_depth) RR_TRY(check(c, cudaMemcpyAsync(out_depth, c->d_zbuf, (size_t)w * h * sizeof(float), cudaMemcpyDeviceToHost, c->stream), "rr_draw_trigrid"));
+  if (out_rgba || out_depth) RR_TRY(check(c, cudaStreamSynchronize(c->stream), "rr_draw_trigrid"));
+  return RR_OK;
+}
+
 int rr_fill_colors(rr_ctx* c, float* out_rgba) {
   if (!c) return RR_ERR_INVALID;
   RR_REQUIRE(c, c->d_rgba && c->view_w > 0 && c->view_h > 0, "rr_fill_colors: no view yet (rr_raymarch / rr_composite / rr_upload_view first)");
@@ -956,6 +973,7 @@ int rr_set_tunable(const char* name, int value) {
   else if (n == "stage_ctas") t.stage_ctas = value;
   else if (n == "stage_cwarps") t.stage_cwarps = value;
   else if (n == "stage_bulk_fill") t.stage_bulk_fill = value;
+  else if (n == "trigrid_pool") t.trigrid_pool = value;
   else return RR_ERR_INVALID;
   ++t.generation;              // captured frame graphs bake the launch shapes in: stale keys never match again
   return RR_OK;

@@ -183,6 +183,13 @@ struct rr_ctx {
   uint32_t* d_step = nullptr;      // step index of the hit, 0xFFFFFFFF = none (multi-GPU compositing key)
   unsigned long long* d_point_keys = nullptr;   // rr_draw_points / rr_draw_calibs: per pixel (depth bits << 32 | vertex id), atomicMin
 
+  // rr_draw_trigrid (rr_trigrid.cu): vertex records, pass-1 depth bits, per-pixel fragment lists (grown on demand)
+  float4* d_tg_verts = nullptr; size_t tg_verts_cap = 0;
+  uint32_t* d_tg_depth = nullptr; size_t tg_depth_cap = 0;
+  uint32_t* d_tg_head = nullptr; size_t tg_head_cap = 0;
+  float4* d_tg_frag_rgba = nullptr; uint2* d_tg_frag_link = nullptr; size_t tg_frag_cap = 0;
+  uint32_t* d_tg_count = nullptr;
+
   // colour hole filling (rr_colorfill.cu): atlas right of column W, squeezed copy, filled colour
   int fill_w = 0, fill_h = 0;
   float4* d_fill_fc = nullptr; float* d_fill_fd = nullptr;
@@ -215,6 +222,7 @@ struct Tunables {
  int stage_tail_cap = 2;     // items in flight per CTA towards the end of the item list (0: the ring's capacity throughout)
   int stage_ctas = 0;         // CTAs of the staged integrator (0: one per SM)
   int stage_fill_lsu = 0;     // 1: rows without occupied bricks are cleared by per-lane stores instead of bulk stores
+  int trigrid_pool = 64;      // rr_draw_trigrid: initial capacity of the fragment pool, in fragments per 16 view pixels (it grows on demand)
   int stage_debug = 0;  // measurement only, results are WRONG: bit 0 skips the clear stream, bit 1 the brick evaluation
   unsigned generation = 0;   // bumped by every rr_set_tunable (invalidates captured graphs)
 };
@@ -238,6 +246,8 @@ int launch_partial_keys(rr_ctx* c, const float4* d_rec, int rank, long long* d_k
 int launch_partial_keep(rr_ctx* c, float4* d_rec, const long long* d_keys_min, int rank);
 int launch_fill_colors(rr_ctx* c);
 int launch_draw_points(rr_ctx* c, const rr_view* v, int mode, float calib_limit);   // rr_points.cu
+int launch_draw_trigrid(rr_ctx* c, const rr_view* v, float min_length);             // rr_trigrid.cu
+void trigrid_release(rr_ctx* c);
 int launch_unpack_frames(rr_ctx* c, int slot);
 int launch_calib_invert(rr_ctx* c, int sensor, const uint32_t out_res[3], float4* d_out);
 int staged_prepare(rr_ctx* c);        // (re)builds the staged integrator's tables when dirty; RR_OK also when it declines

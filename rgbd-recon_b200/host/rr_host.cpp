@@ -364,6 +364,11 @@ void ReconPoints::draw() {                                   // recon_points.cpp
   m_rgba.resize(n * 4); m_depth.resize(n);
   ck(rr_draw_points(ctx(), &m_view, m_rgba.data(), m_depth.data()), "rr_draw_points");
 }
+void ReconTrigrid::draw() {                                  // recon_trigrid.cpp:82-149
+  const std::size_t n = (std::size_t)m_view.viewport[2] * m_view.viewport[3];
+  m_rgba.resize(n * 4); m_depth.resize(n);
+  ck(rr_draw_trigrid(ctx(), &m_view, m_min_length, m_rgba.data(), m_depth.data()), "rr_draw_trigrid");
+}
 void ReconCalibs::draw() {                                   // recon_calibs.cpp:56-66
   const std::size_t n = (std::size_t)m_view.viewport[2] * m_view.viewport[3];
   m_rgba.resize(n * 4); m_depth.resize(n);

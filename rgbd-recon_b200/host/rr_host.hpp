@@ -330,6 +330,22 @@ class ReconPoints : public Reconstruction {
   std::vector<float> m_rgba, m_depth;
 };
 
+// ---- framework/reconstruction/recon_trigrid.hpp: a triangle mesh over every sensor's depth pixels, the sensors blended by ----
+// quality within epsilon of the front-most surface (depth pass, additive accumulation pass, normalisation pass). m_min_length
+// comes from the calibration files like Reconstruction::m_min_length (reconstruction.cpp:20).
+class ReconTrigrid : public Reconstruction {
+ public:
+  ReconTrigrid(CalibrationFiles const& cfs, CalibVolumes const* cv, gloost::BoundingBox const& bbox)
+      : Reconstruction(cfs, cv, bbox), m_min_length(cfs.minLength()) {}
+  void draw() override;
+  void setShadeMode(int mode) { m_view.shade_mode = mode; }
+  std::vector<float> const& colorImage() const { return m_rgba; }
+  std::vector<float> const& depthImage() const { return m_depth; }
+ private:
+  float m_min_length;
+  std::vector<float> m_rgba, m_depth;
+};
+
 // ---- framework/reconstruction/recon_calibs.hpp: the inverse-volume grid's voxel centres coloured by the TSDF (debug view) ----
 // Reads the TSDF volume of the first device; with several devices that member holds its own z-slab only.
 class ReconCalibs : public Reconstruction {

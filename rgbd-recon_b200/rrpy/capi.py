@@ -96,6 +96,7 @@ def lib():
     L.rr_integrator_profile.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.rr_draw_points.argtypes = [vp, C.POINTER(View), f32, f32]
     L.rr_draw_calibs.argtypes = [vp, C.POINTER(View), C.c_int, C.c_float, f32, f32]
+    L.rr_draw_trigrid.argtypes = [vp, C.POINTER(View), C.c_float, f32, f32]
     L.rr_view_export.argtypes = [vp, C.c_int, C.c_int, vp]
     L.rr_composite_peers.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, f32, f32]
     # one process, several GPUs
@@ -322,6 +323,14 @@ class Fusion:
         self._vw, self._vh = int(width), int(height)
         rgba, depth = np.zeros((height, width, 4), np.float32), np.zeros((height, width), np.float32)
         self._ck(self.L.rr_draw_calibs(self.h, C.byref(v), int(active_kinect), float(limit), _f32(rgba), _f32(depth)))
+        return rgba, depth
+
+    def draw_trigrid(self, modelview, projection, width, height, shade_mode=0, min_length=0.0125):
+        """ReconTrigrid::draw (rr_draw_trigrid) of the maps of the last preprocess; returns (rgba, depth)."""
+        v = self._view(modelview, projection, width, height, shade_mode)
+        self._vw, self._vh = int(width), int(height)
+        rgba, depth = np.zeros((height, width, 4), np.float32), np.zeros((height, width), np.float32)
+        self._ck(self.L.rr_draw_trigrid(self.h, C.byref(v), float(min_length), _f32(rgba), _f32(depth)))
         return rgba, depth
 
     def fill_colors(self, download=True):
