@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "glsl_compat.hpp"
+#include "../ro_raster.h"
 
 namespace glsl {
 struct S_pre_morph {
@@ -86,6 +87,30 @@ struct S_calib_vis_vs {
 struct S_calib_vis_fs {
   bool discarded = false;
 #include "calib_vis_fs.inc"
+};
+struct S_trigrid_vs {
+  vec4 gl_Position;
+#include "trigrid_vs.inc"
+};
+struct S_trigrid_gs {
+  struct { vec4 gl_Position; } gl_in[3];
+  vec4 gl_Position;
+  struct Emitted { vec4 pos; vec2 texcoord; vec3 pos_es, pos_cs, normal_es; float depth, quality; };
+  std::vector<Emitted> emitted;
+  void EmitVertex() { emitted.push_back(Emitted{gl_Position, pass_texcoord, pass_pos_es, pass_pos_cs, pass_normal_es, pass_depth, pass_quality}); }
+  void EndPrimitive() {}
+#include "trigrid_gs.inc"
+};
+struct S_trigrid_fs {
+  vec4 gl_FragCoord;
+  bool discarded = false;
+#include "trigrid_fs.inc"
+};
+struct S_trigrid_norm_fs {
+  vec4 gl_FragCoord, gl_FragColor;
+  float gl_FragDepth = 0.0f;
+  bool discarded = false;
+#include "trigrid_norm_fs.inc"
 };
 struct S_framebuffer_transfer {
 #include "framebuffer_transfer.inc"
@@ -655,5 +680,111 @@ void rg_draw_calibs(const float* tsdf, const uint32_t* res, int N, const float* 
           return !f.discarded;
         });
       }
+}
+// ReconTrigrid::draw (recon_trigrid.cpp:48-61 grid, :82-149 passes) with the reference's trigrid_accum.vs -> trigrid_accum.gs ->
+// fixed-function stages (oracle/ro_raster.h, the OpenGL 4.4 pipeline in fp64) -> trigrid_accum.fs, then trigrid_normalize.fs.
+// The vertex shader runs once per grid vertex (GL runs it per triangle corner on identical inputs). Pass 1: depth only, GL_LESS
+// against 1; pass 2: no depth test, glBlendFunc(ONE, ONE) into a cleared RGBA32F target, in draw order; pass 3: a screen quad.
+// uniforms16: gl_ModelViewMatrix, gl_ProjectionMatrix, gl_NormalMatrix, img_to_eye_curr.
+void rg_draw_trigrid(int N, int W, int H, const float* depth_b, const float* quality, const uint8_t* color, int CW, int CH,
+                     const float* cv_xyz, const float* cv_uv, const int32_t* cv_res, const float* bbox_min, const float* bbox_max,
+                     const float* uniforms16, int vw, int vh, int shade_mode, float min_length, float* out_rgba, float* out_depth) {
+  const size_t npx = (size_t)vw * vh;
+  for (size_t i = 0; i < npx; ++i) { out_rgba[i * 4] = out_rgba[i * 4 + 1] = out_rgba[i * 4 + 2] = out_rgba[i * 4 + 3] = 0.f; out_depth[i] = 1.f; }
+  if (N > 5) return;
+  sampler2DArray col;
+  col.u8 = color; col.W = CW; col.H = CH; col.L = N; col.C = 3; col.linear = true;
+  sampler2DArray d = tex2d(depth_b, W, H, 2, false), q = tex2d(quality, W, H, 1, true);
+  d.L = q.L = N;
+  const size_t cv_vox = (size_t)cv_res[0] * cv_res[1] * cv_res[2];
+  S_trigrid_vs vs{};
+  vs.kinect_depths = d; vs.kinect_qualities = q;
+  for (int i = 0; i < N; ++i) {
+    vs.cv_xyz[i] = tex3d(cv_xyz + (size_t)i * cv_vox * 3, cv_res[0], cv_res[1], cv_res[2], 3);
+    vs.cv_uv[i] = tex3d(cv_uv + (size_t)i * cv_vox * 2, cv_res[0], cv_res[1], cv_res[2], 2);
+  }
+  vs.gl_ModelViewMatrix = mat4(uniforms16); vs.gl_ProjectionMatrix = mat4(uniforms16 + 16);
+  S_trigrid_gs gs{};
+  gs.min_length = min_length;
+  std::vector<float> depth1(npx, 1.0f), accum(npx * 4, 0.0f);
+  S_trigrid_fs fs{};
+  fs.kinect_colors = col;
+  fs.depth_map_curr = tex2d(depth1.data(), vw, vh, 1, false);         // ViewArray's depth array is NEAREST (ViewArray.cpp:22)
+  fs.gl_NormalMatrix = mat4(uniforms16 + 32); fs.img_to_eye_curr = mat4(uniforms16 + 48);
+  fs.viewportSizeInv = vec2(1.0f / (float)vw, 1.0f / (float)vh);
+  fs.epsilon = 0.075f;                                               // recon_trigrid.cpp:35
+  fs.g_shade_mode = shade_mode;
+  fs.bbox_min = vec3(bbox_min[0], bbox_min[1], bbox_min[2]); fs.bbox_max = vec3(bbox_max[0], bbox_max[1], bbox_max[2]);
+
+  const int GW = H + 1, GH = W + 1;                                   // cells x < tex_height, y < tex_width, as :51-52 loop
+  const float stepX = 1.0f / (float)W, stepY = 1.0f / (float)H;
+  std::vector<S_trigrid_vs> verts;
+  verts.reserve((size_t)N * GW * GH);
+  for (int layer = 0; layer < N; ++layer)
+    for (int j = 0; j < GH; ++j)
+      for (int i = 0; i < GW; ++i) {
+        S_trigrid_vs v(vs);
+        v.layer = (uint)layer;
+        v.in_Position = vec2((float)(((double)i + 0.5) * (double)stepX), (float)(((double)j + 0.5) * (double)stepY));
+        v.main();
+        verts.push_back(v);
+      }
+  for (int stage = 0; stage < 2; ++stage)
+    for (int layer = 0; layer < N; ++layer)
+      for (int y = 0; y < W; ++y)
+        for (int x = 0; x < H; ++x)
+          for (int k = 0; k < 2; ++k) {
+            const S_trigrid_vs* g0 = verts.data() + (size_t)layer * GW * GH;
+            const S_trigrid_vs* tv[3] = {k == 0 ? g0 + (size_t)y * GW + x : g0 + (size_t)y * GW + x + 1,
+                                         k == 0 ? g0 + (size_t)y * GW + x + 1 : g0 + (size_t)(y + 1) * GW + x + 1, g0 + (size_t)(y + 1) * GW + x};
+            S_trigrid_gs g(gs);
+            for (int c = 0; c < 3; ++c) {
+              g.geo_texcoord[c] = tv[c]->geo_texcoord; g.geo_pos_es[c] = tv[c]->geo_pos_es; g.geo_pos_cs[c] = tv[c]->geo_pos_cs;
+              g.geo_depth[c] = tv[c]->geo_depth; g.geo_quality[c] = tv[c]->geo_quality; g.gl_in[c].gl_Position = tv[c]->gl_Position;
+            }
+            g.main();
+            if (g.emitted.size() < 3) continue;
+            const S_trigrid_gs::Emitted* e = g.emitted.data();
+            const float clip[3][4] = {{e[0].pos.x, e[0].pos.y, e[0].pos.z, e[0].pos.w}, {e[1].pos.x, e[1].pos.y, e[1].pos.z, e[1].pos.w},
+                                      {e[2].pos.x, e[2].pos.y, e[2].pos.z, e[2].pos.w}};
+            ro::raster_triangle(clip, vw, vh, [&](int fx, int fy, float zw, const double* B) {
+              S_trigrid_fs f(fs);
+              f.stage = (uint)stage; f.layer = (uint)layer;
+              f.gl_FragCoord = vec4((float)fx + 0.5f, (float)fy + 0.5f, zw, 1.0f);
+              f.pass_texcoord = vec2(ro::rinterp(B, e[0].texcoord.x, e[1].texcoord.x, e[2].texcoord.x), ro::rinterp(B, e[0].texcoord.y, e[1].texcoord.y, e[2].texcoord.y));
+              f.pass_pos_es = vec3(ro::rinterp(B, e[0].pos_es.x, e[1].pos_es.x, e[2].pos_es.x), ro::rinterp(B, e[0].pos_es.y, e[1].pos_es.y, e[2].pos_es.y),
+                                   ro::rinterp(B, e[0].pos_es.z, e[1].pos_es.z, e[2].pos_es.z));
+              f.pass_pos_cs = vec3(ro::rinterp(B, e[0].pos_cs.x, e[1].pos_cs.x, e[2].pos_cs.x), ro::rinterp(B, e[0].pos_cs.y, e[1].pos_cs.y, e[2].pos_cs.y),
+                                   ro::rinterp(B, e[0].pos_cs.z, e[1].pos_cs.z, e[2].pos_cs.z));
+              f.pass_normal_es = vec3(ro::rinterp(B, e[0].normal_es.x, e[1].normal_es.x, e[2].normal_es.x), ro::rinterp(B, e[0].normal_es.y, e[1].normal_es.y, e[2].normal_es.y),
+                                      ro::rinterp(B, e[0].normal_es.z, e[1].normal_es.z, e[2].normal_es.z));
+              f.pass_depth = ro::rinterp(B, e[0].depth, e[1].depth, e[2].depth);
+              f.pass_quality = ro::rinterp(B, e[0].quality, e[1].quality, e[2].quality);
+              f.main();
+              if (f.discarded) return;
+              const size_t o = (size_t)fy * vw + fx;
+              if (stage == 0) {
+                if (zw < depth1[o]) depth1[o] = zw;                      // GL_LESS, depth writes on
+              } else {
+                float* a = accum.data() + o * 4;                         // GL_FUNC_ADD, ONE, ONE
+                a[0] += f.gl_FragColor.x; a[1] += f.gl_FragColor.y; a[2] += f.gl_FragColor.z; a[3] += f.gl_FragColor.w;
+              }
+            });
+          }
+  S_trigrid_norm_fs nf{};
+  nf.color_map = tex2d(accum.data(), vw, vh, 4, true);
+  nf.depth_map = tex2d(depth1.data(), vw, vh, 1, false);
+  nf.texSizeInv = vec2(1.0f / (float)vw, 1.0f / (float)vh);
+  nf.offset = vec2(0.0f, 0.0f);
+  for (int y = 0; y < vh; ++y)
+    for (int x = 0; x < vw; ++x) {
+      S_trigrid_norm_fs f(nf);
+      f.gl_FragCoord = vec4((float)x + 0.5f, (float)y + 0.5f, 0.0f, 1.0f);
+      f.main();
+      if (f.discarded) continue;
+      const size_t o = (size_t)y * vw + x;
+      out_rgba[o * 4] = f.gl_FragColor.x; out_rgba[o * 4 + 1] = f.gl_FragColor.y; out_rgba[o * 4 + 2] = f.gl_FragColor.z; out_rgba[o * 4 + 3] = f.gl_FragColor.w;
+      out_depth[o] = f.gl_FragDepth;
+    }
 }
 }  // extern "C"

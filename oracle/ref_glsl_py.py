@@ -278,6 +278,29 @@ def draw_points(scene, pre, modelview, projection, width, height, shade_mode=0):
     return rgba, depth
 
 
+def draw_trigrid(scene, pre, modelview, projection, width, height, shade_mode=0, min_length=0.0125):
+    """ReconTrigrid::draw with the reference's glsl/trigrid_accum.vs, trigrid_accum.gs, trigrid_accum.fs (+ shading.glsl,
+    inc_bbox_test.glsl) and trigrid_normalize.fs through the fixed-function stages of oracle/ro_raster.h.
+    Returns (rgba [h,w,4], depth [h,w])."""
+    import oracle_py as O
+    L = lib()
+    L.rg_draw_trigrid.argtypes = [C.c_int, C.c_int, C.c_int, f32p, f32p, u8p, C.c_int, C.c_int, f32p, f32p, i32p, f32p, f32p, f32p,
+                                  C.c_int, C.c_int, C.c_int, C.c_float, f32p, f32p]
+    X, Y, Z = scene.cv_res
+    N, H, W = pre["quality"].shape
+    mv = np.ascontiguousarray(modelview, np.float32).reshape(16)
+    pr = np.ascontiguousarray(projection, np.float32).reshape(16)
+    bmin, bmax = np.ascontiguousarray(scene.bbox_min, np.float32), np.ascontiguousarray(scene.bbox_max, np.float32)
+    u = O.raymarch_uniforms(mv, pr, bmin, bmax, width, height)
+    uniforms = np.ascontiguousarray(np.concatenate([mv, pr, _gl_normal_matrix(mv), u[0:16]]), np.float32)
+    rgba, depth = np.zeros((height, width, 4), np.float32), np.zeros((height, width), np.float32)
+    L.rg_draw_trigrid(N, W, H, np.ascontiguousarray(pre["depth_b"], np.float32), np.ascontiguousarray(pre["quality"], np.float32),
+                      np.ascontiguousarray(scene.color), scene.CW, scene.CH, np.ascontiguousarray(scene.cv_xyz, np.float32),
+                      np.ascontiguousarray(scene.cv_uv, np.float32), np.array([X, Y, Z], np.int32), bmin, bmax, uniforms,
+                      int(width), int(height), int(shade_mode), float(min_length), rgba, depth)
+    return rgba, depth
+
+
 def draw_calibs(tsdf, inv, scene, layer, limit, modelview, projection, width, height):
     """ReconCalibs::draw with the reference's glsl/calib_vis.vs and calib_vis.fs over VolumeSampler's voxel centres."""
     draw_points.__doc__

@@ -453,6 +453,81 @@ def test_oracle_point_renderers_against_the_committed_shader_outputs(O):
     _assert_points(O.draw_calibs(tsdf, (20, 22, 20), 0.01, sc.bbox_min, sc.bbox_max, mv, pr, V["w"], V["h"]), (g["calibs_rgba"], g["calibs_depth"]), "calibs")
 
 
+def _assert_trigrid(got, want, what):
+    """Triangle-mesh renderings agree when coverage is the same up to a handful of pixels (a fragment test that lands on the
+    other side of a threshold), depth to 2e-5 (window depth of triangles cut by the near plane) and colour to 5e-5."""
+    (rgba, depth), (w_rgba, w_depth) = got, want
+    cov, w_cov = depth < 1.0, w_depth < 1.0
+    assert w_cov.sum() > 100, what
+    assert (cov != w_cov).sum() <= max(2, int(0.002 * w_cov.sum())), f"{what}: coverage differs on {(cov != w_cov).sum()} pixels"
+    both = cov & w_cov
+    assert np.abs(depth - w_depth)[both].max() <= 2e-5, what
+    d = np.abs(rgba - w_rgba)[both]
+    assert (d > 5e-5).any(axis=-1).sum() <= max(2, int(0.002 * both.sum())), f"{what}: colour differs by up to {d.max()}"
+
+
+def test_oracle_trigrid_matches_the_reference_shaders_run_on_cpu(O, small_scene, small_frame):
+    """ReconTrigrid::draw (SURVEY.md 8f-4): the oracle's restatement (oracle/ro_trigrid.cpp) against the reference's own
+    trigrid_accum.vs / .gs / .fs and trigrid_normalize.fs run on the CPU through the same fixed-function stages
+    (oracle/ro_raster.h), every shade mode, camera outside and inside the volume."""
+    import ref_glsl_py as G
+    if not G.available() or not hasattr(G.lib(), "rg_draw_trigrid"):
+        pytest.skip("oracle/_ref/libref_glsl.so not built with the trigrid shaders (needs the reference tree at build time)")
+    from rrpy import synth
+    sc, pre = small_scene, small_frame["pre"]
+    VW, VH = 200, 112
+    for eye in ((1.6, 1.5, 2.2), (0.2, 1.2, 0.3)):
+        mv, pr = synth.look_at(eye, (0.0, 1.1, 0.0)), synth.perspective(50.0, VW / VH, 0.1, 10.0)
+        for mode in range(4):
+            _assert_trigrid(O.draw_trigrid(sc, pre, mv, pr, VW, VH, mode, min_length=0.06), G.draw_trigrid(sc, pre, mv, pr, VW, VH, mode, min_length=0.06),
+                            f"trigrid eye {eye} mode {mode}")
+
+
+def test_oracle_trigrid_against_the_committed_shader_outputs(O):
+    """The same pin on machines without the reference tree: tests/golden/ref_glsl_trigrid.npz holds what the reference's shaders
+    drew for the golden scene (tools/make_golden.py::golden_glsl_trigrid)."""
+    from rrpy import synth
+    g = gold("ref_glsl_trigrid.npz")
+    sc = synth.make_scene(N=1, W=128, H=106, CW=160, CH=135, cv_res=(24, 24, 48), seed=77)    # tools/make_golden.py::glsl_scene
+    grid = O.brick_grid(sc.bbox_min, sc.bbox_max, float(g["voxel"]), 0.1)
+    cams = [O.frustum(sc.cv_xyz[i])[1] for i in range(sc.N)]
+    pre = O.preprocess(sc, grid, cams)
+    assert hashlib.sha256(np.ascontiguousarray(pre["quality"]).tobytes()).hexdigest() == str(g["quality_sha"]), "the golden's input maps changed"
+    V = dict(eye=(1.2, 1.4, 1.6), at=(0.0, 1.1, 0.0), fovy=50.0, w=160, h=90)                  # make_golden.py::RM_VIEW
+    pr = synth.perspective(V["fovy"], V["w"] / V["h"], 0.1, 10.0)
+    for tag, eye in (("", V["eye"]), ("in_", tuple(float(x) for x in g["eye_in"]))):
+        mv = synth.look_at(eye, V["at"])
+        for mode in range(4):
+            _assert_trigrid(O.draw_trigrid(sc, pre, mv, pr, V["w"], V["h"], mode, min_length=float(g["min_length"])),
+                            (g[f"{tag}rgba{mode}"], g[f"{tag}depth{mode}"]), f"trigrid {tag}mode {mode}")
+
+
+def test_the_rasteriser_partitions_a_shared_edge(O):
+    """The fixed-function stages' claim (oracle/ro_raster.h): two triangles that share an edge never both cover a pixel centre and
+    never leave one out - checked on the accumulation target: with one sensor, shade mode 3 and a fragment pass that keeps
+    everything within epsilon, the summed quality of a pixel is that of ONE fragment, i.e. rgb / alpha is the pure camera colour
+    and the alpha equals the interpolated quality, never twice it."""
+    from rrpy import synth
+    sc = synth.make_scene(N=1, W=128, H=106, CW=160, CH=135, cv_res=(24, 24, 48), seed=77)
+    grid = O.brick_grid(sc.bbox_min, sc.bbox_max, 0.035, 0.1)
+    pre = O.preprocess(sc, grid, [O.frustum(sc.cv_xyz[0])[1]])
+    mv, pr = synth.look_at((1.2, 1.4, 1.6), (0.0, 1.1, 0.0)), synth.perspective(50.0, 320 / 180, 0.1, 10.0)
+    rgba, depth, accum, depth1 = O.draw_trigrid(sc, pre, mv, pr, 320, 180, 3, min_length=0.06, want_passes=True)
+    cov = depth < 1.0
+    assert cov.sum() > 500
+    # every covered pixel holds the quality of one fragment: bounded by the map's maximum (two fragments would exceed it on
+    # the many pixels whose quality is above half of it)
+    qmax = float(pre["quality"].max())
+    assert accum[..., 3][cov].max() <= qmax * (1 + 1e-6)
+    hi = cov & (accum[..., 3] > 0.5 * qmax)
+    assert hi.sum() > 20
+    # and pass 1 covers exactly what pass 2 covers from the front surface (no seam holes inside the silhouette): a covered pixel's
+    # four neighbours are covered unless the pixel is on the silhouette; count isolated single-pixel holes
+    pad = np.pad(cov, 1)
+    holes = (~cov) & pad[:-2, 1:-1] & pad[2:, 1:-1] & pad[1:-1, :-2] & pad[1:-1, 2:]
+    assert holes.sum() <= 2, f"{holes.sum()} one-pixel holes inside the mesh"
+
+
 def test_depth_peels_from_the_reference_brick_shaders_and_a_rasteriser(O, small_scene, small_frame):
     """drawDepthLimits with the reference's bricks.vs / bricks.gs / bricks.fs and a rasteriser (glsl_harness.cpp::rg_depth_peels;
     the cube strip is read from unit_cube.cpp) against the ray-cast statement ref_glsl_py.depth_peels: same coverage, nearest and

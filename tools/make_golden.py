@@ -137,9 +137,35 @@ def golden_glsl_points():
     np.savez_compressed(os.path.join(OUT, "ref_glsl_points.npz"), voxel=np.float32(voxel), tsdf_sha=np.array(sha(tsdf)), **out)
 
 
+TRIGRID_MIN_LENGTH = 0.06     # the golden scene's depth pixels are ~2 cm apart (the reference's 0.0125 belongs to 512 x 424 sensors)
+
+
+def golden_glsl_trigrid():
+    """glsl/trigrid_accum.{vs,gs,fs} and trigrid_normalize.fs run on the CPU (oracle/glsl_host: ReconTrigrid::draw through the
+    OpenGL 4.4 fixed-function stages of oracle/ro_raster.h) on the ORACLE's stages of glsl_scene(), every shade mode, the
+    camera outside (RM_VIEW) and inside the volume (triangles cut by the near plane)."""
+    import ref_glsl_py as G
+    sc = glsl_scene()
+    voxel = 0.035
+    grid = O.brick_grid(sc.bbox_min, sc.bbox_max, voxel, 0.1)
+    cams = [O.frustum(sc.cv_xyz[i])[1] for i in range(sc.N)]
+    pre = O.preprocess(sc, grid, cams)
+    pr = synth.perspective(RM_VIEW["fovy"], RM_VIEW["w"] / RM_VIEW["h"], 0.1, 10.0)
+    out = {}
+    for tag, eye in (("", RM_VIEW["eye"]), ("in_", (0.3, 1.2, 0.4))):
+        mv = synth.look_at(eye, RM_VIEW["at"])
+        for mode in range(4):
+            out[f"{tag}rgba{mode}"], out[f"{tag}depth{mode}"] = G.draw_trigrid(sc, pre, mv, pr, RM_VIEW["w"], RM_VIEW["h"], mode, TRIGRID_MIN_LENGTH)
+    np.savez_compressed(os.path.join(OUT, "ref_glsl_trigrid.npz"), voxel=np.float32(voxel), min_length=np.float32(TRIGRID_MIN_LENGTH),
+                        quality_sha=np.array(sha(pre["quality"])), eye_in=np.array((0.3, 1.2, 0.4), np.float32), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     assert R.available(), "build oracle/_ref first (make -C oracle all)"
+    if "--only-trigrid" in sys.argv:
+        golden_glsl_trigrid()
+        return
     if "--only-points" in sys.argv:
         golden_glsl_points()
         return
@@ -154,6 +180,7 @@ def main():
     golden_dxt1()
     golden_dxt5()
     golden_glsl_points()
+    golden_glsl_trigrid()
     golden_glsl()
     golden_glsl_raymarch()
     sc = golden_scene()
