@@ -17,39 +17,39 @@ namespace rr {
 static_assert(TILE_X * TILE_Y == 256, "k_bilateral fills its 256-entry byte table with one entry per thread");
 
 // ------------------------------------------------------------------------------------------------ pre_morph
-// glsl/pre_morph.fs:73-112 dilate(kernel 1), main mode 0; mode 1 is a copy and is folded away.
+// glsl/pre_morph.fs:73-112 dilate(kernel 1), main mode 0; mode 1 is a copy and is folded away. nb = the 3x3 neighbourhood
+// (row-major, CLAMP_TO_EDGE), read only when the centre is not a valid depth.
+__device__ __forceinline__ float morph_value(float depth, const float* nb) {
+  const float min_depth = 0.5f, max_depth = 4.5f, max_dist = 0.2f;
+  if (depth > min_depth && depth < max_depth) return depth;
+  float average_depth = 0.0f, num = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 9; ++i)
+    if (nb[i] > min_depth && nb[i] < max_depth) { average_depth += nb[i]; num += 1.0f; }
+  if (num == 0.0f) return 0.0f;
+  average_depth /= num;
+  float new_depth = 0.0f;
+  num = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 9; ++i)
+    if (nb[i] > min_depth && nb[i] < max_depth && fabsf(average_depth - nb[i]) < max_dist) { new_depth += nb[i]; num += 1.0f; }
+  return (num == 0.0f) ? 0.0f : new_depth / num;
+}
+
 __global__ void __launch_bounds__(256) k_morph(const float* __restrict__ in, float* __restrict__ out, int W, int H) {
   const int px = blockIdx.x * TILE_X + threadIdx.x, py = blockIdx.y * TILE_Y + threadIdx.y;
   if (px >= W || py >= H) return;
   const float* img = in + (size_t)blockIdx.z * W * H;
-  const float min_depth = 0.5f, max_depth = 4.5f, max_dist = 0.2f;
+  float nb[9];
   const float depth = img[(size_t)py * W + px];
-  float result;
-  if (depth > min_depth && depth < max_depth) {
-    result = depth;
-  } else {
-    float nb[9];
+  if (!(depth > 0.5f && depth < 4.5f)) {
 #pragma unroll
     for (int y = -1; y < 2; ++y)
 #pragma unroll
       for (int x = -1; x < 2; ++x)
         nb[(y + 1) * 3 + (x + 1)] = img[(size_t)iclamp(py + y, 0, H - 1) * W + iclamp(px + x, 0, W - 1)];
-    float average_depth = 0.0f, num = 0.0f;
-#pragma unroll
-    for (int i = 0; i < 9; ++i)
-      if (nb[i] > min_depth && nb[i] < max_depth) { average_depth += nb[i]; num += 1.0f; }
-    if (num == 0.0f) {
-      result = 0.0f;
-    } else {
-      average_depth /= num;
-      float new_depth = 0.0f;
-      num = 0.0f;
-#pragma unroll
-      for (int i = 0; i < 9; ++i)
-        if (nb[i] > min_depth && nb[i] < max_depth && fabsf(average_depth - nb[i]) < max_dist) { new_depth += nb[i]; num += 1.0f; }
-      result = (num == 0.0f) ? 0.0f : new_depth / num;
-    }
   }
+  const float result = morph_value(depth, nb);
   out[(size_t)blockIdx.z * W * H + (size_t)py * W + px] = result;
 }
 
@@ -80,12 +80,17 @@ struct DepthParams {
 // glsl/pre_depth.fs:129-154 main + :85-127 bilateral_filter (13x13, linear space/range kernels).
 __global__ void __launch_bounds__(256) k_bilateral(const float* __restrict__ depth_in, const uint8_t* __restrict__ color,
                                                    float2* __restrict__ out_depth, float4* __restrict__ out_lab,
-                                                   int W, int H, int CW, int CH,
+                                                   float* __restrict__ out_morph, int W, int H, int CW, int CH,
                                                    const __grid_constant__ SensorTables st, const __grid_constant__ DepthParams dp) {
   // Tile of the 13x13 neighbourhoods. A sample the shader would skip because it lies outside the depth limits
   // (is_outside, pre_depth.fs:40-42) is stored as +inf: |inf - depth| = inf exceeds every finite range threshold, so the
   // single range comparison below also rejects it. The centre depth itself is kept in a register, untouched.
+  // out_morph != null: depth_in is the RAW depth and pre_morph.fs runs here, on a raw tile one pixel wider all round
+  // (k_morph's arithmetic per tile element; the CTA's own pixels are also written to the morph stage image) - one launch
+  // and one pass over the depth image less.
   __shared__ float tile[SM_H][SM_W];
+  __shared__ float raw[SM_H + 2][SM_W + 2];
+  __shared__ float centre[TILE_Y][TILE_X];
   __shared__ float byte_lut[256];          // c / 255 of the colour fetch (tex2d_rgb8_lut)
   const int layer = blockIdx.z;
   const float* img = depth_in + (size_t)layer * W * H;
@@ -98,16 +103,46 @@ __global__ void __launch_bounds__(256) k_bilateral(const float* __restrict__ dep
     if (compress) d = (d < dp.scaled_near[layer]) ? 0.0f : (d * d + 0.15f * dp.scaled_near[layer]) * dp.scale[layer] + dp.near_[layer];
     return d;
   };
-  for (int i = tid; i < SM_W * SM_H; i += TILE_X * TILE_Y) {
-    int ty = i / SM_W, tx = i - ty * SM_W;
-    const float d = decode(img[(size_t)iclamp(by + ty - KS, 0, H - 1) * W + iclamp(bx + tx - KS, 0, W - 1)]);
-    tile[ty][tx] = ((d < cv_min) || (d > cv_max)) ? __int_as_float(0x7f800000) : d;
+  if (out_morph) {
+    for (int i = tid; i < (SM_W + 2) * (SM_H + 2); i += TILE_X * TILE_Y) {
+      const int ty = i / (SM_W + 2), tx = i - ty * (SM_W + 2);
+      raw[ty][tx] = img[(size_t)iclamp(by + ty - KS - 1, 0, H - 1) * W + iclamp(bx + tx - KS - 1, 0, W - 1)];
+    }
+    __syncthreads();
+    for (int i = tid; i < SM_W * SM_H; i += TILE_X * TILE_Y) {
+      const int ty = i / SM_W, tx = i - ty * SM_W;
+      // the tile element is the image pixel (cx, cy) after CLAMP_TO_EDGE; its 3x3 neighbourhood clamps around THAT pixel
+      const int cx = iclamp(bx + tx - KS, 0, W - 1), cy = iclamp(by + ty - KS, 0, H - 1);
+      const int rx = cx - bx + KS + 1, ry = cy - by + KS + 1;
+      float nb[9];
+      const float d0 = raw[ry][rx];
+      if (!(d0 > 0.5f && d0 < 4.5f)) {
+#pragma unroll
+        for (int y = -1; y < 2; ++y)
+#pragma unroll
+          for (int x = -1; x < 2; ++x) nb[(y + 1) * 3 + (x + 1)] = raw[ry + y][rx + x];
+      }
+      const float m = morph_value(d0, nb);
+      const int ly = ty - KS, lx = tx - KS;
+      if (ly >= 0 && ly < TILE_Y && lx >= 0 && lx < TILE_X) {
+        centre[ly][lx] = m;
+        if (by + ly < H && bx + lx < W) out_morph[(size_t)layer * W * H + (size_t)(by + ly) * W + (bx + lx)] = m;
+      }
+      const float d = decode(m);
+      tile[ty][tx] = ((d < cv_min) || (d > cv_max)) ? __int_as_float(0x7f800000) : d;
+    }
+  } else {
+    for (int i = tid; i < SM_W * SM_H; i += TILE_X * TILE_Y) {
+      int ty = i / SM_W, tx = i - ty * SM_W;
+      const float d = decode(img[(size_t)iclamp(by + ty - KS, 0, H - 1) * W + iclamp(bx + tx - KS, 0, W - 1)]);
+      tile[ty][tx] = ((d < cv_min) || (d > cv_max)) ? __int_as_float(0x7f800000) : d;
+    }
   }
   __syncthreads();
   const int px = bx + threadIdx.x, py = by + threadIdx.y;
   if (px >= W || py >= H) return;
   const float tcx = ((float)px + 0.5f) / (float)W, tcy = ((float)py + 0.5f) / (float)H;
-  const float depth = decode(img[(size_t)py * W + px]);
+  const float depth = decode(out_morph ? centre[threadIdx.y][threadIdx.x] : img[(size_t)py * W + px]);
   const float depth_norm = (depth - cv_min) / (cv_max - cv_min);
   const float3 pos_world = tex3d_xyz(st.xyz[layer], st.cx[layer], st.cy[layer], st.cz[layer], tcx, tcy, depth_norm);
   const bool in_box = pos_world.x >= dp.bmin[0] && pos_world.y >= dp.bmin[1] && pos_world.z >= dp.bmin[2] &&
@@ -147,7 +182,16 @@ __global__ void __launch_bounds__(256) k_bilateral(const float* __restrict__ dep
     for (int y = -KS; y <= KS; ++y) {
 #pragma unroll 1
       for (int x = -KS; x <= KS; ++x) {
-        const float depth_s = decode(img[(size_t)iclamp(py + y, 0, H - 1) * W + iclamp(px + x, 0, W - 1)]);
+        float depth_s;
+        if (out_morph) {                      // pre_morph.fs of the sample, straight from the raw image
+          const int sx = iclamp(px + x, 0, W - 1), sy = iclamp(py + y, 0, H - 1);
+          float nb[9];
+          for (int yy = -1; yy < 2; ++yy)
+            for (int xx = -1; xx < 2; ++xx) nb[(yy + 1) * 3 + (xx + 1)] = img[(size_t)iclamp(sy + yy, 0, H - 1) * W + iclamp(sx + xx, 0, W - 1)];
+          depth_s = decode(morph_value(nb[4], nb));
+        } else {
+          depth_s = decode(img[(size_t)iclamp(py + y, 0, H - 1) * W + iclamp(px + x, 0, W - 1)]);
+        }
         const float depth_range = fabsf(depth_s - depth);
         if ((depth_s < cv_min) || (depth_s > cv_max) || (depth_range > dist_range_max)) continue;
         const float gauss_range = 1.0f - gmin(depth_range, dist_range_max) * dist_range_max_inv;
@@ -367,6 +411,141 @@ __global__ void __launch_bounds__(256) k_quality(const float2* __restrict__ dept
   emit(q);
 }
 
+// ------------------------------------------------------------------------------------------------ pre_normal + pre_quality
+// The two passes in one launch: pre_normal.fs is per pixel over depth_b's 4-neighbourhood, which pre_quality.fs's 13x13 tile
+// already holds (its +inf code for a sample outside (0, 1) is pre_normal's is_outside), the normal feeds pre_quality's angle term
+// from registers, and the centre's world position (the same tex3d_xyz of the same coordinates in both shaders) is fetched once.
+// The four neighbour fetches are issued ahead of the 169-tap loop, whose arithmetic hides their latency. Every value is
+// computed by the expressions of k_normal / k_quality above: bit-identical stage images and brick counters.
+__global__ void __launch_bounds__(256) k_normal_quality(const float2* __restrict__ depth_b, float4* __restrict__ out_normal,
+                                                        uint32_t* __restrict__ bricks, float* __restrict__ out_quality,
+                                                        const float* __restrict__ sil, float2* __restrict__ pairs, int pair_pitch,
+                                                        uint32_t* __restrict__ flags, int W, int H,
+                                                        const __grid_constant__ SensorTables st, const __grid_constant__ BrickParams bp) {
+  __shared__ float tile[SM_H][SM_W];
+  const int layer = blockIdx.z;
+  const size_t base = (size_t)layer * W * H;
+  const int bx = blockIdx.x * TILE_X, by = blockIdx.y * TILE_Y;
+  const int tid = threadIdx.y * TILE_X + threadIdx.x;
+  for (int i = tid; i < SM_W * SM_H; i += TILE_X * TILE_Y) {
+    int ty = i / SM_W, tx = i - ty * SM_W;
+    const float d = depth_b[base + (size_t)iclamp(by + ty - KS, 0, H - 1) * W + iclamp(bx + tx - KS, 0, W - 1)].x;
+    tile[ty][tx] = ((d <= 0.0f) || (d >= 1.0f)) ? __int_as_float(0x7f800000) : d;
+  }
+  __syncthreads();
+  const int px = bx + threadIdx.x, py = by + threadIdx.y;
+  const bool inside = (px < W && py < H);
+  const size_t o = base + (size_t)(inside ? py : 0) * W + (inside ? px : 0);
+  const float depth = inside ? depth_b[o].x : 0.0f;
+  const bool valid = inside && !((depth <= 0.0f) || (depth >= 1.0f));          // a NaN centre is valid, as in both shaders
+  const float4* xyz = st.xyz[layer];
+  const int CX = st.cx[layer], CY = st.cy[layer], CZ = st.cz[layer];
+  const float tcx = ((float)px + 0.5f) / (float)W, tcy = ((float)py + 0.5f) / (float)H;
+  // ---- pre_normal.fs:26-56 + inc_bricks.glsl:40-58 (k_normal) ----
+  uint32_t id_own = 0, id_nb = 0;
+  bool add_own = false, add_nb = false;
+  float3 world = make_float3(0.f, 0.f, 0.f);
+  if (valid) {
+    world = tex3d_xyz(xyz, CX, CY, CZ, tcx, tcy, depth);
+    const float3 bmin = make_float3(bp.bmin[0], bp.bmin[1], bp.bmin[2]);
+    const float3 rel = (world - bmin) / bp.brick_size;
+    const uint32_t ix = f2u_sat(floorf(rel.x)), iy = f2u_sat(floorf(rel.y)), iz = f2u_sat(floorf(rel.z));
+    const float3 fidx = make_float3((float)ix, (float)iy, (float)iz);
+    const float hb = 0.5f * bp.brick_size;
+    const float3 center = (fidx * bp.brick_size + bmin) + make_float3(hb, hb, hb);
+    const float3 diff = world - center;
+    const float3 d_abs = make_float3(fabsf(diff.x), fabsf(diff.y), fabsf(diff.z));
+    const float min_v = gmax(d_abs.x, gmax(d_abs.y, d_abs.z));
+    const float cx = (d_abs.x < min_v) ? 0.0f : 1.0f, cy = (d_abs.y < min_v) ? 0.0f : 1.0f, cz = (d_abs.z < min_v) ? 0.0f : 1.0f;
+    const int ox = (int)gsign(diff.x * cx), oy = (int)gsign(diff.y * cy), oz = (int)gsign(diff.z * cz);
+    const int nx = iclamp((int)ix + ox, 0, (int)(bp.res[0] - 1u));
+    const int ny = iclamp((int)iy + oy, 0, (int)(bp.res[1] - 1u));
+    const int nz = iclamp((int)iz + oz, 0, (int)(bp.res[2] - 1u));
+    id_nb = (uint32_t)nz * bp.res[1] * bp.res[0] + (uint32_t)ny * bp.res[0] + (uint32_t)nx;
+    add_nb = (d_abs.x > bp.brick_size * 0.1f) && id_nb < bp.num;
+    id_own = iz * bp.res[1] * bp.res[0] + iy * bp.res[0] + ix;
+    add_own = id_own < bp.num;
+  }
+  brick_add(bricks, id_nb, add_nb);
+  brick_add(bricks, id_own, add_own);
+  if (!inside) return;
+  auto emit = [&](float q) {
+    out_quality[o] = q;
+    if (!pairs) return;
+    uint32_t bits = __float_as_uint(q);
+    if ((bits >> 31) && !(q != q) && q != 0.0f) atomicAdd(flags, 1u);
+    bits &= 0x7fffffffu;
+    if (sil[o] >= 1.0f) bits |= 0x80000000u;
+    const float2 v = make_float2(depth, __uint_as_float(bits));
+    float2* img = pairs + (size_t)layer * (H + 2) * pair_pitch;
+    const int xs0 = px + 1, xs1 = (px == 0) ? 0 : ((px == W - 1) ? W + 1 : -1);
+    const int ys0 = py + 1, ys1 = (py == 0) ? 0 : ((py == H - 1) ? H + 1 : -1);
+    img[(size_t)ys0 * pair_pitch + xs0] = v;
+    if (xs1 >= 0) img[(size_t)ys0 * pair_pitch + xs1] = v;
+    if (ys1 >= 0) img[(size_t)ys1 * pair_pitch + xs0] = v;
+    if (xs1 >= 0 && ys1 >= 0) img[(size_t)ys1 * pair_pitch + xs1] = v;
+    if (W == 1 && px == 0) {
+      img[(size_t)ys0 * pair_pitch + 2] = v;
+      if (ys1 >= 0) img[(size_t)ys1 * pair_pitch + 2] = v;
+    }
+    if (H == 1 && py == 0) {
+      img[(size_t)2 * pair_pitch + xs0] = v;
+      if (xs1 >= 0) img[(size_t)2 * pair_pitch + xs1] = v;
+      if (W == 1) img[(size_t)2 * pair_pitch + 2] = v;
+    }
+  };
+  if (!valid) { out_normal[o] = make_float4(0.f, 0.f, 0.f, 0.f); emit(0.0f); return; }
+  const float tsx = 1.0f / (float)W, tsy = 1.0f / (float)H;
+  const float tty = tcy + tsy, tby = tcy - tsy, tlx = tcx - tsx, trx = tcx + tsx;
+  const int cyi = threadIdx.y + KS, cxi = threadIdx.x + KS;
+  const float inf = __int_as_float(0x7f800000);
+  float depth_t = tile[cyi + 1][cxi], depth_bb = tile[cyi - 1][cxi], depth_l = tile[cyi][cxi - 1], depth_r = tile[cyi][cxi + 1];
+  depth_t = (depth_t == inf) ? depth : depth_t;            // is_outside(neighbour) ? depth : neighbour
+  depth_bb = (depth_bb == inf) ? depth : depth_bb;
+  depth_l = (depth_l == inf) ? depth : depth_l;
+  depth_r = (depth_r == inf) ? depth : depth_r;
+  const float3 world_t = tex3d_xyz(xyz, CX, CY, CZ, tcx, tty, depth_t);
+  const float3 world_b = tex3d_xyz(xyz, CX, CY, CZ, tcx, tby, depth_bb);
+  const float3 world_l = tex3d_xyz(xyz, CX, CY, CZ, tlx, tcy, depth_l);
+  const float3 world_r = tex3d_xyz(xyz, CX, CY, CZ, trx, tcy, depth_r);
+  // ---- pre_quality.fs:65-119 (k_quality) ----
+  const float dist_range_max = 0.35f * (depth / 1.0f);
+  const float dist_range_max_inv = 1.0f / dist_range_max;
+  float w_range = 0.0f, border = 0.0f;
+  if (depth - depth == 0.0f) {
+#pragma unroll
+    for (int y = 0; y <= 2 * KS; ++y) {
+#pragma unroll
+      for (int x = 0; x <= 2 * KS; ++x) {
+        const float depth_range = fabsf(tile[threadIdx.y + y][threadIdx.x + x] - depth);
+        if (depth_range > dist_range_max) { border += 1.0f; continue; }
+        w_range += 1.0f - depth_range * dist_range_max_inv;
+      }
+    }
+  } else {
+#pragma unroll 1
+    for (int y = -KS; y <= KS; ++y) {
+#pragma unroll 1
+      for (int x = -KS; x <= KS; ++x) {
+        const float depth_s = depth_b[base + (size_t)iclamp(py + y, 0, H - 1) * W + iclamp(px + x, 0, W - 1)].x;
+        const float depth_range = fabsf(depth_s - depth);
+        if ((depth_s <= 0.0f) || (depth_s >= 1.0f) || (depth_range > dist_range_max)) { border += 1.0f; continue; }
+        w_range += 1.0f - gmin(depth_range, dist_range_max) * dist_range_max_inv;
+      }
+    }
+  }
+  const float3 n = normalize3(cross3(world_b - world_t, world_l - world_r));
+  out_normal[o] = make_float4(n.x, n.y, n.z, 0.0f);
+  const float lateral_quality = 1.0f - border / 169.0f;
+  float q = gpow(lateral_quality, 6.0f);
+  q *= gpow(w_range / 169.0f, 6.0f);
+  q /= depth * 6.5f;
+  const float3 cam = make_float3(st.cam[layer][0], st.cam[layer][1], st.cam[layer][2]);
+  const float angle = dot3(normalize3(cam - world), n);
+  q *= gpow(angle, 2.0f);
+  emit(q);
+}
+
 // ------------------------------------------------------------------------------------------------ gather texels
 // Entry (ex, ey) in [0,W]x[0,H] serves the bilinear footprint whose unclamped lower-left texel is (ex-1, ey-1):
 //   .lo = depth_b.x at (x0,y0) (x1,y0) (x0,y1) (x1,y1);  .hi = quality at the same taps with the silhouette
@@ -405,10 +584,15 @@ int launch_preprocess(rr_ctx* c, int filter_textures, int use_processed_depth, i
   RR_TRY_RC(staged_prepare(c));            // decides which integrator the frame set is packed for (no-op unless settings changed)
   timer_begin(c, "1preprocess");
 
-  timer_begin(c, "morph");
-  k_morph<<<grd, blk, 0, s>>>(c->d_depth_raw, c->d_morph, W, H);
-  RR_LAUNCH_CHECK(c, "k_morph");
-  timer_end(c, "morph");
+  // pre_morph.fs: inside k_bilateral when its output feeds the bilateral pass (fuse_morph), else its own launch (the morph
+  // stage image is produced either way, like the reference's processDepth does regardless of useProcessedDepths)
+  const bool morph_inside = tunables().fuse_morph && use_processed_depth;
+  if (!morph_inside) {
+    timer_begin(c, "morph");
+    k_morph<<<grd, blk, 0, s>>>(c->d_depth_raw, c->d_morph, W, H);
+    RR_LAUNCH_CHECK(c, "k_morph");
+    timer_end(c, "morph");
+  }
 
   timer_begin(c, "bilateral");
   DepthParams dp{};
@@ -421,8 +605,8 @@ int launch_preprocess(rr_ctx* c, int filter_textures, int use_processed_depth, i
     dp.scale[i] = c->depth_far[i] - c->depth_near[i];
     dp.scaled_near[i] = dp.scale[i] / 255.0f;
   }
-  k_bilateral<<<grd, blk, 0, s>>>(use_processed_depth ? c->d_morph : c->d_depth_raw, c->d_color, c->d_depth, c->d_lab,
-                                  W, H, c->CW, c->CH, st, dp);
+  k_bilateral<<<grd, blk, 0, s>>>((use_processed_depth && !morph_inside) ? c->d_morph : c->d_depth_raw, c->d_color, c->d_depth, c->d_lab,
+                                  morph_inside ? c->d_morph : nullptr, W, H, c->CW, c->CH, st, dp);
   RR_LAUNCH_CHECK(c, "k_bilateral");
   timer_end(c, "bilateral");
 
@@ -431,21 +615,27 @@ int launch_preprocess(rr_ctx* c, int filter_textures, int use_processed_depth, i
   RR_LAUNCH_CHECK(c, "k_boundary");
   timer_end(c, "boundary");
 
-  timer_begin(c, "normal");
   BrickParams bp{};
   for (int a = 0; a < 3; ++a) { bp.bmin[a] = c->bbox_min[a]; bp.res[a] = c->bricks.res[a]; }
   bp.brick_size = c->bricks.brick_size;
   bp.num = c->bricks.num;
-  k_normal<<<grd, blk, 0, s>>>(c->d_depth_b, c->d_normal, c->d_counters, W, H, st, bp);
-  RR_LAUNCH_CHECK(c, "k_normal");
-  timer_end(c, "normal");
-
-  timer_begin(c, "quality");
   // The staged integrator reads the pair image k_quality writes on its way out; the 32-byte gather texels of the direct
   // kernels (dense mode, configurations the staged kernel declines) cost one more pass and are built only when needed.
   const bool staged = staged_selected(c);
-  k_quality<<<grd, blk, 0, s>>>(c->d_depth_b, c->d_normal, c->d_quality, c->d_sil, c->d_pairs, c->pair_pitch, c->d_flags, W, H, st);
-  RR_LAUNCH_CHECK(c, "k_quality");
+  if (tunables().fuse_nq) {
+    timer_begin(c, "quality");
+    k_normal_quality<<<grd, blk, 0, s>>>(c->d_depth_b, c->d_normal, c->d_counters, c->d_quality, c->d_sil, c->d_pairs, c->pair_pitch,
+                                         c->d_flags, W, H, st, bp);
+    RR_LAUNCH_CHECK(c, "k_normal_quality");
+  } else {
+    timer_begin(c, "normal");
+    k_normal<<<grd, blk, 0, s>>>(c->d_depth_b, c->d_normal, c->d_counters, W, H, st, bp);
+    RR_LAUNCH_CHECK(c, "k_normal");
+    timer_end(c, "normal");
+    timer_begin(c, "quality");
+    k_quality<<<grd, blk, 0, s>>>(c->d_depth_b, c->d_normal, c->d_quality, c->d_sil, c->d_pairs, c->pair_pitch, c->d_flags, W, H, st);
+    RR_LAUNCH_CHECK(c, "k_quality");
+  }
   if (!staged) {
     const dim3 grd_g((W + 1 + TILE_X - 1) / TILE_X, (H + 1 + TILE_Y - 1) / TILE_Y, N);
     k_pack_gather<<<grd_g, blk, 0, s>>>(c->d_depth_b, c->d_quality, c->d_sil, c->d_gather, c->d_flags, W, H);
