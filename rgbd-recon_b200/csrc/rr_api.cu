@@ -975,7 +975,6 @@ int rr_set_tunable(const char* name, int value) {
   else if (n == "stage_bulk_fill") t.stage_bulk_fill = value;
   else if (n == "trigrid_pool") t.trigrid_pool = value;
   else if (n == "fuse_nq") t.fuse_nq = value;
-  else if (n == "fuse_morph") t.fuse_morph = value;
   else return RR_ERR_INVALID;
   ++t.generation;              // captured frame graphs bake the launch shapes in: stale keys never match again
   return RR_OK;

@@ -222,7 +222,6 @@ struct Tunables {
  int stage_tail_cap = 2;     // items in flight per CTA towards the end of the item list (0: the ring's capacity throughout)
   int stage_ctas = 0;         // CTAs of the staged integrator (0: one per SM)
   int stage_fill_lsu = 0;     // 1: rows without occupied bricks are cleared by per-lane stores instead of bulk stores
-XX
   int fuse_nq = 1;            // pre_normal + pre_quality in one launch (k_normal_quality; 0: the two kernels)
   int trigrid_pool = 64;      // rr_draw_trigrid: initial capacity of the fragment pool, in fragments per 16 view pixels (it grows on demand)
   int stage_debug = 0;  // measurement only, results are WRONG: bit 0 skips the clear stream, bit 1 the brick evaluation

@@ -2,8 +2,9 @@
 // passes per sensor (framework/NetKinectArray.cpp:251-290, 311-428; glsl/pre_morph.fs, pre_depth.fs,
 // pre_boundary.fs, pre_normal.fs + inc_bricks.glsl, pre_quality.fs). One launch per pass covers all sensors
 // (blockIdx.z = sensor layer). The 13x13 passes stage a (32+12)x(8+12) depth tile in shared memory; brick
-// occupancy counts are aggregated per warp (__match_any_sync) before one RED per distinct brick.
-// A sixth kernel packs depth_b / quality / silhouette into the 32-byte gather texels the integrator reads.
+// occupancy counts are aggregated per warp (__match_any_sync) before one RED per distinct brick. pre_normal and pre_quality
+// run as ONE launch (k_normal_quality; the separate kernels stay behind the tunable fuse_nq = 0).
+// A further kernel packs depth_b / quality / silhouette into the 32-byte gather texels the integrator reads.
 #include "rr_context.h"
 #include "rr_math.cuh"
 
@@ -17,39 +18,39 @@ namespace rr {
 static_assert(TILE_X * TILE_Y == 256, "k_bilateral fills its 256-entry byte table with one entry per thread");
 
 // ------------------------------------------------------------------------------------------------ pre_morph
-// glsl/pre_morph.fs:73-112 dilate(kernel 1), main mode 0; mode 1 is a copy and is folded away. nb = the 3x3 neighbourhood
-// (row-major, CLAMP_TO_EDGE), read only when the centre is not a valid depth.
-__device__ __forceinline__ float morph_value(float depth, const float* nb) {
-  const float min_depth = 0.5f, max_depth = 4.5f, max_dist = 0.2f;
-  if (depth > min_depth && depth < max_depth) return depth;
-  float average_depth = 0.0f, num = 0.0f;
-#pragma unroll
-  for (int i = 0; i < 9; ++i)
-    if (nb[i] > min_depth && nb[i] < max_depth) { average_depth += nb[i]; num += 1.0f; }
-  if (num == 0.0f) return 0.0f;
-  average_depth /= num;
-  float new_depth = 0.0f;
-  num = 0.0f;
-#pragma unroll
-  for (int i = 0; i < 9; ++i)
-    if (nb[i] > min_depth && nb[i] < max_depth && fabsf(average_depth - nb[i]) < max_dist) { new_depth += nb[i]; num += 1.0f; }
-  return (num == 0.0f) ? 0.0f : new_depth / num;
-}
-
+// glsl/pre_morph.fs:73-112 dilate(kernel 1), main mode 0; mode 1 is a copy and is folded away.
 __global__ void __launch_bounds__(256) k_morph(const float* __restrict__ in, float* __restrict__ out, int W, int H) {
   const int px = blockIdx.x * TILE_X + threadIdx.x, py = blockIdx.y * TILE_Y + threadIdx.y;
   if (px >= W || py >= H) return;
   const float* img = in + (size_t)blockIdx.z * W * H;
-  float nb[9];
+  const float min_depth = 0.5f, max_depth = 4.5f, max_dist = 0.2f;
   const float depth = img[(size_t)py * W + px];
-  if (!(depth > 0.5f && depth < 4.5f)) {
+  float result;
+  if (depth > min_depth && depth < max_depth) {
+    result = depth;
+  } else {
+    float nb[9];
 #pragma unroll
     for (int y = -1; y < 2; ++y)
 #pragma unroll
       for (int x = -1; x < 2; ++x)
         nb[(y + 1) * 3 + (x + 1)] = img[(size_t)iclamp(py + y, 0, H - 1) * W + iclamp(px + x, 0, W - 1)];
+    float average_depth = 0.0f, num = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 9; ++i)
+      if (nb[i] > min_depth && nb[i] < max_depth) { average_depth += nb[i]; num += 1.0f; }
+    if (num == 0.0f) {
+      result = 0.0f;
+    } else {
+      average_depth /= num;
+      float new_depth = 0.0f;
+      num = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 9; ++i)
+        if (nb[i] > min_depth && nb[i] < max_depth && fabsf(average_depth - nb[i]) < max_dist) { new_depth += nb[i]; num += 1.0f; }
+      result = (num == 0.0f) ? 0.0f : new_depth / num;
+    }
   }
-  const float result = morph_value(depth, nb);
   out[(size_t)blockIdx.z * W * H + (size_t)py * W + px] = result;
 }
 
@@ -80,17 +81,12 @@ struct DepthParams {
 // glsl/pre_depth.fs:129-154 main + :85-127 bilateral_filter (13x13, linear space/range kernels).
 __global__ void __launch_bounds__(256) k_bilateral(const float* __restrict__ depth_in, const uint8_t* __restrict__ color,
                                                    float2* __restrict__ out_depth, float4* __restrict__ out_lab,
-                                                   float* __restrict__ out_morph, int W, int H, int CW, int CH,
+                                                   int W, int H, int CW, int CH,
                                                    const __grid_constant__ SensorTables st, const __grid_constant__ DepthParams dp) {
   // Tile of the 13x13 neighbourhoods. A sample the shader would skip because it lies outside the depth limits
   // (is_outside, pre_depth.fs:40-42) is stored as +inf: |inf - depth| = inf exceeds every finite range threshold, so the
   // single range comparison below also rejects it. The centre depth itself is kept in a register, untouched.
-  // out_morph != null: depth_in is the RAW depth and pre_morph.fs runs here, on a raw tile one pixel wider all round
-  // (k_morph's arithmetic per tile element; the CTA's own pixels are also written to the morph stage image) - one launch
-  // and one pass over the depth image less.
   __shared__ float tile[SM_H][SM_W];
-  __shared__ float raw[SM_H + 2][SM_W + 2];
-  __shared__ float centre[TILE_Y][TILE_X];
   __shared__ float byte_lut[256];          // c / 255 of the colour fetch (tex2d_rgb8_lut)
   const int layer = blockIdx.z;
   const float* img = depth_in + (size_t)layer * W * H;
@@ -103,46 +99,16 @@ __global__ void __launch_bounds__(256) k_bilateral(const float* __restrict__ dep
     if (compress) d = (d < dp.scaled_near[layer]) ? 0.0f : (d * d + 0.15f * dp.scaled_near[layer]) * dp.scale[layer] + dp.near_[layer];
     return d;
   };
-  if (out_morph) {
-    for (int i = tid; i < (SM_W + 2) * (SM_H + 2); i += TILE_X * TILE_Y) {
-      const int ty = i / (SM_W + 2), tx = i - ty * (SM_W + 2);
-      raw[ty][tx] = img[(size_t)iclamp(by + ty - KS - 1, 0, H - 1) * W + iclamp(bx + tx - KS - 1, 0, W - 1)];
-    }
-    __syncthreads();
-    for (int i = tid; i < SM_W * SM_H; i += TILE_X * TILE_Y) {
-      const int ty = i / SM_W, tx = i - ty * SM_W;
-      // the tile element is the image pixel (cx, cy) after CLAMP_TO_EDGE; its 3x3 neighbourhood clamps around THAT pixel
-      const int cx = iclamp(bx + tx - KS, 0, W - 1), cy = iclamp(by + ty - KS, 0, H - 1);
-      const int rx = cx - bx + KS + 1, ry = cy - by + KS + 1;
-      float nb[9];
-      const float d0 = raw[ry][rx];
-      if (!(d0 > 0.5f && d0 < 4.5f)) {
-#pragma unroll
-        for (int y = -1; y < 2; ++y)
-#pragma unroll
-          for (int x = -1; x < 2; ++x) nb[(y + 1) * 3 + (x + 1)] = raw[ry + y][rx + x];
-      }
-      const float m = morph_value(d0, nb);
-      const int ly = ty - KS, lx = tx - KS;
-      if (ly >= 0 && ly < TILE_Y && lx >= 0 && lx < TILE_X) {
-        centre[ly][lx] = m;
-        if (by + ly < H && bx + lx < W) out_morph[(size_t)layer * W * H + (size_t)(by + ly) * W + (bx + lx)] = m;
-      }
-      const float d = decode(m);
-      tile[ty][tx] = ((d < cv_min) || (d > cv_max)) ? __int_as_float(0x7f800000) : d;
-    }
-  } else {
-    for (int i = tid; i < SM_W * SM_H; i += TILE_X * TILE_Y) {
-      int ty = i / SM_W, tx = i - ty * SM_W;
-      const float d = decode(img[(size_t)iclamp(by + ty - KS, 0, H - 1) * W + iclamp(bx + tx - KS, 0, W - 1)]);
-      tile[ty][tx] = ((d < cv_min) || (d > cv_max)) ? __int_as_float(0x7f800000) : d;
-    }
+  for (int i = tid; i < SM_W * SM_H; i += TILE_X * TILE_Y) {
+    int ty = i / SM_W, tx = i - ty * SM_W;
+    const float d = decode(img[(size_t)iclamp(by + ty - KS, 0, H - 1) * W + iclamp(bx + tx - KS, 0, W - 1)]);
+    tile[ty][tx] = ((d < cv_min) || (d > cv_max)) ? __int_as_float(0x7f800000) : d;
   }
   __syncthreads();
   const int px = bx + threadIdx.x, py = by + threadIdx.y;
   if (px >= W || py >= H) return;
   const float tcx = ((float)px + 0.5f) / (float)W, tcy = ((float)py + 0.5f) / (float)H;
-  const float depth = decode(out_morph ? centre[threadIdx.y][threadIdx.x] : img[(size_t)py * W + px]);
+  const float depth = decode(img[(size_t)py * W + px]);
   const float depth_norm = (depth - cv_min) / (cv_max - cv_min);
   const float3 pos_world = tex3d_xyz(st.xyz[layer], st.cx[layer], st.cy[layer], st.cz[layer], tcx, tcy, depth_norm);
   const bool in_box = pos_world.x >= dp.bmin[0] && pos_world.y >= dp.bmin[1] && pos_world.z >= dp.bmin[2] &&
@@ -182,16 +148,7 @@ __global__ void __launch_bounds__(256) k_bilateral(const float* __restrict__ dep
     for (int y = -KS; y <= KS; ++y) {
 #pragma unroll 1
       for (int x = -KS; x <= KS; ++x) {
-        float depth_s;
-        if (out_morph) {                      // pre_morph.fs of the sample, straight from the raw image
-          const int sx = iclamp(px + x, 0, W - 1), sy = iclamp(py + y, 0, H - 1);
-          float nb[9];
-          for (int yy = -1; yy < 2; ++yy)
-            for (int xx = -1; xx < 2; ++xx) nb[(yy + 1) * 3 + (xx + 1)] = img[(size_t)iclamp(sy + yy, 0, H - 1) * W + iclamp(sx + xx, 0, W - 1)];
-          depth_s = decode(morph_value(nb[4], nb));
-        } else {
-          depth_s = decode(img[(size_t)iclamp(py + y, 0, H - 1) * W + iclamp(px + x, 0, W - 1)]);
-        }
+        const float depth_s = decode(img[(size_t)iclamp(py + y, 0, H - 1) * W + iclamp(px + x, 0, W - 1)]);
         const float depth_range = fabsf(depth_s - depth);
         if ((depth_s < cv_min) || (depth_s > cv_max) || (depth_range > dist_range_max)) continue;
         const float gauss_range = 1.0f - gmin(depth_range, dist_range_max) * dist_range_max_inv;
@@ -584,15 +541,10 @@ int launch_preprocess(rr_ctx* c, int filter_textures, int use_processed_depth, i
   RR_TRY_RC(staged_prepare(c));            // decides which integrator the frame set is packed for (no-op unless settings changed)
   timer_begin(c, "1preprocess");
 
-  // pre_morph.fs: inside k_bilateral when its output feeds the bilateral pass (fuse_morph), else its own launch (the morph
-  // stage image is produced either way, like the reference's processDepth does regardless of useProcessedDepths)
-  const bool morph_inside = tunables().fuse_morph && use_processed_depth;
-  if (!morph_inside) {
-    timer_begin(c, "morph");
-    k_morph<<<grd, blk, 0, s>>>(c->d_depth_raw, c->d_morph, W, H);
-    RR_LAUNCH_CHECK(c, "k_morph");
-    timer_end(c, "morph");
-  }
+  timer_begin(c, "morph");
+  k_morph<<<grd, blk, 0, s>>>(c->d_depth_raw, c->d_morph, W, H);
+  RR_LAUNCH_CHECK(c, "k_morph");
+  timer_end(c, "morph");
 
   timer_begin(c, "bilateral");
   DepthParams dp{};
@@ -605,8 +557,8 @@ int launch_preprocess(rr_ctx* c, int filter_textures, int use_processed_depth, i
     dp.scale[i] = c->depth_far[i] - c->depth_near[i];
     dp.scaled_near[i] = dp.scale[i] / 255.0f;
   }
-  k_bilateral<<<grd, blk, 0, s>>>((use_processed_depth && !morph_inside) ? c->d_morph : c->d_depth_raw, c->d_color, c->d_depth, c->d_lab,
-                                  morph_inside ? c->d_morph : nullptr, W, H, c->CW, c->CH, st, dp);
+  k_bilateral<<<grd, blk, 0, s>>>(use_processed_depth ? c->d_morph : c->d_depth_raw, c->d_color, c->d_depth, c->d_lab,
+                                  W, H, c->CW, c->CH, st, dp);
   RR_LAUNCH_CHECK(c, "k_bilateral");
   timer_end(c, "bilateral");
 

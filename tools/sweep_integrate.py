@@ -18,7 +18,7 @@ import bench  # noqa: E402
 from rrpy import capi  # noqa: E402
 
 DEFAULTS = dict(fused=1, zchunk=13, fill_rows=16, fill_warps=2, ctas=2, threads=512, chunk=1, ldg256=1,
-                staged=1, stage_zchunk=13, stage_ychunk=0, stage_tile=0, stage_fill_rows=16, stage_debug=0, stage_cwarps=0, stage_bulk_fill=4, stage_fill_depth=0, stage_fill_lsu=0, stage_tail_cap=2, fuse_nq=1, fuse_morph=0)
+                staged=1, stage_zchunk=13, stage_ychunk=0, stage_tile=0, stage_fill_rows=16, stage_debug=0, stage_cwarps=0, stage_bulk_fill=4, stage_fill_depth=0, stage_fill_lsu=0, stage_tail_cap=2, fuse_nq=1)
 
 
 def main():
