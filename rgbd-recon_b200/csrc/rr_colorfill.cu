@@ -10,7 +10,7 @@
 // and each level kernel writes its lod into F AND refreshes exactly the squeezed pixels whose source lies in that lod.
 // A squeezed pixel whose source lies in a lod that is not finished yet reads as the cleared value it has in the
 // reference at that moment, so levels never race with their own output. Lods of <= TAIL_PIXELS pixels run back to back
-// in one CTA. Result: 6 launches at 1280x720 instead of 20 draw calls, same pixels (tests/test_colorfill_gpu.py).
+// in one CTA. Result: 7 launches at 1280x720 instead of 20 draw calls, same pixels (tests/test_colorfill_gpu.py).
 #include "rr_context.h"
 #include "rr_math.cuh"
 
@@ -20,7 +20,7 @@
 namespace rr {
 
 #define FILL_MAX_LODS 20
-#define TAIL_PIXELS 4096
+#define TAIL_PIXELS 1024
 
 struct FillParams {
   int n;                                   // number of lods
@@ -61,13 +61,19 @@ __device__ __forceinline__ int squeeze_src(const FillParams& p, int px) {
 
 // texelFetch on S as it is while lod `level` is being rendered (lods < level finished, the others still cleared)
 __device__ __forceinline__ void fetch_S(const FillParams& p, int level, int x, int y, float4& c, float& d) {
-  if (x < 0 || y < 0 || x >= p.FW || y >= p.H) { c = make_float4(0.f, 0.f, 0.f, 0.f); d = 0.0f; return; }
-  if (x >= p.W) { c = clear_color(); d = 1.0f; return; }
+  // Branch-free: the two loads are issued unconditionally from a clamped address and the special cases select afterwards, so
+  // the sixteen fetches of an inpaint fragment are in flight together instead of one L2 round trip after the other.
+  const bool outside = (x < 0 || y < 0 || x >= p.FW || y >= p.H);
+  const bool right = x >= p.W;                         // F's lod columns: S holds the clear colour there
   // rows of the lods that are not finished yet: everything above lod level-1's rows (all rows for level 1)
   const int unfinished_below = (level == 1) ? p.H : p.off[level - 1][1];
-  if (y < unfinished_below && squeeze_src(p, x) >= p.W) { c = clear_color(); d = 1.0f; return; }
-  const size_t i = (size_t)y * p.W + x;
-  c = __ldcg(p.sc + i); d = __ldcg(p.sd + i);      // L2 reads: the tail kernel reads what earlier levels of the same CTA wrote
+  const bool cleared = right || (y < unfinished_below && squeeze_src(p, x) >= p.W);
+  const bool load = !outside && !cleared;
+  const size_t i = load ? (size_t)y * p.W + x : 0;
+  const float4 cv = __ldcg(p.sc + i);                  // L2 reads: the tail kernel reads what earlier levels of the same CTA wrote
+  const float dv = __ldcg(p.sd + i);
+  c = outside ? make_float4(0.f, 0.f, 0.f, 0.f) : (cleared ? clear_color() : cv);
+  d = outside ? 0.0f : (cleared ? 1.0f : dv);
 }
 
 // tsdf_inpaint.fs:34-88 for fragment (fx, fy) of lod `level` (shader uniform lod = level - 1)
@@ -137,7 +143,7 @@ __global__ void __launch_bounds__(256) k_fill_level(const __grid_constant__ Fill
 }
 
 // lods first..n-1 in one CTA, one after the other
-__global__ void __launch_bounds__(1024) k_fill_tail(const __grid_constant__ FillParams p, int first) {
+__global__ void __launch_bounds__(512) k_fill_tail(const __grid_constant__ FillParams p, int first) {
   for (int level = first; level < p.n; ++level) {
     const int rx = p.res[level][0], n = rx * p.res[level][1];
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -258,7 +264,7 @@ int launch_fill_colors(rr_ctx* c) {
     RR_LAUNCH_CHECK(c, "k_fill_level");
   }
   if (level < p.n) {
-    k_fill_tail<<<1, 1024, 0, c->stream>>>(p, level);
+    k_fill_tail<<<1, 512, 0, c->stream>>>(p, level);
     RR_LAUNCH_CHECK(c, "k_fill_tail");
   }
   k_fill_final<<<grd, blk, 0, c->stream>>>(p);

@@ -37,10 +37,18 @@ def main():
     for name, call in calls.items():
         ms = []
         l0 = fu.launch_count()
+        fill = []
         for i in range(a.views + 2):
             r = call()
             if i >= 2:
                 ms.append(fu.stage_ms("draw"))
+            if name == "raymarch":                       # ReconIntegration::drawF: the colour hole filling follows the march
+                fu.fill_colors(download=False)
+                fu.synchronize()
+                if i >= 2:
+                    fill.append(fu.stage_ms("holefill"))
+        if fill:
+            out["fill_colors"] = {"ms_per_view": round(float(np.median(fill)), 4)}
         out[name] = {"ms_per_view": round(float(np.median(ms)), 4), "launches_per_view": (fu.launch_count() - l0) // (a.views + 2),
                      "covered_px": int((r[1] < 1.0).sum())}
     fu.close()
