@@ -280,6 +280,17 @@ static int tg_reserve(rr_ctx* c, T** ptr, size_t* have, size_t want, const char*
   return RR_OK;
 }
 
+// the fragment pool (colour contributions + list links) holds at least `want` fragments; it only ever grows
+static int tg_reserve_pool(rr_ctx* c, size_t want) {
+  if (c->tg_frag_cap >= want && c->d_tg_frag_rgba && c->d_tg_frag_link) return RR_OK;
+  cudaFree(c->d_tg_frag_rgba); cudaFree(c->d_tg_frag_link);
+  c->d_tg_frag_rgba = nullptr; c->d_tg_frag_link = nullptr; c->tg_frag_cap = 0;
+  RR_TRY_RC(check(c, cudaMalloc((void**)&c->d_tg_frag_rgba, want * sizeof(float4)), "trigrid fragments"));
+  RR_TRY_RC(check(c, cudaMalloc((void**)&c->d_tg_frag_link, want * sizeof(uint2)), "trigrid fragment links"));
+  c->tg_frag_cap = want;
+  return RR_OK;
+}
+
 // The view images of the context (d_rgba, d_zbuf) receive the result, like a raymarch. One host synchronisation per draw: the
 // fragment count of pass 2 is read back, and the pass is repeated with a larger pool if the lists did not fit.
 int launch_draw_trigrid(rr_ctx* c, const rr_view* v, float min_length) {
@@ -306,15 +317,7 @@ int launch_draw_trigrid(rr_ctx* c, const rr_view* v, float min_length) {
   RR_TRY_RC(tg_reserve(c, &c->d_tg_depth, &c->tg_depth_cap, (size_t)npx, "trigrid depth"));
   RR_TRY_RC(tg_reserve(c, &c->d_tg_head, &c->tg_head_cap, (size_t)npx, "trigrid list heads"));
   if (!c->d_tg_count) RR_TRY_RC(check(c, cudaMalloc((void**)&c->d_tg_count, sizeof(uint32_t)), "trigrid counter"));
-  const size_t pool0 = (size_t)npx * (size_t)(tunables().trigrid_pool > 0 ? tunables().trigrid_pool : 1) / 16 + 16;
-  if (c->tg_frag_cap < pool0) {
-    const size_t want = pool0;
-    size_t have = c->tg_frag_cap;
-    RR_TRY_RC(tg_reserve(c, &c->d_tg_frag_rgba, &have, want, "trigrid fragments"));
-    have = c->tg_frag_cap;
-    RR_TRY_RC(tg_reserve(c, &c->d_tg_frag_link, &have, want, "trigrid fragment links"));
-    c->tg_frag_cap = want;
-  }
+  RR_TRY_RC(tg_reserve_pool(c, (size_t)npx * (size_t)(tunables().trigrid_pool > 0 ? tunables().trigrid_pool : 1) / 16 + 16));
   p.verts = c->d_tg_verts; p.depth1 = c->d_tg_depth; p.head = c->d_tg_head; p.frag_count = c->d_tg_count;
   p.out_rgba = c->d_rgba; p.out_depth = c->d_zbuf;
   timer_begin(c, "3recon");
@@ -336,12 +339,7 @@ int launch_draw_trigrid(rr_ctx* c, const rr_view* v, float min_length) {
     if (count <= p.frag_cap) break;
     if (attempt > 0 || count >= 0xFFFFFFF0u) return fail(c, RR_ERR_UNSUPPORTED, "rr_draw_trigrid: fragment lists do not fit");
     // the lists did not fit: grow the pool to what this view needs (+ 1/8) and repeat pass 2
-    const size_t want = (size_t)count + (size_t)count / 8 + 1024;
-    size_t have = c->tg_frag_cap;
-    RR_TRY_RC(tg_reserve(c, &c->d_tg_frag_rgba, &have, want, "trigrid fragments"));
-    have = c->tg_frag_cap;
-    RR_TRY_RC(tg_reserve(c, &c->d_tg_frag_link, &have, want, "trigrid fragment links"));
-    c->tg_frag_cap = want;
+    RR_TRY_RC(tg_reserve_pool(c, (size_t)count + (size_t)count / 8 + 1024));
     k_tg_clear_lists<<<(npx + 255) / 256, 256, 0, c->stream>>>(p.head, p.frag_count, npx);
     RR_LAUNCH_CHECK(c, "k_tg_clear_lists");
   }

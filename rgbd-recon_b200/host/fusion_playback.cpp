@@ -3,7 +3,10 @@
 // raymarches it. Prints the TimerDatabase stage means; optionally dumps the last TSDF volume and image.
 //   fusion_playback <file.ks> (--streams "s0;s1;..." | --messages file) [--depth W H --color CW CH] [--frames K] [--voxel m]
 //                   [--limit l] [--eye x y z | --matrices file] [--view W H] [--shade m] [--dump-tsdf file] [--dump-image file] [--dense]
-//                   [--gpus N | --devices a,b,...]
+//                   [--gpus N | --devices a,b,...] [--recon points|trigrid|calibs [--min-length m] [--dump-recon file]]
+// --recon: like kinect_client's reconstruction list (source/kinect_client.cpp:252-258, key-selected g_recon_mode), one of the
+// other reconstructions also draws the last frame set's maps - ReconPoints, ReconTrigrid (min_length from the sensor .yml
+// unless --min-length is given) or ReconCalibs - and --dump-recon writes its image (rgba float32 [h][w][4], then depth [h][w]).
 // --gpus N / --devices: the volume is split into z-slabs over several devices in this one process (rr_group: frame sets by
 // peer copies from the first device, per-slab integration, the view composited on the first device); after the first frame
 // the slabs are re-cut to equal integrate cost. A device may be named more than once (slabs sharing a GPU).
@@ -41,7 +44,8 @@ static void perspective(float fovy_deg, float aspect, float n, float f, float m[
 }
 
 int main(int argc, char** argv) {
-  std::string ks, streams, messages, dump_tsdf, dump_image, matrices;
+  std::string ks, streams, messages, dump_tsdf, dump_image, matrices, recon_mode, dump_recon;
+  float min_length = 0.0f;
   bool explicit_sizes = false;
   unsigned W = 512, H = 424, CW = 1280, CH = 1080, VW = 1280, VH = 720;
   int frames = 10, shade = 1;
@@ -68,6 +72,9 @@ int main(int argc, char** argv) {
       devices.clear();
       for (char* tok = std::strtok(argv[++i], ","); tok; tok = std::strtok(nullptr, ",")) devices.push_back(std::atoi(tok));
     }
+    else if (!std::strcmp(argv[i], "--recon")) recon_mode = argv[++i];
+    else if (!std::strcmp(argv[i], "--min-length")) min_length = (float)std::atof(argv[++i]);
+    else if (!std::strcmp(argv[i], "--dump-recon")) dump_recon = argv[++i];
     else if (!std::strcmp(argv[i], "--matrices")) matrices = argv[++i];     // 32 floats: modelview, projection (column-major)
     else ks = argv[i];
   }
@@ -138,6 +145,34 @@ int main(int argc, char** argv) {
       std::vector<float> tsdf;
       recon.downloadTsdf(tsdf);
       std::ofstream(dump_tsdf, std::ios::binary).write(reinterpret_cast<char const*>(tsdf.data()), (std::streamsize)(tsdf.size() * sizeof(float)));
+    }
+    if (!recon_mode.empty()) {
+      // the other reconstructions consume the maps of the last processTextures() (and, ReconCalibs, the fused volume)
+      std::vector<float> const* rgba = nullptr; std::vector<float> const* depth = nullptr;
+      ReconPoints points(calib_files, &cv, sc.bbox);
+      ReconTrigrid trigrid(calib_files, &cv, sc.bbox);
+      ReconCalibs calibs(calib_files, &cv, sc.bbox);
+      if (recon_mode == "points") {
+        points.setShadeMode(shade); points.resize(VW, VH); points.setViewMatrices(mv, pr); points.drawF();
+        rgba = &points.colorImage(); depth = &points.depthImage();
+      } else if (recon_mode == "trigrid") {
+        if (min_length > 0.0f) trigrid.setMinLength(min_length);
+        trigrid.setShadeMode(shade); trigrid.resize(VW, VH); trigrid.setViewMatrices(mv, pr); trigrid.drawF();
+        rgba = &trigrid.colorImage(); depth = &trigrid.depthImage();
+      } else if (recon_mode == "calibs") {
+        calibs.setTsdfLimit(limit); calibs.resize(VW, VH); calibs.setViewMatrices(mv, pr); calibs.drawF();
+        rgba = &calibs.colorImage(); depth = &calibs.depthImage();
+      } else {
+        throw std::runtime_error("--recon takes points, trigrid or calibs");
+      }
+      std::size_t covered = 0;
+      for (float d : *depth) covered += d < 1.0f ? 1 : 0;
+      std::cout << "recon " << recon_mode << " covered pixels " << covered << std::endl;
+      if (!dump_recon.empty()) {
+        std::ofstream o(dump_recon, std::ios::binary);
+        o.write(reinterpret_cast<char const*>(rgba->data()), (std::streamsize)(rgba->size() * sizeof(float)));
+        o.write(reinterpret_cast<char const*>(depth->data()), (std::streamsize)(depth->size() * sizeof(float)));
+      }
     }
     if (!dump_image.empty()) {
       std::ofstream o(dump_image, std::ios::binary);

@@ -339,6 +339,7 @@ class ReconTrigrid : public Reconstruction {
       : Reconstruction(cfs, cv, bbox), m_min_length(cfs.minLength()) {}
   void draw() override;
   void setShadeMode(int mode) { m_view.shade_mode = mode; }
+  void setMinLength(float min_length) { m_min_length = min_length; }     // (the reference takes it from the .yml only)
   std::vector<float> const& colorImage() const { return m_rgba; }
   std::vector<float> const& depthImage() const { return m_depth; }
  private:

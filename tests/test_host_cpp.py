@@ -139,6 +139,49 @@ def test_fusion_playback_program_matches_oracle(tmp_path, small_scene, devices):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["points", "trigrid", "calibs"])
+def test_fusion_playback_other_reconstructions(tmp_path, small_scene, mode):
+    """SURVEY.md 8f-4 through the C++ look-alike classes (ReconPoints, ReconTrigrid, ReconCalibs in host/rr_host.hpp): the
+    program draws the last frame set with the named reconstruction, like kinect_client switches its g_recons, and the image
+    equals the oracle's bit for bit."""
+    import oracle_py as O
+    from rrpy import synth, volume_io
+    sc = small_scene
+    ks, streams = write_scene_files(str(tmp_path), sc)
+    for i in range(sc.N):                                     # sizes, formats and min_length arrive the reference's way: the sensors' .yml
+        open(os.path.join(str(tmp_path), f"sensor{i}.yml"), "w").write(
+            f"serial: 00{i}\nrgb_size: [ {sc.CW}, {sc.CH} ]\ndepth_size: [ {sc.W}, {sc.H} ]\nnear_far: [ 0.5, 4.5 ]\n"
+            "compress_rgb: [ 0, 0 ]\ncompress_depth: [ 0, 0 ]\nmin_length: [ 0.06, 0 ]\n")
+    inv = synth.analytic_inverse(sc, (40, 44, 40))
+    for i in range(sc.N):
+        volume_io.write_volume(str(tmp_path / f"sensor{i}.cv_xyz_inv"), inv[i])
+    VW, VH = 240, 136
+    mv, pr = synth.look_at((1.4, 1.5, 2.0), (0.0, 1.1, 0.0)), synth.perspective(50.0, VW / VH, 0.1, 10.0)
+    np.concatenate([mv, pr]).astype(np.float32).tofile(str(tmp_path / "view.bin"))
+    r = subprocess.run([os.path.join(BIN, "fusion_playback"), ks,
+                        "--streams", ";".join(streams), "--frames", "2", "--voxel", "0.02", "--view", str(VW), str(VH), "--shade", "1",
+                        "--matrices", str(tmp_path / "view.bin"), "--recon", mode, "--dump-recon", str(tmp_path / "recon.bin")],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert f"recon {mode} covered pixels" in r.stdout
+    img = np.fromfile(str(tmp_path / "recon.bin"), np.float32)
+    rgba, depth = img[:VW * VH * 4].reshape(VH, VW, 4), img[VW * VH * 4:].reshape(VH, VW)
+    grid = O.brick_grid(sc.bbox_min, sc.bbox_max, 0.02, 0.1)
+    cams = [O.frustum(sc.cv_xyz[i])[1] for i in range(sc.N)]
+    pre = O.preprocess(sc, grid, cams)
+    if mode == "points":
+        want = O.draw_points(sc, pre, mv, pr, VW, VH, shade_mode=1)
+    elif mode == "trigrid":
+        want = O.draw_trigrid(sc, pre, mv, pr, VW, VH, shade_mode=1, min_length=0.06)
+    else:
+        tsdf = O.integrate(inv, pre, grid, 0.01, True, O.occupied_bricks(pre["bricks"], 10))
+        want = O.draw_calibs(tsdf, (40, 44, 40), 0.01, sc.bbox_min, sc.bbox_max, mv, pr, VW, VH)
+    assert (want[1] < 1.0).sum() > 300
+    assert bits_equal(depth, want[1]).all(), mismatch_report(f"{mode} depth", depth, want[1])
+    assert bits_equal(rgba, want[0]).all(), mismatch_report(f"{mode} rgba", rgba, want[0])
+
+
+@pytest.mark.gpu
 def test_fusion_playback_from_yml_and_server_messages(tmp_path):
     """The reference's default stream format end to end through the host layer: sizes, DXT1 colour, 8-bit depth and its
     near/far range come from the sensors' .yml (CalibrationFiles), the frames arrive as server messages
