@@ -113,11 +113,13 @@ int launch_bricks_update(rr_ctx* c) {
   RR_TRY_RC(staged_prepare(c));
   const bool classify = staged_classify_params(c, cq);
   const uint32_t cls_blocks = classify ? (nb * (uint32_t)cq.per_brick + 31u) / 32u : 0u;
+  timer_begin(c, "bricks");
   k_bricks_update<<<1 + mask_blocks + cls_blocks, 1024, 0, c->stream>>>(
       c->d_counters, nb, c->bricks.res[0], c->bricks.res[1], c->bricks.res[2], c->cfg.min_voxels_per_brick, c->d_ranges, c->mask_words,
       c->d_occupied, c->d_num_occ, grid_ok ? c->d_near_occ : nullptr, c->d_occ_mask, (grid_ok && c->fused_ok) ? c->d_rowmask : nullptr, c->d_rowany,
       c->d_work, mask_blocks, cq);
   RR_LAUNCH_CHECK(c, "k_bricks_update");
+  timer_end(c, "bricks");
   c->work_fresh = true;
   cudaError_t e = cudaMemcpyAsync(c->h_num_occ, c->d_num_occ, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
   return check(c, e, "bricks count copy");

@@ -45,21 +45,22 @@ def main():
         for _ in range(5):
             fu.frame()
         fu.synchronize()
-        fu.set_timing(1)
-        fu.stage_stats("2integrate"); fu.stage_stats("1preprocess")
+        fu.set_timing(int(os.environ.get("SWEEP_TIMING", "1")))      # 2: per-pass timers too ("bricks")
+        fu.stage_stats("2integrate"); fu.stage_stats("1preprocess"); fu.stage_stats("bricks")
         fu.integrator_profile()          # reset (counts only with the profiling build: RR_B200_LIB=.../librr_b200_prof.so, stage_debug bit 7)
         for _ in range(40):
             fu.frame()
         fu.synchronize()
         ms, n = fu.stage_stats("2integrate")
         pms, pn = fu.stage_stats("1preprocess")
+        bms, bn = fu.stage_stats("bricks")
         fu.set_timing(0)
         h = hashlib.sha1(fu.download_tsdf().tobytes()).hexdigest()[:12]
         if ref_hash is None:
             ref_hash = h
         info = fu.integrator_info()
         info = {k: info[k] for k in ("staged", "tile", "zchunk", "oversize_pairs", "smem_bytes", "fill_warps", "flags", "slots", "slot_bytes")}
-        rec = {"config": spec, "integrate_ms": round(ms / n, 5), "integrator": info, "preprocess_ms": round(pms / max(1, pn), 5),
+        rec = {"config": spec, "integrate_ms": round(ms / n, 5), "integrator": info, "preprocess_ms": round(pms / max(1, pn), 5), "bricks_ms": round(bms / max(1, bn), 5),
                "tsdf_sha1": h, "same_as_first": h == ref_hash}
         prof = fu.integrator_profile()
         if any(prof.values()):
