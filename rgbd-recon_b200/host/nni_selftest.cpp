@@ -6,6 +6,9 @@
 #include <cstdio>
 #include <iostream>
 #include <random>
+#include <string>
+#include <utility>
+#include <vector>
 
 #include "natural_neighbour_interpolator.hpp"
 
@@ -68,7 +71,46 @@ static double check_queries(kinect::NaturalNeighbourInterpolator& nni, std::mt19
   return worst;
 }
 
-int main() {
+// --coords sites.bin queries.bin out.bin: float32 [n][3] sites and float32 [m][3] queries in, per query one row of float64 [n]
+// normalised Sibson coordinates out (all zeros where the query has no natural neighbours). Used by tests/test_nni_cpu.py to put
+// the coordinates next to an independent computation (Voronoi cell volumes from Qhull).
+static int dump_coordinates(const char* sites_path, const char* queries_path, const char* out_path) {
+  auto slurp = [](const char* path, std::vector<float>& v) {
+    std::FILE* f = std::fopen(path, "rb");
+    if (!f) return false;
+    std::fseek(f, 0, SEEK_END);
+    const long bytes = std::ftell(f);
+    std::fseek(f, 0, SEEK_SET);
+    v.resize((size_t)bytes / sizeof(float));
+    const size_t got = std::fread(v.data(), sizeof(float), v.size(), f);
+    std::fclose(f);
+    return got == v.size();
+  };
+  std::vector<float> sites, queries;
+  if (!slurp(sites_path, sites) || !slurp(queries_path, queries) || sites.size() % 3 || queries.size() % 3) {
+    std::cerr << "nni_selftest --coords: cannot read the inputs" << std::endl;
+    return 1;
+  }
+  std::vector<nniSample> s(sites.size() / 3);
+  for (size_t i = 0; i < s.size(); ++i) { s[i] = nniSample{}; s[i].s_pos = {sites[3 * i], sites[3 * i + 1], sites[3 * i + 2]}; s[i].quality = 1.0f; }
+  kinect::NaturalNeighbourInterpolator nni(s);
+  std::FILE* o = std::fopen(out_path, "wb");
+  if (!o) return 1;
+  std::vector<double> row(s.size());
+  for (size_t q = 0; q < queries.size() / 3; ++q) {
+    std::fill(row.begin(), row.end(), 0.0);
+    std::vector<std::pair<uint32_t, double>> c;
+    double norm = 0.0;
+    if (nni.coordinates(queries[3 * q], queries[3 * q + 1], queries[3 * q + 2], c, norm) && norm > 0.0)
+      for (const auto& e : c) row[e.first] += e.second / norm;
+    std::fwrite(row.data(), sizeof(double), row.size(), o);
+  }
+  std::fclose(o);
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  if (argc == 5 && std::string(argv[1]) == "--coords") return dump_coordinates(argv[2], argv[3], argv[4]);
   std::mt19937 rng(12345);
   std::uniform_real_distribution<double> U(0.0, 1.0);
 
