@@ -81,6 +81,44 @@ def test_raymarch_kernel_against_the_reference_shader_directly(small_scene, eye,
     assert np.abs(rgba[ok] - want["rgba"][ok]).max() <= 2e-3
 
 
+@pytest.mark.parametrize("eye", [(1.6, 1.5, 2.2), (0.2, 1.2, 0.3)])
+def test_trigrid_and_points_kernels_against_the_reference_shaders_directly(small_scene, eye):
+    """rr_draw_trigrid and rr_draw_points on the maps the kernels pre-processed, against glsl/trigrid_accum.{vs,gs,fs} +
+    trigrid_normalize.fs and glsl/points.{vs,gs,fs} run on the CPU on the same maps (oracle/_ref/libref_glsl.so), no oracle in
+    between: same coverage up to a handful of threshold pixels, window depth within 2e-5, colours within 5e-5 (trigrid) /
+    2e-5 (points) - the bars of the oracle's own pin in tests/test_oracle_cpu.py."""
+    import ref_glsl_py as G
+    if not G.available() or not hasattr(G.lib(), "rg_draw_trigrid"):
+        pytest.skip("oracle/_ref/libref_glsl.so not built with the trigrid shaders (needs the reference tree at build time)")
+    from rrpy import capi, synth
+    sc = small_scene
+    VW, VH = 200, 112
+    fu = capi.Fusion(sc.N, sc.W, sc.H, sc.CW, sc.CH)
+    capi.load_scene(fu, sc, synth.analytic_inverse(sc, (40, 44, 40)))
+    fu.configure(limit=0.01, voxel_size=0.02, brick_size=0.1, min_voxels=10, use_bricks=True)
+    fu.upload_frames(sc.color, sc.depth)
+    fu.frame(sync_bricks=True)
+    pre = {k: fu.download_stage(k) for k in ("depth_b", "quality", "normal")}
+    mv, pr = synth.look_at(eye, (0.0, 1.1, 0.0)), synth.perspective(50.0, VW / VH, 0.1, 10.0)
+    for mode in (0, 1, 3):
+        rgba, depth = fu.draw_trigrid(mv, pr, VW, VH, shade_mode=mode, min_length=0.06)
+        w_rgba, w_depth = G.draw_trigrid(sc, pre, mv, pr, VW, VH, mode, 0.06)
+        cov, w_cov = depth < 1.0, w_depth < 1.0
+        assert w_cov.sum() > 100 and (cov != w_cov).sum() <= max(2, int(0.002 * w_cov.sum())), f"trigrid mode {mode}: coverage"
+        both = cov & w_cov
+        assert np.abs(depth - w_depth)[both].max() <= 2e-5
+        d = np.abs(rgba - w_rgba)[both]
+        assert (d > 5e-5).any(axis=-1).sum() <= max(2, int(0.002 * both.sum())), f"trigrid mode {mode}: colour differs by up to {d.max()}"
+        rgba, depth = fu.draw_points(mv, pr, VW, VH, shade_mode=mode)
+        w_rgba, w_depth = G.draw_points(sc, pre, mv, pr, VW, VH, mode)
+        cov, w_cov = depth < 1.0, w_depth < 1.0
+        assert w_cov.sum() > 50 and (cov != w_cov).sum() <= max(2, int(0.002 * w_cov.sum())), f"points mode {mode}: coverage"
+        same = cov & w_cov & (np.abs(depth - w_depth) <= 2e-7)
+        assert same.sum() >= 0.995 * (cov & w_cov).sum()
+        assert np.abs(rgba - w_rgba)[same].max() <= 2e-5
+    fu.close()
+
+
 def test_empty_frame_set_on_the_gpu():
     """Edge case: a frame set without a single depth return. No brick marks, an empty occupied list, a volume that is -limit
     everywhere, a raymarch without samples - bit-identical to the oracle (whose empty-frame behaviour is checked against the
