@@ -593,6 +593,28 @@ def run_ours(args):
     rig.barrier()
     view_ms = rig.max_over_ranks(v0.elapsed_time(v1) / n_views)
 
+    # ---- the other reconstructions of SURVEY.md 8f-4 on the same maps, one view each (device time of the library's `draw`
+    # stage timer; tools/bench_renderers.py is the same measurement on its own). Evidence beside the headline, never a
+    # reason to fail the line.
+    renderers = None
+    if world == 1 and args.subrecords:
+        try:
+            fu.set_timing(2)
+            renderers = {"resolution": [VW, VH], "what": "one view of rr_draw_points / rr_draw_calibs / rr_draw_trigrid (ReconPoints, ReconCalibs, "
+                         "ReconTrigrid) on the last frame set's maps; median device ms of 10 views"}
+            for name, call in (("draw_points", lambda: fu.draw_points(mv, pr, VW, VH, shade_mode=1)),
+                               ("draw_calibs", lambda: fu.draw_calibs(mv, pr, VW, VH, active_kinect=0, limit=LIMIT)),
+                               ("draw_trigrid", lambda: fu.draw_trigrid(mv, pr, VW, VH, shade_mode=1))):
+                ms = []
+                for i in range(12):
+                    img = call()
+                    if i >= 2:
+                        ms.append(fu.stage_ms("draw"))
+                renderers[name] = {"ms_per_view": round(float(np.median(ms)), 4), "covered_px": int((img[1] < 1.0).sum())}
+            fu.set_timing(0)
+        except Exception as e:                                   # pragma: no cover
+            renderers = {"error": str(e)[:200]}
+
     # ---- N > 1: this run's slabs and composited view against a single-context run, bit for bit ---------------------------
     verified = None
     if world > 1:
@@ -652,6 +674,7 @@ def run_ours(args):
                          (" per slab; one compositing kernel on rank 0 reads the other ranks' first-hit keys and the winners' pixels through CUDA IPC peer memory (rr_composite_peers), fenced by two one-element all-reduces" if world > 1 else "")},
         # SURVEY.md 8d "reported separately and combined": one fused frame set followed by one view
         "combined_frames_per_s": round(1e3 / (ms_step + view_ms), 2),
+        "renderers": renderers,
         "roofline": {"bound": "hbm", "kernel": integrate_kernel_name(bricks, info),
                      "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                      "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": int(abytes), "peak_source": peak_src,
