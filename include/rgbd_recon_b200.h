@@ -187,8 +187,9 @@ int rr_draw_calibs(rr_ctx* ctx, const rr_view* view, int active_kinect, float ts
  * window depth of the triangles that survive validSurface (no invalid depth, every edge shorter than
  * min_length * average depth * 4), the bounding box, the colour view's border and back-face culling; pass 2 adds
  * shade() * quality, quality of every fragment within epsilon = 0.075 (:35) of that surface; pass 3 divides by the summed
- * quality. A software rasteriser (OpenGL 4.4 clipping, coverage and perspective-correct interpolation in fp64) whose additive
- * blend is performed in draw order (per-pixel fragment lists summed by ascending triangle id), so the result is deterministic.
+ * quality. A software rasteriser (OpenGL 4.4 clipping, coverage and perspective-correct interpolation in fp64) that walks the
+ * triangles once for both passes and performs the additive blend in draw order (per-pixel fragment lists, epsilon-tested against
+ * the final depth and summed by ascending triangle id), so the result is deterministic.
  * min_length: CalibrationFiles::minLength() (the sensor .yml's "min_length:", default 0.0125, KinectCalibrationFile.cpp:96,341).
  * Writes the context's view images like rr_raymarch: rgba float32 [h][w][4] (alpha 1 where something was drawn, zeros
  * elsewhere), depth float32 [h][w] (pass 1's depth, 1.0 elsewhere). Synchronises the context's stream once per call. */

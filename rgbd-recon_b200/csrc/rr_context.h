@@ -187,7 +187,7 @@ struct rr_ctx {
   float4* d_tg_verts = nullptr; size_t tg_verts_cap = 0;
   uint32_t* d_tg_depth = nullptr; size_t tg_depth_cap = 0;
   uint32_t* d_tg_head = nullptr; size_t tg_head_cap = 0;
-  float4* d_tg_frag_rgba = nullptr; uint2* d_tg_frag_link = nullptr; size_t tg_frag_cap = 0;
+  float4* d_tg_frag_rgba = nullptr; float4* d_tg_frag_pos = nullptr; uint2* d_tg_frag_link = nullptr; size_t tg_frag_cap = 0;
   uint32_t* d_tg_count = nullptr;
 
   // colour hole filling (rr_colorfill.cu): atlas right of column W, squeezed copy, filled colour

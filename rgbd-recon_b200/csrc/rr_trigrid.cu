@@ -4,12 +4,14 @@
 // the pass-1 surface (additive blending, no depth test), pass 3 divides by the summed quality.
 // Kernels:
 //   k_tg_vertices   one thread per grid vertex: trigrid_accum.vs once per vertex instead of six times (64-byte records);
-//   k_tg_raster<0>  one thread per triangle: trigrid_accum.gs (validSurface, flat normal), the fixed-function stages below, the
-//                   stage-0 fragment tests, atomicMin of the window depth's bits (order-independent, like GL_LESS's result);
-//   k_tg_raster<1>  the same walk; fragments that pass the epsilon test are appended to a per-pixel list (A-buffer: one atomic
-//                   counter, one atomicExch per fragment) with their triangle id;
-//   k_tg_resolve    one thread per pixel: the list is summed in ascending triangle id - binary32 additions in exactly the order
-//                   in-order blending performs them, so the sums do not depend on the scheduling - then trigrid_normalize.fs.
+//   k_tg_raster     one thread per triangle, ONE walk for both passes: trigrid_accum.gs (validSurface, flat normal), the
+//                   fixed-function stages below, the fragment tests both stages share; every surviving fragment lowers the
+//                   pixel's window depth (atomicMin of the bits: order-independent, like GL_LESS's result) AND is appended,
+//                   with its eye-space position, its colour * quality and its triangle id, to the pixel's list (A-buffer:
+//                   one atomic counter, one atomicExch per fragment);
+//   k_tg_resolve    one thread per pixel: pass 2's epsilon test of every listed fragment against the FINAL depth of pass 1,
+//                   the survivors summed in ascending triangle id - binary32 additions in exactly the order in-order
+//                   blending performs them, so the sums do not depend on the scheduling - then trigrid_normalize.fs.
 // Fixed-function stages (OpenGL 4.4), fp64 from the binary32 clip coordinates: near / far clipping in clip space (§13.5; new
 // vertices carry barycentric coordinates of the original triangle), perspective divide and viewport transform with depth range
 // [0, 1] (§13.6.1), a fragment for every pixel centre inside the (fanned) polygon (§14.6.1), window z interpolated affinely and
@@ -37,7 +39,7 @@ struct TrigridParams {
   float4* verts;                 // [N][W + 1][H + 1][4]
   uint32_t* depth1;              // [vh][vw] bits of the pass-1 window depth (non-negative floats order like their bits)
   uint32_t* head;                // [vh][vw] newest fragment of the pixel's list, 0xFFFFFFFF = none
-  float4* frag_rgba; uint2* frag_link;     // (triangle id, next)
+  float4* frag_rgba; float4* frag_pos; uint2* frag_link;     // colour * quality | quality; eye-space position; (triangle id, next)
   uint32_t frag_cap; uint32_t* frag_count;
   float4* out_rgba; float* out_depth;
 };
@@ -108,7 +110,6 @@ __device__ __forceinline__ float tg_interp(const double* B, float a0, float a1, 
   return (float)((B[0] * (double)a0 + B[1] * (double)a1) + B[2] * (double)a2);
 }
 
-template <int STAGE>
 __global__ void __launch_bounds__(128) k_tg_raster(const __grid_constant__ TrigridParams p, uint32_t n_triangles) {
   const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= n_triangles) return;
@@ -209,14 +210,8 @@ __global__ void __launch_bounds__(128) k_tg_raster(const __grid_constant__ Trigr
         const float3 pos_es = make_float3(tg_interp(B, e0.x, e1.x, e2.x), tg_interp(B, e0.y, e1.y, e2.y), tg_interp(B, e0.z, e1.z, e2.z));
         if (dot3(normal, normalize3(pos_es)) > 0.0f) continue;
         const size_t o = (size_t)py * p.vw + px;
-        if (STAGE == 0) {
-          atomicMin(p.depth1 + o, __float_as_uint(zw));
-          continue;
-        }
-        const float depth_curr = __uint_as_float(p.depth1[o]);
-        const float4 pc = pmulv(p.img_to_eye, make_float4(((float)px + 0.5f) + 0.5f, ((float)py + 0.5f) + 0.5f, depth_curr, 1.0f));
-        const float3 cur = make_float3(pc.x / pc.w, pc.y / pc.w, pc.z / pc.w);
-        if (p.epsilon < length3(cur - pos_es)) continue;
+        atomicMin(p.depth1 + o, __float_as_uint(zw));                // pass 1 (stage 0): GL_LESS, depth writes on
+        // pass 2 (stage 1) up to its epsilon test, which needs the final depth of pass 1 and is applied by k_tg_resolve
         const float q = tg_interp(B, c0.w, c1.w, c2.w);
         float3 c;
         if (p.shade_mode == 3) {
@@ -228,30 +223,39 @@ __global__ void __launch_bounds__(128) k_tg_raster(const __grid_constant__ Trigr
         const uint32_t slot = atomicAdd(p.frag_count, 1u);
         if (slot < p.frag_cap) {
           p.frag_rgba[slot] = make_float4(c.x * q, c.y * q, c.z * q, q);
+          p.frag_pos[slot] = make_float4(pos_es.x, pos_es.y, pos_es.z, 0.0f);
           p.frag_link[slot] = make_uint2(id, atomicExch(p.head + o, slot));
         }
       }
   }
 }
 
-// the additive blend in draw order + trigrid_normalize.fs:13-31
+// trigrid_accum.fs:60-69 (the epsilon test against pass 1's depth), the additive blend in draw order, trigrid_normalize.fs:13-31
 __global__ void __launch_bounds__(256) k_tg_resolve(const __grid_constant__ TrigridParams p) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.vw * p.vh) return;
   const uint32_t head = p.head[i];
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  long long last = -1;
-  for (;;) {                                        // selection by ascending triangle id: lists are a handful of entries long
-    long long best = 0x7fffffffffffffffll; uint32_t best_slot = 0xFFFFFFFFu;
-    for (uint32_t s = head; s != 0xFFFFFFFFu;) {
-      const uint2 lk = p.frag_link[s];
-      if ((long long)lk.x > last && (long long)lk.x < best) { best = (long long)lk.x; best_slot = s; }
-      s = lk.y;
+  if (head != 0xFFFFFFFFu) {
+    const int py = i / p.vw, px = i - py * p.vw;
+    const float depth_curr = __uint_as_float(p.depth1[i]);
+    const float4 pc = pmulv(p.img_to_eye, make_float4(((float)px + 0.5f) + 0.5f, ((float)py + 0.5f) + 0.5f, depth_curr, 1.0f));
+    const float3 cur = make_float3(pc.x / pc.w, pc.y / pc.w, pc.z / pc.w);
+    long long last = -1;
+    for (;;) {                                      // selection by ascending triangle id: lists are a handful of entries long
+      long long best = 0x7fffffffffffffffll; uint32_t best_slot = 0xFFFFFFFFu;
+      for (uint32_t s = head; s != 0xFFFFFFFFu;) {
+        const uint2 lk = p.frag_link[s];
+        if ((long long)lk.x > last && (long long)lk.x < best) { best = (long long)lk.x; best_slot = s; }
+        s = lk.y;
+      }
+      if (best_slot == 0xFFFFFFFFu) break;
+      last = best;
+      const float4 pe = p.frag_pos[best_slot];
+      if (p.epsilon < length3(cur - make_float3(pe.x, pe.y, pe.z))) continue;      // occluded by the triangles in front
+      const float4 v = p.frag_rgba[best_slot];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
-    if (best_slot == 0xFFFFFFFFu) break;
-    const float4 v = p.frag_rgba[best_slot];
-    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-    last = best;
   }
   if (acc.w > 0.0f) {
     p.out_rgba[i] = make_float4(acc.x / acc.w, acc.y / acc.w, acc.z / acc.w, acc.w / acc.w);
@@ -282,17 +286,18 @@ static int tg_reserve(rr_ctx* c, T** ptr, size_t* have, size_t want, const char*
 
 // the fragment pool (colour contributions + list links) holds at least `want` fragments; it only ever grows
 static int tg_reserve_pool(rr_ctx* c, size_t want) {
-  if (c->tg_frag_cap >= want && c->d_tg_frag_rgba && c->d_tg_frag_link) return RR_OK;
-  cudaFree(c->d_tg_frag_rgba); cudaFree(c->d_tg_frag_link);
-  c->d_tg_frag_rgba = nullptr; c->d_tg_frag_link = nullptr; c->tg_frag_cap = 0;
+  if (c->tg_frag_cap >= want && c->d_tg_frag_rgba && c->d_tg_frag_pos && c->d_tg_frag_link) return RR_OK;
+  cudaFree(c->d_tg_frag_rgba); cudaFree(c->d_tg_frag_pos); cudaFree(c->d_tg_frag_link);
+  c->d_tg_frag_rgba = nullptr; c->d_tg_frag_pos = nullptr; c->d_tg_frag_link = nullptr; c->tg_frag_cap = 0;
   RR_TRY_RC(check(c, cudaMalloc((void**)&c->d_tg_frag_rgba, want * sizeof(float4)), "trigrid fragments"));
+  RR_TRY_RC(check(c, cudaMalloc((void**)&c->d_tg_frag_pos, want * sizeof(float4)), "trigrid fragment positions"));
   RR_TRY_RC(check(c, cudaMalloc((void**)&c->d_tg_frag_link, want * sizeof(uint2)), "trigrid fragment links"));
   c->tg_frag_cap = want;
   return RR_OK;
 }
 
 // The view images of the context (d_rgba, d_zbuf) receive the result, like a raymarch. One host synchronisation per draw: the
-// fragment count of pass 2 is read back, and the pass is repeated with a larger pool if the lists did not fit.
+// fragment count is read back, and the walk is repeated with a larger pool if the lists did not fit.
 int launch_draw_trigrid(rr_ctx* c, const rr_view* v, float min_length) {
   TrigridParams p{};
   const int vw = v->viewport[2], vh = v->viewport[3], npx = vw * vh;
@@ -326,19 +331,18 @@ int launch_draw_trigrid(rr_ctx* c, const rr_view* v, float min_length) {
   RR_LAUNCH_CHECK(c, "k_tg_clear");
   k_tg_vertices<<<(unsigned)((n_vertices + 255) / 256), 256, 0, c->stream>>>(p, (uint32_t)n_vertices);
   RR_LAUNCH_CHECK(c, "k_tg_vertices");
-  k_tg_raster<0><<<(unsigned)((n_triangles + 127) / 128), 128, 0, c->stream>>>(p, (uint32_t)n_triangles);
-  RR_LAUNCH_CHECK(c, "k_tg_raster<0>");
   for (int attempt = 0;; ++attempt) {
-    p.frag_rgba = c->d_tg_frag_rgba; p.frag_link = c->d_tg_frag_link;
+    p.frag_rgba = c->d_tg_frag_rgba; p.frag_pos = c->d_tg_frag_pos; p.frag_link = c->d_tg_frag_link;
     p.frag_cap = (uint32_t)(c->tg_frag_cap > 0xFFFFFFF0ull ? 0xFFFFFFF0ull : c->tg_frag_cap);
-    k_tg_raster<1><<<(unsigned)((n_triangles + 127) / 128), 128, 0, c->stream>>>(p, (uint32_t)n_triangles);
-    RR_LAUNCH_CHECK(c, "k_tg_raster<1>");
+    k_tg_raster<<<(unsigned)((n_triangles + 127) / 128), 128, 0, c->stream>>>(p, (uint32_t)n_triangles);
+    RR_LAUNCH_CHECK(c, "k_tg_raster");
     uint32_t count = 0;
     RR_TRY_RC(check(c, cudaMemcpyAsync(&count, p.frag_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream), "trigrid fragment count"));
     RR_TRY_RC(check(c, cudaStreamSynchronize(c->stream), "trigrid fragment count"));
     if (count <= p.frag_cap) break;
     if (attempt > 0 || count >= 0xFFFFFFF0u) return fail(c, RR_ERR_UNSUPPORTED, "rr_draw_trigrid: fragment lists do not fit");
-    // the lists did not fit: grow the pool to what this view needs (+ 1/8) and repeat pass 2
+    // the lists did not fit: grow the pool to what this view needs (+ 1/8) and walk the triangles again (the depths the first
+    // walk left are the final ones already: lowering them again changes nothing)
     RR_TRY_RC(tg_reserve_pool(c, (size_t)count + (size_t)count / 8 + 1024));
     k_tg_clear_lists<<<(npx + 255) / 256, 256, 0, c->stream>>>(p.head, p.frag_count, npx);
     RR_LAUNCH_CHECK(c, "k_tg_clear_lists");
@@ -351,8 +355,8 @@ int launch_draw_trigrid(rr_ctx* c, const rr_view* v, float min_length) {
 }
 
 void trigrid_release(rr_ctx* c) {
-  cudaFree(c->d_tg_verts); cudaFree(c->d_tg_depth); cudaFree(c->d_tg_head); cudaFree(c->d_tg_frag_rgba); cudaFree(c->d_tg_frag_link); cudaFree(c->d_tg_count);
-  c->d_tg_verts = nullptr; c->d_tg_depth = nullptr; c->d_tg_head = nullptr; c->d_tg_frag_rgba = nullptr; c->d_tg_frag_link = nullptr; c->d_tg_count = nullptr;
+  cudaFree(c->d_tg_verts); cudaFree(c->d_tg_depth); cudaFree(c->d_tg_head); cudaFree(c->d_tg_frag_rgba); cudaFree(c->d_tg_frag_pos); cudaFree(c->d_tg_frag_link); cudaFree(c->d_tg_count);
+  c->d_tg_verts = nullptr; c->d_tg_depth = nullptr; c->d_tg_head = nullptr; c->d_tg_frag_rgba = nullptr; c->d_tg_frag_pos = nullptr; c->d_tg_frag_link = nullptr; c->d_tg_count = nullptr;
   c->tg_verts_cap = c->tg_depth_cap = c->tg_head_cap = c->tg_frag_cap = 0;
 }
 
