@@ -304,7 +304,8 @@ uint64_t rr_launch_count(const rr_ctx* ctx);
 /* Launch-shape knob of the integrator, process-wide (no reference counterpart; the reference's draw-call structure is
  * fixed). Names: "fused", "zchunk", "fill_rows", "fill_warps", "ctas", "threads", "chunk", "brick_grid",
  * "ldg256", "graph", "staged", "stage_zchunk", "stage_ychunk", "stage_tile", "stage_cwarps", "stage_fill_rows", "stage_bulk_fill", "stage_fill_depth",
- * "stage_tail_cap", "stage_ctas", "stage_fill_lsu", "stage_debug", "trigrid_pool" (rr_draw_trigrid: initial fragment-pool
+ * "stage_tail_cap", "stage_ctas", "stage_fill_lsu", "stage_debug", "fuse_nq" (1: pre_normal and pre_quality as one launch,
+ * k_normal_quality; 0: two kernels), "trigrid_pool" (rr_draw_trigrid: initial fragment-pool
  * capacity in fragments per 16 view pixels; the pool grows when a view needs more).
  * Results never depend on these. Returns RR_ERR_INVALID for an unknown name. */
 int rr_set_tunable(const char* name, int value);
