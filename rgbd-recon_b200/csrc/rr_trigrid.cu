@@ -119,9 +119,9 @@ __global__ void __launch_bounds__(128) k_tg_raster(const __grid_constant__ Trigr
   const uint32_t r = id - (uint32_t)layer * per_layer, cell = r >> 1;
   const int k = (int)(r & 1u), y = (int)(cell / (uint32_t)p.H), x = (int)(cell - (uint32_t)y * p.H);
   const float4* g = p.verts + (size_t)layer * GW * GH * 4;
-  const float4* a0 = g + ((size_t)(k == 0 ? y : y) * GW + (k == 0 ? x : x + 1)) * 4;
-  const float4* a1 = g + ((size_t)(k == 0 ? y : y + 1) * GW + x + 1) * 4;
-  const float4* a2 = g + ((size_t)(y + 1) * GW + x) * 4;
+  const float4* a0 = g + ((size_t)y * GW + (k == 0 ? x : x + 1)) * 4;                  // (x, y) | (x + 1, y)
+  const float4* a1 = g + ((size_t)(k == 0 ? y : y + 1) * GW + x + 1) * 4;              // (x + 1, y) | (x + 1, y + 1)
+  const float4* a2 = g + ((size_t)(y + 1) * GW + x) * 4;                               // (x, y + 1)
   const float4 e0 = __ldg(a0 + 1), e1 = __ldg(a1 + 1), e2 = __ldg(a2 + 1);            // pos_es, depth
   // trigrid_accum.gs:27-37,44-55
   if (e0.w < 0.0f || e1.w < 0.0f || e2.w < 0.0f) return;

@@ -4,7 +4,7 @@
 //   fusion_playback <file.ks> (--streams "s0;s1;..." | --messages file) [--depth W H --color CW CH] [--frames K] [--voxel m]
 //                   [--limit l] [--eye x y z | --matrices file] [--view W H] [--shade m] [--dump-tsdf file] [--dump-image file] [--dense]
 //                   [--gpus N | --devices a,b,...] [--recon points|trigrid|calibs [--min-length m] [--dump-recon file]]
-// --recon: like kinect_client's reconstruction list (source/kinect_client.cpp:252-258, key-selected g_recon_mode), one of the
+// --recon: like kinect_client's reconstruction list (source/kinect_client.cpp:251-257, key-selected g_recon_mode), one of the
 // other reconstructions also draws the last frame set's maps - ReconPoints, ReconTrigrid (min_length from the sensor .yml
 // unless --min-length is given) or ReconCalibs - and --dump-recon writes its image (rgba float32 [h][w][4], then depth [h][w]).
 // --gpus N / --devices: the volume is split into z-slabs over several devices in this one process (rr_group: frame sets by
